@@ -1,0 +1,227 @@
+// oracle/ref_harness.cpp — TEST INFRASTRUCTURE ONLY (never linked into the product path).
+//
+// Thin C-ABI around the UNMODIFIED reference (b-tudor/mpmcxx) compiled from the sources where
+// they lie under /root/reference/src (see oracle/Makefile, target `ref`).  It lets the tests,
+// the golden-vector generator (tests/golden/make_golden.py) and bench.py's `--impl reference`
+// arm drive the reference's own System::energy() and its public term functions
+// (System.h:314-410) and read doubles at full precision instead of the 6-decimal energy.dat.
+//
+// What it steps around: a non-MPI build leaves `size`=0 (main.cpp:19) — we set
+// size=1; SimulationControl's PI members are private — opened with the usual test-only macro.
+// Nothing here re-implements reference arithmetic: every number comes from reference code.
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <cmath>
+#include <unistd.h>
+#include <fcntl.h>
+#include <vector>
+#include <map>
+#include <string>
+#include <random>
+#include <iostream>
+#include <sstream>
+#include <stdint.h>
+
+// standard headers are all included above, so the macro only touches the reference's own classes
+#define private public
+#define protected public
+#include "SimulationControl.h"
+#undef private
+#undef protected
+#include "Atom.h"
+#include "Molecule.h"
+#include "Pair.h"
+#include "Rando.h"
+
+// globals the reference declares `extern` (System.cpp:13, Output.cpp, ...) and main.cpp defines
+int  rank = 0;
+int  size = 1;
+bool mpi  = false;
+
+static int g_last_error = 0;
+
+namespace {
+
+struct Quiet {   // the reference prints a banner per call; silence stdout while it runs
+	int saved;
+	Quiet() { fflush(stdout); saved = dup(1); int nul = open("/dev/null", O_WRONLY); dup2(nul, 1); close(nul); }
+	~Quiet() { fflush(stdout); dup2(saved, 1); close(saved); }
+};
+
+System *pick(SimulationControl *sc, int s) {
+	if (s < 0 || sc->systems.empty()) return &sc->sys;
+	return sc->systems[(size_t)s];
+}
+
+} // namespace
+
+extern "C" {
+
+int mref_last_error() { return g_last_error; }
+
+void *mref_open(const char *input_path, int P) {
+	g_last_error = 0;
+	char *path = strdup(input_path);
+	SimulationControl *sc = nullptr;
+	try {
+		Quiet q;
+		sc = new SimulationControl(path, P, false, nullptr);
+		sc->initializeSimulationObjects();
+	} catch (int e) {
+		g_last_error = e;
+		sc = nullptr;   // leak on failure: the reference's dtor is not exception-safe
+	}
+	free(path);
+	return sc;
+}
+
+void mref_close(void *h) {
+	// the reference's ~System double-frees in some configurations; tests are short-lived, so leak.
+	(void)h;
+}
+
+int mref_nsys(void *h) { return (int)((SimulationControl *)h)->systems.size(); }
+
+int mref_natoms(void *h, int s) { return pick((SimulationControl *)h, s)->countNatoms(); }
+
+// Flatten the molecule list in list order (the order pairs()/atom_array use, System.cpp:881-904).
+void mref_get_sites(void *h, int s, double *pos, double *charge, double *alpha, double *eps,
+                    double *sigma, double *mass, int *mol, int *frozen) {
+	System *sy = pick((SimulationControl *)h, s);
+	int n = 0, m = 0;
+	for (Molecule *mp = sy->molecules; mp; mp = mp->next, m++)
+		for (Atom *ap = mp->atoms; ap; ap = ap->next, n++) {
+			for (int p = 0; p < 3; p++) pos[3 * n + p] = ap->pos[p];
+			charge[n] = ap->charge; alpha[n] = ap->polarizability; eps[n] = ap->epsilon;
+			sigma[n] = ap->sigma; mass[n] = ap->mass; mol[n] = m; frozen[n] = ap->frozen;
+		}
+}
+
+void mref_set_pos(void *h, int s, const double *pos) {
+	System *sy = pick((SimulationControl *)h, s);
+	int n = 0;
+	for (Molecule *mp = sy->molecules; mp; mp = mp->next)
+		for (Atom *ap = mp->atoms; ap; ap = ap->next, n++)
+			for (int p = 0; p < 3; p++) ap->pos[p] = pos[3 * n + p];
+}
+
+// out: basis[9], recip[9], volume, cutoff, ewald_alpha, polar_ewald_alpha  (22 doubles)
+void mref_get_cell(void *h, int s, double *out) {
+	System *sy = pick((SimulationControl *)h, s);
+	for (int i = 0; i < 3; i++)
+		for (int j = 0; j < 3; j++) {
+			out[3 * i + j]     = sy->pbc.basis[i][j];
+			out[9 + 3 * i + j] = sy->pbc.reciprocal_basis[i][j];
+		}
+	out[18] = sy->pbc.volume; out[19] = sy->pbc.cutoff;
+	out[20] = sy->ewald_alpha; out[21] = sy->polar_ewald_alpha;
+}
+
+// One reference energy() exactly as the MC loop calls it (cache semantics included).
+// out[0..8] = energy, rd, coulombic, polarization, vdw, polarization_iterations, dipole_rrms,
+//             iterator_failed, N
+int mref_energy(void *h, int s, double *out) {
+	System *sy = pick((SimulationControl *)h, s);
+	try {
+		Quiet q;
+		sy->iterator_failed = 0;
+		out[0] = sy->energy();
+	} catch (int e) { return g_last_error = e; }
+	out[1] = sy->observables->rd_energy;
+	out[2] = sy->observables->coulombic_energy;
+	out[3] = sy->observables->polarization_energy;
+	out[4] = sy->observables->vdw_energy;
+	out[5] = sy->nodestats ? sy->nodestats->polarization_iterations : 0;
+	out[6] = sy->observables->dipole_rrms;
+	out[7] = sy->iterator_failed;
+	out[8] = sy->observables->N;
+	return 0;
+}
+
+// Cold evaluation of every sub-term through the reference's public term functions, all pairs
+// flagged.  out (16 doubles):
+//  0 lj() total            1 Σ pair rd_energy      2 Σ pair lrc         3 Σ lj_lrc_self
+//  4 coulombic_real()      5 Σ es_real_energy      6 Σ es_self_intra    7 coulombic_reciprocal()
+//  8 coulombic_self()      9 polar() (0 if off)   10 iterations        11 dipole_rrms
+// 12 iterator_failed      13 n pairs              14 n pairs with rimg<cutoff (not frozen)  15 spare
+int mref_terms(void *h, int s, double *out) {
+	System *sy = pick((SimulationControl *)h, s);
+	for (int i = 0; i < 16; i++) out[i] = 0;
+	try {
+		Quiet q;
+		sy->natoms = sy->countNatoms();
+		sy->pairs();
+		sy->flag_all_pairs();
+		sy->iterator_failed = 0;
+		if (!(sy->use_sg || sy->rd_only)) {
+			out[4] = sy->coulombic_real();
+			out[7] = sy->coulombic_reciprocal();
+			out[8] = sy->coulombic_self();
+			if (sy->polarization) {
+				out[9]  = sy->polar();
+				out[10] = sy->nodestats ? sy->nodestats->polarization_iterations : 0;
+				out[11] = sy->observables->dipole_rrms;
+				out[12] = sy->iterator_failed;
+			}
+		}
+		out[0] = sy->lj();
+		double cutoff = sy->pbc.cutoff;
+		for (Molecule *mp = sy->molecules; mp; mp = mp->next)
+			for (Atom *ap = mp->atoms; ap; ap = ap->next) {
+				if (sy->rd_lrc) out[3] += sy->lj_lrc_self(ap, cutoff);
+				for (Pair *pp = ap->pairs; pp; pp = pp->next) {
+					out[1] += pp->rd_energy;
+					out[2] += pp->lrc;
+					out[5] += pp->es_real_energy;
+					out[6] += pp->es_self_intra_energy;
+					out[13] += 1;
+					if (!pp->frozen && pp->rimg - SMALL_dR < cutoff) out[14] += 1;
+				}
+			}
+	} catch (int e) { return g_last_error = e; }
+	return 0;
+}
+
+// per-site polarization state after polar(): mu, ef_static, ef_induced, ef_induced_change (3n each),
+// rank_metric (n)
+void mref_get_dipoles(void *h, int s, double *mu, double *efs, double *efi, double *efic, double *rankm) {
+	System *sy = pick((SimulationControl *)h, s);
+	int n = 0;
+	for (Molecule *mp = sy->molecules; mp; mp = mp->next)
+		for (Atom *ap = mp->atoms; ap; ap = ap->next, n++) {
+			for (int p = 0; p < 3; p++) {
+				mu[3 * n + p]  = ap->mu[p];
+				efs[3 * n + p] = ap->ef_static[p];
+				efi[3 * n + p] = ap->ef_induced[p];
+				efic[3 * n + p] = ap->ef_induced_change[p];
+			}
+			rankm[n] = ap->rank_metric;
+		}
+}
+
+// Path-integral aggregates (SimulationControl.PathIntegral.cpp:752-828, 859-904).
+// out: potential, rd, coulombic, polarization, vdw, kinetic, chain_mass_len2   (7 doubles)
+int mref_pi_energy(void *h, double *out) {
+	SimulationControl *sc = (SimulationControl *)h;
+	try {
+		Quiet q;
+		out[5] = sc->PI_calculate_kinetic();
+		out[0] = sc->PI_calculate_potential();
+		out[6] = sc->PI_chain_mass_length2_ENTIRE_SYSTEM();
+	} catch (int e) { return g_last_error = e; }
+	out[1] = sc->sys.observables->rd_energy;
+	out[2] = sc->sys.observables->coulombic_energy;
+	out[3] = sc->sys.observables->polarization_energy;
+	out[4] = sc->sys.observables->vdw_energy;
+	return 0;
+}
+
+// Just the potential sweep (what BFC.potential.trial costs per move, PathIntegral.cpp:118)
+double mref_pi_potential(void *h) {
+	SimulationControl *sc = (SimulationControl *)h;
+	Quiet q;
+	return sc->PI_calculate_potential();
+}
+
+} // extern "C"
