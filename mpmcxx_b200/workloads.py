@@ -223,12 +223,24 @@ def triclinic_mix(n_mol: int = 24, seed: int = 5, solver: dict | None = None) ->
     pos = []; q = []; alpha = []; eps = []; sig = []; mass = []; mol = []; frozen = []; at = []; mt = []
     nfz = 12
     for i in range(nfz):
-        f = rs.random_sample(3)
+        f = np.array([(i % 3 + 0.5) / 3.0, ((i // 3) % 2 + 0.5) / 2.0, (i // 6 + 0.5) / 2.0])
         pos.append(f @ basis); q.append(0.4 if i % 2 == 0 else -0.4); alpha.append(1.1); eps.append(25.0)
         sig.append(3.2); mass.append(12.0); mol.append(0); frozen.append(1); at.append("C"); mt.append("FRM")
+    inv = np.linalg.inv(basis)
+
+    def too_close(p):
+        if not pos:
+            return False
+        d = (np.array(pos) - p) @ inv
+        d -= np.rint(d)
+        return bool((np.linalg.norm(d @ basis, axis=1) < 2.6).any())
+
     for m in range(n_mol):
-        c = (rs.random_sample(3) * 3.0 - 1.0) @ basis     # deliberately spills outside the cell: unwrapped coords
-        ax = _random_axes(rs, 1)[0]
+        while True:
+            c = (rs.random_sample(3) * 3.0 - 1.0) @ basis     # deliberately spills outside the cell: unwrapped coords
+            ax = _random_axes(rs, 1)[0]
+            if not any(too_close(c + off * ax) for off in (0.0, 0.9, -0.9)):
+                break
         for (name, off, qq, al, ee, ss, ms) in (("OA", 0.0, -0.6, 0.85, 60.0, 3.0, 16.0), ("HA", 0.9, 0.3, 0.0, 0.0, 0.0, 1.0),
                                                ("HB", -0.9, 0.3, 0.3, 8.0, 2.2, 1.0)):
             pos.append(c + off * ax); q.append(qq); alpha.append(al); eps.append(ee); sig.append(ss); mass.append(ms)

@@ -1,0 +1,64 @@
+"""Generate tests/golden/*.npz from the UNMODIFIED reference (oracle/_ref, built by `make -C oracle ref`).
+
+Run in the build container only (needs /root/reference):   python tests/golden/make_golden.py
+Each fixture stores the full input (flat, list-ordered sites + cell + input keywords) and the reference's
+outputs read as doubles through oracle/ref_harness.cpp: every energy sub-term, and for polarizable cases the
+per-site dipoles / fields / rank metric.  tests/cases.py names the cases; this script only evaluates them.
+"""
+import json
+import os
+import sys
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.dirname(os.path.dirname(HERE)))
+
+from oracle import ref  # noqa: E402
+from tests import cases  # noqa: E402
+
+
+def pack_system(s):
+    return dict(basis=s.basis, pos=s.pos, charge_e=s.charge_e, alpha=s.alpha, eps=s.eps, sigma=s.sigma, mass=s.mass,
+                mol=s.mol, frozen=s.frozen, opts=np.array(json.dumps(s.opts)), atomtype=np.array(s.atomtype),
+                moltype=np.array(s.moltype))
+
+
+def main():
+    for name, build in cases.CLASSIC.items():
+        s = build()
+        r = ref.RefSystem(s, ensemble="nvt")
+        t = r.terms()
+        d = r.dipoles()
+        c = r.cell()
+        out = pack_system(s)
+        out.update({"ref_" + k: np.float64(v) for k, v in t.items()})
+        out.update({"ref_" + k: v for k, v in d.items()})
+        out.update({"cell_" + k: v for k, v in c.items()})
+        # the MC-loop view: energy() as mc() calls it, cold then after moving one molecule (warm pair cache)
+        r2 = ref.RefSystem(s, ensemble="nvt")
+        e0 = r2.energy()
+        moved = cases.displaced(s)
+        r2.set_pos(moved.pos)
+        e1 = r2.energy()
+        out["ref_energy_cold"] = np.array([e0[k] for k in ("energy", "rd", "coulombic", "polar")])
+        out["ref_energy_moved"] = np.array([e1[k] for k in ("energy", "rd", "coulombic", "polar")])
+        out["moved_pos"] = moved.pos
+        np.savez_compressed(os.path.join(HERE, name + ".npz"), **out)
+        print("%-22s n=%4d  E=%.15g  pol=%.15g  it=%d" % (name, s.n, e0["energy"], t["polar"], t["iterations"]))
+    for name, build in cases.PI.items():
+        tmpl, beads = build()
+        P = beads.shape[0]
+        r = ref.RefSystem(tmpl, P=P)
+        for b in range(P):
+            r.set_pos(beads[b], b)
+        e = r.pi_energy()
+        out = pack_system(tmpl)
+        out["beads"] = beads
+        out.update({"ref_pi_" + k: np.float64(v) for k, v in e.items()})
+        np.savez_compressed(os.path.join(HERE, name + ".npz"), **out)
+        print("%-22s P=%d n=%4d  U=%.15g  K=%.15g" % (name, P, tmpl.n, e["potential"], e["kinetic"]))
+
+
+if __name__ == "__main__":
+    main()
