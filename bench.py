@@ -1,0 +1,439 @@
+#!/usr/bin/env python
+"""bench.py — MC moves/s of the mpmc++ energy hot path on B200 (one JSON line; contract in the task brief).
+
+A "step" is one Monte Carlo trial move on the headline workload: BASELINE.json config 4, the polarizable
+H2-in-framework system (8000 frozen framework sites + 400 five-site H2 = 10 000 sites, Ewald kmax 7, Thole
+exponential damping, solver = GS-ranked x4 + Palmo unless --solver says otherwise).  One move = displace one H2
+rigidly on the host -> mpmc_update_sites -> mpmc_energy (a FULL System::energy(): LJ + Ewald real/reciprocal/self +
+Thole solve) -> Metropolis accept/reject on the host (restore through mpmc_update_sites on reject).
+
+  value : moves/s with the configuration resident in HBM: K full energy evaluations timed with CUDA events on the
+          engine's stream (per-step events, L2 flushed between steps), max over ranks.
+  e2e   : moves/s through the C-ABI with HOST buffers: the move's coordinates go host->device and every energy
+          component comes back device->host inside the timed region (wall clock around each step, max over ranks).
+  N > 1 : the classic ensembles do not shard inside a move: N independent Markov chains, one per GPU,
+          no data-path collective -> weak scaling.  (The bead-sharded path-integral config is `--workload pi_h2`.)
+  --impl reference : the reference's own CPU energy() (oracle/_ref, the unmodified reference compiled from its
+          sources) on the host cores, on a bounded sample of the same workload (see `cpu_baseline.sample`).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+from mpmcxx_b200 import workloads as W  # noqa: E402
+
+FLOP_PER_DIPOLE_PAIR = 100.0     # K6, geometry + damping recomputed on the fly, per ORDERED pair per sweep
+FLOP_PER_LJ_PAIR = 54.0          # K1
+FLOP_PER_ES_PAIR = 82.0          # K1 + K2
+BYTES_PER_SITE_SWEEP = 56.0 + 4.0 + 24.0 + 24.0   # 56 B/site + id/flags + mu read + mu written
+
+
+def env_int(k, d):
+    return int(os.environ.get(k, d))
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# workloads
+# ----------------------------------------------------------------------------------------------------------------
+SOLVERS = {"gs_ranked_palmo": W.SOLVER_GS_RANKED_PALMO, "jacobi10": W.SOLVER_JACOBI10}
+
+
+def build_workload(name, solver, scale=1.0):
+    if name == "h2_framework":
+        ncell = max(2, int(round(20 * scale)))
+        n_h2 = max(2, int(round(400 * scale ** 3)))
+        s = W.h2_framework(ncell=ncell, n_h2=n_h2, solver=SOLVERS[solver], ensemble="nvt")
+        desc = "config4: H2 in frozen framework, %d sites (%d frozen + %d x 5-site H2), L=%g A, Ewald kmax 7, Thole exp damping, solver %s" % (
+            s.n, ncell ** 3, n_h2, ncell * 4.0, solver)
+        return s, desc
+    if name == "lj_argon":
+        side = max(2, int(round(16 * scale)))
+        s = W.lj_argon(n_side=side, L=60.0 * side / 16)
+        return s, "config3: bulk LJ argon NVT, %d atoms, L=%g A, rd_lrc on, rd_only" % (s.n, 60.0 * side / 16)
+    raise ValueError(name)
+
+
+class MoveGen:
+    """Host-side trial moves: rigid translation (uniform in +-step per axis) and rotation about a random axis of one
+    uniformly chosen mobile molecule (System.MonteCarlo.cpp:875 displace); Metropolis at temperature T."""
+
+    def __init__(self, s, seed, step=0.5, max_angle_deg=18.0):
+        self.s = s
+        self.rs = np.random.RandomState(seed)
+        starts = np.nonzero(np.diff(np.concatenate([[-1], s.mol])))[0]
+        ends = np.concatenate([starts[1:], [s.n]])
+        self.mols = [(int(a), int(b)) for a, b in zip(starts, ends) if not s.frozen[a]]
+        self.step, self.ang = step, np.deg2rad(max_angle_deg)
+        self.T = float(s.opts.get("temperature", 77.0))
+
+    def propose(self, pos):
+        a, b = self.mols[self.rs.randint(len(self.mols))]
+        old = pos[a:b].copy()
+        m = self.s.mass[a:b]
+        com = (old * m[:, None]).sum(0) / m.sum() if m.sum() > 0 else old.mean(0)
+        ax = self.rs.normal(size=3)
+        ax /= np.linalg.norm(ax)
+        th = (self.rs.random_sample() * 2 - 1) * self.ang
+        K = np.array([[0, -ax[2], ax[1]], [ax[2], 0, -ax[0]], [-ax[1], ax[0], 0]])
+        R = np.eye(3) + np.sin(th) * K + (1 - np.cos(th)) * (K @ K)
+        new = (old - com) @ R.T + com + (self.rs.random_sample(3) * 2 - 1) * self.step
+        return a, old, new
+
+    def accept(self, e_old, e_new):
+        if not np.isfinite(e_new):
+            return False                         # System.MonteCarlo.cpp:56-59
+        return self.rs.random_sample() < np.exp(min(0.0, -(e_new - e_old) / self.T))
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# clocks
+# ----------------------------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = "index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, gpu_index):
+        self.idx, self.rows, self.proc = gpu_index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.idx), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "200"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.th = threading.Thread(target=self._read, daemon=True)
+            self.th.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc:
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=2)
+            except Exception:
+                pass
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[1])); mx.append(float(r[2]))
+                for nme, v in zip(names, r[5:9]):
+                    if v.lower().startswith("active"):
+                        reasons.add(nme)
+            except Exception:
+                pass
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unavailable"], "samples": 0}
+        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# CPU baseline (the one place bench.py may execute oracle/)
+# ----------------------------------------------------------------------------------------------------------------
+def _ref_worker(args):
+    """One independent chain on one host core: reference energy() after one-molecule moves (warm pair cache)."""
+    workload, solver, scale, nsteps, seed, kind = args
+    from oracle import port, ref
+    s, _ = build_workload(workload, solver, scale)
+    gen = MoveGen(s, seed)
+    pos = s.pos.copy()
+    if kind == "reference":
+        r = ref.RefSystem(s, ensemble="nvt")
+        r.energy()                                  # cold first evaluation (mc_initial_energy), untimed
+        t0 = time.perf_counter()
+        for _ in range(nsteps):
+            a, old, new = gen.propose(pos)
+            pos[a:a + len(new)] = new
+            r.set_pos(pos)
+            r.energy()
+        dt = time.perf_counter() - t0
+    else:
+        port.energy(s, pos=pos, want_sites=False)
+        t0 = time.perf_counter()
+        for _ in range(nsteps):
+            a, old, new = gen.propose(pos)
+            pos[a:a + len(new)] = new
+            port.energy(s, pos=pos, want_sites=False)
+        dt = time.perf_counter() - t0
+    return dt, s.n
+
+
+def cpu_baseline(workload, solver, steps, budget_s=20.0, scale=None, chains=None):
+    """moves/s of the reference's CPU energy() on the host cores, on a bounded sample: `chains` independent Markov chains
+    (the reference is single-threaded inside energy(); its 'all cores' mode is independent chains) of the same
+    system built at linear scale `scale` (N ~ scale^3), extrapolated to the full size with the reference's O(N^2) cost."""
+    import multiprocessing as mp
+    from oracle import ref
+    kind = "reference" if ref.available() else "port"
+    cores = os.cpu_count() or 1
+    full, _ = build_workload(workload, solver, 1.0)
+    if scale is None:
+        scale = 0.5 if workload == "h2_framework" else 0.5
+    chains = chains or (cores if kind == "reference" else 1)
+    if kind == "port":
+        os.environ.setdefault("OMP_NUM_THREADS", str(cores))
+    small, _ = build_workload(workload, solver, scale)
+    # pick the step count from a one-step probe so that the whole leg stays near the budget
+    t_probe, _ = _ref_worker((workload, solver, scale, 1, 1, kind))
+    nsteps = int(max(1, min(steps, budget_s / max(t_probe, 1e-3))))
+    with mp.get_context("spawn").Pool(chains) as pool:
+        res = pool.map(_ref_worker, [(workload, solver, scale, nsteps, 100 + c, kind) for c in range(chains)])
+    wall = max(r[0] for r in res)
+    moves_small = chains * nsteps / wall
+    ratio = (small.n / full.n) ** 2
+    value = moves_small * ratio
+    return {"value": value, "unit": "moves/s", "cores": chains if kind == "reference" else cores, "kind": kind,
+            "sample": "%d independent chains x %d moves of the same system at N=%d (scale %.2f); measured %.4g moves/s aggregate, scaled to "
+                      "N=%d by (N_s/N)^2 = %.4g (the reference's energy() is O(N^2); full-size single chain measured 37 s/move, 17 GB, in "
+                      "the build container)" % (chains, nsteps, small.n, scale, moves_small, full.n, ratio),
+            "measured_sample_moves_per_s": moves_small, "sample_sites": small.n, "host_cpus": cores}
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# our arm
+# ----------------------------------------------------------------------------------------------------------------
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    from mpmcxx_b200 import engine
+
+    rank, world, local = env_int("RANK", 0), env_int("WORLD_SIZE", 1), env_int("LOCAL_RANK", 0)
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def sum_over_ranks(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        return float(t.item())
+
+    s, desc = build_workload(args.workload, args.solver, args.scale)
+    eng = engine.Engine(s, device=local)
+    gen = MoveGen(s, seed=1000 + rank)
+    pos = s.pos.copy()
+    flush_buf = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")     # > 126 MB L2
+
+    def flush_l2():
+        flush_buf.zero_()
+        torch.cuda.synchronize()
+
+    ext = torch.cuda.ExternalStream(eng.stream(), device=torch.device("cuda", local))
+    peak_tflops, _ = engine.probe_fp64_peak(local)
+
+    e_cur = eng.energy()["energy"]
+    naccept = 0
+
+    def mc_step():
+        nonlocal e_cur, naccept
+        a, old, new = gen.propose(pos)
+        eng.update_sites(a, new)                       # host -> device
+        out = eng.energy()                             # kernels + device -> host of every component
+        if gen.accept(e_cur, out["energy"]) and not out["iterator_failed"]:
+            pos[a:a + len(new)] = new
+            e_cur = out["energy"]
+            naccept += 1
+        else:
+            eng.update_sites(a, old)                   # restore()
+        return out
+
+    for _ in range(args.warmup):
+        mc_step()
+    # ---- e2e: wall clock around each step through the C-ABI with host buffers --------------------------------------
+    clocks = ClockSampler(local)
+    barrier()
+    clocks.start()
+    launches0 = eng.launches()
+    eng.set_timing(True)
+    t_e2e = 0.0
+    for _ in range(args.steps):
+        flush_l2()
+        t0 = time.perf_counter()
+        last = mc_step()
+        t_e2e += time.perf_counter() - t0
+    barrier()
+    timing = eng.timing()
+    eng.set_timing(False)
+    launches_e2e = eng.launches() - launches0
+    # ---- value: device-resident, CUDA events on the engine's stream -------------------------------------------------
+    t_dev_ms = 0.0
+    launches1 = eng.launches()
+    for _ in range(args.steps):
+        flush_l2()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(ext)
+        eng.enqueue()
+        e1.record(ext)
+        eng.fetch()
+        e1.synchronize()
+        t_dev_ms += e0.elapsed_time(e1)
+    barrier()
+    clk = clocks.stop()
+    launches_dev = eng.launches() - launches1
+
+    t_dev = max_over_ranks(t_dev_ms * 1e-3)
+    t_wall = max_over_ranks(t_e2e)
+    value = world * args.steps / t_dev
+    e2e_value = world * args.steps / t_wall
+    nmol_sites = len(gen.mols) and (gen.mols[0][1] - gen.mols[0][0])
+    polar_on = s.opts.get("polarization") == "on"
+
+    # ---- roofline of the dominant kernel (live CUDA-event timing of that kernel class inside the e2e region) ---------
+    np_pol = int(np.count_nonzero(s.alpha))
+    cands = {k: v for k, v in timing.items() if k != "energy_total" and v[1] > 0}
+    dom = max(cands, key=lambda k: cands[k][0]) if cands else None
+    roof = None
+    if dom:
+        ms_per_launch = cands[dom][0] / cands[dom][1]
+        if dom in ("gs_sweep", "dipole_sweep", "palmo"):
+            flops = FLOP_PER_DIPOLE_PAIR * np_pol * (np_pol - 1)
+            work = "%d x %d ordered dipole pairs x %g flop (SURVEY 8d K6)" % (np_pol, np_pol - 1, FLOP_PER_DIPOLE_PAIR)
+        elif dom == "pair":
+            flops = (FLOP_PER_LJ_PAIR if s.opts.get("rd_only") == "on" else FLOP_PER_ES_PAIR) * last["n_pair_evals"]
+            work = "%d pairs x %g flop (SURVEY 8d K1/K2)" % (last["n_pair_evals"], flops / last["n_pair_evals"])
+        else:
+            flops, work = float("nan"), "n/a"
+        ach = flops / (ms_per_launch * 1e-3) / 1e12
+        bytes_alg = BYTES_PER_SITE_SWEEP * s.n
+        roof = {"kernel": dom, "bound": "fp64", "achieved": ach, "peak": peak_tflops, "unit": "TFLOP/s", "frac": ach / peak_tflops,
+                "traffic": None, "ms_per_launch": ms_per_launch, "launches_timed": cands[dom][1], "work_per_launch": work,
+                "peak_source": "measured in this run: register-resident DFMA loop on all SMs (MEASURED_PEAKS.json has no FP64 entry)",
+                "share_of_step": cands[dom][0] / max(timing["energy_total"][0], 1e-9),
+                "hbm_view": {"algorithmic_bytes": bytes_alg, "achieved_gbs": bytes_alg / (ms_per_launch * 1e-3) / 1e9,
+                             "note": "the contraction reads O(N) bytes per sweep; HBM is not the binding limit (FP64 pipe is)"},
+                "kernel_ms_per_step": {k: v[0] / args.steps for k, v in timing.items()}}
+
+    out = {"metric": "mc_moves_per_sec", "value": value, "unit": "moves/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+           "ms_per_step": 1e3 * t_dev / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+           "data": "synthetic",
+           "config": {"workload": desc, "chains": world, "parallelism": "replicas only (one independent Markov chain per GPU, no collective)",
+                      "l2": "flushed between timed iterations (256 MiB write); working set itself is < 1 MB",
+                      "moves": "rigid displace+rotate of one H2, Metropolis T=%g K" % gen.T,
+                      "pair_evals_per_move": last["n_pair_evals"], "polarization_iterations": last["polarization_iterations"]},
+           "clocks": clk,
+           "e2e": {"value": e2e_value, "unit": "moves/s", "h2d_bytes_per_step": 32 * nmol_sites * (2 - naccept / max(1, args.steps + args.warmup)),
+                   "d2h_bytes_per_step": 32 * last_tiles(eng) + 32, "ms_per_step": 1e3 * t_wall / args.steps,
+                   "acceptance": naccept / max(1, args.steps + args.warmup)},
+           "gpu_launches": int(sum_over_ranks(launches_e2e + launches_dev)),
+           "pair_evals_per_sec": value * last["n_pair_evals"],
+           "roofline": roof}
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        out["cpu_baseline"] = cpu_baseline(args.workload, args.solver, args.steps, budget_s=args.cpu_budget)
+    if rank == 0 and world == 1 and not args.no_extra:
+        out["extra"] = extra_workloads(engine, local, peak_tflops)
+    if rank == 0:
+        print(json.dumps(out))
+    eng.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def last_tiles(eng):
+    # D2H per energy(): one 32-byte partial per listed tile + 32 bytes of scalars
+    n = eng.n
+    nt = (n + 127) // 128
+    fz = np.array([bool(np.all(eng.system.frozen[t * 128:(t + 1) * 128])) for t in range(nt)])
+    nff = int(fz.sum())
+    return nt * (nt + 1) // 2 - nff * (nff + 1) // 2
+
+
+def extra_workloads(engine, device, peak_tflops, steps=20):
+    """Secondary single-GPU numbers: config 3 (bulk LJ argon, the pair kernel alone) and the Jacobi solver variant of config 4."""
+    import torch
+    res = {}
+    for name, wl, solver in (("lj_argon_4096", "lj_argon", "jacobi10"), ("h2_framework_jacobi10", "h2_framework", "jacobi10")):
+        s, desc = build_workload(wl, solver, 1.0)
+        eng = engine.Engine(s, device=device)
+        ext = torch.cuda.ExternalStream(eng.stream(), device=torch.device("cuda", device))
+        for _ in range(3):
+            eng.energy()
+        eng.set_timing(True)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(ext)
+        for _ in range(steps):
+            eng.enqueue()
+            out = eng.fetch()[0]
+        e1.record(ext)
+        e1.synchronize()
+        ms = e0.elapsed_time(e1) / steps
+        tm = eng.timing()
+        eng.set_timing(False)
+        r = {"workload": desc, "moves_per_sec": 1e3 / ms, "ms_per_move": ms, "pair_evals_per_sec": out["n_pair_evals"] * 1e3 / ms,
+             "kernel_ms_per_move": {k: v[0] / steps for k, v in tm.items() if v[1]}}
+        if wl == "lj_argon":
+            kms = tm["pair"][0] / tm["pair"][1]
+            ach = FLOP_PER_LJ_PAIR * out["n_pair_evals"] / (kms * 1e-3) / 1e12
+            r["pair_kernel"] = {"ms_per_launch": kms, "achieved_tflops": ach, "frac_of_fp64_peak": ach / peak_tflops,
+                                "work": "%d pairs x %g flop" % (out["n_pair_evals"], FLOP_PER_LJ_PAIR)}
+        else:
+            npol = int(np.count_nonzero(s.alpha))
+            kms = tm["dipole_sweep"][0] / tm["dipole_sweep"][1]
+            ach = FLOP_PER_DIPOLE_PAIR * npol * (npol - 1) / (kms * 1e-3) / 1e12
+            r["dipole_kernel"] = {"ms_per_launch": kms, "achieved_tflops": ach, "frac_of_fp64_peak": ach / peak_tflops}
+        res[name] = r
+        eng.close()
+    return res
+
+
+def run_reference(args):
+    rank = env_int("RANK", 0)
+    if rank != 0:
+        return
+    t0 = time.perf_counter()
+    cb = cpu_baseline(args.workload, args.solver, args.steps + args.warmup, budget_s=max(20.0, args.cpu_budget * 3))
+    _, desc = build_workload(args.workload, args.solver, args.scale)
+    out = {"impl": "reference", "metric": "mc_moves_per_sec", "value": cb["value"], "unit": "moves/s", "n_gpus": env_int("WORLD_SIZE", 1),
+           "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 / cb["value"], "higher_is_better": True, "scaling": "weak",
+           "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": {"workload": desc},
+           "cpu_baseline": cb, "e2e": {"value": cb["value"], "unit": "moves/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+           "gpu_launches": 0, "wall_s": time.perf_counter() - t0}
+    print(json.dumps(out))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=30)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="h2_framework", choices=["h2_framework", "lj_argon"])
+    ap.add_argument("--solver", default="gs_ranked_palmo", choices=sorted(SOLVERS))
+    ap.add_argument("--scale", type=float, default=1.0, help="linear size factor of the synthetic system (1.0 = the named config)")
+    ap.add_argument("--cpu-budget", type=float, default=20.0, help="seconds of CPU work for the cpu_baseline leg")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extra", action="store_true")
+    args = ap.parse_args()
+    if args.warmup < 3:
+        args.warmup = 3
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,119 @@
+// device_math.cuh — FP64 building blocks shared by every kernel of the engine (sm_100a).
+//
+// Geometry follows System::minimum_image() (reference src/System.cpp:1202-1279) operation by operation and
+// WITHOUT fused multiply-add: the reference is built for baseline x86-64 (no FMA contraction) and its cutoff
+// tests (`rimg - 1e-12 < rc`, `r > rc`) act on the last bit of rimg for lattice configurations, so the pair
+// distance must round exactly as the reference's does.  Everything downstream of the distance (LJ, erfc,
+// exp, tensor contraction) is free to use FMA: those only move results at the 1e-16 level.
+#pragma once
+#include <cuda_runtime.h>
+#include <math.h>
+
+namespace mpmc {
+
+constexpr double kPi           = 3.141592653589793238462643383279502884;   // constants.h:12
+constexpr double kOneOverSqrtPi = 0.5641895835477562869480794515607725858440506293289988; // constants.h:48
+constexpr double kMaxValue     = 1.0e40;   // constants.h:53
+constexpr double kSmallDr      = 1.0e-12;  // constants.h:54
+constexpr double kDebye2Ska    = 85.10597636; // constants.h:38
+
+struct CellDev {
+	double b[3][3];     // pbc.basis            (rows = lattice vectors)
+	double rb[3][3];    // pbc.reciprocal_basis (plain inverse, PeriodicBoundary.cpp:83-101)
+	double cutoff, volume, ewald_alpha, polar_alpha;
+};
+
+// Thole / solver parameters handed to the polarization kernels
+struct PolarDev {
+	double damp;        // polar_damp (lambda)
+	double gamma;       // polar_gamma
+	double allowed_sqerr; // (polar_precision * DEBYE2SKA)^2, System.Energy.cpp:3228
+	int    damp_type;   // 0 off, 1 linear, 2 exponential
+	int    gs;          // polar_gs || polar_gs_ranked
+	int    sor, esor;
+};
+
+// rint() (ties to even) for |x| < 2^51 as two FP64 adds; identical to libm rint on that range.
+__device__ __forceinline__ double rint_magic(double x) {
+	const double M = 6755399441055744.0;   // 1.5 * 2^52
+	return __dadd_rn(__dadd_rn(x, M), -M);
+}
+
+// d = r_i - r_j  ->  minimum-image displacement (ix,iy,iz).  ORTHO is selected when every off-diagonal element
+// of the basis is exactly 0; then the general formula's extra terms are exact zeros and this short form is
+// bit-identical to it.
+template <bool ORTHO>
+__device__ __forceinline__ void min_image(const CellDev &c, double dx, double dy, double dz, double &ix, double &iy, double &iz) {
+	if (ORTHO) {
+		double fx = rint_magic(__dmul_rn(c.rb[0][0], dx));
+		double fy = rint_magic(__dmul_rn(c.rb[1][1], dy));
+		double fz = rint_magic(__dmul_rn(c.rb[2][2], dz));
+		ix = __dsub_rn(dx, __dmul_rn(c.b[0][0], fx));
+		iy = __dsub_rn(dy, __dmul_rn(c.b[1][1], fy));
+		iz = __dsub_rn(dz, __dmul_rn(c.b[2][2], fz));
+	} else {
+		// img[p] = sum_q recip[q][p] * d[q]   (System.cpp:1228-1235), accumulation order q = 0,1,2
+		double f0 = rint_magic(__dadd_rn(__dadd_rn(__dmul_rn(c.rb[0][0], dx), __dmul_rn(c.rb[1][0], dy)), __dmul_rn(c.rb[2][0], dz)));
+		double f1 = rint_magic(__dadd_rn(__dadd_rn(__dmul_rn(c.rb[0][1], dx), __dmul_rn(c.rb[1][1], dy)), __dmul_rn(c.rb[2][1], dz)));
+		double f2 = rint_magic(__dadd_rn(__dadd_rn(__dmul_rn(c.rb[0][2], dx), __dmul_rn(c.rb[1][2], dy)), __dmul_rn(c.rb[2][2], dz)));
+		// di[p] = sum_q basis[q][p] * img[q]  (:1238-1242); d - di (:1245-1246)
+		ix = __dsub_rn(dx, __dadd_rn(__dadd_rn(__dmul_rn(c.b[0][0], f0), __dmul_rn(c.b[1][0], f1)), __dmul_rn(c.b[2][0], f2)));
+		iy = __dsub_rn(dy, __dadd_rn(__dadd_rn(__dmul_rn(c.b[0][1], f0), __dmul_rn(c.b[1][1], f1)), __dmul_rn(c.b[2][1], f2)));
+		iz = __dsub_rn(dz, __dadd_rn(__dadd_rn(__dmul_rn(c.b[0][2], f0), __dmul_rn(c.b[1][2], f1)), __dmul_rn(c.b[2][2], f2)));
+	}
+}
+
+// |v|^2 summed x, y, z with separate multiplies and adds (System.cpp:1250-1255)
+__device__ __forceinline__ double norm2_nofma(double x, double y, double z) {
+	return __dadd_rn(__dadd_rn(__dmul_rn(x, x), __dmul_rn(y, y)), __dmul_rn(z, z));
+}
+
+// Thole damping factors (System.Energy.cpp:2713-2742) at separation r.  `excluded` and `alpha_prod` are only
+// read by the OFF / LINEAR variants.
+__device__ __forceinline__ void thole_damping(const PolarDev &p, double r, double r2, bool excluded, double alpha_prod,
+                                               double &damp1, double &damp2) {
+	if (p.damp_type == 2) {
+		const double l = p.damp, l2 = l * l, l3 = l2 * l;
+		double explr = exp(-l * r);
+		damp1 = 1.0 - explr * (0.5 * l2 * r2 + l * r + 1.0);
+		damp2 = damp1 - explr * (l3 * r2 * r / 6.0);
+	} else if (p.damp_type == 1) {
+		double s = p.damp * pow(alpha_prod, 1.0 / 6.0);
+		double v = r / s;
+		if (r < s) { damp1 = (4.0 - 3.0 * v) * v * v * v; damp2 = v * v * v * v; }
+		else damp1 = damp2 = 1.0;
+	} else {
+		damp1 = damp2 = excluded ? 0.0 : 1.0;
+	}
+}
+
+// acc += T_ij mu_j with T = damp1/r^3 I - 3 damp2/r^5 d d^T on the minimum-image displacement; no cutoff and
+// same-molecule pairs included (thole_amatrix, System.Energy.cpp:2694-2767).
+template <bool ORTHO>
+__device__ __forceinline__ void tensor_contract(const CellDev &c, const PolarDev &p, double xi, double yi, double zi,
+                                                double xj, double yj, double zj, bool excluded, double alpha_prod,
+                                                double mx, double my, double mz, double &ax, double &ay, double &az) {
+	double dx, dy, dz;
+	min_image<ORTHO>(c, __dsub_rn(xi, xj), __dsub_rn(yi, yj), __dsub_rn(zi, zj), dx, dy, dz);
+	double r2 = norm2_nofma(dx, dy, dz);
+	double r = sqrt(r2);
+	double ir3, ir5;
+	if (r == 0.0) { ir3 = ir5 = kMaxValue; }
+	else { double ir = 1.0 / r; double ir2 = ir * ir; ir3 = ir2 * ir; ir5 = ir3 * ir2; }
+	double damp1, damp2;
+	thole_damping(p, r, r2, excluded, alpha_prod, damp1, damp2);
+	double a = damp1 * ir3;
+	double b = 3.0 * damp2 * ir5 * (dx * mx + dy * my + dz * mz);
+	ax += a * mx - b * dx;
+	ay += a * my - b * dy;
+	az += a * mz - b * dz;
+}
+
+// deterministic warp reductions (xor tree: every lane ends with the same value)
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+	for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+	return v;
+}
+
+} // namespace mpmc

@@ -1,0 +1,889 @@
+// engine.cu — host side of the B200 energy engine and its C-ABI (include/mpmc_b200.h).
+//
+// One engine = the device-resident image of one reference `System` (or of P_local path-integral bead systems that
+// share a topology).  The host keeps a shadow of the flat site table (the reference's linked lists stay the source of
+// truth in the caller); the device holds
+//     posq  double4[n_beads][cap]   x, y, z, q                (32 B/site, the only array a move rewrites)
+//     lj    double2[cap]            sqrt(eps) (0 if LJ-null), sigma/2
+//     alpha double [cap], mass double[cap], meta int[cap]  (molecule index | frozen<<31)
+// plus O(N) work arrays for the polarization solve.  Nothing O(N^2) is ever stored (the reference keeps 200 B per
+// pair and a 3N x 3N matrix).  energy() = a fixed sequence of kernels on one stream; every reduction has a fixed
+// shape, so the same configuration always gives the same bits.
+#include "../../include/mpmc_b200.h"
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <string>
+#include <vector>
+
+#include "kernels_pair.cuh"
+#include "kernels_polar.cuh"
+#include "kernels_recip.cuh"
+
+using namespace mpmc;
+
+static thread_local std::string g_err;
+
+#define CK(call)                                                                                           \
+	do {                                                                                                   \
+		cudaError_t _e = (call);                                                                           \
+		if (_e != cudaSuccess) {                                                                           \
+			char _b[512];                                                                                  \
+			snprintf(_b, sizeof _b, "%s:%d: %s -> %s", __FILE__, __LINE__, #call, cudaGetErrorString(_e)); \
+			g_err = _b;                                                                                    \
+			return MPMC_ERR_CUDA;                                                                          \
+		}                                                                                                  \
+	} while (0)
+
+#define FAIL(code, ...)                        \
+	do {                                       \
+		char _b[512];                          \
+		snprintf(_b, sizeof _b, __VA_ARGS__);  \
+		g_err = _b;                            \
+		return (code);                         \
+	} while (0)
+
+namespace {
+
+template <class T> struct DevBuf {
+	T *p = nullptr;
+	size_t cap = 0;
+	int ensure(size_t count) {
+		if (count <= cap) return MPMC_OK;
+		if (p) cudaFree(p);
+		p = nullptr; cap = 0;
+		size_t want = std::max<size_t>(count, 16);
+		if (cudaMalloc(&p, want * sizeof(T)) != cudaSuccess) { cudaGetLastError(); g_err = "cudaMalloc failed"; return MPMC_ERR_ALLOC; }
+		cap = want;
+		return MPMC_OK;
+	}
+	void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+};
+
+// per-energy() scalars written by the kernels and copied back once: [0, B) reciprocal energy per bead,
+// [B, 4B) per bead { sum mu.E_s, sum mu.dE_ind, sum rrms }
+inline size_t res_len(int B) { return (size_t)4 * B; }
+
+} // namespace
+
+struct mpmc_engine {
+	mpmc_config cfg;
+	int B = 1, n = 0, cap = 0, dev = 0, num_sms = 0;
+	cudaStream_t stream = nullptr;
+	long long launches = 0;
+	// cell
+	CellDev cell;
+	bool ortho = false;
+	std::vector<KVec> kvec;
+	// host shadow (list order)
+	std::vector<double> h_pos;   // [B][n][3]
+	std::vector<double> h_q, h_alpha, h_eps, h_sigma, h_mass;
+	std::vector<int> h_mol, h_frozen;
+	// derived host state
+	std::vector<int2> tiles;
+	std::vector<int> plist, mobile_q, frozen_q, mol_start;
+	std::vector<unsigned char> blk_frozen, mol_mobile;
+	double lrc_pair = 0, lrc_self = 0, es_self = 0, n_pair_evals = 0;
+	bool topo_dirty = true, frozen_sk_dirty = true;
+	// device
+	DevBuf<double4> d_posq;
+	DevBuf<double2> d_lj;
+	DevBuf<double> d_alpha, d_mass;
+	DevBuf<int> d_meta, d_plist, d_mobile_q, d_frozen_q, d_mol_start, d_order, d_flags;
+	DevBuf<int2> d_tiles;
+	DevBuf<unsigned char> d_blk_frozen, d_mol_mobile;
+	DevBuf<KVec> d_kvec;
+	DevBuf<PairPartial> d_partials;
+	DevBuf<double2> d_sk_part, d_S_mobile, d_S_frozen, d_S_all;
+	DevBuf<double> d_efs, d_efi, d_efic, d_mu, d_new_mu, d_old_mu, d_rrms, d_rank, d_gs_part, d_com, d_mol_mass, d_chain;
+	DevBuf<unsigned long long> d_rmin;
+	DevBuf<double> d_result;
+	// pinned staging
+	double4 *h_stage = nullptr; size_t stage_cap = 0;
+	PairPartial *h_partials = nullptr; size_t partials_cap = 0;
+	double *h_result = nullptr;
+	int *h_flags = nullptr;
+	// polarization bookkeeping of the last energy()
+	int last_iterations = 0;
+	std::vector<int> last_failed;
+	bool enqueued = false;
+	int gs_grid = 0;
+	// optional per-kernel-class timing with CUDA events on the engine's stream (mpmc_set_timing)
+	bool timing = false;
+	std::vector<std::pair<cudaEvent_t, cudaEvent_t>> ev_pool;
+	std::vector<int> ev_class;          // class of every event pair used since the last collect
+	size_t ev_used = 0;
+	double t_ms[MPMC_NUM_KERNEL_CLASSES] = {0};
+	long long t_count[MPMC_NUM_KERNEL_CLASSES] = {0};
+};
+
+namespace {
+// RAII bracket: records an event pair around the kernels launched in its scope when timing is enabled
+struct Timed {
+	mpmc_engine *e; size_t slot = 0; bool on;
+	Timed(mpmc_engine *eng, int cls) : e(eng), on(eng->timing) {
+		if (!on) return;
+		if (e->ev_used == e->ev_pool.size()) {
+			cudaEvent_t a, b;
+			cudaEventCreate(&a); cudaEventCreate(&b);
+			e->ev_pool.push_back({a, b}); e->ev_class.push_back(cls);
+		}
+		slot = e->ev_used++;
+		e->ev_class[slot] = cls;
+		cudaEventRecord(e->ev_pool[slot].first, e->stream);
+	}
+	~Timed() { if (on) cudaEventRecord(e->ev_pool[slot].second, e->stream); }
+};
+void collect_timing(mpmc_engine *e) {   // call after a stream synchronize
+	for (size_t i = 0; i < e->ev_used; i++) {
+		float ms = 0;
+		if (cudaEventElapsedTime(&ms, e->ev_pool[i].first, e->ev_pool[i].second) == cudaSuccess) {
+			e->t_ms[e->ev_class[i]] += ms; e->t_count[e->ev_class[i]] += 1;
+		}
+	}
+	e->ev_used = 0;
+}
+} // namespace
+
+// ------------------------------------------------------------------------------------------------------------
+// host helpers
+// ------------------------------------------------------------------------------------------------------------
+namespace {
+
+// PeriodicBoundary::update (src/PeriodicBoundary.cpp:31-101) + update_pbc alphas (src/System.cpp:871-874)
+int compute_cell(mpmc_engine *e, const double basis[9]) {
+	CellDev &c = e->cell;
+	for (int i = 0; i < 3; i++) for (int j = 0; j < 3; j++) c.b[i][j] = basis[3 * i + j];
+	double (*b)[3] = c.b;
+	double v = b[0][0] * (b[1][1] * b[2][2] - b[1][2] * b[2][1]);
+	v += b[0][1] * (b[1][2] * b[2][0] - b[1][0] * b[2][2]);
+	v += b[0][2] * (b[1][0] * b[2][1] - b[1][1] * b[2][0]);
+	c.volume = v;
+	if (!(v > 0)) FAIL(MPMC_ERR_INVALID_BOX, "invalid simulation box dimensions (volume %g)", v);   // System.cpp:467-470
+	double short_mag = kMaxValue;
+	for (int i = -15; i <= 15; i++) for (int j = -15; j <= 15; j++) for (int k = -15; k <= 15; k++) {
+		if (!i && !j && !k) continue;
+		double cv[3];
+		for (int p = 0; p < 3; p++) cv[p] = i * b[0][p] + j * b[1][p] + k * b[2][p];
+		double m = std::sqrt(cv[0] * cv[0] + cv[1] * cv[1] + cv[2] * cv[2]);
+		if (m < short_mag) short_mag = m;
+	}
+	c.cutoff = 0.5 * short_mag;
+	if (!(c.cutoff > 0)) FAIL(MPMC_ERR_INVALID_BOX, "invalid simulation box dimensions (cutoff %g)", c.cutoff);
+	double iv = 1.0 / v;
+	double (*r)[3] = c.rb;
+	r[0][0] = iv * (b[1][1] * b[2][2] - b[1][2] * b[2][1]);
+	r[0][1] = iv * (b[0][2] * b[2][1] - b[0][1] * b[2][2]);
+	r[0][2] = iv * (b[0][1] * b[1][2] - b[0][2] * b[1][1]);
+	r[1][0] = iv * (b[1][2] * b[2][0] - b[1][0] * b[2][2]);
+	r[1][1] = iv * (b[0][0] * b[2][2] - b[0][2] * b[2][0]);
+	r[1][2] = iv * (b[0][2] * b[1][0] - b[0][0] * b[1][2]);
+	r[2][0] = iv * (b[1][0] * b[2][1] - b[1][1] * b[2][0]);
+	r[2][1] = iv * (b[0][1] * b[2][0] - b[0][0] * b[2][1]);
+	r[2][2] = iv * (b[0][0] * b[1][1] - b[0][1] * b[1][0]);
+	c.ewald_alpha = e->cfg.ewald_alpha > 0 ? e->cfg.ewald_alpha : 3.5 / c.cutoff;
+	c.polar_alpha = e->cfg.polar_ewald_alpha > 0 ? e->cfg.polar_ewald_alpha : 3.5 / c.cutoff;
+	e->ortho = b[0][1] == 0 && b[0][2] == 0 && b[1][0] == 0 && b[1][2] == 0 && b[2][0] == 0 && b[2][1] == 0;
+	// hemisphere of k vectors (src/System.Energy.cpp:1577-1590) with the two Gaussian weights precomputed
+	e->kvec.clear();
+	const int kmax = e->cfg.ewald_kmax;
+	int l[3];
+	for (l[0] = 0; l[0] <= kmax; l[0]++)
+		for (l[1] = (!l[0] ? 0 : -kmax); l[1] <= kmax; l[1]++)
+			for (l[2] = ((!l[0] && !l[1]) ? 1 : -kmax); l[2] <= kmax; l[2]++) {
+				if (l[0] * l[0] + l[1] * l[1] + l[2] * l[2] > kmax * kmax) continue;
+				KVec k;
+				double kk[3];
+				for (int p = 0; p < 3; p++) {
+					kk[p] = 0;
+					for (int q = 0; q < 3; q++) kk[p] += 2.0 * kPi * c.rb[p][q] * l[q];
+				}
+				k.kx = kk[0]; k.ky = kk[1]; k.kz = kk[2];
+				const double k2 = kk[0] * kk[0] + kk[1] * kk[1] + kk[2] * kk[2];
+				k.w_energy = std::exp(-k2 / (4.0 * c.ewald_alpha * c.ewald_alpha)) / k2;
+				k.w_field = std::exp(-k2 / (4.0 * c.polar_alpha * c.polar_alpha)) / k2;
+				k.l0 = l[0]; k.l1 = l[1]; k.l2 = l[2]; k.pad = 0;
+				e->kvec.push_back(k);
+			}
+	int rc = e->d_kvec.ensure(e->kvec.size());
+	if (rc) return rc;
+	if (!e->kvec.empty()) CK(cudaMemcpyAsync(e->d_kvec.p, e->kvec.data(), e->kvec.size() * sizeof(KVec), cudaMemcpyHostToDevice, e->stream));
+	CK(cudaStreamSynchronize(e->stream));
+	e->frozen_sk_dirty = true;
+	e->topo_dirty = true;   // LRC and self terms depend on volume / cutoff / alpha
+	return MPMC_OK;
+}
+
+// lj_lrc_corr / lj_lrc_self (src/System.Energy.cpp:1036-1096), plain-LJ branch
+double lrc_formula(double eps, double sigma, double cutoff, double volume) {
+	double sig_cut = std::fabs(sigma) / cutoff;
+	double sig3 = std::fabs(sigma);
+	sig3 *= sig3 * sig3;
+	double sig_cut3 = sig_cut * sig_cut * sig_cut;
+	double sig_cut9 = sig_cut3 * sig_cut3 * sig_cut3;
+	return ((16.0 / 3.0) * kPi * eps * sig3) * ((1.0 / 3.0) * sig_cut9 - sig_cut3) / volume;
+}
+
+// Everything that depends on the site table but not on coordinates: device parameter arrays, work lists and the
+// configuration-independent energy terms (pair/self LRC, Ewald point-self term).
+int rebuild_topology(mpmc_engine *e) {
+	const int n = e->n;
+	int rc;
+	if ((rc = e->d_lj.ensure(e->cap)) || (rc = e->d_alpha.ensure(e->cap)) || (rc = e->d_mass.ensure(e->cap)) || (rc = e->d_meta.ensure(e->cap))) return rc;
+	std::vector<double2> lj(n);
+	std::vector<int> meta(n);
+	for (int i = 0; i < n; i++) {
+		const bool active = e->h_eps[i] != 0.0 && e->h_sigma[i] > 0.0;   // sigma < 0 leaves pair epsilon at 0 in the reference (System.cpp:1167-1169)
+		lj[i] = make_double2(active ? std::sqrt(e->h_eps[i]) : 0.0, 0.5 * e->h_sigma[i]);
+		meta[i] = (e->h_mol[i] & 0x7fffffff) | (e->h_frozen[i] ? (int)0x80000000u : 0);
+	}
+	if (n) {
+		CK(cudaMemcpyAsync(e->d_lj.p, lj.data(), n * sizeof(double2), cudaMemcpyHostToDevice, e->stream));
+		CK(cudaMemcpyAsync(e->d_meta.p, meta.data(), n * sizeof(int), cudaMemcpyHostToDevice, e->stream));
+		CK(cudaMemcpyAsync(e->d_alpha.p, e->h_alpha.data(), n * sizeof(double), cudaMemcpyHostToDevice, e->stream));
+		CK(cudaMemcpyAsync(e->d_mass.p, e->h_mass.data(), n * sizeof(double), cudaMemcpyHostToDevice, e->stream));
+	}
+	// frozen-block flags (32-site granularity) and the triangular tile list of the energy sweep
+	const int nb32 = (n + kOrdI - 1) / kOrdI;
+	e->blk_frozen.assign(std::max(nb32, 1), 0);
+	for (int b = 0; b < nb32; b++) {
+		bool all = true;
+		for (int i = b * kOrdI; i < std::min(n, (b + 1) * kOrdI); i++) all = all && e->h_frozen[i];
+		e->blk_frozen[b] = all;
+	}
+	const int nt = (n + kPairTile - 1) / kPairTile;
+	std::vector<unsigned char> tile_frozen(std::max(nt, 1), 0);
+	for (int t = 0; t < nt; t++) {
+		bool all = true;
+		for (int i = t * kPairTile; i < std::min(n, (t + 1) * kPairTile); i++) all = all && e->h_frozen[i];
+		tile_frozen[t] = all;
+	}
+	e->tiles.clear();
+	for (int a = 0; a < nt; a++)
+		for (int b = a; b < nt; b++)
+			if (!(tile_frozen[a] && tile_frozen[b])) e->tiles.push_back(make_int2(a, b));
+	// work lists
+	e->plist.clear(); e->mobile_q.clear(); e->frozen_q.clear(); e->mol_start.clear(); e->mol_mobile.clear();
+	long long nfrozen = 0;
+	for (int i = 0; i < n; i++) {
+		if (e->h_alpha[i] != 0.0) e->plist.push_back(i);
+		if (e->h_q[i] != 0.0) (e->h_frozen[i] ? e->frozen_q : e->mobile_q).push_back(i);
+		if (i == 0 || e->h_mol[i] != e->h_mol[i - 1]) { e->mol_start.push_back(i); e->mol_mobile.push_back(e->h_frozen[i] ? 0 : 1); }
+		nfrozen += e->h_frozen[i] ? 1 : 0;
+	}
+	e->mol_start.push_back(n);
+	e->n_pair_evals = 0.5 * ((double)n * (n - 1) - (double)nfrozen * (nfrozen - 1));
+	auto up = [&](auto &dbuf, const auto &vec) -> int {
+		int r = dbuf.ensure(std::max<size_t>(vec.size(), 1));
+		if (r) return r;
+		if (!vec.empty()) CK(cudaMemcpyAsync(dbuf.p, vec.data(), vec.size() * sizeof(vec[0]), cudaMemcpyHostToDevice, e->stream));
+		return MPMC_OK;
+	};
+	if ((rc = up(e->d_tiles, e->tiles)) || (rc = up(e->d_plist, e->plist)) || (rc = up(e->d_mobile_q, e->mobile_q)) ||
+	    (rc = up(e->d_frozen_q, e->frozen_q)) || (rc = up(e->d_mol_start, e->mol_start)) || (rc = up(e->d_blk_frozen, e->blk_frozen)) ||
+	    (rc = up(e->d_mol_mobile, e->mol_mobile))) return rc;
+	CK(cudaStreamSynchronize(e->stream));   // the std::vectors above go out of scope / may be rebuilt
+
+	// configuration-independent terms, by (eps, sigma) type instead of by pair.  Pair LRC covers every non-frozen pair with
+	// eps_ij != 0 and sigma_ij != 0, intramolecular pairs included (System.Energy.cpp:1045-1050); self LRC every non-frozen
+	// site with eps, sigma != 0 (:1076-1079).
+	e->lrc_pair = e->lrc_self = e->es_self = 0;
+	const CellDev &c = e->cell;
+	if (e->cfg.rd_lrc) {
+		struct Cnt { double total = 0, frozen = 0; };
+		std::map<std::pair<double, double>, Cnt> types;   // sites that can form a pair with eps_ij, sigma_ij != 0
+		for (int i = 0; i < n; i++) {
+			if (e->h_sigma[i] != 0 && e->h_eps[i] != 0 && !e->h_frozen[i]) e->lrc_self += lrc_formula(e->h_eps[i], e->h_sigma[i], c.cutoff, c.volume);
+			if (e->h_eps[i] != 0.0 && e->h_sigma[i] > 0.0) {
+				Cnt &t = types[{e->h_eps[i], e->h_sigma[i]}];
+				t.total += 1; t.frozen += e->h_frozen[i] ? 1 : 0;
+			}
+		}
+		for (auto a = types.begin(); a != types.end(); ++a)
+			for (auto b = a; b != types.end(); ++b) {
+				double npairs = (a == b) ? 0.5 * (a->second.total * (a->second.total - 1) - a->second.frozen * (a->second.frozen - 1))
+				                         : a->second.total * b->second.total - a->second.frozen * b->second.frozen;
+				if (npairs == 0) continue;
+				const double eps = std::sqrt(a->first.first * b->first.first), sig = 0.5 * (a->first.second + b->first.second);
+				e->lrc_pair += npairs * lrc_formula(eps, sig, c.cutoff, c.volume);
+			}
+	}
+	if (!e->cfg.rd_only)
+		for (int i = 0; i < n; i++)
+			if (!e->h_frozen[i]) e->es_self -= c.ewald_alpha * e->h_q[i] * e->h_q[i] / std::sqrt(kPi);   // System.Energy.cpp:1626-1643
+	e->topo_dirty = false;
+	e->frozen_sk_dirty = true;
+	return MPMC_OK;
+}
+
+int ensure_stage(mpmc_engine *e, size_t count) {
+	if (count <= e->stage_cap) return MPMC_OK;
+	if (e->h_stage) cudaFreeHost(e->h_stage);
+	e->h_stage = nullptr; e->stage_cap = 0;
+	size_t want = std::max<size_t>(count, 1024);
+	CK(cudaMallocHost(&e->h_stage, want * sizeof(double4)));
+	e->stage_cap = want;
+	return MPMC_OK;
+}
+
+// copy sites [first, first+count) of every bead (or one bead) from the shadow to the device posq array
+int push_positions(mpmc_engine *e, int bead_lo, int bead_hi, int first, int count) {
+	if (count <= 0) return MPMC_OK;
+	const int nb = bead_hi - bead_lo;
+	int rc = ensure_stage(e, (size_t)nb * count);
+	if (rc) return rc;
+	CK(cudaStreamSynchronize(e->stream));   // the staging buffer may still be in flight from the previous move
+	for (int b = 0; b < nb; b++)
+		for (int i = 0; i < count; i++) {
+			const double *p = &e->h_pos[((size_t)(bead_lo + b) * e->n + first + i) * 3];
+			e->h_stage[(size_t)b * count + i] = make_double4(p[0], p[1], p[2], e->h_q[first + i]);
+		}
+	for (int b = 0; b < nb; b++)
+		CK(cudaMemcpyAsync(e->d_posq.p + (size_t)(bead_lo + b) * e->cap + first, e->h_stage + (size_t)b * count, count * sizeof(double4),
+		                   cudaMemcpyHostToDevice, e->stream));
+	return MPMC_OK;
+}
+
+int validate_config(const mpmc_config *cfg) {
+	if (cfg->n_beads < 1) FAIL(MPMC_ERR_INVALID_SETTING, "n_beads must be >= 1");
+	if (cfg->ewald_kmax < 1 || cfg->ewald_kmax > kMaxKmax) FAIL(MPMC_ERR_INVALID_SETTING, "ewald_kmax must be in [1, %d]", kMaxKmax);
+	if (cfg->polarization && !cfg->rd_only) {
+		// the reference's own validator for `cuda on` (src/SimulationControl.cpp:2612-2627) requires the iterative solver
+		if (!cfg->polar_iterative) FAIL(MPMC_ERR_UNSUPPORTED, "GPU acceleration available for iterative Thole only, enable polar_iterative");
+		if (cfg->damp_type < 0 || cfg->damp_type > 2) FAIL(MPMC_ERR_INVALID_SETTING, "Thole damping method not specified");
+		if (cfg->polar_damp <= 0.0 && cfg->damp_type != MPMC_DAMPING_OFF) FAIL(MPMC_ERR_INVALID_SETTING, "damping factor must be specified");
+		if (cfg->polar_precision > 0.0 && cfg->polar_max_iter > 0) FAIL(MPMC_ERR_INCOMPATIBLE, "cannot specify both polar_precision and polar_max_iter");
+		if (cfg->polar_precision < 0.0) FAIL(MPMC_ERR_INVALID_SETTING, "invalid polarization iterative precision");
+		if (!cfg->polar_zodid && cfg->polar_precision == 0.0 && cfg->polar_max_iter <= 0)
+			FAIL(MPMC_ERR_MISSING_SETTING, "polar_max_iter or polar_precision must be set for the iterative solver");
+		if (cfg->polar_sor && cfg->polar_esor) FAIL(MPMC_ERR_INCOMPATIBLE, "cannot specify both SOR and ESOR SCF methods");
+	}
+	return MPMC_OK;
+}
+
+template <class K> int set_smem(K kernel, size_t bytes) {
+	CK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+	return MPMC_OK;
+}
+
+} // namespace
+
+static int adopt_table(mpmc_engine *e) {
+	// (re)size device arrays for e->n sites and push everything
+	const int n = e->n;
+	if (n > e->cap || !e->d_posq.p) e->cap = std::max({e->cap, n + n / 2, 64});
+	int rc;
+	if ((rc = e->d_posq.ensure((size_t)e->B * e->cap))) return rc;
+	for (int i = 1; i < n; i++)
+		if (e->h_mol[i] < e->h_mol[i - 1]) FAIL(MPMC_ERR_INVALID_INPUT, "mol[] must be non-decreasing (site %d)", i);
+	if ((rc = rebuild_topology(e))) return rc;
+	return push_positions(e, 0, e->B, 0, n);
+}
+
+
+// ---- energy ----------------------------------------------------------------------------------------------
+#define LAUNCHED(e) ((e)->launches++)
+
+static int run_structure(mpmc_engine *e, DevBuf<int> &list, int nlist, DevBuf<double2> &S, const double2 *addend) {
+	const int nk = (int)e->kvec.size(), kmax = e->cfg.ewald_kmax, B = e->B;
+	int rc;
+	if ((rc = S.ensure((size_t)B * nk))) return rc;
+	const int nchunks = (nlist + kSkSites - 1) / kSkSites;
+	if (nchunks > 0) {
+		if ((rc = e->d_sk_part.ensure((size_t)B * nchunks * nk))) return rc;
+		const size_t smem = sizeof(double2) * kSkSites * 3 * (kmax + 1);
+{ Timed _t(e, MPMC_K_STRUCTURE);
+		k_structure_partial<<<dim3(nchunks, B), kSkThreads, smem, e->stream>>>(e->d_posq.p, e->cap, list.p, nlist, e->d_kvec.p, nk, kmax, e->cell,
+		                                                                        e->d_sk_part.p, nchunks);
+		LAUNCHED(e);
+ }	}
+	k_structure_reduce<<<dim3((nk + 127) / 128, B), 128, 0, e->stream>>>(e->d_sk_part.p, nchunks, nk, S.p, addend);
+	LAUNCHED(e);
+	CK(cudaGetLastError());
+	return MPMC_OK;
+}
+
+template <bool ORTHO>
+static int run_polar(mpmc_engine *e) {
+	const int n = e->n, B = e->B, np = (int)e->plist.size();
+	const mpmc_config &cf = e->cfg;
+	const size_t len = (size_t)B * n * 3;
+	int rc;
+	if ((rc = e->d_efs.ensure(len)) || (rc = e->d_efi.ensure(len)) || (rc = e->d_efic.ensure(len)) || (rc = e->d_mu.ensure(len)) ||
+	    (rc = e->d_new_mu.ensure(len)) || (rc = e->d_old_mu.ensure(len)) || (rc = e->d_rrms.ensure((size_t)B * n)) ||
+	    (rc = e->d_rank.ensure((size_t)B * n)) || (rc = e->d_order.ensure(std::max(np, 1))) ||
+	    (rc = e->d_gs_part.ensure((size_t)e->gs_grid * kGsB * 3))) return rc;
+	const dim3 ogrid((n + kOrdI - 1) / kOrdI, B);
+	const int nk = (int)e->kvec.size(), kmax = cf.ewald_kmax;
+	// thole_field(): static field (System.Energy.cpp:3271-3296)
+	if (cf.polar_ewald) {
+		// S_all = S_frozen + S_mobile: the mobile chunk partials computed for coulombic_reciprocal() are still in d_sk_part
+		if ((rc = e->d_S_all.ensure((size_t)B * nk))) return rc;
+		k_structure_reduce<<<dim3((nk + 127) / 128, B), 128, 0, e->stream>>>(e->d_sk_part.p, ((int)e->mobile_q.size() + kSkSites - 1) / kSkSites, nk,
+		                                                                     e->d_S_all.p, e->d_S_frozen.p);
+		LAUNCHED(e);
+		const size_t smem = sizeof(double2) * kFrSites * 3 * (kmax + 1);
+{ Timed _t(e, MPMC_K_FIELD_RECIP);
+		k_field_recip<<<dim3((n + kFrSites - 1) / kFrSites, B), kFrSites, smem, e->stream>>>(e->d_posq.p, n, e->cap, e->d_kvec.p, nk, kmax, e->d_S_all.p,
+		                                                                                     e->cell, 8.0 * kPi / e->cell.volume, e->d_efs.p);
+		LAUNCHED(e);
+ }{ Timed _t(e, MPMC_K_FIELD_REAL);
+		k_field_real<ORTHO, true><<<ogrid, kOrdThreads, 0, e->stream>>>(e->d_posq.p, e->d_meta.p, e->d_blk_frozen.p, n, e->cap, e->cell, e->d_efs.p);
+		LAUNCHED(e);
+ }	} else {
+		CK(cudaMemsetAsync(e->d_efs.p, 0, len * sizeof(double), e->stream));
+{ Timed _t(e, MPMC_K_FIELD_REAL);
+		k_field_real<ORTHO, false><<<ogrid, kOrdThreads, 0, e->stream>>>(e->d_posq.p, e->d_meta.p, e->d_blk_frozen.p, n, e->cap, e->cell, e->d_efs.p);
+		LAUNCHED(e);
+ }	}
+	PolarDev pd;
+	pd.damp = cf.polar_damp; pd.gamma = cf.polar_gamma; pd.damp_type = cf.damp_type;
+	pd.gs = cf.polar_gs || cf.polar_gs_ranked; pd.sor = cf.polar_sor; pd.esor = cf.polar_esor;
+	pd.allowed_sqerr = cf.polar_precision * cf.polar_precision * kDebye2Ska * kDebye2Ska;
+	const double gamma_init = (!cf.polar_sor && !cf.polar_esor) ? cf.polar_gamma : 1.0;
+	const int eb = 256;
+	k_dipole_init<<<(unsigned)((len + eb - 1) / eb), eb, 0, e->stream>>>(e->d_alpha.p, e->d_efs.p, n, B, gamma_init, e->d_mu.p, e->d_new_mu.p,
+	                                                                    e->d_old_mu.p, e->d_efi.p, e->d_efic.p, e->d_rrms.p);
+	LAUNCHED(e);
+	// GS ranking (System.cpp:1000-1029) — the metric only depends on the geometry, so both sweep orders are known up front
+	const bool ranked = cf.polar_gs_ranked && !cf.polar_zodid;
+	if (ranked && np > 0) {
+		k_fill_u64<<<1, 32, 0, e->stream>>>(e->d_rmin.p, B, 0x7ff0000000000000ull);   // +inf
+		LAUNCHED(e);
+{ Timed _t(e, MPMC_K_RANK);
+		k_rank_rmin<ORTHO><<<ogrid, kOrdThreads, 0, e->stream>>>(e->d_posq.p, e->d_alpha.p, n, e->cap, e->cell, e->d_rmin.p);
+		k_rank_count<<<ogrid, kOrdThreads, 0, e->stream>>>(e->d_posq.p, e->d_alpha.p, n, e->cap, e->d_rmin.p, e->d_rank.p);
+		e->launches += 2;
+ }	} else CK(cudaMemsetAsync(e->d_rank.p, 0, sizeof(double) * (size_t)B * n, e->stream));
+
+	e->last_iterations = 0;
+	std::fill(e->last_failed.begin(), e->last_failed.end(), 0);
+	if (cf.polar_zodid || np == 0) return MPMC_OK;
+	if (pd.gs && B != 1) FAIL(MPMC_ERR_UNSUPPORTED, "Gauss-Seidel polarization with n_beads > 1 is not supported yet");
+
+	const bool need_old = cf.polar_rrms || cf.polar_precision > 0 || cf.polar_sor || cf.polar_esor;
+	const bool want_check = cf.polar_rrms || cf.polar_precision > 0;
+	int it = 0;
+	bool keep = true;
+	while (keep) {
+		it++;
+		if (it >= 128 && cf.polar_precision > 0) {   // MAX_ITERATION_COUNT (constants.h:52), System.Energy.cpp:3483-3494
+			for (int b = 0; b < B; b++) {
+				k_dipole_fail<<<(n * 3 + eb - 1) / eb, eb, 0, e->stream>>>(e->d_alpha.p, e->d_efs.p, n, (size_t)b * n * 3, e->d_mu.p, e->d_efic.p);
+				LAUNCHED(e);
+				e->last_failed[b] = 1;
+			}
+			break;
+		}
+		if (need_old) CK(cudaMemcpyAsync(e->d_old_mu.p, e->d_mu.p, len * sizeof(double), cudaMemcpyDeviceToDevice, e->stream));
+		if (!pd.gs) {
+{ Timed _t(e, MPMC_K_DIPOLE_SWEEP);
+			k_dipole_sweep<ORTHO, false><<<ogrid, kOrdThreads, 0, e->stream>>>(e->d_posq.p, e->d_alpha.p, e->d_meta.p, e->d_plist.p, np, n, e->cap, e->cell, pd,
+			                                                                  e->d_mu.p, e->d_efs.p, e->d_efi.p, e->d_new_mu.p, e->d_efic.p);
+			LAUNCHED(e);
+ }		} else {
+			const int *order = e->d_plist.p;                        // first sweep: list order (ranked_array = identity, :3463)
+			if (ranked && it >= 2) {
+				if (it == 2) { k_rank_order_plist<<<(np + 255) / 256, 256, 0, e->stream>>>(e->d_rank.p, e->d_plist.p, np, e->d_order.p); LAUNCHED(e); }
+				order = e->d_order.p;
+			}
+			const double4 *pq = e->d_posq.p;
+			const double *al = e->d_alpha.p, *efs = e->d_efs.p;
+			const int *meta = e->d_meta.p;
+			double *mu = e->d_mu.p, *efi = e->d_efi.p, *nmu = e->d_new_mu.p, *part = e->d_gs_part.p;
+			int npv = np;
+			CellDev cell = e->cell;
+			void *args[] = {&pq, &al, &meta, &order, &npv, &cell, &pd, &mu, &efs, &efi, &nmu, &part};
+{ Timed _t(e, MPMC_K_GS_SWEEP);
+			CK(cudaLaunchCooperativeKernel((void *)k_gs_sweep<ORTHO>, dim3(e->gs_grid), dim3(kGsThreads), args, kGsSmemBytes, e->stream));
+			LAUNCHED(e);
+ }		}
+		if (want_check) {
+			CK(cudaMemsetAsync(e->d_flags.p, 0, sizeof(int) * B, e->stream));
+			k_dipole_check<<<(B * n + eb - 1) / eb, eb, 0, e->stream>>>(e->d_new_mu.p, e->d_old_mu.p, n, B, 1, pd.allowed_sqerr, e->d_rrms.p, e->d_flags.p);
+			LAUNCHED(e);
+		}
+		if (cf.polar_precision == 0.0) keep = (it != cf.polar_max_iter);     // are_we_done_yet, fixed-iteration branch (:3222-3225)
+		else {
+			CK(cudaMemcpyAsync(e->h_flags, e->d_flags.p, sizeof(int) * B, cudaMemcpyDeviceToHost, e->stream));
+			CK(cudaStreamSynchronize(e->stream));
+			keep = false;
+			for (int b = 0; b < B; b++) keep = keep || e->h_flags[b];        // bead systems iterate in lock-step until all have converged
+		}
+		if (cf.polar_palmo && !keep) {                                       // :3518-3519
+{ Timed _t(e, MPMC_K_PALMO);
+			k_dipole_sweep<ORTHO, true><<<ogrid, kOrdThreads, 0, e->stream>>>(e->d_posq.p, e->d_alpha.p, e->d_meta.p, e->d_plist.p, np, n, e->cap, e->cell, pd,
+			                                                                 e->d_mu.p, e->d_efs.p, e->d_efi.p, e->d_new_mu.p, e->d_efic.p);
+			LAUNCHED(e);
+ }		}
+		k_mu_update<<<(unsigned)((len + eb - 1) / eb), eb, 0, e->stream>>>(e->d_new_mu.p, e->d_old_mu.p, len, cf.polar_sor, cf.polar_esor, cf.polar_gamma,
+		                                                                  std::exp(-cf.polar_gamma * it), e->d_mu.p);
+		LAUNCHED(e);
+	}
+	e->last_iterations = it;
+	CK(cudaGetLastError());
+	return MPMC_OK;
+}
+
+template <bool ORTHO>
+static int enqueue_energy(mpmc_engine *e) {
+	const int n = e->n, B = e->B;
+	const mpmc_config &cf = e->cfg;
+	int rc;
+	if (n < 1) FAIL(MPMC_ERR_NO_MOLECULES, "energy: no sites uploaded");
+	if (e->topo_dirty && (rc = rebuild_topology(e))) return rc;
+	Timed _whole(e, MPMC_K_ENERGY_TOTAL);
+	const bool es = !cf.rd_only;
+	// pair sweep: lj() + coulombic_real()
+	const int ntiles = (int)e->tiles.size();
+	if ((rc = e->d_partials.ensure((size_t)B * std::max(ntiles, 1)))) return rc;
+	if ((size_t)B * ntiles > e->partials_cap) {
+		if (e->h_partials) cudaFreeHost(e->h_partials);
+		e->h_partials = nullptr;
+		CK(cudaMallocHost(&e->h_partials, sizeof(PairPartial) * (size_t)B * ntiles));
+		e->partials_cap = (size_t)B * ntiles;
+	}
+	if (ntiles) {
+{ Timed _t(e, MPMC_K_PAIR);
+		if (es) k_pair_energy<ORTHO, true><<<dim3(ntiles, B), kPairTile, 0, e->stream>>>(e->d_posq.p, e->d_lj.p, e->d_meta.p, n, e->cap, e->d_tiles.p, ntiles, e->cell, e->d_partials.p);
+		else    k_pair_energy<ORTHO, false><<<dim3(ntiles, B), kPairTile, 0, e->stream>>>(e->d_posq.p, e->d_lj.p, e->d_meta.p, n, e->cap, e->d_tiles.p, ntiles, e->cell, e->d_partials.p);
+		LAUNCHED(e);
+ }		CK(cudaMemcpyAsync(e->h_partials, e->d_partials.p, sizeof(PairPartial) * (size_t)B * ntiles, cudaMemcpyDeviceToHost, e->stream));
+	}
+	CK(cudaMemsetAsync(e->d_result.p, 0, sizeof(double) * res_len(B), e->stream));
+	if (es) {
+		const int nk = (int)e->kvec.size();
+		// framework structure factor: only when the cell or a frozen charged site changed
+		if (e->frozen_sk_dirty) {
+			if ((rc = run_structure(e, e->d_frozen_q, (int)e->frozen_q.size(), e->d_S_frozen, nullptr))) return rc;
+			e->frozen_sk_dirty = false;
+		}
+		if ((rc = run_structure(e, e->d_mobile_q, (int)e->mobile_q.size(), e->d_S_mobile, nullptr))) return rc;
+		k_recip_energy<<<B, 256, 0, e->stream>>>(e->d_S_mobile.p, e->d_kvec.p, nk, 4.0 * kPi / e->cell.volume, e->d_result.p);
+		LAUNCHED(e);
+		if (cf.polarization) {
+			if ((rc = run_polar<ORTHO>(e))) return rc;
+			k_polar_energy<<<B, 256, 0, e->stream>>>(e->d_mu.p, e->d_efs.p, e->d_efic.p, e->d_rrms.p, n, e->d_result.p + B);
+			LAUNCHED(e);
+		}
+	}
+	CK(cudaMemcpyAsync(e->h_result, e->d_result.p, sizeof(double) * res_len(B), cudaMemcpyDeviceToHost, e->stream));
+	CK(cudaGetLastError());
+	e->enqueued = true;
+	return MPMC_OK;
+}
+
+
+// ------------------------------------------------------------------------------------------------------------
+// C-ABI
+// ------------------------------------------------------------------------------------------------------------
+extern "C" {
+
+int mpmc_abi_version(void) { return MPMC_ABI_VERSION; }
+const char *mpmc_last_error(void) { return g_err.c_str(); }
+
+int mpmc_device_count(int *count) {
+	*count = 0;
+	CK(cudaGetDeviceCount(count));
+	return MPMC_OK;
+}
+
+int mpmc_create(const mpmc_config *cfg, mpmc_engine **out) {
+	*out = nullptr;
+	int rc = validate_config(cfg);
+	if (rc) return rc;
+	int ndev = 0;
+	if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+		cudaGetLastError();
+		FAIL(MPMC_ERR_CUDA, "no CUDA device: this engine has no CPU fallback");
+	}
+	if (cfg->device < 0 || cfg->device >= ndev) FAIL(MPMC_ERR_INVALID_SETTING, "device %d out of range (%d devices)", cfg->device, ndev);
+	CK(cudaSetDevice(cfg->device));
+	mpmc_engine *e = new mpmc_engine();
+	e->cfg = *cfg;
+	e->B = cfg->n_beads;
+	e->dev = cfg->device;
+	cudaDeviceProp prop;
+	CK(cudaGetDeviceProperties(&prop, cfg->device));
+	e->num_sms = prop.multiProcessorCount;
+	CK(cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking));
+	CK(cudaMallocHost(&e->h_result, sizeof(double) * res_len(e->B)));
+	CK(cudaMallocHost(&e->h_flags, sizeof(int) * e->B));
+	if ((rc = e->d_result.ensure(res_len(e->B))) || (rc = e->d_flags.ensure(e->B)) || (rc = e->d_rmin.ensure(e->B))) { mpmc_destroy(e); return rc; }
+	e->last_failed.assign(e->B, 0);
+	// shared-memory opt-ins
+	if ((rc = set_smem(k_structure_partial, sizeof(double2) * kSkSites * 3 * (kMaxKmax + 1))) ||
+	    (rc = set_smem(k_field_recip, sizeof(double2) * kFrSites * 3 * (kMaxKmax + 1))) ||
+	    (rc = set_smem(k_gs_sweep<true>, kGsSmemBytes)) || (rc = set_smem(k_gs_sweep<false>, kGsSmemBytes))) { mpmc_destroy(e); return rc; }
+	int occ = 0;
+	CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_gs_sweep<false>, kGsThreads, kGsSmemBytes));
+	e->gs_grid = std::max(1, occ) * e->num_sms;
+	if ((rc = compute_cell(e, cfg->basis))) { mpmc_destroy(e); return rc; }
+	if (cfg->capacity > 0) e->cap = cfg->capacity;
+	*out = e;
+	return MPMC_OK;
+}
+
+int mpmc_destroy(mpmc_engine *e) {
+	if (!e) return MPMC_OK;
+	cudaSetDevice(e->dev);
+	if (e->stream) cudaStreamSynchronize(e->stream);
+	e->d_posq.release(); e->d_lj.release(); e->d_alpha.release(); e->d_mass.release(); e->d_meta.release(); e->d_plist.release();
+	e->d_mobile_q.release(); e->d_frozen_q.release(); e->d_mol_start.release(); e->d_order.release(); e->d_flags.release();
+	e->d_tiles.release(); e->d_blk_frozen.release(); e->d_mol_mobile.release(); e->d_kvec.release(); e->d_partials.release();
+	e->d_sk_part.release(); e->d_S_mobile.release(); e->d_S_frozen.release(); e->d_S_all.release();
+	e->d_efs.release(); e->d_efi.release(); e->d_efic.release(); e->d_mu.release(); e->d_new_mu.release(); e->d_old_mu.release();
+	e->d_rrms.release(); e->d_rank.release(); e->d_gs_part.release(); e->d_com.release(); e->d_mol_mass.release(); e->d_chain.release();
+	e->d_rmin.release(); e->d_result.release();
+	if (e->h_stage) cudaFreeHost(e->h_stage);
+	if (e->h_partials) cudaFreeHost(e->h_partials);
+	if (e->h_result) cudaFreeHost(e->h_result);
+	if (e->h_flags) cudaFreeHost(e->h_flags);
+	for (auto &p : e->ev_pool) { cudaEventDestroy(p.first); cudaEventDestroy(p.second); }
+	if (e->stream) cudaStreamDestroy(e->stream);
+	delete e;
+	return MPMC_OK;
+}
+
+int mpmc_set_cell(mpmc_engine *e, const double basis[9]) {
+	CK(cudaSetDevice(e->dev));
+	memcpy(e->cfg.basis, basis, sizeof(double) * 9);
+	return compute_cell(e, basis);
+}
+
+int mpmc_get_cell(mpmc_engine *e, double out[22]) {
+	for (int i = 0; i < 3; i++) for (int j = 0; j < 3; j++) { out[3 * i + j] = e->cell.b[i][j]; out[9 + 3 * i + j] = e->cell.rb[i][j]; }
+	out[18] = e->cell.volume; out[19] = e->cell.cutoff; out[20] = e->cell.ewald_alpha; out[21] = e->cell.polar_alpha;
+	return MPMC_OK;
+}
+
+int mpmc_num_sites(mpmc_engine *e, int *n) { *n = e->n; return MPMC_OK; }
+
+int mpmc_upload_sites(mpmc_engine *e, int n, const double *pos, const double *charge, const double *alpha,
+                      const double *epsilon, const double *sigma, const double *mass, const int *mol, const int *frozen) {
+	CK(cudaSetDevice(e->dev));
+	if (n < 1) FAIL(MPMC_ERR_NO_MOLECULES, "no sites");
+	bool mobile = false;
+	for (int i = 0; i < n; i++) mobile = mobile || !frozen[i];
+	if (!mobile) FAIL(6000 /* missing_required_datum, System.cpp:757-760 */, "no moveable molecules found");
+	e->n = n;
+	e->h_pos.assign(pos, pos + (size_t)e->B * n * 3);
+	e->h_q.assign(charge, charge + n); e->h_alpha.assign(alpha, alpha + n); e->h_eps.assign(epsilon, epsilon + n);
+	e->h_sigma.assign(sigma, sigma + n); e->h_mass.assign(mass, mass + n);
+	e->h_mol.assign(mol, mol + n); e->h_frozen.assign(frozen, frozen + n);
+	return adopt_table(e);
+}
+
+int mpmc_update_sites(mpmc_engine *e, int bead, int first, int count, const double *pos) {
+	CK(cudaSetDevice(e->dev));
+	if (bead < 0 || bead >= e->B || first < 0 || count < 0 || first + count > e->n) FAIL(MPMC_ERR_INVALID_INPUT, "update_sites: range out of bounds");
+	memcpy(&e->h_pos[((size_t)bead * e->n + first) * 3], pos, sizeof(double) * 3 * count);
+	for (int i = first; i < first + count; i++) if (e->h_frozen[i] && e->h_q[i] != 0.0) e->frozen_sk_dirty = true;
+	return push_positions(e, bead, bead + 1, first, count);
+}
+
+int mpmc_update_sites_all_beads(mpmc_engine *e, int first, int count, const double *pos) {
+	CK(cudaSetDevice(e->dev));
+	if (first < 0 || count < 0 || first + count > e->n) FAIL(MPMC_ERR_INVALID_INPUT, "update_sites: range out of bounds");
+	for (int b = 0; b < e->B; b++) memcpy(&e->h_pos[((size_t)b * e->n + first) * 3], pos + (size_t)b * count * 3, sizeof(double) * 3 * count);
+	for (int i = first; i < first + count; i++) if (e->h_frozen[i] && e->h_q[i] != 0.0) e->frozen_sk_dirty = true;
+	return push_positions(e, 0, e->B, first, count);
+}
+
+int mpmc_insert_sites(mpmc_engine *e, int before, int count, const double *pos, const double *charge, const double *alpha,
+                      const double *epsilon, const double *sigma, const double *mass, int frozen) {
+	CK(cudaSetDevice(e->dev));
+	if (before < 0 || before > e->n || count < 1) FAIL(MPMC_ERR_INVALID_INPUT, "insert_sites: bad position");
+	const int n0 = e->n, n1 = n0 + count;
+	// the inserted sites form one new molecule; molecule indices after it shift up by one
+	const int newmol = before < n0 ? e->h_mol[before] : (n0 ? e->h_mol[n0 - 1] + 1 : 0);
+	if (before > 0 && before < n0 && e->h_mol[before - 1] == e->h_mol[before]) FAIL(MPMC_ERR_INVALID_INPUT, "insert_sites: position splits a molecule");
+	std::vector<double> np((size_t)e->B * n1 * 3);
+	for (int b = 0; b < e->B; b++) {
+		const double *src = &e->h_pos[(size_t)b * n0 * 3];
+		double *dst = &np[(size_t)b * n1 * 3];
+		memcpy(dst, src, sizeof(double) * 3 * before);
+		memcpy(dst + 3 * before, pos + (size_t)b * count * 3, sizeof(double) * 3 * count);
+		memcpy(dst + 3 * (before + count), src + 3 * before, sizeof(double) * 3 * (n0 - before));
+	}
+	e->h_pos.swap(np);
+	auto ins = [&](std::vector<double> &v, const double *src) { v.insert(v.begin() + before, src, src + count); };
+	ins(e->h_q, charge); ins(e->h_alpha, alpha); ins(e->h_eps, epsilon); ins(e->h_sigma, sigma); ins(e->h_mass, mass);
+	for (int i = before; i < n0; i++) e->h_mol[i] += 1;
+	e->h_mol.insert(e->h_mol.begin() + before, count, newmol);
+	e->h_frozen.insert(e->h_frozen.begin() + before, count, frozen ? 1 : 0);
+	e->n = n1;
+	return adopt_table(e);
+}
+
+int mpmc_remove_sites(mpmc_engine *e, int first, int count) {
+	CK(cudaSetDevice(e->dev));
+	if (first < 0 || count < 1 || first + count > e->n) FAIL(MPMC_ERR_INVALID_INPUT, "remove_sites: range out of bounds");
+	if (count == e->n) FAIL(MPMC_ERR_NO_MOLECULES, "remove_sites: would empty the system");
+	const int n0 = e->n, n1 = n0 - count;
+	std::vector<double> np((size_t)e->B * n1 * 3);
+	for (int b = 0; b < e->B; b++) {
+		const double *src = &e->h_pos[(size_t)b * n0 * 3];
+		double *dst = &np[(size_t)b * n1 * 3];
+		memcpy(dst, src, sizeof(double) * 3 * first);
+		memcpy(dst + 3 * first, src + 3 * (first + count), sizeof(double) * 3 * (n0 - first - count));
+	}
+	e->h_pos.swap(np);
+	auto del = [&](auto &v) { v.erase(v.begin() + first, v.begin() + first + count); };
+	del(e->h_q); del(e->h_alpha); del(e->h_eps); del(e->h_sigma); del(e->h_mass); del(e->h_mol); del(e->h_frozen);
+	e->n = n1;
+	return adopt_table(e);
+}
+
+int mpmc_energy_enqueue(mpmc_engine *e) {
+	CK(cudaSetDevice(e->dev));
+	return e->ortho ? enqueue_energy<true>(e) : enqueue_energy<false>(e);
+}
+
+int mpmc_energy_fetch(mpmc_engine *e, mpmc_energy_out *out) {
+	if (!e->enqueued) FAIL(MPMC_ERR_INTERNAL, "energy_fetch without energy_enqueue");
+	CK(cudaSetDevice(e->dev));
+	CK(cudaStreamSynchronize(e->stream));
+	e->enqueued = false;
+	if (e->timing) collect_timing(e);
+	const int B = e->B, ntiles = (int)e->tiles.size();
+	const mpmc_config &cf = e->cfg;
+	for (int b = 0; b < B; b++) {
+		mpmc_energy_out &o = out[b];
+		memset(&o, 0, sizeof o);
+		double rd = 0, re = 0, in = 0, cnt = 0;
+		for (int t = 0; t < ntiles; t++) {           // fixed order: tile list order
+			const PairPartial &p = e->h_partials[(size_t)b * ntiles + t];
+			rd += p.rd; re += p.es_real; in += p.es_intra; cnt += p.n_in;
+		}
+		o.rd_pair = rd; o.rd_lrc_pair = e->lrc_pair; o.rd_lrc_self = e->lrc_self;
+		o.rd_energy = rd + e->lrc_pair + e->lrc_self;
+		o.n_pairs_in_cutoff = cnt; o.n_pair_evals = e->n_pair_evals;
+		if (!cf.rd_only) {
+			o.es_real = re; o.es_self_intra = in; o.es_reciprocal = e->h_result[b]; o.es_self = e->es_self;
+			o.coulombic_energy = (re - in) + o.es_reciprocal + o.es_self;     // System.Energy.cpp:1407-1412, :1510
+			if (cf.polarization) {
+				const double *pr = e->h_result + B + 3 * b;
+				double pot = pr[0];
+				if (cf.polar_palmo) pot += pr[1];
+				o.polarization_energy = -0.5 * pot;                           // :2609-2618
+				o.dipole_rrms = pr[2] / e->n;               // :2639-2657
+				o.polarization_iterations = e->last_iterations;
+				o.iterator_failed = e->last_failed[b];
+			}
+		}
+		o.energy = o.rd_energy + o.coulombic_energy + o.polarization_energy + o.vdw_energy;   // :136
+	}
+	return MPMC_OK;
+}
+
+int mpmc_energy(mpmc_engine *e, mpmc_energy_out *out) {
+	int rc = mpmc_energy_enqueue(e);
+	if (rc) return rc;
+	return mpmc_energy_fetch(e, out);
+}
+
+int mpmc_download_dipoles(mpmc_engine *e, int bead, double *mu, double *ef_static, double *ef_induced, double *ef_induced_change) {
+	CK(cudaSetDevice(e->dev));
+	if (bead < 0 || bead >= e->B) FAIL(MPMC_ERR_INVALID_INPUT, "bead out of range");
+	if (!e->d_mu.p) FAIL(MPMC_ERR_INVALID_SETTING, "polarization has not been evaluated");
+	const size_t len = (size_t)e->n * 3, off = (size_t)bead * len;
+	CK(cudaStreamSynchronize(e->stream));
+	if (mu) CK(cudaMemcpy(mu, e->d_mu.p + off, len * sizeof(double), cudaMemcpyDeviceToHost));
+	if (ef_static) CK(cudaMemcpy(ef_static, e->d_efs.p + off, len * sizeof(double), cudaMemcpyDeviceToHost));
+	if (ef_induced) CK(cudaMemcpy(ef_induced, e->d_efi.p + off, len * sizeof(double), cudaMemcpyDeviceToHost));
+	if (ef_induced_change) CK(cudaMemcpy(ef_induced_change, e->d_efic.p + off, len * sizeof(double), cudaMemcpyDeviceToHost));
+	return MPMC_OK;
+}
+
+int mpmc_download_rank_metric(mpmc_engine *e, int bead, double *rank_metric) {
+	CK(cudaSetDevice(e->dev));
+	if (bead < 0 || bead >= e->B) FAIL(MPMC_ERR_INVALID_INPUT, "bead out of range");
+	if (!e->d_rank.p) FAIL(MPMC_ERR_INVALID_SETTING, "polarization has not been evaluated");
+	CK(cudaStreamSynchronize(e->stream));
+	CK(cudaMemcpy(rank_metric, e->d_rank.p + (size_t)bead * e->n, e->n * sizeof(double), cudaMemcpyDeviceToHost));
+	return MPMC_OK;
+}
+
+int mpmc_pi_potential(mpmc_engine *e, double *per_bead, double sums[4]) {
+	std::vector<mpmc_energy_out> out(e->B);
+	int rc = mpmc_energy(e, out.data());
+	if (rc) return rc;
+	sums[0] = sums[1] = sums[2] = sums[3] = 0;
+	for (int b = 0; b < e->B; b++) {                 // PathIntegral.cpp:791-796, bead order
+		const double v[4] = {out[b].rd_energy, out[b].coulombic_energy, out[b].polarization_energy, out[b].vdw_energy};
+		for (int q = 0; q < 4; q++) { if (per_bead) per_bead[4 * b + q] = v[q]; sums[q] += v[q]; }
+	}
+	return MPMC_OK;
+}
+
+int mpmc_pi_chain(mpmc_engine *e, int closed, double *chain_mass_len2, double *com, double *mol_mass, int *n_mol) {
+	CK(cudaSetDevice(e->dev));
+	const int nmol = (int)e->mol_start.size() - 1, B = e->B;
+	if (nmol < 1) FAIL(MPMC_ERR_NO_MOLECULES, "pi_chain: no sites uploaded");
+	int rc;
+	if ((rc = e->d_com.ensure((size_t)B * nmol * 3)) || (rc = e->d_mol_mass.ensure(nmol)) || (rc = e->d_chain.ensure(nmol))) return rc;
+	k_mol_com<<<(nmol * B + 127) / 128, 128, 0, e->stream>>>(e->d_posq.p, e->cap, e->d_mass.p, e->d_mol_start.p, nmol, B, e->d_com.p, e->d_mol_mass.p);
+	k_chain_len2<<<(nmol + 127) / 128, 128, 0, e->stream>>>(e->d_com.p, e->d_mol_mass.p, e->d_mol_mobile.p, nmol, B, closed, e->d_chain.p);
+	e->launches += 2;
+	std::vector<double> per(nmol);
+	CK(cudaMemcpyAsync(per.data(), e->d_chain.p, sizeof(double) * nmol, cudaMemcpyDeviceToHost, e->stream));
+	if (com) CK(cudaMemcpyAsync(com, e->d_com.p, sizeof(double) * (size_t)B * nmol * 3, cudaMemcpyDeviceToHost, e->stream));
+	if (mol_mass) CK(cudaMemcpyAsync(mol_mass, e->d_mol_mass.p, sizeof(double) * nmol, cudaMemcpyDeviceToHost, e->stream));
+	CK(cudaStreamSynchronize(e->stream));
+	double s = 0;
+	for (int m = 0; m < nmol; m++) s += per[m];      // PathIntegral.cpp:880-901, molecule order
+	*chain_mass_len2 = s;
+	if (n_mol) *n_mol = nmol;
+	return MPMC_OK;
+}
+
+int mpmc_set_timing(mpmc_engine *e, int on) {
+	CK(cudaSetDevice(e->dev));
+	CK(cudaStreamSynchronize(e->stream));
+	e->timing = on != 0;
+	e->ev_used = 0;
+	for (int i = 0; i < MPMC_NUM_KERNEL_CLASSES; i++) { e->t_ms[i] = 0; e->t_count[i] = 0; }
+	return MPMC_OK;
+}
+
+int mpmc_get_timing(mpmc_engine *e, double ms[MPMC_NUM_KERNEL_CLASSES], long long count[MPMC_NUM_KERNEL_CLASSES]) {
+	for (int i = 0; i < MPMC_NUM_KERNEL_CLASSES; i++) { ms[i] = e->t_ms[i]; count[i] = e->t_count[i]; }
+	return MPMC_OK;
+}
+
+void *mpmc_stream(mpmc_engine *e) { return (void *)e->stream; }
+long long mpmc_kernel_launches(mpmc_engine *e) { return e->launches; }
+
+int mpmc_probe_fp64_peak(int device, double *tflops, double *sm_clock_mhz_guess) {
+	CK(cudaSetDevice(device));
+	cudaDeviceProp prop;
+	CK(cudaGetDeviceProperties(&prop, device));
+	const int blocks = prop.multiProcessorCount * 8, threads = 256, iters = 1 << 14;
+	double *d = nullptr;
+	CK(cudaMalloc(&d, sizeof(double) * blocks * threads));
+	cudaEvent_t a, b;
+	CK(cudaEventCreate(&a)); CK(cudaEventCreate(&b));
+	k_fp64_probe<<<blocks, threads>>>(d, iters);   // warm-up
+	CK(cudaDeviceSynchronize());
+	float best = 1e30f;
+	for (int rep = 0; rep < 5; rep++) {
+		CK(cudaEventRecord(a));
+		k_fp64_probe<<<blocks, threads>>>(d, iters);
+		CK(cudaEventRecord(b));
+		CK(cudaEventSynchronize(b));
+		float ms = 0;
+		CK(cudaEventElapsedTime(&ms, a, b));
+		best = std::min(best, ms);
+	}
+	const double flops = 2.0 * 8.0 * iters * (double)blocks * threads;
+	*tflops = flops / (best * 1e-3) / 1e12;
+	if (sm_clock_mhz_guess) *sm_clock_mhz_guess = *tflops * 1e12 / (2.0 * 64.0 * prop.multiProcessorCount) / 1e6;   // if 64 FP64 lanes per SM
+	cudaFree(d); cudaEventDestroy(a); cudaEventDestroy(b);
+	return MPMC_OK;
+}
+
+} // extern "C"
