@@ -167,6 +167,8 @@ enum {
 	MPMC_NUM_KERNEL_CLASSES
 };
 int mpmc_set_timing(mpmc_engine *e, int on);
+/* developer hook: SM-clock stamps of the Gauss-Seidel pipeline (solver and one updater CTA), see tools/gs_profile.py */
+int mpmc_debug_gs_profile(mpmc_engine *e, int enable, long long *out, int max_blocks, int *nblk);
 int mpmc_get_timing(mpmc_engine *e, double ms[MPMC_NUM_KERNEL_CLASSES], long long count[MPMC_NUM_KERNEL_CLASSES]);
 void     *mpmc_stream(mpmc_engine *e);
 long long mpmc_kernel_launches(mpmc_engine *e);

@@ -95,15 +95,30 @@ __device__ __forceinline__ void tensor_contract(const CellDev &c, const PolarDev
                                                 double mx, double my, double mz, double &ax, double &ay, double &az) {
 	double dx, dy, dz;
 	min_image<ORTHO>(c, __dsub_rn(xi, xj), __dsub_rn(yi, yj), __dsub_rn(zi, zj), dx, dy, dz);
-	double r2 = norm2_nofma(dx, dy, dz);
-	double r = sqrt(r2);
-	double ir3, ir5;
-	if (r == 0.0) { ir3 = ir5 = kMaxValue; }
-	else { double ir = 1.0 / r; double ir2 = ir * ir; ir3 = ir2 * ir; ir5 = ir3 * ir2; }
-	double damp1, damp2;
-	thole_damping(p, r, r2, excluded, alpha_prod, damp1, damp2);
-	double a = damp1 * ir3;
-	double b = 3.0 * damp2 * ir5 * (dx * mx + dy * my + dz * mz);
+	double a, b;
+	if (p.damp_type == 2) {
+		// exponential damping, the `cuda on` configuration: one rsqrt gives r and every inverse power.  At r = 0 the reference
+		// multiplies MAXVALUE by damping factors that are exactly 0 (:2704-2705, :2733-2734): the pair contributes nothing.
+		const double r2 = fma(dz, dz, fma(dy, dy, dx * dx));
+		if (r2 == 0.0) return;
+		const double ir = rsqrt(r2), r = r2 * ir, ir2 = ir * ir, ir3 = ir2 * ir;
+		const double lr = p.damp * r;
+		const double e = exp(-lr);
+		const double damp1 = fma(-e, fma(0.5 * lr, lr, lr) + 1.0, 1.0);            // 1 - e (l^2 r^2 / 2 + l r + 1)
+		const double damp2 = fma(-e, lr * lr * lr * (1.0 / 6.0), damp1);           // damp1 - e l^3 r^3 / 6
+		a = damp1 * ir3;
+		b = 3.0 * damp2 * ir3 * ir2 * (dx * mx + dy * my + dz * mz);
+	} else {
+		double r2 = norm2_nofma(dx, dy, dz);
+		double r = sqrt(r2);
+		double ir3, ir5;
+		if (r == 0.0) { ir3 = ir5 = kMaxValue; }
+		else { double ir = 1.0 / r; double ir2 = ir * ir; ir3 = ir2 * ir; ir5 = ir3 * ir2; }
+		double damp1, damp2;
+		thole_damping(p, r, r2, excluded, alpha_prod, damp1, damp2);
+		a = damp1 * ir3;
+		b = 3.0 * damp2 * ir5 * (dx * mx + dy * my + dz * mz);
+	}
 	ax += a * mx - b * dx;
 	ay += a * my - b * dy;
 	az += a * mz - b * dz;

@@ -19,6 +19,7 @@
 #include <string>
 #include <vector>
 
+#include "kernels_gs.cuh"
 #include "kernels_pair.cuh"
 #include "kernels_polar.cuh"
 #include "kernels_recip.cuh"
@@ -98,7 +99,11 @@ struct mpmc_engine {
 	DevBuf<KVec> d_kvec;
 	DevBuf<PairPartial> d_partials;
 	DevBuf<double2> d_sk_part, d_S_mobile, d_S_frozen, d_S_all;
-	DevBuf<double> d_efs, d_efi, d_efic, d_mu, d_new_mu, d_old_mu, d_rrms, d_rank, d_gs_part, d_com, d_mol_mass, d_chain;
+	DevBuf<double> d_efs, d_efi, d_efic, d_mu, d_new_mu, d_old_mu, d_rrms, d_rank, d_acc, d_dmu, d_tri, d_com, d_mol_mass, d_chain;
+	DevBuf<int> d_gsctl;
+	DevBuf<long long> d_gsprof;
+	bool gs_prof_enabled = false;
+	int gs_prof_nblk = 0;
 	DevBuf<unsigned long long> d_rmin;
 	DevBuf<double> d_result;
 	// pinned staging
@@ -415,7 +420,7 @@ static int run_polar(mpmc_engine *e) {
 	if ((rc = e->d_efs.ensure(len)) || (rc = e->d_efi.ensure(len)) || (rc = e->d_efic.ensure(len)) || (rc = e->d_mu.ensure(len)) ||
 	    (rc = e->d_new_mu.ensure(len)) || (rc = e->d_old_mu.ensure(len)) || (rc = e->d_rrms.ensure((size_t)B * n)) ||
 	    (rc = e->d_rank.ensure((size_t)B * n)) || (rc = e->d_order.ensure(std::max(np, 1))) ||
-	    (rc = e->d_gs_part.ensure((size_t)e->gs_grid * kGsB * 3))) return rc;
+	    (rc = e->d_order.ensure(1))) return rc;
 	const dim3 ogrid((n + kOrdI - 1) / kOrdI, B);
 	const int nk = (int)e->kvec.size(), kmax = cf.ewald_kmax;
 	// thole_field(): static field (System.Energy.cpp:3271-3296)
@@ -467,7 +472,8 @@ static int run_polar(mpmc_engine *e) {
 	const bool need_old = cf.polar_rrms || cf.polar_precision > 0 || cf.polar_sor || cf.polar_esor;
 	const bool want_check = cf.polar_rrms || cf.polar_precision > 0;
 	int it = 0;
-	bool keep = true;
+	bool keep = true, acc_stale = false;
+	const int *gs_order = e->d_plist.p;
 	while (keep) {
 		it++;
 		if (it >= 128 && cf.polar_precision > 0) {   // MAX_ITERATION_COUNT (constants.h:52), System.Energy.cpp:3483-3494
@@ -481,26 +487,58 @@ static int run_polar(mpmc_engine *e) {
 		if (need_old) CK(cudaMemcpyAsync(e->d_old_mu.p, e->d_mu.p, len * sizeof(double), cudaMemcpyDeviceToDevice, e->stream));
 		if (!pd.gs) {
 { Timed _t(e, MPMC_K_DIPOLE_SWEEP);
-			k_dipole_sweep<ORTHO, false><<<ogrid, kOrdThreads, 0, e->stream>>>(e->d_posq.p, e->d_alpha.p, e->d_meta.p, e->d_plist.p, np, n, e->cap, e->cell, pd,
+			k_dipole_sweep<ORTHO, SWEEP_JACOBI><<<ogrid, kOrdThreads, 0, e->stream>>>(e->d_posq.p, e->d_alpha.p, e->d_meta.p, e->d_plist.p, np, n, e->cap, e->cell, pd,
 			                                                                  e->d_mu.p, e->d_efs.p, e->d_efi.p, e->d_new_mu.p, e->d_efic.p);
 			LAUNCHED(e);
  }		} else {
-			const int *order = e->d_plist.p;                        // first sweep: list order (ranked_array = identity, :3463)
-			if (ranked && it >= 2) {
-				if (it == 2) { k_rank_order_plist<<<(np + 255) / 256, 256, 0, e->stream>>>(e->d_rank.p, e->d_plist.p, np, e->d_order.p); LAUNCHED(e); }
-				order = e->d_order.p;
+			// Gauss-Seidel pipeline (kernels_gs.cuh).  First sweep in list order (ranked_array = identity, :3463); from the second
+			// sweep on in rank order when polar_gs_ranked (update_ranking after the first pass, :3522-3523).
+			const int nblk = (np + kGsB - 1) / kGsB, nchunks = (np + kGsRows - 1) / kGsRows;
+			if ((rc = e->d_acc.ensure(len)) || (rc = e->d_dmu.ensure((size_t)np * 3)) || (rc = e->d_tri.ensure((size_t)nblk * 6 * kGsPairs)) ||
+			    (rc = e->d_gsctl.ensure(sizeof(GsCtl) / sizeof(int) + nchunks))) return rc;
+			if (it == 1 || acc_stale) {
+				Timed _t(e, MPMC_K_DIPOLE_SWEEP);
+				k_dipole_sweep<ORTHO, SWEEP_ACC><<<ogrid, kOrdThreads, 0, e->stream>>>(e->d_posq.p, e->d_alpha.p, e->d_meta.p, e->d_plist.p, np, n, e->cap, e->cell, pd,
+				                                                                e->d_mu.p, e->d_efs.p, e->d_efi.p, e->d_acc.p, e->d_efic.p);
+				LAUNCHED(e);
+				acc_stale = false;
 			}
+			if (it == 1 || (ranked && it == 2)) {
+				gs_order = e->d_plist.p;
+				if (ranked && it == 2) {
+					k_rank_order_plist<<<(np + 255) / 256, 256, 0, e->stream>>>(e->d_rank.p, e->d_plist.p, np, e->d_order.p);
+					LAUNCHED(e);
+					gs_order = e->d_order.p;
+				}
+				Timed _t(e, MPMC_K_GS_SWEEP);
+				k_gs_tensors<ORTHO><<<nblk, kGsThreads, 0, e->stream>>>(e->d_posq.p, e->d_alpha.p, e->d_meta.p, gs_order, np, e->cell, pd, e->d_tri.p);
+				LAUNCHED(e);
+			}
+			int ns = 1;
+			if (!need_old && !want_check && cf.polar_precision == 0.0) ns = (ranked && it == 1) ? 1 : (cf.polar_max_iter - it + 1);
+			CK(cudaMemsetAsync(e->d_gsctl.p, 0, sizeof(int) * (sizeof(GsCtl) / sizeof(int) + nchunks), e->stream));
 			const double4 *pq = e->d_posq.p;
-			const double *al = e->d_alpha.p, *efs = e->d_efs.p;
+			const double *al = e->d_alpha.p, *efs = e->d_efs.p, *tri = e->d_tri.p;
 			const int *meta = e->d_meta.p;
-			double *mu = e->d_mu.p, *efi = e->d_efi.p, *nmu = e->d_new_mu.p, *part = e->d_gs_part.p;
+			double *mu = e->d_mu.p, *efi = e->d_efi.p, *nmu = e->d_new_mu.p, *acc = e->d_acc.p, *dmu = e->d_dmu.p;
+			GsCtl *ctl = (GsCtl *)e->d_gsctl.p;
 			int npv = np;
 			CellDev cell = e->cell;
-			void *args[] = {&pq, &al, &meta, &order, &npv, &cell, &pd, &mu, &efs, &efi, &nmu, &part};
-{ Timed _t(e, MPMC_K_GS_SWEEP);
-			CK(cudaLaunchCooperativeKernel((void *)k_gs_sweep<ORTHO>, dim3(e->gs_grid), dim3(kGsThreads), args, kGsSmemBytes, e->stream));
-			LAUNCHED(e);
- }		}
+			long long *prof = nullptr;
+			if (e->gs_prof_enabled) {
+				if ((rc = e->d_gsprof.ensure((size_t)nblk * 16))) return rc;
+				CK(cudaMemsetAsync(e->d_gsprof.p, 0, sizeof(long long) * nblk * 16, e->stream));
+				prof = e->d_gsprof.p;
+				e->gs_prof_nblk = nblk;
+			}
+			void *args[] = {&pq, &al, &meta, &gs_order, &npv, &cell, &pd, &efs, &mu, &efi, &nmu, &acc, &dmu, &tri, &ctl, &ns, &prof};
+			{
+				Timed _t(e, MPMC_K_GS_SWEEP);
+				CK(cudaLaunchCooperativeKernel((void *)k_gs_pipeline<ORTHO>, dim3(e->gs_grid), dim3(kGsThreads), args, kGsSmemBytes, e->stream));
+				LAUNCHED(e);
+			}
+			it += ns - 1;
+		}
 		if (want_check) {
 			CK(cudaMemsetAsync(e->d_flags.p, 0, sizeof(int) * B, e->stream));
 			k_dipole_check<<<(B * n + eb - 1) / eb, eb, 0, e->stream>>>(e->d_new_mu.p, e->d_old_mu.p, n, B, 1, pd.allowed_sqerr, e->d_rrms.p, e->d_flags.p);
@@ -514,14 +552,24 @@ static int run_polar(mpmc_engine *e) {
 			for (int b = 0; b < B; b++) keep = keep || e->h_flags[b];        // bead systems iterate in lock-step until all have converged
 		}
 		if (cf.polar_palmo && !keep) {                                       // :3518-3519
-{ Timed _t(e, MPMC_K_PALMO);
-			k_dipole_sweep<ORTHO, true><<<ogrid, kOrdThreads, 0, e->stream>>>(e->d_posq.p, e->d_alpha.p, e->d_meta.p, e->d_plist.p, np, n, e->cap, e->cell, pd,
-			                                                                 e->d_mu.p, e->d_efs.p, e->d_efi.p, e->d_new_mu.p, e->d_efic.p);
+			Timed _t(e, MPMC_K_PALMO);
+			if (pd.gs) {   // the running contraction already is sum_j T_ij mu_j for the polarizable rows
+				k_gs_palmo<<<(np * 3 + eb - 1) / eb, eb, 0, e->stream>>>(e->d_plist.p, np, e->d_efi.p, e->d_acc.p, e->d_efic.p);
+				k_dipole_sweep<ORTHO, SWEEP_PALMO_NONPOLAR><<<ogrid, kOrdThreads, 0, e->stream>>>(e->d_posq.p, e->d_alpha.p, e->d_meta.p, e->d_plist.p, np, n, e->cap,
+				                                                                           e->cell, pd, e->d_mu.p, e->d_efs.p, e->d_efi.p, e->d_new_mu.p, e->d_efic.p);
+				e->launches += 2;
+			} else {
+				k_dipole_sweep<ORTHO, SWEEP_PALMO><<<ogrid, kOrdThreads, 0, e->stream>>>(e->d_posq.p, e->d_alpha.p, e->d_meta.p, e->d_plist.p, np, n, e->cap, e->cell, pd,
+				                                                                  e->d_mu.p, e->d_efs.p, e->d_efi.p, e->d_new_mu.p, e->d_efic.p);
+				LAUNCHED(e);
+			}
+		}
+		if (!pd.gs || cf.polar_sor || cf.polar_esor) {                       // :3526-3536 (plain GS already has mu == new_mu)
+			k_mu_update<<<(unsigned)((len + eb - 1) / eb), eb, 0, e->stream>>>(e->d_new_mu.p, e->d_old_mu.p, len, cf.polar_sor, cf.polar_esor, cf.polar_gamma,
+			                                                                  std::exp(-cf.polar_gamma * it), e->d_mu.p);
 			LAUNCHED(e);
- }		}
-		k_mu_update<<<(unsigned)((len + eb - 1) / eb), eb, 0, e->stream>>>(e->d_new_mu.p, e->d_old_mu.p, len, cf.polar_sor, cf.polar_esor, cf.polar_gamma,
-		                                                                  std::exp(-cf.polar_gamma * it), e->d_mu.p);
-		LAUNCHED(e);
+			if (pd.gs) acc_stale = true;                                     // relaxation moved mu: the running contraction must be rebuilt
+		}
 	}
 	e->last_iterations = it;
 	CK(cudaGetLastError());
@@ -617,9 +665,9 @@ int mpmc_create(const mpmc_config *cfg, mpmc_engine **out) {
 	// shared-memory opt-ins
 	if ((rc = set_smem(k_structure_partial, sizeof(double2) * kSkSites * 3 * (kMaxKmax + 1))) ||
 	    (rc = set_smem(k_field_recip, sizeof(double2) * kFrSites * 3 * (kMaxKmax + 1))) ||
-	    (rc = set_smem(k_gs_sweep<true>, kGsSmemBytes)) || (rc = set_smem(k_gs_sweep<false>, kGsSmemBytes))) { mpmc_destroy(e); return rc; }
+	    (rc = set_smem(k_gs_pipeline<true>, kGsSmemBytes)) || (rc = set_smem(k_gs_pipeline<false>, kGsSmemBytes))) { mpmc_destroy(e); return rc; }
 	int occ = 0;
-	CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_gs_sweep<false>, kGsThreads, kGsSmemBytes));
+	CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_gs_pipeline<false>, kGsThreads, kGsSmemBytes));
 	e->gs_grid = std::max(1, occ) * e->num_sms;
 	if ((rc = compute_cell(e, cfg->basis))) { mpmc_destroy(e); return rc; }
 	if (cfg->capacity > 0) e->cap = cfg->capacity;
@@ -636,7 +684,7 @@ int mpmc_destroy(mpmc_engine *e) {
 	e->d_tiles.release(); e->d_blk_frozen.release(); e->d_mol_mobile.release(); e->d_kvec.release(); e->d_partials.release();
 	e->d_sk_part.release(); e->d_S_mobile.release(); e->d_S_frozen.release(); e->d_S_all.release();
 	e->d_efs.release(); e->d_efi.release(); e->d_efic.release(); e->d_mu.release(); e->d_new_mu.release(); e->d_old_mu.release();
-	e->d_rrms.release(); e->d_rank.release(); e->d_gs_part.release(); e->d_com.release(); e->d_mol_mass.release(); e->d_chain.release();
+	e->d_rrms.release(); e->d_rank.release(); e->d_acc.release(); e->d_dmu.release(); e->d_tri.release(); e->d_gsctl.release(); e->d_com.release(); e->d_mol_mass.release(); e->d_chain.release();
 	e->d_rmin.release(); e->d_result.release();
 	if (e->h_stage) cudaFreeHost(e->h_stage);
 	if (e->h_partials) cudaFreeHost(e->h_partials);
@@ -838,6 +886,20 @@ int mpmc_pi_chain(mpmc_engine *e, int closed, double *chain_mass_len2, double *c
 	for (int m = 0; m < nmol; m++) s += per[m];      // PathIntegral.cpp:880-901, molecule order
 	*chain_mass_len2 = s;
 	if (n_mol) *n_mol = nmol;
+	return MPMC_OK;
+}
+
+// developer hook (not part of the drop-in surface): cycle stamps of the Gauss-Seidel pipeline's last launch
+int mpmc_debug_gs_profile(mpmc_engine *e, int enable, long long *out, int max_blocks, int *nblk) {
+	CK(cudaSetDevice(e->dev));
+	e->gs_prof_enabled = enable != 0;
+	if (out && e->d_gsprof.p && e->gs_prof_nblk) {
+		CK(cudaStreamSynchronize(e->stream));
+		const int nb = std::min(max_blocks, e->gs_prof_nblk);
+		CK(cudaMemcpy(out, e->d_gsprof.p, sizeof(long long) * 8 * nb, cudaMemcpyDeviceToHost));
+		CK(cudaMemcpy(out + (size_t)8 * max_blocks, e->d_gsprof.p + (size_t)8 * e->gs_prof_nblk, sizeof(long long) * 8 * nb, cudaMemcpyDeviceToHost));
+		if (nblk) *nblk = nb;
+	}
 	return MPMC_OK;
 }
 

@@ -22,11 +22,14 @@ __global__ void k_dipole_init(const double *__restrict__ alpha, const double *__
 }
 
 // One full contraction acc_i = sum_{j != i} T_ij mu_j over the polarizable sites j (mu_j == 0 exactly elsewhere).
-//   PALMO = false: contract_dipoles() in Jacobi form (:3564-3598): efi = -acc, new_mu = alpha (E_s + efi); sites with
+//   SWEEP_JACOBI : contract_dipoles() in Jacobi form (:3564-3598): efi = -acc, new_mu = alpha (E_s + efi); sites with
 //                  alpha == 0 get efi = new_mu = 0.  mu is NOT touched (the caller relaxes it afterwards, :3526-3536).
-//   PALMO = true : palmo_contraction() (:3602-3627): efic = -efi - acc, for every site.
+//   SWEEP_PALMO  : palmo_contraction() (:3602-3627): efic = -efi - acc, for every site.
+//   SWEEP_PALMO_NONPOLAR : the same, but only for the sites with alpha == 0 (the Gauss-Seidel path already holds acc for the rest).
+//   SWEEP_ACC    : acc_out = acc for the polarizable sites (the running contraction the Gauss-Seidel pipeline keeps up to date).
 // Layout as the other ordered sweeps: CTA = 32 sites x 8 j-lanes.
-template <bool ORTHO, bool PALMO>
+enum { SWEEP_JACOBI = 0, SWEEP_PALMO = 1, SWEEP_PALMO_NONPOLAR = 2, SWEEP_ACC = 3 };
+template <bool ORTHO, int MODE>
 __global__ void __launch_bounds__(kOrdThreads)
 k_dipole_sweep(const double4 *__restrict__ posq, const double *__restrict__ alpha, const int *__restrict__ meta,
                const int *__restrict__ plist, int np, int n, int stride, CellDev c, PolarDev p,
@@ -45,7 +48,7 @@ k_dipole_sweep(const double4 *__restrict__ posq, const double *__restrict__ alph
 	double4 pi = make_double4(0, 0, 0, 0);
 	double ai = 0; int mi = 0;
 	if (i < n) { pi = pq[i]; ai = alpha[i]; mi = meta[i]; }
-	const bool active = (i < n) && (PALMO || ai != 0.0);
+	const bool active = (i < n) && (MODE == SWEEP_PALMO || (MODE == SWEEP_PALMO_NONPOLAR ? ai == 0.0 : ai != 0.0));
 	double ax = 0, ay = 0, az = 0;
 	for (int j0 = 0; j0 < np; j0 += kOrdTileJ) {
 		__syncthreads();
@@ -68,8 +71,10 @@ k_dipole_sweep(const double4 *__restrict__ posq, const double *__restrict__ alph
 	ax = jlane_sum(ax); ay = jlane_sum(ay); az = jlane_sum(az);
 	if (jl == 0 && i < n) {
 		const size_t o = ((size_t)bead * n + i) * 3;
-		if (PALMO) {
-			efic[o] = -efi[o] - ax; efic[o + 1] = -efi[o + 1] - ay; efic[o + 2] = -efi[o + 2] - az;
+		if (MODE == SWEEP_PALMO || MODE == SWEEP_PALMO_NONPOLAR) {
+			if (active) { efic[o] = -efi[o] - ax; efic[o + 1] = -efi[o + 1] - ay; efic[o + 2] = -efi[o + 2] - az; }
+		} else if (MODE == SWEEP_ACC) {
+			if (active) { new_mu[o] = ax; new_mu[o + 1] = ay; new_mu[o + 2] = az; }     // new_mu doubles as the acc output pointer
 		} else if (ai != 0.0) {
 			efi[o] = -ax; efi[o + 1] = -ay; efi[o + 2] = -az;
 			new_mu[o] = ai * (efs[o] - ax); new_mu[o + 1] = ai * (efs[o + 1] - ay); new_mu[o + 2] = ai * (efs[o + 2] - az);
@@ -162,165 +167,6 @@ __global__ void k_rank_order_plist(const double *__restrict__ rank, const int *_
 		}
 	}
 	if (t < np) order[pos] = i;
-}
-
-// ---------------------------------------------------------------------------------------------------------
-// Gauss-Seidel sweep, mathematically sequential in `order` (contract_dipoles with polar_gs / polar_gs_ranked,
-// :3570-3595: mu_i is overwritten as soon as it is computed, so site i sees the NEW dipoles of every site swept
-// before it and the OLD dipoles of the rest).  Blocked: kGsB sites at a time.
-//   phase A (all CTAs): ext_i = sum over every j outside the block of T_ij mu_j(current)          -> grid.sync
-//   phase B (CTA 0)   : in-block tensors in shared memory, acc_i = ext_i + sum_{m in block} T_im mu_m(old);
-//                       warp 0 then walks the block in order: mu_k = alpha_k (E_s,k - acc_k), and every lane adds
-//                       T_mk (mu_k_new - mu_k_old) to the rows m > k it owns                          -> grid.sync
-// One cooperative launch per sweep; grid = every CTA the device can hold at once.
-// ---------------------------------------------------------------------------------------------------------
-constexpr int kGsB = 64, kGsThreads = 256, kGsJL = kGsThreads / kGsB;
-constexpr int kGsPairs = kGsB * (kGsB - 1) / 2;
-__host__ __device__ constexpr int gs_tri(int a, int b) { return a * (2 * kGsB - a - 1) / 2 + (b - a - 1); }   // a < b
-constexpr size_t kGsSmemBytes = sizeof(double) * (6 * kGsPairs + kGsJL * kGsB * 3 + kGsB * 16) + sizeof(int) * kGsB * 2;
-
-template <bool ORTHO>
-__global__ void __launch_bounds__(kGsThreads)
-k_gs_sweep(const double4 *__restrict__ pq, const double *__restrict__ alpha, const int *__restrict__ meta,
-           const int *__restrict__ order, int np, CellDev c, PolarDev p,
-           double *mu, const double *__restrict__ efs, double *efi, double *new_mu, double *part) {
-	cg::grid_group grid = cg::this_grid();
-	extern __shared__ double s_raw[];
-	double *s_tri  = s_raw;                                  // [6][kGsPairs]
-	double *s_acc  = s_tri + 6 * kGsPairs;                   // [kGsJL][kGsB][3]   (phase A lane partials / phase B scratch)
-	double *s_site = s_acc + kGsJL * kGsB * 3;               // [16][kGsB]: x y z q alpha mu_old(3) efs(3) acc(3) new(2 spare)
-	int    *s_idx  = (int *)(s_site + 16 * kGsB);            // [kGsB] site index, [kGsB] meta
-	int    *s_met  = s_idx + kGsB;
-	const int tid = threadIdx.x, il = tid % kGsB, jl = tid / kGsB;
-	const int G = gridDim.x, cta = blockIdx.x;
-	const int nblk = (np + kGsB - 1) / kGsB;
-
-	for (int blk = 0; blk < nblk; blk++) {
-		const int base = blk * kGsB, cnt = min(kGsB, np - base);
-		// ---- phase A ----
-		if (tid < cnt) {
-			const int s = order[base + tid];
-			const double4 v = pq[s];
-			s_idx[tid] = s; s_met[tid] = meta[s];
-			s_site[0 * kGsB + tid] = v.x; s_site[1 * kGsB + tid] = v.y; s_site[2 * kGsB + tid] = v.z; s_site[3 * kGsB + tid] = v.w;
-			s_site[4 * kGsB + tid] = alpha[s];
-		}
-		__syncthreads();
-		double ax = 0, ay = 0, az = 0;
-		if (il < cnt) {
-			const double xi = s_site[il], yi = s_site[kGsB + il], zi = s_site[2 * kGsB + il], qi = s_site[3 * kGsB + il], ai = s_site[4 * kGsB + il];
-			const int mi = s_met[il];
-			if (ai != 0.0)
-				for (int pos = cta * kGsJL + jl; pos < np; pos += G * kGsJL) {
-					if (pos >= base && pos < base + cnt) continue;
-					const int j = order[pos];                           // same j for the whole warp: broadcast loads
-					const double4 pj = pq[j];
-					const bool excl = (meta_mol(mi) == meta_mol(meta[j])) || qi == 0.0 || pj.w == 0.0;
-					tensor_contract<ORTHO>(c, p, xi, yi, zi, pj.x, pj.y, pj.z, excl, ai * alpha[j], __ldcg(mu + 3 * j), __ldcg(mu + 3 * j + 1), __ldcg(mu + 3 * j + 2), ax, ay, az);
-				}
-		}
-		s_acc[(jl * kGsB + il) * 3 + 0] = ax; s_acc[(jl * kGsB + il) * 3 + 1] = ay; s_acc[(jl * kGsB + il) * 3 + 2] = az;
-		__syncthreads();
-		if (tid < kGsB * 3) {
-			double v = 0;
-			for (int q = 0; q < kGsJL; q++) v += s_acc[q * kGsB * 3 + tid];
-			part[(size_t)cta * kGsB * 3 + tid] = v;
-		}
-		__threadfence();
-		grid.sync();
-		// ---- phase B ----
-		if (cta == 0) {
-			if (tid < kGsB * 3) {                                   // ext = sum over CTAs in CTA order
-				double v = 0;
-				for (int q = 0; q < G; q++) v += __ldcg(part + (size_t)q * kGsB * 3 + tid);
-				const int m = tid / 3, comp = tid % 3;
-				s_site[(11 + comp) * kGsB + m] = v;                  // acc rows 11..13
-				if (m < cnt) {
-					const int s = s_idx[m];
-					s_site[(5 + comp) * kGsB + m] = __ldcg(mu + 3 * s + comp);   // mu_old rows 5..7
-					s_site[(8 + comp) * kGsB + m] = efs[3 * s + comp];    // E_static rows 8..10
-				}
-			}
-			for (int q = tid; q < cnt * cnt; q += kGsThreads) {       // in-block tensors, a < b
-				const int a = q / cnt, b = q % cnt;
-				if (a >= b) continue;
-				double dx, dy, dz;
-				min_image<ORTHO>(c, __dsub_rn(s_site[a], s_site[b]), __dsub_rn(s_site[kGsB + a], s_site[kGsB + b]),
-				                 __dsub_rn(s_site[2 * kGsB + a], s_site[2 * kGsB + b]), dx, dy, dz);
-				const double r2 = norm2_nofma(dx, dy, dz), r = sqrt(r2);
-				double ir3, ir5;
-				if (r == 0.0) { ir3 = ir5 = kMaxValue; } else { const double ir = 1.0 / r, ir2 = ir * ir; ir3 = ir2 * ir; ir5 = ir3 * ir2; }
-				const bool excl = (meta_mol(s_met[a]) == meta_mol(s_met[b])) || s_site[3 * kGsB + a] == 0.0 || s_site[3 * kGsB + b] == 0.0;
-				double d1, d2;
-				thole_damping(p, r, r2, excl, s_site[4 * kGsB + a] * s_site[4 * kGsB + b], d1, d2);
-				const double ta = d1 * ir3, tb = 3.0 * d2 * ir5;
-				const int t = gs_tri(a, b);
-				s_tri[0 * kGsPairs + t] = ta - tb * dx * dx; s_tri[1 * kGsPairs + t] = ta - tb * dy * dy; s_tri[2 * kGsPairs + t] = ta - tb * dz * dz;
-				s_tri[3 * kGsPairs + t] = -tb * dx * dy;     s_tri[4 * kGsPairs + t] = -tb * dx * dz;     s_tri[5 * kGsPairs + t] = -tb * dy * dz;
-			}
-			__syncthreads();
-			if (tid < kGsB * 3) {                                   // acc_m += sum_{m' != m in block} T_mm' mu_m'(old)
-				const int m = tid / 3, comp = tid % 3;
-				if (m < cnt) {
-					double v = s_site[(11 + comp) * kGsB + m];
-					for (int o = 0; o < cnt; o++) {
-						if (o == m) continue;
-						const int t = m < o ? gs_tri(m, o) : gs_tri(o, m);
-						// row `comp` of the symmetric 3x3: (xx xy xz / xy yy yz / xz yz zz)
-						const double t0 = s_tri[(comp == 0 ? 0 : comp == 1 ? 3 : 4) * kGsPairs + t];
-						const double t1 = s_tri[(comp == 0 ? 3 : comp == 1 ? 1 : 5) * kGsPairs + t];
-						const double t2 = s_tri[(comp == 0 ? 4 : comp == 1 ? 5 : 2) * kGsPairs + t];
-						v += t0 * s_site[5 * kGsB + o] + t1 * s_site[6 * kGsB + o] + t2 * s_site[7 * kGsB + o];
-					}
-					s_acc[m * 3 + comp] = v;
-				}
-			}
-			__syncthreads();
-			if (tid < 32) {                                         // sequential walk by one warp; lane owns rows lane, lane+32
-				const int lane = tid;
-				double acc[2][3], res_mu[2][3], res_ef[2][3];
-				for (int h = 0; h < 2; h++) for (int q = 0; q < 3; q++) { acc[h][q] = s_acc[(lane + 32 * h) * 3 + q]; res_mu[h][q] = 0; res_ef[h][q] = 0; }
-				for (int k = 0; k < cnt; k++) {
-					const int owner = k & 31, h = k >> 5;
-					double dmx = 0, dmy = 0, dmz = 0;
-					if (lane == owner) {
-						const double ak = s_site[4 * kGsB + k];
-						const double c0 = h ? acc[1][0] : acc[0][0], c1 = h ? acc[1][1] : acc[0][1], c2 = h ? acc[1][2] : acc[0][2];
-						double nx = 0, ny = 0, nz = 0, ex = 0, ey = 0, ez = 0;
-						if (ak != 0.0) {
-							ex = -c0; ey = -c1; ez = -c2;
-							nx = ak * (s_site[8 * kGsB + k] + ex); ny = ak * (s_site[9 * kGsB + k] + ey); nz = ak * (s_site[10 * kGsB + k] + ez);
-						}
-						if (h == 0) { res_mu[0][0] = nx; res_mu[0][1] = ny; res_mu[0][2] = nz; res_ef[0][0] = ex; res_ef[0][1] = ey; res_ef[0][2] = ez; }
-						else        { res_mu[1][0] = nx; res_mu[1][1] = ny; res_mu[1][2] = nz; res_ef[1][0] = ex; res_ef[1][1] = ey; res_ef[1][2] = ez; }
-						dmx = nx - s_site[5 * kGsB + k]; dmy = ny - s_site[6 * kGsB + k]; dmz = nz - s_site[7 * kGsB + k];
-					}
-					dmx = __shfl_sync(0xffffffffu, dmx, owner); dmy = __shfl_sync(0xffffffffu, dmy, owner); dmz = __shfl_sync(0xffffffffu, dmz, owner);
-#pragma unroll
-					for (int hh = 0; hh < 2; hh++) {
-						const int m = lane + 32 * hh;
-						if (m > k && m < cnt) {
-							const int t = gs_tri(k, m);
-							const double xx = s_tri[t], yy = s_tri[kGsPairs + t], zz = s_tri[2 * kGsPairs + t];
-							const double xy = s_tri[3 * kGsPairs + t], xz = s_tri[4 * kGsPairs + t], yz = s_tri[5 * kGsPairs + t];
-							acc[hh][0] += xx * dmx + xy * dmy + xz * dmz;
-							acc[hh][1] += xy * dmx + yy * dmy + yz * dmz;
-							acc[hh][2] += xz * dmx + yz * dmy + zz * dmz;
-						}
-					}
-				}
-				for (int h = 0; h < 2; h++) {
-					const int m = lane + 32 * h;
-					if (m < cnt) {
-						const int s = s_idx[m];
-						for (int q = 0; q < 3; q++) { mu[3 * s + q] = res_mu[h][q]; new_mu[3 * s + q] = res_mu[h][q]; efi[3 * s + q] = res_ef[h][q]; }
-					}
-				}
-			}
-		}
-		__threadfence();
-		grid.sync();
-	}
 }
 
 // bead-chain bookkeeping ------------------------------------------------------------------------------------

@@ -47,7 +47,7 @@ class MpmcError(RuntimeError):
 EXPORTS = ["mpmc_abi_version", "mpmc_last_error", "mpmc_device_count", "mpmc_create", "mpmc_destroy", "mpmc_set_cell", "mpmc_get_cell",
            "mpmc_upload_sites", "mpmc_update_sites", "mpmc_update_sites_all_beads", "mpmc_insert_sites", "mpmc_remove_sites",
            "mpmc_num_sites", "mpmc_energy", "mpmc_energy_enqueue", "mpmc_energy_fetch", "mpmc_download_dipoles",
-           "mpmc_download_rank_metric", "mpmc_pi_potential", "mpmc_pi_chain", "mpmc_set_timing", "mpmc_get_timing", "mpmc_stream", "mpmc_kernel_launches",
+           "mpmc_download_rank_metric", "mpmc_pi_potential", "mpmc_pi_chain", "mpmc_set_timing", "mpmc_get_timing", "mpmc_debug_gs_profile", "mpmc_stream", "mpmc_kernel_launches",
            "mpmc_probe_fp64_peak"]
 
 
@@ -79,6 +79,7 @@ def lib():
         L.mpmc_download_rank_metric.argtypes = [vp, C.c_int, _dp]
         L.mpmc_pi_potential.argtypes = [vp, vp, _dp]
         L.mpmc_pi_chain.argtypes = [vp, C.c_int, C.POINTER(C.c_double), vp, vp, C.POINTER(C.c_int)]
+        L.mpmc_debug_gs_profile.argtypes = [vp, C.c_int, vp, C.c_int, C.POINTER(C.c_int)]
         L.mpmc_set_timing.argtypes = [vp, C.c_int]
         L.mpmc_get_timing.argtypes = [vp, C.POINTER(C.c_double), C.POINTER(C.c_longlong)]
         L.mpmc_stream.argtypes = [vp]

@@ -1,0 +1,34 @@
+"""Developer tool: where does a Gauss-Seidel sweep spend its time?  Prints per-block SM-clock deltas of the solver CTA and
+of updater CTA 1 for the first sweep of one energy() on config 4 (run on the GPU box)."""
+import ctypes as C
+import sys, os
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np
+from mpmcxx_b200 import engine, workloads as W
+
+s = W.h2_framework(solver={"polar_gs": "on", "polar_max_iter": "2"}, ensemble="nvt")
+e = engine.Engine(s)
+L = engine.lib()
+e.energy()
+L.mpmc_debug_gs_profile(e.h, 1, None, 0, None)
+e.energy()
+MAXB = 256
+buf = np.zeros(2 * 8 * MAXB, dtype=np.int64)
+nb = C.c_int()
+L.mpmc_debug_gs_profile(e.h, 0, buf.ctypes.data_as(C.c_void_p), MAXB, C.byref(nb))
+nb = nb.value
+sol = buf[:8 * MAXB].reshape(MAXB, 8)[:nb]
+upd = buf[8 * MAXB:].reshape(MAXB, 8)[:nb]
+names = ["tri+site load", "flag wait", "acc load", "walk", "publish"]
+d = np.diff(sol[:, :6], axis=1)
+print("solver: cycles per phase, mean over %d blocks (SM clock ~1.9 GHz)" % nb)
+for i, nme in enumerate(names):
+    print("  %-14s mean %8.0f  median %8.0f  max %8.0f" % (nme, d[:, i].mean(), np.median(d[:, i]), d[:, i].max()))
+per_blk = np.diff(sol[:, 0])
+print("  block period   mean %8.0f cycles" % per_blk.mean())
+du = upd[:, 1:4] - upd[:, 0:3]
+print("updater 1: wait-for-solved %8.0f, first chunk %8.0f, remaining chunks %8.0f (chunks/panel %.1f)" % (
+    du[:, 0].mean(), du[:, 1].mean(), du[:, 2].mean(), upd[:, 4].mean()))
+print("updater 1 panel period mean %8.0f" % np.diff(upd[:, 0]).mean())
+for b in (1, 2, 50, 100):
+    print(" blk", b, "solver", (sol[b, :6] - sol[b, 0]).tolist(), "upd", (upd[b, :4] - sol[b, 0]).tolist())
