@@ -336,7 +336,7 @@ def run_ours(args):
                       "pair_evals_per_move": last["n_pair_evals"], "polarization_iterations": last["polarization_iterations"]},
            "clocks": clk,
            "e2e": {"value": e2e_value, "unit": "moves/s", "h2d_bytes_per_step": 32 * nmol_sites * (2 - naccept / max(1, args.steps + args.warmup)),
-                   "d2h_bytes_per_step": 32 * last_tiles(eng) + 32, "ms_per_step": 1e3 * t_wall / args.steps,
+                   "d2h_bytes_per_step": 64, "ms_per_step": 1e3 * t_wall / args.steps,
                    "acceptance": naccept / max(1, args.steps + args.warmup)},
            "gpu_launches": int(sum_over_ranks(launches_e2e + launches_dev)),
            "pair_evals_per_sec": value * last["n_pair_evals"],
@@ -347,6 +347,134 @@ def run_ours(args):
         out["extra"] = extra_workloads(engine, local, peak_tflops)
     if rank == 0:
         print(json.dumps(out))
+    eng.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def run_pi(args):
+    """BASELINE config 5: path-integral H2 cluster, 512 molecules x P=64 beads, beads sharded over the GPUs (strong scaling).
+    One move = bead-chain perturbation or rigid displacement of one molecule in every bead system -> mpmc_update_sites_all_beads ->
+    mpmc_pi_potential_allreduce (local sweep + ONE ncclAllReduce of 4 doubles) -> bead-spring term of the moved molecule on the host ->
+    PI_NVT_boltzmann_factor accept/reject.  Every rank replays the same RNG stream, as the reference's MPI ranks do."""
+    import torch
+    import torch.distributed as dist
+    from mpmcxx_b200 import engine, pi
+
+    rank, world, local = env_int("RANK", 0), env_int("WORLD_SIZE", 1), env_int("LOCAL_RANK", 0)
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    P = args.beads
+    five = args.workload == "pi_h2_five"
+    tmpl, beads = W.pi_h2_cluster(n_side=8, P=P, five_site=five)
+    lo, hi = pi.bead_range(P, rank, world)
+    eng = engine.Engine(tmpl, beads=np.ascontiguousarray(beads[lo:hi]), device=local)
+    if world > 1:
+        uid = [engine.nccl_unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(uid, src=0)
+        eng.nccl_init(uid[0], rank, world)
+    ext = torch.cuda.ExternalStream(eng.stream(), device=torch.device("cuda", local))
+    rs = np.random.RandomState(4242)            # the same stream on every rank
+    T = float(tmpl.opts["temperature"])
+    starts = np.nonzero(np.diff(np.concatenate([[-1], tmpl.mol])))[0]
+    ends = np.concatenate([starts[1:], [tmpl.n]])
+    nchain = int(tmpl.opts["PI_trial_chain_length"])
+    pos = beads.copy()                           # every rank keeps all P geometries on the host (as the reference does)
+    u_cur, _ = eng.pi_potential_allreduce(P)
+    nacc = 0
+
+    def step():
+        nonlocal u_cur, nacc
+        m = rs.randint(len(starts))
+        a, b = int(starts[m]), int(ends[m])
+        old = pos[:, a:b, :].copy()
+        mass = tmpl.mass[a:b]
+        com_old = (old * mass[None, :, None]).sum(1) / mass.sum()
+        if rs.random_sample() < 0.5:             # bead_perturb_probability 0.5
+            s0 = rs.randint(P)
+            idx = (s0 + np.arange(nchain)) % P
+            pos[idx, a:b, :] += rs.normal(scale=0.05, size=(nchain, 1, 3))
+            perturb = True
+        else:
+            pos[:, a:b, :] += (rs.random_sample(3) * 2 - 1) * 0.3
+            perturb = False
+        eng.update_sites_all_beads(a, pos[lo:hi, a:b, :])
+        u_new, _ = eng.pi_potential_allreduce(P)
+        if perturb:
+            com_new = (pos[:, a:b, :] * mass[None, :, None]).sum(1) / mass.sum()
+            dchain = pi.chain_mass_len2(com_new, float(mass.sum())) - pi.chain_mass_len2(com_old, float(mass.sum()))
+            bf = pi.bead_perturb_boltzmann(u_new - u_cur, dchain, P, T)
+        else:
+            bf = float(np.exp(min(0.0, -(u_new - u_cur) / T)))
+        if np.isfinite(u_new) and rs.random_sample() < bf:
+            u_cur = u_new
+            nacc += 1
+        else:
+            pos[:, a:b, :] = old
+            eng.update_sites_all_beads(a, pos[lo:hi, a:b, :])
+        return u_new
+
+    peak_tflops, _ = engine.probe_fp64_peak(local)
+    for _ in range(args.warmup):
+        step()
+    clocks = ClockSampler(local)
+    barrier()
+    clocks.start()
+    l0 = eng.launches()
+    eng.set_timing(True)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        step()
+    barrier()
+    t_wall = max_over_ranks(time.perf_counter() - t0)
+    timing = eng.timing()
+    eng.set_timing(False)
+    # device-resident: K sweeps + all-reduce, CUDA events on the engine's stream
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record(ext)
+    for _ in range(args.steps):
+        eng.pi_potential_allreduce(P)
+    e1.record(ext)
+    e1.synchronize()
+    barrier()
+    t_dev = max_over_ranks(e0.elapsed_time(e1) * 1e-3)
+    clk = clocks.stop()
+    launches = eng.launches() - l0
+    out1 = eng.energy_all()[0]
+    pairs_per_sweep = out1["n_pair_evals"] * P
+    pk = timing["pair"]
+    kms = pk[0] / max(pk[1], 1)
+    flop = (FLOP_PER_ES_PAIR if five else FLOP_PER_LJ_PAIR) * out1["n_pair_evals"] * (hi - lo)
+    ach = flop / (kms * 1e-3) / 1e12 if kms > 0 else float("nan")
+    res = {"metric": "mc_moves_per_sec", "value": args.steps / t_dev, "unit": "moves/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+           "ms_per_step": 1e3 * t_dev / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+           "config": {"workload": "config5: path-integral H2 cluster, 512 molecules x %d beads, %s, beads sharded %d per GPU, one NCCL all-reduce of 4 doubles per sweep"
+                                  % (P, "five-site H2 + Ewald (N=2560 per bead)" if five else "single-site H2, rd_only (N=512 per bead)", hi - lo),
+                      "l2": "inputs are < 1 MB per rank and L2-resident by nature; no flush (latency-bound path)", "pair_evals_per_sweep": pairs_per_sweep},
+           "clocks": clk,
+           "e2e": {"value": args.steps / t_wall, "unit": "moves/s", "h2d_bytes_per_step": 32 * (ends[0] - starts[0]) * (hi - lo), "d2h_bytes_per_step": 32,
+                   "ms_per_step": 1e3 * t_wall / args.steps, "acceptance": nacc / (args.steps + args.warmup)},
+           "gpu_launches": int(launches), "pair_evals_per_sec": pairs_per_sweep * args.steps / t_dev,
+           "roofline": {"kernel": "pair", "bound": "fp64", "achieved": ach, "peak": peak_tflops, "unit": "TFLOP/s", "frac": ach / peak_tflops, "traffic": None,
+                        "ms_per_launch": kms, "peak_source": "measured in this run (DFMA probe)",
+                        "kernel_ms_per_step": {k: v[0] / args.steps for k, v in timing.items() if v[1]}}}
+    if rank == 0:
+        print(json.dumps(res))
     eng.close()
     if world > 1:
         dist.destroy_process_group()
@@ -420,7 +548,8 @@ def main():
     ap.add_argument("--steps", type=int, default=30)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="h2_framework", choices=["h2_framework", "lj_argon"])
+    ap.add_argument("--workload", default="h2_framework", choices=["h2_framework", "lj_argon", "pi_h2", "pi_h2_five"])
+    ap.add_argument("--beads", type=int, default=64, help="Trotter number of the path-integral workloads")
     ap.add_argument("--solver", default="gs_ranked_palmo", choices=sorted(SOLVERS))
     ap.add_argument("--scale", type=float, default=1.0, help="linear size factor of the synthetic system (1.0 = the named config)")
     ap.add_argument("--cpu-budget", type=float, default=20.0, help="seconds of CPU work for the cpu_baseline leg")
@@ -431,6 +560,8 @@ def main():
         args.warmup = 3
     if args.impl == "reference":
         run_reference(args)
+    elif args.workload.startswith("pi_"):
+        run_pi(args)
     else:
         run_ours(args)
 

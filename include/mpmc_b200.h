@@ -150,6 +150,17 @@ int mpmc_pi_potential(mpmc_engine *e, double *per_bead, double sums[4]);
  * `closed` != 0, the link from the last local bead back to the first (single-GPU ring).  kg*m^2. */
 int mpmc_pi_chain(mpmc_engine *e, int closed, double *chain_mass_len2, double *com, double *mol_mass, int *n_mol);
 
+/* Beads sharded over the GPUs of one box (replaces the 4 MPI_Allgather of PathIntegral.cpp:763-766 and the rank-per-bead layout of
+ * SimulationControl.cpp:53-65): rank 0 makes an id, every rank joins with its engine (NCCL is loaded with dlopen on first use).
+ * mpmc_pi_potential_allreduce: one sweep over the local beads, device-side assembly of the four per-bead-sum scalars, ONE ncclAllReduce
+ * of 4 doubles on the engine's stream, then means[4] = rd, coulombic, polarization, vdw divided by the global Trotter number and
+ * *potential = their sum (what PI_calculate_potential returns).  Works without mpmc_nccl_init too (single GPU).
+ * mpmc_pi_chain_allreduce: PI_chain_mass_length2_ENTIRE_SYSTEM over the whole ring, the link between consecutive ranks included. */
+int mpmc_nccl_get_unique_id(char id[128]);
+int mpmc_nccl_init(mpmc_engine *e, const char id[128], int rank, int nranks);
+int mpmc_pi_potential_allreduce(mpmc_engine *e, int P_global, double means[4], double *potential);
+int mpmc_pi_chain_allreduce(mpmc_engine *e, double *chain_mass_len2);
+
 /* measurement hooks (bench.py): the CUDA stream every kernel of this engine is launched on (a cudaStream_t),
  * and the number of kernels this engine has launched so far. */
 /* per-kernel-class device time, measured with CUDA events recorded on the engine's stream around each launch

@@ -13,6 +13,7 @@ HOSTLIB = os.path.join(HERE, "libmpmc_host.so")
 
 NVCC_FLAGS = ["-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-Xcompiler", "-fPIC",
               "-shared"]
+NVCC_LIBS = ["-ldl"]
 
 
 def _nvcc() -> str:
@@ -38,6 +39,6 @@ def engine_sources():
 def build_library(force: bool = False, verbose: bool = False) -> str:
     """nvcc -gencode arch=compute_100a,code=sm_100a -lineinfo ... -> mpmcxx_b200/libmpmc_b200.so"""
     if force or _stale(LIB, engine_sources()):
-        cmd = [_nvcc()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB, os.path.join(CSRC, "engine.cu")]
+        cmd = [_nvcc()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB, os.path.join(CSRC, "engine.cu")] + NVCC_LIBS
         subprocess.run(cmd, check=True)
     return LIB

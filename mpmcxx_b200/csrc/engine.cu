@@ -11,6 +11,8 @@
 // shape, so the same configuration always gives the same bits.
 #include "../../include/mpmc_b200.h"
 
+#include <dlfcn.h>
+
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
@@ -49,6 +51,47 @@ static thread_local std::string g_err;
 
 namespace {
 
+// NCCL is reached through dlopen so that single-GPU users need no NCCL at all; only the bead-sharded path-integral calls use it.
+typedef struct ncclComm *nccl_comm_t;
+struct NcclId { char internal[128]; };          // ncclUniqueId (nccl.h), passed by value
+struct NcclApi {
+	void *lib = nullptr;
+	int (*GetUniqueId)(void *) = nullptr;
+	int (*CommInitRank)(nccl_comm_t *, int, NcclId, int) = nullptr;
+	int (*AllReduce)(const void *, void *, size_t, int, int, nccl_comm_t, cudaStream_t) = nullptr;
+	int (*AllGather)(const void *, void *, size_t, int, nccl_comm_t, cudaStream_t) = nullptr;
+	int (*CommDestroy)(nccl_comm_t) = nullptr;
+	const char *(*GetErrorString)(int) = nullptr;
+};
+NcclApi g_nccl;
+constexpr int kNcclFloat64 = 8, kNcclSum = 0;   // ncclDataType_t / ncclRedOp_t values (nccl.h)
+
+int load_nccl() {
+	if (g_nccl.lib) return MPMC_OK;
+	void *h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+	if (!h) h = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+	if (!h) { g_err = std::string("cannot load libnccl: ") + dlerror(); return MPMC_ERR_UNSUPPORTED; }
+	g_nccl.GetUniqueId = (int (*)(void *))dlsym(h, "ncclGetUniqueId");
+	g_nccl.CommInitRank = (int (*)(nccl_comm_t *, int, NcclId, int))dlsym(h, "ncclCommInitRank");
+	g_nccl.AllReduce = (int (*)(const void *, void *, size_t, int, int, nccl_comm_t, cudaStream_t))dlsym(h, "ncclAllReduce");
+	g_nccl.AllGather = (int (*)(const void *, void *, size_t, int, nccl_comm_t, cudaStream_t))dlsym(h, "ncclAllGather");
+	g_nccl.CommDestroy = (int (*)(nccl_comm_t))dlsym(h, "ncclCommDestroy");
+	g_nccl.GetErrorString = (const char *(*)(int))dlsym(h, "ncclGetErrorString");
+	if (!g_nccl.GetUniqueId || !g_nccl.CommInitRank || !g_nccl.AllReduce || !g_nccl.AllGather || !g_nccl.CommDestroy) {
+		g_err = "libnccl is missing required symbols"; return MPMC_ERR_UNSUPPORTED;
+	}
+	g_nccl.lib = h;
+	return MPMC_OK;
+}
+#define NK(call)                                                                                              \
+	do {                                                                                                      \
+		int _r = (call);                                                                                      \
+		if (_r != 0) {                                                                                        \
+			g_err = std::string("NCCL: ") + #call + " -> " + (g_nccl.GetErrorString ? g_nccl.GetErrorString(_r) : "error"); \
+			return MPMC_ERR_CUDA;                                                                             \
+		}                                                                                                     \
+	} while (0)
+
 template <class T> struct DevBuf {
 	T *p = nullptr;
 	size_t cap = 0;
@@ -64,9 +107,9 @@ template <class T> struct DevBuf {
 	void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
 };
 
-// per-energy() scalars written by the kernels and copied back once: [0, B) reciprocal energy per bead,
-// [B, 4B) per bead { sum mu.E_s, sum mu.dE_ind, sum rrms }
-inline size_t res_len(int B) { return (size_t)4 * B; }
+// per-energy() scalars written by the kernels and copied back once: kResStride doubles per bead
+// (rd_pair, es_real, es_intra, n_in, es_recip, sum mu.E_s, sum mu.dE_ind, sum rrms)
+inline size_t res_len(int B) { return (size_t)kResStride * B; }
 
 } // namespace
 
@@ -108,7 +151,6 @@ struct mpmc_engine {
 	DevBuf<double> d_result;
 	// pinned staging
 	double4 *h_stage = nullptr; size_t stage_cap = 0;
-	PairPartial *h_partials = nullptr; size_t partials_cap = 0;
 	double *h_result = nullptr;
 	int *h_flags = nullptr;
 	// polarization bookkeeping of the last energy()
@@ -116,6 +158,11 @@ struct mpmc_engine {
 	std::vector<int> last_failed;
 	bool enqueued = false;
 	int gs_grid = 0;
+	// bead sharding over GPUs
+	nccl_comm_t comm = nullptr;
+	int rank = 0, nranks = 1;
+	DevBuf<double> d_pisums, d_firstcom;
+	double *h_pisums = nullptr;
 	// optional per-kernel-class timing with CUDA events on the engine's stream (mpmc_set_timing)
 	bool timing = false;
 	std::vector<std::pair<cudaEvent_t, cudaEvent_t>> ev_pool;
@@ -588,20 +635,15 @@ static int enqueue_energy(mpmc_engine *e) {
 	// pair sweep: lj() + coulombic_real()
 	const int ntiles = (int)e->tiles.size();
 	if ((rc = e->d_partials.ensure((size_t)B * std::max(ntiles, 1)))) return rc;
-	if ((size_t)B * ntiles > e->partials_cap) {
-		if (e->h_partials) cudaFreeHost(e->h_partials);
-		e->h_partials = nullptr;
-		CK(cudaMallocHost(&e->h_partials, sizeof(PairPartial) * (size_t)B * ntiles));
-		e->partials_cap = (size_t)B * ntiles;
-	}
 	if (ntiles) {
 { Timed _t(e, MPMC_K_PAIR);
 		if (es) k_pair_energy<ORTHO, true><<<dim3(ntiles, B), kPairTile, 0, e->stream>>>(e->d_posq.p, e->d_lj.p, e->d_meta.p, n, e->cap, e->d_tiles.p, ntiles, e->cell, e->d_partials.p);
 		else    k_pair_energy<ORTHO, false><<<dim3(ntiles, B), kPairTile, 0, e->stream>>>(e->d_posq.p, e->d_lj.p, e->d_meta.p, n, e->cap, e->d_tiles.p, ntiles, e->cell, e->d_partials.p);
 		LAUNCHED(e);
- }		CK(cudaMemcpyAsync(e->h_partials, e->d_partials.p, sizeof(PairPartial) * (size_t)B * ntiles, cudaMemcpyDeviceToHost, e->stream));
-	}
+ }	}
 	CK(cudaMemsetAsync(e->d_result.p, 0, sizeof(double) * res_len(B), e->stream));
+	k_reduce_partials<<<B, 256, 0, e->stream>>>(e->d_partials.p, ntiles, e->d_result.p);
+	LAUNCHED(e);
 	if (es) {
 		const int nk = (int)e->kvec.size();
 		// framework structure factor: only when the cell or a frozen charged site changed
@@ -614,7 +656,7 @@ static int enqueue_energy(mpmc_engine *e) {
 		LAUNCHED(e);
 		if (cf.polarization) {
 			if ((rc = run_polar<ORTHO>(e))) return rc;
-			k_polar_energy<<<B, 256, 0, e->stream>>>(e->d_mu.p, e->d_efs.p, e->d_efic.p, e->d_rrms.p, n, e->d_result.p + B);
+			k_polar_energy<<<B, 256, 0, e->stream>>>(e->d_mu.p, e->d_efs.p, e->d_efic.p, e->d_rrms.p, n, e->d_result.p);
 			LAUNCHED(e);
 		}
 	}
@@ -687,9 +729,11 @@ int mpmc_destroy(mpmc_engine *e) {
 	e->d_rrms.release(); e->d_rank.release(); e->d_acc.release(); e->d_dmu.release(); e->d_tri.release(); e->d_gsctl.release(); e->d_com.release(); e->d_mol_mass.release(); e->d_chain.release();
 	e->d_rmin.release(); e->d_result.release();
 	if (e->h_stage) cudaFreeHost(e->h_stage);
-	if (e->h_partials) cudaFreeHost(e->h_partials);
 	if (e->h_result) cudaFreeHost(e->h_result);
 	if (e->h_flags) cudaFreeHost(e->h_flags);
+	if (e->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(e->comm);
+	e->d_pisums.release(); e->d_firstcom.release();
+	if (e->h_pisums) cudaFreeHost(e->h_pisums);
 	for (auto &p : e->ev_pool) { cudaEventDestroy(p.first); cudaEventDestroy(p.second); }
 	if (e->stream) cudaStreamDestroy(e->stream);
 	delete e;
@@ -797,24 +841,21 @@ int mpmc_energy_fetch(mpmc_engine *e, mpmc_energy_out *out) {
 	CK(cudaStreamSynchronize(e->stream));
 	e->enqueued = false;
 	if (e->timing) collect_timing(e);
-	const int B = e->B, ntiles = (int)e->tiles.size();
+	const int B = e->B;
 	const mpmc_config &cf = e->cfg;
 	for (int b = 0; b < B; b++) {
 		mpmc_energy_out &o = out[b];
 		memset(&o, 0, sizeof o);
-		double rd = 0, re = 0, in = 0, cnt = 0;
-		for (int t = 0; t < ntiles; t++) {           // fixed order: tile list order
-			const PairPartial &p = e->h_partials[(size_t)b * ntiles + t];
-			rd += p.rd; re += p.es_real; in += p.es_intra; cnt += p.n_in;
-		}
+		const double *res = e->h_result + (size_t)kResStride * b;
+		const double rd = res[0], re = res[1], in = res[2], cnt = res[3];
 		o.rd_pair = rd; o.rd_lrc_pair = e->lrc_pair; o.rd_lrc_self = e->lrc_self;
 		o.rd_energy = rd + e->lrc_pair + e->lrc_self;
 		o.n_pairs_in_cutoff = cnt; o.n_pair_evals = e->n_pair_evals;
 		if (!cf.rd_only) {
-			o.es_real = re; o.es_self_intra = in; o.es_reciprocal = e->h_result[b]; o.es_self = e->es_self;
+			o.es_real = re; o.es_self_intra = in; o.es_reciprocal = res[4]; o.es_self = e->es_self;
 			o.coulombic_energy = (re - in) + o.es_reciprocal + o.es_self;     // System.Energy.cpp:1407-1412, :1510
 			if (cf.polarization) {
-				const double *pr = e->h_result + B + 3 * b;
+				const double *pr = res + 5;
 				double pot = pr[0];
 				if (cf.polar_palmo) pot += pr[1];
 				o.polarization_energy = -0.5 * pot;                           // :2609-2618
@@ -856,15 +897,96 @@ int mpmc_download_rank_metric(mpmc_engine *e, int bead, double *rank_metric) {
 	return MPMC_OK;
 }
 
-int mpmc_pi_potential(mpmc_engine *e, double *per_bead, double sums[4]) {
-	std::vector<mpmc_energy_out> out(e->B);
-	int rc = mpmc_energy(e, out.data());
+// enqueue one sweep over the local bead systems and leave {sum rd, sum coulombic, sum polarization, sum vdw} in d_pisums[0..3]
+static int pi_sums_enqueue(mpmc_engine *e, double *d_per_bead) {
+	int rc = mpmc_energy_enqueue(e);
 	if (rc) return rc;
-	sums[0] = sums[1] = sums[2] = sums[3] = 0;
-	for (int b = 0; b < e->B; b++) {                 // PathIntegral.cpp:791-796, bead order
-		const double v[4] = {out[b].rd_energy, out[b].coulombic_energy, out[b].polarization_energy, out[b].vdw_energy};
-		for (int q = 0; q < 4; q++) { if (per_bead) per_bead[4 * b + q] = v[q]; sums[q] += v[q]; }
+	if ((rc = e->d_pisums.ensure(8 + 4 * (size_t)e->B))) return rc;
+	if (!e->h_pisums) CK(cudaMallocHost(&e->h_pisums, sizeof(double) * (8 + 4 * (size_t)e->B)));
+	const mpmc_config &cf = e->cfg;
+	k_pi_sums<<<1, 32, 0, e->stream>>>(e->d_result.p, e->B, e->lrc_pair + e->lrc_self, e->es_self, !cf.rd_only, cf.polarization, cf.polar_palmo,
+	                                   d_per_bead, e->d_pisums.p);
+	e->launches++;
+	CK(cudaGetLastError());
+	return MPMC_OK;
+}
+
+int mpmc_pi_potential(mpmc_engine *e, double *per_bead, double sums[4]) {
+	CK(cudaSetDevice(e->dev));
+	int rc = pi_sums_enqueue(e, nullptr);
+	if (rc) return rc;
+	// re-run the tiny assembly with the per-bead output placed right after the sums
+	const mpmc_config &cf = e->cfg;
+	k_pi_sums<<<1, 32, 0, e->stream>>>(e->d_result.p, e->B, e->lrc_pair + e->lrc_self, e->es_self, !cf.rd_only, cf.polarization, cf.polar_palmo,
+	                                   e->d_pisums.p + 8, e->d_pisums.p);
+	e->launches++;
+	CK(cudaMemcpyAsync(e->h_pisums, e->d_pisums.p, sizeof(double) * (8 + 4 * (size_t)e->B), cudaMemcpyDeviceToHost, e->stream));
+	std::vector<mpmc_energy_out> out(e->B);
+	if ((rc = mpmc_energy_fetch(e, out.data()))) return rc;     // synchronises the stream (and keeps iterator_failed etc. current)
+	for (int q = 0; q < 4; q++) sums[q] = e->h_pisums[q];
+	if (per_bead) memcpy(per_bead, e->h_pisums + 8, sizeof(double) * 4 * e->B);
+	return MPMC_OK;
+}
+
+int mpmc_nccl_get_unique_id(char id[128]) {
+	int rc = load_nccl();
+	if (rc) return rc;
+	NK(g_nccl.GetUniqueId(id));
+	return MPMC_OK;
+}
+
+int mpmc_nccl_init(mpmc_engine *e, const char id[128], int rank, int nranks) {
+	int rc = load_nccl();
+	if (rc) return rc;
+	CK(cudaSetDevice(e->dev));
+	if (rank < 0 || rank >= nranks) FAIL(MPMC_ERR_INVALID_SETTING, "nccl_init: bad rank %d of %d", rank, nranks);
+	NcclId nid;
+	memcpy(nid.internal, id, 128);
+	NK(g_nccl.CommInitRank(&e->comm, nranks, nid, rank));
+	e->rank = rank; e->nranks = nranks;
+	return MPMC_OK;
+}
+
+int mpmc_pi_potential_allreduce(mpmc_engine *e, int P_global, double means[4], double *potential) {
+	CK(cudaSetDevice(e->dev));
+	if (P_global < e->B) FAIL(MPMC_ERR_BEADS, "P_global (%d) smaller than the local bead count (%d)", P_global, e->B);
+	int rc = pi_sums_enqueue(e, nullptr);
+	if (rc) return rc;
+	if (e->comm) NK(g_nccl.AllReduce(e->d_pisums.p, e->d_pisums.p, 4, kNcclFloat64, kNcclSum, e->comm, e->stream));
+	CK(cudaMemcpyAsync(e->h_pisums, e->d_pisums.p, sizeof(double) * 4, cudaMemcpyDeviceToHost, e->stream));
+	CK(cudaStreamSynchronize(e->stream));
+	e->enqueued = false;
+	if (e->timing) collect_timing(e);
+	for (int q = 0; q < 4; q++) means[q] = e->h_pisums[q] / P_global;          // PathIntegral.cpp:798-801
+	if (potential) *potential = means[0] + means[1] + means[3] + means[2];     // :803-804
+	return MPMC_OK;
+}
+
+int mpmc_pi_chain_allreduce(mpmc_engine *e, double *chain_mass_len2) {
+	CK(cudaSetDevice(e->dev));
+	const int nmol = (int)e->mol_start.size() - 1, B = e->B;
+	if (nmol < 1) FAIL(MPMC_ERR_NO_MOLECULES, "pi_chain: no sites uploaded");
+	int rc;
+	if ((rc = e->d_com.ensure((size_t)B * nmol * 3)) || (rc = e->d_mol_mass.ensure(nmol)) || (rc = e->d_chain.ensure(nmol)) ||
+	    (rc = e->d_firstcom.ensure((size_t)e->nranks * nmol * 3)) || (rc = e->d_pisums.ensure(8 + 4 * (size_t)B))) return rc;
+	if (!e->h_pisums) CK(cudaMallocHost(&e->h_pisums, sizeof(double) * (8 + 4 * (size_t)B)));
+	k_mol_com<<<(nmol * B + 127) / 128, 128, 0, e->stream>>>(e->d_posq.p, e->cap, e->d_mass.p, e->d_mol_start.p, nmol, B, e->d_com.p, e->d_mol_mass.p);
+	k_chain_len2<<<(nmol + 127) / 128, 128, 0, e->stream>>>(e->d_com.p, e->d_mol_mass.p, e->d_mol_mobile.p, nmol, B, e->nranks == 1, e->d_chain.p);
+	e->launches += 2;
+	if (e->nranks > 1) {
+		// the link from my last bead to the first bead of the next rank: all-gather every rank's first-bead COMs
+		NK(g_nccl.AllGather(e->d_com.p, e->d_firstcom.p, (size_t)nmol * 3, kNcclFloat64, e->comm, e->stream));
+		k_chain_boundary<<<(nmol + 127) / 128, 128, 0, e->stream>>>(e->d_com.p + (size_t)(B - 1) * nmol * 3,
+		                                                          e->d_firstcom.p + (size_t)((e->rank + 1) % e->nranks) * nmol * 3, e->d_mol_mass.p,
+		                                                          e->d_mol_mobile.p, nmol, e->d_chain.p);
+		e->launches++;
 	}
+	k_sum_array<<<1, 256, 0, e->stream>>>(e->d_chain.p, nmol, e->d_pisums.p + 4);
+	e->launches++;
+	if (e->comm) NK(g_nccl.AllReduce(e->d_pisums.p + 4, e->d_pisums.p + 4, 1, kNcclFloat64, kNcclSum, e->comm, e->stream));
+	CK(cudaMemcpyAsync(e->h_pisums + 4, e->d_pisums.p + 4, sizeof(double), cudaMemcpyDeviceToHost, e->stream));
+	CK(cudaStreamSynchronize(e->stream));
+	*chain_mass_len2 = e->h_pisums[4];
 	return MPMC_OK;
 }
 

@@ -95,6 +95,46 @@ k_pair_energy(const double4 *__restrict__ posq, const double2 *__restrict__ lj, 
 	}
 }
 
+// Sum the per-tile partials of one bead in a fixed order (strided per thread, then a shared-memory tree) into the per-bead
+// result record: res[bead*kResStride + 0..3] = rd_pair, es_real, es_intra, n_in.
+constexpr int kResStride = 8;   // + 4 es_recip, 5 sum mu.E_s, 6 sum mu.dE_ind, 7 sum rrms
+__global__ void __launch_bounds__(256)
+k_reduce_partials(const PairPartial *__restrict__ partials, int ntiles, double *__restrict__ res) {
+	__shared__ double s_red[4][256];
+	const int bead = blockIdx.x, tid = threadIdx.x;
+	double a = 0, b = 0, c = 0, d = 0;
+	for (int t = tid; t < ntiles; t += 256) {
+		const PairPartial p = partials[(size_t)bead * ntiles + t];
+		a += p.rd; b += p.es_real; c += p.es_intra; d += p.n_in;
+	}
+	s_red[0][tid] = a; s_red[1][tid] = b; s_red[2][tid] = c; s_red[3][tid] = d;
+	__syncthreads();
+	for (int o = 128; o > 0; o >>= 1) {
+		if (tid < o) for (int q = 0; q < 4; q++) s_red[q][tid] += s_red[q][tid + o];
+		__syncthreads();
+	}
+	if (tid < 4) res[bead * kResStride + tid] = s_red[tid][0];
+}
+
+// PI_calculate_potential (SimulationControl.PathIntegral.cpp:786-796): sums over this engine's bead systems of
+// rd, coulombic, polarization, vdw — assembled on the device so that a collective can follow without a host round trip.
+// konst = { lrc_pair + lrc_self, es_self, palmo flag, polarization flag }
+__global__ void k_pi_sums(const double *__restrict__ res, int nbeads, double rd_const, double es_self, int es_on, int polar_on, int palmo,
+                          double *__restrict__ per_bead, double *__restrict__ sums) {
+	if (threadIdx.x != 0 || blockIdx.x != 0) return;
+	double s0 = 0, s1 = 0, s2 = 0;
+	for (int b = 0; b < nbeads; b++) {
+		const double *r = res + b * kResStride;
+		const double rd = r[0] + rd_const;
+		const double es = es_on ? (r[1] - r[2]) + r[4] + es_self : 0.0;
+		double pol = 0;
+		if (es_on && polar_on) pol = -0.5 * (r[5] + (palmo ? r[6] : 0.0));
+		if (per_bead) { per_bead[4 * b] = rd; per_bead[4 * b + 1] = es; per_bead[4 * b + 2] = pol; per_bead[4 * b + 3] = 0; }
+		s0 += rd; s1 += es; s2 += pol;
+	}
+	sums[0] = s0; sums[1] = s1; sums[2] = s2; sums[3] = 0;
+}
+
 // ---------------------------------------------------------------------------------------------------------
 // Ordered sweeps: CTA = kOrdI sites i x kOrdJ j-lanes (256 threads); thread (il, jl) accumulates site i's sum over
 // j = jl, jl+kOrdJ, ... of every j tile; the j-lanes of one site are the 8 neighbouring lanes of a warp and are

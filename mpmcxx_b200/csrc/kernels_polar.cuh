@@ -125,7 +125,7 @@ __global__ void k_dipole_fail(const double *__restrict__ alpha, const double *__
 	efic[off + t] = 0;
 }
 
-// tail of polar() (:2609-2618) and get_dipole_rrms() (:2639-2657): out[bead] = { sum mu.E_s, sum mu.dE_ind, sum rrms }
+// tail of polar() (:2609-2618) and get_dipole_rrms() (:2639-2657): result record slots 5..7 = sum mu.E_s, sum mu.dE_ind, sum rrms
 __global__ void k_polar_energy(const double *__restrict__ mu, const double *__restrict__ efs, const double *__restrict__ efic,
                                const double *__restrict__ rrms, int n, double *__restrict__ out) {
 	__shared__ double s_red[3][256];
@@ -145,7 +145,7 @@ __global__ void k_polar_energy(const double *__restrict__ mu, const double *__re
 			for (int q = 0; q < 3; q++) s_red[q][threadIdx.x] += s_red[q][threadIdx.x + o];
 		__syncthreads();
 	}
-	if (threadIdx.x == 0) { out[3 * bead] = s_red[0][0]; out[3 * bead + 1] = s_red[1][0]; out[3 * bead + 2] = s_red[2][0]; }
+	if (threadIdx.x == 0) { out[kResStride * bead + 5] = s_red[0][0]; out[kResStride * bead + 6] = s_red[1][0]; out[kResStride * bead + 7] = s_red[2][0]; }
 }
 
 // stable descending order of the polarizable sites by rank metric (update_ranking, :3631-3656, restricted to alpha != 0:
@@ -205,6 +205,29 @@ __global__ void k_chain_len2(const double *__restrict__ com, const double *__res
 		len *= (mol_mass[m] * 1.66053873e-27) * (1.0e-10 * 1.0e-10);   // AMU2KG, ANGSTROM2METER^2 (constants.h:35,27)
 	}
 	per_mol[m] = len;
+}
+
+// the link between this rank's last bead and the next rank's first bead (bead chains sharded over GPUs)
+__global__ void k_chain_boundary(const double *__restrict__ com_last, const double *__restrict__ com_next_first, const double *__restrict__ mol_mass,
+                                 const unsigned char *__restrict__ mol_mobile, int nmol, double *__restrict__ per_mol) {
+	const int m = blockIdx.x * blockDim.x + threadIdx.x;
+	if (m >= nmol || !mol_mobile[m]) return;
+	const double dx = com_last[3 * m] - com_next_first[3 * m], dy = com_last[3 * m + 1] - com_next_first[3 * m + 1], dz = com_last[3 * m + 2] - com_next_first[3 * m + 2];
+	per_mol[m] += (dx * dx + dy * dy + dz * dz) * (mol_mass[m] * 1.66053873e-27) * (1.0e-10 * 1.0e-10);
+}
+
+// out[0] = sum of v[0..n) in a fixed order (one CTA)
+__global__ void k_sum_array(const double *__restrict__ v, int n, double *__restrict__ out) {
+	__shared__ double s_red[256];
+	double a = 0;
+	for (int i = threadIdx.x; i < n; i += blockDim.x) a += v[i];
+	s_red[threadIdx.x] = a;
+	__syncthreads();
+	for (int o = blockDim.x / 2; o > 0; o >>= 1) {
+		if ((int)threadIdx.x < o) s_red[threadIdx.x] += s_red[threadIdx.x + o];
+		__syncthreads();
+	}
+	if (threadIdx.x == 0) out[0] = s_red[0];
 }
 
 // FP64 FMA peak probe: 8 independent chains per thread, 4096 x 8 FMAs each

@@ -110,7 +110,7 @@ __global__ void k_recip_energy(const double2 *__restrict__ S, const KVec *__rest
 		if ((int)threadIdx.x < o) s_red[threadIdx.x] += s_red[threadIdx.x + o];
 		__syncthreads();
 	}
-	if (threadIdx.x == 0) out[bead] = s_red[0] * four_pi_over_v;
+	if (threadIdx.x == 0) out[bead * 8 + 4] = s_red[0] * four_pi_over_v;   // kResStride record, slot 4
 }
 
 // K5 (reciprocal part): recip_term() (src/System.Energy.cpp:2834-2896).  One thread per site; S_all(k) includes the

@@ -47,7 +47,8 @@ class MpmcError(RuntimeError):
 EXPORTS = ["mpmc_abi_version", "mpmc_last_error", "mpmc_device_count", "mpmc_create", "mpmc_destroy", "mpmc_set_cell", "mpmc_get_cell",
            "mpmc_upload_sites", "mpmc_update_sites", "mpmc_update_sites_all_beads", "mpmc_insert_sites", "mpmc_remove_sites",
            "mpmc_num_sites", "mpmc_energy", "mpmc_energy_enqueue", "mpmc_energy_fetch", "mpmc_download_dipoles",
-           "mpmc_download_rank_metric", "mpmc_pi_potential", "mpmc_pi_chain", "mpmc_set_timing", "mpmc_get_timing", "mpmc_debug_gs_profile", "mpmc_stream", "mpmc_kernel_launches",
+           "mpmc_download_rank_metric", "mpmc_pi_potential", "mpmc_pi_chain", "mpmc_nccl_get_unique_id", "mpmc_nccl_init", "mpmc_pi_potential_allreduce",
+           "mpmc_pi_chain_allreduce", "mpmc_set_timing", "mpmc_get_timing", "mpmc_debug_gs_profile", "mpmc_stream", "mpmc_kernel_launches",
            "mpmc_probe_fp64_peak"]
 
 
@@ -79,6 +80,10 @@ def lib():
         L.mpmc_download_rank_metric.argtypes = [vp, C.c_int, _dp]
         L.mpmc_pi_potential.argtypes = [vp, vp, _dp]
         L.mpmc_pi_chain.argtypes = [vp, C.c_int, C.POINTER(C.c_double), vp, vp, C.POINTER(C.c_int)]
+        L.mpmc_nccl_get_unique_id.argtypes = [C.c_char_p]
+        L.mpmc_nccl_init.argtypes = [vp, C.c_char_p, C.c_int, C.c_int]
+        L.mpmc_pi_potential_allreduce.argtypes = [vp, C.c_int, _dp, C.POINTER(C.c_double)]
+        L.mpmc_pi_chain_allreduce.argtypes = [vp, C.POINTER(C.c_double)]
         L.mpmc_debug_gs_profile.argtypes = [vp, C.c_int, vp, C.c_int, C.POINTER(C.c_int)]
         L.mpmc_set_timing.argtypes = [vp, C.c_int]
         L.mpmc_get_timing.argtypes = [vp, C.POINTER(C.c_double), C.POINTER(C.c_longlong)]
@@ -108,6 +113,12 @@ def make_config(basis, opts: _config.EnergyOptions, n_beads=1, device=0, capacit
               "polar_gamma", "polar_precision", "polar_ewald_alpha"):
         setattr(cfg, k, getattr(opts, k))
     return cfg
+
+
+def nccl_unique_id() -> bytes:
+    buf = C.create_string_buffer(128)
+    _ck(lib().mpmc_nccl_get_unique_id(buf))
+    return buf.raw
 
 
 def probe_fp64_peak(device=0):
@@ -208,6 +219,20 @@ class Engine:
         sums = np.zeros(4)
         _ck(lib().mpmc_pi_potential(self.h, per.ctypes.data_as(C.c_void_p), sums))
         return per, sums
+
+    def nccl_init(self, uid: bytes, rank: int, nranks: int):
+        _ck(lib().mpmc_nccl_init(self.h, uid, rank, nranks))
+
+    def pi_potential_allreduce(self, P_global):
+        means = np.zeros(4)
+        pot = C.c_double()
+        _ck(lib().mpmc_pi_potential_allreduce(self.h, P_global, means, C.byref(pot)))
+        return pot.value, means
+
+    def pi_chain_allreduce(self):
+        v = C.c_double()
+        _ck(lib().mpmc_pi_chain_allreduce(self.h, C.byref(v)))
+        return v.value
 
     def pi_chain(self, closed=True):
         nmol = int(self.system.mol.max()) + 1 if self.n == self.system.n else None

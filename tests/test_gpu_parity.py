@@ -121,6 +121,25 @@ def test_pi_matches_reference_golden(name):
     e.close()
 
 
+def test_pi_allreduce_api_single_rank():
+    """mpmc_pi_potential_allreduce / mpmc_pi_chain_allreduce without a communicator equal the reference's aggregates."""
+    eng = _engine_mod()
+    s, r = cases.load_golden("pi_h2_single_27x8")
+    beads = r["beads"]
+    P = beads.shape[0]
+    e = eng.Engine(s, beads=beads)
+    pot, means = e.pi_potential_allreduce(P)
+    assert _rel(means[0], float(r["ref_pi_rd"])) < RTOL and _rel(pot, float(r["ref_pi_potential"])) < RTOL
+    assert _rel(e.pi_chain_allreduce(), float(r["ref_pi_chain_mass_len2"])) < 1e-12
+    # a bead slice gives the slice's share: summing two halves reproduces the whole (what two ranks would all-reduce)
+    e1, e2 = eng.Engine(s, beads=np.ascontiguousarray(beads[:P // 2])), eng.Engine(s, beads=np.ascontiguousarray(beads[P // 2:]))
+    _, s1 = e1.pi_potential()
+    _, s2 = e2.pi_potential()
+    assert _rel((s1[0] + s2[0]) / P, float(r["ref_pi_rd"])) < RTOL
+    for x in (e, e1, e2):
+        x.close()
+
+
 def test_deterministic_bits():
     eng = _engine_mod()
     s = cases.CLASSIC["h2fw_6_gs_ranked_palmo"]()
