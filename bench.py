@@ -37,6 +37,12 @@ FLOP_PER_ES_PAIR = 82.0          # K1 + K2
 BYTES_PER_SITE_SWEEP = 56.0 + 4.0 + 24.0 + 24.0   # 56 B/site + id/flags + mu read + mu written
 
 
+def _np_default(o):
+    if isinstance(o, np.generic):
+        return o.item()
+    raise TypeError(type(o))
+
+
 def env_int(k, d):
     return int(os.environ.get(k, d))
 
@@ -346,7 +352,7 @@ def run_ours(args):
     if rank == 0 and world == 1 and not args.no_extra:
         out["extra"] = extra_workloads(engine, local, peak_tflops)
     if rank == 0:
-        print(json.dumps(out))
+        print(json.dumps(out, default=_np_default))
     eng.close()
     if world > 1:
         dist.destroy_process_group()
@@ -474,7 +480,7 @@ def run_pi(args):
                         "ms_per_launch": kms, "peak_source": "measured in this run (DFMA probe)",
                         "kernel_ms_per_step": {k: v[0] / args.steps for k, v in timing.items() if v[1]}}}
     if rank == 0:
-        print(json.dumps(res))
+        print(json.dumps(res, default=_np_default))
     eng.close()
     if world > 1:
         dist.destroy_process_group()
@@ -539,7 +545,7 @@ def run_reference(args):
            "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": {"workload": desc},
            "cpu_baseline": cb, "e2e": {"value": cb["value"], "unit": "moves/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
            "gpu_launches": 0, "wall_s": time.perf_counter() - t0}
-    print(json.dumps(out))
+    print(json.dumps(out, default=_np_default))
 
 
 def main():

@@ -42,3 +42,25 @@ def build_library(force: bool = False, verbose: bool = False) -> str:
         cmd = [_nvcc()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB, os.path.join(CSRC, "engine.cu")] + NVCC_LIBS
         subprocess.run(cmd, check=True)
     return LIB
+
+
+HOST_DIR = os.path.join(HERE, "host")
+HOST_BIN = os.path.join(HERE, "mpmcxx-b200")
+HOST_FLAGS = ["-O2", "-std=c++17", "-ffp-contract=off", "-fPIC", "-Wall"]
+
+
+def host_sources():
+    return [os.path.join(HOST_DIR, f) for f in sorted(os.listdir(HOST_DIR)) if f.endswith((".cpp", ".h"))] + [os.path.join(ROOT, "include", "mpmc_b200.h")]
+
+
+def build_host(force: bool = False) -> str:
+    """g++ -> mpmcxx_b200/libmpmc_host.so (the C++ mirror of System/Molecule/Atom/SimulationControl over the C-ABI) and the
+    mpmcxx-b200 command-line driver; both link libmpmc_b200.so through an $ORIGIN rpath."""
+    build_library(force=False)
+    if force or _stale(HOSTLIB, host_sources()) or _stale(HOST_BIN, host_sources()):
+        cxx = "g++"
+        srcs = [os.path.join(HOST_DIR, f) for f in ("host.cpp", "sim_control.cpp", "host_capi.cpp")]
+        link = ["-L" + HERE, "-lmpmc_b200", "-Wl,-rpath,$ORIGIN"]
+        subprocess.run([cxx] + HOST_FLAGS + ["-shared", "-o", HOSTLIB] + srcs + link, check=True)
+        subprocess.run([cxx] + HOST_FLAGS + ["-o", HOST_BIN, os.path.join(HOST_DIR, "main.cpp")] + srcs + link, check=True)
+    return HOSTLIB

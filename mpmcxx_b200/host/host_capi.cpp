@@ -1,0 +1,54 @@
+// host_capi.cpp — C entry points over the host mirror, used by the trajectory-parity tests and the command-line driver.
+#include <cstring>
+#include <vector>
+
+#include "mpmc_host.h"
+
+using namespace mpmc_host;
+
+extern "C" {
+
+// Run the simulation an input file describes (ensemble nvt | uvt | pi_nvt), with `P` beads for pi_nvt, for at most max_steps
+// steps (0 = numsteps from the file).  log receives 5 doubles per step: move type, trial energy (potential for pi_nvt),
+// Boltzmann factor, accepted (0/1), N (classic) or kinetic energy (pi_nvt).  summary[8] = final observables: energy, rd, coulombic,
+// polarization, kinetic, N, accepted count, rejected count.  Returns 0 or the reference-style error code that was thrown.
+int mpmc_host_run(const char *input_file, int P, int max_steps, double *log, int log_capacity, int *n_logged, double *summary) {
+	try {
+		SimulationControl sc(input_file, P);
+		if (max_steps > 0) sc.sys.numsteps = (uint32_t)max_steps;
+		sc.initializeSimulationObjects();
+		std::vector<System::step_record> rec;
+		sc.runSimulation(&rec);
+		const int n = (int)std::min<size_t>(rec.size(), (size_t)log_capacity);
+		for (int i = 0; i < n; i++) {
+			log[5 * i] = rec[i].movetype; log[5 * i + 1] = rec[i].final_energy; log[5 * i + 2] = rec[i].boltzmann_factor;
+			log[5 * i + 3] = rec[i].accepted; log[5 * i + 4] = rec[i].N;
+		}
+		if (n_logged) *n_logged = n;
+		if (summary) {
+			const System::observables_t &o = *sc.sys.observables;
+			summary[0] = o.energy; summary[1] = o.rd_energy; summary[2] = o.coulombic_energy; summary[3] = o.polarization_energy;
+			summary[4] = o.kinetic_energy; summary[5] = o.N; summary[6] = sc.sys.nodestats->accept; summary[7] = sc.sys.nodestats->reject;
+		}
+	} catch (int e) {
+		return e ? e : internal_error;
+	}
+	return 0;
+}
+
+// One energy() of the system an input file describes, through the mirror (reader + flatten + engine): out[5] = energy, rd,
+// coulombic, polarization, iterations.
+int mpmc_host_energy(const char *input_file, double *out) {
+	try {
+		SimulationControl sc(input_file, 0);
+		sc.initializeSimulationObjects();
+		out[0] = sc.sys.energy();
+		out[1] = sc.sys.observables->rd_energy; out[2] = sc.sys.observables->coulombic_energy;
+		out[3] = sc.sys.observables->polarization_energy; out[4] = sc.sys.nodestats->polarization_iterations;
+	} catch (int e) {
+		return e ? e : internal_error;
+	}
+	return 0;
+}
+
+} // extern "C"

@@ -1,0 +1,447 @@
+// sim_control.cpp — SimulationControl mirror: the input keywords that parameterise the hot path and its two callers
+// (src/SimulationControl.cpp:258-1616 subset), and the path-integral Markov chain (src/SimulationControl.PathIntegral.cpp).
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+#include <fstream>
+#include <sstream>
+
+#include "mpmc_host.h"
+
+namespace mpmc_host {
+
+static bool ieq(const std::string &a, const char *b) {
+	size_t n = strlen(b);
+	if (a.size() != n) return false;
+	for (size_t i = 0; i < n; i++) if (tolower((unsigned char)a[i]) != tolower((unsigned char)b[i])) return false;
+	return true;
+}
+static double num(const std::string &s) {
+	size_t idx = 0; double d;
+	try { d = std::stod(s, &idx); } catch (...) { throw invalid_input; }
+	if (idx != s.size()) throw invalid_input;
+	return d;
+}
+static int onoff(const std::string &s) {
+	if (ieq(s, "on")) return 1;
+	if (ieq(s, "off")) return 0;
+	throw invalid_input;
+}
+
+SimulationControl::SimulationControl(const char *inFilename, int P) : nSys(P) {
+	read_config(inFilename);
+	check_system();
+}
+
+SimulationControl::~SimulationControl() {
+	if (pi_gpu) mpmc_destroy(pi_gpu);
+	for (System *s : systems) delete s;
+}
+
+void SimulationControl::read_config(const char *inFilename) {
+	std::ifstream in(inFilename);
+	if (!in) throw fopen_fail_read;
+	std::string line;
+	while (std::getline(in, line)) {
+		std::istringstream ss(line);
+		std::vector<std::string> t;
+		for (std::string w; ss >> w;) t.push_back(w);
+		if (t.empty() || t[0][0] == '!' || t[0][0] == '#') continue;
+		if (!process_command(t)) throw invalid_input;
+	}
+}
+
+// the keywords that reach energy() and the two MC loops; everything else the reference knows is either accepted and ignored
+// here (output/bookkeeping options) or refused (physics this engine does not implement)
+bool SimulationControl::process_command(const std::vector<std::string> &t) {
+	const std::string &k = t[0];
+	auto arg = [&](size_t i) -> const std::string & { if (t.size() <= i) throw invalid_input; return t[i]; };
+	if (ieq(k, "job_name")) { strncpy(sys.job_name, arg(1).c_str(), sizeof sys.job_name - 1); return true; }
+	if (ieq(k, "ensemble")) {
+		if (ieq(arg(1), "nvt")) sys.ensemble = ENSEMBLE_NVT;
+		else if (ieq(arg(1), "uvt")) sys.ensemble = ENSEMBLE_UVT;
+		else if (ieq(arg(1), "pi_nvt")) sys.ensemble = ENSEMBLE_PATH_INTEGRAL_NVT;
+		else throw unsupported_setting;
+		return true;
+	}
+	if (ieq(k, "seed")) { sys.preset_seed = (unsigned int)std::stoul(arg(1)); sys.preset_seed_on = 1; return true; }
+	if (ieq(k, "numsteps")) { sys.numsteps = (uint32_t)num(arg(1)); return true; }
+	if (ieq(k, "corrtime")) { sys.corrtime = (uint32_t)num(arg(1)); return true; }
+	if (ieq(k, "move_factor")) { sys.move_factor = num(arg(1)); return true; }
+	if (ieq(k, "rot_factor")) { sys.rot_factor = num(arg(1)); return true; }
+	if (ieq(k, "insert_probability")) { sys.insert_probability = num(arg(1)); return true; }
+	if (ieq(k, "bead_perturb_probability")) { sys.bead_perturb_probability = num(arg(1)); return true; }
+	if (ieq(k, "PI_trial_chain_length")) { PI_trial_chain_length = (int)num(arg(1)); return true; }
+	if (ieq(k, "temperature")) { sys.temperature = num(arg(1)); return true; }
+	if (ieq(k, "pressure")) { sys.pressure = num(arg(1)); return true; }
+	if (ieq(k, "free_volume")) { sys.free_volume = num(arg(1)); return true; }
+	if (ieq(k, "scale_charge")) { sys.scale_charge = num(arg(1)); return true; }
+	if (ieq(k, "basis1") || ieq(k, "basis2") || ieq(k, "basis3")) {
+		const int r = k[5] - '1';
+		for (int j = 0; j < 3; j++) sys.pbc.basis[r][j] = num(arg(1 + j));
+		return true;
+	}
+	if (ieq(k, "pqr_input")) { strncpy(sys.pqr_input, arg(1).c_str(), sizeof sys.pqr_input - 1); return true; }
+	if (ieq(k, "rd_only")) { sys.rd_only = onoff(arg(1)); return true; }
+	if (ieq(k, "rd_lrc")) { sys.rd_lrc = onoff(arg(1)); return true; }
+	if (ieq(k, "wrapall")) { sys.wrapall = onoff(arg(1)); return true; }
+	if (ieq(k, "parallel_restarts")) { sys.parallel_restarts = onoff(arg(1)); return true; }
+	if (ieq(k, "cuda")) { sys.cuda = onoff(arg(1)); return true; }
+	if (ieq(k, "ewald_alpha")) { sys.ewald_alpha = num(arg(1)); sys.ewald_alpha_set = 1; return true; }
+	if (ieq(k, "ewald_kmax")) { sys.ewald_kmax = (int)num(arg(1)); return true; }
+	if (ieq(k, "polarization")) { sys.polarization = onoff(arg(1)); return true; }
+	if (ieq(k, "polar_ewald")) { sys.polar_ewald = onoff(arg(1)); return true; }
+	if (ieq(k, "polar_ewald_alpha")) { sys.polar_ewald_alpha = num(arg(1)); sys.polar_ewald_alpha_set = 1; return true; }
+	if (ieq(k, "polar_iterative")) { sys.polar_iterative = onoff(arg(1)); return true; }
+	if (ieq(k, "polar_zodid")) { sys.polar_zodid = onoff(arg(1)); return true; }
+	if (ieq(k, "polar_palmo")) { sys.polar_palmo = onoff(arg(1)); return true; }
+	if (ieq(k, "polar_gs")) { sys.polar_gs = onoff(arg(1)); return true; }
+	if (ieq(k, "polar_gs_ranked")) { sys.polar_gs_ranked = onoff(arg(1)); return true; }
+	if (ieq(k, "polar_sor")) { sys.polar_sor = onoff(arg(1)); return true; }
+	if (ieq(k, "polar_esor")) { sys.polar_esor = onoff(arg(1)); return true; }
+	if (ieq(k, "polar_rrms")) { sys.polar_rrms = onoff(arg(1)); return true; }
+	if (ieq(k, "polar_gamma")) { sys.polar_gamma = num(arg(1)); return true; }
+	if (ieq(k, "polar_damp")) { sys.polar_damp = num(arg(1)); return true; }
+	if (ieq(k, "polar_precision")) { sys.polar_precision = num(arg(1)); return true; }
+	if (ieq(k, "polar_max_iter")) { sys.polar_max_iter = (int)num(arg(1)); return true; }
+	if (ieq(k, "polar_damp_type")) {
+		if (ieq(arg(1), "none") || ieq(arg(1), "off")) sys.damp_type = DAMPING_OFF;
+		else if (ieq(arg(1), "linear")) sys.damp_type = DAMPING_LINEAR;
+		else if (ieq(arg(1), "exponential")) sys.damp_type = DAMPING_EXPONENTIAL;
+		else return false;
+		return true;
+	}
+	// physics switches this engine refuses unless they are off
+	for (const char *w : {"feynman_hibbs", "h2_fugacity", "co2_fugacity", "ch4_fugacity", "n2_fugacity", "wolf", "sg", "dreiding", "spectre", "gwp", "cavity_bias",
+	                      "rd_anharmonic", "polar_ewald_full", "polar_wolf", "polar_wolf_full", "quantum_rotation", "simulated_annealing", "waldmanhagler",
+	                      "halgren_mixing", "c6_mixing", "axilrod_teller", "disp_expansion", "lj_buffered_14_7", "cdvdw", "rd_crystal"})
+		if (ieq(k, w)) { if (onoff(arg(1))) throw unsupported_setting; return true; }
+	// bookkeeping / output options: accepted, not used on this path
+	for (const char *w : {"pop_histogram", "traj_output", "energy_output", "energy_output_csv", "pqr_output", "pqr_restart", "dipole_output", "field_output",
+	                      "frozen_output", "pop_histogram_output", "pop_hist_resolution", "read_pqr_box", "long_output", "traj_input", "insert_input",
+	                      "max_bondlength", "calc_pressure", "rot_probability", "move_probability"})
+		if (ieq(k, w)) return true;
+	return false;
+}
+
+void SimulationControl::check_system() {
+	if (sys.temperature <= 0) throw missing_setting;
+	if (!sys.numsteps) throw missing_setting;
+	if (!sys.pqr_input[0]) { strncpy(sys.pqr_input, sys.job_name, sizeof sys.pqr_input - 16); strcat(sys.pqr_input, ".initial.pqr"); }
+	if (sys.ensemble == ENSEMBLE_PATH_INTEGRAL_NVT) {      // check_PI_options, PathIntegral.cpp:552-606
+		int bits = 0;
+		for (unsigned v = (unsigned)nSys; v; v >>= 1) bits += v & 1;
+		if (nSys < 4 || bits != 1) throw invalid_MPI_size_for_PI;
+		if (!PI_trial_chain_length || PI_trial_chain_length >= nSys) throw invalid_setting;
+	}
+	if (sys.ensemble == ENSEMBLE_UVT && sys.pressure <= 0) throw missing_setting;
+}
+
+void SimulationControl::initializeSimulationObjects() {      // src/SimulationControl.cpp:80-199
+	if (!sys.preset_seed_on) throw missing_setting;          // trajectories are only comparable with a preset seed
+	Rando::seed(sys.preset_seed);
+	if (sys.ensemble == ENSEMBLE_PATH_INTEGRAL_NVT) { initialize_PI_NVT_Systems(); return; }
+	sys.read_molecules(sys.pqr_input);
+	sys.update_pbc();
+	sys.mt_rand.seed(sys.preset_seed);
+}
+
+bool SimulationControl::runSimulation(std::vector<System::step_record> *log) {
+	if (sys.ensemble == ENSEMBLE_PATH_INTEGRAL_NVT) return PI_nvt_mc(log);
+	return sys.mc(log);
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// path integrals
+// ------------------------------------------------------------------------------------------------------------
+void SimulationControl::initialize_PI_NVT_Systems() {        // PathIntegral.cpp:611-694
+	for (int i = 0; i < nSys; i++) {
+		System *s = new System(sys);
+		s->read_molecules(sys.pqr_input);
+		s->update_pbc();
+		for (Molecule *m = s->molecules; m; m = m->next) m->update_COM();
+		systems.push_back(s);
+	}
+	sys.pbc = systems[0]->pbc;
+}
+
+// energy() of every bead system in one batched engine call; means over beads (PathIntegral.cpp:752-805)
+double SimulationControl::PI_calculate_potential() {
+	const int P = nSys, n = systems[0]->countNatoms();
+	std::vector<double> pos;
+	pos.reserve((size_t)P * n * 3);
+	int rc;
+	std::vector<double> q, al, ep, sg, ms;
+	std::vector<int> mol, fz;
+	for (int s = 0; s < P; s++) {
+		std::vector<double> q1, a1, e1, s1, m1;
+		std::vector<int> mo1, f1;
+		systems[s]->flatten(pos, q1, a1, e1, s1, m1, mo1, f1);
+		if (s == 0) { q.swap(q1); al.swap(a1); ep.swap(e1); sg.swap(s1); ms.swap(m1); mol.swap(mo1); fz.swap(f1); }
+		else if ((int)q1.size() != n) throw 6005;          // incongruent_bead_states
+	}
+	if (!pi_gpu) {
+		mpmc_config c;
+		systems[0]->fill_config(c, P);
+		if ((rc = mpmc_create(&c, &pi_gpu))) throw rc;
+		if ((rc = mpmc_upload_sites(pi_gpu, n, pos.data(), q.data(), al.data(), ep.data(), sg.data(), ms.data(), mol.data(), fz.data()))) throw rc;
+	} else {
+		int lo = n, hi = -1;                                // the moved molecule is the same contiguous run of sites in every bead system
+		for (int s = 0; s < P; s++)
+			for (int i = 0; i < n; i++)
+				if (memcmp(&pos[((size_t)s * n + i) * 3], &pi_gpu_pos[((size_t)s * n + i) * 3], 3 * sizeof(double))) { lo = std::min(lo, i); hi = std::max(hi, i); }
+		if (hi >= lo) {
+			const int cnt = hi - lo + 1;
+			std::vector<double> seg((size_t)P * cnt * 3);
+			for (int s = 0; s < P; s++) memcpy(&seg[(size_t)s * cnt * 3], &pos[((size_t)s * n + lo) * 3], sizeof(double) * 3 * cnt);
+			if ((rc = mpmc_update_sites_all_beads(pi_gpu, lo, cnt, seg.data()))) throw rc;
+		}
+	}
+	pi_gpu_pos.swap(pos);
+	double means[4], U;
+	if ((rc = mpmc_pi_potential_allreduce(pi_gpu, P, means, &U))) throw rc;
+	System::observables_t *obs = sys.observables;
+	obs->rd_energy = means[0]; obs->coulombic_energy = means[1]; obs->polarization_energy = means[2]; obs->vdw_energy = means[3];
+	return obs->rd_energy + obs->coulombic_energy + obs->vdw_energy + obs->polarization_energy;
+}
+
+double SimulationControl::PI_calculate_kinetic() {            // :810-828
+	const double d = 3.0, N = (double)systems[0]->countN(), P = (double)nSys, T = sys.temperature;
+	const double beta = 1.0 / (kB * T), omega2 = P / (beta * beta * hBar2);
+	const double chain_mass_len2 = PI_chain_mass_length2_ENTIRE_SYSTEM();
+	const double term_1 = 0.5 * d * N * kB * T * P, term_2 = 0.5 * omega2 * chain_mass_len2;
+	sys.observables->kinetic_energy = (1.0 / kB) * (term_1 - term_2);
+	return sys.observables->kinetic_energy;
+}
+
+double SimulationControl::PI_calculate_energy() {             // :734-748
+	const double kinetic = PI_calculate_kinetic();
+	const double potential = PI_calculate_potential();
+	sys.observables->energy = kinetic + potential;
+	return sys.observables->energy;
+}
+
+double SimulationControl::PI_chain_mass_length2_ENTIRE_SYSTEM() {   // :859-904
+	double sum = 0;
+	std::vector<Molecule *> ptr(nSys);
+	for (int s = 0; s < nSys; s++) ptr[s] = systems[s]->molecules;
+	while (ptr[0]) {
+		if (!(ptr[0]->frozen || ptr[0]->adiabatic || ptr[0]->target)) {
+			for (int s = 0; s < nSys; s++) if (!ptr[s]) throw internal_error;
+			sum += PI_chain_mass_length2(ptr);
+		}
+		for (int s = 0; s < nSys; s++) ptr[s] = ptr[s]->next;
+	}
+	return sum;
+}
+
+double SimulationControl::PI_chain_mass_length2() {           // :905-915
+	std::vector<Molecule *> mol;
+	for (System *s : systems) {
+		if (!s->checkpoint->molecule_altered) throw internal_error;
+		mol.push_back(s->checkpoint->molecule_altered);
+	}
+	return PI_chain_mass_length2(mol);
+}
+
+double SimulationControl::PI_chain_mass_length2(std::vector<Molecule *> &molecule) {   // :916-970
+	std::vector<double> c(3 * (size_t)nSys);
+	for (int s = 0; s < nSys; s++) {
+		molecule[s]->update_COM();
+		for (int p = 0; p < 3; p++) c[3 * s + p] = molecule[s]->com[p];
+	}
+	double len2 = 0;
+	for (int i = 0; i < nSys; i++) {
+		const int j = (i + 1) % nSys;
+		const double dx = c[3 * i] - c[3 * j], dy = c[3 * i + 1] - c[3 * j + 1], dz = c[3 * i + 2] - c[3 * j + 2];
+		len2 += dx * dx + dy * dy + dz * dz;
+	}
+	len2 *= (molecule[0]->mass * AMU2KG) * (ANGSTROM2METER * ANGSTROM2METER);
+	return len2;
+}
+
+// two uniforms from Rando: move type, then the target index (the same index in every bead system) (:1047-1116)
+int SimulationControl::PI_pick_NVT_move() {
+	const double dice_move = Rando::rand(), dice_target = Rando::rand();
+	for (int s = 0; s < nSys; s++) {
+		System *S = systems[s];
+		std::vector<Molecule *> cand;
+		for (Molecule *m = S->molecules; m; m = m->next) if (!(m->frozen || m->adiabatic || m->target)) cand.push_back(m);
+		if (cand.empty()) throw no_molecules_in_system;
+		const int target = (int)std::floor(cand.size() * dice_target);
+		S->checkpoint->molecule_altered = cand[target];
+		S->checkpoint->movetype = (dice_move < sys.bead_perturb_probability) ? MOVETYPE_PERTURB_BEADS : MOVETYPE_DISPLACE;
+		Molecule *prev = nullptr;
+		for (Molecule *m = S->molecules; m; m = m->next) {
+			if (m == S->checkpoint->molecule_altered) { S->checkpoint->head = prev; S->checkpoint->tail = m->next; break; }
+			prev = m;
+		}
+		delete S->checkpoint->molecule_backup;
+		S->checkpoint->molecule_backup = new Molecule(*S->checkpoint->molecule_altered);
+	}
+	return systems[0]->checkpoint->movetype;
+}
+
+void SimulationControl::PI_make_move(int move) {
+	switch (move) {
+	case MOVETYPE_DISPLACE: PI_displace(); break;
+	case MOVETYPE_PERTURB_BEADS: PI_perturb_beads(); break;
+	default: throw invalid_monte_carlo_move;
+	}
+}
+
+// the same translation for every bead, then one rotation of the whole chain about the chain's centre (:1320-1387).
+// Rando order: six uniforms, three normals, one uniform (angle = u * rot_factor DEGREES, no factor 360).
+void SimulationControl::PI_displace() {
+	double dice[6];
+	for (int i = 0; i < 6; i++) dice[i] = Rando::rand();
+	const int n = (int)systems.size();
+	double pc[3] = {0, 0, 0};
+	std::vector<Molecule *> alt;
+	for (int s = 0; s < n; s++) {
+		Molecule *m = systems[s]->checkpoint->molecule_altered;
+		alt.push_back(m);
+		m->update_COM();
+		m->translate_rand_pbc(sys.move_factor, systems[s]->pbc, dice);
+		pc[0] = pc[0] + m->com[0]; pc[1] = pc[1] + m->com[1]; pc[2] = pc[2] + m->com[2];
+	}
+	pc[0] /= n; pc[1] /= n; pc[2] /= n;
+	const double dx = Rando::rand_normal(), dy = Rando::rand_normal(), dz = Rando::rand_normal();
+	const double angle = Rando::rand() * sys.rot_factor;
+	// Quaternion(x, y, z, angle, AXIS_ANGLE_DEGREE) and Quaternion::rotate(v) = (q v) q*   (src/Quaternion.cpp)
+	double ang = angle / 57.2957795, X, Y, Z, W;
+	{
+		double mag = std::sqrt(dx * dx + dy * dy + dz * dz);
+		if (mag == 0.0) { X = Y = Z = 0; W = 1; }
+		else {
+			const double x = dx / mag, y = dy / mag, z = dz / mag, sn = std::sin(ang / 2.0);
+			X = x * sn; Y = y * sn; Z = z * sn; W = std::cos(ang / 2.0);
+		}
+	}
+	for (Molecule *m : alt) {
+		m->translate(-pc[0], -pc[1], -pc[2]);
+		for (Atom *a = m->atoms; a; a = a->next) {
+			const double vx = a->pos[0], vy = a->pos[1], vz = a->pos[2], vw = 0;
+			// t = q * v
+			const double tw = W * vw - X * vx - Y * vy - Z * vz;
+			const double tx = W * vx + X * vw + Y * vz - Z * vy;
+			const double ty = W * vy - X * vz + Y * vw + Z * vx;
+			const double tz = W * vz + X * vy - Y * vx + Z * vw;
+			// r = t * conj(q)
+			const double cx = -X, cy = -Y, cz = -Z, cw = W;
+			a->pos[0] = tw * cx + tx * cw + ty * cz - tz * cy;
+			a->pos[1] = tw * cy - tx * cz + ty * cw + tz * cx;
+			a->pos[2] = tw * cz + tx * cy - ty * cx + tz * cw;
+		}
+		m->translate(pc[0], pc[1], pc[2]);
+		m->update_COM();
+	}
+}
+
+void SimulationControl::PI_perturb_beads() {
+	// PI_perturb_beads_orientations() returns at once unless sorbate_orientation_site / bond length metadata are configured
+	// (:1559-1572); this mirror has no such keywords.
+	PI_perturb_bead_COMs();
+}
+
+void SimulationControl::PI_perturb_bead_COMs_ENTIRE_SYSTEM() {      // :1402-1449
+	std::vector<Molecule *> ptr(nSys), backup(nSys);
+	for (int s = 0; s < nSys; s++) { ptr[s] = systems[s]->molecules; backup[s] = systems[s]->checkpoint->molecule_altered; }
+	while (ptr[0]) {
+		if (!(ptr[0]->frozen || ptr[0]->adiabatic || ptr[0]->target)) {
+			for (int s = 0; s < nSys; s++) { if (!ptr[s]) throw internal_error; systems[s]->checkpoint->molecule_altered = ptr[s]; }
+			PI_perturb_bead_COMs(nSys);
+		}
+		for (int s = 0; s < nSys; s++) ptr[s] = ptr[s]->next;
+	}
+	for (int s = 0; s < nSys; s++) systems[s]->checkpoint->molecule_altered = backup[s];
+}
+
+void SimulationControl::PI_perturb_bead_COMs() { PI_perturb_bead_COMs(PI_trial_chain_length); }
+
+// Coker et al. staging of n consecutive beads between two anchors, then removal of the chain-COM drift (:1453-1554).
+// Rando order: three normals per moved bead.  The anchor advances by one bead per call.
+void SimulationControl::PI_perturb_bead_COMs(int n) {
+	const double beta = 1.0 / (kB * sys.temperature), P = (double)nSys;
+	const double Mass = AMU2KG * systems[0]->checkpoint->molecule_altered->mass;
+	int prev = starterBead, bead = (prev + 1) % nSys;
+	const int last = (prev + n + 1) % nSys;
+	starterBead = (starterBead + 1) % nSys;
+	std::vector<double> b(3 * (size_t)nSys);
+	double cc[3] = {0, 0, 0};
+	for (int s = 0; s < nSys; s++) {
+		Molecule *m = systems[s]->checkpoint->molecule_altered;
+		m->update_COM();
+		for (int p = 0; p < 3; p++) { b[3 * s + p] = m->com[p]; cc[p] = cc[p] + m->com[p]; }
+	}
+	for (int p = 0; p < 3; p++) cc[p] /= P;
+	double tB = (double)n, tA = 1.0 + n;
+	for (int j = 1; j <= n; j++) {
+		const double init_factor = tB-- / tA--;
+		const double term_factor = 1.0 - init_factor;
+		const double sigma_factor = std::sqrt((hBar2 * beta * init_factor) / (P * Mass)) * METER2ANGSTROM;
+		const double px = Rando::rand_normal(), py = Rando::rand_normal(), pz = Rando::rand_normal();
+		const double pert[3] = {px, py, pz};
+		for (int p = 0; p < 3; p++) b[3 * bead + p] = (init_factor * b[3 * prev + p] + term_factor * b[3 * last + p]) + sigma_factor * pert[p];
+		prev = (prev + 1) % nSys;
+		bead = (prev + 1) % nSys;
+	}
+	double dc[3] = {0, 0, 0};
+	for (int s = 0; s < nSys; s++) for (int p = 0; p < 3; p++) dc[p] = dc[p] + b[3 * s + p];
+	for (int p = 0; p < 3; p++) dc[p] = (dc[p] / P) - cc[p];
+	for (int s = 0; s < nSys; s++) for (int p = 0; p < 3; p++) b[3 * s + p] -= dc[p];
+	for (int s = 0; s < nSys; s++) systems[s]->checkpoint->molecule_altered->move_to_(b[3 * s], b[3 * s + 1], b[3 * s + 2]);
+}
+
+void SimulationControl::restore_PI_systems() {
+	for (System *S : systems) { S->iterator_failed = 0; S->restore(); }
+}
+
+double SimulationControl::PI_NVT_boltzmann_factor(double d_potential, double d_chain, int movetype) {   // :490-547
+	const double P = (double)nSys, T = sys.temperature;
+	if (movetype == MOVETYPE_PERTURB_BEADS) {
+		const double PIchain_2_K = (P * pi * pi * kB * T) / (2.0 * h * h);
+		const double potential_contrib = d_potential / T, PI_COM_contrib = d_chain * PIchain_2_K, PI_orientation_contrib = 0;
+		return exp(-potential_contrib - PI_COM_contrib - PI_orientation_contrib);
+	}
+	return exp(-d_potential / T);
+}
+
+bool SimulationControl::PI_nvt_mc(std::vector<System::step_record> *log) {     // :31-196
+	for (System *S : systems) { S->observables->temperature = sys.temperature; S->observables->volume = S->pbc.volume; }
+	if (!sys.parallel_restarts) PI_perturb_bead_COMs_ENTIRE_SYSTEM();
+	PI_calculate_energy();
+	int move = PI_pick_NVT_move();
+	System::observables_t saved = *sys.observables;
+	double pot_current = sys.observables->potential();
+	if (!std::isfinite(pot_current)) sys.observables->energy = pot_current = MAXVALUE;
+	for (sys.step = 1; sys.step <= sys.numsteps; sys.step++) {
+		const double pot_init = pot_current;
+		const double chain_init = (move == MOVETYPE_PERTURB_BEADS) ? PI_chain_mass_length2() : 0;
+		PI_make_move(move);
+		double pot_trial = PI_calculate_potential();
+		const double chain_trial = (move == MOVETYPE_PERTURB_BEADS) ? PI_chain_mass_length2() : 0;
+		double bf;
+		if (!std::isfinite(pot_trial)) { pot_trial = sys.observables->energy = MAXVALUE; bf = 0; }
+		else bf = PI_NVT_boltzmann_factor(pot_trial - pot_init, chain_trial - chain_init, move);
+		sys.nodestats->boltzmann_factor = bf;
+		int accepted;
+		if ((Rando::rand() < bf) && (systems[0]->iterator_failed == 0)) {
+			accepted = 1;
+			pot_current = pot_trial;
+			PI_calculate_energy();                           // an accepted move costs a second sweep (:148)
+			saved = *sys.observables;
+			sys.nodestats->accept++;
+		} else {
+			accepted = 0;
+			restore_PI_systems();
+			*sys.observables = saved;
+			sys.nodestats->reject++;
+		}
+		if (log) log->push_back({move, pot_trial, bf, accepted, sys.observables->kinetic_energy});
+		move = PI_pick_NVT_move();
+	}
+	return true;
+}
+
+} // namespace mpmc_host

@@ -196,6 +196,35 @@ def h2_framework(ncell: int = 20, a: float = 4.0, n_h2: int = 400, seed: int = 2
     return _mk(np.eye(3) * L, np.concatenate(pos, axis=0), q, alpha, eps, sig, mass, mol, frozen, at, mt, opts)
 
 
+def uvt_pore(ncell: int = 5, n_h2: int = 6, seed: int = 3, pressure: float = 5.0, solver: dict | None = None) -> SiteSystem:
+    """Small grand-canonical test system: the config-4 framework with an open channel along z (so that insertions can be
+    accepted) and a few five-site H2 inside it; uVT with fugacity = pressure (no equation of state)."""
+    s = h2_framework(ncell=ncell, n_h2=n_h2, solver=solver if solver is not None else SOLVER_GS_RANKED_PALMO, ensemble="uvt", seed=seed)
+    L = ncell * 4.0
+    keep = ~((s.frozen == 1) & (np.abs(s.pos[:, 0]) < 5.5) & (np.abs(s.pos[:, 1]) < 5.5))
+    rs = np.random.RandomState(seed)
+    pos = s.pos.copy()
+    for m in range(1, n_h2 + 1):
+        idx = np.nonzero(s.mol == m)[0]
+        newc = np.array([rs.uniform(-3, 3), rs.uniform(-3, 3), -L / 2 + (m - 0.5) * L / n_h2])
+        pos[idx] += newc - pos[idx[0]]
+    t = SiteSystem(s.basis, pos[keep], s.charge_e[keep], s.alpha[keep], s.eps[keep], s.sigma[keep], s.mass[keep], s.mol[keep], s.frozen[keep],
+                   [a for a, k in zip(s.atomtype, keep) if k], [a for a, k in zip(s.moltype, keep) if k], dict(s.opts))
+    t.opts.update({"pressure": str(pressure), "h2_fugacity": "off", "insert_probability": "0.4", "move_factor": "0.05", "rot_factor": "0.05"})
+    return t
+
+
+def argon_dimer_pi() -> SiteSystem:
+    """sample-input/pi001-argon-dimer-2K as shipped by the reference (Ar-Ar-4A.pqr + equilibrate.in), rebuilt here: two LJ argon
+    atoms 4 A apart in a 10^4 A box at 2 K, bead perturbation probability 0.9, trial chain length 4."""
+    opts = {"job_name": "ArAr2K", "ensemble": "pi_nvt", "temperature": "2.0", "polarization": "off", "numsteps": "100000", "corrtime": "25",
+            "seed": "1", "move_factor": "0.03", "rot_factor": "1.0", "bead_perturb_probability": "0.90", "free_volume": "1.0e12",
+            "PI_trial_chain_length": "4", "pqr_restart": "ArAr2K.restart.pqr"}
+    pos = np.array([[-2.0, 0.0, 0.0], [2.0, 0.0, 0.0]])
+    return _mk(np.eye(3) * 10000.0, pos, np.zeros(2), np.zeros(2), np.full(2, AR["eps"]), np.full(2, AR["sigma"]), np.full(2, AR["mass"]),
+               [0, 1], [0, 0], ["Ar", "Ar"], ["Ar", "Ar"], opts)
+
+
 def polar_kat(solver: dict | None = None) -> SiteSystem:
     """104-site polarizable + Ewald known-answer system of SURVEY §8c: 4^3 frozen sites + 8 H2 on axis x, L = 16."""
     ncell, a, L = 4, 4.0, 16.0

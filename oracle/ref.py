@@ -35,6 +35,8 @@ def lib():
         L.mref_terms.argtypes = [C.c_void_p, C.c_int, _dp]
         L.mref_get_dipoles.argtypes = [C.c_void_p, C.c_int, _dp, _dp, _dp, _dp, _dp]
         L.mref_pi_energy.argtypes = [C.c_void_p, _dp]
+        L.mref_mc_trajectory.argtypes = [C.c_void_p, C.c_int, _dp]
+        L.mref_pi_trajectory.argtypes = [C.c_void_p, C.c_int, _dp]
         L.mref_pi_potential.argtypes = [C.c_void_p]
         L.mref_pi_potential.restype = C.c_double
         _lib = L
@@ -118,6 +120,20 @@ class RefSystem:
         if rc:
             raise RuntimeError("reference PI energy threw %d" % rc)
         return dict(potential=o[0], rd=o[1], coulombic=o[2], polar=o[3], vdw=o[4], kinetic=o[5], chain_mass_len2=o[6])
+
+    def mc_trajectory(self, nsteps: int):
+        log = np.zeros(5 * nsteps)
+        rc = lib().mref_mc_trajectory(self.h, nsteps, log)
+        if rc:
+            raise RuntimeError("reference mc loop threw %d" % rc)
+        return log.reshape(nsteps, 5)
+
+    def pi_trajectory(self, nsteps: int):
+        log = np.zeros(5 * nsteps)
+        rc = lib().mref_pi_trajectory(self.h, nsteps, log)
+        if rc:
+            raise RuntimeError("reference PI loop threw %d" % rc)
+        return log.reshape(nsteps, 5)
 
     def pi_potential(self) -> float:
         return lib().mref_pi_potential(self.h)

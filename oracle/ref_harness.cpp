@@ -224,4 +224,79 @@ double mref_pi_potential(void *h) {
 	return sc->PI_calculate_potential();
 }
 
+// The reference's own classic Markov chain, step by step: the body of System::mc() (System.MonteCarlo.cpp:38-94) driven from
+// here so that every step's move type, trial energy, Boltzmann factor and decision can be read as doubles (the reference only
+// prints 6-decimal averages at corrtime, and its bookkeeping writes through an unallocated struct in a non-MPI build).
+// log: 5 doubles per step = movetype, final_energy, boltzmann_factor, accepted, observables->N.
+int mref_mc_trajectory(void *h, int nsteps, double *log) {
+	SimulationControl *sc = (SimulationControl *)h;
+	System &s = sc->sys;
+	try {
+		Quiet q;
+		s.observables->volume = s.pbc.volume;
+		double initial_energy = s.mc_initial_energy(), final_energy = 0;
+		s.do_checkpoint();
+		for (int step = 1; step <= nsteps; step++) {
+			s.step = step;
+			initial_energy = s.observables->energy;
+			s.make_move();
+			final_energy = s.energy();
+			if (!std::isfinite(final_energy)) { s.observables->energy = MAXVALUE; s.nodestats->boltzmann_factor = 0; }
+			else s.boltzmann_factor(initial_energy, final_energy);
+			double *L = log + 5 * (step - 1);
+			L[0] = s.checkpoint->movetype; L[1] = final_energy; L[2] = s.nodestats->boltzmann_factor;
+			if ((s.get_rand() < s.nodestats->boltzmann_factor) && !s.iterator_failed) { L[3] = 1; s.do_checkpoint(); }
+			else { L[3] = 0; s.iterator_failed = 0; s.restore(); }
+			L[4] = s.observables->N;
+		}
+	} catch (int e) { return g_last_error = e; }
+	return 0;
+}
+
+// The reference's path-integral chain, step by step: the body of SimulationControl::PI_nvt_mc() (PathIntegral.cpp:31-196) without
+// the file output and statistics.  log: 5 doubles per step = move, trial potential, boltzmann_factor, accepted, kinetic energy.
+int mref_pi_trajectory(void *h, int nsteps, double *log) {
+	SimulationControl *sc = (SimulationControl *)h;
+	try {
+		Quiet q;
+		for (System *S : sc->systems) { S->observables->temperature = sc->sys.temperature; S->observables->volume = S->pbc.volume; }
+		if (!sc->sys.parallel_restarts) sc->PI_perturb_bead_COMs_ENTIRE_SYSTEM();
+		sc->PI_calculate_energy();
+		int move = sc->PI_pick_NVT_move();
+		sc->backup_observables_ALL_SYSTEMS();
+		auto &B = sc->BFC;
+		B.potential.current = sc->sys.observables->potential();
+		if (!std::isfinite(B.potential.current)) sc->sys.observables->energy = B.potential.current = MAXVALUE;
+		B.chain_mass_len2.current = 0; B.orient_mu_len2.current = 0;
+		for (int step = 1; step <= nsteps; step++) {
+			sc->sys.step = step;
+			B.potential.init = B.potential.current;
+			B.chain_mass_len2.init = (move == MOVETYPE_PERTURB_BEADS) ? sc->PI_chain_mass_length2() : 0;
+			B.orient_mu_len2.init = (move == MOVETYPE_PERTURB_BEADS) ? sc->PI_orientational_mu_length2() : 0;
+			sc->PI_make_move(move);
+			B.potential.trial = sc->PI_calculate_potential();
+			B.chain_mass_len2.trial = (move == MOVETYPE_PERTURB_BEADS) ? sc->PI_chain_mass_length2() : 0;
+			B.orient_mu_len2.trial = (move == MOVETYPE_PERTURB_BEADS) ? sc->PI_orientational_mu_length2() : 0;
+			double bf;
+			if (!std::isfinite(B.potential.trial)) { B.potential.trial = sc->sys.observables->energy = MAXVALUE; bf = 0; }
+			else bf = sc->PI_NVT_boltzmann_factor(B);
+			double *L = log + 5 * (step - 1);
+			L[0] = move; L[1] = B.potential.trial; L[2] = bf;
+			if ((Rando::rand() < bf) && (sc->systems[0]->iterator_failed == 0)) {
+				L[3] = 1;
+				B.potential.current = B.potential.trial;
+				sc->PI_calculate_energy();
+				sc->backup_observables_ALL_SYSTEMS();
+			} else {
+				L[3] = 0;
+				sc->restore_PI_systems();
+				*sc->sys.observables = *sc->sys.checkpoint->observables;
+			}
+			L[4] = sc->sys.observables->kinetic_energy;
+			move = sc->PI_pick_NVT_move();
+		}
+	} catch (int e) { return g_last_error = e; }
+	return 0;
+}
+
 } // extern "C"

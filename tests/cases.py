@@ -51,6 +51,40 @@ PI = {
 }
 
 
+# seeded Markov chains whose accept/reject trajectory must reproduce the reference's: name -> (builder, P, steps)
+def _traj_lj():
+    s = W.lj_lattice(6, 24.0, jitter=0.3, round4=False)
+    s.opts.update({"ensemble": "nvt", "temperature": "87.0", "seed": "7", "move_factor": "0.02", "rot_factor": "0.1", "numsteps": "10000"})
+    return s
+
+
+def _traj_kat():
+    s = W.polar_kat(W.SOLVER_GS_RANKED_PALMO)
+    s.opts.update({"ensemble": "nvt", "seed": "5", "move_factor": "0.06", "rot_factor": "0.1", "numsteps": "10000"})
+    return s
+
+
+def _traj_uvt():
+    s = W.uvt_pore()
+    s.opts.update({"seed": "11", "numsteps": "4000"})
+    return s
+
+
+def _traj_pi_h2():
+    tmpl, _ = W.pi_h2_cluster(n_side=3, P=8, L=40.0)
+    tmpl.opts.update({"seed": "3", "numsteps": "5000", "PI_trial_chain_length": "3"})
+    return tmpl
+
+
+TRAJ = {
+    "traj_nvt_lj216": (_traj_lj, 0, 10000),
+    "traj_nvt_kat_gs_ranked": (_traj_kat, 0, 10000),
+    "traj_uvt_pore": (_traj_uvt, 0, 4000),
+    "traj_pi_argon_dimer": (W.argon_dimer_pi, 8, 10000),
+    "traj_pi_h2_27x8": (_traj_pi_h2, 8, 5000),
+}
+
+
 def displaced(s, seed=99):
     """Move the last mobile molecule rigidly (a displace move, System.MonteCarlo.cpp:875) — deterministic."""
     rs = np.random.RandomState(seed)
@@ -67,3 +101,10 @@ def load_golden(name):
                      [str(a) for a in z["atomtype"]], [str(a) for a in z["moltype"]], json.loads(str(z["opts"])))
     refd = {k: z[k] for k in z.files if k.startswith(("ref_", "cell_")) or k in ("moved_pos", "beads")}
     return s, refd
+
+
+def load_golden_traj(name):
+    z = np.load(os.path.join(GOLDEN_DIR, name + ".npz"))
+    s = W.SiteSystem(z["basis"], z["pos"], z["charge_e"], z["alpha"], z["eps"], z["sigma"], z["mass"], z["mol"], z["frozen"],
+                     [str(a) for a in z["atomtype"]], [str(a) for a in z["moltype"]], json.loads(str(z["opts"])))
+    return s, {"P": z["P"], "traj": z["traj"]}

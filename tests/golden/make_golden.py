@@ -60,5 +60,22 @@ def main():
         print("%-22s P=%d n=%4d  U=%.15g  K=%.15g" % (name, P, tmpl.n, e["potential"], e["kinetic"]))
 
 
+def trajectories():
+    """Seeded runs of the reference's own Markov chains (System::mc loop body / PI_nvt_mc loop body replayed by the harness)."""
+    for name, (build, P, steps) in cases.TRAJ.items():
+        s = build()
+        r = ref.RefSystem(s, P=P)
+        traj = r.pi_trajectory(steps) if P else r.mc_trajectory(steps)
+        out = pack_system(s)
+        out["P"] = np.int32(P)
+        out["traj"] = traj
+        np.savez_compressed(os.path.join(HERE, name + ".npz"), **out)
+        print("%-24s steps=%d acceptance=%.3f moves=%s" % (name, steps, traj[:, 3].mean(), np.bincount(traj[:, 0].astype(int)).tolist()))
+
+
 if __name__ == "__main__":
+    if len(sys.argv) > 1 and sys.argv[1] == "traj":
+        trajectories()
+        sys.exit(0)
     main()
+    trajectories()
