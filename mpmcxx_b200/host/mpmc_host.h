@@ -35,7 +35,8 @@ constexpr int internal_error = 101, invalid_monte_carlo_move = 102, fopen_fail_r
 // src/Rando.h: one global engine shared by a uniform and a (stateful) normal distribution
 class Rando {
 public:
-	static void seed(unsigned int s) { mt.seed(s); }
+	// reset(): a fresh reference process starts with no cached Box-Muller value; seeding here restores exactly that state
+	static void seed(unsigned int s) { mt.seed(s); normal_distribution.reset(); uniform_distribution.reset(); }
 	static double rand() { return uniform_distribution(mt); }
 	static double rand_normal() { return normal_distribution(mt); }
 private:

@@ -380,7 +380,12 @@ void SimulationControl::PI_perturb_bead_COMs(int n) {
 		const double init_factor = tB-- / tA--;
 		const double term_factor = 1.0 - init_factor;
 		const double sigma_factor = std::sqrt((hBar2 * beta * init_factor) / (P * Mass)) * METER2ANGSTROM;
-		const double px = Rando::rand_normal(), py = Rando::rand_normal(), pz = Rando::rand_normal();
+		// The reference builds `Vector3D perturbation(rand_normal(), rand_normal(), rand_normal())` (:1523): the order in which a
+		// compiler evaluates call arguments is unspecified, and the g++ build that serves as the oracle evaluates them right to
+		// left, so the FIRST draw is z.  Reproduced here explicitly.
+		const double pz = Rando::rand_normal();
+		const double py = Rando::rand_normal();
+		const double px = Rando::rand_normal();
 		const double pert[3] = {px, py, pz};
 		for (int p = 0; p < 3; p++) b[3 * bead + p] = (init_factor * b[3 * prev + p] + term_factor * b[3 * last + p]) + sigma_factor * pert[p];
 		prev = (prev + 1) % nSys;

@@ -60,20 +60,31 @@ def main():
         print("%-22s P=%d n=%4d  U=%.15g  K=%.15g" % (name, P, tmpl.n, e["potential"], e["kinetic"]))
 
 
+def one_trajectory(name):
+    build, P, steps = cases.TRAJ[name]
+    s = build()
+    r = ref.RefSystem(s, P=P)
+    traj = r.pi_trajectory(steps) if P else r.mc_trajectory(steps)
+    out = pack_system(s)
+    out["P"] = np.int32(P)
+    out["traj"] = traj
+    np.savez_compressed(os.path.join(HERE, name + ".npz"), **out)
+    print("%-24s steps=%d acceptance=%.3f moves=%s" % (name, steps, traj[:, 3].mean(), np.bincount(traj[:, 0].astype(int)).tolist()), flush=True)
+
+
 def trajectories():
-    """Seeded runs of the reference's own Markov chains (System::mc loop body / PI_nvt_mc loop body replayed by the harness)."""
-    for name, (build, P, steps) in cases.TRAJ.items():
-        s = build()
-        r = ref.RefSystem(s, P=P)
-        traj = r.pi_trajectory(steps) if P else r.mc_trajectory(steps)
-        out = pack_system(s)
-        out["P"] = np.int32(P)
-        out["traj"] = traj
-        np.savez_compressed(os.path.join(HERE, name + ".npz"), **out)
-        print("%-24s steps=%d acceptance=%.3f moves=%s" % (name, steps, traj[:, 3].mean(), np.bincount(traj[:, 0].astype(int)).tolist()))
+    """Seeded runs of the reference's own Markov chains (System::mc loop body / PI_nvt_mc loop body replayed by the harness).
+    One fresh process per case: the reference's global Rando keeps a cached Box-Muller value inside its normal_distribution
+    (src/Rando.h:12-14) that Rando::seed does not clear, so a run's draws depend on what the process did before."""
+    import subprocess
+    for name in cases.TRAJ:
+        subprocess.run([sys.executable, os.path.abspath(__file__), "traj1", name], check=True)
 
 
 if __name__ == "__main__":
+    if len(sys.argv) > 2 and sys.argv[1] == "traj1":
+        one_trajectory(sys.argv[2])
+        sys.exit(0)
     if len(sys.argv) > 1 and sys.argv[1] == "traj":
         trajectories()
         sys.exit(0)

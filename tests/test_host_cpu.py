@@ -1,0 +1,53 @@
+"""CPU-side checks of the C++ host mirror: it builds and loads, parses the reference's input keywords, and fails with the
+reference's own error codes (src/constants.h:108-147) before any device work; with no GPU the energy call fails loudly."""
+import os
+
+import pytest
+
+from mpmcxx_b200 import host_binding, workloads as W
+
+
+def _job(tmp_path, system, extra=None, drop=()):
+    s = system.copy()
+    s.opts.update({"seed": "1", "numsteps": "5"})
+    s.opts.update(extra or {})
+    for k in drop:
+        s.opts.pop(k, None)
+    return W.write_reference_job(s, str(tmp_path))
+
+
+def _code(fn):
+    with pytest.raises(RuntimeError) as ei:
+        fn()
+    return int(str(ei.value).split()[-1])
+
+
+def test_parser_error_codes(tmp_path):
+    lj = W.lj_lattice(3, 20.0)
+    inp = _job(tmp_path / "a", lj, {"no_such_keyword": "1"})
+    assert _code(lambda: host_binding.run(inp)) == 3000              # invalid_input
+    inp = _job(tmp_path / "b", lj, drop=("temperature",))
+    with open(inp) as f:
+        text = "".join(l for l in f if not l.startswith("temperature"))
+    open(inp, "w").write(text)
+    assert _code(lambda: host_binding.run(inp)) == 4003              # missing_setting
+    inp = _job(tmp_path / "c", lj, {"feynman_hibbs": "on"})
+    assert _code(lambda: host_binding.run(inp)) == 4004              # unsupported_setting
+    tmpl, _ = W.pi_h2_cluster(n_side=2, P=8, L=30.0)
+    inp = _job(tmp_path / "d", tmpl)
+    assert _code(lambda: host_binding.run(inp, P=6)) == 12000        # Trotter number must be a power of two >= 4
+    inp = _job(tmp_path / "e", tmpl, {"PI_trial_chain_length": "8"})
+    assert _code(lambda: host_binding.run(inp, P=8)) == 4000         # chain length must be < P
+
+
+def test_no_gpu_means_loud_failure(tmp_path):
+    import ctypes as C
+    from mpmcxx_b200 import engine
+    n = C.c_int(0)
+    have_gpu = engine.lib().mpmc_device_count(C.byref(n)) == 0 and n.value > 0
+    inp = _job(tmp_path, W.lj_lattice(3, 20.0))
+    if have_gpu:
+        assert host_binding.energy(inp)["rd"] < 0
+    else:
+        assert _code(lambda: host_binding.energy(inp)) == 30000       # MPMC_ERR_CUDA: no CPU fallback
+    assert os.path.exists(os.path.join(os.path.dirname(host_binding.__file__), "mpmcxx-b200"))
