@@ -128,6 +128,7 @@ struct mpmc_engine {
 	std::vector<int> h_mol, h_frozen;
 	// derived host state
 	std::vector<int2> tiles;
+	int pair_tile = kPairTile;       // tile side of the pair sweep chosen for this system size
 	std::vector<int> plist, mobile_q, frozen_q, mol_start;
 	std::vector<unsigned char> blk_frozen, mol_mobile;
 	double lrc_pair = 0, lrc_self = 0, es_self = 0, n_pair_evals = 0;
@@ -306,17 +307,23 @@ int rebuild_topology(mpmc_engine *e) {
 		for (int i = b * kOrdI; i < std::min(n, (b + 1) * kOrdI); i++) all = all && e->h_frozen[i];
 		e->blk_frozen[b] = all;
 	}
-	const int nt = (n + kPairTile - 1) / kPairTile;
-	std::vector<unsigned char> tile_frozen(std::max(nt, 1), 0);
-	for (int t = 0; t < nt; t++) {
-		bool all = true;
-		for (int i = t * kPairTile; i < std::min(n, (t + 1) * kPairTile); i++) all = all && e->h_frozen[i];
-		tile_frozen[t] = all;
+	// tile side: the largest of 128/64/32 that still gives >= 16 CTAs per SM (balance matters more than tile reuse: the sweep is
+	// FP64-bound and a tile's loads are 2/T of its work)
+	for (int T : {128, 64, 32}) {
+		e->pair_tile = T;
+		const int nt = (n + T - 1) / T;
+		std::vector<unsigned char> tile_frozen(std::max(nt, 1), 0);
+		for (int t = 0; t < nt; t++) {
+			bool all = true;
+			for (int i = t * T; i < std::min(n, (t + 1) * T); i++) all = all && e->h_frozen[i];
+			tile_frozen[t] = all;
+		}
+		e->tiles.clear();
+		for (int ta = 0; ta < nt; ta++)
+			for (int tb = ta; tb < nt; tb++)
+				if (!(tile_frozen[ta] && tile_frozen[tb])) e->tiles.push_back(make_int2(ta, tb));
+		if ((long long)e->tiles.size() * e->B >= 16LL * e->num_sms) break;
 	}
-	e->tiles.clear();
-	for (int a = 0; a < nt; a++)
-		for (int b = a; b < nt; b++)
-			if (!(tile_frozen[a] && tile_frozen[b])) e->tiles.push_back(make_int2(a, b));
 	// work lists
 	e->plist.clear(); e->mobile_q.clear(); e->frozen_q.clear(); e->mol_start.clear(); e->mol_mobile.clear();
 	long long nfrozen = 0;
@@ -637,11 +644,13 @@ static int enqueue_energy(mpmc_engine *e) {
 	if ((rc = e->d_partials.ensure((size_t)B * std::max(ntiles, 1)))) return rc;
 	if (ntiles) {
 { Timed _t(e, MPMC_K_PAIR);
-		if (es) k_pair_energy<ORTHO, true><<<dim3(ntiles, B), kPairTile, 0, e->stream>>>(e->d_posq.p, e->d_lj.p, e->d_meta.p, n, e->cap, e->d_tiles.p, ntiles, e->cell, e->d_partials.p);
-		else    k_pair_energy<ORTHO, false><<<dim3(ntiles, B), kPairTile, 0, e->stream>>>(e->d_posq.p, e->d_lj.p, e->d_meta.p, n, e->cap, e->d_tiles.p, ntiles, e->cell, e->d_partials.p);
+#define PAIR_LAUNCH(ESV, TV) k_pair_energy<ORTHO, ESV, TV><<<dim3(ntiles, B), TV, 0, e->stream>>>(e->d_posq.p, e->d_lj.p, e->d_meta.p, n, e->cap, e->d_tiles.p, ntiles, e->cell, e->d_partials.p)
+		if (e->pair_tile == 128) { if (es) PAIR_LAUNCH(true, 128); else PAIR_LAUNCH(false, 128); }
+		else if (e->pair_tile == 64) { if (es) PAIR_LAUNCH(true, 64); else PAIR_LAUNCH(false, 64); }
+		else { if (es) PAIR_LAUNCH(true, 32); else PAIR_LAUNCH(false, 32); }
+#undef PAIR_LAUNCH
 		LAUNCHED(e);
  }	}
-	CK(cudaMemsetAsync(e->d_result.p, 0, sizeof(double) * res_len(B), e->stream));
 	k_reduce_partials<<<B, 256, 0, e->stream>>>(e->d_partials.p, ntiles, e->d_result.p);
 	LAUNCHED(e);
 	if (es) {

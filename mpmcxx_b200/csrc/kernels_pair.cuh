@@ -6,7 +6,7 @@
 
 namespace mpmc {
 
-constexpr int kPairTile = 128;   // sites per tile side of the triangular energy sweep (= threads per CTA)
+constexpr int kPairTile = 128;   // largest tile side of the triangular energy sweep (= threads per CTA); 64 and 32 are used for small systems
 
 // site metadata word: molecule index in the low 31 bits, frozen flag in the sign bit
 __device__ __forceinline__ int  meta_mol(int m)    { return m & 0x7fffffff; }
@@ -19,23 +19,24 @@ struct PairPartial { double rd, es_real, es_intra, n_in; };
 // K1/K2: lj() + coulombic_real()  (reference src/System.Energy.cpp:897-1032, 1466-1517) over the pairs i<j that
 // pairs() would visit (src/System.cpp:967-991).  One CTA per (tile_i <= tile_j) entry of the host-built tile list
 // (tiles whose two blocks are entirely frozen are not listed: pair->frozen pairs contribute nothing, :936, :1487).
-// Thread t owns site i = tile_i*128 + t in registers and walks the j tile in shared memory.
+// Thread t owns site i = tile_i*T + t in registers and walks the j tile in shared memory.  The tile side T (128, 64 or 32) is
+// chosen by the host so that there are enough CTAs to fill and balance 148 SMs even for a few hundred sites per bead.
 // ---------------------------------------------------------------------------------------------------------
-template <bool ORTHO, bool ES>
-__global__ void __launch_bounds__(kPairTile)
+template <bool ORTHO, bool ES, int T>
+__global__ void __launch_bounds__(T)
 k_pair_energy(const double4 *__restrict__ posq, const double2 *__restrict__ lj, const int *__restrict__ meta,
               int n, int stride, const int2 *__restrict__ tiles, int ntiles, CellDev c, PairPartial *__restrict__ partials) {
-	__shared__ double4 s_pq[kPairTile];
-	__shared__ double2 s_lj[kPairTile];
-	__shared__ int     s_meta[kPairTile];
-	__shared__ double  s_red[4][kPairTile / 32];
+	__shared__ double4 s_pq[T];
+	__shared__ double2 s_lj[T];
+	__shared__ int     s_meta[T];
+	__shared__ double  s_red[4][T / 32];
 
 	const int bead = blockIdx.y;
 	const int2 tile = tiles[blockIdx.x];
 	const double4 *pq = posq + (size_t)bead * stride;
 	const int tid = threadIdx.x;
-	const int i = tile.x * kPairTile + tid;
-	const int j0 = tile.y * kPairTile;
+	const int i = tile.x * T + tid;
+	const int j0 = tile.y * T;
 
 	double4 pi = make_double4(0, 0, 0, 0);
 	double2 li = make_double2(0, 0);
@@ -48,7 +49,7 @@ k_pair_energy(const double4 *__restrict__ posq, const double2 *__restrict__ lj, 
 	__syncthreads();
 
 	double a_rd = 0, a_re = 0, a_in = 0, a_cnt = 0;
-	const int jn = min(kPairTile, n - j0);
+	const int jn = min(T, n - j0);
 	const int jstart = (tile.x == tile.y) ? tid + 1 : 0;
 	const double rc = c.cutoff, alpha = c.ewald_alpha;
 	if (i < n) {
@@ -90,7 +91,7 @@ k_pair_energy(const double4 *__restrict__ posq, const double2 *__restrict__ lj, 
 	__syncthreads();
 	if (tid == 0) {
 		PairPartial p = {0, 0, 0, 0};
-		for (int k = 0; k < kPairTile / 32; k++) { p.rd += s_red[0][k]; p.es_real += s_red[1][k]; p.es_intra += s_red[2][k]; p.n_in += s_red[3][k]; }
+		for (int k = 0; k < T / 32; k++) { p.rd += s_red[0][k]; p.es_real += s_red[1][k]; p.es_intra += s_red[2][k]; p.n_in += s_red[3][k]; }
 		partials[(size_t)bead * ntiles + blockIdx.x] = p;
 	}
 }
@@ -113,7 +114,7 @@ k_reduce_partials(const PairPartial *__restrict__ partials, int ntiles, double *
 		if (tid < o) for (int q = 0; q < 4; q++) s_red[q][tid] += s_red[q][tid + o];
 		__syncthreads();
 	}
-	if (tid < 4) res[bead * kResStride + tid] = s_red[tid][0];
+	if (tid < kResStride) res[bead * kResStride + tid] = tid < 4 ? s_red[tid][0] : 0.0;   // slots 4..7 are filled by later kernels
 }
 
 // PI_calculate_potential (SimulationControl.PathIntegral.cpp:786-796): sums over this engine's bead systems of
