@@ -349,16 +349,24 @@ def run_ours(args):
            "roofline": roof}
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         out["cpu_baseline"] = cpu_baseline(args.workload, args.solver, args.steps, budget_s=args.cpu_budget)
+    eng.close()
     if rank == 0 and world == 1 and not args.no_extra:
         out["extra"] = extra_workloads(engine, local, peak_tflops)
+    if not args.no_extra:
+        # BASELINE config 5, the bead-sharded path-integral workload (STRONG scaling over the same N GPUs; one NCCL all-reduce per sweep)
+        import copy
+        a2 = copy.copy(args)
+        a2.workload, a2.steps, a2.warmup = "pi_h2_five", 100, 10
+        pi_res = run_pi(a2, embedded=True)
+        if rank == 0:
+            out.setdefault("extra", {})["pi_h2_five_bead_sharded"] = {k: pi_res[k] for k in ("value", "unit", "n_gpus", "ms_per_step", "scaling", "config", "e2e", "pair_evals_per_sec")}
     if rank == 0:
         print(json.dumps(out, default=_np_default))
-    eng.close()
     if world > 1:
         dist.destroy_process_group()
 
 
-def run_pi(args):
+def run_pi(args, embedded=False):
     """BASELINE config 5: path-integral H2 cluster, 512 molecules x P=64 beads, beads sharded over the GPUs (strong scaling).
     One move = bead-chain perturbation or rigid displacement of one molecule in every bead system -> mpmc_update_sites_all_beads ->
     mpmc_pi_potential_allreduce (local sweep + ONE ncclAllReduce of 4 doubles) -> bead-spring term of the moved molecule on the host ->
@@ -369,7 +377,7 @@ def run_pi(args):
 
     rank, world, local = env_int("RANK", 0), env_int("WORLD_SIZE", 1), env_int("LOCAL_RANK", 0)
     torch.cuda.set_device(local)
-    if world > 1:
+    if world > 1 and not embedded:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 
     def barrier():
@@ -479,9 +487,11 @@ def run_pi(args):
            "roofline": {"kernel": "pair", "bound": "fp64", "achieved": ach, "peak": peak_tflops, "unit": "TFLOP/s", "frac": ach / peak_tflops, "traffic": None,
                         "ms_per_launch": kms, "peak_source": "measured in this run (DFMA probe)",
                         "kernel_ms_per_step": {k: v[0] / args.steps for k, v in timing.items() if v[1]}}}
+    eng.close()
+    if embedded:
+        return res
     if rank == 0:
         print(json.dumps(res, default=_np_default))
-    eng.close()
     if world > 1:
         dist.destroy_process_group()
 
