@@ -31,7 +31,7 @@ def _stale(target: str, sources) -> bool:
 
 
 def engine_sources():
-    srcs = [os.path.join(CSRC, f) for f in sorted(os.listdir(CSRC)) if f.endswith((".cu", ".cuh"))]
+    srcs = [os.path.join(CSRC, f) for f in sorted(os.listdir(CSRC)) if f.endswith((".cu", ".cuh", ".h"))]
     srcs.append(os.path.join(ROOT, "include", "mpmc_b200.h"))
     return srcs
 

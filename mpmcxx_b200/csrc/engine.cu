@@ -15,7 +15,9 @@
 
 #include <algorithm>
 #include <cmath>
+#include <cstdint>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <map>
 #include <string>
@@ -23,6 +25,7 @@
 
 #include "kernels_gs.cuh"
 #include "kernels_pair.cuh"
+#include "kernels_pair2.cuh"
 #include "kernels_polar.cuh"
 #include "kernels_recip.cuh"
 
@@ -139,6 +142,15 @@ struct mpmc_engine {
 	DevBuf<double> d_alpha, d_mass;
 	DevBuf<int> d_meta, d_plist, d_mobile_q, d_frozen_q, d_mol_start, d_order, d_flags;
 	DevBuf<int2> d_tiles;
+	// second-generation pair sweep (kernels_pair2.cuh)
+	bool pair_v1 = false;            // developer switch (env MPMC_PAIR_V1=1): the first-generation tile kernel, for A/B timing
+	std::vector<PairSeg> segs;
+	PairParams pp;
+	RadialTable erf_tab;
+	DevBuf<PairSeg> d_segs;
+	DevBuf<int> d_pmeta, d_item_seg;
+	DevBuf<double> d_erf_tab;
+	int pair_grid = 0;
 	DevBuf<unsigned char> d_blk_frozen, d_mol_mobile;
 	DevBuf<KVec> d_kvec;
 	DevBuf<PairPartial> d_partials;
@@ -280,6 +292,8 @@ double lrc_formula(double eps, double sigma, double cutoff, double volume) {
 	return ((16.0 / 3.0) * kPi * eps * sig3) * ((1.0 / 3.0) * sig_cut9 - sig_cut3) / volume;
 }
 
+int prepare_pair_sweep(mpmc_engine *e);
+
 // Everything that depends on the site table but not on coordinates: device parameter arrays, work lists and the
 // configuration-independent energy terms (pair/self LRC, Ewald point-self term).
 int rebuild_topology(mpmc_engine *e) {
@@ -345,6 +359,7 @@ int rebuild_topology(mpmc_engine *e) {
 	    (rc = up(e->d_frozen_q, e->frozen_q)) || (rc = up(e->d_mol_start, e->mol_start)) || (rc = up(e->d_blk_frozen, e->blk_frozen)) ||
 	    (rc = up(e->d_mol_mobile, e->mol_mobile))) return rc;
 	CK(cudaStreamSynchronize(e->stream));   // the std::vectors above go out of scope / may be rebuilt
+	if ((rc = prepare_pair_sweep(e))) return rc;
 
 	// configuration-independent terms, by (eps, sigma) type instead of by pair.  Pair LRC covers every non-frozen pair with
 	// eps_ij != 0 and sigma_ij != 0, intramolecular pairs included (System.Energy.cpp:1045-1050); self LRC every non-frozen
@@ -375,6 +390,93 @@ int rebuild_topology(mpmc_engine *e) {
 			if (!e->h_frozen[i]) e->es_self -= c.ewald_alpha * e->h_q[i] * e->h_q[i] / std::sqrt(kPi);   // System.Energy.cpp:1626-1643
 	e->topo_dirty = false;
 	e->frozen_sk_dirty = true;
+	return MPMC_OK;
+}
+
+// ---- second-generation pair sweep: host-side preparation (kernels_pair2.cuh) ----
+// Largest double x in [0, hi] for which pred holds, for a predicate that is true up to some point and false beyond
+// (positive doubles order like their bit patterns, so this is a bisection on the bits).
+template <class P> double largest_true(P pred, double hi) {
+	auto bits = [](double v) { uint64_t b; memcpy(&b, &v, 8); return b; };
+	auto val = [](uint64_t b) { double v; memcpy(&v, &b, 8); return v; };
+	if (pred(hi)) return hi;
+	uint64_t lo = 0, up = bits(hi);
+	while (up - lo > 1) {
+		const uint64_t mid = lo + (up - lo) / 2;
+		if (pred(val(mid))) lo = mid; else up = mid;
+	}
+	return val(lo);
+}
+
+int prepare_pair_sweep(mpmc_engine *e) {
+	const int n = e->n;
+	const CellDev &c = e->cell;
+	PairParams &pp = e->pp;
+	// the reference's cutoff tests as thresholds on r^2 (both act on rimg = sqrt(r^2), correctly rounded on the reference's host and here)
+	const volatile double rc = c.cutoff;
+	const double top = 4.0 * c.cutoff * c.cutoff + 1.0;
+	pp.t2_lj = largest_true([&](double x) { volatile double r = std::sqrt(x); volatile double d = r - kSmallDr; return d < rc; }, top);   // System.Energy.cpp:934
+	pp.t2_es = largest_true([&](double x) { volatile double r = std::sqrt(x); return !(r > rc); }, top);                                  // :1490
+	pp.t2_adm = pp.t2_lj * (1.0 + 1e-9);
+	pp.t2_safe = std::min(pp.t2_es, pp.t2_lj) * (1.0 - 1e-9);
+	int rc2;
+	const bool es = !e->cfg.rd_only;
+	if (es) {
+		const long double alpha = c.ewald_alpha;
+		e->erf_tab.build(1, std::min(0.25, pp.t2_adm / 64.0), pp.t2_adm * 1.001, [&](long double u, long double *o) {
+			const long double r = sqrtl(u);
+			o[0] = erfcl(alpha * r) / r;
+		});
+		pp.u_tab_lo = e->erf_tab.u_lo; pp.tab_base = e->erf_tab.base; pp.tab_rows = e->erf_tab.nrows;
+		if ((rc2 = e->d_erf_tab.ensure(e->erf_tab.rows.size()))) return rc2;
+		CK(cudaMemcpyAsync(e->d_erf_tab.p, e->erf_tab.rows.data(), e->erf_tab.rows.size() * sizeof(double), cudaMemcpyHostToDevice, e->stream));
+	} else { pp.u_tab_lo = 0; pp.tab_base = 0; pp.tab_rows = 0; }
+	// per-site word and the column segments: i-group g meets every later site, except that an all-frozen group skips all-frozen blocks
+	std::vector<int> pm(n);
+	for (int i = 0; i < n; i++) {
+		const bool lj_on = e->h_eps[i] != 0.0 && e->h_sigma[i] > 0.0;
+		const int molw = e->h_frozen[i] ? kPmFrozenMol : e->h_mol[i];
+		pm[i] = (molw << kPmMolShift) | (lj_on ? kPmLJ : 0) | (e->h_q[i] != 0.0 ? kPmQ : 0) | (e->h_frozen[i] ? (int)0x80000000u : 0);
+	}
+	if (e->h_mol[n - 1] >= kPmFrozenMol) FAIL(MPMC_ERR_INVALID_INPUT, "more than 2^28 - 1 molecules");
+	e->segs.clear();
+	const int ng = (n + 31) / 32;
+	int col = 0;
+	for (int g = 0; g < ng; g++) {
+		const int jb = g * 32 + 1;
+		if (jb >= n) break;
+		if (!e->blk_frozen[g]) { e->segs.push_back({g, jb, n, col}); col += n - jb; continue; }
+		int b = g + 1;                       // the group's own block is all frozen: nothing there
+		while (b < ng) {
+			while (b < ng && e->blk_frozen[b]) b++;
+			if (b >= ng) break;
+			int b2 = b;
+			while (b2 < ng && !e->blk_frozen[b2]) b2++;
+			const int ja = b * 32, jz = std::min(n, b2 * 32);
+			e->segs.push_back({g, ja, jz, col}); col += jz - ja;
+			b = b2;
+		}
+	}
+	pp.ncols = col; pp.nseg = (int)e->segs.size();
+	const int ctas = e->num_sms * pair_ctas_per_sm(es);
+	const int warps = ctas * kPwWarps;
+	int K = std::max(1, warps / e->B);
+	K = std::min(K, std::max(1, (col + 15) / 16));        // at least 16 columns per item
+	pp.items_per_bead = K;
+	pp.cols_per_item = std::max(1, (col + K - 1) / K);
+	e->pair_grid = std::max(1, std::min(ctas, (e->B * K + kPwWarps - 1) / kPwWarps));
+	std::vector<int> item_seg(K, 0);
+	for (int k = 0, sgi = 0; k < K; k++) {
+		const int c0 = k * pp.cols_per_item;
+		while (sgi + 1 < pp.nseg && e->segs[sgi + 1].col0 <= c0) sgi++;
+		item_seg[k] = sgi;
+	}
+	if ((rc2 = e->d_item_seg.ensure(K))) return rc2;
+	CK(cudaMemcpyAsync(e->d_item_seg.p, item_seg.data(), K * sizeof(int), cudaMemcpyHostToDevice, e->stream));
+	if ((rc2 = e->d_pmeta.ensure(std::max(n, 1))) || (rc2 = e->d_segs.ensure(std::max<size_t>(e->segs.size(), 1)))) return rc2;
+	CK(cudaMemcpyAsync(e->d_pmeta.p, pm.data(), n * sizeof(int), cudaMemcpyHostToDevice, e->stream));
+	if (!e->segs.empty()) CK(cudaMemcpyAsync(e->d_segs.p, e->segs.data(), e->segs.size() * sizeof(PairSeg), cudaMemcpyHostToDevice, e->stream));
+	CK(cudaStreamSynchronize(e->stream));
 	return MPMC_OK;
 }
 
@@ -640,7 +742,16 @@ static int enqueue_energy(mpmc_engine *e) {
 	Timed _whole(e, MPMC_K_ENERGY_TOTAL);
 	const bool es = !cf.rd_only;
 	// pair sweep: lj() + coulombic_real()
-	const int ntiles = (int)e->tiles.size();
+	int ntiles = (int)e->tiles.size();
+	if (!e->pair_v1) {
+		ntiles = e->pp.items_per_bead;
+		if ((rc = e->d_partials.ensure((size_t)B * std::max(ntiles, 1)))) return rc;
+		const size_t smem = pair_sweep_smem(es, e->pp.tab_rows);
+		Timed _t(e, MPMC_K_PAIR);
+		if (es) k_pair_sweep<ORTHO, true><<<e->pair_grid, kPwThreads, smem, e->stream>>>(e->d_posq.p, e->d_lj.p, e->d_pmeta.p, n, e->cap, B, e->d_segs.p, e->d_item_seg.p, e->pp, e->cell, e->d_erf_tab.p, e->d_partials.p);
+		else k_pair_sweep<ORTHO, false><<<e->pair_grid, kPwThreads, smem, e->stream>>>(e->d_posq.p, e->d_lj.p, e->d_pmeta.p, n, e->cap, B, e->d_segs.p, e->d_item_seg.p, e->pp, e->cell, nullptr, e->d_partials.p);
+		LAUNCHED(e);
+	} else {
 	if ((rc = e->d_partials.ensure((size_t)B * std::max(ntiles, 1)))) return rc;
 	if (ntiles) {
 { Timed _t(e, MPMC_K_PAIR);
@@ -651,6 +762,7 @@ static int enqueue_energy(mpmc_engine *e) {
 #undef PAIR_LAUNCH
 		LAUNCHED(e);
  }	}
+	}
 	k_reduce_partials<<<B, 256, 0, e->stream>>>(e->d_partials.p, ntiles, e->d_result.p);
 	LAUNCHED(e);
 	if (es) {
@@ -717,6 +829,13 @@ int mpmc_create(const mpmc_config *cfg, mpmc_engine **out) {
 	if ((rc = set_smem(k_structure_partial, sizeof(double2) * kSkSites * 3 * (kMaxKmax + 1))) ||
 	    (rc = set_smem(k_field_recip, sizeof(double2) * kFrSites * 3 * (kMaxKmax + 1))) ||
 	    (rc = set_smem(k_gs_pipeline<true>, kGsSmemBytes)) || (rc = set_smem(k_gs_pipeline<false>, kGsSmemBytes))) { mpmc_destroy(e); return rc; }
+	{
+		const size_t pmax = pair_sweep_smem(true, 1024);     // tables of up to 1024 rows (64 octaves)
+		if ((rc = set_smem(k_pair_sweep<true, true>, pmax)) || (rc = set_smem(k_pair_sweep<false, true>, pmax)) ||
+		    (rc = set_smem(k_pair_sweep<true, false>, pmax)) || (rc = set_smem(k_pair_sweep<false, false>, pmax))) { mpmc_destroy(e); return rc; }
+		const char *v1 = getenv("MPMC_PAIR_V1");
+		e->pair_v1 = v1 && v1[0] == '1';
+	}
 	int occ = 0;
 	CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_gs_pipeline<false>, kGsThreads, kGsSmemBytes));
 	e->gs_grid = std::max(1, occ) * e->num_sms;
@@ -732,7 +851,7 @@ int mpmc_destroy(mpmc_engine *e) {
 	if (e->stream) cudaStreamSynchronize(e->stream);
 	e->d_posq.release(); e->d_lj.release(); e->d_alpha.release(); e->d_mass.release(); e->d_meta.release(); e->d_plist.release();
 	e->d_mobile_q.release(); e->d_frozen_q.release(); e->d_mol_start.release(); e->d_order.release(); e->d_flags.release();
-	e->d_tiles.release(); e->d_blk_frozen.release(); e->d_mol_mobile.release(); e->d_kvec.release(); e->d_partials.release();
+	e->d_tiles.release(); e->d_segs.release(); e->d_item_seg.release(); e->d_pmeta.release(); e->d_erf_tab.release(); e->d_blk_frozen.release(); e->d_mol_mobile.release(); e->d_kvec.release(); e->d_partials.release();
 	e->d_sk_part.release(); e->d_S_mobile.release(); e->d_S_frozen.release(); e->d_S_all.release();
 	e->d_efs.release(); e->d_efi.release(); e->d_efic.release(); e->d_mu.release(); e->d_new_mu.release(); e->d_old_mu.release();
 	e->d_rrms.release(); e->d_rank.release(); e->d_acc.release(); e->d_dmu.release(); e->d_tri.release(); e->d_gsctl.release(); e->d_com.release(); e->d_mol_mass.release(); e->d_chain.release();
