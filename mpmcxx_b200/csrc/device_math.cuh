@@ -8,6 +8,7 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <math.h>
+#include "radial_table.h"
 
 namespace mpmc {
 
@@ -28,6 +29,7 @@ struct PolarDev {
 	double damp;        // polar_damp (lambda)
 	double gamma;       // polar_gamma
 	double allowed_sqerr; // (polar_precision * DEBYE2SKA)^2, System.Energy.cpp:3228
+	double u_damp;      // (50 / lambda)^2: beyond this squared distance exponential damping is exactly 1 in double precision
 	int    damp_type;   // 0 off, 1 linear, 2 exponential
 	int    gs;          // polar_gs || polar_gs_ranked
 	int    sor, esor;
@@ -122,6 +124,66 @@ __device__ __forceinline__ void tensor_contract(const CellDev &c, const PolarDev
 	ax += a * mx - b * dx;
 	ay += a * my - b * dy;
 	az += a * mz - b * dz;
+}
+
+
+// ---- fast paths: FMA geometry + radial tables in r^2 (radial_table.h) ------------------------------------------------------
+// None of the polarization tensor work involves a cutoff decision, so nothing there depends on the last bit of the distance:
+// geometry may use FMA, and the radial factors come from tables.
+
+// minimum-image displacement for the vector/tensor kernels.  The IMAGE is chosen exactly as the reference chooses it — the
+// fractional coordinate is formed with the reference's roundings before rint (System.cpp:1228-1235), because for a pair that
+// sits half a cell apart (any lattice start) the two images are equally near and the choice flips the sign of that component of
+// dimg, hence of the field and of the off-diagonal tensor elements — while the back-projection d - basis^T img uses FMA (that
+// only moves the result by an ulp).
+template <bool ORTHO>
+__device__ __forceinline__ void min_image_fast(const CellDev &c, double dx, double dy, double dz, double &ix, double &iy, double &iz) {
+	if (ORTHO) {
+		const double fx = rint_magic(__dmul_rn(c.rb[0][0], dx)), fy = rint_magic(__dmul_rn(c.rb[1][1], dy)), fz = rint_magic(__dmul_rn(c.rb[2][2], dz));
+		ix = fma(-c.b[0][0], fx, dx); iy = fma(-c.b[1][1], fy, dy); iz = fma(-c.b[2][2], fz, dz);
+	} else {
+		const double f0 = rint_magic(__dadd_rn(__dadd_rn(__dmul_rn(c.rb[0][0], dx), __dmul_rn(c.rb[1][0], dy)), __dmul_rn(c.rb[2][0], dz)));
+		const double f1 = rint_magic(__dadd_rn(__dadd_rn(__dmul_rn(c.rb[0][1], dx), __dmul_rn(c.rb[1][1], dy)), __dmul_rn(c.rb[2][1], dz)));
+		const double f2 = rint_magic(__dadd_rn(__dadd_rn(__dmul_rn(c.rb[0][2], dx), __dmul_rn(c.rb[1][2], dy)), __dmul_rn(c.rb[2][2], dz)));
+		ix = fma(-c.b[2][0], f2, fma(-c.b[1][0], f1, fma(-c.b[0][0], f0, dx)));
+		iy = fma(-c.b[2][1], f2, fma(-c.b[1][1], f1, fma(-c.b[0][1], f0, dy)));
+		iz = fma(-c.b[2][2], f2, fma(-c.b[1][2], f1, fma(-c.b[0][2], f0, dz)));
+	}
+}
+
+// acc += T_ij mu_j like tensor_contract(), for the configuration the reference's `cuda on` validator demands (exponential
+// damping, thole_amatrix, System.Energy.cpp:2731-2742): FMA geometry, one rsqrt for every inverse power, and the damping
+// factors only where they differ from 1 in double precision: for lambda r >= 50 the terms e^{-lr}(l^2 r^2/2 + l r + 1) and
+// e^{-lr} l^3 r^3/6 are below 2^-54, so damp1 = damp2 = 1 exactly as the closed form would round.  (A radial table was tried
+// here and lost: two functions x 8 coefficients per lane make the shared-memory pipe, not the FP64 pipe, the bottleneck.)
+// ~37 FP64 instructions per far pair, ~65 per damped pair, against ~75 for every pair before.  u_damp = (50 / lambda)^2.
+template <bool ORTHO>
+__device__ __forceinline__ void tensor_contract_exp(const CellDev &c, double lambda, double u_damp, double xi, double yi, double zi,
+                                                    double xj, double yj, double zj, double mx, double my, double mz,
+                                                    double &ax, double &ay, double &az) {
+	double dx, dy, dz;
+	min_image_fast<ORTHO>(c, __dsub_rn(xi, xj), __dsub_rn(yi, yj), __dsub_rn(zi, zj), dx, dy, dz);
+	const double u = fma(dz, dz, fma(dy, dy, dx * dx));
+	// coincident sites (and the i == j column): the reference multiplies MAXVALUE by damping factors that are exactly 0 (:2704-2705)
+	const double ir = u > 0.0 ? rsqrt(u) : 0.0;
+	const double ir2 = ir * ir, ir3 = ir2 * ir;
+	double a = ir3, b = 3.0 * ir3 * ir2;
+	if (u < u_damp) {
+		const double lr = lambda * (u * ir);
+		const double e = exp(-lr);
+		const double damp1 = fma(-e, fma(0.5 * lr, lr, lr) + 1.0, 1.0);            // 1 - e (l^2 r^2 / 2 + l r + 1)
+		const double damp2 = fma(-e, lr * lr * lr * (1.0 / 6.0), damp1);           // damp1 - e l^3 r^3 / 6
+		a *= damp1; b *= damp2;
+	}
+	const double bd = b * fma(dz, mz, fma(dy, my, dx * mx));
+	ax = fma(-bd, dx, fma(a, mx, ax));
+	ay = fma(-bd, dy, fma(a, my, ay));
+	az = fma(-bd, dz, fma(a, mz, az));
+}
+
+// copy a table into shared memory (all threads of the CTA; the caller synchronises)
+__device__ __forceinline__ void stage_table(double *dst, const double *__restrict__ src, int len) {
+	for (int q = threadIdx.x; q < len; q += blockDim.x) dst[q] = src[q];
 }
 
 // deterministic warp reductions (xor tree: every lane ends with the same value)

@@ -27,6 +27,7 @@
 #include "kernels_pair.cuh"
 #include "kernels_pair2.cuh"
 #include "kernels_polar.cuh"
+#include "kernels_polar2.cuh"
 #include "kernels_recip.cuh"
 
 using namespace mpmc;
@@ -156,7 +157,11 @@ struct mpmc_engine {
 	DevBuf<PairPartial> d_partials;
 	DevBuf<double2> d_sk_part, d_S_mobile, d_S_frozen, d_S_all;
 	DevBuf<double> d_efs, d_efi, d_efic, d_mu, d_new_mu, d_old_mu, d_rrms, d_rank, d_acc, d_dmu, d_tri, d_com, d_mol_mass, d_chain;
-	DevBuf<int> d_gsctl;
+	DevBuf<int> d_gsctl, d_gmeta, d_nplist;
+	DevBuf<double4> d_gpq;
+	DevBuf<double> d_cparts;
+	std::vector<int> nplist;
+	int ct_parts = 1, ct_part_len = 0;
 	DevBuf<long long> d_gsprof;
 	bool gs_prof_enabled = false;
 	int gs_prof_nblk = 0;
@@ -293,6 +298,7 @@ double lrc_formula(double eps, double sigma, double cutoff, double volume) {
 }
 
 int prepare_pair_sweep(mpmc_engine *e);
+int prepare_polar(mpmc_engine *e);
 
 // Everything that depends on the site table but not on coordinates: device parameter arrays, work lists and the
 // configuration-independent energy terms (pair/self LRC, Ewald point-self term).
@@ -360,6 +366,7 @@ int rebuild_topology(mpmc_engine *e) {
 	    (rc = up(e->d_mol_mobile, e->mol_mobile))) return rc;
 	CK(cudaStreamSynchronize(e->stream));   // the std::vectors above go out of scope / may be rebuilt
 	if ((rc = prepare_pair_sweep(e))) return rc;
+	if ((rc = prepare_polar(e))) return rc;
 
 	// configuration-independent terms, by (eps, sigma) type instead of by pair.  Pair LRC covers every non-frozen pair with
 	// eps_ij != 0 and sigma_ij != 0, intramolecular pairs included (System.Energy.cpp:1045-1050); self LRC every non-frozen
@@ -476,6 +483,28 @@ int prepare_pair_sweep(mpmc_engine *e) {
 	if ((rc2 = e->d_pmeta.ensure(std::max(n, 1))) || (rc2 = e->d_segs.ensure(std::max<size_t>(e->segs.size(), 1)))) return rc2;
 	CK(cudaMemcpyAsync(e->d_pmeta.p, pm.data(), n * sizeof(int), cudaMemcpyHostToDevice, e->stream));
 	if (!e->segs.empty()) CK(cudaMemcpyAsync(e->d_segs.p, e->segs.data(), e->segs.size() * sizeof(PairSeg), cudaMemcpyHostToDevice, e->stream));
+	CK(cudaStreamSynchronize(e->stream));
+	return MPMC_OK;
+}
+
+// polarization work lists and the Thole radial table (kernels_polar2.cuh, kernels_gs.cuh)
+int prepare_polar(mpmc_engine *e) {
+	const mpmc_config &cf = e->cfg;
+	if (!cf.polarization || cf.rd_only) return MPMC_OK;
+	const int n = e->n, np = (int)e->plist.size();
+	int rc;
+	e->nplist.clear();
+	for (int i = 0; i < n; i++) if (e->h_alpha[i] == 0.0) e->nplist.push_back(i);
+	if ((rc = e->d_nplist.ensure(std::max<size_t>(e->nplist.size(), 1)))) return rc;
+	if (!e->nplist.empty()) CK(cudaMemcpyAsync(e->d_nplist.p, e->nplist.data(), e->nplist.size() * sizeof(int), cudaMemcpyHostToDevice, e->stream));
+	// column parts of the contraction sweeps: enough (32-row block x part) CTAs for ~8 per SM, parts a multiple of the 8 column lanes
+	const int row_blocks = std::max(1, (n + kOrdI - 1) / kOrdI) * e->B;
+	int parts = std::max(1, std::min(32, (8 * e->num_sms + row_blocks - 1) / row_blocks));
+	int len = (std::max(np, 1) + parts - 1) / parts;
+	len = std::max(kOrdJ, (len + kOrdJ - 1) / kOrdJ * kOrdJ);
+	parts = std::max(1, (std::max(np, 1) + len - 1) / len);
+	e->ct_parts = parts; e->ct_part_len = len;
+	if ((rc = e->d_cparts.ensure((size_t)parts * e->B * n * 3))) return rc;
 	CK(cudaStreamSynchronize(e->stream));
 	return MPMC_OK;
 }
@@ -604,6 +633,7 @@ static int run_polar(mpmc_engine *e) {
 	pd.damp = cf.polar_damp; pd.gamma = cf.polar_gamma; pd.damp_type = cf.damp_type;
 	pd.gs = cf.polar_gs || cf.polar_gs_ranked; pd.sor = cf.polar_sor; pd.esor = cf.polar_esor;
 	pd.allowed_sqerr = cf.polar_precision * cf.polar_precision * kDebye2Ska * kDebye2Ska;
+	pd.u_damp = cf.polar_damp > 0 ? (50.0 / cf.polar_damp) * (50.0 / cf.polar_damp) : 0.0;
 	const double gamma_init = (!cf.polar_sor && !cf.polar_esor) ? cf.polar_gamma : 1.0;
 	const int eb = 256;
 	k_dipole_init<<<(unsigned)((len + eb - 1) / eb), eb, 0, e->stream>>>(e->d_alpha.p, e->d_efs.p, n, B, gamma_init, e->d_mu.p, e->d_new_mu.p,
@@ -627,6 +657,25 @@ static int run_polar(mpmc_engine *e) {
 
 	const bool need_old = cf.polar_rrms || cf.polar_precision > 0 || cf.polar_sor || cf.polar_esor;
 	const bool want_check = cf.polar_rrms || cf.polar_precision > 0;
+	const bool expd = cf.damp_type == MPMC_DAMPING_EXPONENTIAL;
+	// one contraction sweep acc_i = sum_j T_ij mu_j over a row list, then the epilogue of `mode`
+	auto contract = [&](int mode, const int *rowlist, int nrows, double *out_acc) -> int {
+		if (nrows <= 0) return MPMC_OK;
+		const dim3 grid((nrows + kOrdI - 1) / kOrdI, e->ct_parts, B);
+		if (expd) k_contract_parts<ORTHO, true><<<grid, kOrdThreads, 0, e->stream>>>(e->d_posq.p, e->d_alpha.p, e->d_meta.p, e->d_plist.p, np, e->ct_part_len,
+		                                                                         rowlist, nrows, n, e->cap, e->cell, pd, e->d_mu.p, e->d_cparts.p);
+		else k_contract_parts<ORTHO, false><<<grid, kOrdThreads, 0, e->stream>>>(e->d_posq.p, e->d_alpha.p, e->d_meta.p, e->d_plist.p, np, e->ct_part_len,
+		                                                                        rowlist, nrows, n, e->cap, e->cell, pd, e->d_mu.p, e->d_cparts.p);
+		const int fb = 128, fg = (nrows * B + fb - 1) / fb;
+#define FINISH(M) k_contract_finish<M><<<fg, fb, 0, e->stream>>>(e->d_cparts.p, e->ct_parts, rowlist, nrows, n, B, e->d_alpha.p, e->d_efs.p, e->d_efi.p, e->d_new_mu.p, e->d_efic.p, out_acc)
+		if (mode == SWEEP_JACOBI) FINISH(SWEEP_JACOBI);
+		else if (mode == SWEEP_ACC) FINISH(SWEEP_ACC);
+		else FINISH(SWEEP_PALMO);
+#undef FINISH
+		e->launches += 2;
+		CK(cudaGetLastError());
+		return MPMC_OK;
+	};
 	int it = 0;
 	bool keep = true, acc_stale = false;
 	const int *gs_order = e->d_plist.p;
@@ -642,21 +691,17 @@ static int run_polar(mpmc_engine *e) {
 		}
 		if (need_old) CK(cudaMemcpyAsync(e->d_old_mu.p, e->d_mu.p, len * sizeof(double), cudaMemcpyDeviceToDevice, e->stream));
 		if (!pd.gs) {
-{ Timed _t(e, MPMC_K_DIPOLE_SWEEP);
-			k_dipole_sweep<ORTHO, SWEEP_JACOBI><<<ogrid, kOrdThreads, 0, e->stream>>>(e->d_posq.p, e->d_alpha.p, e->d_meta.p, e->d_plist.p, np, n, e->cap, e->cell, pd,
-			                                                                  e->d_mu.p, e->d_efs.p, e->d_efi.p, e->d_new_mu.p, e->d_efic.p);
-			LAUNCHED(e);
- }		} else {
+			Timed _t(e, MPMC_K_DIPOLE_SWEEP);
+			if ((rc = contract(SWEEP_JACOBI, e->d_plist.p, np, nullptr))) return rc;
+		} else {
 			// Gauss-Seidel pipeline (kernels_gs.cuh).  First sweep in list order (ranked_array = identity, :3463); from the second
 			// sweep on in rank order when polar_gs_ranked (update_ranking after the first pass, :3522-3523).
 			const int nblk = (np + kGsB - 1) / kGsB, nchunks = (np + kGsRows - 1) / kGsRows;
 			if ((rc = e->d_acc.ensure(len)) || (rc = e->d_dmu.ensure((size_t)np * 3)) || (rc = e->d_tri.ensure((size_t)nblk * 6 * kGsPairs)) ||
-			    (rc = e->d_gsctl.ensure(sizeof(GsCtl) / sizeof(int) + nchunks))) return rc;
+			    (rc = e->d_gsctl.ensure(sizeof(GsCtl) / sizeof(int) + nchunks)) || (rc = e->d_gpq.ensure(np)) || (rc = e->d_gmeta.ensure(np))) return rc;
 			if (it == 1 || acc_stale) {
 				Timed _t(e, MPMC_K_DIPOLE_SWEEP);
-				k_dipole_sweep<ORTHO, SWEEP_ACC><<<ogrid, kOrdThreads, 0, e->stream>>>(e->d_posq.p, e->d_alpha.p, e->d_meta.p, e->d_plist.p, np, n, e->cap, e->cell, pd,
-				                                                                e->d_mu.p, e->d_efs.p, e->d_efi.p, e->d_acc.p, e->d_efic.p);
-				LAUNCHED(e);
+				if ((rc = contract(SWEEP_ACC, e->d_plist.p, np, e->d_acc.p))) return rc;
 				acc_stale = false;
 			}
 			if (it == 1 || (ranked && it == 2)) {
@@ -667,15 +712,16 @@ static int run_polar(mpmc_engine *e) {
 					gs_order = e->d_order.p;
 				}
 				Timed _t(e, MPMC_K_GS_SWEEP);
-				k_gs_tensors<ORTHO><<<nblk, kGsThreads, 0, e->stream>>>(e->d_posq.p, e->d_alpha.p, e->d_meta.p, gs_order, np, e->cell, pd, e->d_tri.p);
-				LAUNCHED(e);
+				k_gs_gather<<<(np + 255) / 256, 256, 0, e->stream>>>(e->d_posq.p, e->d_alpha.p, e->d_meta.p, gs_order, np, e->d_gpq.p, e->d_gmeta.p);
+				k_gs_tensors<ORTHO><<<nblk, kGsThreads, 0, e->stream>>>(e->d_gpq.p, e->d_gmeta.p, np, e->cell, pd, e->d_tri.p);
+				e->launches += 2;
 			}
 			int ns = 1;
 			if (!need_old && !want_check && cf.polar_precision == 0.0) ns = (ranked && it == 1) ? 1 : (cf.polar_max_iter - it + 1);
 			CK(cudaMemsetAsync(e->d_gsctl.p, 0, sizeof(int) * (sizeof(GsCtl) / sizeof(int) + nchunks), e->stream));
-			const double4 *pq = e->d_posq.p;
-			const double *al = e->d_alpha.p, *efs = e->d_efs.p, *tri = e->d_tri.p;
-			const int *meta = e->d_meta.p;
+			const double4 *gpq = e->d_gpq.p;
+			const int *gmeta = e->d_gmeta.p;
+			const double *efs = e->d_efs.p, *tri = e->d_tri.p;
 			double *mu = e->d_mu.p, *efi = e->d_efi.p, *nmu = e->d_new_mu.p, *acc = e->d_acc.p, *dmu = e->d_dmu.p;
 			GsCtl *ctl = (GsCtl *)e->d_gsctl.p;
 			int npv = np;
@@ -687,10 +733,11 @@ static int run_polar(mpmc_engine *e) {
 				prof = e->d_gsprof.p;
 				e->gs_prof_nblk = nblk;
 			}
-			void *args[] = {&pq, &al, &meta, &gs_order, &npv, &cell, &pd, &efs, &mu, &efi, &nmu, &acc, &dmu, &tri, &ctl, &ns, &prof};
+			void *args[] = {&gpq, &gmeta, &gs_order, &npv, &cell, &pd, &efs, &mu, &efi, &nmu, &acc, &dmu, &tri, &ctl, &ns, &prof};
 			{
 				Timed _t(e, MPMC_K_GS_SWEEP);
-				CK(cudaLaunchCooperativeKernel((void *)k_gs_pipeline<ORTHO>, dim3(e->gs_grid), dim3(kGsThreads), args, kGsSmemBytes, e->stream));
+				const void *fn = expd ? (const void *)k_gs_pipeline<ORTHO, true> : (const void *)k_gs_pipeline<ORTHO, false>;
+				CK(cudaLaunchCooperativeKernel(fn, dim3(e->gs_grid), dim3(kGsThreads), args, kGsSmemBytes, e->stream));
 				LAUNCHED(e);
 			}
 			it += ns - 1;
@@ -711,13 +758,10 @@ static int run_polar(mpmc_engine *e) {
 			Timed _t(e, MPMC_K_PALMO);
 			if (pd.gs) {   // the running contraction already is sum_j T_ij mu_j for the polarizable rows
 				k_gs_palmo<<<(np * 3 + eb - 1) / eb, eb, 0, e->stream>>>(e->d_plist.p, np, e->d_efi.p, e->d_acc.p, e->d_efic.p);
-				k_dipole_sweep<ORTHO, SWEEP_PALMO_NONPOLAR><<<ogrid, kOrdThreads, 0, e->stream>>>(e->d_posq.p, e->d_alpha.p, e->d_meta.p, e->d_plist.p, np, n, e->cap,
-				                                                                           e->cell, pd, e->d_mu.p, e->d_efs.p, e->d_efi.p, e->d_new_mu.p, e->d_efic.p);
-				e->launches += 2;
-			} else {
-				k_dipole_sweep<ORTHO, SWEEP_PALMO><<<ogrid, kOrdThreads, 0, e->stream>>>(e->d_posq.p, e->d_alpha.p, e->d_meta.p, e->d_plist.p, np, n, e->cap, e->cell, pd,
-				                                                                  e->d_mu.p, e->d_efs.p, e->d_efi.p, e->d_new_mu.p, e->d_efic.p);
 				LAUNCHED(e);
+				if ((rc = contract(SWEEP_PALMO_NONPOLAR, e->d_nplist.p, (int)e->nplist.size(), nullptr))) return rc;
+			} else {
+				if ((rc = contract(SWEEP_PALMO, nullptr, n, nullptr))) return rc;
 			}
 		}
 		if (!pd.gs || cf.polar_sor || cf.polar_esor) {                       // :3526-3536 (plain GS already has mu == new_mu)
@@ -828,17 +872,19 @@ int mpmc_create(const mpmc_config *cfg, mpmc_engine **out) {
 	// shared-memory opt-ins
 	if ((rc = set_smem(k_structure_partial, sizeof(double2) * kSkSites * 3 * (kMaxKmax + 1))) ||
 	    (rc = set_smem(k_field_recip, sizeof(double2) * kFrSites * 3 * (kMaxKmax + 1))) ||
-	    (rc = set_smem(k_gs_pipeline<true>, kGsSmemBytes)) || (rc = set_smem(k_gs_pipeline<false>, kGsSmemBytes))) { mpmc_destroy(e); return rc; }
+	    false) { mpmc_destroy(e); return rc; }
 	{
-		const size_t pmax = pair_sweep_smem(true, 1024);     // tables of up to 1024 rows (64 octaves)
+		if ((rc = set_smem(k_gs_pipeline<true, true>, kGsSmemBytes)) || (rc = set_smem(k_gs_pipeline<false, true>, kGsSmemBytes)) ||
+		    (rc = set_smem(k_gs_pipeline<true, false>, kGsSmemBytes)) || (rc = set_smem(k_gs_pipeline<false, false>, kGsSmemBytes))) { mpmc_destroy(e); return rc; }
+	}
+	{
+		const size_t pmax = pair_sweep_smem(true, 1024);     // tables of up to 1024 rows (32 octaves)
 		if ((rc = set_smem(k_pair_sweep<true, true>, pmax)) || (rc = set_smem(k_pair_sweep<false, true>, pmax)) ||
 		    (rc = set_smem(k_pair_sweep<true, false>, pmax)) || (rc = set_smem(k_pair_sweep<false, false>, pmax))) { mpmc_destroy(e); return rc; }
 		const char *v1 = getenv("MPMC_PAIR_V1");
 		e->pair_v1 = v1 && v1[0] == '1';
 	}
-	int occ = 0;
-	CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_gs_pipeline<false>, kGsThreads, kGsSmemBytes));
-	e->gs_grid = std::max(1, occ) * e->num_sms;
+	e->gs_grid = e->num_sms;   // one CTA per SM: the solver's shared memory (table + block tensors) fills an SM
 	if ((rc = compute_cell(e, cfg->basis))) { mpmc_destroy(e); return rc; }
 	if (cfg->capacity > 0) e->cap = cfg->capacity;
 	*out = e;
@@ -854,7 +900,7 @@ int mpmc_destroy(mpmc_engine *e) {
 	e->d_tiles.release(); e->d_segs.release(); e->d_item_seg.release(); e->d_pmeta.release(); e->d_erf_tab.release(); e->d_blk_frozen.release(); e->d_mol_mobile.release(); e->d_kvec.release(); e->d_partials.release();
 	e->d_sk_part.release(); e->d_S_mobile.release(); e->d_S_frozen.release(); e->d_S_all.release();
 	e->d_efs.release(); e->d_efi.release(); e->d_efic.release(); e->d_mu.release(); e->d_new_mu.release(); e->d_old_mu.release();
-	e->d_rrms.release(); e->d_rank.release(); e->d_acc.release(); e->d_dmu.release(); e->d_tri.release(); e->d_gsctl.release(); e->d_com.release(); e->d_mol_mass.release(); e->d_chain.release();
+	e->d_rrms.release(); e->d_rank.release(); e->d_acc.release(); e->d_dmu.release(); e->d_tri.release(); e->d_gsctl.release(); e->d_gmeta.release(); e->d_nplist.release(); e->d_gpq.release(); e->d_cparts.release(); e->d_com.release(); e->d_mol_mass.release(); e->d_chain.release();
 	e->d_rmin.release(); e->d_result.release();
 	if (e->h_stage) cudaFreeHost(e->h_stage);
 	if (e->h_result) cudaFreeHost(e->h_result);

@@ -19,16 +19,17 @@
 
 namespace mpmc {
 
-constexpr int kTabLog2PerOctave = 5;                     // 32 intervals per octave
-constexpr int kTabPerOctave = 1 << kTabLog2PerOctave;
+constexpr int kTabLog2PerOctave = 5;                     // 32 intervals per octave: interpolation error below the rounding of the evaluation
 constexpr int kTabDeg = 7;
 constexpr int kTabShift = 20 - kTabLog2PerOctave;        // high word of a double: sign(1) exponent(11) mantissa(20)
+constexpr int kTabLog2PerOctaveCoarse = 4;               // 16 per octave: <= 1.3e-13 relative on r^-5 (two-function tables that must stay small)
+constexpr int kTabShiftCoarse = 20 - kTabLog2PerOctaveCoarse;
 constexpr int kTabPad = 2;
 
 inline int tab_row_stride(int nfun) { return nfun * (kTabDeg + 1) + kTabPad; }
 
 struct RadialTable {
-	int nfun = 0, base = 0, nrows = 0, stride = 0;
+	int nfun = 0, base = 0, nrows = 0, stride = 0, shift = kTabShift;
 	double u_lo = 0, u_hi = 0;                           // valid for u_lo <= u < u_hi
 	std::vector<double> rows;
 
@@ -37,8 +38,9 @@ struct RadialTable {
 
 	// f(u, out[nfun]) in long double; lo/hi are rounded outwards to interval boundaries
 	template <class F>
-	void build(int nfun_, double lo, double hi, F f) {
-		nfun = nfun_; stride = tab_row_stride(nfun);
+	void build(int nfun_, double lo, double hi, F f, int shift_ = kTabShift) {
+		nfun = nfun_; stride = tab_row_stride(nfun); shift = shift_;
+		const int kTabShift = shift_;
 		base = hi_word(lo) >> kTabShift;
 		const int last = hi_word(hi) >> kTabShift;
 		nrows = last - base + 1;
@@ -81,6 +83,7 @@ struct RadialTable {
 
 	// the device's evaluation order (Horner with FMA), for host-side checks
 	double eval(int fun, double u) const {
+		const int kTabShift = shift;
 		const int hi = hi_word(u);
 		const int idx = (hi >> kTabShift) - base;
 		const double mid = from_hi((hi & ~((1 << kTabShift) - 1)) | (1 << (kTabShift - 1)));

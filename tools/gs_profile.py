@@ -19,16 +19,12 @@ L.mpmc_debug_gs_profile(e.h, 0, buf.ctypes.data_as(C.c_void_p), MAXB, C.byref(nb
 nb = nb.value
 sol = buf[:8 * MAXB].reshape(MAXB, 8)[:nb]
 upd = buf[8 * MAXB:].reshape(MAXB, 8)[:nb]
-names = ["tri+site load", "flag wait", "acc load", "walk", "publish"]
-d = np.diff(sol[:, :6], axis=1)
+names = ["flag wait + acc load", "walk (pushes overlap)", "write-back + push tail", "pending sum"]
+d = np.diff(np.concatenate([sol[:, :4], np.concatenate([sol[1:, :1], sol[-1:, 3:4]])], axis=1), axis=1)
 print("solver: cycles per phase, mean over %d blocks (SM clock ~1.9 GHz)" % nb)
 for i, nme in enumerate(names):
-    print("  %-14s mean %8.0f  median %8.0f  max %8.0f" % (nme, d[:, i].mean(), np.median(d[:, i]), d[:, i].max()))
+    print("  %-24s mean %8.0f  median %8.0f  max %8.0f" % (nme, d[:-1, i].mean(), np.median(d[:-1, i]), d[:-1, i].max()))
 per_blk = np.diff(sol[:, 0])
-print("  block period   mean %8.0f cycles" % per_blk.mean())
-du = upd[:, 1:4] - upd[:, 0:3]
-print("updater 1: wait-for-solved %8.0f, first chunk %8.0f, remaining chunks %8.0f (chunks/panel %.1f)" % (
-    du[:, 0].mean(), du[:, 1].mean(), du[:, 2].mean(), upd[:, 4].mean()))
-print("updater 1 panel period mean %8.0f" % np.diff(upd[:, 0]).mean())
+print("  block period             mean %8.0f cycles" % per_blk.mean())
 for b in (1, 2, 50, 100):
-    print(" blk", b, "solver", (sol[b, :6] - sol[b, 0]).tolist(), "upd", (upd[b, :4] - sol[b, 0]).tolist())
+    print(" blk", b, "solver", (sol[b, :4] - sol[b, 0]).tolist())
