@@ -697,7 +697,7 @@ static int run_polar(mpmc_engine *e) {
 			// Gauss-Seidel pipeline (kernels_gs.cuh).  First sweep in list order (ranked_array = identity, :3463); from the second
 			// sweep on in rank order when polar_gs_ranked (update_ranking after the first pass, :3522-3523).
 			const int nblk = (np + kGsB - 1) / kGsB, nchunks = (np + kGsRows - 1) / kGsRows;
-			if ((rc = e->d_acc.ensure(len)) || (rc = e->d_dmu.ensure((size_t)np * 3)) || (rc = e->d_tri.ensure((size_t)nblk * 6 * kGsPairs)) ||
+			if ((rc = e->d_acc.ensure(len)) || (rc = e->d_dmu.ensure((size_t)np * 3)) || (rc = e->d_tri.ensure((size_t)nblk * kGsMat)) ||
 			    (rc = e->d_gsctl.ensure(sizeof(GsCtl) / sizeof(int) + nchunks)) || (rc = e->d_gpq.ensure(np)) || (rc = e->d_gmeta.ensure(np))) return rc;
 			if (it == 1 || acc_stale) {
 				Timed _t(e, MPMC_K_DIPOLE_SWEEP);
@@ -1189,6 +1189,7 @@ int mpmc_pi_chain(mpmc_engine *e, int closed, double *chain_mass_len2, double *c
 int mpmc_debug_gs_profile(mpmc_engine *e, int enable, long long *out, int max_blocks, int *nblk) {
 	CK(cudaSetDevice(e->dev));
 	e->gs_prof_enabled = enable != 0;
+	{ const int dbg = enable & ~1; CK(cudaMemcpyToSymbol(g_gs_debug, &dbg, sizeof(int))); }
 	if (out && e->d_gsprof.p && e->gs_prof_nblk) {
 		CK(cudaStreamSynchronize(e->stream));
 		const int nb = std::min(max_blocks, e->gs_prof_nblk);

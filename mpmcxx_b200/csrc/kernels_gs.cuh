@@ -15,7 +15,9 @@
 //     per row, every warp on its own — in panel order, and flag each 8-row chunk when it has received a panel.  The rows of
 //     panels p and p+1 are the solver's, so an updater has a whole block period before its work is needed: its flag latency is
 //     off the critical path.
-//   * the solver may start block b when its rows have received panels 0..b-2 from the updaters (panel b-1 is its own push).
+//   * the solver may start block b when its rows have received panels 0..b-3 from the updaters (panels b-2 and b-1 are its own
+//     pushes): an updater has two block periods (~10 us) to deliver, which is what a flag - fence - load - compute - fence - flag
+//     round trip across the chip takes.
 // Every row receives its updates in a fixed order, so the result does not depend on timing.  Pushing panels into rows that
 // were already swept prepares acc for the next sweep, and after the last sweep acc_i is exactly the contraction
 // palmo_contraction() needs (:3602-3627), so Palmo costs no extra sweep.
@@ -31,17 +33,18 @@ constexpr int kGsB = 64;                  // sites per solver block
 constexpr int kGsRows = 8;                // rows per updater chunk (one warp: 8 rows x 4 column lanes)
 constexpr int kGsThreads = 256;
 constexpr int kGsWarps = kGsThreads / 32;
-constexpr int kGsPairs = kGsB * (kGsB - 1) / 2;
-constexpr int kGsTriLen = 6 * (kGsPairs + 1);   // doubles per tensor buffer (+1: an all-zero dummy pair)
-__host__ __device__ constexpr int gs_tri(int a, int b) { return a * (2 * kGsB - a - 1) / 2 + (b - a - 1); }   // a < b
+constexpr int kGsMat = kGsB * kGsB * 6;   // doubles of one block's tensor matrix: [column k][row m][xx yy zz xy xz yz]
 
-// shared memory (doubles).  Solver: two tensor buffers, two site-column buffers, pending push (3 slices + sum), two row buffers,
-// panel dmu, ints.  Updaters: per warp the panel's columns and dmu.
+// shared memory (doubles).  Solver: the block's tensor matrix, two site-column buffers, pending push (3 slices + sum), two row
+// buffers, panel dmu, the walk's results, ints.  Updaters: per warp the panel's columns and dmu.
 constexpr int kGsSiteCols = 10;           // 0 alpha, 1-3 mu_old, 4-6 E_static, 7-9 acc
-constexpr size_t kGsSolverDoubles = 2 * (size_t)kGsTriLen + 2 * kGsSiteCols * kGsB + 4 * 3 * kGsB + 2 * 4 * kGsB + 4 * kGsB + 3 * kGsB + 16;
+constexpr int kGsAhead = 2;               // the solver pushes a panel into this many following blocks itself; the updaters take the rest
+constexpr int kGsPushWarps = 6, kGsPushThreads = kGsPushWarps * 32;
+constexpr size_t kGsSolverDoubles = (size_t)kGsMat + kGsSiteCols * kGsB + 3 * (kGsAhead * kGsB * 3) + 3 * 3 * kGsB + 3 * 4 * kGsB + 4 * kGsB + 3 * kGsB + 16;
 constexpr size_t kGsUpdaterDoubles = (size_t)kGsWarps * 8 * kGsB;
 constexpr size_t kGsSmemBytes = sizeof(double) * (kGsSolverDoubles > kGsUpdaterDoubles ? kGsSolverDoubles : kGsUpdaterDoubles);
 
+__device__ int g_gs_debug = 0;            // developer switch (mpmc_debug_gs_profile enable bits 1..): 2 = pushers idle, 4 = no rolling copy
 struct GsCtl { int solved; int pad[31]; };   // followed in memory by int applied[nchunks]
 
 __device__ __forceinline__ int ld_flag(const int *p) { return *(const volatile int *)p; }
@@ -69,41 +72,37 @@ __device__ __forceinline__ void gs_contract(const CellDev &c, const PolarDev &p,
 	}
 }
 
-// in-block tensors for every block of the sweep order: tri[blk][kGsPairs][6] = xx yy zz xy xz yz of T_ab, a < b in block
+// in-block tensors for every block of the sweep order, as a full matrix so that the walk reads column k with unit stride:
+// mat[blk][k][m][6] = xx yy zz xy xz yz of T_mk (zero on the diagonal and for rows/columns past the end)
 template <bool ORTHO>
 __global__ void __launch_bounds__(kGsThreads)
-k_gs_tensors(const double4 *__restrict__ gpq, const int *__restrict__ gmeta, int np, CellDev c, PolarDev p, double *__restrict__ tri) {
+k_gs_tensors(const double4 *__restrict__ gpq, const int *__restrict__ gmeta, int np, CellDev c, PolarDev p, double *__restrict__ mat) {
 	__shared__ double4 s_pq[kGsB];
 	__shared__ int     s_met[kGsB];
 	const int blk = blockIdx.x, base = blk * kGsB, cnt = min(kGsB, np - base), tid = threadIdx.x;
 	if (tid < cnt) { s_pq[tid] = gpq[base + tid]; s_met[tid] = gmeta[base + tid]; }
 	__syncthreads();
-	double *out = tri + (size_t)blk * 6 * kGsPairs;
-	for (int q = tid; q < cnt * cnt; q += kGsThreads) {
-		const int a = q / cnt, b = q % cnt;
-		if (a >= b) continue;
-		// the tensor itself = the contraction applied to the three unit dipoles (columns of T)
+	double *out = mat + (size_t)blk * kGsMat;
+	for (int q = tid; q < kGsB * kGsB; q += kGsThreads) {
+		const int a = q / kGsB, b = q % kGsB;
+		if (a > b) continue;
 		double xx = 0, xy = 0, xz = 0, yy = 0, yz = 0, zz = 0, t0 = 0, t1 = 0;
-		if (p.damp_type == 2) {
-			gs_contract<ORTHO, true>(c, p, s_pq[a], s_met[a], s_pq[b], s_met[b], make_double4(1, 0, 0, 0), xx, xy, xz);
-			gs_contract<ORTHO, true>(c, p, s_pq[a], s_met[a], s_pq[b], s_met[b], make_double4(0, 1, 0, 0), t0, yy, yz);
-			gs_contract<ORTHO, true>(c, p, s_pq[a], s_met[a], s_pq[b], s_met[b], make_double4(0, 0, 1, 0), t0, t1, zz);
-		} else {
-			gs_contract<ORTHO, false>(c, p, s_pq[a], s_met[a], s_pq[b], s_met[b], make_double4(1, 0, 0, 0), xx, xy, xz);
-			gs_contract<ORTHO, false>(c, p, s_pq[a], s_met[a], s_pq[b], s_met[b], make_double4(0, 1, 0, 0), t0, yy, yz);
-			gs_contract<ORTHO, false>(c, p, s_pq[a], s_met[a], s_pq[b], s_met[b], make_double4(0, 0, 1, 0), t0, t1, zz);
+		if (a < b && b < cnt) {
+			// the tensor itself = the contraction applied to the three unit dipoles (columns of T)
+			if (p.damp_type == 2) {
+				gs_contract<ORTHO, true>(c, p, s_pq[a], s_met[a], s_pq[b], s_met[b], make_double4(1, 0, 0, 0), xx, xy, xz);
+				gs_contract<ORTHO, true>(c, p, s_pq[a], s_met[a], s_pq[b], s_met[b], make_double4(0, 1, 0, 0), t0, yy, yz);
+				gs_contract<ORTHO, true>(c, p, s_pq[a], s_met[a], s_pq[b], s_met[b], make_double4(0, 0, 1, 0), t0, t1, zz);
+			} else {
+				gs_contract<ORTHO, false>(c, p, s_pq[a], s_met[a], s_pq[b], s_met[b], make_double4(1, 0, 0, 0), xx, xy, xz);
+				gs_contract<ORTHO, false>(c, p, s_pq[a], s_met[a], s_pq[b], s_met[b], make_double4(0, 1, 0, 0), t0, yy, yz);
+				gs_contract<ORTHO, false>(c, p, s_pq[a], s_met[a], s_pq[b], s_met[b], make_double4(0, 0, 1, 0), t0, t1, zz);
+			}
 		}
-		const int k = gs_tri(a, b);
-		// pair-major: xx yy zz xy xz yz of pair k are 48 contiguous bytes (three 128-bit shared loads in the solver's walk)
-		out[6 * k + 0] = xx; out[6 * k + 1] = yy; out[6 * k + 2] = zz;
-		out[6 * k + 3] = xy; out[6 * k + 4] = xz; out[6 * k + 5] = yz;
+		double *u = out + ((size_t)a * kGsB + b) * 6, *l = out + ((size_t)b * kGsB + a) * 6;
+		u[0] = xx; u[1] = yy; u[2] = zz; u[3] = xy; u[4] = xz; u[5] = yz;
+		l[0] = xx; l[1] = yy; l[2] = zz; l[3] = xy; l[4] = xz; l[5] = yz;
 	}
-}
-
-// index of pair (m, k) in the block's triangular store; the all-zero dummy pair for rows that must not move
-__device__ __forceinline__ int gs_pair_index(int m, int k) {
-	const int lo = min(m, k), hi = max(m, k);
-	return (m == k || m < 0) ? kGsPairs : lo * (2 * kGsB - lo - 1) / 2 + (hi - lo - 1);
 }
 
 template <bool ORTHO, bool EXPD>
@@ -122,164 +121,207 @@ k_gs_pipeline(const double4 *__restrict__ gpq, const int *__restrict__ gmeta, co
 	for (int sweep = 0; sweep < nsweeps; sweep++) {
 		if (cta == 0) {
 			// ------------------------------------------------ solver ------------------------------------------------
-			double *s_tri = s_raw;                                         // [2][kGsTriLen]
-			double *s_site = s_tri + 2 * kGsTriLen;                        // [2][kGsSiteCols][kGsB]
-			double *s_pendp = s_site + 2 * kGsSiteCols * kGsB;             // [3 slices][kGsB][3] partial pushes, then [kGsB][3] their sum
-			double *s_pend = s_pendp + 3 * 3 * kGsB;
-			double4 *s_rows = (double4 *)(s_pend + 3 * kGsB);              // [2][kGsB] x y z alpha of this block / the next block
-			double4 *s_dm = s_rows + 2 * kGsB;                             // [kGsB] dmu of the block being walked
-			int *s_meta = (int *)(s_dm + kGsB);                            // [2][kGsB]
-			int *s_idx = s_meta + 2 * kGsB;                                // [2][kGsB] site ids
-			volatile int *s_prog = (volatile int *)(s_idx + 2 * kGsB);     // columns of the current walk that are final
-			auto load_tri = [&](int blk) {                                 // cp.async: tensors of block blk -> buffer blk & 1 (+ commit)
-				const double2 *tsrc = (const double2 *)(tri + (size_t)blk * 6 * kGsPairs);
-				double2 *tdst = (double2 *)(s_tri + (blk & 1) * kGsTriLen);
-				for (int q = tid; q < 3 * kGsPairs; q += kGsThreads) __pipeline_memcpy_async(tdst + q, tsrc + q, sizeof(double2));
-				__pipeline_commit();
-			};
+			double *s_mat = s_raw;                                         // [kGsB columns][kGsB rows][6], rolled: column k of the next block replaces column k once the walk has passed it
+			double *s_site = s_mat + kGsMat;                               // [kGsSiteCols][kGsB]
+			double *s_pendp = s_site + kGsSiteCols * kGsB;                 // [3][kGsAhead * kGsB][3] partial pushes of the panel being walked
+			double *s_pend = s_pendp + 3 * (kGsAhead * kGsB * 3);          // [3][kGsB][3] pushes already made into the rows of blocks b, b+1, b+2 (slot = block % 3)
+			double4 *s_rows = (double4 *)(s_pend + 3 * 3 * kGsB);          // [3][kGsB] x y z alpha of blocks b, b+1, b+2 (slot = block % 3)
+			double4 *s_dm = s_rows + 3 * kGsB;                             // [kGsB] dmu of the block being walked
+			int *s_meta = (int *)(s_dm + kGsB);                            // [3][kGsB]
+			int *s_idx = s_meta + 3 * kGsB;                                // [3][kGsB] site ids
+			volatile int *s_prog = (volatile int *)(s_idx + 3 * kGsB);     // columns of the current walk that are final
 			auto load_rows = [&](int blk, int m) {                         // position, alpha, meta and site id of row m of block blk
-				const int pos = blk * kGsB + m, b = blk & 1;
+				const int pos = blk * kGsB + m, b = blk % 3;
 				const bool on = pos < np;
 				s_idx[b * kGsB + m] = on ? order[pos] : 0;
 				s_rows[b * kGsB + m] = on ? gpq[pos] : make_double4(0, 0, 0, 0);
 				s_meta[b * kGsB + m] = on ? gmeta[pos] : 0;
 			};
 			auto load_cols = [&](int blk, int m) {                         // site columns of row m (all but the running contraction); after load_rows
-				const int b = blk & 1;
+				const int b = blk % 3;
 				const bool on = blk * kGsB + m < np;
 				const int s = s_idx[b * kGsB + m];
-				double *sc = s_site + b * kGsSiteCols * kGsB;
-				sc[m] = s_rows[b * kGsB + m].w;
+				s_site[m] = s_rows[b * kGsB + m].w;
 				for (int q = 0; q < 3; q++) {
-					sc[(1 + q) * kGsB + m] = on ? __ldcg(mu + 3 * s + q) : 0.0;
-					sc[(4 + q) * kGsB + m] = on ? efs[3 * s + q] : 0.0;
+					s_site[(1 + q) * kGsB + m] = on ? __ldcg(mu + 3 * s + q) : 0.0;
+					s_site[(4 + q) * kGsB + m] = on ? efs[3 * s + q] : 0.0;
 				}
 			};
-			if (tid < 12) { s_tri[6 * kGsPairs + (tid % 6) + (tid / 6) * kGsTriLen] = 0.0; }   // dummy pair of both buffers
-			for (int q = tid; q < 3 * kGsB; q += kGsThreads) s_pend[q] = 0.0;
-			load_tri(0);
-			if (tid < kGsB) { load_rows(0, tid); load_cols(0, tid); }
+			auto load_acc = [&](int blk, int m) {                          // running contraction of row m as the updaters left it
+				const bool on = blk * kGsB + m < np;
+				const int s = s_idx[(blk % 3) * kGsB + m];
+				for (int q = 0; q < 3; q++) s_site[(7 + q) * kGsB + m] = on ? __ldcg(acc + 3 * s + q) : 0.0;
+			};
+			for (int q = tid; q < 3 * 3 * kGsB; q += kGsThreads) s_pend[q] = 0.0;
+			{
+				const double2 *src = (const double2 *)tri;
+				double2 *dst = (double2 *)s_mat;
+				for (int q = tid; q < kGsMat / 2; q += kGsThreads) __pipeline_memcpy_async(dst + q, src + q, sizeof(double2));
+				__pipeline_commit();
+			}
+			if (tid < kGsB) { load_rows(0, tid); load_cols(0, tid); load_acc(0, tid); }
+			else if (tid < 2 * kGsB) load_rows(1, tid - kGsB);
 			if (tid == 0) *s_prog = 0;
 			for (int blk = 0; blk < nblk; blk++) {
-				const int base = blk * kGsB, cnt = min(kGsB, np - base), cur = blk & 1;
-				double *ss = s_site + cur * kGsSiteCols * kGsB;
+				const int base = blk * kGsB, cnt = min(kGsB, np - base), cur = blk % 3;
 				if (prof && tid == 0 && sweep == 0) prof[blk * 8 + 0] = clock64();
-				// (A) rows of this block must have received panels 0..blk-2 from the updaters; then the running contraction is the
-				//     global value plus my own push of the previous panel
-				const int c0 = base / kGsRows, c1 = (base + cnt + kGsRows - 1) / kGsRows;
-				if (blk >= 2 && tid >= 128 && tid - 128 < c1 - c0) while (ld_flag(applied + c0 + tid - 128) < blk - 1) { }
-				if (tid >= kGsB && tid < 2 * kGsB && blk + 1 < nblk) load_rows(blk + 1, tid - kGsB);     // the pushing warps need them during the walk
-				__syncthreads();
-				__threadfence();
-				if (tid < cnt) {
-					const int s = s_idx[cur * kGsB + tid];
-					for (int q = 0; q < 3; q++) ss[(7 + q) * kGsB + tid] = __ldcg(acc + 3 * s + q) + s_pend[3 * tid + q];
-				}
+				// (A) the running contraction of this block's rows = what the updaters left (fetched during the previous walk)
+				//     + my own pushes of the two previous panels.  Rows of block b+2 for the pushing warps.
 				__pipeline_wait_prior(0);
 				__syncthreads();
+				if (tid < kGsB) { for (int q = 0; q < 3; q++) s_site[(7 + q) * kGsB + tid] += s_pend[(cur * kGsB + tid) * 3 + q]; }
+				else if (tid < 2 * kGsB) load_rows(blk + 2, tid - kGsB);
+				__syncthreads();
 				if (prof && tid == 0 && sweep == 0) prof[blk * 8 + 1] = clock64();
-				// (B) warp 0 walks; warps 1-3 and 5-7 push every column into the next block's rows as soon as it is final; warp 4
-				//     (the walker's scheduler partner) only fetches the next block's site columns
-				if (blk + 1 < nblk) load_tri(blk + 1);
+				// (B) warp 0 walks.  Warps 1-3 and 5-7 push every column, as soon as it is final, into the rows of the next two
+				//     blocks and publish the panel.  Warp 4 (the walker's scheduler partner: kept light, and asleep while it waits)
+				//     rolls the next block's tensors into the columns the walk has left behind and fetches the next block's site columns.
 				if (warp == 0) {
-					const double *tb = s_tri + cur * kGsTriLen;
 					// lane owns rows lane (slot 0) and lane+32 (slot 1); everything a row needs lives in registers during the walk.
 					// With c = alpha E_s - mu_old the change of a dipole is a single FMA:  dmu = c - alpha acc.
-					double al[2], cx[2], cy[2], cz[2], ax[2], ay[2], az[2], ex[2], ey[2], ez[2];
-					int mrow[2];
+					double al[2], cx[2], cy[2], cz[2], ax[2], ay[2], az[2], ex[2], ey[2], ez[2], sx[2], sy[2], sz[2];
 #pragma unroll
 					for (int h = 0; h < 2; h++) {
 						const int m = lane + 32 * h;
-						al[h] = ss[m];
-						cx[h] = al[h] * ss[4 * kGsB + m] - ss[1 * kGsB + m];
-						cy[h] = al[h] * ss[5 * kGsB + m] - ss[2 * kGsB + m];
-						cz[h] = al[h] * ss[6 * kGsB + m] - ss[3 * kGsB + m];
-						ax[h] = ss[7 * kGsB + m]; ay[h] = ss[8 * kGsB + m]; az[h] = ss[9 * kGsB + m];
+						al[h] = s_site[m];
+						sx[h] = s_site[4 * kGsB + m]; sy[h] = s_site[5 * kGsB + m]; sz[h] = s_site[6 * kGsB + m];
+						cx[h] = al[h] * sx[h] - s_site[1 * kGsB + m];
+						cy[h] = al[h] * sy[h] - s_site[2 * kGsB + m];
+						cz[h] = al[h] * sz[h] - s_site[3 * kGsB + m];
+						ax[h] = s_site[7 * kGsB + m]; ay[h] = s_site[8 * kGsB + m]; az[h] = s_site[9 * kGsB + m];
 						ex[h] = ey[h] = ez[h] = 0;
-						mrow[h] = m < cnt ? m : -1;                               // rows past the end never match and never move
 					}
-					// tensor entries of column 0 for my two rows (independent of the dipoles: always one step ahead of the chain)
+					__syncwarp();
+					if (lane == 0) *s_prog = -1;                                  // the site columns are in registers: warp 4 may refill them
+					// tensor entries of column k for my two rows: (xx yy) (zz xy) (xz yz); always one column ahead of the dependent chain
+					const double2 *tcol = (const double2 *)s_mat + lane * 3;
 					double2 tn[2][3];
 #pragma unroll
-					for (int hh = 0; hh < 2; hh++) {
-						const double2 *tp = (const double2 *)(tb + 6 * gs_pair_index(mrow[hh], 0));
-						tn[hh][0] = tp[0]; tn[hh][1] = tp[1]; tn[hh][2] = tp[2];
-					}
+					for (int hh = 0; hh < 2; hh++) { tn[hh][0] = tcol[hh * 96]; tn[hh][1] = tcol[hh * 96 + 1]; tn[hh][2] = tcol[hh * 96 + 2]; }
 #pragma unroll
 					for (int half = 0; half < 2; half++) {
 						const int kend = min(32, cnt - 32 * half);
+#pragma unroll 2
 						for (int kk = 0; kk < kend; kk++) {
 							const int k = kk + 32 * half;
 							double2 tc[2][3];
+							const double2 *tnext = tcol + min(k + 1, kGsB - 1) * (kGsB * 3);
 #pragma unroll
 							for (int hh = 0; hh < 2; hh++) {
-								tc[hh][0] = tn[hh][0]; tc[hh][1] = tn[hh][1]; tc[hh][2] = tn[hh][2];     // (xx yy) (zz xy) (xz yz)
-								const double2 *tp = (const double2 *)(tb + 6 * gs_pair_index(mrow[hh], min(k + 1, kGsB - 1)));
-								tn[hh][0] = tp[0]; tn[hh][1] = tp[1]; tn[hh][2] = tp[2];
+								tc[hh][0] = tn[hh][0]; tc[hh][1] = tn[hh][1]; tc[hh][2] = tn[hh][2];
+								tn[hh][0] = tnext[hh * 96]; tn[hh][1] = tnext[hh * 96 + 1]; tn[hh][2] = tnext[hh * 96 + 2];
 							}
 							// every lane forms the candidate change of its own slot-`half` row; the owner's is the real one
 							const double dxc = fma(-al[half], ax[half], cx[half]), dyc = fma(-al[half], ay[half], cy[half]), dzc = fma(-al[half], az[half], cz[half]);
 							const double dx = __shfl_sync(0xffffffffu, dxc, kk), dy = __shfl_sync(0xffffffffu, dyc, kk), dz = __shfl_sync(0xffffffffu, dzc, kk);
 							if (lane == kk) { ex[half] = ax[half]; ey[half] = ay[half]; ez[half] = az[half]; }   // acc at the moment of the update
 #pragma unroll
-							for (int hh = 0; hh < 2; hh++) {
+							for (int hh = 0; hh < 2; hh++) {                      // the diagonal entry is zero: a row does not move itself
 								ax[hh] = fma(tc[hh][0].x, dx, fma(tc[hh][1].y, dy, fma(tc[hh][2].x, dz, ax[hh])));
 								ay[hh] = fma(tc[hh][1].y, dx, fma(tc[hh][0].y, dy, fma(tc[hh][2].y, dz, ay[hh])));
 								az[hh] = fma(tc[hh][2].x, dx, fma(tc[hh][2].y, dy, fma(tc[hh][1].x, dz, az[hh])));
 							}
-							// hand the finished column to the pushing warps (published in groups of 4 columns)
-							if (lane == 0) {
-								s_dm[k] = make_double4(dx, dy, dz, 0.0);
-								if ((k & 3) == 3 || k == cnt - 1) { __threadfence_block(); *s_prog = k + 1; }
+							// hand the finished column to the other warps.  No fence: both stores are volatile shared-memory stores of one
+							// thread, which the LSU performs in program order (a MEMBAR here costs more than the whole step); every lane
+							// stores the same values, so the walk has no divergent region
+							{
+								volatile double *vd = (volatile double *)(s_dm + k);
+								vd[0] = dx; vd[1] = dy; vd[2] = dz;
+								*s_prog = k + 1;
 							}
 						}
 					}
 					if (prof && tid == 0 && sweep == 0) prof[blk * 8 + 2] = clock64();
+					// contract_dipoles: ef_induced = -acc at the moment of the update, mu = alpha (E_s + ef_induced)  (:3583-3592)
 #pragma unroll
 					for (int hh = 0; hh < 2; hh++) {
 						const int m = lane + 32 * hh;
 						if (m < cnt) {
 							const int s = s_idx[cur * kGsB + m];
-							// contract_dipoles: ef_induced = -acc at the moment of the update, mu = alpha (E_s + ef_induced)  (:3583-3592);
-							// the published change is recomputed exactly as the walk formed it
-							const double fx = -ex[hh], fy = -ey[hh], fz = -ez[hh];
-							const double nx = al[hh] * (ss[4 * kGsB + m] + fx), ny = al[hh] * (ss[5 * kGsB + m] + fy), nz = al[hh] * (ss[6 * kGsB + m] + fz);
+							const double nx = al[hh] * (sx[hh] - ex[hh]), ny = al[hh] * (sy[hh] - ey[hh]), nz = al[hh] * (sz[hh] - ez[hh]);
 							__stcg(mu + 3 * s, nx); __stcg(mu + 3 * s + 1, ny); __stcg(mu + 3 * s + 2, nz);
 							new_mu[3 * s] = nx; new_mu[3 * s + 1] = ny; new_mu[3 * s + 2] = nz;
-							efi[3 * s] = fx; efi[3 * s + 1] = fy; efi[3 * s + 2] = fz;
+							efi[3 * s] = -ex[hh]; efi[3 * s + 1] = -ey[hh]; efi[3 * s + 2] = -ez[hh];
 							__stcg(acc + 3 * s, ax[hh]); __stcg(acc + 3 * s + 1, ay[hh]); __stcg(acc + 3 * s + 2, az[hh]);
-							__stcg(dmu + 3 * (base + m), fma(-al[hh], ex[hh], cx[hh]));
-							__stcg(dmu + 3 * (base + m) + 1, fma(-al[hh], ey[hh], cy[hh]));
-							__stcg(dmu + 3 * (base + m) + 2, fma(-al[hh], ez[hh], cz[hh]));
 						}
 					}
-					__threadfence();
-					__syncwarp();
-					if (lane == 0) st_flag(&ctl->solved, blk + 1);
 				} else if (warp == 4) {
-					if (blk + 1 < nblk) { load_cols(blk + 1, lane); load_cols(blk + 1, lane + 32); }
-				} else if (blk + 1 < nblk) {
+					if (blk + 1 < nblk) {
+						while (*s_prog == 0) __nanosleep(100);                     // the walker has taken the site columns into registers
+						load_cols(blk + 1, lane); load_cols(blk + 1, lane + 32);
+						// roll the next block's tensor matrix in behind the walk: column k is dead once column k+1 has been fetched
+						const double2 *src = (const double2 *)(tri + (size_t)(blk + 1) * kGsMat);
+						double2 *dst = (double2 *)s_mat;
+						int done = 0;
+						while (done < kGsB && !(g_gs_debug & 4)) {
+							int pg = *s_prog;
+							if (pg >= cnt) pg = kGsB;                               // the walk is over: the remaining (unused) columns too
+							if (pg <= done) { __nanosleep(200); continue; }
+							for (int q = done * (kGsB * 3) + lane; q < pg * (kGsB * 3); q += 32) __pipeline_memcpy_async(dst + q, src + q, sizeof(double2));
+							done = pg;
+						}
+						__pipeline_commit();
+						// the running contraction of the next block's rows, once the updaters have applied panels 0..blk-2 to them
+						const int c0 = (base + kGsB) / kGsRows, c1 = min(nchunks, c0 + kChunksPerBlk);
+						if (blk >= kGsAhead && lane < c1 - c0) while (ld_flag(applied + c0 + lane) < blk + 1 - kGsAhead) __nanosleep(100);
+						__syncwarp();
+						__threadfence();
+						load_acc(blk + 1, lane); load_acc(blk + 1, lane + 32);
+					}
+				} else {
 					const int h = (warp < 4 ? warp - 1 : warp - 2) * 32 + lane;       // 0..191
-					const int r = h & (kGsB - 1), sl = h >> 6;                         // row of the next block, column slice (warp-uniform)
-					const double4 pr = s_rows[(cur ^ 1) * kGsB + r];
-					const int mr = s_meta[(cur ^ 1) * kGsB + r];
-					const bool on = base + kGsB + r < np;
-					double ax = 0, ay = 0, az = 0;
-					for (int k = sl; k < cnt; k += 3) {
-						while (*s_prog <= k) { }
+					const int r4 = h & 31, sl = h >> 5;                                // my four target rows r4 + 32 j; my columns k = sl mod 6 (warp-uniform)
+					double4 pr[4]; int mr[4]; bool on[4];
+					double ax[4] = {0, 0, 0, 0}, ay[4] = {0, 0, 0, 0}, az[4] = {0, 0, 0, 0};
+#pragma unroll
+					for (int j = 0; j < 4; j++) {
+						const int tb = blk + 1 + (j >> 1), row = r4 + 32 * (j & 1);
+						pr[j] = s_rows[(tb % 3) * kGsB + row];
+						mr[j] = s_meta[(tb % 3) * kGsB + row];
+						on[j] = tb < nblk && tb * kGsB + row < np && !(g_gs_debug & 2);
+					}
+					for (int k = (g_gs_debug & 8) ? cnt : sl; k < cnt; k += kGsPushWarps) {
+						while (*s_prog <= k) __nanosleep(40);
 						const volatile double *vd = (const volatile double *)(s_dm + k);
 						const double4 dm = make_double4(vd[0], vd[1], vd[2], 0.0);
-						if (on) gs_contract<ORTHO, EXPD>(c, p, pr, mr, s_rows[cur * kGsB + k], s_meta[cur * kGsB + k], dm, ax, ay, az);
+						const double4 pc = s_rows[cur * kGsB + k];
+						const int mc = s_meta[cur * kGsB + k];
+#pragma unroll
+						for (int j = 0; j < 4; j++)
+							if (on[j]) gs_contract<ORTHO, EXPD>(c, p, pr[j], mr[j], pc, mc, dm, ax[j], ay[j], az[j]);
+						// publish the panel: the change of every dipole of the block (the flag follows the barrier)
+						if (r4 == 0) { __stcg(dmu + 3 * (base + k), dm.x); __stcg(dmu + 3 * (base + k) + 1, dm.y); __stcg(dmu + 3 * (base + k) + 2, dm.z); }
 					}
-					double *o = s_pendp + (sl * kGsB + r) * 3;
-					o[0] = ax; o[1] = ay; o[2] = az;
+					if (r4 == 0) __threadfence();
+					// the six column slices of a target row, summed in a fixed order: slices 0-2 store, slices 3-5 add
+					if (sl < 3) {
+#pragma unroll
+						for (int j = 0; j < 4; j++) {
+							double *o = s_pendp + ((sl * kGsAhead * kGsB) + (j >> 1) * kGsB + r4 + 32 * (j & 1)) * 3;
+							o[0] = ax[j]; o[1] = ay[j]; o[2] = az[j];
+						}
+					}
+					asm volatile("bar.sync 1, %0;" ::"n"(kGsPushThreads) : "memory");
+					if (sl >= 3) {
+#pragma unroll
+						for (int j = 0; j < 4; j++) {
+							double *o = s_pendp + (((sl - 3) * kGsAhead * kGsB) + (j >> 1) * kGsB + r4 + 32 * (j & 1)) * 3;
+							o[0] += ax[j]; o[1] += ay[j]; o[2] += az[j];
+						}
+					}
 				}
 				__syncthreads();
 				if (prof && tid == 0 && sweep == 0) prof[blk * 8 + 3] = clock64();
-				// (C) my push of this panel into the next block's rows, slices summed in a fixed order
-				if (tid < 3 * kGsB) {
-					const int r = tid / 3, q = tid % 3;
-					s_pend[3 * r + q] = (blk + 1 < nblk) ? (s_pendp[(0 * kGsB + r) * 3 + q] + s_pendp[(1 * kGsB + r) * 3 + q]) + s_pendp[(2 * kGsB + r) * 3 + q] : 0.0;
+				// (C) publish the panel (the slice leaders have fenced their dmu stores before the barrier); my pushes of this panel
+				//     into the rows of the next two blocks
+				if (tid == 32) st_flag(&ctl->solved, blk + 1);
+				if (tid < kGsAhead * kGsB) {
+					const int tb = blk + 1 + tid / kGsB, row = tid % kGsB;
+					double *dst = s_pend + ((tb % 3) * kGsB + row) * 3;
+					for (int q = 0; q < 3; q++) {
+						const double v = (s_pendp[(0 * kGsAhead * kGsB + tid) * 3 + q] + s_pendp[(1 * kGsAhead * kGsB + tid) * 3 + q]) + s_pendp[(2 * kGsAhead * kGsB + tid) * 3 + q];
+						dst[q] = (tid < kGsB ? dst[q] : 0.0) + v;                 // block b+1 already holds panel b-1; block b+2 starts here
+					}
 				}
 				if (tid == 0) *s_prog = 0;
 			}
@@ -294,7 +336,7 @@ k_gs_pipeline(const double4 *__restrict__ gpq, const int *__restrict__ gmeta, co
 			for (int blk = 0; blk < nblk; blk++) {
 				const int base = blk * kGsB, cnt = min(kGsB, np - base);
 				// the panel's own rows and the rows of the next block belong to the solver
-				const int skip0 = blk * kChunksPerBlk, skip1 = (blk + 1 < nblk) ? (blk + 2) * kChunksPerBlk : (blk + 1) * kChunksPerBlk;
+				const int skip0 = blk * kChunksPerBlk, skip1 = min(blk + 1 + kGsAhead, nblk) * kChunksPerBlk;
 				bool any = false;
 				for (int ch = gwid; ch < nchunks; ch += GW) any = any || !(ch >= skip0 && ch < skip1);
 				if (!any) continue;

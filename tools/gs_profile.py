@@ -10,12 +10,13 @@ s = W.h2_framework(solver={"polar_gs": "on", "polar_max_iter": "2"}, ensemble="n
 e = engine.Engine(s)
 L = engine.lib()
 e.energy()
-L.mpmc_debug_gs_profile(e.h, 1, None, 0, None)
+DBG = int(sys.argv[1]) if len(sys.argv) > 1 else 0
+L.mpmc_debug_gs_profile(e.h, 1 | DBG, None, 0, None)
 e.energy()
 MAXB = 256
 buf = np.zeros(2 * 8 * MAXB, dtype=np.int64)
 nb = C.c_int()
-L.mpmc_debug_gs_profile(e.h, 0, buf.ctypes.data_as(C.c_void_p), MAXB, C.byref(nb))
+L.mpmc_debug_gs_profile(e.h, 0 | DBG, buf.ctypes.data_as(C.c_void_p), MAXB, C.byref(nb))
 nb = nb.value
 sol = buf[:8 * MAXB].reshape(MAXB, 8)[:nb]
 upd = buf[8 * MAXB:].reshape(MAXB, 8)[:nb]
@@ -27,4 +28,4 @@ for i, nme in enumerate(names):
 per_blk = np.diff(sol[:, 0])
 print("  block period             mean %8.0f cycles" % per_blk.mean())
 for b in (1, 2, 50, 100):
-    print(" blk", b, "solver", (sol[b, :4] - sol[b, 0]).tolist())
+    print(" blk", b, "solver", (sol[b, :7] - sol[b, 0]).tolist(), "next start", int(sol[b + 1, 0] - sol[b, 0]))
