@@ -159,7 +159,14 @@ struct mpmc_engine {
 	DevBuf<double> d_efs, d_efi, d_efic, d_mu, d_new_mu, d_old_mu, d_rrms, d_rank, d_acc, d_dmu, d_tri, d_com, d_mol_mass, d_chain;
 	DevBuf<int> d_gsctl, d_gmeta, d_nplist;
 	DevBuf<double4> d_gpq;
-	DevBuf<double> d_cparts;
+	DevBuf<double> d_cparts, d_field_tab;
+	DevBuf<int> d_mobile_sites, d_frozen_sites, d_allq, d_fp_list, d_mp_list, d_recount;
+	std::vector<int> mobile_sites, frozen_sites, allq, fp_list, mp_list;
+	DevBuf<unsigned long long> d_r2min_ff;
+	DevBuf<double> d_t2, d_t2_cached, d_cnt_ff;
+	bool rank_ff_dirty = true;
+	RadialTable field_tab;
+	FieldParams fpar;
 	std::vector<int> nplist;
 	int ct_parts = 1, ct_part_len = 0;
 	DevBuf<long long> d_gsprof;
@@ -504,7 +511,43 @@ int prepare_polar(mpmc_engine *e) {
 	len = std::max(kOrdJ, (len + kOrdJ - 1) / kOrdJ * kOrdJ);
 	parts = std::max(1, (std::max(np, 1) + len - 1) / len);
 	e->ct_parts = parts; e->ct_part_len = len;
-	if ((rc = e->d_cparts.ensure((size_t)parts * e->B * n * 3))) return rc;
+	if ((rc = e->d_cparts.ensure((size_t)32 * e->B * n * 3))) return rc;
+	// static field: row / column lists and the radial table of real_term() (System.Energy.cpp:2921-2929)
+	e->mobile_sites.clear(); e->frozen_sites.clear(); e->allq.clear();
+	for (int i = 0; i < n; i++) {
+		(e->h_frozen[i] ? e->frozen_sites : e->mobile_sites).push_back(i);
+		if (e->h_q[i] != 0.0) e->allq.push_back(i);
+	}
+	auto upl = [&](DevBuf<int> &d, const std::vector<int> &v) -> int {
+		int r2 = d.ensure(std::max<size_t>(v.size(), 1));
+		if (r2) return r2;
+		if (!v.empty()) CK(cudaMemcpyAsync(d.p, v.data(), v.size() * sizeof(int), cudaMemcpyHostToDevice, e->stream));
+		return MPMC_OK;
+	};
+	e->fp_list.clear(); e->mp_list.clear();
+	for (int i : e->plist) (e->h_frozen[i] ? e->fp_list : e->mp_list).push_back(i);
+	if ((rc = upl(e->d_mobile_sites, e->mobile_sites)) || (rc = upl(e->d_frozen_sites, e->frozen_sites)) || (rc = upl(e->d_allq, e->allq)) ||
+	    (rc = upl(e->d_fp_list, e->fp_list)) || (rc = upl(e->d_mp_list, e->mp_list))) return rc;
+	if ((rc = e->d_r2min_ff.ensure(e->B)) || (rc = e->d_t2.ensure(e->B)) || (rc = e->d_t2_cached.ensure(e->B)) || (rc = e->d_recount.ensure(e->B)) ||
+	    (rc = e->d_cnt_ff.ensure((size_t)e->B * n))) return rc;
+	e->rank_ff_dirty = true;
+	{
+		FieldParams &fp = e->fpar;
+		fp.t2_in = cf.polar_ewald ? e->pp.t2_es : e->pp.t2_lj;          // `r > rc` (:2917) / `r - 1e-12 < rc` (:3319)
+		fp.t2_adm = fp.t2_in * (1.0 + 1e-9); fp.t2_safe = fp.t2_in * (1.0 - 1e-9);
+		fp.u_tab_lo = 0; fp.tab_base = 0; fp.tab_rows = 0; fp.tab_len = 0;
+		if (cf.polar_ewald) {
+			const long double a = e->cell.polar_alpha, osp = 0.5641895835477562869480794515607725858440506293289988L;
+			e->field_tab.build(2, std::min(0.25, fp.t2_adm / 64.0), fp.t2_adm * 1.001, [&](long double u, long double *o) {
+				const long double r = sqrtl(u), g = 2.0L * a * osp * expl(-a * a * u) * r;
+				o[0] = (g + erfcl(a * r)) / (u * r);
+				o[1] = (g - erfl(a * r)) / (u * r);
+			}, kTabShiftCoarse);
+			fp.u_tab_lo = e->field_tab.u_lo; fp.tab_base = e->field_tab.base; fp.tab_rows = e->field_tab.nrows; fp.tab_len = (int)e->field_tab.rows.size();
+			if ((rc = e->d_field_tab.ensure(e->field_tab.rows.size()))) return rc;
+			CK(cudaMemcpyAsync(e->d_field_tab.p, e->field_tab.rows.data(), e->field_tab.rows.size() * sizeof(double), cudaMemcpyHostToDevice, e->stream));
+		}
+	}
 	CK(cudaStreamSynchronize(e->stream));
 	return MPMC_OK;
 }
@@ -596,6 +639,30 @@ static int run_structure(mpmc_engine *e, DevBuf<int> &list, int nlist, DevBuf<do
 	return MPMC_OK;
 }
 
+// real-space part of the static field, added into d_efs: (mobile rows x all charged columns) + (frozen rows x mobile charged columns)
+template <bool ORTHO, bool EWALD>
+static int run_field_real(mpmc_engine *e) {
+	const int n = e->n, B = e->B;
+	const size_t smem = EWALD ? sizeof(double) * (size_t)e->fpar.tab_len : 0;
+	struct Job { const int *rows; int nrows; const int *cols; int ncols; };
+	const Job jobs[2] = {{e->d_mobile_sites.p, (int)e->mobile_sites.size(), e->d_allq.p, (int)e->allq.size()},
+	                     {e->d_frozen_sites.p, (int)e->frozen_sites.size(), e->d_mobile_q.p, (int)e->mobile_q.size()}};
+	for (const Job &j : jobs) {
+		if (j.nrows == 0 || j.ncols == 0) continue;
+		const int row_blocks = (j.nrows + kOrdI - 1) / kOrdI * B;
+		int parts = std::max(1, std::min(32, (8 * e->num_sms + row_blocks - 1) / row_blocks));
+		int len = (j.ncols + parts - 1) / parts;
+		len = std::max(kOrdJ, (len + kOrdJ - 1) / kOrdJ * kOrdJ);
+		parts = (j.ncols + len - 1) / len;
+		k_field_parts<ORTHO, EWALD><<<dim3((j.nrows + kOrdI - 1) / kOrdI, parts, B), kOrdThreads, smem, e->stream>>>(
+		    e->d_posq.p, e->d_meta.p, j.cols, j.ncols, len, j.rows, j.nrows, e->cap, e->cell, e->fpar, e->d_field_tab.p, e->d_cparts.p);
+		k_field_finish<<<(j.nrows * B + 127) / 128, 128, 0, e->stream>>>(e->d_cparts.p, parts, j.rows, j.nrows, n, B, e->d_efs.p);
+		e->launches += 2;
+	}
+	CK(cudaGetLastError());
+	return MPMC_OK;
+}
+
 template <bool ORTHO>
 static int run_polar(mpmc_engine *e) {
 	const int n = e->n, B = e->B, np = (int)e->plist.size();
@@ -620,15 +687,11 @@ static int run_polar(mpmc_engine *e) {
 		k_field_recip<<<dim3((n + kFrSites - 1) / kFrSites, B), kFrSites, smem, e->stream>>>(e->d_posq.p, n, e->cap, e->d_kvec.p, nk, kmax, e->d_S_all.p,
 		                                                                                     e->cell, 8.0 * kPi / e->cell.volume, e->d_efs.p);
 		LAUNCHED(e);
- }{ Timed _t(e, MPMC_K_FIELD_REAL);
-		k_field_real<ORTHO, true><<<ogrid, kOrdThreads, 0, e->stream>>>(e->d_posq.p, e->d_meta.p, e->d_blk_frozen.p, n, e->cap, e->cell, e->d_efs.p);
-		LAUNCHED(e);
- }	} else {
+ }		{ Timed _t(e, MPMC_K_FIELD_REAL); if ((rc = run_field_real<ORTHO, true>(e))) return rc; }
+	} else {
 		CK(cudaMemsetAsync(e->d_efs.p, 0, len * sizeof(double), e->stream));
-{ Timed _t(e, MPMC_K_FIELD_REAL);
-		k_field_real<ORTHO, false><<<ogrid, kOrdThreads, 0, e->stream>>>(e->d_posq.p, e->d_meta.p, e->d_blk_frozen.p, n, e->cap, e->cell, e->d_efs.p);
-		LAUNCHED(e);
- }	}
+		{ Timed _t(e, MPMC_K_FIELD_REAL); if ((rc = run_field_real<ORTHO, false>(e))) return rc; }
+	}
 	PolarDev pd;
 	pd.damp = cf.polar_damp; pd.gamma = cf.polar_gamma; pd.damp_type = cf.damp_type;
 	pd.gs = cf.polar_gs || cf.polar_gs_ranked; pd.sor = cf.polar_sor; pd.esor = cf.polar_esor;
@@ -642,13 +705,64 @@ static int run_polar(mpmc_engine *e) {
 	// GS ranking (System.cpp:1000-1029) — the metric only depends on the geometry, so both sweep orders are known up front
 	const bool ranked = cf.polar_gs_ranked && !cf.polar_zodid;
 	if (ranked && np > 0) {
-		k_fill_u64<<<1, 32, 0, e->stream>>>(e->d_rmin.p, B, 0x7ff0000000000000ull);   // +inf
+		Timed _t(e, MPMC_K_RANK);
+		auto split = [&](int nrows, int ncols, int &parts, int &plen) {
+			const int row_blocks = std::max(1, (nrows + kOrdI - 1) / kOrdI) * B;
+			parts = std::max(1, std::min(32, (8 * e->num_sms + row_blocks - 1) / row_blocks));
+			plen = (std::max(ncols, 1) + parts - 1) / parts;
+			plen = std::max(kOrdJ, (plen + kOrdJ - 1) / kOrdJ * kOrdJ);
+			parts = std::max(1, (std::max(ncols, 1) + plen - 1) / plen);
+		};
+		const int nfp = (int)e->fp_list.size(), nmp = (int)e->mp_list.size();
+		int parts, plen;
+		const unsigned long long inf_bits = 0x7ff0000000000000ull;
+		if (e->rank_ff_dirty) {
+			// the frozen-frozen part depends only on the frozen coordinates: once per topology / cell / framework move
+			k_fill_u64<<<1, 32, 0, e->stream>>>(e->d_r2min_ff.p, B, inf_bits);
+			k_fill_u64<<<1, 32, 0, e->stream>>>((unsigned long long *)e->d_t2_cached.p, B, 0xbff0000000000000ull);   // -1: no cached counts
+			CK(cudaMemsetAsync(e->d_cnt_ff.p, 0, sizeof(double) * (size_t)B * n, e->stream));
+			e->launches += 2;
+			if (nfp > 1) {
+				split(nfp, nfp, parts, plen);
+				k_rank_min_parts<ORTHO><<<dim3((nfp + kOrdI - 1) / kOrdI, parts, B), kOrdThreads, 0, e->stream>>>(e->d_posq.p, e->d_fp_list.p, nfp, plen, e->d_fp_list.p, nfp,
+				                                                                                                e->cap, e->cell, e->d_r2min_ff.p);
+				LAUNCHED(e);
+			}
+			e->rank_ff_dirty = false;
+		}
+		k_fill_u64<<<1, 32, 0, e->stream>>>(e->d_rmin.p, B, inf_bits);
 		LAUNCHED(e);
-{ Timed _t(e, MPMC_K_RANK);
-		k_rank_rmin<ORTHO><<<ogrid, kOrdThreads, 0, e->stream>>>(e->d_posq.p, e->d_alpha.p, n, e->cap, e->cell, e->d_rmin.p);
-		k_rank_count<<<ogrid, kOrdThreads, 0, e->stream>>>(e->d_posq.p, e->d_alpha.p, n, e->cap, e->d_rmin.p, e->d_rank.p);
+		if (nmp > 0) {   // every pair with a mobile member (the frozen x mobile pairs by symmetry)
+			split(nmp, np, parts, plen);
+			k_rank_min_parts<ORTHO><<<dim3((nmp + kOrdI - 1) / kOrdI, parts, B), kOrdThreads, 0, e->stream>>>(e->d_posq.p, e->d_plist.p, np, plen, e->d_mp_list.p, nmp,
+			                                                                                                e->cap, e->cell, e->d_rmin.p);
+			LAUNCHED(e);
+		}
+		k_rank_lim<<<(B + 31) / 32, 32, 0, e->stream>>>(e->d_rmin.p, e->d_r2min_ff.p, B, e->d_t2.p, e->d_t2_cached.p, e->d_recount.p);
+		k_rank_clear_gated<<<(unsigned)(((size_t)B * n + 255) / 256), 256, 0, e->stream>>>(e->d_recount.p, n, B, e->d_cnt_ff.p);
 		e->launches += 2;
- }	} else CK(cudaMemsetAsync(e->d_rank.p, 0, sizeof(double) * (size_t)B * n, e->stream));
+		if (nfp > 1) {   // skipped on the device unless 1.5 rmin changed
+			split(nfp, nfp, parts, plen);
+			k_rank_count_parts<<<dim3((nfp + kOrdI - 1) / kOrdI, parts, B), kOrdThreads, 0, e->stream>>>(e->d_posq.p, e->d_fp_list.p, nfp, plen, e->d_fp_list.p, nfp, n, e->cap,
+			                                                                                           e->d_t2.p, e->d_recount.p, e->d_cnt_ff.p);
+			LAUNCHED(e);
+		}
+		k_rank_init<<<(unsigned)(((size_t)B * n + 255) / 256), 256, 0, e->stream>>>(e->d_cnt_ff.p, n, B, e->d_rank.p);
+		LAUNCHED(e);
+		if (nmp > 0) {
+			split(nmp, np, parts, plen);
+			k_rank_count_parts<<<dim3((nmp + kOrdI - 1) / kOrdI, parts, B), kOrdThreads, 0, e->stream>>>(e->d_posq.p, e->d_plist.p, np, plen, e->d_mp_list.p, nmp, n, e->cap,
+			                                                                                           e->d_t2.p, nullptr, e->d_rank.p);
+			LAUNCHED(e);
+			if (nfp > 0) {
+				split(nfp, nmp, parts, plen);
+				k_rank_count_parts<<<dim3((nfp + kOrdI - 1) / kOrdI, parts, B), kOrdThreads, 0, e->stream>>>(e->d_posq.p, e->d_mp_list.p, nmp, plen, e->d_fp_list.p, nfp, n, e->cap,
+				                                                                                           e->d_t2.p, nullptr, e->d_rank.p);
+				LAUNCHED(e);
+			}
+		}
+		CK(cudaGetLastError());
+	} else CK(cudaMemsetAsync(e->d_rank.p, 0, sizeof(double) * (size_t)B * n, e->stream));
 
 	e->last_iterations = 0;
 	std::fill(e->last_failed.begin(), e->last_failed.end(), 0);
@@ -718,14 +832,6 @@ static int run_polar(mpmc_engine *e) {
 			}
 			int ns = 1;
 			if (!need_old && !want_check && cf.polar_precision == 0.0) ns = (ranked && it == 1) ? 1 : (cf.polar_max_iter - it + 1);
-			CK(cudaMemsetAsync(e->d_gsctl.p, 0, sizeof(int) * (sizeof(GsCtl) / sizeof(int) + nchunks), e->stream));
-			const double4 *gpq = e->d_gpq.p;
-			const int *gmeta = e->d_gmeta.p;
-			const double *efs = e->d_efs.p, *tri = e->d_tri.p;
-			double *mu = e->d_mu.p, *efi = e->d_efi.p, *nmu = e->d_new_mu.p, *acc = e->d_acc.p, *dmu = e->d_dmu.p;
-			GsCtl *ctl = (GsCtl *)e->d_gsctl.p;
-			int npv = np;
-			CellDev cell = e->cell;
 			long long *prof = nullptr;
 			if (e->gs_prof_enabled) {
 				if ((rc = e->d_gsprof.ensure((size_t)nblk * 16))) return rc;
@@ -733,12 +839,17 @@ static int run_polar(mpmc_engine *e) {
 				prof = e->d_gsprof.p;
 				e->gs_prof_nblk = nblk;
 			}
-			void *args[] = {&gpq, &gmeta, &gs_order, &npv, &cell, &pd, &efs, &mu, &efi, &nmu, &acc, &dmu, &tri, &ctl, &ns, &prof};
 			{
 				Timed _t(e, MPMC_K_GS_SWEEP);
-				const void *fn = expd ? (const void *)k_gs_pipeline<ORTHO, true> : (const void *)k_gs_pipeline<ORTHO, false>;
-				CK(cudaLaunchCooperativeKernel(fn, dim3(e->gs_grid), dim3(kGsThreads), args, kGsSmemBytes, e->stream));
-				LAUNCHED(e);
+				for (int sw = 0; sw < ns; sw++) {   // one launch per sweep: the kernel boundary is the barrier between sweeps
+					CK(cudaMemsetAsync(e->d_gsctl.p, 0, sizeof(int) * (sizeof(GsCtl) / sizeof(int) + nchunks), e->stream));
+					if (expd) k_gs_pipeline<ORTHO, true><<<e->gs_grid, kGsThreads, kGsSmemBytes, e->stream>>>(e->d_gpq.p, e->d_gmeta.p, gs_order, np, e->cell, pd, e->d_efs.p,
+					        e->d_mu.p, e->d_efi.p, e->d_new_mu.p, e->d_acc.p, e->d_dmu.p, e->d_tri.p, (GsCtl *)e->d_gsctl.p, sw == 0 ? prof : nullptr);
+					else k_gs_pipeline<ORTHO, false><<<e->gs_grid, kGsThreads, kGsSmemBytes, e->stream>>>(e->d_gpq.p, e->d_gmeta.p, gs_order, np, e->cell, pd, e->d_efs.p,
+					        e->d_mu.p, e->d_efi.p, e->d_new_mu.p, e->d_acc.p, e->d_dmu.p, e->d_tri.p, (GsCtl *)e->d_gsctl.p, sw == 0 ? prof : nullptr);
+					LAUNCHED(e);
+				}
+				CK(cudaGetLastError());
 			}
 			it += ns - 1;
 		}
@@ -874,6 +985,8 @@ int mpmc_create(const mpmc_config *cfg, mpmc_engine **out) {
 	    (rc = set_smem(k_field_recip, sizeof(double2) * kFrSites * 3 * (kMaxKmax + 1))) ||
 	    false) { mpmc_destroy(e); return rc; }
 	{
+		const size_t fmax = 96 * 1024;
+		if ((rc = set_smem(k_field_parts<true, true>, fmax)) || (rc = set_smem(k_field_parts<false, true>, fmax))) { mpmc_destroy(e); return rc; }
 		if ((rc = set_smem(k_gs_pipeline<true, true>, kGsSmemBytes)) || (rc = set_smem(k_gs_pipeline<false, true>, kGsSmemBytes)) ||
 		    (rc = set_smem(k_gs_pipeline<true, false>, kGsSmemBytes)) || (rc = set_smem(k_gs_pipeline<false, false>, kGsSmemBytes))) { mpmc_destroy(e); return rc; }
 	}
@@ -884,7 +997,18 @@ int mpmc_create(const mpmc_config *cfg, mpmc_engine **out) {
 		const char *v1 = getenv("MPMC_PAIR_V1");
 		e->pair_v1 = v1 && v1[0] == '1';
 	}
-	e->gs_grid = e->num_sms;   // one CTA per SM: the solver's shared memory (table + block tensors) fills an SM
+	{
+		// the Gauss-Seidel pipeline needs every CTA resident (its CTAs wait on each other's flags): as many clusters of kGsCluster CTAs
+		// as the device can hold at one CTA per SM
+		cudaLaunchConfig_t lc = {};
+		lc.gridDim = dim3(e->num_sms / kGsCluster * kGsCluster); lc.blockDim = dim3(kGsThreads); lc.dynamicSmemBytes = kGsSmemBytes;
+		cudaLaunchAttribute at[1];
+		at[0].id = cudaLaunchAttributeClusterDimension; at[0].val.clusterDim.x = kGsCluster; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+		lc.attrs = at; lc.numAttrs = 1;
+		int ncl = 0;
+		CK(cudaOccupancyMaxActiveClusters(&ncl, k_gs_pipeline<true, true>, &lc));
+		e->gs_grid = std::max(2, ncl) * kGsCluster;
+	}
 	if ((rc = compute_cell(e, cfg->basis))) { mpmc_destroy(e); return rc; }
 	if (cfg->capacity > 0) e->cap = cfg->capacity;
 	*out = e;
@@ -900,7 +1024,7 @@ int mpmc_destroy(mpmc_engine *e) {
 	e->d_tiles.release(); e->d_segs.release(); e->d_item_seg.release(); e->d_pmeta.release(); e->d_erf_tab.release(); e->d_blk_frozen.release(); e->d_mol_mobile.release(); e->d_kvec.release(); e->d_partials.release();
 	e->d_sk_part.release(); e->d_S_mobile.release(); e->d_S_frozen.release(); e->d_S_all.release();
 	e->d_efs.release(); e->d_efi.release(); e->d_efic.release(); e->d_mu.release(); e->d_new_mu.release(); e->d_old_mu.release();
-	e->d_rrms.release(); e->d_rank.release(); e->d_acc.release(); e->d_dmu.release(); e->d_tri.release(); e->d_gsctl.release(); e->d_gmeta.release(); e->d_nplist.release(); e->d_gpq.release(); e->d_cparts.release(); e->d_com.release(); e->d_mol_mass.release(); e->d_chain.release();
+	e->d_rrms.release(); e->d_rank.release(); e->d_acc.release(); e->d_dmu.release(); e->d_tri.release(); e->d_gsctl.release(); e->d_gmeta.release(); e->d_nplist.release(); e->d_gpq.release(); e->d_cparts.release(); e->d_field_tab.release(); e->d_fp_list.release(); e->d_mp_list.release(); e->d_recount.release(); e->d_r2min_ff.release(); e->d_t2.release(); e->d_t2_cached.release(); e->d_cnt_ff.release(); e->d_mobile_sites.release(); e->d_frozen_sites.release(); e->d_allq.release(); e->d_com.release(); e->d_mol_mass.release(); e->d_chain.release();
 	e->d_rmin.release(); e->d_result.release();
 	if (e->h_stage) cudaFreeHost(e->h_stage);
 	if (e->h_result) cudaFreeHost(e->h_result);
@@ -947,7 +1071,7 @@ int mpmc_update_sites(mpmc_engine *e, int bead, int first, int count, const doub
 	CK(cudaSetDevice(e->dev));
 	if (bead < 0 || bead >= e->B || first < 0 || count < 0 || first + count > e->n) FAIL(MPMC_ERR_INVALID_INPUT, "update_sites: range out of bounds");
 	memcpy(&e->h_pos[((size_t)bead * e->n + first) * 3], pos, sizeof(double) * 3 * count);
-	for (int i = first; i < first + count; i++) if (e->h_frozen[i] && e->h_q[i] != 0.0) e->frozen_sk_dirty = true;
+	for (int i = first; i < first + count; i++) if (e->h_frozen[i]) { e->rank_ff_dirty = true; if (e->h_q[i] != 0.0) e->frozen_sk_dirty = true; }
 	return push_positions(e, bead, bead + 1, first, count);
 }
 
@@ -955,7 +1079,7 @@ int mpmc_update_sites_all_beads(mpmc_engine *e, int first, int count, const doub
 	CK(cudaSetDevice(e->dev));
 	if (first < 0 || count < 0 || first + count > e->n) FAIL(MPMC_ERR_INVALID_INPUT, "update_sites: range out of bounds");
 	for (int b = 0; b < e->B; b++) memcpy(&e->h_pos[((size_t)b * e->n + first) * 3], pos + (size_t)b * count * 3, sizeof(double) * 3 * count);
-	for (int i = first; i < first + count; i++) if (e->h_frozen[i] && e->h_q[i] != 0.0) e->frozen_sk_dirty = true;
+	for (int i = first; i < first + count; i++) if (e->h_frozen[i]) { e->rank_ff_dirty = true; if (e->h_q[i] != 0.0) e->frozen_sk_dirty = true; }
 	return push_positions(e, 0, e->B, first, count);
 }
 
@@ -1190,6 +1314,7 @@ int mpmc_debug_gs_profile(mpmc_engine *e, int enable, long long *out, int max_bl
 	CK(cudaSetDevice(e->dev));
 	e->gs_prof_enabled = enable != 0;
 	{ const int dbg = enable & ~1; CK(cudaMemcpyToSymbol(g_gs_debug, &dbg, sizeof(int))); }
+	if (nblk) *nblk = e->gs_grid;
 	if (out && e->d_gsprof.p && e->gs_prof_nblk) {
 		CK(cudaStreamSynchronize(e->stream));
 		const int nb = std::min(max_blocks, e->gs_prof_nblk);

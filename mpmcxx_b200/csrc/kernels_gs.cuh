@@ -6,22 +6,24 @@
 //       acc_i = sum_{j != i} T_ij mu_j(current)
 // so that a site's update is just  mu_i = alpha_i (E_s,i - acc_i),  and the change  dmu_i = mu_i(new) - mu_i(old)  is pushed
 // into every other row:  acc_m += T_mi dmu_i.  Sites are processed in blocks of kGsB = 64 in sweep order ("panels"):
-//   * the SOLVER CTA (block 0) owns the critical path.  One warp walks a block (two rows per lane in registers, the block's
-//     tensors in shared memory, tensor loads issued one step ahead of the dependent chain).  While it walks, six other warps
-//     push every column, as soon as it is final, into the 64 rows of the NEXT block (so that push costs the critical path only
-//     its tail), a seventh fetches the next block's site columns, and the next block's tensors stream into the second
-//     shared-memory buffer with cp.async.  Nothing on the critical path crosses the chip.
-//   * the UPDATER CTAs (one per remaining SM) push each published panel into all other rows — 8 rows per warp, 4 column lanes
-//     per row, every warp on its own — in panel order, and flag each 8-row chunk when it has received a panel.  The rows of
-//     panels p and p+1 are the solver's, so an updater has a whole block period before its work is needed: its flag latency is
-//     off the critical path.
-//   * the solver may start block b when its rows have received panels 0..b-3 from the updaters (panels b-2 and b-1 are its own
-//     pushes): an updater has two block periods (~10 us) to deliver, which is what a flag - fence - load - compute - fence - flag
-//     round trip across the chip takes.
+//   * the SOLVER CTA (block 0) owns the critical path and keeps its SM quiet: one warp walks a block (two rows per lane in
+//     registers, the block's tensor matrix in shared memory, tensor loads one column ahead of the dependent chain; ~135
+//     cycles per site on B200, see tools/ubench/walk_ubench.cu), a second warp rolls the next block's tensors into the columns
+//     the walk has left behind and fetches the next block's site columns, a third publishes the panel.
+//   * three HELPER CTAs share a thread-block cluster with the solver.  They read every finished column straight out of the
+//     solver's shared memory (distributed shared memory: no trip through L2, no flag round trip) and push it into the rows
+//     of the next kGsAhead = 3 blocks, then drop their sums into the solver's shared memory.  Those are the rows the walk
+//     needs next; doing them inside the cluster costs the critical path only the tail of the last few columns.
+//   * the UPDATER CTAs (every other SM) push each published panel into all remaining rows — 8 rows per warp, 4 column lanes
+//     per row, every warp on its own — in panel order, and flag each 8-row chunk when it has received a panel.  An updater
+//     has kGsAhead block periods (~20 us) to deliver, several times what a flag - fence - load - compute - fence - flag round
+//     trip across the chip takes (~10 us measured), so that latency never reaches the solver.
+//   * the solver may start block b when its rows have received panels 0..b-1-kGsAhead from the updaters; the later panels
+//     are the cluster's own pushes.
 // Every row receives its updates in a fixed order, so the result does not depend on timing.  Pushing panels into rows that
 // were already swept prepares acc for the next sweep, and after the last sweep acc_i is exactly the contraction
 // palmo_contraction() needs (:3602-3627), so Palmo costs no extra sweep.
-// One cooperative launch runs `nsweeps` sweeps (grid barrier between sweeps); all CTAs are co-resident, which makes the
+// One launch = one sweep; every CTA must be resident (the grid is sized from cudaOccupancyMaxActiveClusters), which makes the
 // flag waits safe.
 #pragma once
 #include <cuda_pipeline.h>
@@ -38,9 +40,10 @@ constexpr int kGsMat = kGsB * kGsB * 6;   // doubles of one block's tensor matri
 // shared memory (doubles).  Solver: the block's tensor matrix, two site-column buffers, pending push (3 slices + sum), two row
 // buffers, panel dmu, the walk's results, ints.  Updaters: per warp the panel's columns and dmu.
 constexpr int kGsSiteCols = 10;           // 0 alpha, 1-3 mu_old, 4-6 E_static, 7-9 acc
-constexpr int kGsAhead = 2;               // the solver pushes a panel into this many following blocks itself; the updaters take the rest
-constexpr int kGsPushWarps = 6, kGsPushThreads = kGsPushWarps * 32;
-constexpr size_t kGsSolverDoubles = (size_t)kGsMat + kGsSiteCols * kGsB + 3 * (kGsAhead * kGsB * 3) + 3 * 3 * kGsB + 3 * 4 * kGsB + 4 * kGsB + 3 * kGsB + 16;
+constexpr int kGsAhead = 3;               // the cluster pushes a panel into this many following blocks itself; the updaters take the rest
+constexpr int kGsHelpers = 3, kGsCluster = 1 + kGsHelpers;
+constexpr int kGsSlots = kGsAhead + 1;    // ring of per-block buffers
+constexpr size_t kGsSolverDoubles = (size_t)kGsMat + kGsSiteCols * kGsB + kGsHelpers * (kGsAhead * kGsB * 3) + kGsSlots * 3 * kGsB + 4 * kGsB + 2 * kGsB + 16;
 constexpr size_t kGsUpdaterDoubles = (size_t)kGsWarps * 8 * kGsB;
 constexpr size_t kGsSmemBytes = sizeof(double) * (kGsSolverDoubles > kGsUpdaterDoubles ? kGsSolverDoubles : kGsUpdaterDoubles);
 
@@ -105,290 +108,325 @@ k_gs_tensors(const double4 *__restrict__ gpq, const int *__restrict__ gmeta, int
 	}
 }
 
+// what the cluster shares: the solver's shared-memory words the helpers read (progress, dmu) and write (partial pushes, done)
+struct GsShared { int prog; int done; int loaded; int pad; };
+
 template <bool ORTHO, bool EXPD>
-__global__ void __launch_bounds__(kGsThreads, 1)
+__global__ void __cluster_dims__(kGsCluster, 1, 1) __launch_bounds__(kGsThreads, 1)
 k_gs_pipeline(const double4 *__restrict__ gpq, const int *__restrict__ gmeta, const int *__restrict__ order, int np, CellDev c, PolarDev p,
               const double *__restrict__ efs, double *mu, double *efi, double *new_mu, double *acc, double *dmu,
-              const double *__restrict__ tri, GsCtl *ctl, int nsweeps, long long *prof) {
-	cg::grid_group grid = cg::this_grid();
+              const double *__restrict__ tri, GsCtl *ctl, long long *prof) {
+	cg::cluster_group cluster = cg::this_cluster();
 	extern __shared__ __align__(16) double s_raw[];
 	int *applied = (int *)(ctl + 1);
 	const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-	const int G = gridDim.x, cta = blockIdx.x, U = G - 1;
+	const int cta = blockIdx.x, U = gridDim.x - kGsCluster;
 	const int nblk = (np + kGsB - 1) / kGsB, nchunks = (np + kGsRows - 1) / kGsRows;
 	constexpr int kChunksPerBlk = kGsB / kGsRows;
+	// the solver's layout (helpers address the shared part of it through the cluster)
+	double *s_mat = s_raw;                                         // [kGsB columns][kGsB rows][6], rolled: column k of the next block replaces column k once the walk has passed it
+	double *s_site = s_mat + kGsMat;                               // [kGsSiteCols][kGsB]
+	double *s_pendp = s_site + kGsSiteCols * kGsB;                 // [kGsHelpers][kGsAhead * kGsB][3] the helpers' pushes of the last panel
+	double *s_pend = s_pendp + kGsHelpers * (kGsAhead * kGsB * 3); // [kGsSlots][kGsB][3] pushes already made into the rows of blocks b .. b+kGsAhead (slot = block % kGsSlots)
+	double4 *s_dm = (double4 *)(s_pend + kGsSlots * 3 * kGsB);     // [kGsB] dmu of the block being walked
+	int *s_idx = (int *)(s_dm + kGsB);                             // [2][kGsB] site ids of this block / the next block
+	GsShared *s_sh = (GsShared *)(s_idx + 2 * kGsB);
 
-	for (int sweep = 0; sweep < nsweeps; sweep++) {
-		if (cta == 0) {
-			// ------------------------------------------------ solver ------------------------------------------------
-			double *s_mat = s_raw;                                         // [kGsB columns][kGsB rows][6], rolled: column k of the next block replaces column k once the walk has passed it
-			double *s_site = s_mat + kGsMat;                               // [kGsSiteCols][kGsB]
-			double *s_pendp = s_site + kGsSiteCols * kGsB;                 // [3][kGsAhead * kGsB][3] partial pushes of the panel being walked
-			double *s_pend = s_pendp + 3 * (kGsAhead * kGsB * 3);          // [3][kGsB][3] pushes already made into the rows of blocks b, b+1, b+2 (slot = block % 3)
-			double4 *s_rows = (double4 *)(s_pend + 3 * 3 * kGsB);          // [3][kGsB] x y z alpha of blocks b, b+1, b+2 (slot = block % 3)
-			double4 *s_dm = s_rows + 3 * kGsB;                             // [kGsB] dmu of the block being walked
-			int *s_meta = (int *)(s_dm + kGsB);                            // [3][kGsB]
-			int *s_idx = s_meta + 3 * kGsB;                                // [3][kGsB] site ids
-			volatile int *s_prog = (volatile int *)(s_idx + 3 * kGsB);     // columns of the current walk that are final
-			auto load_rows = [&](int blk, int m) {                         // position, alpha, meta and site id of row m of block blk
-				const int pos = blk * kGsB + m, b = blk % 3;
-				const bool on = pos < np;
-				s_idx[b * kGsB + m] = on ? order[pos] : 0;
-				s_rows[b * kGsB + m] = on ? gpq[pos] : make_double4(0, 0, 0, 0);
-				s_meta[b * kGsB + m] = on ? gmeta[pos] : 0;
-			};
-			auto load_cols = [&](int blk, int m) {                         // site columns of row m (all but the running contraction); after load_rows
-				const int b = blk % 3;
-				const bool on = blk * kGsB + m < np;
-				const int s = s_idx[b * kGsB + m];
-				s_site[m] = s_rows[b * kGsB + m].w;
-				for (int q = 0; q < 3; q++) {
-					s_site[(1 + q) * kGsB + m] = on ? __ldcg(mu + 3 * s + q) : 0.0;
-					s_site[(4 + q) * kGsB + m] = on ? efs[3 * s + q] : 0.0;
-				}
-			};
-			auto load_acc = [&](int blk, int m) {                          // running contraction of row m as the updaters left it
-				const bool on = blk * kGsB + m < np;
-				const int s = s_idx[(blk % 3) * kGsB + m];
-				for (int q = 0; q < 3; q++) s_site[(7 + q) * kGsB + m] = on ? __ldcg(acc + 3 * s + q) : 0.0;
-			};
-			for (int q = tid; q < 3 * 3 * kGsB; q += kGsThreads) s_pend[q] = 0.0;
-			{
-				const double2 *src = (const double2 *)tri;
-				double2 *dst = (double2 *)s_mat;
-				for (int q = tid; q < kGsMat / 2; q += kGsThreads) __pipeline_memcpy_async(dst + q, src + q, sizeof(double2));
-				__pipeline_commit();
+	if (cta == 0) {
+		// ------------------------------------------------ solver ------------------------------------------------
+		volatile int *s_prog = &s_sh->prog;                        // blk * kGsB + columns of the walk that are final
+		volatile int *s_done = &s_sh->done;                        // helpers that have delivered, summed over panels
+		volatile int *s_loaded = &s_sh->loaded;                    // blocks whose site columns the walker has taken into registers
+		auto load_cols = [&](int blk, int m) {                     // site id and site columns of row m (all but the running contraction)
+			const int pos = blk * kGsB + m;
+			const bool on = pos < np;
+			const int s = on ? order[pos] : 0;
+			s_idx[(blk & 1) * kGsB + m] = s;
+			s_site[m] = on ? gpq[pos].w : 0.0;
+			for (int q = 0; q < 3; q++) {
+				s_site[(1 + q) * kGsB + m] = on ? __ldcg(mu + 3 * s + q) : 0.0;
+				s_site[(4 + q) * kGsB + m] = on ? efs[3 * s + q] : 0.0;
 			}
-			if (tid < kGsB) { load_rows(0, tid); load_cols(0, tid); load_acc(0, tid); }
-			else if (tid < 2 * kGsB) load_rows(1, tid - kGsB);
-			if (tid == 0) *s_prog = 0;
-			for (int blk = 0; blk < nblk; blk++) {
-				const int base = blk * kGsB, cnt = min(kGsB, np - base), cur = blk % 3;
-				if (prof && tid == 0 && sweep == 0) prof[blk * 8 + 0] = clock64();
-				// (A) the running contraction of this block's rows = what the updaters left (fetched during the previous walk)
-				//     + my own pushes of the two previous panels.  Rows of block b+2 for the pushing warps.
-				__pipeline_wait_prior(0);
+		};
+		auto load_acc = [&](int blk, int m) {                      // running contraction of row m as the updaters left it
+			const bool on = blk * kGsB + m < np;
+			const int s = s_idx[(blk & 1) * kGsB + m];
+			for (int q = 0; q < 3; q++) s_site[(7 + q) * kGsB + m] = on ? __ldcg(acc + 3 * s + q) : 0.0;
+		};
+		for (int q = tid; q < kGsSlots * 3 * kGsB; q += kGsThreads) s_pend[q] = 0.0;
+		{
+			const double2 *src = (const double2 *)tri;
+			double2 *dst = (double2 *)s_mat;
+			for (int q = tid; q < kGsMat / 2; q += kGsThreads) __pipeline_memcpy_async(dst + q, src + q, sizeof(double2));
+			__pipeline_commit();
+		}
+		if (tid < kGsB) { load_cols(0, tid); load_acc(0, tid); }
+		if (tid == 0) { *s_prog = 0; *s_done = 0; *s_loaded = 0; }
+		cluster.sync();                                            // the helpers may look at prog / done from here on
+		for (int blk = 0; blk < nblk; blk++) {
+			const int base = blk * kGsB, cnt = min(kGsB, np - base);
+			if (prof && tid == 0) prof[blk * 8 + 0] = clock64();
+			// (A) fold the helpers' pushes of the previous panel into the pending sums (fixed order), then the running contraction
+			//     of this block's rows = what the updaters left (fetched during the previous walk) + the cluster's own pushes
+			if (blk > 0) {
+				if (tid == 0) while (*s_done < kGsHelpers * blk) { }
 				__syncthreads();
-				if (tid < kGsB) { for (int q = 0; q < 3; q++) s_site[(7 + q) * kGsB + tid] += s_pend[(cur * kGsB + tid) * 3 + q]; }
-				else if (tid < 2 * kGsB) load_rows(blk + 2, tid - kGsB);
-				__syncthreads();
-				if (prof && tid == 0 && sweep == 0) prof[blk * 8 + 1] = clock64();
-				// (B) warp 0 walks.  Warps 1-3 and 5-7 push every column, as soon as it is final, into the rows of the next two
-				//     blocks and publish the panel.  Warp 4 (the walker's scheduler partner: kept light, and asleep while it waits)
-				//     rolls the next block's tensors into the columns the walk has left behind and fetches the next block's site columns.
-				if (warp == 0) {
-					// lane owns rows lane (slot 0) and lane+32 (slot 1); everything a row needs lives in registers during the walk.
-					// With c = alpha E_s - mu_old the change of a dipole is a single FMA:  dmu = c - alpha acc.
-					double al[2], cx[2], cy[2], cz[2], ax[2], ay[2], az[2], ex[2], ey[2], ez[2], sx[2], sy[2], sz[2];
-#pragma unroll
-					for (int h = 0; h < 2; h++) {
-						const int m = lane + 32 * h;
-						al[h] = s_site[m];
-						sx[h] = s_site[4 * kGsB + m]; sy[h] = s_site[5 * kGsB + m]; sz[h] = s_site[6 * kGsB + m];
-						cx[h] = al[h] * sx[h] - s_site[1 * kGsB + m];
-						cy[h] = al[h] * sy[h] - s_site[2 * kGsB + m];
-						cz[h] = al[h] * sz[h] - s_site[3 * kGsB + m];
-						ax[h] = s_site[7 * kGsB + m]; ay[h] = s_site[8 * kGsB + m]; az[h] = s_site[9 * kGsB + m];
-						ex[h] = ey[h] = ez[h] = 0;
-					}
-					__syncwarp();
-					if (lane == 0) *s_prog = -1;                                  // the site columns are in registers: warp 4 may refill them
-					// tensor entries of column k for my two rows: (xx yy) (zz xy) (xz yz); always one column ahead of the dependent chain
-					const double2 *tcol = (const double2 *)s_mat + lane * 3;
-					double2 tn[2][3];
-#pragma unroll
-					for (int hh = 0; hh < 2; hh++) { tn[hh][0] = tcol[hh * 96]; tn[hh][1] = tcol[hh * 96 + 1]; tn[hh][2] = tcol[hh * 96 + 2]; }
-#pragma unroll
-					for (int half = 0; half < 2; half++) {
-						const int kend = min(32, cnt - 32 * half);
-#pragma unroll 2
-						for (int kk = 0; kk < kend; kk++) {
-							const int k = kk + 32 * half;
-							double2 tc[2][3];
-							const double2 *tnext = tcol + min(k + 1, kGsB - 1) * (kGsB * 3);
-#pragma unroll
-							for (int hh = 0; hh < 2; hh++) {
-								tc[hh][0] = tn[hh][0]; tc[hh][1] = tn[hh][1]; tc[hh][2] = tn[hh][2];
-								tn[hh][0] = tnext[hh * 96]; tn[hh][1] = tnext[hh * 96 + 1]; tn[hh][2] = tnext[hh * 96 + 2];
-							}
-							// every lane forms the candidate change of its own slot-`half` row; the owner's is the real one
-							const double dxc = fma(-al[half], ax[half], cx[half]), dyc = fma(-al[half], ay[half], cy[half]), dzc = fma(-al[half], az[half], cz[half]);
-							const double dx = __shfl_sync(0xffffffffu, dxc, kk), dy = __shfl_sync(0xffffffffu, dyc, kk), dz = __shfl_sync(0xffffffffu, dzc, kk);
-							if (lane == kk) { ex[half] = ax[half]; ey[half] = ay[half]; ez[half] = az[half]; }   // acc at the moment of the update
-#pragma unroll
-							for (int hh = 0; hh < 2; hh++) {                      // the diagonal entry is zero: a row does not move itself
-								ax[hh] = fma(tc[hh][0].x, dx, fma(tc[hh][1].y, dy, fma(tc[hh][2].x, dz, ax[hh])));
-								ay[hh] = fma(tc[hh][1].y, dx, fma(tc[hh][0].y, dy, fma(tc[hh][2].y, dz, ay[hh])));
-								az[hh] = fma(tc[hh][2].x, dx, fma(tc[hh][2].y, dy, fma(tc[hh][1].x, dz, az[hh])));
-							}
-							// hand the finished column to the other warps.  No fence: both stores are volatile shared-memory stores of one
-							// thread, which the LSU performs in program order (a MEMBAR here costs more than the whole step); every lane
-							// stores the same values, so the walk has no divergent region
-							{
-								volatile double *vd = (volatile double *)(s_dm + k);
-								vd[0] = dx; vd[1] = dy; vd[2] = dz;
-								*s_prog = k + 1;
-							}
-						}
-					}
-					if (prof && tid == 0 && sweep == 0) prof[blk * 8 + 2] = clock64();
-					// contract_dipoles: ef_induced = -acc at the moment of the update, mu = alpha (E_s + ef_induced)  (:3583-3592)
-#pragma unroll
-					for (int hh = 0; hh < 2; hh++) {
-						const int m = lane + 32 * hh;
-						if (m < cnt) {
-							const int s = s_idx[cur * kGsB + m];
-							const double nx = al[hh] * (sx[hh] - ex[hh]), ny = al[hh] * (sy[hh] - ey[hh]), nz = al[hh] * (sz[hh] - ez[hh]);
-							__stcg(mu + 3 * s, nx); __stcg(mu + 3 * s + 1, ny); __stcg(mu + 3 * s + 2, nz);
-							new_mu[3 * s] = nx; new_mu[3 * s + 1] = ny; new_mu[3 * s + 2] = nz;
-							efi[3 * s] = -ex[hh]; efi[3 * s + 1] = -ey[hh]; efi[3 * s + 2] = -ez[hh];
-							__stcg(acc + 3 * s, ax[hh]); __stcg(acc + 3 * s + 1, ay[hh]); __stcg(acc + 3 * s + 2, az[hh]);
-						}
-					}
-				} else if (warp == 4) {
-					if (blk + 1 < nblk) {
-						while (*s_prog == 0) __nanosleep(100);                     // the walker has taken the site columns into registers
-						load_cols(blk + 1, lane); load_cols(blk + 1, lane + 32);
-						// roll the next block's tensor matrix in behind the walk: column k is dead once column k+1 has been fetched
-						const double2 *src = (const double2 *)(tri + (size_t)(blk + 1) * kGsMat);
-						double2 *dst = (double2 *)s_mat;
-						int done = 0;
-						while (done < kGsB && !(g_gs_debug & 4)) {
-							int pg = *s_prog;
-							if (pg >= cnt) pg = kGsB;                               // the walk is over: the remaining (unused) columns too
-							if (pg <= done) { __nanosleep(200); continue; }
-							for (int q = done * (kGsB * 3) + lane; q < pg * (kGsB * 3); q += 32) __pipeline_memcpy_async(dst + q, src + q, sizeof(double2));
-							done = pg;
-						}
-						__pipeline_commit();
-						// the running contraction of the next block's rows, once the updaters have applied panels 0..blk-2 to them
-						const int c0 = (base + kGsB) / kGsRows, c1 = min(nchunks, c0 + kChunksPerBlk);
-						if (blk >= kGsAhead && lane < c1 - c0) while (ld_flag(applied + c0 + lane) < blk + 1 - kGsAhead) __nanosleep(100);
-						__syncwarp();
-						__threadfence();
-						load_acc(blk + 1, lane); load_acc(blk + 1, lane + 32);
-					}
-				} else {
-					const int h = (warp < 4 ? warp - 1 : warp - 2) * 32 + lane;       // 0..191
-					const int r4 = h & 31, sl = h >> 5;                                // my four target rows r4 + 32 j; my columns k = sl mod 6 (warp-uniform)
-					double4 pr[4]; int mr[4]; bool on[4];
-					double ax[4] = {0, 0, 0, 0}, ay[4] = {0, 0, 0, 0}, az[4] = {0, 0, 0, 0};
-#pragma unroll
-					for (int j = 0; j < 4; j++) {
-						const int tb = blk + 1 + (j >> 1), row = r4 + 32 * (j & 1);
-						pr[j] = s_rows[(tb % 3) * kGsB + row];
-						mr[j] = s_meta[(tb % 3) * kGsB + row];
-						on[j] = tb < nblk && tb * kGsB + row < np && !(g_gs_debug & 2);
-					}
-					for (int k = (g_gs_debug & 8) ? cnt : sl; k < cnt; k += kGsPushWarps) {
-						while (*s_prog <= k) __nanosleep(40);
-						const volatile double *vd = (const volatile double *)(s_dm + k);
-						const double4 dm = make_double4(vd[0], vd[1], vd[2], 0.0);
-						const double4 pc = s_rows[cur * kGsB + k];
-						const int mc = s_meta[cur * kGsB + k];
-#pragma unroll
-						for (int j = 0; j < 4; j++)
-							if (on[j]) gs_contract<ORTHO, EXPD>(c, p, pr[j], mr[j], pc, mc, dm, ax[j], ay[j], az[j]);
-						// publish the panel: the change of every dipole of the block (the flag follows the barrier)
-						if (r4 == 0) { __stcg(dmu + 3 * (base + k), dm.x); __stcg(dmu + 3 * (base + k) + 1, dm.y); __stcg(dmu + 3 * (base + k) + 2, dm.z); }
-					}
-					if (r4 == 0) __threadfence();
-					// the six column slices of a target row, summed in a fixed order: slices 0-2 store, slices 3-5 add
-					if (sl < 3) {
-#pragma unroll
-						for (int j = 0; j < 4; j++) {
-							double *o = s_pendp + ((sl * kGsAhead * kGsB) + (j >> 1) * kGsB + r4 + 32 * (j & 1)) * 3;
-							o[0] = ax[j]; o[1] = ay[j]; o[2] = az[j];
-						}
-					}
-					asm volatile("bar.sync 1, %0;" ::"n"(kGsPushThreads) : "memory");
-					if (sl >= 3) {
-#pragma unroll
-						for (int j = 0; j < 4; j++) {
-							double *o = s_pendp + (((sl - 3) * kGsAhead * kGsB) + (j >> 1) * kGsB + r4 + 32 * (j & 1)) * 3;
-							o[0] += ax[j]; o[1] += ay[j]; o[2] += az[j];
-						}
-					}
-				}
-				__syncthreads();
-				if (prof && tid == 0 && sweep == 0) prof[blk * 8 + 3] = clock64();
-				// (C) publish the panel (the slice leaders have fenced their dmu stores before the barrier); my pushes of this panel
-				//     into the rows of the next two blocks
-				if (tid == 32) st_flag(&ctl->solved, blk + 1);
+				__threadfence();
 				if (tid < kGsAhead * kGsB) {
-					const int tb = blk + 1 + tid / kGsB, row = tid % kGsB;
-					double *dst = s_pend + ((tb % 3) * kGsB + row) * 3;
+					const int j = tid / kGsB, row = tid % kGsB;         // target block blk + j
+					double *dst = s_pend + (((blk + j) % kGsSlots) * kGsB + row) * 3;
 					for (int q = 0; q < 3; q++) {
 						const double v = (s_pendp[(0 * kGsAhead * kGsB + tid) * 3 + q] + s_pendp[(1 * kGsAhead * kGsB + tid) * 3 + q]) + s_pendp[(2 * kGsAhead * kGsB + tid) * 3 + q];
-						dst[q] = (tid < kGsB ? dst[q] : 0.0) + v;                 // block b+1 already holds panel b-1; block b+2 starts here
+						dst[q] = (j < kGsAhead - 1 ? dst[q] : 0.0) + v;     // the farthest target starts here; the nearer ones already hold earlier panels
 					}
 				}
-				if (tid == 0) *s_prog = 0;
 			}
-		} else {
-			// ------------------------------------------------ updaters ----------------------------------------------
-			// warps work independently: global warp gwid owns the chunks ch = gwid, gwid + GW, ...  (8 consecutive rows of the
-			// sweep order each) and keeps its own copy of the panel in shared memory
-			double4 *w_col = (double4 *)s_raw + warp * 2 * kGsB;
-			double4 *w_dm = w_col + kGsB;
-			const int GW = U * kGsWarps, gwid = (cta - 1) * kGsWarps + warp;
-			const int r = lane & 7, cl = lane >> 3;             // row of the chunk, column lane
-			for (int blk = 0; blk < nblk; blk++) {
-				const int base = blk * kGsB, cnt = min(kGsB, np - base);
-				// the panel's own rows and the rows of the next block belong to the solver
-				const int skip0 = blk * kChunksPerBlk, skip1 = min(blk + 1 + kGsAhead, nblk) * kChunksPerBlk;
-				bool any = false;
-				for (int ch = gwid; ch < nchunks; ch += GW) any = any || !(ch >= skip0 && ch < skip1);
-				if (!any) continue;
-				__syncwarp();
-				for (int cc = lane; cc < cnt; cc += 32) {
-					const double4 g = gpq[base + cc];
-					w_col[cc] = make_double4(g.x, g.y, g.z, __longlong_as_double((long long)gmeta[base + cc]));   // alpha travels in w_dm.w
+			__pipeline_wait_prior(0);
+			__syncthreads();
+			if (tid < kGsB) for (int q = 0; q < 3; q++) s_site[(7 + q) * kGsB + tid] += s_pend[((blk % kGsSlots) * kGsB + tid) * 3 + q];
+			__syncthreads();
+			if (prof && tid == 0) prof[blk * 8 + 1] = clock64();
+			// (B)
+			if (warp == 0) {
+				// lane owns rows lane (slot 0) and lane+32 (slot 1); everything a row needs lives in registers during the walk.
+				// With c = alpha E_s - mu_old the change of a dipole is a single FMA:  dmu = c - alpha acc.
+				double al[2], cx[2], cy[2], cz[2], ax[2], ay[2], az[2], ex[2], ey[2], ez[2], sx[2], sy[2], sz[2];
+#pragma unroll
+				for (int h = 0; h < 2; h++) {
+					const int m = lane + 32 * h;
+					al[h] = s_site[m];
+					sx[h] = s_site[4 * kGsB + m]; sy[h] = s_site[5 * kGsB + m]; sz[h] = s_site[6 * kGsB + m];
+					cx[h] = al[h] * sx[h] - s_site[1 * kGsB + m];
+					cy[h] = al[h] * sy[h] - s_site[2 * kGsB + m];
+					cz[h] = al[h] * sz[h] - s_site[3 * kGsB + m];
+					ax[h] = s_site[7 * kGsB + m]; ay[h] = s_site[8 * kGsB + m]; az[h] = s_site[9 * kGsB + m];
+					ex[h] = ey[h] = ez[h] = 0;
 				}
-				if (lane == 0) while (ld_flag(&ctl->solved) <= blk) __nanosleep(32);
 				__syncwarp();
-				__threadfence();
-				for (int cc = lane; cc < cnt; cc += 32)
-					w_dm[cc] = make_double4(__ldcg(dmu + 3 * (base + cc)), __ldcg(dmu + 3 * (base + cc) + 1), __ldcg(dmu + 3 * (base + cc) + 2), EXPD ? 0.0 : gpq[base + cc].w);
-				__syncwarp();
-				for (int ch = gwid; ch < nchunks; ch += GW) {
-					if (ch >= skip0 && ch < skip1) continue;
-					const int pos = ch * kGsRows + r;
-					const bool on = pos < np;
-					const double4 pr = on ? gpq[pos] : make_double4(0, 0, 0, 0);
-					const int mr = on ? gmeta[pos] : 0;
-					double ax = 0, ay = 0, az = 0;
-					if (on) {
-#pragma unroll 4
-						for (int cc = cl; cc < cnt; cc += 4) {
-							double4 pc = w_col[cc];
-							const double4 dm = w_dm[cc];
-							const int mc = __double2loint(pc.w);
-							if (!EXPD) pc.w = dm.w;                           // alpha of the column (linear damping)
-							gs_contract<ORTHO, EXPD>(c, p, pr, mr, pc, mc, dm, ax, ay, az);
+				if (lane == 0) { *s_prog = base; *s_loaded = blk + 1; }     // the site columns are in registers: warp 1 may refill them
+				// tensor entries of column k for my two rows: (xx yy) (zz xy) (xz yz); always one column ahead of the dependent chain
+				const double2 *tcol = (const double2 *)s_mat + lane * 3;
+				double2 tn[2][3];
+#pragma unroll
+				for (int hh = 0; hh < 2; hh++) { tn[hh][0] = tcol[hh * 96]; tn[hh][1] = tcol[hh * 96 + 1]; tn[hh][2] = tcol[hh * 96 + 2]; }
+#pragma unroll
+				for (int half = 0; half < 2; half++) {
+					const int kend = min(32, cnt - 32 * half);
+#pragma unroll 2
+					for (int kk = 0; kk < kend; kk++) {
+						const int k = kk + 32 * half;
+						double2 tc[2][3];
+						const double2 *tnext = tcol + min(k + 1, kGsB - 1) * (kGsB * 3);
+#pragma unroll
+						for (int hh = 0; hh < 2; hh++) {
+							tc[hh][0] = tn[hh][0]; tc[hh][1] = tn[hh][1]; tc[hh][2] = tn[hh][2];
+							tn[hh][0] = tnext[hh * 96]; tn[hh][1] = tnext[hh * 96 + 1]; tn[hh][2] = tnext[hh * 96 + 2];
+						}
+						// every lane forms the candidate change of its own slot-`half` row; the owner's is the real one
+						const double dxc = fma(-al[half], ax[half], cx[half]), dyc = fma(-al[half], ay[half], cy[half]), dzc = fma(-al[half], az[half], cz[half]);
+						const double dx = __shfl_sync(0xffffffffu, dxc, kk), dy = __shfl_sync(0xffffffffu, dyc, kk), dz = __shfl_sync(0xffffffffu, dzc, kk);
+						if (lane == kk) { ex[half] = ax[half]; ey[half] = ay[half]; ez[half] = az[half]; }   // acc at the moment of the update
+#pragma unroll
+						for (int hh = 0; hh < 2; hh++) {                      // the diagonal entry is zero: a row does not move itself
+							ax[hh] = fma(tc[hh][0].x, dx, fma(tc[hh][1].y, dy, fma(tc[hh][2].x, dz, ax[hh])));
+							ay[hh] = fma(tc[hh][1].y, dx, fma(tc[hh][0].y, dy, fma(tc[hh][2].y, dz, ay[hh])));
+							az[hh] = fma(tc[hh][2].x, dx, fma(tc[hh][2].y, dy, fma(tc[hh][1].x, dz, az[hh])));
+						}
+						// hand the finished column to the other warps and CTAs.  No fence: both are volatile shared-memory stores of one
+						// thread, which the LSU performs in program order (a MEMBAR here costs more than the whole step); every lane
+						// stores the same values, so the walk has no divergent region
+						{
+							volatile double *vd = (volatile double *)(s_dm + k);
+							vd[0] = dx; vd[1] = dy; vd[2] = dz;
+							*s_prog = base + k + 1;
 						}
 					}
-					ax += __shfl_xor_sync(0xffffffffu, ax, 8); ay += __shfl_xor_sync(0xffffffffu, ay, 8); az += __shfl_xor_sync(0xffffffffu, az, 8);
-					ax += __shfl_xor_sync(0xffffffffu, ax, 16); ay += __shfl_xor_sync(0xffffffffu, ay, 16); az += __shfl_xor_sync(0xffffffffu, az, 16);
-					if (cl == 0 && on) {
-						const int i = order[pos];
-						__stcg(acc + 3 * i, __ldcg(acc + 3 * i) + ax);
-						__stcg(acc + 3 * i + 1, __ldcg(acc + 3 * i + 1) + ay);
-						__stcg(acc + 3 * i + 2, __ldcg(acc + 3 * i + 2) + az);
-					}
-					__threadfence();
-					__syncwarp();
-					if (lane == 0) st_flag(applied + ch, blk + 1);
 				}
+				if (prof && tid == 0) prof[blk * 8 + 2] = clock64();
+				// contract_dipoles: ef_induced = -acc at the moment of the update, mu = alpha (E_s + ef_induced)  (:3583-3592)
+#pragma unroll
+				for (int hh = 0; hh < 2; hh++) {
+					const int m = lane + 32 * hh;
+					if (m < cnt) {
+						const int s = s_idx[(blk & 1) * kGsB + m];
+						const double nx = al[hh] * (sx[hh] - ex[hh]), ny = al[hh] * (sy[hh] - ey[hh]), nz = al[hh] * (sz[hh] - ez[hh]);
+						__stcg(mu + 3 * s, nx); __stcg(mu + 3 * s + 1, ny); __stcg(mu + 3 * s + 2, nz);
+						new_mu[3 * s] = nx; new_mu[3 * s + 1] = ny; new_mu[3 * s + 2] = nz;
+						efi[3 * s] = -ex[hh]; efi[3 * s + 1] = -ey[hh]; efi[3 * s + 2] = -ez[hh];
+						__stcg(acc + 3 * s, ax[hh]); __stcg(acc + 3 * s + 1, ay[hh]); __stcg(acc + 3 * s + 2, az[hh]);
+					}
+				}
+				asm volatile("bar.sync 1, 96;" ::: "memory");
+			} else if (warp == 1) {
+				// the next block: site columns (once the walker has taken its own into registers), tensors rolled in behind the walk
+				// (column k is dead once column k+1 has been fetched), running contraction once the updaters have delivered
+				if (blk + 1 < nblk) {
+					while (*s_loaded <= blk) __nanosleep(100);
+					load_cols(blk + 1, lane); load_cols(blk + 1, lane + 32);
+					// (no updater touches these rows between panel blk-kGsAhead and my own write-back: safe to fetch now)
+					const int c0 = (base + kGsB) / kGsRows, c1 = min(nchunks, c0 + kChunksPerBlk);
+					if (blk >= kGsAhead && lane < c1 - c0) while (ld_flag(applied + c0 + lane) < blk + 1 - kGsAhead) __nanosleep(100);
+					__syncwarp();
+					__threadfence();
+					load_acc(blk + 1, lane); load_acc(blk + 1, lane + 32);
+					const double2 *src = (const double2 *)(tri + (size_t)(blk + 1) * kGsMat);
+					double2 *dst = (double2 *)s_mat;
+					int done = 0;
+					while (done < kGsB) {
+						int pg = max(*s_prog - base, 0);
+						if (pg >= cnt) pg = kGsB;                               // the walk is over: the remaining (unused) columns too
+						if (pg <= done) { __nanosleep(200); continue; }
+						for (int q = done * (kGsB * 3) + lane; q < pg * (kGsB * 3); q += 32) __pipeline_memcpy_async(dst + q, src + q, sizeof(double2));
+						done = pg;
+					}
+					__pipeline_commit();
+					__pipeline_wait_prior(0);
+				}
+				asm volatile("bar.sync 1, 96;" ::: "memory");                   // walker + this warp + the publisher have what the next block needs
+			} else if (warp == 2) {
+				// publish the panel for the updaters: the change of every dipole of the block, then the flag
+				while (*s_prog < base + cnt) __nanosleep(100);
+				double d[2][3];
+#pragma unroll
+				for (int h = 0; h < 2; h++) {
+					const volatile double *vd = (const volatile double *)(s_dm + min(lane + 32 * h, kGsB - 1));
+					d[h][0] = vd[0]; d[h][1] = vd[1]; d[h][2] = vd[2];
+				}
+				asm volatile("bar.sync 1, 96;" ::: "memory");                   // s_dm may be overwritten by the next walk from here on
+#pragma unroll
+				for (int h = 0; h < 2; h++) {
+					const int k = lane + 32 * h;
+					if (k < cnt) { __stcg(dmu + 3 * (base + k), d[h][0]); __stcg(dmu + 3 * (base + k) + 1, d[h][1]); __stcg(dmu + 3 * (base + k) + 2, d[h][2]); }
+				}
+				__threadfence();
+				__syncwarp();
+				if (lane == 0) st_flag(&ctl->solved, blk + 1);
+			}
+			if (prof && tid == 0) prof[blk * 8 + 3] = clock64();
+		}
+		__syncthreads();
+		cluster.sync();                                            // the helpers are done with my shared memory
+	} else if (cta < kGsCluster) {
+		// ------------------------------------------------ helpers -----------------------------------------------
+		// helper hj takes the columns k = hj mod 3 of every panel, for all rows of the next kGsAhead blocks
+		const int hj = cta - 1;
+		double4 *h_rows = (double4 *)s_raw;                        // [kGsSlots][kGsB] x y z alpha, slot = block % kGsSlots
+		int *h_meta = (int *)(h_rows + kGsSlots * kGsB);           // [kGsSlots][kGsB]
+		double *h_part = (double *)(h_meta + kGsSlots * kGsB);     // [4 column sub-slices][kGsAhead * kGsB][3]
+		const volatile int *r_prog = &cluster.map_shared_rank(s_sh, 0)->prog;
+		int *r_done = &cluster.map_shared_rank(s_sh, 0)->done;
+		const volatile double *r_dm = (const volatile double *)cluster.map_shared_rank(s_dm, 0);
+		double *r_pendp = cluster.map_shared_rank(s_pendp, 0) + hj * (kGsAhead * kGsB * 3);
+		auto load_rows = [&](int blk) {
+			if (tid < kGsB) {
+				const int pos = blk * kGsB + tid;
+				const bool on = pos < np;
+				h_rows[(blk % kGsSlots) * kGsB + tid] = on ? gpq[pos] : make_double4(0, 0, 0, 0);
+				h_meta[(blk % kGsSlots) * kGsB + tid] = on ? gmeta[pos] : 0;
+			}
+		};
+		for (int b = 0; b < kGsAhead; b++) load_rows(b);
+		cluster.sync();
+		const int r = tid & (kGsB - 1), s4 = tid >> 6;            // my row of each target block; my column sub-slice
+		for (int blk = 0; blk < nblk; blk++) {
+			const int base = blk * kGsB, cnt = min(kGsB, np - base);
+			load_rows(blk + kGsAhead);
+			__syncthreads();
+			double4 pr[kGsAhead]; int mr[kGsAhead]; bool on[kGsAhead];
+			double ax[kGsAhead], ay[kGsAhead], az[kGsAhead];
+#pragma unroll
+			for (int j = 0; j < kGsAhead; j++) {
+				const int tb = blk + 1 + j;
+				pr[j] = h_rows[(tb % kGsSlots) * kGsB + r];
+				mr[j] = h_meta[(tb % kGsSlots) * kGsB + r];
+				on[j] = tb < nblk && tb * kGsB + r < np;
+				ax[j] = ay[j] = az[j] = 0.0;
+			}
+			for (int k = hj + kGsHelpers * s4; k < cnt; k += kGsHelpers * 4) {
+				if (lane == 0) while (*r_prog < base + k + 1) __nanosleep(100);
+				__syncwarp();
+				const double4 dm = make_double4(r_dm[4 * k], r_dm[4 * k + 1], r_dm[4 * k + 2], 0.0);
+				const double4 pc = h_rows[(blk % kGsSlots) * kGsB + k];
+				const int mc = h_meta[(blk % kGsSlots) * kGsB + k];
+#pragma unroll
+				for (int j = 0; j < kGsAhead; j++)
+					if (on[j]) gs_contract<ORTHO, EXPD>(c, p, pr[j], mr[j], pc, mc, dm, ax[j], ay[j], az[j]);
+			}
+#pragma unroll
+			for (int j = 0; j < kGsAhead; j++) {
+				double *o = h_part + ((s4 * kGsAhead + j) * kGsB + r) * 3;
+				o[0] = ax[j]; o[1] = ay[j]; o[2] = az[j];
+			}
+			__syncthreads();
+			// sub-slices summed in a fixed order, straight into the solver's shared memory
+			if (tid < kGsAhead * kGsB) {
+				for (int q = 0; q < 3; q++)
+					r_pendp[tid * 3 + q] = (h_part[((0 * kGsAhead * kGsB) + tid) * 3 + q] + h_part[((1 * kGsAhead * kGsB) + tid) * 3 + q]) +
+					                       (h_part[((2 * kGsAhead * kGsB) + tid) * 3 + q] + h_part[((3 * kGsAhead * kGsB) + tid) * 3 + q]);
+			}
+			asm volatile("fence.acq_rel.cluster;" ::: "memory");
+			__syncthreads();
+			if (tid == 0) atomicAdd(r_done, 1);
+			// the solver folds these sums before it starts the next walk, and only then publishes columns of the next panel:
+			// r_pendp is free again by the time this helper writes it
+		}
+		cluster.sync();
+	} else {
+		// ------------------------------------------------ updaters ----------------------------------------------
+		// warps work independently: global warp gwid owns the chunks ch = gwid, gwid + GW, ...  (8 consecutive rows of the
+		// sweep order each) and keeps its own copy of the panel in shared memory
+		double4 *w_col = (double4 *)s_raw + warp * 2 * kGsB;
+		double4 *w_dm = w_col + kGsB;
+		const int GW = U * kGsWarps, gwid = (cta - kGsCluster) * kGsWarps + warp;
+		const int r = lane & 7, cl = lane >> 3;             // row of the chunk, column lane
+		for (int blk = 0; blk < nblk; blk++) {
+			const int base = blk * kGsB, cnt = min(kGsB, np - base);
+			// the panel's own rows and the rows of the next kGsAhead blocks belong to the cluster
+			const int skip0 = blk * kChunksPerBlk, skip1 = min(blk + 1 + kGsAhead, nblk) * kChunksPerBlk;
+			bool any = false;
+			for (int ch = gwid; ch < nchunks; ch += GW) any = any || !(ch >= skip0 && ch < skip1);
+			if (!any) continue;
+			__syncwarp();
+			for (int cc = lane; cc < cnt; cc += 32) {
+				const double4 g = gpq[base + cc];
+				w_col[cc] = make_double4(g.x, g.y, g.z, __longlong_as_double((long long)gmeta[base + cc]));   // alpha travels in w_dm.w
+			}
+			if (lane == 0) while (ld_flag(&ctl->solved) <= blk) __nanosleep(32);
+			__syncwarp();
+			__threadfence();
+			for (int cc = lane; cc < cnt; cc += 32)
+				w_dm[cc] = make_double4(__ldcg(dmu + 3 * (base + cc)), __ldcg(dmu + 3 * (base + cc) + 1), __ldcg(dmu + 3 * (base + cc) + 2), EXPD ? 0.0 : gpq[base + cc].w);
+			__syncwarp();
+			for (int ch = gwid; ch < nchunks; ch += GW) {
+				if (ch >= skip0 && ch < skip1) continue;
+				const int pos = ch * kGsRows + r;
+				const bool on = pos < np;
+				const double4 pr = on ? gpq[pos] : make_double4(0, 0, 0, 0);
+				const int mr = on ? gmeta[pos] : 0;
+				double ax = 0, ay = 0, az = 0;
+				if (on) {
+#pragma unroll 4
+					for (int cc = cl; cc < cnt; cc += 4) {
+						double4 pc = w_col[cc];
+						const double4 dm = w_dm[cc];
+						const int mc = __double2loint(pc.w);
+						if (!EXPD) pc.w = dm.w;                           // alpha of the column (linear damping)
+						gs_contract<ORTHO, EXPD>(c, p, pr, mr, pc, mc, dm, ax, ay, az);
+					}
+				}
+				ax += __shfl_xor_sync(0xffffffffu, ax, 8); ay += __shfl_xor_sync(0xffffffffu, ay, 8); az += __shfl_xor_sync(0xffffffffu, az, 8);
+				ax += __shfl_xor_sync(0xffffffffu, ax, 16); ay += __shfl_xor_sync(0xffffffffu, ay, 16); az += __shfl_xor_sync(0xffffffffu, az, 16);
+				if (cl == 0 && on) {
+					const int i = order[pos];
+					__stcg(acc + 3 * i, __ldcg(acc + 3 * i) + ax);
+					__stcg(acc + 3 * i + 1, __ldcg(acc + 3 * i + 1) + ay);
+					__stcg(acc + 3 * i + 2, __ldcg(acc + 3 * i + 2) + az);
+				}
+				__threadfence();
+				__syncwarp();
+				if (lane == 0) st_flag(applied + ch, blk + 1);
 			}
 		}
-		__threadfence();
-		grid.sync();
-		// reset the flags for the next sweep
-		for (int q = cta * kGsThreads + tid; q < nchunks; q += G * kGsThreads) applied[q] = 0;
-		if (cta == 0 && tid == 0) ctl->solved = 0;
-		__threadfence();
-		grid.sync();
 	}
 }
 
