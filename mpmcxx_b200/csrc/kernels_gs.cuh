@@ -171,7 +171,7 @@ k_gs_pipeline(const double4 *__restrict__ gpq, const int *__restrict__ gmeta, co
 			if (blk > 0) {
 				if (tid == 0) while (*s_done < kGsHelpers * blk) { }
 				__syncthreads();
-				__threadfence();
+				asm volatile("fence.acq_rel.cluster;" ::: "memory");
 				if (tid < kGsAhead * kGsB) {
 					const int j = tid / kGsB, row = tid % kGsB;         // target block blk + j
 					double *dst = s_pend + (((blk + j) % kGsSlots) * kGsB + row) * 3;
@@ -272,7 +272,7 @@ k_gs_pipeline(const double4 *__restrict__ gpq, const int *__restrict__ gmeta, co
 					const double2 *src = (const double2 *)(tri + (size_t)(blk + 1) * kGsMat);
 					double2 *dst = (double2 *)s_mat;
 					int done = 0;
-					while (done < kGsB) {
+					while (done < kGsB && !(g_gs_debug & 4)) {
 						int pg = max(*s_prog - base, 0);
 						if (pg >= cnt) pg = kGsB;                               // the walk is over: the remaining (unused) columns too
 						if (pg <= done) { __nanosleep(200); continue; }
@@ -343,7 +343,12 @@ k_gs_pipeline(const double4 *__restrict__ gpq, const int *__restrict__ gmeta, co
 				ax[j] = ay[j] = az[j] = 0.0;
 			}
 			for (int k = hj + kGsHelpers * s4; k < cnt; k += kGsHelpers * 4) {
-				if (lane == 0) while (*r_prog < base + k + 1) __nanosleep(100);
+				if (lane == 0) {
+					// a column takes the walk ~180 cycles (~95 ns): sleep about as long as the columns still to come need, so that
+					// 24 helper warps do not keep reading the solver's shared memory while it walks
+					int pg;
+					while ((pg = *r_prog) < base + k + 1) __nanosleep(min(2000, 40 + 80 * (base + k - pg)));
+				}
 				__syncwarp();
 				const double4 dm = make_double4(r_dm[4 * k], r_dm[4 * k + 1], r_dm[4 * k + 2], 0.0);
 				const double4 pc = h_rows[(blk % kGsSlots) * kGsB + k];
