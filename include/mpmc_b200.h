@@ -181,6 +181,14 @@ int mpmc_set_timing(mpmc_engine *e, int on);
 /* developer hook: SM-clock stamps of the Gauss-Seidel pipeline (solver and one updater CTA), see tools/gs_profile.py */
 int mpmc_debug_gs_profile(mpmc_engine *e, int enable, long long *out, int max_blocks, int *nblk);
 int mpmc_get_timing(mpmc_engine *e, double ms[MPMC_NUM_KERNEL_CLASSES], long long count[MPMC_NUM_KERNEL_CLASSES]);
+/* test hooks for the host-side numerics (no device needed).
+ * mpmc_debug_radial_table: build the r^2-indexed piecewise-polynomial table the kernels use (kind 0: erfc(a r)/r of
+ * coulombic_real, src/System.Energy.cpp:1493-1497; kind 1: the two radial factors of real_term, :2921-2929; param = alpha)
+ * on [u_lo, u_hi) and evaluate it exactly as the device does at u[0..n).
+ * mpmc_debug_cutoff_thresholds: out[0] = largest r^2 with sqrt(r^2) - 1e-12 < cutoff (lj, :934), out[1] = largest r^2 with
+ * !(sqrt(r^2) > cutoff) (coulombic_real, :1490; real_term, :2917). */
+int mpmc_debug_radial_table(int kind, double param, double u_lo, double u_hi, const double *u, int n, double *out0, double *out1);
+int mpmc_debug_cutoff_thresholds(double cutoff, double out[2]);
 void     *mpmc_stream(mpmc_engine *e);
 long long mpmc_kernel_launches(mpmc_engine *e);
 

@@ -1325,6 +1325,31 @@ int mpmc_debug_gs_profile(mpmc_engine *e, int enable, long long *out, int max_bl
 	return MPMC_OK;
 }
 
+// developer / test hooks for the host-side numerics (no device needed): the radial tables and the r^2 cutoff thresholds
+int mpmc_debug_radial_table(int kind, double param, double u_lo, double u_hi, const double *u, int n, double *out0, double *out1) {
+	RadialTable t;
+	const long double a = param, osp = 0.5641895835477562869480794515607725858440506293289988L;
+	if (kind == 0) t.build(1, u_lo, u_hi, [&](long double x, long double *o) { const long double r = sqrtl(x); o[0] = erfcl(a * r) / r; });
+	else if (kind == 1) t.build(2, u_lo, u_hi, [&](long double x, long double *o) {
+		const long double r = sqrtl(x), g = 2.0L * a * osp * expl(-a * a * x) * r;
+		o[0] = (g + erfcl(a * r)) / (x * r); o[1] = (g - erfl(a * r)) / (x * r); }, kTabShiftCoarse);
+	else FAIL(MPMC_ERR_INVALID_INPUT, "unknown table kind %d", kind);
+	for (int i = 0; i < n; i++) {
+		if (!(u[i] >= t.u_lo && u[i] < t.u_hi)) FAIL(MPMC_ERR_INVALID_INPUT, "u[%d] = %g outside the table [%g, %g)", i, u[i], t.u_lo, t.u_hi);
+		out0[i] = t.eval(0, u[i]);
+		if (kind == 1 && out1) out1[i] = t.eval(1, u[i]);
+	}
+	return MPMC_OK;
+}
+
+int mpmc_debug_cutoff_thresholds(double cutoff, double out[2]) {
+	const volatile double rc = cutoff;
+	const double top = 4.0 * cutoff * cutoff + 1.0;
+	out[0] = largest_true([&](double x) { volatile double r = std::sqrt(x); volatile double d = r - kSmallDr; return d < rc; }, top);
+	out[1] = largest_true([&](double x) { volatile double r = std::sqrt(x); return !(r > rc); }, top);
+	return MPMC_OK;
+}
+
 int mpmc_set_timing(mpmc_engine *e, int on) {
 	CK(cudaSetDevice(e->dev));
 	CK(cudaStreamSynchronize(e->stream));

@@ -49,7 +49,7 @@ EXPORTS = ["mpmc_abi_version", "mpmc_last_error", "mpmc_device_count", "mpmc_cre
            "mpmc_num_sites", "mpmc_energy", "mpmc_energy_enqueue", "mpmc_energy_fetch", "mpmc_download_dipoles",
            "mpmc_download_rank_metric", "mpmc_pi_potential", "mpmc_pi_chain", "mpmc_nccl_get_unique_id", "mpmc_nccl_init", "mpmc_pi_potential_allreduce",
            "mpmc_pi_chain_allreduce", "mpmc_set_timing", "mpmc_get_timing", "mpmc_debug_gs_profile", "mpmc_stream", "mpmc_kernel_launches",
-           "mpmc_probe_fp64_peak"]
+           "mpmc_probe_fp64_peak", "mpmc_debug_radial_table", "mpmc_debug_cutoff_thresholds"]
 
 
 KERNEL_CLASSES = ["energy_total", "pair", "structure", "field_recip", "field_real", "rank", "dipole_sweep", "gs_sweep", "palmo"]
@@ -93,6 +93,8 @@ def lib():
         L.mpmc_kernel_launches.restype = C.c_longlong
         L.mpmc_probe_fp64_peak.argtypes = [C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_double)]
         L.mpmc_device_count.argtypes = [C.POINTER(C.c_int)]
+        L.mpmc_debug_radial_table.argtypes = [C.c_int, C.c_double, C.c_double, C.c_double, _dp, C.c_int, _dp, C.c_void_p]
+        L.mpmc_debug_cutoff_thresholds.argtypes = [C.c_double, _dp]
         _lib = L
     return _lib
 
@@ -119,6 +121,20 @@ def nccl_unique_id() -> bytes:
     buf = C.create_string_buffer(128)
     _ck(lib().mpmc_nccl_get_unique_id(buf))
     return buf.raw
+
+
+def radial_table(kind, param, u_lo, u_hi, u):
+    """Host-side evaluation of the kernels' r^2-indexed table (kind 0: erfc(a r)/r; kind 1: the two real_term factors)."""
+    u = np.ascontiguousarray(u, np.float64)
+    o0, o1 = np.zeros_like(u), np.zeros_like(u)
+    _ck(lib().mpmc_debug_radial_table(kind, param, u_lo, u_hi, u, u.size, o0, o1.ctypes.data_as(C.c_void_p)))
+    return (o0, o1) if kind == 1 else o0
+
+
+def cutoff_thresholds(cutoff):
+    o = np.zeros(2)
+    _ck(lib().mpmc_debug_cutoff_thresholds(cutoff, o))
+    return o
 
 
 def probe_fp64_peak(device=0):

@@ -209,3 +209,27 @@ def test_full_size_properties():
     for k in ("rd_pair", "es_real", "es_self_intra", "es_reciprocal", "polarization_energy"):
         assert _rel(b[k], a[k]) < 1e-10, (k, a[k], b[k])
     e4.close(); e5.close()
+
+
+@pytest.mark.parametrize("solver", ["SOLVER_GS_RANKED_PALMO", "SOLVER_JACOBI10"])
+def test_cached_framework_state_equals_fresh_upload(solver):
+    """What the engine keeps across moves (framework structure factor, frozen-frozen part of the Gauss-Seidel rank metric,
+    work lists) must not leak into the result: after a move, energy() equals a fresh engine's energy() of the same sites bit for bit."""
+    from mpmcxx_b200 import workloads as W
+    eng = _engine_mod()
+    s = W.h2_framework(ncell=6, n_h2=20, solver=getattr(W, solver), ensemble="nvt")
+    e = eng.Engine(s)
+    e.energy()
+    rs = np.random.RandomState(11)
+    t = s.copy()
+    for _ in range(3):
+        m = int(rs.randint(1, int(s.mol.max()) + 1))
+        idx = np.nonzero(t.mol == m)[0]
+        t.pos = t.pos.copy()
+        t.pos[idx] += rs.uniform(-0.7, 0.7, 3)
+        e.update_sites(int(idx[0]), t.pos[idx])
+        o = e.energy()
+        f = eng.Engine(t)
+        assert f.energy() == o
+        f.close()
+    e.close()
