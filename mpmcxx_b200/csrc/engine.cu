@@ -149,7 +149,10 @@ struct mpmc_engine {
 	PairParams pp;
 	RadialTable erf_tab;
 	DevBuf<PairSeg> d_segs;
-	DevBuf<int> d_pmeta, d_item_seg;
+	DevBuf<int> d_pmeta, d_item_seg, d_perm;
+	DevBuf<double2> d_slj;
+	DevBuf<double4> d_spq;
+	bool perm_identity = true;
 	DevBuf<double> d_erf_tab;
 	int pair_grid = 0;
 	DevBuf<unsigned char> d_blk_frozen, d_mol_mobile;
@@ -445,30 +448,44 @@ int prepare_pair_sweep(mpmc_engine *e) {
 		if ((rc2 = e->d_erf_tab.ensure(e->erf_tab.rows.size()))) return rc2;
 		CK(cudaMemcpyAsync(e->d_erf_tab.p, e->erf_tab.rows.data(), e->erf_tab.rows.size() * sizeof(double), cudaMemcpyHostToDevice, e->stream));
 	} else { pp.u_tab_lo = 0; pp.tab_base = 0; pp.tab_rows = 0; }
-	// per-site word and the column segments: i-group g meets every later site, except that an all-frozen group skips all-frozen blocks
-	std::vector<int> pm(n);
+	// the class-sorted site table of the sweep: class = (frozen, charged, LJ-active); sites keep their list order inside a class
+	std::vector<int> cls(n), perm(n);
 	for (int i = 0; i < n; i++) {
-		const bool lj_on = e->h_eps[i] != 0.0 && e->h_sigma[i] > 0.0;
-		const int molw = e->h_frozen[i] ? kPmFrozenMol : e->h_mol[i];
-		pm[i] = (molw << kPmMolShift) | (lj_on ? kPmLJ : 0) | (e->h_q[i] != 0.0 ? kPmQ : 0) | (e->h_frozen[i] ? (int)0x80000000u : 0);
+		const bool lj_on = e->h_eps[i] != 0.0 && e->h_sigma[i] > 0.0;   // sigma < 0 leaves pair epsilon at 0 in the reference (System.cpp:1167-1169)
+		cls[i] = (e->h_frozen[i] ? 4 : 0) | ((es && e->h_q[i] != 0.0) ? 2 : 0) | (lj_on ? 1 : 0);
+		perm[i] = i;
 	}
-	if (e->h_mol[n - 1] >= kPmFrozenMol) FAIL(MPMC_ERR_INVALID_INPUT, "more than 2^28 - 1 molecules");
+	std::stable_sort(perm.begin(), perm.end(), [&](int a, int b) { return cls[a] < cls[b]; });
+	e->perm_identity = true;
+	for (int k = 0; k < n; k++) e->perm_identity = e->perm_identity && perm[k] == k;
+	std::vector<int> pm(n);
+	std::vector<double2> slj(n);
+	int cbeg[9];
+	{
+		int k = 0;
+		for (int cc = 0; cc < 8; cc++) { cbeg[cc] = k; while (k < n && cls[perm[k]] == cc) k++; }
+		cbeg[8] = n;
+	}
+	for (int k = 0; k < n; k++) {
+		const int i = perm[k];
+		const bool lj_on = (cls[i] & 1) != 0;
+		pm[k] = e->h_mol[i];
+		slj[k] = make_double2(lj_on ? std::sqrt(e->h_eps[i]) : 0.0, 0.5 * e->h_sigma[i]);
+	}
+	// blocks of pairs: class A x class B (A <= B), what they need, none for frozen x frozen (pair->frozen, :936 / :1487)
 	e->segs.clear();
-	const int ng = (n + 31) / 32;
 	int col = 0;
-	for (int g = 0; g < ng; g++) {
-		const int jb = g * 32 + 1;
-		if (jb >= n) break;
-		if (!e->blk_frozen[g]) { e->segs.push_back({g, jb, n, col}); col += n - jb; continue; }
-		int b = g + 1;                       // the group's own block is all frozen: nothing there
-		while (b < ng) {
-			while (b < ng && e->blk_frozen[b]) b++;
-			if (b >= ng) break;
-			int b2 = b;
-			while (b2 < ng && !e->blk_frozen[b2]) b2++;
-			const int ja = b * 32, jz = std::min(n, b2 * 32);
-			e->segs.push_back({g, ja, jz, col}); col += jz - ja;
-			b = b2;
+	for (int ca = 0; ca < 8; ca++) {
+		for (int gs = cbeg[ca]; gs < cbeg[ca + 1]; gs += 32) {
+			for (int cb = ca; cb < 8; cb++) {
+				if ((ca & 4) && (cb & 4)) continue;
+				const int kind = ((ca & cb & 1) ? kPairLJ : 0) | ((ca & cb & 2) ? kPairES : 0);
+				if (!kind) continue;
+				const int jb = cb == ca ? gs + 1 : cbeg[cb], je = cbeg[cb + 1];
+				if (jb >= je) continue;
+				e->segs.push_back({gs, cbeg[ca + 1], jb, je, col, kind});
+				col += je - jb;
+			}
 		}
 	}
 	pp.ncols = col; pp.nseg = (int)e->segs.size();
@@ -487,8 +504,11 @@ int prepare_pair_sweep(mpmc_engine *e) {
 	}
 	if ((rc2 = e->d_item_seg.ensure(K))) return rc2;
 	CK(cudaMemcpyAsync(e->d_item_seg.p, item_seg.data(), K * sizeof(int), cudaMemcpyHostToDevice, e->stream));
-	if ((rc2 = e->d_pmeta.ensure(std::max(n, 1))) || (rc2 = e->d_segs.ensure(std::max<size_t>(e->segs.size(), 1)))) return rc2;
+	if ((rc2 = e->d_pmeta.ensure(std::max(n, 1))) || (rc2 = e->d_segs.ensure(std::max<size_t>(e->segs.size(), 1))) || (rc2 = e->d_perm.ensure(std::max(n, 1))) ||
+	    (rc2 = e->d_slj.ensure(std::max(n, 1))) || (rc2 = e->d_spq.ensure((size_t)e->B * e->cap))) return rc2;
 	CK(cudaMemcpyAsync(e->d_pmeta.p, pm.data(), n * sizeof(int), cudaMemcpyHostToDevice, e->stream));
+	CK(cudaMemcpyAsync(e->d_perm.p, perm.data(), n * sizeof(int), cudaMemcpyHostToDevice, e->stream));
+	CK(cudaMemcpyAsync(e->d_slj.p, slj.data(), n * sizeof(double2), cudaMemcpyHostToDevice, e->stream));
 	if (!e->segs.empty()) CK(cudaMemcpyAsync(e->d_segs.p, e->segs.data(), e->segs.size() * sizeof(PairSeg), cudaMemcpyHostToDevice, e->stream));
 	CK(cudaStreamSynchronize(e->stream));
 	return MPMC_OK;
@@ -903,8 +923,14 @@ static int enqueue_energy(mpmc_engine *e) {
 		if ((rc = e->d_partials.ensure((size_t)B * std::max(ntiles, 1)))) return rc;
 		const size_t smem = pair_sweep_smem(es, e->pp.tab_rows);
 		Timed _t(e, MPMC_K_PAIR);
-		if (es) k_pair_sweep<ORTHO, true><<<e->pair_grid, kPwThreads, smem, e->stream>>>(e->d_posq.p, e->d_lj.p, e->d_pmeta.p, n, e->cap, B, e->d_segs.p, e->d_item_seg.p, e->pp, e->cell, e->d_erf_tab.p, e->d_partials.p);
-		else k_pair_sweep<ORTHO, false><<<e->pair_grid, kPwThreads, smem, e->stream>>>(e->d_posq.p, e->d_lj.p, e->d_pmeta.p, n, e->cap, B, e->d_segs.p, e->d_item_seg.p, e->pp, e->cell, nullptr, e->d_partials.p);
+		const double4 *spq = e->d_posq.p;        // one class in list order (bulk LJ, single-site models): the table already is sorted
+		if (!e->perm_identity) {
+			k_pair_gather<<<(unsigned)(((size_t)B * n + 255) / 256), 256, 0, e->stream>>>(e->d_posq.p, e->d_perm.p, n, e->cap, B, e->d_spq.p);
+			LAUNCHED(e);
+			spq = e->d_spq.p;
+		}
+		if (es) k_pair_sweep<ORTHO, true><<<e->pair_grid, kPwThreads, smem, e->stream>>>(spq, e->d_slj.p, e->d_pmeta.p, e->cap, B, e->d_segs.p, e->d_item_seg.p, e->pp, e->cell, e->d_erf_tab.p, e->d_partials.p);
+		else k_pair_sweep<ORTHO, false><<<e->pair_grid, kPwThreads, smem, e->stream>>>(spq, e->d_slj.p, e->d_pmeta.p, e->cap, B, e->d_segs.p, e->d_item_seg.p, e->pp, e->cell, nullptr, e->d_partials.p);
 		LAUNCHED(e);
 	} else {
 	if ((rc = e->d_partials.ensure((size_t)B * std::max(ntiles, 1)))) return rc;
@@ -1021,7 +1047,7 @@ int mpmc_destroy(mpmc_engine *e) {
 	if (e->stream) cudaStreamSynchronize(e->stream);
 	e->d_posq.release(); e->d_lj.release(); e->d_alpha.release(); e->d_mass.release(); e->d_meta.release(); e->d_plist.release();
 	e->d_mobile_q.release(); e->d_frozen_q.release(); e->d_mol_start.release(); e->d_order.release(); e->d_flags.release();
-	e->d_tiles.release(); e->d_segs.release(); e->d_item_seg.release(); e->d_pmeta.release(); e->d_erf_tab.release(); e->d_blk_frozen.release(); e->d_mol_mobile.release(); e->d_kvec.release(); e->d_partials.release();
+	e->d_tiles.release(); e->d_segs.release(); e->d_item_seg.release(); e->d_pmeta.release(); e->d_perm.release(); e->d_slj.release(); e->d_spq.release(); e->d_erf_tab.release(); e->d_blk_frozen.release(); e->d_mol_mobile.release(); e->d_kvec.release(); e->d_partials.release();
 	e->d_sk_part.release(); e->d_S_mobile.release(); e->d_S_frozen.release(); e->d_S_all.release();
 	e->d_efs.release(); e->d_efi.release(); e->d_efic.release(); e->d_mu.release(); e->d_new_mu.release(); e->d_old_mu.release();
 	e->d_rrms.release(); e->d_rank.release(); e->d_acc.release(); e->d_dmu.release(); e->d_tri.release(); e->d_gsctl.release(); e->d_gmeta.release(); e->d_nplist.release(); e->d_gpq.release(); e->d_cparts.release(); e->d_field_tab.release(); e->d_fp_list.release(); e->d_mp_list.release(); e->d_recount.release(); e->d_r2min_ff.release(); e->d_t2.release(); e->d_t2_cached.release(); e->d_cnt_ff.release(); e->d_mobile_sites.release(); e->d_frozen_sites.release(); e->d_allq.release(); e->d_com.release(); e->d_mol_mass.release(); e->d_chain.release();

@@ -12,8 +12,13 @@
 //   * the ~48 % of pairs outside the cutoff sphere cost nothing more: the lanes of a warp push the pairs that do interact into a
 //     per-warp queue (ballot + popc, fixed order) and the expensive part runs on full warps, 32 queued pairs at a time.
 //   * erfc(alpha r)/r comes from a table in r^2 (radial_table.h): 1 add + 7 FMA, no sqrt, no exp; LJ needs only 1/r^2.
-//   * work is dealt to warps, not CTAs: the (i-group of 32 sites) x (j site) columns of the triangle are flattened and cut into
-//     equal ranges, so 148 SMs x 32 warps stay busy to the end whatever N is.
+//   * the pair sum does not depend on the order of the sites, so the sweep runs over a copy of the site table sorted by CLASS
+//     (frozen?, charged?, LJ-active?).  A block of pairs between two classes needs LJ only, Coulomb only, both or nothing at all
+//     — frozen x frozen and (charge-only) x (LJ-only) blocks are simply not in the work list — and the inner loop is compiled once
+//     per kind, so a five-site H2 system (one LJ+charge site, two charge-only, two LJ-only) does half the arithmetic it would
+//     with every pair going through both formulas.
+//   * work is dealt to warps, not CTAs: the (i-group of 32 sites) x (j site) columns of every class block are flattened and cut
+//     into equal ranges, so 148 SMs x 16 warps stay busy to the end whatever N is.
 // Sums are accumulated per item in a fixed order and reduced by k_reduce_partials: results are bit-reproducible.
 #pragma once
 #include "device_math.cuh"
@@ -25,13 +30,13 @@ namespace mpmc {
 constexpr int kPwWarps = 8, kPwThreads = kPwWarps * 32;
 constexpr int kErfRow = (kTabDeg + 1) + kTabPad;        // doubles per row of the erfc table
 
-// per-site word of the pair sweep: bit 0 = has LJ, bits 1..28 = molecule index — every FROZEN site carries the same pseudo index
-// kPmFrozenMol, so that "both frozen" (pair->frozen, :936/:1487) and "same molecule" (rd_excluded/es_excluded) are ONE test —
-// bit 29 = has charge, sign bit = frozen (looked at only on the rare intramolecular branch).
-constexpr int kPmLJ = 1, kPmMolShift = 1, kPmFrozenMol = 0x0fffffff, kPmExclMask = 0x1ffffffe, kPmQ = 1 << 29;
-constexpr int kPmPad = (int)0x80000000u | (kPmFrozenMol << kPmMolShift);   // padding lanes / columns: frozen, inert
+// per-site word of the pair sweep: the molecule index (same molecule = rd_excluded / es_excluded); padding lanes and columns carry
+// kPmPad, which equals no molecule and marks the site as absent
+constexpr int kPmPad = -1;
+enum { kPairLJ = 1, kPairES = 2 };                      // what a block of pairs needs
 
-struct PairSeg { int g, j_begin, j_end, col0; };        // i-group g (sites 32g..32g+31) meets sites [j_begin, j_end); col0 = columns before it
+// i-group = sorted sites [i_begin, min(i_begin + 32, i_end)) meets sorted sites [j_begin, j_end), which need `kind`; col0 = columns before it
+struct PairSeg { int i_begin, i_end, j_begin, j_end, col0, kind; };
 
 struct PairParams {
 	double t2_lj;       // largest r^2 with  sqrt(r^2) - 1e-12 < cutoff      (lj, :934)
@@ -108,9 +113,85 @@ __device__ __forceinline__ double rcp_full(double x) {
 	return fma(y, fma(e, e, e), y);
 }
 
+// the class-sorted copy of the coordinates: spq[bead][k] = posq[bead][perm[k]]
+__global__ void k_pair_gather(const double4 *__restrict__ posq, const int *__restrict__ perm, int n, int stride, int nbeads, double4 *__restrict__ spq) {
+	const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+	if (t >= (size_t)n * nbeads) return;
+	const int bead = (int)(t / n), k = (int)(t - (size_t)bead * n);
+	spq[(size_t)bead * stride + k] = posq[(size_t)bead * stride + perm[k]];
+}
+
+// one staged chunk (cnt <= 32 columns in shared memory) against the warp's 32 i sites, for a block of pairs of one kind
+template <bool ORTHO, int KIND>
+__device__ __forceinline__ void pair_chunk(const CellDev &c, const PairParams &pp, const double *s_tab, const double4 *s_pq, const double2 *s_lj,
+                                           const int *s_pm, int cnt, int dlim, const double4 pi, const double2 li, int mi, PairAcc &a) {
+	constexpr bool LJ = (KIND & kPairLJ) != 0, ES = (KIND & kPairES) != 0;
+	const double t2_adm = pp.t2_adm, t2_safe = pp.t2_safe;
+	for (int jj = 0; jj < cnt; jj += kPwCols) {
+		double r2[kPwCols], elj[kPwCols], ees[kPwCols];
+		bool in[kPwCols], excl[kPwCols], band[kPwCols];
+#pragma unroll
+		for (int u = 0; u < kPwCols; u++) {
+			const double4 pj = s_pq[jj + u];
+			const int mj = s_pm[jj + u];
+			r2[u] = r2_fast<ORTHO>(c, pi.x - pj.x, pi.y - pj.y, pi.z - pj.z);
+			excl[u] = mi == mj;                                              // same molecule (rd_excluded / es_excluded)
+			in[u] = !excl[u] && (mi | mj) >= 0 && dlim < jj + u && r2[u] <= t2_adm;   // present, i < j, inside the (1e-9 widened) cutoff sphere
+			band[u] = in[u] && r2[u] > t2_safe;
+			if (LJ) {
+				// Lorentz-Berthelot LJ (:965-993); 4 eps_ij is applied after the sum
+				const double2 ljj = s_lj[jj + u];
+				const double sig = li.y + ljj.y;
+				const double s2 = sig * sig * rcp_full(r2[u]), s6 = s2 * s2 * s2;
+				elj[u] = (li.x * ljj.x) * fma(s6, s6, -s6);
+			}
+			if (ES) {                                                            // :1493-1497
+				ees[u] = 0.0;
+				if (in[u]) {
+					double f = tab_eval1(s_tab, pp.tab_base, pp.tab_rows, r2[u]);
+					if (r2[u] < pp.u_tab_lo) { const double r = sqrt(r2[u]); f = erfc(c.ewald_alpha * r) / r; }   // closer than the table starts
+					ees[u] = pi.w * pj.w * f;
+				}
+			}
+		}
+		bool in_es[kPwCols];
+#pragma unroll
+		for (int u = 0; u < kPwCols; u++) in_es[u] = in[u];
+		if (band[0] || band[1] || band[2] || band[3]) {
+			// within 1e-9 of a cutoff: decide on the reference's own rounding of r^2 (System.cpp:1228-1255)
+#pragma unroll
+			for (int u = 0; u < kPwCols; u++)
+				if (band[u]) {
+					const double4 pj = s_pq[jj + u];
+					double ex, ey, ez;
+					min_image<ORTHO>(c, __dsub_rn(pi.x, pj.x), __dsub_rn(pi.y, pj.y), __dsub_rn(pi.z, pj.z), ex, ey, ez);
+					const double r2x = norm2_nofma(ex, ey, ez);
+					in[u] = r2x <= pp.t2_lj;
+					in_es[u] = r2x <= pp.t2_es;
+				}
+		}
+#pragma unroll
+		for (int u = 0; u < kPwCols; u++) {
+			if (LJ && in[u]) { a.rd += elj[u]; a.cnt++; }
+			if (ES && in_es[u]) a.re += ees[u];
+		}
+		if (ES && (excl[0] || excl[1] || excl[2] || excl[3])) {
+			// es_self_intra = q_i q_j erf(alpha r)/r on the UN-imaged distance (:1503-1504)
+#pragma unroll
+			for (int u = 0; u < kPwCols; u++)
+				if (excl[u] && mi >= 0 && dlim < jj + u) {
+					const double4 pj = s_pq[jj + u];
+					const double dx = pi.x - pj.x, dy = pi.y - pj.y, dz = pi.z - pj.z;
+					const double r = sqrt(fma(dz, dz, fma(dy, dy, dx * dx)));
+					a.in += pi.w * pj.w * erf(c.ewald_alpha * r) / r;
+				}
+		}
+	}
+}
+
 template <bool ORTHO, bool ES>
 __global__ void __launch_bounds__(kPwThreads, kPwCtas)
-k_pair_sweep(const double4 *__restrict__ posq, const double2 *__restrict__ lj, const int *__restrict__ pmeta, int n, int stride, int nbeads,
+k_pair_sweep(const double4 *__restrict__ spq, const double2 *__restrict__ lj, const int *__restrict__ pmeta, int stride, int nbeads,
              const PairSeg *__restrict__ seg, const int *__restrict__ item_seg, const PairParams pp, const CellDev c,
              const double *__restrict__ tab, PairPartial *__restrict__ partials) {
 	extern __shared__ __align__(16) double s_raw[];
@@ -125,7 +206,6 @@ k_pair_sweep(const double4 *__restrict__ posq, const double2 *__restrict__ lj, c
 		for (int q = tid; q < tab_len; q += kPwThreads) s_tab[q] = tab[q];
 		__syncthreads();
 	}
-	const double t2_adm = pp.t2_adm, t2_safe = pp.t2_safe;
 	const int W = gridDim.x * kPwWarps, gw = blockIdx.x * kPwWarps + warp;
 	const int items = nbeads * pp.items_per_bead;
 	if (lane < kPwCols) { s_pq[32 + lane] = make_double4(0, 0, 0, 0); s_lj[32 + lane] = make_double2(0, 0); s_pm[32 + lane] = kPmPad; }
@@ -133,7 +213,7 @@ k_pair_sweep(const double4 *__restrict__ posq, const double2 *__restrict__ lj, c
 
 	for (int it = gw; it < items; it += W) {
 		const int bead = it / pp.items_per_bead, k = it - bead * pp.items_per_bead;
-		const double4 *pq = posq + (size_t)bead * stride;
+		const double4 *pq = spq + (size_t)bead * stride;
 		int col = k * pp.cols_per_item;
 		const int col_end = min(col + pp.cols_per_item, pp.ncols);
 		PairAcc a = {0.0, 0.0, 0.0, 0};
@@ -143,11 +223,11 @@ k_pair_sweep(const double4 *__restrict__ posq, const double2 *__restrict__ lj, c
 				const PairSeg sg = seg[s];
 				const int j0 = sg.j_begin + (col - sg.col0);
 				const int j1 = min(sg.j_end, j0 + (col_end - col));
-				const int i = sg.g * 32 + lane;
+				const int i = sg.i_begin + lane;
 				double4 pi = make_double4(0, 0, 0, 0);
 				double2 li = make_double2(0, 0);
 				int mi = kPmPad;
-				if (i < n) { pi = pq[i]; li = lj[i]; mi = pmeta[i]; }
+				if (i < sg.i_end) { pi = pq[i]; li = lj[i]; mi = pmeta[i]; }
 				// first chunk of the segment into registers; later chunks are fetched while the previous one is being swept
 				double4 npq = make_double4(0, 0, 0, 0); double2 nlj = make_double2(0, 0); int npm = kPmPad;
 				if (j0 + lane < j1) { npq = pq[j0 + lane]; nlj = lj[j0 + lane]; npm = pmeta[j0 + lane]; }
@@ -161,71 +241,12 @@ k_pair_sweep(const double4 *__restrict__ posq, const double2 *__restrict__ lj, c
 						npm = kPmPad; npq = make_double4(0, 0, 0, 0); nlj = make_double2(0, 0);
 						if (jn < j1) { npq = pq[jn]; nlj = lj[jn]; npm = pmeta[jn]; }
 					}
-					const int dlim = (jc < sg.g * 32 + 32) ? i - jc : -1;   // diagonal chunk: keep i < j only
-					for (int jj = 0; jj < cnt; jj += kPwCols) {
-						double r2[kPwCols], elj[kPwCols], ees[kPwCols];
-						bool in[kPwCols], excl[kPwCols], band[kPwCols];
-						int cl[kPwCols];
-#pragma unroll
-						for (int u = 0; u < kPwCols; u++) {
-							const double4 pj = s_pq[jj + u];
-							const double2 ljj = s_lj[jj + u];
-							const int mj = s_pm[jj + u];
-							r2[u] = r2_fast<ORTHO>(c, pi.x - pj.x, pi.y - pj.y, pi.z - pj.z);
-							excl[u] = ((mi ^ mj) & kPmExclMask) == 0;                    // same molecule, or both frozen
-							in[u] = !excl[u] && dlim < jj + u && r2[u] <= t2_adm;        // i < j, inside the (1e-9 widened) cutoff sphere
-							band[u] = in[u] && r2[u] > t2_safe;
-							cl[u] = mi & mj & kPmLJ;
-							// Lorentz-Berthelot LJ (:965-993); 4 eps_ij is applied after the sum.  LJ-null sites carry sqrt(eps) = 0.
-							const double sig = li.y + ljj.y;
-							const double s2 = sig * sig * rcp_full(r2[u]), s6 = s2 * s2 * s2;
-							elj[u] = (li.x * ljj.x) * fma(s6, s6, -s6);
-							if (ES) {                                                    // :1493-1497; q = 0 sites add exactly 0
-								const double qq = pi.w * pj.w;
-								ees[u] = 0.0;
-								if (in[u] && qq != 0.0) {
-									double f = tab_eval1(s_tab, pp.tab_base, pp.tab_rows, r2[u]);
-									if (r2[u] < pp.u_tab_lo) { const double r = sqrt(r2[u]); f = erfc(c.ewald_alpha * r) / r; }   // closer than the table starts
-									ees[u] = qq * f;
-								}
-							}
-						}
-						bool in_es[kPwCols];
-#pragma unroll
-						for (int u = 0; u < kPwCols; u++) in_es[u] = in[u];
-						if (band[0] || band[1] || band[2] || band[3]) {
-							// within 1e-9 of a cutoff: decide on the reference's own rounding of r^2 (System.cpp:1228-1255)
-#pragma unroll
-							for (int u = 0; u < kPwCols; u++)
-								if (band[u]) {
-									const double4 pj = s_pq[jj + u];
-									double ex, ey, ez;
-									min_image<ORTHO>(c, __dsub_rn(pi.x, pj.x), __dsub_rn(pi.y, pj.y), __dsub_rn(pi.z, pj.z), ex, ey, ez);
-									const double r2x = norm2_nofma(ex, ey, ez);
-									in[u] = r2x <= pp.t2_lj;
-									in_es[u] = r2x <= pp.t2_es;
-								}
-						}
-#pragma unroll
-						for (int u = 0; u < kPwCols; u++) {
-							if (in[u]) { a.rd += elj[u]; a.cnt += cl[u]; }
-							if (ES && in_es[u]) a.re += ees[u];
-						}
-						if (ES && (excl[0] || excl[1] || excl[2] || excl[3])) {
-							// es_self_intra = q_i q_j erf(alpha r)/r on the UN-imaged distance (:1503-1504), not for frozen pairs (:1487)
-#pragma unroll
-							for (int u = 0; u < kPwCols; u++)
-								if (excl[u] && mi >= 0 && dlim < jj + u) {
-									const double4 pj = s_pq[jj + u];
-									const double qq = pi.w * pj.w;
-									if (qq != 0.0) {
-										const double dx = pi.x - pj.x, dy = pi.y - pj.y, dz = pi.z - pj.z;
-										const double r = sqrt(fma(dz, dz, fma(dy, dy, dx * dx)));
-										a.in += qq * erf(c.ewald_alpha * r) / r;
-									}
-								}
-						}
-					}
+					const int dlim = (jc < sg.i_begin + 32) ? i - jc : -1;   // a chunk that overlaps the i-group (same class): keep i < j only
+					if (ES) {
+						if (sg.kind == (kPairLJ | kPairES)) pair_chunk<ORTHO, kPairLJ | kPairES>(c, pp, s_tab, s_pq, s_lj, s_pm, cnt, dlim, pi, li, mi, a);
+						else if (sg.kind == kPairES) pair_chunk<ORTHO, kPairES>(c, pp, s_tab, s_pq, s_lj, s_pm, cnt, dlim, pi, li, mi, a);
+						else pair_chunk<ORTHO, kPairLJ>(c, pp, s_tab, s_pq, s_lj, s_pm, cnt, dlim, pi, li, mi, a);
+					} else pair_chunk<ORTHO, kPairLJ>(c, pp, s_tab, s_pq, s_lj, s_pm, cnt, dlim, pi, li, mi, a);
 				}
 				col += j1 - j0;
 				s++;
