@@ -151,7 +151,7 @@ struct mpmc_engine {
 	DevBuf<PairSeg> d_segs;
 	DevBuf<int> d_pmeta, d_item_seg, d_perm;
 	DevBuf<double2> d_slj;
-	DevBuf<double4> d_spq;
+	DevBuf<double4> d_spq, d_stage;
 	bool perm_identity = true;
 	DevBuf<double> d_erf_tab;
 	int pair_grid = 0;
@@ -190,6 +190,10 @@ struct mpmc_engine {
 	nccl_comm_t comm = nullptr;
 	int rank = 0, nranks = 1;
 	DevBuf<double> d_pisums, d_firstcom;
+	// the path-integral sweep (kernels + all-reduce + result copy) as a CUDA graph: one launch per Monte Carlo move
+	cudaGraphExec_t pi_graph = nullptr;
+	bool pi_graph_off = false;
+	long long pi_graph_launches = 0;
 	double *h_pisums = nullptr;
 	// optional per-kernel-class timing with CUDA events on the engine's stream (mpmc_set_timing)
 	bool timing = false;
@@ -594,9 +598,17 @@ int push_positions(mpmc_engine *e, int bead_lo, int bead_hi, int first, int coun
 			const double *p = &e->h_pos[((size_t)(bead_lo + b) * e->n + first + i) * 3];
 			e->h_stage[(size_t)b * count + i] = make_double4(p[0], p[1], p[2], e->h_q[first + i]);
 		}
-	for (int b = 0; b < nb; b++)
-		CK(cudaMemcpyAsync(e->d_posq.p + (size_t)(bead_lo + b) * e->cap + first, e->h_stage + (size_t)b * count, count * sizeof(double4),
-		                   cudaMemcpyHostToDevice, e->stream));
+	if (nb == 1) {
+		CK(cudaMemcpyAsync(e->d_posq.p + (size_t)bead_lo * e->cap + first, e->h_stage, count * sizeof(double4), cudaMemcpyHostToDevice, e->stream));
+	} else {
+		// one copy for all bead systems, then a scatter into the per-bead rows of posq
+		int rc2 = e->d_stage.ensure((size_t)nb * count);
+		if (rc2) return rc2;
+		CK(cudaMemcpyAsync(e->d_stage.p, e->h_stage, (size_t)nb * count * sizeof(double4), cudaMemcpyHostToDevice, e->stream));
+		k_scatter_sites<<<(nb * count + 127) / 128, 128, 0, e->stream>>>(e->d_stage.p, e->d_posq.p, e->cap, bead_lo, nb, first, count);
+		e->launches++;
+		CK(cudaGetLastError());
+	}
 	return MPMC_OK;
 }
 
@@ -624,7 +636,12 @@ template <class K> int set_smem(K kernel, size_t bytes) {
 
 } // namespace
 
+static void drop_pi_graph(mpmc_engine *e) {
+	if (e->pi_graph) { cudaGraphExecDestroy(e->pi_graph); e->pi_graph = nullptr; }
+}
+
 static int adopt_table(mpmc_engine *e) {
+	drop_pi_graph(e);
 	// (re)size device arrays for e->n sites and push everything
 	const int n = e->n;
 	if (n > e->cap || !e->d_posq.p) e->cap = std::max({e->cap, n + n / 2, 64});
@@ -1047,7 +1064,7 @@ int mpmc_destroy(mpmc_engine *e) {
 	if (e->stream) cudaStreamSynchronize(e->stream);
 	e->d_posq.release(); e->d_lj.release(); e->d_alpha.release(); e->d_mass.release(); e->d_meta.release(); e->d_plist.release();
 	e->d_mobile_q.release(); e->d_frozen_q.release(); e->d_mol_start.release(); e->d_order.release(); e->d_flags.release();
-	e->d_tiles.release(); e->d_segs.release(); e->d_item_seg.release(); e->d_pmeta.release(); e->d_perm.release(); e->d_slj.release(); e->d_spq.release(); e->d_erf_tab.release(); e->d_blk_frozen.release(); e->d_mol_mobile.release(); e->d_kvec.release(); e->d_partials.release();
+	e->d_tiles.release(); e->d_segs.release(); e->d_item_seg.release(); e->d_pmeta.release(); e->d_perm.release(); e->d_slj.release(); e->d_spq.release(); e->d_stage.release(); e->d_erf_tab.release(); e->d_blk_frozen.release(); e->d_mol_mobile.release(); e->d_kvec.release(); e->d_partials.release();
 	e->d_sk_part.release(); e->d_S_mobile.release(); e->d_S_frozen.release(); e->d_S_all.release();
 	e->d_efs.release(); e->d_efi.release(); e->d_efic.release(); e->d_mu.release(); e->d_new_mu.release(); e->d_old_mu.release();
 	e->d_rrms.release(); e->d_rank.release(); e->d_acc.release(); e->d_dmu.release(); e->d_tri.release(); e->d_gsctl.release(); e->d_gmeta.release(); e->d_nplist.release(); e->d_gpq.release(); e->d_cparts.release(); e->d_field_tab.release(); e->d_fp_list.release(); e->d_mp_list.release(); e->d_recount.release(); e->d_r2min_ff.release(); e->d_t2.release(); e->d_t2_cached.release(); e->d_cnt_ff.release(); e->d_mobile_sites.release(); e->d_frozen_sites.release(); e->d_allq.release(); e->d_com.release(); e->d_mol_mass.release(); e->d_chain.release();
@@ -1055,6 +1072,7 @@ int mpmc_destroy(mpmc_engine *e) {
 	if (e->h_stage) cudaFreeHost(e->h_stage);
 	if (e->h_result) cudaFreeHost(e->h_result);
 	if (e->h_flags) cudaFreeHost(e->h_flags);
+	drop_pi_graph(e);
 	if (e->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(e->comm);
 	e->d_pisums.release(); e->d_firstcom.release();
 	if (e->h_pisums) cudaFreeHost(e->h_pisums);
@@ -1066,6 +1084,7 @@ int mpmc_destroy(mpmc_engine *e) {
 
 int mpmc_set_cell(mpmc_engine *e, const double basis[9]) {
 	CK(cudaSetDevice(e->dev));
+	drop_pi_graph(e);
 	memcpy(e->cfg.basis, basis, sizeof(double) * 9);
 	return compute_cell(e, basis);
 }
@@ -1274,10 +1293,42 @@ int mpmc_nccl_init(mpmc_engine *e, const char id[128], int rank, int nranks) {
 int mpmc_pi_potential_allreduce(mpmc_engine *e, int P_global, double means[4], double *potential) {
 	CK(cudaSetDevice(e->dev));
 	if (P_global < e->B) FAIL(MPMC_ERR_BEADS, "P_global (%d) smaller than the local bead count (%d)", P_global, e->B);
-	int rc = pi_sums_enqueue(e, nullptr);
-	if (rc) return rc;
-	if (e->comm) NK(g_nccl.AllReduce(e->d_pisums.p, e->d_pisums.p, 4, kNcclFloat64, kNcclSum, e->comm, e->stream));
-	CK(cudaMemcpyAsync(e->h_pisums, e->d_pisums.p, sizeof(double) * 4, cudaMemcpyDeviceToHost, e->stream));
+	int rc;
+	// Steady state (same topology, no framework move pending, no per-kernel timing, no polarization loop with host decisions):
+	// the whole sweep — gather, pair sweep, reductions, structure factor, per-bead assembly, all-reduce, result copy — is one
+	// CUDA graph, captured on the second call and replayed afterwards.  At 8 beads per GPU the sweep is ~150 us of kernels: ten
+	// separate launches would leave the GPU idle for a third of that.
+	const bool graphable = !e->pi_graph_off && !e->timing && !e->cfg.polarization && !e->topo_dirty && !e->frozen_sk_dirty && e->d_pisums.p && e->h_pisums;
+	if (graphable && e->pi_graph) {
+		CK(cudaGraphLaunch(e->pi_graph, e->stream));
+		e->launches += e->pi_graph_launches;
+	} else if (graphable) {
+		const long long l0 = e->launches;
+		cudaGraph_t g = nullptr;
+		CK(cudaStreamBeginCapture(e->stream, cudaStreamCaptureModeThreadLocal));
+		rc = pi_sums_enqueue(e, nullptr);
+		int nrc = 0;
+		if (!rc && e->comm) nrc = g_nccl.AllReduce(e->d_pisums.p, e->d_pisums.p, 4, kNcclFloat64, kNcclSum, e->comm, e->stream);
+		cudaError_t ce = (!rc && !nrc) ? cudaMemcpyAsync(e->h_pisums, e->d_pisums.p, sizeof(double) * 4, cudaMemcpyDeviceToHost, e->stream) : cudaSuccess;
+		cudaError_t ee = cudaStreamEndCapture(e->stream, &g);
+		if (rc || nrc || ce != cudaSuccess || ee != cudaSuccess || !g || cudaGraphInstantiate(&e->pi_graph, g, 0) != cudaSuccess) {
+			cudaGetLastError();
+			if (g) cudaGraphDestroy(g);
+			e->pi_graph = nullptr; e->pi_graph_off = true;      // fall back to plain launches for the rest of this engine's life
+			e->launches = l0;
+			if ((rc = pi_sums_enqueue(e, nullptr))) return rc;
+			if (e->comm) NK(g_nccl.AllReduce(e->d_pisums.p, e->d_pisums.p, 4, kNcclFloat64, kNcclSum, e->comm, e->stream));
+			CK(cudaMemcpyAsync(e->h_pisums, e->d_pisums.p, sizeof(double) * 4, cudaMemcpyDeviceToHost, e->stream));
+		} else {
+			cudaGraphDestroy(g);
+			e->pi_graph_launches = e->launches - l0;
+			CK(cudaGraphLaunch(e->pi_graph, e->stream));
+		}
+	} else {
+		if ((rc = pi_sums_enqueue(e, nullptr))) return rc;
+		if (e->comm) NK(g_nccl.AllReduce(e->d_pisums.p, e->d_pisums.p, 4, kNcclFloat64, kNcclSum, e->comm, e->stream));
+		CK(cudaMemcpyAsync(e->h_pisums, e->d_pisums.p, sizeof(double) * 4, cudaMemcpyDeviceToHost, e->stream));
+	}
 	CK(cudaStreamSynchronize(e->stream));
 	e->enqueued = false;
 	if (e->timing) collect_timing(e);

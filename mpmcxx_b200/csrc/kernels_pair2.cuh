@@ -121,6 +121,14 @@ __global__ void k_pair_gather(const double4 *__restrict__ posq, const int *__res
 	spq[(size_t)bead * stride + k] = posq[(size_t)bead * stride + perm[k]];
 }
 
+// a move of `count` consecutive sites in every bead system: stage[b][k] -> posq[bead_lo + b][first + k]
+__global__ void k_scatter_sites(const double4 *__restrict__ stage, double4 *__restrict__ posq, int stride, int bead_lo, int nb, int first, int count) {
+	const int t = blockIdx.x * blockDim.x + threadIdx.x;
+	if (t >= nb * count) return;
+	const int b = t / count, k = t - b * count;
+	posq[(size_t)(bead_lo + b) * stride + first + k] = stage[t];
+}
+
 // one staged chunk (cnt <= 32 columns in shared memory) against the warp's 32 i sites, for a block of pairs of one kind
 template <bool ORTHO, int KIND>
 __device__ __forceinline__ void pair_chunk(const CellDev &c, const PairParams &pp, const double *s_tab, const double4 *s_pq, const double2 *s_lj,

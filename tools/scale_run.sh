@@ -9,7 +9,7 @@ run() {
 }
 run --steps 10 --warmup 3 --no-cpu-baseline --no-extra
 run --workload pi_h2_five --steps 100 --warmup 10
-run --workload pi_h2 --steps 200 --warmup 20
+[ "${FULL:-0}" = "1" ] && run --workload pi_h2 --steps 200 --warmup 20
 python - <<PY
 import json
 for l in open("$OUT"):
