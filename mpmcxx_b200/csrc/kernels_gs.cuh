@@ -204,43 +204,48 @@ k_gs_pipeline(const double4 *__restrict__ gpq, const int *__restrict__ gmeta, co
 				}
 				__syncwarp();
 				if (lane == 0) { *s_prog = base; *s_loaded = blk + 1; }     // the site columns are in registers: warp 1 may refill them
-				// tensor entries of column k for my two rows: (xx yy) (zz xy) (xz yz); always one column ahead of the dependent chain
+				// tensor entries of column k for my two rows: (xx yy) (zz xy) (xz yz); always one column ahead of the dependent chain.
+				// Two register sets used alternately (the loop is unrolled by hand: a copy would cost 24 moves per step on the
+				// one warp the whole sweep waits for).
 				const double2 *tcol = (const double2 *)s_mat + lane * 3;
-				double2 tn[2][3];
+				double2 ta[2][3], tb[2][3];
 #pragma unroll
-				for (int hh = 0; hh < 2; hh++) { tn[hh][0] = tcol[hh * 96]; tn[hh][1] = tcol[hh * 96 + 1]; tn[hh][2] = tcol[hh * 96 + 2]; }
+				for (int hh = 0; hh < 2; hh++) { ta[hh][0] = tcol[hh * 96]; ta[hh][1] = tcol[hh * 96 + 1]; ta[hh][2] = tcol[hh * 96 + 2]; }
+				const unsigned tcol_s = (unsigned)__cvta_generic_to_shared(tcol);
+				auto step = [&](const int half, const int kk, double2 (&tc)[2][3], double2 (&tn)[2][3]) {
+					const int k = kk + 32 * half;
+					// every lane forms the candidate change of its own slot-`half` row; the owner's is the real one
+					const double dxc = fma(-al[half], ax[half], cx[half]), dyc = fma(-al[half], ay[half], cy[half]), dzc = fma(-al[half], az[half], cz[half]);
+					const double dx = __shfl_sync(0xffffffffu, dxc, kk), dy = __shfl_sync(0xffffffffu, dyc, kk), dz = __shfl_sync(0xffffffffu, dzc, kk);
+					if (lane == kk) { ex[half] = ax[half]; ey[half] = ay[half]; ez[half] = az[half]; }   // acc at the moment of the update
+					// hand the finished column to the other warps and CTAs.  No fence: both are volatile shared-memory stores of one
+					// thread, which the LSU performs in program order (a MEMBAR here costs more than the whole step); every lane
+					// stores the same values, so the walk has no divergent region
+					volatile double *vd = (volatile double *)(s_dm + k);
+					vd[0] = dx; vd[1] = dy; vd[2] = dz;
+					*s_prog = base + k + 1;
+					// the next column into the register set the previous step has finished with.  Volatile (ordered after the stores
+					// above) so that the compiler does not hoist these loads over the previous step's FMAs, which would cost it a third
+					// register set and 24 moves per step
+					const unsigned tnext = tcol_s + (unsigned)(min(k + 1, kGsB - 1) * (kGsB * 3) * sizeof(double2));
+#pragma unroll
+					for (int hh = 0; hh < 2; hh++)
+#pragma unroll
+						for (int q = 0; q < 3; q++)
+							asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(tn[hh][q].x), "=d"(tn[hh][q].y) : "r"(tnext + (unsigned)((hh * 96 + q) * sizeof(double2))));
+#pragma unroll
+					for (int hh = 0; hh < 2; hh++) {                      // the diagonal entry is zero: a row does not move itself
+						ax[hh] = fma(tc[hh][0].x, dx, fma(tc[hh][1].y, dy, fma(tc[hh][2].x, dz, ax[hh])));
+						ay[hh] = fma(tc[hh][1].y, dx, fma(tc[hh][0].y, dy, fma(tc[hh][2].y, dz, ay[hh])));
+						az[hh] = fma(tc[hh][2].x, dx, fma(tc[hh][2].y, dy, fma(tc[hh][1].x, dz, az[hh])));
+					}
+				};
 #pragma unroll
 				for (int half = 0; half < 2; half++) {
 					const int kend = min(32, cnt - 32 * half);
-#pragma unroll 2
-					for (int kk = 0; kk < kend; kk++) {
-						const int k = kk + 32 * half;
-						double2 tc[2][3];
-						const double2 *tnext = tcol + min(k + 1, kGsB - 1) * (kGsB * 3);
-#pragma unroll
-						for (int hh = 0; hh < 2; hh++) {
-							tc[hh][0] = tn[hh][0]; tc[hh][1] = tn[hh][1]; tc[hh][2] = tn[hh][2];
-							tn[hh][0] = tnext[hh * 96]; tn[hh][1] = tnext[hh * 96 + 1]; tn[hh][2] = tnext[hh * 96 + 2];
-						}
-						// every lane forms the candidate change of its own slot-`half` row; the owner's is the real one
-						const double dxc = fma(-al[half], ax[half], cx[half]), dyc = fma(-al[half], ay[half], cy[half]), dzc = fma(-al[half], az[half], cz[half]);
-						const double dx = __shfl_sync(0xffffffffu, dxc, kk), dy = __shfl_sync(0xffffffffu, dyc, kk), dz = __shfl_sync(0xffffffffu, dzc, kk);
-						if (lane == kk) { ex[half] = ax[half]; ey[half] = ay[half]; ez[half] = az[half]; }   // acc at the moment of the update
-#pragma unroll
-						for (int hh = 0; hh < 2; hh++) {                      // the diagonal entry is zero: a row does not move itself
-							ax[hh] = fma(tc[hh][0].x, dx, fma(tc[hh][1].y, dy, fma(tc[hh][2].x, dz, ax[hh])));
-							ay[hh] = fma(tc[hh][1].y, dx, fma(tc[hh][0].y, dy, fma(tc[hh][2].y, dz, ay[hh])));
-							az[hh] = fma(tc[hh][2].x, dx, fma(tc[hh][2].y, dy, fma(tc[hh][1].x, dz, az[hh])));
-						}
-						// hand the finished column to the other warps and CTAs.  No fence: both are volatile shared-memory stores of one
-						// thread, which the LSU performs in program order (a MEMBAR here costs more than the whole step); every lane
-						// stores the same values, so the walk has no divergent region
-						{
-							volatile double *vd = (volatile double *)(s_dm + k);
-							vd[0] = dx; vd[1] = dy; vd[2] = dz;
-							*s_prog = base + k + 1;
-						}
-					}
+					int kk = 0;
+					for (; kk + 1 < kend; kk += 2) { step(half, kk, ta, tb); step(half, kk + 1, tb, ta); }
+					if (kk < kend) step(half, kk, ta, tb);                    // an odd count: always the last step of the block
 				}
 				if (prof && tid == 0) prof[blk * 8 + 2] = clock64();
 				// contract_dipoles: ef_induced = -acc at the moment of the update, mu = alpha (E_s + ef_induced)  (:3583-3592)
