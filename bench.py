@@ -409,6 +409,8 @@ def run_pi(args, embedded=False):
     nchain = int(tmpl.opts["PI_trial_chain_length"])
     pos = beads.copy()                           # every rank keeps all P geometries on the host (as the reference does)
     u_cur, _ = eng.pi_potential_allreduce(P)
+    u_first = u_cur
+    collective = eng.pi_collective()
     nacc = 0
 
     def step():
@@ -479,7 +481,9 @@ def run_pi(args, embedded=False):
            "ms_per_step": 1e3 * t_dev / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
            "config": {"workload": "config5: path-integral H2 cluster, 512 molecules x %d beads, %s, beads sharded %d per GPU, one NCCL all-reduce of 4 doubles per sweep"
                                   % (P, "five-site H2 + Ewald (N=2560 per bead)" if five else "single-site H2, rd_only (N=512 per bead)", hi - lo),
-                      "l2": "inputs are < 1 MB per rank and L2-resident by nature; no flush (latency-bound path)", "pair_evals_per_sweep": pairs_per_sweep},
+                      "l2": "inputs are < 1 MB per rank and L2-resident by nature; no flush (latency-bound path)", "pair_evals_per_sweep": pairs_per_sweep,
+                      "collective": collective,
+                      "potential_of_start_configuration_K": u_first, "potential_after_run_K": u_cur},
            "clocks": clk,
            "e2e": {"value": args.steps / t_wall, "unit": "moves/s", "h2d_bytes_per_step": 32 * (ends[0] - starts[0]) * (hi - lo), "d2h_bytes_per_step": 32,
                    "ms_per_step": 1e3 * t_wall / args.steps, "acceptance": nacc / (args.steps + args.warmup)},

@@ -160,6 +160,9 @@ int mpmc_nccl_get_unique_id(char id[128]);
 int mpmc_nccl_init(mpmc_engine *e, const char id[128], int rank, int nranks);
 int mpmc_pi_potential_allreduce(mpmc_engine *e, int P_global, double means[4], double *potential);
 int mpmc_pi_chain_allreduce(mpmc_engine *e, double *chain_mass_len2);
+/* how mpmc_pi_potential_allreduce sums over ranks: 0 = single GPU, 1 = ncclAllReduce, 2 = peer-memory mailboxes written over NVLink by
+ * the assembly kernel itself (set up by mpmc_nccl_init when CUDA IPC + peer access are available; MPMC_PI_P2P=0 forces 1) */
+int mpmc_pi_collective(mpmc_engine *e);
 
 /* measurement hooks (bench.py): the CUDA stream every kernel of this engine is launched on (a cudaStream_t),
  * and the number of kernels this engine has launched so far. */

@@ -190,6 +190,12 @@ struct mpmc_engine {
 	nccl_comm_t comm = nullptr;
 	int rank = 0, nranks = 1;
 	DevBuf<double> d_pisums, d_firstcom;
+	// peer-memory mailboxes of the fused all-reduce (k_pi_sums_xchg)
+	bool p2p = false;
+	PiMailSlot *d_mbox = nullptr;
+	std::vector<PiMailSlot *> peer_mbox;
+	DevBuf<PiMailSlot *> d_peers;
+	DevBuf<long long> d_step;
 	// the path-integral sweep (kernels + all-reduce + result copy) as a CUDA graph: one launch per Monte Carlo move
 	cudaGraphExec_t pi_graph = nullptr;
 	bool pi_graph_off = false;
@@ -1073,6 +1079,9 @@ int mpmc_destroy(mpmc_engine *e) {
 	if (e->h_result) cudaFreeHost(e->h_result);
 	if (e->h_flags) cudaFreeHost(e->h_flags);
 	drop_pi_graph(e);
+	for (int r = 0; r < (int)e->peer_mbox.size(); r++) if (r != e->rank && e->peer_mbox[r]) cudaIpcCloseMemHandle(e->peer_mbox[r]);
+	if (e->d_mbox) cudaFree(e->d_mbox);
+	e->d_peers.release(); e->d_step.release();
 	if (e->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(e->comm);
 	e->d_pisums.release(); e->d_firstcom.release();
 	if (e->h_pisums) cudaFreeHost(e->h_pisums);
@@ -1241,14 +1250,18 @@ int mpmc_download_rank_metric(mpmc_engine *e, int bead, double *rank_metric) {
 }
 
 // enqueue one sweep over the local bead systems and leave {sum rd, sum coulombic, sum polarization, sum vdw} in d_pisums[0..3]
-static int pi_sums_enqueue(mpmc_engine *e, double *d_per_bead) {
+static int pi_sums_enqueue(mpmc_engine *e, double *d_per_bead, bool xchg = false) {
 	int rc = mpmc_energy_enqueue(e);
 	if (rc) return rc;
 	if ((rc = e->d_pisums.ensure(8 + 4 * (size_t)e->B))) return rc;
 	if (!e->h_pisums) CK(cudaMallocHost(&e->h_pisums, sizeof(double) * (8 + 4 * (size_t)e->B)));
 	const mpmc_config &cf = e->cfg;
-	k_pi_sums<<<1, 32, 0, e->stream>>>(e->d_result.p, e->B, e->lrc_pair + e->lrc_self, e->es_self, !cf.rd_only, cf.polarization, cf.polar_palmo,
-	                                   d_per_bead, e->d_pisums.p);
+	if (e->p2p && xchg)
+		k_pi_sums_xchg<<<1, 32, 0, e->stream>>>(e->d_result.p, e->B, e->lrc_pair + e->lrc_self, e->es_self, !cf.rd_only, cf.polarization, cf.polar_palmo,
+		                                        e->d_pisums.p, e->d_peers.p, e->rank, e->nranks, e->d_step.p);
+	else
+		k_pi_sums<<<1, 32, 0, e->stream>>>(e->d_result.p, e->B, e->lrc_pair + e->lrc_self, e->es_self, !cf.rd_only, cf.polarization, cf.polar_palmo,
+		                                   d_per_bead, e->d_pisums.p);
 	e->launches++;
 	CK(cudaGetLastError());
 	return MPMC_OK;
@@ -1287,6 +1300,54 @@ int mpmc_nccl_init(mpmc_engine *e, const char id[128], int rank, int nranks) {
 	memcpy(nid.internal, id, 128);
 	NK(g_nccl.CommInitRank(&e->comm, nranks, nid, rank));
 	e->rank = rank; e->nranks = nranks;
+	// Peer-memory mailboxes for the fused all-reduce (k_pi_sums_xchg): one allocation per rank, its CUDA IPC handle all-gathered
+	// through the communicator, every peer's mailbox mapped here.  If any step fails (no peer access, IPC unavailable) the engine
+	// keeps using ncclAllReduce.  MPMC_PI_P2P=0 forces that path (A/B measurements).
+	const char *env = getenv("MPMC_PI_P2P");
+	if (nranks > 1 && nranks <= 32 && !(env && env[0] == '0')) {
+		bool ok = true;
+		const size_t bytes = sizeof(PiMailSlot) * 2 * nranks;
+		cudaIpcMemHandle_t mine;
+		char *d_h = nullptr;
+		std::vector<cudaIpcMemHandle_t> all(nranks);
+		ok = ok && cudaMalloc(&e->d_mbox, bytes) == cudaSuccess && cudaMemset(e->d_mbox, 0, bytes) == cudaSuccess;
+		ok = ok && cudaIpcGetMemHandle(&mine, e->d_mbox) == cudaSuccess;
+		ok = ok && cudaMalloc(&d_h, sizeof(mine) * (nranks + 1)) == cudaSuccess;
+		ok = ok && cudaMemcpy(d_h + sizeof(mine) * nranks, &mine, sizeof(mine), cudaMemcpyHostToDevice) == cudaSuccess;
+		// every rank must take part in the collective, whatever happened locally; a rank that failed sends a zero handle
+		if (!ok && d_h) cudaMemset(d_h + sizeof(mine) * nranks, 0, sizeof(mine));
+		if (d_h) {
+			const int r = g_nccl.AllGather(d_h + sizeof(mine) * nranks, d_h, sizeof(mine), /*ncclChar*/ 0, e->comm, e->stream);
+			ok = ok && r == 0 && cudaStreamSynchronize(e->stream) == cudaSuccess &&
+			     cudaMemcpy(all.data(), d_h, sizeof(mine) * nranks, cudaMemcpyDeviceToHost) == cudaSuccess;
+			cudaFree(d_h);
+		}
+		e->peer_mbox.assign(nranks, nullptr);
+		for (int r = 0; ok && r < nranks; r++) {
+			bool zero = true;
+			for (size_t b = 0; b < sizeof(mine); b++) zero = zero && ((const char *)&all[r])[b] == 0;
+			if (zero) { ok = false; break; }
+			if (r == rank) { e->peer_mbox[r] = e->d_mbox; continue; }
+			void *p = nullptr;
+			ok = cudaIpcOpenMemHandle(&p, all[r], cudaIpcMemLazyEnablePeerAccess) == cudaSuccess;
+			e->peer_mbox[r] = (PiMailSlot *)p;
+		}
+		if (ok) ok = e->d_peers.ensure(nranks) == MPMC_OK && e->d_step.ensure(1) == MPMC_OK &&
+		             cudaMemcpy(e->d_peers.p, e->peer_mbox.data(), sizeof(PiMailSlot *) * nranks, cudaMemcpyHostToDevice) == cudaSuccess &&
+		             cudaMemset(e->d_step.p, 0, sizeof(long long)) == cudaSuccess;
+		cudaGetLastError();
+		// all ranks must agree: one more tiny collective on the verdict (sum of failures)
+		double *d_v = nullptr;
+		double v = ok ? 0.0 : 1.0;
+		if (cudaMalloc(&d_v, sizeof(double)) == cudaSuccess) {
+			cudaMemcpy(d_v, &v, sizeof(double), cudaMemcpyHostToDevice);
+			if (g_nccl.AllReduce(d_v, d_v, 1, kNcclFloat64, kNcclSum, e->comm, e->stream) == 0 && cudaStreamSynchronize(e->stream) == cudaSuccess)
+				cudaMemcpy(&v, d_v, sizeof(double), cudaMemcpyDeviceToHost);
+			else v = 1.0;
+			cudaFree(d_v);
+		} else v = 1.0;
+		e->p2p = (v == 0.0);
+	}
 	return MPMC_OK;
 }
 
@@ -1306,9 +1367,9 @@ int mpmc_pi_potential_allreduce(mpmc_engine *e, int P_global, double means[4], d
 		const long long l0 = e->launches;
 		cudaGraph_t g = nullptr;
 		CK(cudaStreamBeginCapture(e->stream, cudaStreamCaptureModeThreadLocal));
-		rc = pi_sums_enqueue(e, nullptr);
+		rc = pi_sums_enqueue(e, nullptr, true);
 		int nrc = 0;
-		if (!rc && e->comm) nrc = g_nccl.AllReduce(e->d_pisums.p, e->d_pisums.p, 4, kNcclFloat64, kNcclSum, e->comm, e->stream);
+		if (!rc && e->comm && !e->p2p) nrc = g_nccl.AllReduce(e->d_pisums.p, e->d_pisums.p, 4, kNcclFloat64, kNcclSum, e->comm, e->stream);
 		cudaError_t ce = (!rc && !nrc) ? cudaMemcpyAsync(e->h_pisums, e->d_pisums.p, sizeof(double) * 4, cudaMemcpyDeviceToHost, e->stream) : cudaSuccess;
 		cudaError_t ee = cudaStreamEndCapture(e->stream, &g);
 		if (rc || nrc || ce != cudaSuccess || ee != cudaSuccess || !g || cudaGraphInstantiate(&e->pi_graph, g, 0) != cudaSuccess) {
@@ -1316,8 +1377,8 @@ int mpmc_pi_potential_allreduce(mpmc_engine *e, int P_global, double means[4], d
 			if (g) cudaGraphDestroy(g);
 			e->pi_graph = nullptr; e->pi_graph_off = true;      // fall back to plain launches for the rest of this engine's life
 			e->launches = l0;
-			if ((rc = pi_sums_enqueue(e, nullptr))) return rc;
-			if (e->comm) NK(g_nccl.AllReduce(e->d_pisums.p, e->d_pisums.p, 4, kNcclFloat64, kNcclSum, e->comm, e->stream));
+			if ((rc = pi_sums_enqueue(e, nullptr, true))) return rc;
+			if (e->comm && !e->p2p) NK(g_nccl.AllReduce(e->d_pisums.p, e->d_pisums.p, 4, kNcclFloat64, kNcclSum, e->comm, e->stream));
 			CK(cudaMemcpyAsync(e->h_pisums, e->d_pisums.p, sizeof(double) * 4, cudaMemcpyDeviceToHost, e->stream));
 		} else {
 			cudaGraphDestroy(g);
@@ -1325,8 +1386,8 @@ int mpmc_pi_potential_allreduce(mpmc_engine *e, int P_global, double means[4], d
 			CK(cudaGraphLaunch(e->pi_graph, e->stream));
 		}
 	} else {
-		if ((rc = pi_sums_enqueue(e, nullptr))) return rc;
-		if (e->comm) NK(g_nccl.AllReduce(e->d_pisums.p, e->d_pisums.p, 4, kNcclFloat64, kNcclSum, e->comm, e->stream));
+		if ((rc = pi_sums_enqueue(e, nullptr, true))) return rc;
+		if (e->comm && !e->p2p) NK(g_nccl.AllReduce(e->d_pisums.p, e->d_pisums.p, 4, kNcclFloat64, kNcclSum, e->comm, e->stream));
 		CK(cudaMemcpyAsync(e->h_pisums, e->d_pisums.p, sizeof(double) * 4, cudaMemcpyDeviceToHost, e->stream));
 	}
 	CK(cudaStreamSynchronize(e->stream));
@@ -1336,6 +1397,8 @@ int mpmc_pi_potential_allreduce(mpmc_engine *e, int P_global, double means[4], d
 	if (potential) *potential = means[0] + means[1] + means[3] + means[2];     // :803-804
 	return MPMC_OK;
 }
+
+int mpmc_pi_collective(mpmc_engine *e) { return e->p2p ? 2 : (e->comm ? 1 : 0); }
 
 int mpmc_pi_chain_allreduce(mpmc_engine *e, double *chain_mass_len2) {
 	CK(cudaSetDevice(e->dev));

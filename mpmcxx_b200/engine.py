@@ -49,7 +49,7 @@ EXPORTS = ["mpmc_abi_version", "mpmc_last_error", "mpmc_device_count", "mpmc_cre
            "mpmc_num_sites", "mpmc_energy", "mpmc_energy_enqueue", "mpmc_energy_fetch", "mpmc_download_dipoles",
            "mpmc_download_rank_metric", "mpmc_pi_potential", "mpmc_pi_chain", "mpmc_nccl_get_unique_id", "mpmc_nccl_init", "mpmc_pi_potential_allreduce",
            "mpmc_pi_chain_allreduce", "mpmc_set_timing", "mpmc_get_timing", "mpmc_debug_gs_profile", "mpmc_stream", "mpmc_kernel_launches",
-           "mpmc_probe_fp64_peak", "mpmc_debug_radial_table", "mpmc_debug_cutoff_thresholds"]
+           "mpmc_probe_fp64_peak", "mpmc_debug_radial_table", "mpmc_debug_cutoff_thresholds", "mpmc_pi_collective"]
 
 
 KERNEL_CLASSES = ["energy_total", "pair", "structure", "field_recip", "field_real", "rank", "dipole_sweep", "gs_sweep", "palmo"]
@@ -93,6 +93,7 @@ def lib():
         L.mpmc_kernel_launches.restype = C.c_longlong
         L.mpmc_probe_fp64_peak.argtypes = [C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_double)]
         L.mpmc_device_count.argtypes = [C.POINTER(C.c_int)]
+        L.mpmc_pi_collective.argtypes = [vp]
         L.mpmc_debug_radial_table.argtypes = [C.c_int, C.c_double, C.c_double, C.c_double, _dp, C.c_int, _dp, C.c_void_p]
         L.mpmc_debug_cutoff_thresholds.argtypes = [C.c_double, _dp]
         _lib = L
@@ -238,6 +239,9 @@ class Engine:
 
     def nccl_init(self, uid: bytes, rank: int, nranks: int):
         _ck(lib().mpmc_nccl_init(self.h, uid, rank, nranks))
+
+    def pi_collective(self):
+        return {0: "none (one GPU)", 1: "ncclAllReduce of 4 doubles", 2: "peer-memory mailboxes fused into the assembly kernel (k_pi_sums_xchg)"}[lib().mpmc_pi_collective(self.h)]
 
     def pi_potential_allreduce(self, P_global):
         means = np.zeros(4)
