@@ -168,6 +168,11 @@ struct mpmc_engine {
 	DevBuf<unsigned long long> d_r2min_ff;
 	DevBuf<double> d_t2, d_t2_cached, d_cnt_ff;
 	bool rank_ff_dirty = true;
+	// Gauss-Seidel pipeline: the updater kernel runs beside the solver cluster on a second stream
+	cudaStream_t stream2 = nullptr;
+	cudaEvent_t ev_upd = nullptr;
+	int *h_started = nullptr, *d_started = nullptr;   // mapped pinned word the solver kernel stamps when it is running
+	int gs_token = 0, gs_upd_grid = 0;
 	RadialTable field_tab;
 	FieldParams fpar;
 	std::vector<int> nplist;
@@ -886,10 +891,25 @@ static int run_polar(mpmc_engine *e) {
 				Timed _t(e, MPMC_K_GS_SWEEP);
 				for (int sw = 0; sw < ns; sw++) {   // one launch per sweep: the kernel boundary is the barrier between sweeps
 					CK(cudaMemsetAsync(e->d_gsctl.p, 0, sizeof(int) * (sizeof(GsCtl) / sizeof(int) + nchunks), e->stream));
-					if (expd) k_gs_pipeline<ORTHO, true><<<e->gs_grid, kGsThreads, kGsSmemBytes, e->stream>>>(e->d_gpq.p, e->d_gmeta.p, gs_order, np, e->cell, pd, e->d_efs.p,
-					        e->d_mu.p, e->d_efi.p, e->d_new_mu.p, e->d_acc.p, e->d_dmu.p, e->d_tri.p, (GsCtl *)e->d_gsctl.p, sw == 0 ? prof : nullptr);
-					else k_gs_pipeline<ORTHO, false><<<e->gs_grid, kGsThreads, kGsSmemBytes, e->stream>>>(e->d_gpq.p, e->d_gmeta.p, gs_order, np, e->cell, pd, e->d_efs.p,
-					        e->d_mu.p, e->d_efi.p, e->d_new_mu.p, e->d_acc.p, e->d_dmu.p, e->d_tri.p, (GsCtl *)e->d_gsctl.p, sw == 0 ? prof : nullptr);
+					const int token = ++e->gs_token;
+					if (expd) k_gs_pipeline<ORTHO, true><<<kGsCluster, kGsThreads, kGsSmemBytes, e->stream>>>(e->d_gpq.p, e->d_gmeta.p, gs_order, np, e->cell, pd, e->d_efs.p,
+					        e->d_mu.p, e->d_efi.p, e->d_new_mu.p, e->d_acc.p, e->d_dmu.p, e->d_tri.p, (GsCtl *)e->d_gsctl.p, sw == 0 ? prof : nullptr, e->d_started, token);
+					else k_gs_pipeline<ORTHO, false><<<kGsCluster, kGsThreads, kGsSmemBytes, e->stream>>>(e->d_gpq.p, e->d_gmeta.p, gs_order, np, e->cell, pd, e->d_efs.p,
+					        e->d_mu.p, e->d_efi.p, e->d_new_mu.p, e->d_acc.p, e->d_dmu.p, e->d_tri.p, (GsCtl *)e->d_gsctl.p, sw == 0 ? prof : nullptr, e->d_started, token);
+					CK(cudaGetLastError());
+					// The updaters must not take the SMs the cluster needs (its CTAs want a whole SM's shared memory each): wait until the
+					// solver kernel is running — it stamps a mapped host word first thing — then fill the rest of the machine.
+					for (long long spin = 0; *(volatile int *)e->h_started != token; spin++) {
+						if (spin > 2000000000ll) FAIL(MPMC_ERR_CUDA, "Gauss-Seidel solver kernel did not start");
+						if ((spin & 0xfffff) == 0xfffff && cudaStreamQuery(e->stream) != cudaErrorNotReady) break;   // it already finished (tiny system) or failed
+					}
+					if (expd) k_gs_updaters<ORTHO, true><<<e->gs_upd_grid, kGsThreads, kGsUpdaterSmemBytes, e->stream2>>>(e->d_gpq.p, e->d_gmeta.p, gs_order, np, e->cell, pd,
+					        e->d_acc.p, e->d_dmu.p, (GsCtl *)e->d_gsctl.p, sw == 0 ? prof : nullptr);
+					else k_gs_updaters<ORTHO, false><<<e->gs_upd_grid, kGsThreads, kGsUpdaterSmemBytes, e->stream2>>>(e->d_gpq.p, e->d_gmeta.p, gs_order, np, e->cell, pd,
+					        e->d_acc.p, e->d_dmu.p, (GsCtl *)e->d_gsctl.p, sw == 0 ? prof : nullptr);
+					CK(cudaEventRecord(e->ev_upd, e->stream2));
+					CK(cudaStreamWaitEvent(e->stream, e->ev_upd, 0));
+					e->launches++;
 					LAUNCHED(e);
 				}
 				CK(cudaGetLastError());
@@ -1047,16 +1067,18 @@ int mpmc_create(const mpmc_config *cfg, mpmc_engine **out) {
 		e->pair_v1 = v1 && v1[0] == '1';
 	}
 	{
-		// the Gauss-Seidel pipeline needs every CTA resident (its CTAs wait on each other's flags): as many clusters of kGsCluster CTAs
-		// as the device can hold at one CTA per SM
-		cudaLaunchConfig_t lc = {};
-		lc.gridDim = dim3(e->num_sms / kGsCluster * kGsCluster); lc.blockDim = dim3(kGsThreads); lc.dynamicSmemBytes = kGsSmemBytes;
-		cudaLaunchAttribute at[1];
-		at[0].id = cudaLaunchAttributeClusterDimension; at[0].val.clusterDim.x = kGsCluster; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
-		lc.attrs = at; lc.numAttrs = 1;
-		int ncl = 0;
-		CK(cudaOccupancyMaxActiveClusters(&ncl, k_gs_pipeline<true, true>, &lc));
-		e->gs_grid = std::max(2, ncl) * kGsCluster;
+		// the Gauss-Seidel pipeline: one cluster (solver + helpers) and an updater kernel on every other SM, 2 CTAs each
+		CK(cudaStreamCreateWithFlags(&e->stream2, cudaStreamNonBlocking));
+		CK(cudaEventCreateWithFlags(&e->ev_upd, cudaEventDisableTiming));
+		CK(cudaHostAlloc(&e->h_started, sizeof(int), cudaHostAllocMapped));
+		*e->h_started = 0;
+		CK(cudaHostGetDevicePointer(&e->d_started, e->h_started, 0));
+		if ((rc = set_smem(k_gs_updaters<true, true>, kGsUpdaterSmemBytes)) || (rc = set_smem(k_gs_updaters<false, true>, kGsUpdaterSmemBytes)) ||
+		    (rc = set_smem(k_gs_updaters<true, false>, kGsUpdaterSmemBytes)) || (rc = set_smem(k_gs_updaters<false, false>, kGsUpdaterSmemBytes))) { mpmc_destroy(e); return rc; }
+		int occ = 0;
+		CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_gs_updaters<true, true>, kGsThreads, kGsUpdaterSmemBytes));
+		e->gs_upd_grid = std::max(1, e->num_sms - kGsCluster) * std::max(1, std::min(occ, 2));
+		e->gs_grid = kGsCluster;
 	}
 	if ((rc = compute_cell(e, cfg->basis))) { mpmc_destroy(e); return rc; }
 	if (cfg->capacity > 0) e->cap = cfg->capacity;
@@ -1079,6 +1101,9 @@ int mpmc_destroy(mpmc_engine *e) {
 	if (e->h_result) cudaFreeHost(e->h_result);
 	if (e->h_flags) cudaFreeHost(e->h_flags);
 	drop_pi_graph(e);
+	if (e->stream2) { cudaStreamSynchronize(e->stream2); cudaStreamDestroy(e->stream2); }
+	if (e->ev_upd) cudaEventDestroy(e->ev_upd);
+	if (e->h_started) cudaFreeHost(e->h_started);
 	for (int r = 0; r < (int)e->peer_mbox.size(); r++) if (r != e->rank && e->peer_mbox[r]) cudaIpcCloseMemHandle(e->peer_mbox[r]);
 	if (e->d_mbox) cudaFree(e->d_mbox);
 	e->d_peers.release(); e->d_step.release();

@@ -45,7 +45,8 @@ constexpr int kGsHelpers = 3, kGsCluster = 1 + kGsHelpers;
 constexpr int kGsSlots = kGsAhead + 1;    // ring of per-block buffers
 constexpr size_t kGsSolverDoubles = (size_t)kGsMat + kGsSiteCols * kGsB + kGsHelpers * (kGsAhead * kGsB * 3) + kGsSlots * 3 * kGsB + 4 * kGsB + 2 * kGsB + 16;
 constexpr size_t kGsUpdaterDoubles = (size_t)kGsWarps * 8 * kGsB;
-constexpr size_t kGsSmemBytes = sizeof(double) * (kGsSolverDoubles > kGsUpdaterDoubles ? kGsSolverDoubles : kGsUpdaterDoubles);
+constexpr size_t kGsSmemBytes = sizeof(double) * kGsSolverDoubles;
+constexpr size_t kGsUpdaterSmemBytes = sizeof(double) * kGsUpdaterDoubles;
 
 __device__ int g_gs_debug = 0;            // developer switch (mpmc_debug_gs_profile enable bits 1..): 2 = pushers idle, 4 = no rolling copy
 struct GsCtl { int solved; int pad[31]; };   // followed in memory by int applied[nchunks]
@@ -115,12 +116,13 @@ template <bool ORTHO, bool EXPD>
 __global__ void __cluster_dims__(kGsCluster, 1, 1) __launch_bounds__(kGsThreads, 1)
 k_gs_pipeline(const double4 *__restrict__ gpq, const int *__restrict__ gmeta, const int *__restrict__ order, int np, CellDev c, PolarDev p,
               const double *__restrict__ efs, double *mu, double *efi, double *new_mu, double *acc, double *dmu,
-              const double *__restrict__ tri, GsCtl *ctl, long long *prof) {
+              const double *__restrict__ tri, GsCtl *ctl, long long *prof, volatile int *started, int token) {
 	cg::cluster_group cluster = cg::this_cluster();
+	if (blockIdx.x == 0 && threadIdx.x == 0) { *started = token; __threadfence_system(); }   // tells the host that the cluster holds its SMs
 	extern __shared__ __align__(16) double s_raw[];
 	int *applied = (int *)(ctl + 1);
 	const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-	const int cta = blockIdx.x, U = gridDim.x - kGsCluster;
+	const int cta = blockIdx.x;
 	const int nblk = (np + kGsB - 1) / kGsB, nchunks = (np + kGsRows - 1) / kGsRows;
 	constexpr int kChunksPerBlk = kGsB / kGsRows;
 	// the solver's layout (helpers address the shared part of it through the cluster)
@@ -381,60 +383,95 @@ k_gs_pipeline(const double4 *__restrict__ gpq, const int *__restrict__ gmeta, co
 			// r_pendp is free again by the time this helper writes it
 		}
 		cluster.sync();
-	} else {
-		// ------------------------------------------------ updaters ----------------------------------------------
+	}
+}
+
+// The updaters: their own kernel (2 CTAs per SM on every SM the solver's cluster leaves free — the solver needs a whole SM's shared
+// memory, the updaters need latency hiding), launched right after the solver kernel on a second stream.
+template <bool ORTHO, bool EXPD>
+__global__ void __launch_bounds__(kGsThreads, 2)
+k_gs_updaters(const double4 *__restrict__ gpq, const int *__restrict__ gmeta, const int *__restrict__ order, int np, CellDev c, PolarDev p,
+              double *acc, const double *dmu, GsCtl *ctl, long long *prof) {
+	extern __shared__ __align__(16) double s_raw[];
+	int *applied = (int *)(ctl + 1);
+	const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+	const int cta = blockIdx.x, U = gridDim.x;
+	const int nblk = (np + kGsB - 1) / kGsB, nchunks = (np + kGsRows - 1) / kGsRows;
+	constexpr int kChunksPerBlk = kGsB / kGsRows;
+	{
 		// warps work independently: global warp gwid owns the chunks ch = gwid, gwid + GW, ...  (8 consecutive rows of the
 		// sweep order each) and keeps its own copy of the panel in shared memory
 		double4 *w_col = (double4 *)s_raw + warp * 2 * kGsB;
 		double4 *w_dm = w_col + kGsB;
-		const int GW = U * kGsWarps, gwid = (cta - kGsCluster) * kGsWarps + warp;
+		// (warp-major numbering: when there are more chunks than warps, the second chunks go one to each CTA instead of eight to a
+		// few CTAs — an SM with twice the work falls behind by a few thousand cycles per panel and stalls the solver at the end)
+		const int GW = U * kGsWarps, gwid = warp * U + cta;
 		const int r = lane & 7, cl = lane >> 3;             // row of the chunk, column lane
 		for (int blk = 0; blk < nblk; blk++) {
 			const int base = blk * kGsB, cnt = min(kGsB, np - base);
 			// the panel's own rows and the rows of the next kGsAhead blocks belong to the cluster
 			const int skip0 = blk * kChunksPerBlk, skip1 = min(blk + 1 + kGsAhead, nblk) * kChunksPerBlk;
+			const int first = gwid;
 			bool any = false;
-			for (int ch = gwid; ch < nchunks; ch += GW) any = any || !(ch >= skip0 && ch < skip1);
+			for (int ch = first; ch < nchunks; ch += GW) any = any || !(ch >= skip0 && ch < skip1);
 			if (!any) continue;
 			__syncwarp();
 			for (int cc = lane; cc < cnt; cc += 32) {
 				const double4 g = gpq[base + cc];
 				w_col[cc] = make_double4(g.x, g.y, g.z, __longlong_as_double((long long)gmeta[base + cc]));   // alpha travels in w_dm.w
 			}
+			const bool pw = prof && cta == 0 && warp == 0 && lane == 0;
+			if (pw) prof[(nblk + blk) * 8 + 0] = clock64();
 			if (lane == 0) while (ld_flag(&ctl->solved) <= blk) __nanosleep(32);
 			__syncwarp();
 			__threadfence();
+			if (pw) prof[(nblk + blk) * 8 + 1] = clock64();
 			for (int cc = lane; cc < cnt; cc += 32)
 				w_dm[cc] = make_double4(__ldcg(dmu + 3 * (base + cc)), __ldcg(dmu + 3 * (base + cc) + 1), __ldcg(dmu + 3 * (base + cc) + 2), EXPD ? 0.0 : gpq[base + cc].w);
 			__syncwarp();
-			for (int ch = gwid; ch < nchunks; ch += GW) {
-				if (ch >= skip0 && ch < skip1) continue;
-				const int pos = ch * kGsRows + r;
-				const bool on = pos < np;
-				const double4 pr = on ? gpq[pos] : make_double4(0, 0, 0, 0);
-				const int mr = on ? gmeta[pos] : 0;
-				double ax = 0, ay = 0, az = 0;
-				if (on) {
+			// all my chunks of this panel first, then their running contractions (each row has exactly one writer, so the atomic adds
+			// are ordered and the result deterministic), ONE fence, then the flags: a warp that owns two chunks must not pay two fences
+			for (int ch0 = first; ch0 < nchunks; ch0 += 2 * GW) {
+				double sx[2], sy[2], sz[2];
+				int chs[2];
+#pragma unroll
+				for (int w = 0; w < 2; w++) {
+					const int ch = ch0 + w * GW;
+					chs[w] = (ch < nchunks && !(ch >= skip0 && ch < skip1)) ? ch : -1;
+					sx[w] = sy[w] = sz[w] = 0.0;
+					if (chs[w] < 0) continue;
+					const int pos = ch * kGsRows + r;
+					const bool on = pos < np;
+					const double4 pr = on ? gpq[pos] : make_double4(0, 0, 0, 0);
+					const int mr = on ? gmeta[pos] : 0;
+					double ax = 0, ay = 0, az = 0;
+					if (on) {
 #pragma unroll 4
-					for (int cc = cl; cc < cnt; cc += 4) {
-						double4 pc = w_col[cc];
-						const double4 dm = w_dm[cc];
-						const int mc = __double2loint(pc.w);
-						if (!EXPD) pc.w = dm.w;                           // alpha of the column (linear damping)
-						gs_contract<ORTHO, EXPD>(c, p, pr, mr, pc, mc, dm, ax, ay, az);
+						for (int cc = cl; cc < cnt; cc += 4) {
+							double4 pc = w_col[cc];
+							const double4 dm = w_dm[cc];
+							const int mc = __double2loint(pc.w);
+							if (!EXPD) pc.w = dm.w;                           // alpha of the column (linear damping)
+							gs_contract<ORTHO, EXPD>(c, p, pr, mr, pc, mc, dm, ax, ay, az);
+						}
 					}
+					ax += __shfl_xor_sync(0xffffffffu, ax, 8); ay += __shfl_xor_sync(0xffffffffu, ay, 8); az += __shfl_xor_sync(0xffffffffu, az, 8);
+					ax += __shfl_xor_sync(0xffffffffu, ax, 16); ay += __shfl_xor_sync(0xffffffffu, ay, 16); az += __shfl_xor_sync(0xffffffffu, az, 16);
+					sx[w] = ax; sy[w] = ay; sz[w] = az;
 				}
-				ax += __shfl_xor_sync(0xffffffffu, ax, 8); ay += __shfl_xor_sync(0xffffffffu, ay, 8); az += __shfl_xor_sync(0xffffffffu, az, 8);
-				ax += __shfl_xor_sync(0xffffffffu, ax, 16); ay += __shfl_xor_sync(0xffffffffu, ay, 16); az += __shfl_xor_sync(0xffffffffu, az, 16);
-				if (cl == 0 && on) {
-					const int i = order[pos];
-					__stcg(acc + 3 * i, __ldcg(acc + 3 * i) + ax);
-					__stcg(acc + 3 * i + 1, __ldcg(acc + 3 * i + 1) + ay);
-					__stcg(acc + 3 * i + 2, __ldcg(acc + 3 * i + 2) + az);
+				if (pw) prof[(nblk + blk) * 8 + 2] = clock64();
+#pragma unroll
+				for (int w = 0; w < 2; w++) {
+					const int pos = chs[w] * kGsRows + r;
+					if (chs[w] >= 0 && cl == 0 && pos < np) {
+						const int i = order[pos];
+						atomicAdd(acc + 3 * i, sx[w]); atomicAdd(acc + 3 * i + 1, sy[w]); atomicAdd(acc + 3 * i + 2, sz[w]);
+					}
 				}
 				__threadfence();
 				__syncwarp();
-				if (lane == 0) st_flag(applied + ch, blk + 1);
+				if (lane < 2 && chs[lane] >= 0) st_flag(applied + chs[lane], blk + 1);
+				if (pw) prof[(nblk + blk) * 8 + 3] = clock64();
 			}
 		}
 	}
