@@ -732,7 +732,7 @@ static int run_polar(mpmc_engine *e) {
 		LAUNCHED(e);
 		const size_t smem = sizeof(double2) * kFrSites * 3 * (kmax + 1);
 { Timed _t(e, MPMC_K_FIELD_RECIP);
-		k_field_recip<<<dim3((n + kFrSites - 1) / kFrSites, B), kFrSites, smem, e->stream>>>(e->d_posq.p, n, e->cap, e->d_kvec.p, nk, kmax, e->d_S_all.p,
+		k_field_recip<<<dim3((n + kFrSites - 1) / kFrSites, B), kFrSites * kFrLanes, smem, e->stream>>>(e->d_posq.p, n, e->cap, e->d_kvec.p, nk, kmax, e->d_S_all.p,
 		                                                                                     e->cell, 8.0 * kPi / e->cell.volume, e->d_efs.p);
 		LAUNCHED(e);
  }		{ Timed _t(e, MPMC_K_FIELD_REAL); if ((rc = run_field_real<ORTHO, true>(e))) return rc; }
@@ -869,7 +869,7 @@ static int run_polar(mpmc_engine *e) {
 			if (it == 1 || (ranked && it == 2)) {
 				gs_order = e->d_plist.p;
 				if (ranked && it == 2) {
-					k_rank_order_plist<<<(np + 255) / 256, 256, 0, e->stream>>>(e->d_rank.p, e->d_plist.p, np, e->d_order.p);
+					k_rank_order_plist<<<(np + kOrdI - 1) / kOrdI, kOrdThreads, 0, e->stream>>>(e->d_rank.p, e->d_plist.p, np, e->d_order.p);
 					LAUNCHED(e);
 					gs_order = e->d_order.p;
 				}
@@ -1001,7 +1001,7 @@ static int enqueue_energy(mpmc_engine *e) {
 		LAUNCHED(e);
 		if (cf.polarization) {
 			if ((rc = run_polar<ORTHO>(e))) return rc;
-			k_polar_energy<<<B, 256, 0, e->stream>>>(e->d_mu.p, e->d_efs.p, e->d_efic.p, e->d_rrms.p, n, e->d_result.p);
+			k_polar_energy<<<B, 1024, 0, e->stream>>>(e->d_mu.p, e->d_efs.p, e->d_efic.p, e->d_rrms.p, n, e->d_result.p);
 			LAUNCHED(e);
 		}
 	}

@@ -126,9 +126,10 @@ __global__ void k_dipole_fail(const double *__restrict__ alpha, const double *__
 }
 
 // tail of polar() (:2609-2618) and get_dipole_rrms() (:2639-2657): result record slots 5..7 = sum mu.E_s, sum mu.dE_ind, sum rrms
-__global__ void k_polar_energy(const double *__restrict__ mu, const double *__restrict__ efs, const double *__restrict__ efic,
-                               const double *__restrict__ rrms, int n, double *__restrict__ out) {
-	__shared__ double s_red[3][256];
+__global__ void __launch_bounds__(1024)
+k_polar_energy(const double *__restrict__ mu, const double *__restrict__ efs, const double *__restrict__ efic,
+               const double *__restrict__ rrms, int n, double *__restrict__ out) {
+	__shared__ double s_red[3][1024];
 	const int bead = blockIdx.x;
 	double a = 0, b = 0, r = 0;
 	for (int i = threadIdx.x; i < n; i += blockDim.x) {
@@ -150,23 +151,28 @@ __global__ void k_polar_energy(const double *__restrict__ mu, const double *__re
 
 // stable descending order of the polarizable sites by rank metric (update_ranking, :3631-3656, restricted to alpha != 0:
 // the other sites only ever set mu = 0).  order[pos] = site.
-__global__ void k_rank_order_plist(const double *__restrict__ rank, const int *__restrict__ plist, int np, int *__restrict__ order) {
-	__shared__ double s_m[256];
-	const int t = blockIdx.x * blockDim.x + threadIdx.x;
+__global__ void __launch_bounds__(kOrdThreads)
+k_rank_order_plist(const double *__restrict__ rank, const int *__restrict__ plist, int np, int *__restrict__ order) {
+	// CTA = 32 sites x 8 j-lanes (the first version walked all np partners with one thread per site: 127 us at np = 9200)
+	__shared__ double s_m[kOrdTileJ];
+	const int tid = threadIdx.x, jl = tid % kOrdJ, il = tid / kOrdJ;
+	const int t = blockIdx.x * kOrdI + il;
 	const int i = t < np ? plist[t] : 0;
 	const double mi = t < np ? rank[i] : 0;
 	int pos = 0;
-	for (int j0 = 0; j0 < np; j0 += 256) {
+	for (int j0 = 0; j0 < np; j0 += kOrdTileJ) {
 		__syncthreads();
-		if (j0 + (int)threadIdx.x < np) s_m[threadIdx.x] = rank[plist[j0 + threadIdx.x]];
+		if (j0 + tid < np) s_m[tid] = rank[plist[j0 + tid]];
 		__syncthreads();
-		const int jn = min(256, np - j0);
-		for (int jj = 0; jj < jn; jj++) {
+		const int jn = min(kOrdTileJ, np - j0);
+		for (int jj = jl; jj < jn; jj += kOrdJ) {
 			const double mj = s_m[jj];
 			pos += (mj > mi) || (mj == mi && j0 + jj < t);
 		}
 	}
-	if (t < np) order[pos] = i;
+#pragma unroll
+	for (int o = kOrdJ / 2; o > 0; o >>= 1) pos += __shfl_xor_sync(0xffffffffu, pos, o);
+	if (jl == 0 && t < np) order[pos] = i;
 }
 
 // bead-chain bookkeeping ------------------------------------------------------------------------------------

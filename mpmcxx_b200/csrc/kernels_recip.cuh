@@ -13,7 +13,8 @@ namespace mpmc {
 constexpr int kMaxKmax   = 15;            // table rows per axis = kmax+1 <= 16
 constexpr int kSkSites   = 64;            // sites per CTA in the structure-factor kernel
 constexpr int kSkThreads = 256;
-constexpr int kFrSites   = 128;           // sites (= threads) per CTA in the reciprocal-field kernel
+constexpr int kFrSites   = 32;            // sites per CTA in the reciprocal-field kernel
+constexpr int kFrLanes   = 4;             // k lanes per site (threads per CTA = kFrSites * kFrLanes)
 
 struct KVec { double kx, ky, kz, w_energy, w_field; int l0, l1, l2, pad; };   // w_field = exp(-k^2/4a_p^2)/k^2
 
@@ -115,25 +116,33 @@ __global__ void k_recip_energy(const double2 *__restrict__ S, const KVec *__rest
 
 // K5 (reciprocal part): recip_term() (src/System.Energy.cpp:2834-2896).  One thread per site; S_all(k) includes the
 // frozen sites (:2868-2872).  ef[i] = (8 pi / V) sum_k k w_field(k) [sin(k.r_i) Re S - cos(k.r_i) Im S]  (overwrites ef).
-__global__ void __launch_bounds__(kFrSites)
+__global__ void __launch_bounds__(kFrSites * kFrLanes)
 k_field_recip(const double4 *__restrict__ posq, int n, int stride, const KVec *__restrict__ kv, int nk, int kmax,
               const double2 *__restrict__ S, CellDev c, double eight_pi_over_v, double *__restrict__ ef) {
+	// 32 sites x 4 k-lanes per CTA: ~2.1 CTAs per SM at N = 10^4 (the first version ran 79 CTAs of 128 threads on 148 SMs)
 	extern __shared__ double2 s_tab[];               // [3*(kmax+1)][kFrSites]
 	const int bead = blockIdx.y;
-	const int i = blockIdx.x * kFrSites + threadIdx.x;
-	const double4 p = (i < n) ? posq[(size_t)bead * stride + i] : make_double4(0, 0, 0, 0);
-	build_phase_table(c, p.x, p.y, p.z, kmax, s_tab, kFrSites, threadIdx.x);
-	// each thread only reads its own column: no barrier needed
+	const int sl = threadIdx.x / kFrLanes, kl = threadIdx.x % kFrLanes;
+	const int i = blockIdx.x * kFrSites + sl;
+	if (kl == 0) {
+		const double4 p = (i < n) ? posq[(size_t)bead * stride + i] : make_double4(0, 0, 0, 0);
+		build_phase_table(c, p.x, p.y, p.z, kmax, s_tab, kFrSites, sl);
+	}
+	__syncthreads();
 	double ex = 0, ey = 0, ez = 0;
-	for (int ik = 0; ik < nk; ik++) {
+	for (int ik = kl; ik < nk; ik += kFrLanes) {
 		const KVec k = kv[ik];
-		const double2 e = cmul(cmul(tab_at(s_tab, kmax, kFrSites, threadIdx.x, 0, k.l0), tab_at(s_tab, kmax, kFrSites, threadIdx.x, 1, k.l1)),
-		                       tab_at(s_tab, kmax, kFrSites, threadIdx.x, 2, k.l2));
+		const double2 e = cmul(cmul(tab_at(s_tab, kmax, kFrSites, sl, 0, k.l0), tab_at(s_tab, kmax, kFrSites, sl, 1, k.l1)),
+		                       tab_at(s_tab, kmax, kFrSites, sl, 2, k.l2));
 		const double2 s = S[(size_t)bead * nk + ik];
 		const double t = k.w_field * (e.y * s.x - e.x * s.y);
 		ex += k.kx * t; ey += k.ky * t; ez += k.kz * t;
 	}
-	if (i < n) {
+#pragma unroll
+	for (int o = kFrLanes / 2; o > 0; o >>= 1) {
+		ex += __shfl_xor_sync(0xffffffffu, ex, o); ey += __shfl_xor_sync(0xffffffffu, ey, o); ez += __shfl_xor_sync(0xffffffffu, ez, o);
+	}
+	if (kl == 0 && i < n) {
 		double *e = ef + ((size_t)bead * n + i) * 3;
 		e[0] = ex * eight_pi_over_v; e[1] = ey * eight_pi_over_v; e[2] = ez * eight_pi_over_v;
 	}
