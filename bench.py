@@ -500,15 +500,6 @@ def run_pi(args, embedded=False):
         dist.destroy_process_group()
 
 
-def last_tiles(eng):
-    # D2H per energy(): one 32-byte partial per listed tile + 32 bytes of scalars
-    n = eng.n
-    nt = (n + 127) // 128
-    fz = np.array([bool(np.all(eng.system.frozen[t * 128:(t + 1) * 128])) for t in range(nt)])
-    nff = int(fz.sum())
-    return nt * (nt + 1) // 2 - nff * (nff + 1) // 2
-
-
 def extra_workloads(engine, device, peak_tflops, steps=20):
     """Secondary single-GPU numbers: config 3 (bulk LJ argon, the pair kernel alone) and the Jacobi solver variant of config 4."""
     import torch

@@ -131,10 +131,8 @@ struct mpmc_engine {
 	std::vector<double> h_q, h_alpha, h_eps, h_sigma, h_mass;
 	std::vector<int> h_mol, h_frozen;
 	// derived host state
-	std::vector<int2> tiles;
-	int pair_tile = kPairTile;       // tile side of the pair sweep chosen for this system size
 	std::vector<int> plist, mobile_q, frozen_q, mol_start;
-	std::vector<unsigned char> blk_frozen, mol_mobile;
+	std::vector<unsigned char> mol_mobile;
 	double lrc_pair = 0, lrc_self = 0, es_self = 0, n_pair_evals = 0;
 	bool topo_dirty = true, frozen_sk_dirty = true;
 	// device
@@ -142,9 +140,7 @@ struct mpmc_engine {
 	DevBuf<double2> d_lj;
 	DevBuf<double> d_alpha, d_mass;
 	DevBuf<int> d_meta, d_plist, d_mobile_q, d_frozen_q, d_mol_start, d_order, d_flags;
-	DevBuf<int2> d_tiles;
 	// second-generation pair sweep (kernels_pair2.cuh)
-	bool pair_v1 = false;            // developer switch (env MPMC_PAIR_V1=1): the first-generation tile kernel, for A/B timing
 	std::vector<PairSeg> segs;
 	PairParams pp;
 	RadialTable erf_tab;
@@ -155,7 +151,7 @@ struct mpmc_engine {
 	bool perm_identity = true;
 	DevBuf<double> d_erf_tab;
 	int pair_grid = 0;
-	DevBuf<unsigned char> d_blk_frozen, d_mol_mobile;
+	DevBuf<unsigned char> d_mol_mobile;
 	DevBuf<KVec> d_kvec;
 	DevBuf<PairPartial> d_partials;
 	DevBuf<double2> d_sk_part, d_S_mobile, d_S_frozen, d_S_all;
@@ -344,31 +340,6 @@ int rebuild_topology(mpmc_engine *e) {
 		CK(cudaMemcpyAsync(e->d_alpha.p, e->h_alpha.data(), n * sizeof(double), cudaMemcpyHostToDevice, e->stream));
 		CK(cudaMemcpyAsync(e->d_mass.p, e->h_mass.data(), n * sizeof(double), cudaMemcpyHostToDevice, e->stream));
 	}
-	// frozen-block flags (32-site granularity) and the triangular tile list of the energy sweep
-	const int nb32 = (n + kOrdI - 1) / kOrdI;
-	e->blk_frozen.assign(std::max(nb32, 1), 0);
-	for (int b = 0; b < nb32; b++) {
-		bool all = true;
-		for (int i = b * kOrdI; i < std::min(n, (b + 1) * kOrdI); i++) all = all && e->h_frozen[i];
-		e->blk_frozen[b] = all;
-	}
-	// tile side: the largest of 128/64/32 that still gives >= 16 CTAs per SM (balance matters more than tile reuse: the sweep is
-	// FP64-bound and a tile's loads are 2/T of its work)
-	for (int T : {128, 64, 32}) {
-		e->pair_tile = T;
-		const int nt = (n + T - 1) / T;
-		std::vector<unsigned char> tile_frozen(std::max(nt, 1), 0);
-		for (int t = 0; t < nt; t++) {
-			bool all = true;
-			for (int i = t * T; i < std::min(n, (t + 1) * T); i++) all = all && e->h_frozen[i];
-			tile_frozen[t] = all;
-		}
-		e->tiles.clear();
-		for (int ta = 0; ta < nt; ta++)
-			for (int tb = ta; tb < nt; tb++)
-				if (!(tile_frozen[ta] && tile_frozen[tb])) e->tiles.push_back(make_int2(ta, tb));
-		if ((long long)e->tiles.size() * e->B >= 16LL * e->num_sms) break;
-	}
 	// work lists
 	e->plist.clear(); e->mobile_q.clear(); e->frozen_q.clear(); e->mol_start.clear(); e->mol_mobile.clear();
 	long long nfrozen = 0;
@@ -386,8 +357,8 @@ int rebuild_topology(mpmc_engine *e) {
 		if (!vec.empty()) CK(cudaMemcpyAsync(dbuf.p, vec.data(), vec.size() * sizeof(vec[0]), cudaMemcpyHostToDevice, e->stream));
 		return MPMC_OK;
 	};
-	if ((rc = up(e->d_tiles, e->tiles)) || (rc = up(e->d_plist, e->plist)) || (rc = up(e->d_mobile_q, e->mobile_q)) ||
-	    (rc = up(e->d_frozen_q, e->frozen_q)) || (rc = up(e->d_mol_start, e->mol_start)) || (rc = up(e->d_blk_frozen, e->blk_frozen)) ||
+	if ((rc = up(e->d_plist, e->plist)) || (rc = up(e->d_mobile_q, e->mobile_q)) ||
+	    (rc = up(e->d_frozen_q, e->frozen_q)) || (rc = up(e->d_mol_start, e->mol_start)) ||
 	    (rc = up(e->d_mol_mobile, e->mol_mobile))) return rc;
 	CK(cudaStreamSynchronize(e->stream));   // the std::vectors above go out of scope / may be rebuilt
 	if ((rc = prepare_pair_sweep(e))) return rc;
@@ -960,10 +931,9 @@ static int enqueue_energy(mpmc_engine *e) {
 	Timed _whole(e, MPMC_K_ENERGY_TOTAL);
 	const bool es = !cf.rd_only;
 	// pair sweep: lj() + coulombic_real()
-	int ntiles = (int)e->tiles.size();
-	if (!e->pair_v1) {
-		ntiles = e->pp.items_per_bead;
-		if ((rc = e->d_partials.ensure((size_t)B * std::max(ntiles, 1)))) return rc;
+	const int nitems = e->pp.items_per_bead;
+	{
+		if ((rc = e->d_partials.ensure((size_t)B * std::max(nitems, 1)))) return rc;
 		const size_t smem = pair_sweep_smem(es, e->pp.tab_rows);
 		Timed _t(e, MPMC_K_PAIR);
 		const double4 *spq = e->d_posq.p;        // one class in list order (bulk LJ, single-site models): the table already is sorted
@@ -975,19 +945,8 @@ static int enqueue_energy(mpmc_engine *e) {
 		if (es) k_pair_sweep<ORTHO, true><<<e->pair_grid, kPwThreads, smem, e->stream>>>(spq, e->d_slj.p, e->d_pmeta.p, e->cap, B, e->d_segs.p, e->d_item_seg.p, e->pp, e->cell, e->d_erf_tab.p, e->d_partials.p);
 		else k_pair_sweep<ORTHO, false><<<e->pair_grid, kPwThreads, smem, e->stream>>>(spq, e->d_slj.p, e->d_pmeta.p, e->cap, B, e->d_segs.p, e->d_item_seg.p, e->pp, e->cell, nullptr, e->d_partials.p);
 		LAUNCHED(e);
-	} else {
-	if ((rc = e->d_partials.ensure((size_t)B * std::max(ntiles, 1)))) return rc;
-	if (ntiles) {
-{ Timed _t(e, MPMC_K_PAIR);
-#define PAIR_LAUNCH(ESV, TV) k_pair_energy<ORTHO, ESV, TV><<<dim3(ntiles, B), TV, 0, e->stream>>>(e->d_posq.p, e->d_lj.p, e->d_meta.p, n, e->cap, e->d_tiles.p, ntiles, e->cell, e->d_partials.p)
-		if (e->pair_tile == 128) { if (es) PAIR_LAUNCH(true, 128); else PAIR_LAUNCH(false, 128); }
-		else if (e->pair_tile == 64) { if (es) PAIR_LAUNCH(true, 64); else PAIR_LAUNCH(false, 64); }
-		else { if (es) PAIR_LAUNCH(true, 32); else PAIR_LAUNCH(false, 32); }
-#undef PAIR_LAUNCH
-		LAUNCHED(e);
- }	}
 	}
-	k_reduce_partials<<<B, 256, 0, e->stream>>>(e->d_partials.p, ntiles, e->d_result.p);
+	k_reduce_partials<<<B, 256, 0, e->stream>>>(e->d_partials.p, nitems, e->d_result.p);
 	LAUNCHED(e);
 	if (es) {
 		const int nk = (int)e->kvec.size();
@@ -1063,8 +1022,6 @@ int mpmc_create(const mpmc_config *cfg, mpmc_engine **out) {
 		const size_t pmax = pair_sweep_smem(true, 1024);     // tables of up to 1024 rows (32 octaves)
 		if ((rc = set_smem(k_pair_sweep<true, true>, pmax)) || (rc = set_smem(k_pair_sweep<false, true>, pmax)) ||
 		    (rc = set_smem(k_pair_sweep<true, false>, pmax)) || (rc = set_smem(k_pair_sweep<false, false>, pmax))) { mpmc_destroy(e); return rc; }
-		const char *v1 = getenv("MPMC_PAIR_V1");
-		e->pair_v1 = v1 && v1[0] == '1';
 	}
 	{
 		// the Gauss-Seidel pipeline: one cluster (solver + helpers) and an updater kernel on every other SM, 2 CTAs each
@@ -1092,7 +1049,7 @@ int mpmc_destroy(mpmc_engine *e) {
 	if (e->stream) cudaStreamSynchronize(e->stream);
 	e->d_posq.release(); e->d_lj.release(); e->d_alpha.release(); e->d_mass.release(); e->d_meta.release(); e->d_plist.release();
 	e->d_mobile_q.release(); e->d_frozen_q.release(); e->d_mol_start.release(); e->d_order.release(); e->d_flags.release();
-	e->d_tiles.release(); e->d_segs.release(); e->d_item_seg.release(); e->d_pmeta.release(); e->d_perm.release(); e->d_slj.release(); e->d_spq.release(); e->d_stage.release(); e->d_erf_tab.release(); e->d_blk_frozen.release(); e->d_mol_mobile.release(); e->d_kvec.release(); e->d_partials.release();
+	e->d_segs.release(); e->d_item_seg.release(); e->d_pmeta.release(); e->d_perm.release(); e->d_slj.release(); e->d_spq.release(); e->d_stage.release(); e->d_erf_tab.release(); e->d_mol_mobile.release(); e->d_kvec.release(); e->d_partials.release();
 	e->d_sk_part.release(); e->d_S_mobile.release(); e->d_S_frozen.release(); e->d_S_all.release();
 	e->d_efs.release(); e->d_efi.release(); e->d_efic.release(); e->d_mu.release(); e->d_new_mu.release(); e->d_old_mu.release();
 	e->d_rrms.release(); e->d_rank.release(); e->d_acc.release(); e->d_dmu.release(); e->d_tri.release(); e->d_gsctl.release(); e->d_gmeta.release(); e->d_nplist.release(); e->d_gpq.release(); e->d_cparts.release(); e->d_field_tab.release(); e->d_fp_list.release(); e->d_mp_list.release(); e->d_recount.release(); e->d_r2min_ff.release(); e->d_t2.release(); e->d_t2_cached.release(); e->d_cnt_ff.release(); e->d_mobile_sites.release(); e->d_frozen_sites.release(); e->d_allq.release(); e->d_com.release(); e->d_mol_mass.release(); e->d_chain.release();

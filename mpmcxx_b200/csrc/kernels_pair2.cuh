@@ -50,15 +50,6 @@ struct PairParams {
 	int nseg;
 };
 
-__device__ __forceinline__ double fast_rcp(double x) {
-	double y;
-	asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
-	double e = fma(-x, y, 1.0);
-	y = fma(y, e, y);
-	e = fma(-x, y, 1.0);
-	return fma(y, e, y);
-}
-
 // row lookup of a radial table held in shared memory: value of function 0 of a 1-function table at u
 // (the row index is clamped to the table: callers discard the value when u lies outside [u_lo, u_hi))
 __device__ __forceinline__ double tab_eval1(const double *rows, int base, int nrows, double u) {

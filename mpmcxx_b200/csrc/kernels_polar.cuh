@@ -21,69 +21,8 @@ __global__ void k_dipole_init(const double *__restrict__ alpha, const double *__
 	if (t % 3 == 0) rrms[t / 3] = 0;
 }
 
-// One full contraction acc_i = sum_{j != i} T_ij mu_j over the polarizable sites j (mu_j == 0 exactly elsewhere).
-//   SWEEP_JACOBI : contract_dipoles() in Jacobi form (:3564-3598): efi = -acc, new_mu = alpha (E_s + efi); sites with
-//                  alpha == 0 get efi = new_mu = 0.  mu is NOT touched (the caller relaxes it afterwards, :3526-3536).
-//   SWEEP_PALMO  : palmo_contraction() (:3602-3627): efic = -efi - acc, for every site.
-//   SWEEP_PALMO_NONPOLAR : the same, but only for the sites with alpha == 0 (the Gauss-Seidel path already holds acc for the rest).
-//   SWEEP_ACC    : acc_out = acc for the polarizable sites (the running contraction the Gauss-Seidel pipeline keeps up to date).
-// Layout as the other ordered sweeps: CTA = 32 sites x 8 j-lanes.
+// modes of the contraction sweeps (kernels_polar2.cuh: k_contract_finish)
 enum { SWEEP_JACOBI = 0, SWEEP_PALMO = 1, SWEEP_PALMO_NONPOLAR = 2, SWEEP_ACC = 3 };
-template <bool ORTHO, int MODE>
-__global__ void __launch_bounds__(kOrdThreads)
-k_dipole_sweep(const double4 *__restrict__ posq, const double *__restrict__ alpha, const int *__restrict__ meta,
-               const int *__restrict__ plist, int np, int n, int stride, CellDev c, PolarDev p,
-               const double *__restrict__ mu, const double *__restrict__ efs, double *__restrict__ efi,
-               double *__restrict__ new_mu, double *__restrict__ efic) {
-	__shared__ double4 s_pq[kOrdTileJ];
-	__shared__ double  s_mu[kOrdTileJ][3];
-	__shared__ double  s_al[kOrdTileJ];
-	__shared__ int     s_meta[kOrdTileJ];
-	__shared__ int     s_idx[kOrdTileJ];
-	const int bead = blockIdx.y;
-	const double4 *pq = posq + (size_t)bead * stride;
-	const double *mub = mu + (size_t)bead * n * 3;
-	const int tid = threadIdx.x, jl = tid % kOrdJ, il = tid / kOrdJ;
-	const int i = blockIdx.x * kOrdI + il;
-	double4 pi = make_double4(0, 0, 0, 0);
-	double ai = 0; int mi = 0;
-	if (i < n) { pi = pq[i]; ai = alpha[i]; mi = meta[i]; }
-	const bool active = (i < n) && (MODE == SWEEP_PALMO || (MODE == SWEEP_PALMO_NONPOLAR ? ai == 0.0 : ai != 0.0));
-	double ax = 0, ay = 0, az = 0;
-	for (int j0 = 0; j0 < np; j0 += kOrdTileJ) {
-		__syncthreads();
-		if (j0 + tid < np) {
-			const int j = plist[j0 + tid];
-			s_idx[tid] = j; s_pq[tid] = pq[j]; s_al[tid] = alpha[j]; s_meta[tid] = meta[j];
-			s_mu[tid][0] = mub[3 * j]; s_mu[tid][1] = mub[3 * j + 1]; s_mu[tid][2] = mub[3 * j + 2];
-		}
-		__syncthreads();
-		const int jn = min(kOrdTileJ, np - j0);
-		if (active)
-			for (int jj = jl; jj < jn; jj += kOrdJ) {
-				if (s_idx[jj] == i) continue;
-				const double4 pj = s_pq[jj];
-				const bool excl = (meta_mol(mi) == meta_mol(s_meta[jj])) || pi.w == 0.0 || pj.w == 0.0;
-				tensor_contract<ORTHO>(c, p, pi.x, pi.y, pi.z, pj.x, pj.y, pj.z, excl, ai * s_al[jj],
-				                       s_mu[jj][0], s_mu[jj][1], s_mu[jj][2], ax, ay, az);
-			}
-	}
-	ax = jlane_sum(ax); ay = jlane_sum(ay); az = jlane_sum(az);
-	if (jl == 0 && i < n) {
-		const size_t o = ((size_t)bead * n + i) * 3;
-		if (MODE == SWEEP_PALMO || MODE == SWEEP_PALMO_NONPOLAR) {
-			if (active) { efic[o] = -efi[o] - ax; efic[o + 1] = -efi[o + 1] - ay; efic[o + 2] = -efi[o + 2] - az; }
-		} else if (MODE == SWEEP_ACC) {
-			if (active) { new_mu[o] = ax; new_mu[o + 1] = ay; new_mu[o + 2] = az; }     // new_mu doubles as the acc output pointer
-		} else if (ai != 0.0) {
-			efi[o] = -ax; efi[o + 1] = -ay; efi[o + 2] = -az;
-			new_mu[o] = ai * (efs[o] - ax); new_mu[o + 1] = ai * (efs[o + 1] - ay); new_mu[o + 2] = ai * (efs[o + 2] - az);
-		} else {
-			efi[o] = efi[o + 1] = efi[o + 2] = 0;
-			new_mu[o] = new_mu[o + 1] = new_mu[o + 2] = 0;
-		}
-	}
-}
 
 // calc_dipole_rrms() (:3147-3177) and the precision branch of are_we_done_yet() (:3227-3236).  flags[bead] is set to 1 when
 // some component still moves by more than the allowed error.
