@@ -168,7 +168,10 @@ struct mpmc_engine {
 	cudaStream_t stream2 = nullptr;
 	cudaEvent_t ev_upd = nullptr;
 	int *h_started = nullptr, *d_started = nullptr;   // mapped pinned word the solver kernel stamps when it is running
-	int gs_token = 0, gs_upd_grid = 0;
+	int gs_token = 0, gs_upd_grid = 0, gs_fused_grid = 0;
+	int *h_gs_abort = nullptr;      // pinned copy of GsCtl::abort after the last sweep of an energy()
+	bool gs_ran = false;
+	bool gs_fused = false;          // MPMC_GS_FUSED=1: updaters inside the solver's launch (for tools that serialise kernel launches)
 	RadialTable field_tab;
 	FieldParams fpar;
 	std::vector<int> nplist;
@@ -863,11 +866,13 @@ static int run_polar(mpmc_engine *e) {
 				for (int sw = 0; sw < ns; sw++) {   // one launch per sweep: the kernel boundary is the barrier between sweeps
 					CK(cudaMemsetAsync(e->d_gsctl.p, 0, sizeof(int) * (sizeof(GsCtl) / sizeof(int) + nchunks), e->stream));
 					const int token = ++e->gs_token;
-					if (expd) k_gs_pipeline<ORTHO, true><<<kGsCluster, kGsThreads, kGsSmemBytes, e->stream>>>(e->d_gpq.p, e->d_gmeta.p, gs_order, np, e->cell, pd, e->d_efs.p,
+					const int sgrid = e->gs_fused ? e->gs_fused_grid : kGsCluster;
+					if (expd) k_gs_pipeline<ORTHO, true><<<sgrid, kGsThreads, kGsSmemBytes, e->stream>>>(e->d_gpq.p, e->d_gmeta.p, gs_order, np, e->cell, pd, e->d_efs.p,
 					        e->d_mu.p, e->d_efi.p, e->d_new_mu.p, e->d_acc.p, e->d_dmu.p, e->d_tri.p, (GsCtl *)e->d_gsctl.p, sw == 0 ? prof : nullptr, e->d_started, token);
-					else k_gs_pipeline<ORTHO, false><<<kGsCluster, kGsThreads, kGsSmemBytes, e->stream>>>(e->d_gpq.p, e->d_gmeta.p, gs_order, np, e->cell, pd, e->d_efs.p,
+					else k_gs_pipeline<ORTHO, false><<<sgrid, kGsThreads, kGsSmemBytes, e->stream>>>(e->d_gpq.p, e->d_gmeta.p, gs_order, np, e->cell, pd, e->d_efs.p,
 					        e->d_mu.p, e->d_efi.p, e->d_new_mu.p, e->d_acc.p, e->d_dmu.p, e->d_tri.p, (GsCtl *)e->d_gsctl.p, sw == 0 ? prof : nullptr, e->d_started, token);
 					CK(cudaGetLastError());
+					if (e->gs_fused) { LAUNCHED(e); continue; }
 					// The updaters must not take the SMs the cluster needs (its CTAs want a whole SM's shared memory each): wait until the
 					// solver kernel is running — it stamps a mapped host word first thing — then fill the rest of the machine.
 					for (long long spin = 0; *(volatile int *)e->h_started != token; spin++) {
@@ -884,6 +889,8 @@ static int run_polar(mpmc_engine *e) {
 					LAUNCHED(e);
 				}
 				CK(cudaGetLastError());
+				CK(cudaMemcpyAsync(e->h_gs_abort, e->d_gsctl.p + 1, sizeof(int), cudaMemcpyDeviceToHost, e->stream));
+				e->gs_ran = true;
 			}
 			it += ns - 1;
 		}
@@ -1029,6 +1036,8 @@ int mpmc_create(const mpmc_config *cfg, mpmc_engine **out) {
 		CK(cudaEventCreateWithFlags(&e->ev_upd, cudaEventDisableTiming));
 		CK(cudaHostAlloc(&e->h_started, sizeof(int), cudaHostAllocMapped));
 		*e->h_started = 0;
+		CK(cudaMallocHost(&e->h_gs_abort, sizeof(int)));
+		*e->h_gs_abort = 0;
 		CK(cudaHostGetDevicePointer(&e->d_started, e->h_started, 0));
 		if ((rc = set_smem(k_gs_updaters<true, true>, kGsUpdaterSmemBytes)) || (rc = set_smem(k_gs_updaters<false, true>, kGsUpdaterSmemBytes)) ||
 		    (rc = set_smem(k_gs_updaters<true, false>, kGsUpdaterSmemBytes)) || (rc = set_smem(k_gs_updaters<false, false>, kGsUpdaterSmemBytes))) { mpmc_destroy(e); return rc; }
@@ -1036,6 +1045,17 @@ int mpmc_create(const mpmc_config *cfg, mpmc_engine **out) {
 		CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_gs_updaters<true, true>, kGsThreads, kGsUpdaterSmemBytes));
 		e->gs_upd_grid = std::max(1, e->num_sms - kGsCluster) * std::max(1, std::min(occ, 2));
 		e->gs_grid = kGsCluster;
+		// single-launch fallback: as many clusters as the device holds at one CTA per SM
+		cudaLaunchConfig_t lc = {};
+		lc.gridDim = dim3(e->num_sms / kGsCluster * kGsCluster); lc.blockDim = dim3(kGsThreads); lc.dynamicSmemBytes = kGsSmemBytes;
+		cudaLaunchAttribute at[1];
+		at[0].id = cudaLaunchAttributeClusterDimension; at[0].val.clusterDim.x = kGsCluster; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+		lc.attrs = at; lc.numAttrs = 1;
+		int ncl = 0;
+		CK(cudaOccupancyMaxActiveClusters(&ncl, k_gs_pipeline<true, true>, &lc));
+		e->gs_fused_grid = std::max(2, ncl) * kGsCluster;
+		const char *fz = getenv("MPMC_GS_FUSED");
+		e->gs_fused = fz && fz[0] == '1';
 	}
 	if ((rc = compute_cell(e, cfg->basis))) { mpmc_destroy(e); return rc; }
 	if (cfg->capacity > 0) e->cap = cfg->capacity;
@@ -1061,6 +1081,7 @@ int mpmc_destroy(mpmc_engine *e) {
 	if (e->stream2) { cudaStreamSynchronize(e->stream2); cudaStreamDestroy(e->stream2); }
 	if (e->ev_upd) cudaEventDestroy(e->ev_upd);
 	if (e->h_started) cudaFreeHost(e->h_started);
+	if (e->h_gs_abort) cudaFreeHost(e->h_gs_abort);
 	for (int r = 0; r < (int)e->peer_mbox.size(); r++) if (r != e->rank && e->peer_mbox[r]) cudaIpcCloseMemHandle(e->peer_mbox[r]);
 	if (e->d_mbox) cudaFree(e->d_mbox);
 	e->d_peers.release(); e->d_step.release();
@@ -1175,6 +1196,19 @@ int mpmc_energy_fetch(mpmc_engine *e, mpmc_energy_out *out) {
 	CK(cudaStreamSynchronize(e->stream));
 	e->enqueued = false;
 	if (e->timing) collect_timing(e);
+	if (e->gs_ran) {
+		e->gs_ran = false;
+		if (*e->h_gs_abort) {
+			// the solver and updater kernels were not run side by side (a tool that serialises kernel launches): the result of this
+			// evaluation is meaningless.  Switch this engine to the single-launch pipeline for good and evaluate again.
+			*e->h_gs_abort = 0;
+			if (e->gs_fused) FAIL(MPMC_ERR_CUDA, "the Gauss-Seidel pipeline timed out waiting for its own CTAs");
+			e->gs_fused = true;
+			int rc = mpmc_energy_enqueue(e);
+			if (rc) return rc;
+			return mpmc_energy_fetch(e, out);
+		}
+	}
 	const int B = e->B;
 	const mpmc_config &cf = e->cfg;
 	for (int b = 0; b < B; b++) {

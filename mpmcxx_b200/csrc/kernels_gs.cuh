@@ -49,7 +49,10 @@ constexpr size_t kGsSmemBytes = sizeof(double) * kGsSolverDoubles;
 constexpr size_t kGsUpdaterSmemBytes = sizeof(double) * kGsUpdaterDoubles;
 
 __device__ int g_gs_debug = 0;            // developer switch (mpmc_debug_gs_profile enable bits 1..): 2 = pushers idle, 4 = no rolling copy
-struct GsCtl { int solved; int pad[31]; };   // followed in memory by int applied[nchunks]
+struct GsCtl { int solved; int abort; int pad[30]; };   // followed in memory by int applied[nchunks]
+// `abort`: set when a CTA has waited ~2 s for the other kernel of the pipeline — the two kernels were not run side by side (a
+// tool that serialises launches).  Everybody then stops waiting, the sweep's result is meaningless and the host reports it.
+constexpr int kGsWaitLimit = 20000000;
 
 __device__ __forceinline__ int ld_flag(const int *p) { return *(const volatile int *)p; }
 __device__ __forceinline__ void st_flag(int *p, int v) { *(volatile int *)p = v; }
@@ -106,6 +109,101 @@ k_gs_tensors(const double4 *__restrict__ gpq, const int *__restrict__ gmeta, int
 		double *u = out + ((size_t)a * kGsB + b) * 6, *l = out + ((size_t)b * kGsB + a) * 6;
 		u[0] = xx; u[1] = yy; u[2] = zz; u[3] = xy; u[4] = xz; u[5] = yz;
 		l[0] = xx; l[1] = yy; l[2] = zz; l[3] = xy; l[4] = xz; l[5] = yz;
+	}
+}
+
+// The updaters' work, shared by the updater kernel and by the single-launch fallback of the pipeline kernel: CTA `cta` of `U`.
+template <bool ORTHO, bool EXPD>
+__device__ __forceinline__ void gs_updater_body(double *s_raw, int cta, int U, const double4 *__restrict__ gpq, const int *__restrict__ gmeta,
+                                                const int *__restrict__ order, int np, const CellDev &c, const PolarDev &p, double *acc,
+                                                const double *dmu, GsCtl *ctl, long long *prof) {
+	int *applied = (int *)(ctl + 1);
+	const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+	const int nblk = (np + kGsB - 1) / kGsB, nchunks = (np + kGsRows - 1) / kGsRows;
+	constexpr int kChunksPerBlk = kGsB / kGsRows;
+	{
+		// warps work independently: global warp gwid owns the chunks ch = gwid, gwid + GW, ...  (8 consecutive rows of the
+		// sweep order each) and keeps its own copy of the panel in shared memory
+		double4 *w_col = (double4 *)s_raw + warp * 2 * kGsB;
+		double4 *w_dm = w_col + kGsB;
+		// (warp-major numbering: when there are more chunks than warps, the second chunks go one to each CTA instead of eight to a
+		// few CTAs — an SM with twice the work falls behind by a few thousand cycles per panel and stalls the solver at the end)
+		const int GW = U * kGsWarps, gwid = warp * U + cta;
+		const int r = lane & 7, cl = lane >> 3;             // row of the chunk, column lane
+		for (int blk = 0; blk < nblk; blk++) {
+			const int base = blk * kGsB, cnt = min(kGsB, np - base);
+			// the panel's own rows and the rows of the next kGsAhead blocks belong to the cluster
+			const int skip0 = blk * kChunksPerBlk, skip1 = min(blk + 1 + kGsAhead, nblk) * kChunksPerBlk;
+			const int first = gwid;
+			bool any = false;
+			for (int ch = first; ch < nchunks; ch += GW) any = any || !(ch >= skip0 && ch < skip1);
+			if (!any) continue;
+			__syncwarp();
+			for (int cc = lane; cc < cnt; cc += 32) {
+				const double4 g = gpq[base + cc];
+				w_col[cc] = make_double4(g.x, g.y, g.z, __longlong_as_double((long long)gmeta[base + cc]));   // alpha travels in w_dm.w
+			}
+			const bool pw = prof && cta == 0 && warp == 0 && lane == 0;
+			if (pw) prof[(nblk + blk) * 8 + 0] = clock64();
+			if (lane == 0) {
+				int spins = 0;
+				while (ld_flag(&ctl->solved) <= blk && !ld_flag(&ctl->abort)) {
+					__nanosleep(32);
+					if (++spins > 3 * kGsWaitLimit) st_flag(&ctl->abort, 1);
+				}
+			}
+			if (__shfl_sync(0xffffffffu, ld_flag(&ctl->abort), 0)) return;
+			__syncwarp();
+			__threadfence();
+			if (pw) prof[(nblk + blk) * 8 + 1] = clock64();
+			for (int cc = lane; cc < cnt; cc += 32)
+				w_dm[cc] = make_double4(__ldcg(dmu + 3 * (base + cc)), __ldcg(dmu + 3 * (base + cc) + 1), __ldcg(dmu + 3 * (base + cc) + 2), EXPD ? 0.0 : gpq[base + cc].w);
+			__syncwarp();
+			// all my chunks of this panel first, then their running contractions (each row has exactly one writer, so the atomic adds
+			// are ordered and the result deterministic), ONE fence, then the flags: a warp that owns two chunks must not pay two fences
+			for (int ch0 = first; ch0 < nchunks; ch0 += 2 * GW) {
+				double sx[2], sy[2], sz[2];
+				int chs[2];
+#pragma unroll
+				for (int w = 0; w < 2; w++) {
+					const int ch = ch0 + w * GW;
+					chs[w] = (ch < nchunks && !(ch >= skip0 && ch < skip1)) ? ch : -1;
+					sx[w] = sy[w] = sz[w] = 0.0;
+					if (chs[w] < 0) continue;
+					const int pos = ch * kGsRows + r;
+					const bool on = pos < np;
+					const double4 pr = on ? gpq[pos] : make_double4(0, 0, 0, 0);
+					const int mr = on ? gmeta[pos] : 0;
+					double ax = 0, ay = 0, az = 0;
+					if (on) {
+#pragma unroll 4
+						for (int cc = cl; cc < cnt; cc += 4) {
+							double4 pc = w_col[cc];
+							const double4 dm = w_dm[cc];
+							const int mc = __double2loint(pc.w);
+							if (!EXPD) pc.w = dm.w;                           // alpha of the column (linear damping)
+							gs_contract<ORTHO, EXPD>(c, p, pr, mr, pc, mc, dm, ax, ay, az);
+						}
+					}
+					ax += __shfl_xor_sync(0xffffffffu, ax, 8); ay += __shfl_xor_sync(0xffffffffu, ay, 8); az += __shfl_xor_sync(0xffffffffu, az, 8);
+					ax += __shfl_xor_sync(0xffffffffu, ax, 16); ay += __shfl_xor_sync(0xffffffffu, ay, 16); az += __shfl_xor_sync(0xffffffffu, az, 16);
+					sx[w] = ax; sy[w] = ay; sz[w] = az;
+				}
+				if (pw) prof[(nblk + blk) * 8 + 2] = clock64();
+#pragma unroll
+				for (int w = 0; w < 2; w++) {
+					const int pos = chs[w] * kGsRows + r;
+					if (chs[w] >= 0 && cl == 0 && pos < np) {
+						const int i = order[pos];
+						atomicAdd(acc + 3 * i, sx[w]); atomicAdd(acc + 3 * i + 1, sy[w]); atomicAdd(acc + 3 * i + 2, sz[w]);
+					}
+				}
+				__threadfence();
+				__syncwarp();
+				if (lane < 2 && chs[lane] >= 0) st_flag(applied + chs[lane], blk + 1);
+				if (pw) prof[(nblk + blk) * 8 + 3] = clock64();
+			}
+		}
 	}
 }
 
@@ -272,7 +370,13 @@ k_gs_pipeline(const double4 *__restrict__ gpq, const int *__restrict__ gmeta, co
 					load_cols(blk + 1, lane); load_cols(blk + 1, lane + 32);
 					// (no updater touches these rows between panel blk-kGsAhead and my own write-back: safe to fetch now)
 					const int c0 = (base + kGsB) / kGsRows, c1 = min(nchunks, c0 + kChunksPerBlk);
-					if (blk >= kGsAhead && lane < c1 - c0) while (ld_flag(applied + c0 + lane) < blk + 1 - kGsAhead) __nanosleep(100);
+					if (blk >= kGsAhead && lane < c1 - c0) {
+						int spins = 0;
+						while (ld_flag(applied + c0 + lane) < blk + 1 - kGsAhead && !ld_flag(&ctl->abort)) {
+							__nanosleep(100);
+							if (++spins > kGsWaitLimit) st_flag(&ctl->abort, 1);
+						}
+					}
 					__syncwarp();
 					__threadfence();
 					load_acc(blk + 1, lane); load_acc(blk + 1, lane + 32);
@@ -383,98 +487,21 @@ k_gs_pipeline(const double4 *__restrict__ gpq, const int *__restrict__ gmeta, co
 			// r_pendp is free again by the time this helper writes it
 		}
 		cluster.sync();
+	} else {
+		// single-launch fallback (MPMC_GS_FUSED=1: for tools that serialise kernel launches, e.g. ncu): the CTAs beyond the
+		// cluster do the updaters' work, one CTA per SM
+		gs_updater_body<ORTHO, EXPD>(s_raw, cta - kGsCluster, gridDim.x - kGsCluster, gpq, gmeta, order, np, c, p, acc, dmu, ctl, prof);
 	}
 }
 
-// The updaters: their own kernel (2 CTAs per SM on every SM the solver's cluster leaves free — the solver needs a whole SM's shared
+// The updaters as their own kernel (2 CTAs per SM on every SM the solver's cluster leaves free — the solver needs a whole SM's shared
 // memory, the updaters need latency hiding), launched right after the solver kernel on a second stream.
 template <bool ORTHO, bool EXPD>
 __global__ void __launch_bounds__(kGsThreads, 2)
 k_gs_updaters(const double4 *__restrict__ gpq, const int *__restrict__ gmeta, const int *__restrict__ order, int np, CellDev c, PolarDev p,
               double *acc, const double *dmu, GsCtl *ctl, long long *prof) {
 	extern __shared__ __align__(16) double s_raw[];
-	int *applied = (int *)(ctl + 1);
-	const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-	const int cta = blockIdx.x, U = gridDim.x;
-	const int nblk = (np + kGsB - 1) / kGsB, nchunks = (np + kGsRows - 1) / kGsRows;
-	constexpr int kChunksPerBlk = kGsB / kGsRows;
-	{
-		// warps work independently: global warp gwid owns the chunks ch = gwid, gwid + GW, ...  (8 consecutive rows of the
-		// sweep order each) and keeps its own copy of the panel in shared memory
-		double4 *w_col = (double4 *)s_raw + warp * 2 * kGsB;
-		double4 *w_dm = w_col + kGsB;
-		// (warp-major numbering: when there are more chunks than warps, the second chunks go one to each CTA instead of eight to a
-		// few CTAs — an SM with twice the work falls behind by a few thousand cycles per panel and stalls the solver at the end)
-		const int GW = U * kGsWarps, gwid = warp * U + cta;
-		const int r = lane & 7, cl = lane >> 3;             // row of the chunk, column lane
-		for (int blk = 0; blk < nblk; blk++) {
-			const int base = blk * kGsB, cnt = min(kGsB, np - base);
-			// the panel's own rows and the rows of the next kGsAhead blocks belong to the cluster
-			const int skip0 = blk * kChunksPerBlk, skip1 = min(blk + 1 + kGsAhead, nblk) * kChunksPerBlk;
-			const int first = gwid;
-			bool any = false;
-			for (int ch = first; ch < nchunks; ch += GW) any = any || !(ch >= skip0 && ch < skip1);
-			if (!any) continue;
-			__syncwarp();
-			for (int cc = lane; cc < cnt; cc += 32) {
-				const double4 g = gpq[base + cc];
-				w_col[cc] = make_double4(g.x, g.y, g.z, __longlong_as_double((long long)gmeta[base + cc]));   // alpha travels in w_dm.w
-			}
-			const bool pw = prof && cta == 0 && warp == 0 && lane == 0;
-			if (pw) prof[(nblk + blk) * 8 + 0] = clock64();
-			if (lane == 0) while (ld_flag(&ctl->solved) <= blk) __nanosleep(32);
-			__syncwarp();
-			__threadfence();
-			if (pw) prof[(nblk + blk) * 8 + 1] = clock64();
-			for (int cc = lane; cc < cnt; cc += 32)
-				w_dm[cc] = make_double4(__ldcg(dmu + 3 * (base + cc)), __ldcg(dmu + 3 * (base + cc) + 1), __ldcg(dmu + 3 * (base + cc) + 2), EXPD ? 0.0 : gpq[base + cc].w);
-			__syncwarp();
-			// all my chunks of this panel first, then their running contractions (each row has exactly one writer, so the atomic adds
-			// are ordered and the result deterministic), ONE fence, then the flags: a warp that owns two chunks must not pay two fences
-			for (int ch0 = first; ch0 < nchunks; ch0 += 2 * GW) {
-				double sx[2], sy[2], sz[2];
-				int chs[2];
-#pragma unroll
-				for (int w = 0; w < 2; w++) {
-					const int ch = ch0 + w * GW;
-					chs[w] = (ch < nchunks && !(ch >= skip0 && ch < skip1)) ? ch : -1;
-					sx[w] = sy[w] = sz[w] = 0.0;
-					if (chs[w] < 0) continue;
-					const int pos = ch * kGsRows + r;
-					const bool on = pos < np;
-					const double4 pr = on ? gpq[pos] : make_double4(0, 0, 0, 0);
-					const int mr = on ? gmeta[pos] : 0;
-					double ax = 0, ay = 0, az = 0;
-					if (on) {
-#pragma unroll 4
-						for (int cc = cl; cc < cnt; cc += 4) {
-							double4 pc = w_col[cc];
-							const double4 dm = w_dm[cc];
-							const int mc = __double2loint(pc.w);
-							if (!EXPD) pc.w = dm.w;                           // alpha of the column (linear damping)
-							gs_contract<ORTHO, EXPD>(c, p, pr, mr, pc, mc, dm, ax, ay, az);
-						}
-					}
-					ax += __shfl_xor_sync(0xffffffffu, ax, 8); ay += __shfl_xor_sync(0xffffffffu, ay, 8); az += __shfl_xor_sync(0xffffffffu, az, 8);
-					ax += __shfl_xor_sync(0xffffffffu, ax, 16); ay += __shfl_xor_sync(0xffffffffu, ay, 16); az += __shfl_xor_sync(0xffffffffu, az, 16);
-					sx[w] = ax; sy[w] = ay; sz[w] = az;
-				}
-				if (pw) prof[(nblk + blk) * 8 + 2] = clock64();
-#pragma unroll
-				for (int w = 0; w < 2; w++) {
-					const int pos = chs[w] * kGsRows + r;
-					if (chs[w] >= 0 && cl == 0 && pos < np) {
-						const int i = order[pos];
-						atomicAdd(acc + 3 * i, sx[w]); atomicAdd(acc + 3 * i + 1, sy[w]); atomicAdd(acc + 3 * i + 2, sz[w]);
-					}
-				}
-				__threadfence();
-				__syncwarp();
-				if (lane < 2 && chs[lane] >= 0) st_flag(applied + chs[lane], blk + 1);
-				if (pw) prof[(nblk + blk) * 8 + 3] = clock64();
-			}
-		}
-	}
+	gs_updater_body<ORTHO, EXPD>(s_raw, blockIdx.x, gridDim.x, gpq, gmeta, order, np, c, p, acc, dmu, ctl, prof);
 }
 
 // Palmo after Gauss-Seidel: efic_i = -efi_i - acc_i for the polarizable sites (acc is the final running contraction)
