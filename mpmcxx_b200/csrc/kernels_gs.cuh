@@ -208,7 +208,7 @@ __device__ __forceinline__ void gs_updater_body(double *s_raw, int cta, int U, c
 }
 
 // what the cluster shares: the solver's shared-memory words the helpers read (progress, dmu) and write (partial pushes, done)
-struct GsShared { int prog; int done; int loaded; int pad; };
+struct GsShared { int prog; int loaded; int folded; int pad; int done[4]; };
 
 template <bool ORTHO, bool EXPD>
 __global__ void __cluster_dims__(kGsCluster, 1, 1) __launch_bounds__(kGsThreads, 1)
@@ -235,7 +235,8 @@ k_gs_pipeline(const double4 *__restrict__ gpq, const int *__restrict__ gmeta, co
 	if (cta == 0) {
 		// ------------------------------------------------ solver ------------------------------------------------
 		volatile int *s_prog = &s_sh->prog;                        // blk * kGsB + columns of the walk that are final
-		volatile int *s_done = &s_sh->done;                        // helpers that have delivered, summed over panels
+		volatile int *s_done = s_sh->done;                         // per helper: panels delivered
+		volatile int *s_folded = &s_sh->folded;                    // panels whose deliveries have been folded (their buffers are free again)
 		volatile int *s_loaded = &s_sh->loaded;                    // blocks whose site columns the walker has taken into registers
 		auto load_cols = [&](int blk, int m) {                     // site id and site columns of row m (all but the running contraction)
 			const int pos = blk * kGsB + m;
@@ -261,7 +262,7 @@ k_gs_pipeline(const double4 *__restrict__ gpq, const int *__restrict__ gmeta, co
 			__pipeline_commit();
 		}
 		if (tid < kGsB) { load_cols(0, tid); load_acc(0, tid); }
-		if (tid == 0) { *s_prog = 0; *s_done = 0; *s_loaded = 0; }
+		if (tid == 0) { *s_prog = 0; *s_loaded = 0; *s_folded = 0; for (int h = 0; h < 4; h++) s_done[h] = 0; }
 		cluster.sync();                                            // the helpers may look at prog / done from here on
 		for (int blk = 0; blk < nblk; blk++) {
 			const int base = blk * kGsB, cnt = min(kGsB, np - base);
@@ -269,7 +270,7 @@ k_gs_pipeline(const double4 *__restrict__ gpq, const int *__restrict__ gmeta, co
 			// (A) fold the helpers' pushes of the previous panel into the pending sums (fixed order), then the running contraction
 			//     of this block's rows = what the updaters left (fetched during the previous walk) + the cluster's own pushes
 			if (blk > 0) {
-				if (tid == 0) while (*s_done < kGsHelpers * blk) { }
+				if (tid < kGsHelpers) while (s_done[tid] < blk) { }         // every helper has delivered panel blk-1
 				__syncthreads();
 				asm volatile("fence.acq_rel.cluster;" ::: "memory");
 				if (tid < kGsAhead * kGsB) {
@@ -283,6 +284,8 @@ k_gs_pipeline(const double4 *__restrict__ gpq, const int *__restrict__ gmeta, co
 			}
 			__pipeline_wait_prior(0);
 			__syncthreads();
+			if (tid == 0) *s_folded = blk;                                 // the helpers may overwrite their delivery buffers (a helper with
+			                                                               // no column in a short last block would otherwise run ahead)
 			if (tid < kGsB) for (int q = 0; q < 3; q++) s_site[(7 + q) * kGsB + tid] += s_pend[((blk % kGsSlots) * kGsB + tid) * 3 + q];
 			__syncthreads();
 			if (prof && tid == 0) prof[blk * 8 + 1] = clock64();
@@ -425,7 +428,8 @@ k_gs_pipeline(const double4 *__restrict__ gpq, const int *__restrict__ gmeta, co
 		int *h_meta = (int *)(h_rows + kGsSlots * kGsB);           // [kGsSlots][kGsB]
 		double *h_part = (double *)(h_meta + kGsSlots * kGsB);     // [4 column sub-slices][kGsAhead * kGsB][3]
 		const volatile int *r_prog = &cluster.map_shared_rank(s_sh, 0)->prog;
-		int *r_done = &cluster.map_shared_rank(s_sh, 0)->done;
+		int *r_done = cluster.map_shared_rank(s_sh, 0)->done + hj;
+		const volatile int *r_folded = &cluster.map_shared_rank(s_sh, 0)->folded;
 		const volatile double *r_dm = (const volatile double *)cluster.map_shared_rank(s_dm, 0);
 		double *r_pendp = cluster.map_shared_rank(s_pendp, 0) + hj * (kGsAhead * kGsB * 3);
 		auto load_rows = [&](int blk) {
@@ -473,6 +477,9 @@ k_gs_pipeline(const double4 *__restrict__ gpq, const int *__restrict__ gmeta, co
 				double *o = h_part + ((s4 * kGsAhead + j) * kGsB + r) * 3;
 				o[0] = ax[j]; o[1] = ay[j]; o[2] = az[j];
 			}
+			// my previous delivery must have been folded before its buffer is written again (true by construction whenever this
+			// helper had a column to wait for; not in a last block shorter than the number of helpers)
+			if (tid == 0) while (*r_folded < blk) __nanosleep(100);
 			__syncthreads();
 			// sub-slices summed in a fixed order, straight into the solver's shared memory
 			if (tid < kGsAhead * kGsB) {
@@ -482,7 +489,7 @@ k_gs_pipeline(const double4 *__restrict__ gpq, const int *__restrict__ gmeta, co
 			}
 			asm volatile("fence.acq_rel.cluster;" ::: "memory");
 			__syncthreads();
-			if (tid == 0) atomicAdd(r_done, 1);
+			if (tid == 0) *(volatile int *)r_done = blk + 1;
 			// the solver folds these sums before it starts the next walk, and only then publishes columns of the next panel:
 			// r_pendp is free again by the time this helper writes it
 		}

@@ -233,3 +233,23 @@ def test_cached_framework_state_equals_fresh_upload(solver):
         assert f.energy() == o
         f.close()
     e.close()
+
+
+@pytest.mark.parametrize("n_h2", [1, 4, 5, 6, 11, 20, 21, 22, 26, 42, 43, 44, 48])
+def test_gauss_seidel_block_boundaries_against_oracle(n_h2):
+    """The Gauss-Seidel pipeline works in blocks of 64 polarizable sites with a 3-block window owned by the solver's cluster and
+    special cases for the first rows of a block: sweep the number of polarizable sites (64 framework sites + 3 per H2) across the
+    block boundaries 64 / 80 / 128 / 192 / 208 and compare energy, iteration count and every dipole with the CPU oracle."""
+    from mpmcxx_b200 import workloads as W
+    from oracle import port
+    eng = _engine_mod()
+    s = W.h2_framework(ncell=4, n_h2=n_h2, solver=W.SOLVER_GS_RANKED_PALMO, ensemble="nvt", seed=100 + n_h2)
+    e = eng.Engine(s)
+    o = e.energy()
+    p = port.energy(s, want_sites=True)
+    assert _rel(o["polarization_energy"], p["polar"]) < RTOL, (n_h2, o["polarization_energy"], p["polar"])
+    assert o["polarization_iterations"] == int(p["iterations"])
+    d = e.dipoles()
+    assert np.abs(d["mu"] - p["mu"]).max() / np.abs(p["mu"]).max() < 1e-9
+    assert np.array_equal(d["rank_metric"], p["rank_metric"])
+    e.close()
