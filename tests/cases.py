@@ -40,6 +40,11 @@ CLASSIC = {
     "tri_nopbc_field": lambda: _with(W.triclinic_mix(), polar_ewald="off"),
     "tri_no_polar": lambda: _with(_without(W.triclinic_mix(), "polar_max_iter"), polarization="off"),
     "tri_alpha_set": lambda: _with(W.triclinic_mix(), ewald_alpha="0.31", polar_ewald_alpha="0.27", ewald_kmax="5"),
+    # the other two Thole damping forms of thole_amatrix (src/System.Energy.cpp:2714-2731): linear and none
+    "tri_linear_jacobi10": lambda: _with(W.triclinic_mix(), polar_damp_type="linear", polar_damp="1.662"),
+    "tri_linear_gs_ranked_palmo": lambda: _with(W.triclinic_mix(solver=W.SOLVER_GS_RANKED_PALMO), polar_damp_type="linear", polar_damp="1.662"),
+    "tri_damp_off_gs6": lambda: _with(W.triclinic_mix(solver={"polar_gs": "on", "polar_max_iter": "6"}), polar_damp_type="off"),
+    "h2fw_6_linear_gs_ranked": lambda: _with(W.h2_framework(ncell=6, n_h2=20, solver=W.SOLVER_GS_RANKED_PALMO, ensemble="nvt"), polar_damp_type="linear", polar_damp="1.662"),
     # scaled-down config 4: frozen framework + randomly oriented five-site H2
     "h2fw_6_gs_ranked_palmo": lambda: W.h2_framework(ncell=6, n_h2=20, solver=W.SOLVER_GS_RANKED_PALMO, ensemble="nvt"),
     "h2fw_6_jacobi10": lambda: W.h2_framework(ncell=6, n_h2=20, solver=W.SOLVER_JACOBI10, ensemble="nvt"),

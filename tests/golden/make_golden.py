@@ -24,8 +24,10 @@ def pack_system(s):
                 moltype=np.array(s.moltype))
 
 
-def main():
+def main(only=None):
     for name, build in cases.CLASSIC.items():
+        if only and name not in only:
+            continue
         s = build()
         r = ref.RefSystem(s, ensemble="nvt")
         t = r.terms()
@@ -47,6 +49,8 @@ def main():
         np.savez_compressed(os.path.join(HERE, name + ".npz"), **out)
         print("%-22s n=%4d  E=%.15g  pol=%.15g  it=%d" % (name, s.n, e0["energy"], t["polar"], t["iterations"]))
     for name, build in cases.PI.items():
+        if only and name not in only:
+            continue
         tmpl, beads = build()
         P = beads.shape[0]
         r = ref.RefSystem(tmpl, P=P)
@@ -87,6 +91,9 @@ if __name__ == "__main__":
         sys.exit(0)
     if len(sys.argv) > 1 and sys.argv[1] == "traj":
         trajectories()
+        sys.exit(0)
+    if len(sys.argv) > 2 and sys.argv[1] == "only":          # regenerate just the named energy cases
+        main(set(sys.argv[2:]))
         sys.exit(0)
     main()
     trajectories()
