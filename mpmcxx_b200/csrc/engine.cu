@@ -145,7 +145,8 @@ struct mpmc_engine {
 	PairParams pp;
 	RadialTable erf_tab;
 	DevBuf<PairSeg> d_segs;
-	DevBuf<int> d_pmeta, d_item_seg, d_perm;
+	DevBuf<int> d_pmeta, d_item_seg, d_item_col, d_item_ctr, d_perm;
+	int pair_ctr_start = 0;
 	DevBuf<double2> d_slj;
 	DevBuf<double4> d_spq, d_stage;
 	bool perm_identity = true;
@@ -478,21 +479,46 @@ int prepare_pair_sweep(mpmc_engine *e) {
 		}
 	}
 	pp.ncols = col; pp.nseg = (int)e->segs.size();
+	pp.h_adm = (unsigned)RadialTable::hi_word(pp.t2_adm); pp.h_safe = (unsigned)RadialTable::hi_word(pp.t2_safe);
+	pp.h_tab_lo = (unsigned)RadialTable::hi_word(pp.u_tab_lo);
+	// items: equal-cost ranges of the flattened columns; ~1 per resident warp for small systems (a second item would cost more in
+	// per-item overhead than it balances), up to 6 per warp for large ones, later ones handed out through a counter
 	const int ctas = e->num_sms * pair_ctas_per_sm(es);
 	const int warps = ctas * kPwWarps;
-	int K = std::max(1, warps / e->B);
-	K = std::min(K, std::max(1, (col + 15) / 16));        // at least 16 columns per item
+	const long total_cols = (long)col * e->B;
+	const int per_warp = (int)std::max(1L, std::min(6L, total_cols / ((long)warps * 96)));
+	int K = std::max(1, (warps * per_warp + e->B / 2) / e->B);
+	K = std::min(K, std::max(1, (col + 15) / 16));        // at least ~16 columns per item
 	pp.items_per_bead = K;
-	pp.cols_per_item = std::max(1, (col + K - 1) / K);
 	e->pair_grid = std::max(1, std::min(ctas, (e->B * K + kPwWarps - 1) / kPwWarps));
-	std::vector<int> item_seg(K, 0);
+	std::vector<int> item_seg(K, 0), item_col(K + 1, 0);
+	{
+		double total_w = 0;
+		for (const PairSeg &sg : e->segs) total_w += (double)(sg.j_end - sg.j_begin) * pair_kind_weight(sg.kind);
+		size_t sgi = 0;
+		double before = 0;                                  // weight of the segments before sgi
+		for (int k = 1; k < K; k++) {
+			const double target = total_w * k / K;
+			while (sgi + 1 < e->segs.size() && before + (double)(e->segs[sgi].j_end - e->segs[sgi].j_begin) * pair_kind_weight(e->segs[sgi].kind) <= target) {
+				before += (double)(e->segs[sgi].j_end - e->segs[sgi].j_begin) * pair_kind_weight(e->segs[sgi].kind);
+				sgi++;
+			}
+			const PairSeg &sg = e->segs[sgi];
+			const int within = (int)std::min<double>(sg.j_end - sg.j_begin, std::max(0.0, (target - before) / pair_kind_weight(sg.kind)));
+			item_col[k] = std::max(item_col[k - 1], sg.col0 + within);
+		}
+		item_col[K] = col;
+		if (e->segs.empty()) std::fill(item_col.begin(), item_col.end(), 0);
+	}
 	for (int k = 0, sgi = 0; k < K; k++) {
-		const int c0 = k * pp.cols_per_item;
-		while (sgi + 1 < pp.nseg && e->segs[sgi + 1].col0 <= c0) sgi++;
+		while (sgi + 1 < pp.nseg && e->segs[sgi + 1].col0 <= item_col[k]) sgi++;
 		item_seg[k] = sgi;
 	}
-	if ((rc2 = e->d_item_seg.ensure(K))) return rc2;
+	if ((rc2 = e->d_item_seg.ensure(K)) || (rc2 = e->d_item_col.ensure(K + 1)) || (rc2 = e->d_item_ctr.ensure(1))) return rc2;
 	CK(cudaMemcpyAsync(e->d_item_seg.p, item_seg.data(), K * sizeof(int), cudaMemcpyHostToDevice, e->stream));
+	CK(cudaMemcpyAsync(e->d_item_col.p, item_col.data(), (K + 1) * sizeof(int), cudaMemcpyHostToDevice, e->stream));
+	e->pair_ctr_start = e->pair_grid * kPwWarps;
+	CK(cudaMemcpyAsync(e->d_item_ctr.p, &e->pair_ctr_start, sizeof(int), cudaMemcpyHostToDevice, e->stream));
 	if ((rc2 = e->d_pmeta.ensure(std::max(n, 1))) || (rc2 = e->d_segs.ensure(std::max<size_t>(e->segs.size(), 1))) || (rc2 = e->d_perm.ensure(std::max(n, 1))) ||
 	    (rc2 = e->d_slj.ensure(std::max(n, 1))) || (rc2 = e->d_spq.ensure((size_t)e->B * e->cap))) return rc2;
 	CK(cudaMemcpyAsync(e->d_pmeta.p, pm.data(), n * sizeof(int), cudaMemcpyHostToDevice, e->stream));
@@ -949,11 +975,11 @@ static int enqueue_energy(mpmc_engine *e) {
 			LAUNCHED(e);
 			spq = e->d_spq.p;
 		}
-		if (es) k_pair_sweep<ORTHO, true><<<e->pair_grid, kPwThreads, smem, e->stream>>>(spq, e->d_slj.p, e->d_pmeta.p, e->cap, B, e->d_segs.p, e->d_item_seg.p, e->pp, e->cell, e->d_erf_tab.p, e->d_partials.p);
-		else k_pair_sweep<ORTHO, false><<<e->pair_grid, kPwThreads, smem, e->stream>>>(spq, e->d_slj.p, e->d_pmeta.p, e->cap, B, e->d_segs.p, e->d_item_seg.p, e->pp, e->cell, nullptr, e->d_partials.p);
+		if (es) k_pair_sweep<ORTHO, true><<<e->pair_grid, kPwThreads, smem, e->stream>>>(spq, e->d_slj.p, e->d_pmeta.p, e->cap, B, e->d_segs.p, e->d_item_seg.p, e->d_item_col.p, e->pp, e->cell, e->d_erf_tab.p, e->d_partials.p, e->d_item_ctr.p);
+		else k_pair_sweep<ORTHO, false><<<e->pair_grid, kPwThreads, smem, e->stream>>>(spq, e->d_slj.p, e->d_pmeta.p, e->cap, B, e->d_segs.p, e->d_item_seg.p, e->d_item_col.p, e->pp, e->cell, nullptr, e->d_partials.p, e->d_item_ctr.p);
 		LAUNCHED(e);
 	}
-	k_reduce_partials<<<B, 256, 0, e->stream>>>(e->d_partials.p, nitems, e->d_result.p);
+	k_reduce_partials<<<B, 256, 0, e->stream>>>(e->d_partials.p, nitems, e->d_result.p, e->d_item_ctr.p, e->pair_ctr_start);
 	LAUNCHED(e);
 	if (es) {
 		const int nk = (int)e->kvec.size();
@@ -1069,7 +1095,7 @@ int mpmc_destroy(mpmc_engine *e) {
 	if (e->stream) cudaStreamSynchronize(e->stream);
 	e->d_posq.release(); e->d_lj.release(); e->d_alpha.release(); e->d_mass.release(); e->d_meta.release(); e->d_plist.release();
 	e->d_mobile_q.release(); e->d_frozen_q.release(); e->d_mol_start.release(); e->d_order.release(); e->d_flags.release();
-	e->d_segs.release(); e->d_item_seg.release(); e->d_pmeta.release(); e->d_perm.release(); e->d_slj.release(); e->d_spq.release(); e->d_stage.release(); e->d_erf_tab.release(); e->d_mol_mobile.release(); e->d_kvec.release(); e->d_partials.release();
+	e->d_segs.release(); e->d_item_seg.release(); e->d_item_col.release(); e->d_item_ctr.release(); e->d_pmeta.release(); e->d_perm.release(); e->d_slj.release(); e->d_spq.release(); e->d_stage.release(); e->d_erf_tab.release(); e->d_mol_mobile.release(); e->d_kvec.release(); e->d_partials.release();
 	e->d_sk_part.release(); e->d_S_mobile.release(); e->d_S_frozen.release(); e->d_S_all.release();
 	e->d_efs.release(); e->d_efi.release(); e->d_efic.release(); e->d_mu.release(); e->d_new_mu.release(); e->d_old_mu.release();
 	e->d_rrms.release(); e->d_rank.release(); e->d_acc.release(); e->d_dmu.release(); e->d_tri.release(); e->d_gsctl.release(); e->d_gmeta.release(); e->d_nplist.release(); e->d_gpq.release(); e->d_cparts.release(); e->d_field_tab.release(); e->d_fp_list.release(); e->d_mp_list.release(); e->d_recount.release(); e->d_r2min_ff.release(); e->d_t2.release(); e->d_t2_cached.release(); e->d_cnt_ff.release(); e->d_mobile_sites.release(); e->d_frozen_sites.release(); e->d_allq.release(); e->d_com.release(); e->d_mol_mass.release(); e->d_chain.release();

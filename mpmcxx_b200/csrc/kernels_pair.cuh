@@ -18,9 +18,10 @@ struct PairPartial { double rd, es_real, es_intra, n_in; };
 // result record: res[bead*kResStride + 0..3] = rd_pair, es_real, es_intra, n_in.
 constexpr int kResStride = 8;   // + 4 es_recip, 5 sum mu.E_s, 6 sum mu.dE_ind, 7 sum rrms
 __global__ void __launch_bounds__(256)
-k_reduce_partials(const PairPartial *__restrict__ partials, int nitems, double *__restrict__ res) {
+k_reduce_partials(const PairPartial *__restrict__ partials, int nitems, double *__restrict__ res, int *__restrict__ item_ctr, int ctr_start) {
 	__shared__ double s_red[4][256];
 	const int bead = blockIdx.x, tid = threadIdx.x;
+	if (bead == 0 && tid == 0) *item_ctr = ctr_start;      // the sweep's item counter, ready for the next launch
 	double a = 0, b = 0, c = 0, d = 0;
 	for (int t = tid; t < nitems; t += 256) {
 		const PairPartial p = partials[(size_t)bead * nitems + t];

@@ -1,16 +1,21 @@
 // kernels_pair2.cuh — the pair-energy sweep, second generation: lj() + coulombic_real() (reference src/System.Energy.cpp:897-1032,
 // 1466-1517) over every pair i<j that pairs() visits (src/System.cpp:967-991).
 //
-// What bounds this sweep on B200 is the FP64 pipe (64 lanes/SM: one warp instruction every 2 cycles per scheduler) and, right behind
-// it, the issue slots (tools/ubench/fp64_ubench.cu).  So the kernel is built to issue as few instructions per pair as the reference's
+// What bounds this sweep on B200 is the FP64 pipe (64 lanes/SM: one warp instruction every 2 cycles per scheduler, during which the
+// scheduler issues nothing else: cost of a pair ~ 2 x FP64 instructions + other instructions, tools/ubench/fp64_ubench.cu and the
+// instruction counts of the ncu source page).  So the kernel is built to issue as few instructions per pair as the reference's
 // semantics allow:
-//   * geometry with FMA (16 FP64 instructions per pair in an orthorhombic cell).  The reference's cutoff tests act on the last bit of
-//     rimg = sqrt(r^2) computed WITHOUT FMA; sqrt and the subtraction of 1e-12 are monotone, so each test is equivalent to
-//     r2_exact <= T for a double T the host finds by bisection (pair_thresholds()).  The FMA r^2 differs from the exact one by < 1e-13
-//     relative, so only pairs within 1e-9 of a threshold (never, except on lattices) are recomputed the reference's way and tested
-//     exactly; every other decision is provably the reference's.
-//   * the ~48 % of pairs outside the cutoff sphere cost nothing more: the lanes of a warp push the pairs that do interact into a
-//     per-warp queue (ballot + popc, fixed order) and the expensive part runs on full warps, 32 queued pairs at a time.
+//   * geometry.  The pair energies need r^2 only.  In an orthorhombic cell the sites are folded into the cell while they are staged
+//     (once per site and chunk, not per pair; into the cell centred on the origin), after which |d_img| = L/2 - | |dx| - L/2 | per axis: 3 adds per axis with the absolute
+//     values as operand modifiers, 12 FP64 instructions per pair with the sum of squares (the rint form needs 15).  A triclinic cell
+//     keeps the general FMA form.
+//   * the reference's cutoff tests act on the last bit of rimg = sqrt(r^2) computed WITHOUT FMA; sqrt and the subtraction of 1e-12 are
+//     monotone, so each test is equivalent to r2_exact <= T for a double T the host finds by bisection (prepare_pair_sweep()).  The
+//     fast r^2 differs from the exact one by < 1e-13 relative, and the tests are done on the HIGH WORD of r^2 with integer compares
+//     (2^-20 relative granularity, no FP64 instruction): below the word of T (1 - 1e-9) the pair is inside both cutoffs, above the
+//     word of T (1 + 1e-9) it is outside, and the few pairs in between (never, except on lattices) are recomputed from the unfolded
+//     coordinates the reference's way and tested exactly; every other decision is provably the reference's.
+//   * padding lanes and columns carry NaN coordinates: their r^2 is NaN, whose high word is above every threshold — no extra test.
 //   * erfc(alpha r)/r comes from a table in r^2 (radial_table.h): 1 add + 7 FMA, no sqrt, no exp; LJ needs only 1/r^2.
 //   * the pair sum does not depend on the order of the sites, so the sweep runs over a copy of the site table sorted by CLASS
 //     (frozen?, charged?, LJ-active?).  A block of pairs between two classes needs LJ only, Coulomb only, both or nothing at all
@@ -18,8 +23,10 @@
 //     per kind, so a five-site H2 system (one LJ+charge site, two charge-only, two LJ-only) does half the arithmetic it would
 //     with every pair going through both formulas.
 //   * work is dealt to warps, not CTAs: the (i-group of 32 sites) x (j site) columns of every class block are flattened and cut
-//     into equal ranges, so 148 SMs x 16 warps stay busy to the end whatever N is.
-// Sums are accumulated per item in a fixed order and reduced by k_reduce_partials: results are bit-reproducible.
+//     into items of equal COST (columns weighted by what their kind issues); a warp takes its first item by its index and the
+//     following ones from a counter, so 148 SMs x 16 warps stay busy to the end whatever N and the mix of kinds are.
+// Sums are accumulated per item in a fixed order and reduced by k_reduce_partials: results are bit-reproducible whichever warp
+// ends up with an item.
 #pragma once
 #include "device_math.cuh"
 #include "kernels_pair.cuh"
@@ -44,11 +51,15 @@ struct PairParams {
 	double t2_adm;      // admission threshold on the FMA r^2: t2_lj (1 + 1e-9)
 	double t2_safe;     // below this both tests hold without looking closer: t2_es (1 - 1e-9)
 	double u_tab_lo;    // the table covers [u_tab_lo, > t2_adm)
+	unsigned h_adm, h_safe, h_tab_lo;   // high words of t2_adm, t2_safe, u_tab_lo (u_tab_lo sits on a word boundary)
 	int tab_base, tab_rows;
 	int ncols;          // columns per bead system
-	int items_per_bead, cols_per_item;
+	int items_per_bead; // items of one bead system; item k covers columns [item_col[k], item_col[k+1])
 	int nseg;
 };
+
+// relative cost of one column (32 pairs) of each kind, ~ 2 x FP64 + other instructions of its inner loop: equal-cost items
+inline int pair_kind_weight(int kind) { return kind == kPairLJ ? 60 : kind == kPairES ? 70 : 95; }
 
 // row lookup of a radial table held in shared memory: value of function 0 of a 1-function table at u
 // (the row index is clamped to the table: callers discard the value when u lies outside [u_lo, u_hi))
@@ -87,6 +98,15 @@ __device__ __forceinline__ double r2_fast(const CellDev &c, double dx, double dy
 
 struct PairAcc { double rd, re, in; int cnt; };
 
+// acc += v (and cnt += 1) under a predicate, as predicated instructions: the compiler's own if-conversion turns `if (p) acc += v`
+// into two selects and an unconditional add, three issue slots more per pair
+__device__ __forceinline__ void add_if(double &acc, int &cnt, double v, bool p) {
+	asm("{\n\t.reg .pred q;\n\tsetp.ne.s32 q, %3, 0;\n\t@q add.f64 %0, %0, %2;\n\t@q add.s32 %1, %1, 1;\n\t}" : "+d"(acc), "+r"(cnt) : "d"(v), "r"((int)p));
+}
+__device__ __forceinline__ void add_if(double &acc, double v, bool p) {
+	asm("{\n\t.reg .pred q;\n\tsetp.ne.s32 q, %2, 0;\n\t@q add.f64 %0, %0, %1;\n\t}" : "+d"(acc) : "d"(v), "r"((int)p));
+}
+
 #ifndef MPMC_PW_CTAS
 #define MPMC_PW_CTAS 2
 #endif
@@ -120,79 +140,118 @@ __global__ void k_scatter_sites(const double4 *__restrict__ stage, double4 *__re
 	posq[(size_t)(bead_lo + b) * stride + first + k] = stage[t];
 }
 
-// one staged chunk (cnt <= 32 columns in shared memory) against the warp's 32 i sites, for a block of pairs of one kind
-template <bool ORTHO, int KIND>
-__device__ __forceinline__ void pair_chunk(const CellDev &c, const PairParams &pp, const double *s_tab, const double4 *s_pq, const double2 *s_lj,
-                                           const int *s_pm, int cnt, int dlim, const double4 pi, const double2 li, int mi, PairAcc &a) {
+// folds a site into the cell centred on the origin along each axis of an orthorhombic cell (coordinates end up in [-L/2, L/2] up to
+// rounding; a site already there is not touched, so a cluster around the origin of a huge box keeps its full precision); the fold
+// moves a site by whole lattice vectors, which changes no image distance by more than the rounding of the coordinate itself
+template <bool ORTHO>
+__device__ __forceinline__ double4 fold_site(const CellDev &c, double4 p) {
+	if (ORTHO) {
+		p.x = fma(-c.b[0][0], rint(p.x * c.rb[0][0]), p.x);
+		p.y = fma(-c.b[1][1], rint(p.y * c.rb[1][1]), p.y);
+		p.z = fma(-c.b[2][2], rint(p.z * c.rb[2][2]), p.z);
+	}
+	return p;
+}
+
+// minimum-image r^2 of two FOLDED sites: per axis |d_img| = h - | |d| - h |, h = L/2 (orthorhombic); general form otherwise
+template <bool ORTHO>
+__device__ __forceinline__ double r2_pair(const CellDev &c, double hx, double hy, double hz, double dx, double dy, double dz) {
+	if (ORTHO) {
+		const double ux = hx - fabs(fabs(dx) - hx), uy = hy - fabs(fabs(dy) - hy), uz = hz - fabs(fabs(dz) - hz);
+		return fma(uz, uz, fma(uy, uy, ux * ux));
+	}
+	return r2_fast<false>(c, dx, dy, dz);
+}
+
+__device__ __forceinline__ double4 nan_site() { const double q = __longlong_as_double(0x7ff8000000000000LL); return make_double4(q, q, q, 0.0); }
+
+// one staged chunk (cnt <= 32 columns in shared memory, folded) against the warp's 32 i sites, for a block of pairs of one kind.
+// a.rd and a.re collect sum_j sqrt(eps_j) (..) and sum_j q_j (..): the factor of site i is applied by the caller when the segment ends.
+// raw = the bead's unfolded sorted table, i / jc = sorted index of the lane's row / of the chunk's first column (rare exact paths).
+template <bool ORTHO, int KIND, bool DIAG>
+__device__ __forceinline__ void pair_chunk(const CellDev &c, const PairParams &pp, double hx, double hy, double hz, const double *s_tab, const double4 *s_pq,
+                                           const double2 *s_lj, const int *s_pm, int cnt, int dlim, const double4 pi, const double2 li, int mi,
+                                           const double4 *__restrict__ raw, int i, int jc, PairAcc &a) {
 	constexpr bool LJ = (KIND & kPairLJ) != 0, ES = (KIND & kPairES) != 0;
-	const double t2_adm = pp.t2_adm, t2_safe = pp.t2_safe;
+	const unsigned h_adm = pp.h_adm, h_safe = pp.h_safe;
 	for (int jj = 0; jj < cnt; jj += kPwCols) {
 		double r2[kPwCols], elj[kPwCols], ees[kPwCols];
-		bool in[kPwCols], excl[kPwCols], band[kPwCols];
+		bool in[kPwCols], excl[kPwCols], band[kPwCols], nearu[kPwCols];
+		const int dl = DIAG ? dlim - jj : -1;                                // diagonal chunk: column u counts for this lane when dl < u (i < j)
 #pragma unroll
 		for (int u = 0; u < kPwCols; u++) {
 			const double4 pj = s_pq[jj + u];
 			const int mj = s_pm[jj + u];
-			r2[u] = r2_fast<ORTHO>(c, pi.x - pj.x, pi.y - pj.y, pi.z - pj.z);
+			r2[u] = r2_pair<ORTHO>(c, hx, hy, hz, pi.x - pj.x, pi.y - pj.y, pi.z - pj.z);
+			const unsigned hw = (unsigned)__double2hiint(r2[u]);               // NaN (padding) compares above every threshold
 			excl[u] = mi == mj;                                              // same molecule (rd_excluded / es_excluded)
-			in[u] = !excl[u] && (mi | mj) >= 0 && dlim < jj + u && r2[u] <= t2_adm;   // present, i < j, inside the (1e-9 widened) cutoff sphere
-			band[u] = in[u] && r2[u] > t2_safe;
+			in[u] = !excl[u] && (!DIAG || dl < u) && hw <= h_adm;             // i < j, inside the (widened) cutoff sphere
+			band[u] = in[u] && hw >= h_safe;
 			if (LJ) {
 				// Lorentz-Berthelot LJ (:965-993); 4 eps_ij is applied after the sum
 				const double2 ljj = s_lj[jj + u];
 				const double sig = li.y + ljj.y;
 				const double s2 = sig * sig * rcp_full(r2[u]), s6 = s2 * s2 * s2;
-				elj[u] = (li.x * ljj.x) * fma(s6, s6, -s6);
+				elj[u] = ljj.x * fma(s6, s6, -s6);                                 // x sqrt(eps_i) once per segment, by the caller
 			}
 			if (ES) {                                                            // :1493-1497
-				ees[u] = 0.0;
-				if (in[u]) {
-					double f = tab_eval1(s_tab, pp.tab_base, pp.tab_rows, r2[u]);
-					if (r2[u] < pp.u_tab_lo) { const double r = sqrt(r2[u]); f = erfc(c.ewald_alpha * r) / r; }   // closer than the table starts
-					ees[u] = pi.w * pj.w * f;
-				}
+				ees[u] = pj.w * tab_eval1(s_tab, pp.tab_base, pp.tab_rows, r2[u]);   // x q_i once per segment, by the caller
+				nearu[u] = in[u] && hw < pp.h_tab_lo;                              // closer than the table starts
 			}
 		}
-		bool in_es[kPwCols];
-#pragma unroll
-		for (int u = 0; u < kPwCols; u++) in_es[u] = in[u];
-		if (band[0] || band[1] || band[2] || band[3]) {
-			// within 1e-9 of a cutoff: decide on the reference's own rounding of r^2 (System.cpp:1228-1255)
+		if (ES && (nearu[0] || nearu[1] || nearu[2] || nearu[3])) {
 #pragma unroll
 			for (int u = 0; u < kPwCols; u++)
-				if (band[u]) {
-					const double4 pj = s_pq[jj + u];
-					double ex, ey, ez;
-					min_image<ORTHO>(c, __dsub_rn(pi.x, pj.x), __dsub_rn(pi.y, pj.y), __dsub_rn(pi.z, pj.z), ex, ey, ez);
-					const double r2x = norm2_nofma(ex, ey, ez);
-					in[u] = r2x <= pp.t2_lj;
-					in_es[u] = r2x <= pp.t2_es;
-				}
+				if (nearu[u]) { const double r = sqrt(r2[u]); ees[u] = s_pq[jj + u].w * erfc(c.ewald_alpha * r) / r; }
 		}
+		if (!(band[0] || band[1] || band[2] || band[3])) {
 #pragma unroll
-		for (int u = 0; u < kPwCols; u++) {
-			if (LJ && in[u]) { a.rd += elj[u]; a.cnt++; }
-			if (ES && in_es[u]) a.re += ees[u];
+			for (int u = 0; u < kPwCols; u++) {
+				if (LJ) add_if(a.rd, a.cnt, elj[u], in[u]);
+				if (ES) add_if(a.re, ees[u], in[u]);
+			}
+		} else {
+			// next to a cutoff: decide on the reference's own rounding of r^2 (System.cpp:1228-1255), from the unfolded coordinates.
+			// The tests are redone from r^2 here (behind an opaque copy) so that the common path keeps no flag alive across the branch.
+			const double4 qi = raw[max(i, 0)];
+#pragma unroll
+			for (int u = 0; u < kPwCols; u++) {
+				unsigned hw = (unsigned)__double2hiint(r2[u]);
+				asm volatile("" : "+r"(hw));
+				bool in_lj = mi != s_pm[jj + u] && (!DIAG || dl < u) && hw <= h_adm, in_es = in_lj;
+				if (in_lj && hw >= h_safe) {
+					const double4 qj = raw[jc + jj + u];
+					double ex, ey, ez;
+					min_image<ORTHO>(c, __dsub_rn(qi.x, qj.x), __dsub_rn(qi.y, qj.y), __dsub_rn(qi.z, qj.z), ex, ey, ez);
+					const double r2x = norm2_nofma(ex, ey, ez);
+					in_lj = r2x <= pp.t2_lj;
+					in_es = r2x <= pp.t2_es;
+				}
+				if (LJ && in_lj) { a.rd += elj[u]; a.cnt++; }
+				if (ES && in_es) a.re += ees[u];
+			}
 		}
 		if (ES && (excl[0] || excl[1] || excl[2] || excl[3])) {
-			// es_self_intra = q_i q_j erf(alpha r)/r on the UN-imaged distance (:1503-1504)
+			// es_self_intra = q_i q_j erf(alpha r)/r on the UN-imaged distance (:1503-1504): unfolded coordinates
 #pragma unroll
 			for (int u = 0; u < kPwCols; u++)
-				if (excl[u] && mi >= 0 && dlim < jj + u) {
-					const double4 pj = s_pq[jj + u];
-					const double dx = pi.x - pj.x, dy = pi.y - pj.y, dz = pi.z - pj.z;
+				if (excl[u] && mi >= 0 && dl < u) {
+					const double4 qi = raw[i], qj = raw[jc + jj + u];
+					const double dx = qi.x - qj.x, dy = qi.y - qj.y, dz = qi.z - qj.z;
 					const double r = sqrt(fma(dz, dz, fma(dy, dy, dx * dx)));
-					a.in += pi.w * pj.w * erf(c.ewald_alpha * r) / r;
+					a.in += qi.w * qj.w * erf(c.ewald_alpha * r) / r;
 				}
 		}
 	}
 }
 
+// item_col[k], k <= items_per_bead: column boundaries of the items; ctr: the next item to hand out (gridDim.x * kPwWarps when the
+// kernel starts — k_reduce_partials puts it back)
 template <bool ORTHO, bool ES>
 __global__ void __launch_bounds__(kPwThreads, kPwCtas)
 k_pair_sweep(const double4 *__restrict__ spq, const double2 *__restrict__ lj, const int *__restrict__ pmeta, int stride, int nbeads,
-             const PairSeg *__restrict__ seg, const int *__restrict__ item_seg, const PairParams pp, const CellDev c,
-             const double *__restrict__ tab, PairPartial *__restrict__ partials) {
+             const PairSeg *__restrict__ seg, const int *__restrict__ item_seg, const int *__restrict__ item_col, const PairParams pp, const CellDev c,
+             const double *__restrict__ tab, PairPartial *__restrict__ partials, int *__restrict__ ctr) {
 	extern __shared__ __align__(16) double s_raw[];
 	double *s_tab = s_raw;
 	const int tab_len = ES ? pp.tab_rows * kErfRow : 0;
@@ -205,16 +264,17 @@ k_pair_sweep(const double4 *__restrict__ spq, const double2 *__restrict__ lj, co
 		for (int q = tid; q < tab_len; q += kPwThreads) s_tab[q] = tab[q];
 		__syncthreads();
 	}
-	const int W = gridDim.x * kPwWarps, gw = blockIdx.x * kPwWarps + warp;
+	const int gw = blockIdx.x * kPwWarps + warp;
 	const int items = nbeads * pp.items_per_bead;
-	if (lane < kPwCols) { s_pq[32 + lane] = make_double4(0, 0, 0, 0); s_lj[32 + lane] = make_double2(0, 0); s_pm[32 + lane] = kPmPad; }
+	const double hx = 0.5 * fabs(c.b[0][0]), hy = 0.5 * fabs(c.b[1][1]), hz = 0.5 * fabs(c.b[2][2]);
+	if (lane < kPwCols) { s_pq[32 + lane] = nan_site(); s_lj[32 + lane] = make_double2(0, 0); s_pm[32 + lane] = kPmPad; }
 	__syncwarp();
 
-	for (int it = gw; it < items; it += W) {
+	for (int it = gw; it < items;) {
 		const int bead = it / pp.items_per_bead, k = it - bead * pp.items_per_bead;
 		const double4 *pq = spq + (size_t)bead * stride;
-		int col = k * pp.cols_per_item;
-		const int col_end = min(col + pp.cols_per_item, pp.ncols);
+		int col = item_col[k];
+		const int col_end = item_col[k + 1];
 		PairAcc a = {0.0, 0.0, 0.0, 0};
 		if (col < col_end) {
 			int s = item_seg[k];                             // segment that holds `col`
@@ -222,37 +282,48 @@ k_pair_sweep(const double4 *__restrict__ spq, const double2 *__restrict__ lj, co
 				const PairSeg sg = seg[s];
 				const int j0 = sg.j_begin + (col - sg.col0);
 				const int j1 = min(sg.j_end, j0 + (col_end - col));
-				const int i = sg.i_begin + lane;
-				double4 pi = make_double4(0, 0, 0, 0);
+				int i = sg.i_begin + lane;
+				double4 pi = nan_site();
 				double2 li = make_double2(0, 0);
 				int mi = kPmPad;
-				if (i < sg.i_end) { pi = pq[i]; li = lj[i]; mi = pmeta[i]; }
+				if (i < sg.i_end) { pi = fold_site<ORTHO>(c, pq[i]); li = lj[i]; mi = pmeta[i]; } else i = -1;
+				PairAcc sa = {0.0, 0.0, 0.0, 0};                 // this segment's sums, without the factors of site i
 				// first chunk of the segment into registers; later chunks are fetched while the previous one is being swept
-				double4 npq = make_double4(0, 0, 0, 0); double2 nlj = make_double2(0, 0); int npm = kPmPad;
+				double4 npq = nan_site(); double2 nlj = make_double2(0, 0); int npm = kPmPad;
 				if (j0 + lane < j1) { npq = pq[j0 + lane]; nlj = lj[j0 + lane]; npm = pmeta[j0 + lane]; }
 				for (int jc = j0; jc < j1; jc += 32) {
 					const int cnt = min(32, j1 - jc);
 					__syncwarp();
-					s_pq[lane] = npq; s_lj[lane] = nlj; s_pm[lane] = npm;
+					s_pq[lane] = fold_site<ORTHO>(c, npq); s_lj[lane] = nlj; s_pm[lane] = npm;
 					__syncwarp();
 					{
 						const int jn = jc + 32 + lane;
-						npm = kPmPad; npq = make_double4(0, 0, 0, 0); nlj = make_double2(0, 0);
+						npm = kPmPad; npq = nan_site(); nlj = make_double2(0, 0);
 						if (jn < j1) { npq = pq[jn]; nlj = lj[jn]; npm = pmeta[jn]; }
 					}
-					const int dlim = (jc < sg.i_begin + 32) ? i - jc : -1;   // a chunk that overlaps the i-group (same class): keep i < j only
-					if (ES) {
-						if (sg.kind == (kPairLJ | kPairES)) pair_chunk<ORTHO, kPairLJ | kPairES>(c, pp, s_tab, s_pq, s_lj, s_pm, cnt, dlim, pi, li, mi, a);
-						else if (sg.kind == kPairES) pair_chunk<ORTHO, kPairES>(c, pp, s_tab, s_pq, s_lj, s_pm, cnt, dlim, pi, li, mi, a);
-						else pair_chunk<ORTHO, kPairLJ>(c, pp, s_tab, s_pq, s_lj, s_pm, cnt, dlim, pi, li, mi, a);
-					} else pair_chunk<ORTHO, kPairLJ>(c, pp, s_tab, s_pq, s_lj, s_pm, cnt, dlim, pi, li, mi, a);
+					const int dlim = (jc < sg.i_begin + 32) ? sg.i_begin + lane - jc : -1;   // a chunk that overlaps the i-group (same class): keep i < j only
+#define MPMC_PAIR_CHUNK(KIND, DIAG) pair_chunk<ORTHO, KIND, DIAG>(c, pp, hx, hy, hz, s_tab, s_pq, s_lj, s_pm, cnt, dlim, pi, li, mi, pq, i, jc, sa)
+					const int kind = ES ? sg.kind : kPairLJ;
+					if (jc < sg.i_begin + 32) {
+						if (kind == (kPairLJ | kPairES)) MPMC_PAIR_CHUNK(kPairLJ | kPairES, true);
+						else if (kind == kPairES) MPMC_PAIR_CHUNK(kPairES, true);
+						else MPMC_PAIR_CHUNK(kPairLJ, true);
+					} else {
+						if (kind == (kPairLJ | kPairES)) MPMC_PAIR_CHUNK(kPairLJ | kPairES, false);
+						else if (kind == kPairES) MPMC_PAIR_CHUNK(kPairES, false);
+						else MPMC_PAIR_CHUNK(kPairLJ, false);
+					}
+#undef MPMC_PAIR_CHUNK
 				}
+				a.rd = fma(li.x, sa.rd, a.rd); a.re = fma(pi.w, sa.re, a.re); a.in += sa.in; a.cnt += sa.cnt;
 				col += j1 - j0;
 				s++;
 			}
 		}
 		const double rd = warp_sum(a.rd), re = warp_sum(a.re), in = warp_sum(a.in), cn = warp_sum((double)a.cnt);
 		if (lane == 0) { PairPartial p; p.rd = 4.0 * rd; p.es_real = re; p.es_intra = in; p.n_in = cn; partials[it] = p; }
+		if (lane == 0) it = atomicAdd(ctr, 1);
+		it = __shfl_sync(0xffffffffu, it, 0);
 	}
 }
 

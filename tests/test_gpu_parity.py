@@ -206,8 +206,13 @@ def test_full_size_properties():
     t4.pos = s4.pos + np.array([80.0, 0.0, -80.0])
     e5 = eng.Engine(t4)
     b = e5.energy()
-    for k in ("rd_pair", "es_real", "es_self_intra", "es_reciprocal", "polarization_energy"):
+    for k in ("rd_pair", "polarization_energy"):
         assert _rel(b[k], a[k]) < 1e-10, (k, a[k], b[k])
+    # the Ewald sub-terms cancel (es_real of the mobile sites is ~1 K out of ~1e5 K of pair terms): judged against their common scale,
+    # SURVEY 8c; the translated coordinates themselves carry 1e-14 A of rounding
+    scale = sum(abs(a[k]) for k in ("es_real", "es_self_intra", "es_reciprocal"))
+    for k in ("es_real", "es_self_intra", "es_reciprocal"):
+        assert abs(b[k] - a[k]) < 1e-10 * scale, (k, a[k], b[k], scale)
     e4.close(); e5.close()
 
 
