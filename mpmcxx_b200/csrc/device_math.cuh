@@ -181,10 +181,15 @@ __device__ __forceinline__ void tensor_contract_exp(const CellDev &c, double lam
 	az = fma(-bd, dz, fma(a, mz, az));
 }
 
-// copy a table into shared memory (all threads of the CTA; the caller synchronises)
+// copy a table into shared memory (all threads of the CTA; len even, both 16-byte aligned): asynchronous 16-byte copies, all in
+// flight at once.  The caller runs stage_table_wait() and then synchronises the CTA before the first look-up.
 __device__ __forceinline__ void stage_table(double *dst, const double *__restrict__ src, int len) {
-	for (int q = threadIdx.x; q < len; q += blockDim.x) dst[q] = src[q];
+	const unsigned s0 = (unsigned)__cvta_generic_to_shared(dst);
+	for (int q = threadIdx.x; q < len / 2; q += blockDim.x)
+		asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" :: "r"(s0 + 16u * q), "l"(src + 2 * q) : "memory");
+	asm volatile("cp.async.commit_group;" ::: "memory");
 }
+__device__ __forceinline__ void stage_table_wait() { asm volatile("cp.async.wait_all;" ::: "memory"); }
 
 // deterministic warp reductions (xor tree: every lane ends with the same value)
 __device__ __forceinline__ double warp_sum(double v) {

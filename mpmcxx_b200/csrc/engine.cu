@@ -167,7 +167,7 @@ struct mpmc_engine {
 	bool rank_ff_dirty = true;
 	// Gauss-Seidel pipeline: the updater kernel runs beside the solver cluster on a second stream
 	cudaStream_t stream2 = nullptr;
-	cudaEvent_t ev_upd = nullptr;
+	cudaEvent_t ev_upd = nullptr, ev_fork = nullptr, ev_sk = nullptr;
 	int *h_started = nullptr, *d_started = nullptr;   // mapped pinned word the solver kernel stamps when it is running
 	int gs_token = 0, gs_upd_grid = 0, gs_fused_grid = 0;
 	int *h_gs_abort = nullptr;      // pinned copy of GsCtl::abort after the last sweep of an energy()
@@ -481,12 +481,14 @@ int prepare_pair_sweep(mpmc_engine *e) {
 	pp.ncols = col; pp.nseg = (int)e->segs.size();
 	pp.h_adm = (unsigned)RadialTable::hi_word(pp.t2_adm); pp.h_safe = (unsigned)RadialTable::hi_word(pp.t2_safe);
 	pp.h_tab_lo = (unsigned)RadialTable::hi_word(pp.u_tab_lo);
-	// items: equal-cost ranges of the flattened columns; ~1 per resident warp for small systems (a second item would cost more in
-	// per-item overhead than it balances), up to 6 per warp for large ones, later ones handed out through a counter
+	// items: equal-cost ranges of the flattened columns.  One per resident warp for small systems (a second item would cost more in
+	// per-item overhead than it balances: ~2 k cycles each); for larger ones items of 64 columns or more, up to 6 per warp, the later ones handed out through a
+	// counter: the sweep ends within a fraction of one item's duration of the ideal.  Boundaries inside a segment sit on whole
+	// 32-column chunks of that segment, so that only its last chunk is partial.
 	const int ctas = e->num_sms * pair_ctas_per_sm(es);
 	const int warps = ctas * kPwWarps;
 	const long total_cols = (long)col * e->B;
-	const int per_warp = (int)std::max(1L, std::min(6L, total_cols / ((long)warps * 96)));
+	const int per_warp = (int)std::max(1L, std::min(6L, total_cols / ((long)warps * 64)));
 	int K = std::max(1, (warps * per_warp + e->B / 2) / e->B);
 	K = std::min(K, std::max(1, (col + 15) / 16));        // at least ~16 columns per item
 	pp.items_per_bead = K;
@@ -497,6 +499,7 @@ int prepare_pair_sweep(mpmc_engine *e) {
 		for (const PairSeg &sg : e->segs) total_w += (double)(sg.j_end - sg.j_begin) * pair_kind_weight(sg.kind);
 		size_t sgi = 0;
 		double before = 0;                                  // weight of the segments before sgi
+		const bool align = per_warp > 1;
 		for (int k = 1; k < K; k++) {
 			const double target = total_w * k / K;
 			while (sgi + 1 < e->segs.size() && before + (double)(e->segs[sgi].j_end - e->segs[sgi].j_begin) * pair_kind_weight(e->segs[sgi].kind) <= target) {
@@ -504,7 +507,9 @@ int prepare_pair_sweep(mpmc_engine *e) {
 				sgi++;
 			}
 			const PairSeg &sg = e->segs[sgi];
-			const int within = (int)std::min<double>(sg.j_end - sg.j_begin, std::max(0.0, (target - before) / pair_kind_weight(sg.kind)));
+			const int len = sg.j_end - sg.j_begin;
+			int within = (int)std::min<double>(len, std::max(0.0, (target - before) / pair_kind_weight(sg.kind)));
+			if (align) { within = (within + 16) / 32 * 32; if (within > len) within = len; }
 			item_col[k] = std::max(item_col[k - 1], sg.col0 + within);
 		}
 		item_col[K] = col;
@@ -668,7 +673,8 @@ static int adopt_table(mpmc_engine *e) {
 // ---- energy ----------------------------------------------------------------------------------------------
 #define LAUNCHED(e) ((e)->launches++)
 
-static int run_structure(mpmc_engine *e, DevBuf<int> &list, int nlist, DevBuf<double2> &S, const double2 *addend) {
+static int run_structure(mpmc_engine *e, DevBuf<int> &list, int nlist, DevBuf<double2> &S, const double2 *addend, cudaStream_t stream = nullptr) {
+	if (!stream) stream = e->stream;
 	const int nk = (int)e->kvec.size(), kmax = e->cfg.ewald_kmax, B = e->B;
 	int rc;
 	if ((rc = S.ensure((size_t)B * nk))) return rc;
@@ -677,11 +683,11 @@ static int run_structure(mpmc_engine *e, DevBuf<int> &list, int nlist, DevBuf<do
 		if ((rc = e->d_sk_part.ensure((size_t)B * nchunks * nk))) return rc;
 		const size_t smem = sizeof(double2) * kSkSites * 3 * (kmax + 1);
 { Timed _t(e, MPMC_K_STRUCTURE);
-		k_structure_partial<<<dim3(nchunks, B), kSkThreads, smem, e->stream>>>(e->d_posq.p, e->cap, list.p, nlist, e->d_kvec.p, nk, kmax, e->cell,
+		k_structure_partial<<<dim3(nchunks, B), kSkThreads, smem, stream>>>(e->d_posq.p, e->cap, list.p, nlist, e->d_kvec.p, nk, kmax, e->cell,
 		                                                                        e->d_sk_part.p, nchunks);
 		LAUNCHED(e);
  }	}
-	k_structure_reduce<<<dim3((nk + 127) / 128, B), 128, 0, e->stream>>>(e->d_sk_part.p, nchunks, nk, S.p, addend);
+	k_structure_reduce<<<dim3((nk + 127) / 128, B), 128, 0, stream>>>(e->d_sk_part.p, nchunks, nk, S.p, addend);
 	LAUNCHED(e);
 	CK(cudaGetLastError());
 	return MPMC_OK;
@@ -963,6 +969,20 @@ static int enqueue_energy(mpmc_engine *e) {
 	if (e->topo_dirty && (rc = rebuild_topology(e))) return rc;
 	Timed _whole(e, MPMC_K_ENERGY_TOTAL);
 	const bool es = !cf.rd_only;
+	// coulombic_reciprocal(), structure factors.  The framework's: only when the cell or a frozen charged site changed.  The mobile
+	// sites': on the second stream, beside the pair sweep — it needs the coordinates only, and the sweep (whose items are dealt through
+	// a counter) takes whatever the structure-factor CTAs leave free, so its ramp-up and tail are no longer idle time.
+	const bool sk_side = es && !e->timing && e->stream2 && e->ev_fork && e->ev_sk;
+	if (es && e->frozen_sk_dirty) {
+		if ((rc = run_structure(e, e->d_frozen_q, (int)e->frozen_q.size(), e->d_S_frozen, nullptr))) return rc;
+		e->frozen_sk_dirty = false;
+	}
+	if (sk_side) {
+		CK(cudaEventRecord(e->ev_fork, e->stream));
+		CK(cudaStreamWaitEvent(e->stream2, e->ev_fork, 0));
+		if ((rc = run_structure(e, e->d_mobile_q, (int)e->mobile_q.size(), e->d_S_mobile, nullptr, e->stream2))) return rc;
+		CK(cudaEventRecord(e->ev_sk, e->stream2));
+	}
 	// pair sweep: lj() + coulombic_real()
 	const int nitems = e->pp.items_per_bead;
 	{
@@ -983,12 +1003,8 @@ static int enqueue_energy(mpmc_engine *e) {
 	LAUNCHED(e);
 	if (es) {
 		const int nk = (int)e->kvec.size();
-		// framework structure factor: only when the cell or a frozen charged site changed
-		if (e->frozen_sk_dirty) {
-			if ((rc = run_structure(e, e->d_frozen_q, (int)e->frozen_q.size(), e->d_S_frozen, nullptr))) return rc;
-			e->frozen_sk_dirty = false;
-		}
-		if ((rc = run_structure(e, e->d_mobile_q, (int)e->mobile_q.size(), e->d_S_mobile, nullptr))) return rc;
+		if (sk_side) CK(cudaStreamWaitEvent(e->stream, e->ev_sk, 0));
+		else if ((rc = run_structure(e, e->d_mobile_q, (int)e->mobile_q.size(), e->d_S_mobile, nullptr))) return rc;
 		k_recip_energy<<<B, 256, 0, e->stream>>>(e->d_S_mobile.p, e->d_kvec.p, nk, 4.0 * kPi / e->cell.volume, e->d_result.p);
 		LAUNCHED(e);
 		if (cf.polarization) {
@@ -1060,6 +1076,8 @@ int mpmc_create(const mpmc_config *cfg, mpmc_engine **out) {
 		// the Gauss-Seidel pipeline: one cluster (solver + helpers) and an updater kernel on every other SM, 2 CTAs each
 		CK(cudaStreamCreateWithFlags(&e->stream2, cudaStreamNonBlocking));
 		CK(cudaEventCreateWithFlags(&e->ev_upd, cudaEventDisableTiming));
+		CK(cudaEventCreateWithFlags(&e->ev_fork, cudaEventDisableTiming));
+		CK(cudaEventCreateWithFlags(&e->ev_sk, cudaEventDisableTiming));
 		CK(cudaHostAlloc(&e->h_started, sizeof(int), cudaHostAllocMapped));
 		*e->h_started = 0;
 		CK(cudaMallocHost(&e->h_gs_abort, sizeof(int)));
@@ -1106,6 +1124,8 @@ int mpmc_destroy(mpmc_engine *e) {
 	drop_pi_graph(e);
 	if (e->stream2) { cudaStreamSynchronize(e->stream2); cudaStreamDestroy(e->stream2); }
 	if (e->ev_upd) cudaEventDestroy(e->ev_upd);
+	if (e->ev_fork) cudaEventDestroy(e->ev_fork);
+	if (e->ev_sk) cudaEventDestroy(e->ev_sk);
 	if (e->h_started) cudaFreeHost(e->h_started);
 	if (e->h_gs_abort) cudaFreeHost(e->h_gs_abort);
 	for (int r = 0; r < (int)e->peer_mbox.size(); r++) if (r != e->rank && e->peer_mbox[r]) cudaIpcCloseMemHandle(e->peer_mbox[r]);

@@ -59,7 +59,7 @@ struct PairParams {
 };
 
 // relative cost of one column (32 pairs) of each kind, ~ 2 x FP64 + other instructions of its inner loop: equal-cost items
-inline int pair_kind_weight(int kind) { return kind == kPairLJ ? 60 : kind == kPairES ? 70 : 95; }
+inline int pair_kind_weight(int kind) { return kind == kPairLJ ? 60 : kind == kPairES ? 90 : 100; }   // the table look-ups of the Coulomb kinds are bound by shared-memory bandwidth
 
 // row lookup of a radial table held in shared memory: value of function 0 of a 1-function table at u
 // (the row index is clamped to the table: callers discard the value when u lies outside [u_lo, u_hi))
@@ -261,13 +261,15 @@ k_pair_sweep(const double4 *__restrict__ spq, const double2 *__restrict__ lj, co
 	double2 *s_lj = reinterpret_cast<double2 *>(s_pq + kPwJ);
 	int *s_pm = reinterpret_cast<int *>(s_lj + kPwJ);
 	if (ES) {
-		for (int q = tid; q < tab_len; q += kPwThreads) s_tab[q] = tab[q];
-		__syncthreads();
+		// the table (~32 KB) in 16-byte asynchronous copies, all in flight at once: a plain copy loop is 16 dependent round trips to L2,
+		// ~5 us during which the CTA does nothing else
+		stage_table(s_tab, tab, tab_len);
 	}
 	const int gw = blockIdx.x * kPwWarps + warp;
 	const int items = nbeads * pp.items_per_bead;
 	const double hx = 0.5 * fabs(c.b[0][0]), hy = 0.5 * fabs(c.b[1][1]), hz = 0.5 * fabs(c.b[2][2]);
 	if (lane < kPwCols) { s_pq[32 + lane] = nan_site(); s_lj[32 + lane] = make_double2(0, 0); s_pm[32 + lane] = kPmPad; }
+	if (ES) { stage_table_wait(); __syncthreads(); }
 	__syncwarp();
 
 	for (int it = gw; it < items;) {

@@ -142,6 +142,7 @@ k_field_parts(const double4 *__restrict__ posq, const int *__restrict__ meta, co
 	for (int j0 = jbeg; j0 < jend; j0 += kCtTile) {
 		__syncthreads();
 		if (j0 + tid < jend) { const int j = collist[j0 + tid]; s_pq[tid] = pq[j]; s_meta[tid] = meta_mol(meta[j]); }
+		if (EWALD && j0 == jbeg) stage_table_wait();
 		__syncthreads();
 		const int jn = min(kCtTile, jend - j0);
 		if (i >= 0) {
