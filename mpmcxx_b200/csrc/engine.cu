@@ -481,27 +481,39 @@ int prepare_pair_sweep(mpmc_engine *e) {
 	pp.ncols = col; pp.nseg = (int)e->segs.size();
 	pp.h_adm = (unsigned)RadialTable::hi_word(pp.t2_adm); pp.h_safe = (unsigned)RadialTable::hi_word(pp.t2_safe);
 	pp.h_tab_lo = (unsigned)RadialTable::hi_word(pp.u_tab_lo);
-	// items: equal-cost ranges of the flattened columns.  One per resident warp for small systems (a second item would cost more in
-	// per-item overhead than it balances: ~2 k cycles each); for larger ones items of 64 columns or more, up to 6 per warp, the later ones handed out through a
-	// counter: the sweep ends within a fraction of one item's duration of the ideal.  Boundaries inside a segment sit on whole
-	// 32-column chunks of that segment, so that only its last chunk is partial.
+	// items: ranges of the flattened columns, dealt in ROUNDS of one item per resident warp (item index = k * B + bead, k-major).
+	// The first round is assigned by warp index, the later ones through a counter.  Guided sizes: the rounds carry 1/2, 1/4, 1/8 ...
+	// of the cost (the last two rounds the same), so that the sweep ends within a fraction of the SMALLEST item's duration of the
+	// ideal while most of the work pays the per-item overhead (~2 k cycles) only once.  Small systems (< 128 columns per warp) get
+	// a single round.  Boundaries inside a segment sit on whole 32-column chunks of that segment, so only its last chunk is partial.
 	const int ctas = e->num_sms * pair_ctas_per_sm(es);
-	const int warps = ctas * kPwWarps;
+	const int warps = ctas * pair_warps(es);
 	const long total_cols = (long)col * e->B;
-	const int per_warp = (int)std::max(1L, std::min(6L, total_cols / ((long)warps * 64)));
-	int K = std::max(1, (warps * per_warp + e->B / 2) / e->B);
-	K = std::min(K, std::max(1, (col + 15) / 16));        // at least ~16 columns per item
+	const double cols_per_warp = (double)total_cols / warps;
+	int rounds = 1;
+	while (rounds < 6 && cols_per_warp / (1 << rounds) >= 32.0) rounds++;
+	if (cols_per_warp < 128.0) rounds = 1;
+	const int per_round = std::max(1, warps / e->B);                  // items of one round in one bead system (never more items than warps)
+	int K = per_round * rounds;
+	if (K > std::max(1, (col + 15) / 16)) { K = std::max(1, (col + 15) / 16); rounds = 1; }    // at least ~16 columns per item
 	pp.items_per_bead = K;
-	e->pair_grid = std::max(1, std::min(ctas, (e->B * K + kPwWarps - 1) / kPwWarps));
+	e->pair_grid = std::max(1, std::min(ctas, (e->B * K + pair_warps(es) - 1) / pair_warps(es)));
 	std::vector<int> item_seg(K, 0), item_col(K + 1, 0);
 	{
 		double total_w = 0;
 		for (const PairSeg &sg : e->segs) total_w += (double)(sg.j_end - sg.j_begin) * pair_kind_weight(sg.kind);
 		size_t sgi = 0;
 		double before = 0;                                  // weight of the segments before sgi
-		const bool align = per_warp > 1;
+		const bool align = rounds > 1;
+		// cumulative share of the cost before item k
+		std::vector<double> cum(K + 1, 0.0);
+		for (int k = 0; k < K; k++) {
+			const int r = rounds > 1 ? std::min(k / per_round, rounds - 1) : 0;
+			const double share = rounds > 1 ? std::ldexp(1.0, -(std::min(r, rounds - 2) + 1)) / per_round : 1.0 / K;
+			cum[k + 1] = cum[k] + share;
+		}
 		for (int k = 1; k < K; k++) {
-			const double target = total_w * k / K;
+			const double target = total_w * cum[k] / cum[K];
 			while (sgi + 1 < e->segs.size() && before + (double)(e->segs[sgi].j_end - e->segs[sgi].j_begin) * pair_kind_weight(e->segs[sgi].kind) <= target) {
 				before += (double)(e->segs[sgi].j_end - e->segs[sgi].j_begin) * pair_kind_weight(e->segs[sgi].kind);
 				sgi++;
@@ -522,7 +534,7 @@ int prepare_pair_sweep(mpmc_engine *e) {
 	if ((rc2 = e->d_item_seg.ensure(K)) || (rc2 = e->d_item_col.ensure(K + 1)) || (rc2 = e->d_item_ctr.ensure(1))) return rc2;
 	CK(cudaMemcpyAsync(e->d_item_seg.p, item_seg.data(), K * sizeof(int), cudaMemcpyHostToDevice, e->stream));
 	CK(cudaMemcpyAsync(e->d_item_col.p, item_col.data(), (K + 1) * sizeof(int), cudaMemcpyHostToDevice, e->stream));
-	e->pair_ctr_start = e->pair_grid * kPwWarps;
+	e->pair_ctr_start = e->pair_grid * pair_warps(es);
 	CK(cudaMemcpyAsync(e->d_item_ctr.p, &e->pair_ctr_start, sizeof(int), cudaMemcpyHostToDevice, e->stream));
 	if ((rc2 = e->d_pmeta.ensure(std::max(n, 1))) || (rc2 = e->d_segs.ensure(std::max<size_t>(e->segs.size(), 1))) || (rc2 = e->d_perm.ensure(std::max(n, 1))) ||
 	    (rc2 = e->d_slj.ensure(std::max(n, 1))) || (rc2 = e->d_spq.ensure((size_t)e->B * e->cap))) return rc2;
@@ -995,8 +1007,8 @@ static int enqueue_energy(mpmc_engine *e) {
 			LAUNCHED(e);
 			spq = e->d_spq.p;
 		}
-		if (es) k_pair_sweep<ORTHO, true><<<e->pair_grid, kPwThreads, smem, e->stream>>>(spq, e->d_slj.p, e->d_pmeta.p, e->cap, B, e->d_segs.p, e->d_item_seg.p, e->d_item_col.p, e->pp, e->cell, e->d_erf_tab.p, e->d_partials.p, e->d_item_ctr.p);
-		else k_pair_sweep<ORTHO, false><<<e->pair_grid, kPwThreads, smem, e->stream>>>(spq, e->d_slj.p, e->d_pmeta.p, e->cap, B, e->d_segs.p, e->d_item_seg.p, e->d_item_col.p, e->pp, e->cell, nullptr, e->d_partials.p, e->d_item_ctr.p);
+		if (es) k_pair_sweep<ORTHO, true><<<e->pair_grid, pair_warps(true) * 32, smem, e->stream>>>(spq, e->d_slj.p, e->d_pmeta.p, e->cap, B, e->d_segs.p, e->d_item_seg.p, e->d_item_col.p, e->pp, e->cell, e->d_erf_tab.p, e->d_partials.p, e->d_item_ctr.p);
+		else k_pair_sweep<ORTHO, false><<<e->pair_grid, pair_warps(false) * 32, smem, e->stream>>>(spq, e->d_slj.p, e->d_pmeta.p, e->cap, B, e->d_segs.p, e->d_item_seg.p, e->d_item_col.p, e->pp, e->cell, nullptr, e->d_partials.p, e->d_item_ctr.p);
 		LAUNCHED(e);
 	}
 	k_reduce_partials<<<B, 256, 0, e->stream>>>(e->d_partials.p, nitems, e->d_result.p, e->d_item_ctr.p, e->pair_ctr_start);

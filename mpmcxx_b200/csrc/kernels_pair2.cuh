@@ -23,8 +23,8 @@
 //     per kind, so a five-site H2 system (one LJ+charge site, two charge-only, two LJ-only) does half the arithmetic it would
 //     with every pair going through both formulas.
 //   * work is dealt to warps, not CTAs: the (i-group of 32 sites) x (j site) columns of every class block are flattened and cut
-//     into items of equal COST (columns weighted by what their kind issues); a warp takes its first item by its index and the
-//     following ones from a counter, so 148 SMs x 16 warps stay busy to the end whatever N and the mix of kinds are.
+//     into items by COST (columns weighted by what their kind issues); a warp takes its first item by its index and the following,
+//     smaller and smaller ones from a counter, so 148 SMs x 16 warps stay busy to the end whatever N and the mix of kinds are.
 // Sums are accumulated per item in a fixed order and reduced by k_reduce_partials: results are bit-reproducible whichever warp
 // ends up with an item.
 #pragma once
@@ -34,7 +34,10 @@
 
 namespace mpmc {
 
-constexpr int kPwWarps = 8, kPwThreads = kPwWarps * 32;
+// CTA shapes: 2 CTAs x 8 warps at <= 128 registers for both kernels (3 CTAs x 6 warps at 96 registers was measured for the LJ-only
+// kernel: 28.6 us instead of 26.2 on config 3)
+__host__ __device__ constexpr int pair_warps(bool) { return 8; }
+__host__ __device__ constexpr int pair_ctas(bool) { return 2; }
 constexpr int kErfRow = (kTabDeg + 1) + kTabPad;        // doubles per row of the erfc table
 
 // per-site word of the pair sweep: the molecule index (same molecule = rd_excluded / es_excluded); padding lanes and columns carry
@@ -107,10 +110,6 @@ __device__ __forceinline__ void add_if(double &acc, double v, bool p) {
 	asm("{\n\t.reg .pred q;\n\tsetp.ne.s32 q, %2, 0;\n\t@q add.f64 %0, %0, %1;\n\t}" : "+d"(acc) : "d"(v), "r"((int)p));
 }
 
-#ifndef MPMC_PW_CTAS
-#define MPMC_PW_CTAS 2
-#endif
-constexpr int kPwCtas = MPMC_PW_CTAS;         // resident CTAs per SM the kernel is compiled for
 constexpr int kPwCols = 4;                      // columns per pass of the inner loop (independent FP64 chains)
 constexpr int kPwJ = 32 + kPwCols;              // staged j sites per warp (+ padding columns)
 constexpr int kPwWarpDoubles = kPwJ * 4 + kPwJ * 2 + kPwJ / 2;   // (x y z q), (sqrt eps, sigma/2), site word
@@ -245,10 +244,10 @@ __device__ __forceinline__ void pair_chunk(const CellDev &c, const PairParams &p
 	}
 }
 
-// item_col[k], k <= items_per_bead: column boundaries of the items; ctr: the next item to hand out (gridDim.x * kPwWarps when the
+// item_col[k], k <= items_per_bead: column boundaries of the items; ctr: the next item to hand out (gridDim.x * warps per CTA when the
 // kernel starts — k_reduce_partials puts it back)
 template <bool ORTHO, bool ES>
-__global__ void __launch_bounds__(kPwThreads, kPwCtas)
+__global__ void __launch_bounds__(pair_warps(ES) * 32, pair_ctas(ES))
 k_pair_sweep(const double4 *__restrict__ spq, const double2 *__restrict__ lj, const int *__restrict__ pmeta, int stride, int nbeads,
              const PairSeg *__restrict__ seg, const int *__restrict__ item_seg, const int *__restrict__ item_col, const PairParams pp, const CellDev c,
              const double *__restrict__ tab, PairPartial *__restrict__ partials, int *__restrict__ ctr) {
@@ -265,7 +264,7 @@ k_pair_sweep(const double4 *__restrict__ spq, const double2 *__restrict__ lj, co
 		// ~5 us during which the CTA does nothing else
 		stage_table(s_tab, tab, tab_len);
 	}
-	const int gw = blockIdx.x * kPwWarps + warp;
+	const int gw = blockIdx.x * pair_warps(ES) + warp;
 	const int items = nbeads * pp.items_per_bead;
 	const double hx = 0.5 * fabs(c.b[0][0]), hy = 0.5 * fabs(c.b[1][1]), hz = 0.5 * fabs(c.b[2][2]);
 	if (lane < kPwCols) { s_pq[32 + lane] = nan_site(); s_lj[32 + lane] = make_double2(0, 0); s_pm[32 + lane] = kPmPad; }
@@ -273,7 +272,7 @@ k_pair_sweep(const double4 *__restrict__ spq, const double2 *__restrict__ lj, co
 	__syncwarp();
 
 	for (int it = gw; it < items;) {
-		const int bead = it / pp.items_per_bead, k = it - bead * pp.items_per_bead;
+		const int k = it / nbeads, bead = it - k * nbeads;      // k-major: the rounds of prepare_pair_sweep() follow each other
 		const double4 *pq = spq + (size_t)bead * stride;
 		int col = item_col[k];
 		const int col_end = item_col[k + 1];
@@ -322,17 +321,28 @@ k_pair_sweep(const double4 *__restrict__ spq, const double2 *__restrict__ lj, co
 				s++;
 			}
 		}
-		const double rd = warp_sum(a.rd), re = warp_sum(a.re), in = warp_sum(a.in), cn = warp_sum((double)a.cnt);
-		if (lane == 0) { PairPartial p; p.rd = 4.0 * rd; p.es_real = re; p.es_intra = in; p.n_in = cn; partials[it] = p; }
+		// the four sums over the warp in one shrinking xor tree (6 shuffles instead of 20, fixed order): lanes 0, 8, 16, 24 end up
+		// with the totals of rd, es_real, es_intra, n_in and store them
+		{
+			const unsigned F = 0xffffffffu;
+			double v0 = a.rd, v1 = a.re, v2 = a.in, v3 = (double)a.cnt;
+			const bool h16 = (lane & 16) != 0, h8 = (lane & 8) != 0;
+			const double r0 = __shfl_xor_sync(F, h16 ? v0 : v2, 16), r1 = __shfl_xor_sync(F, h16 ? v1 : v3, 16);
+			v0 = (h16 ? v2 : v0) + r0; v1 = (h16 ? v3 : v1) + r1;
+			const double r2 = __shfl_xor_sync(F, h8 ? v0 : v1, 8);
+			v0 = (h8 ? v1 : v0) + r2;
+			v0 += __shfl_xor_sync(F, v0, 4); v0 += __shfl_xor_sync(F, v0, 2); v0 += __shfl_xor_sync(F, v0, 1);
+			if ((lane & 7) == 0) reinterpret_cast<double *>(partials + ((size_t)bead * pp.items_per_bead + k))[lane >> 3] = lane == 0 ? 4.0 * v0 : v0;
+		}
 		if (lane == 0) it = atomicAdd(ctr, 1);
 		it = __shfl_sync(0xffffffffu, it, 0);
 	}
 }
 
-inline int pair_ctas_per_sm(bool) { return kPwCtas; }
+inline int pair_ctas_per_sm(bool es) { return pair_ctas(es); }
 inline size_t pair_sweep_smem(bool es, int tab_rows) {
 	const size_t tab_len = es ? ((size_t)tab_rows * kErfRow + 1) & ~(size_t)1 : 0;
-	return sizeof(double) * (tab_len + (size_t)kPwWarps * kPwWarpDoubles);
+	return sizeof(double) * (tab_len + (size_t)pair_warps(es) * kPwWarpDoubles);
 }
 
 } // namespace mpmc
