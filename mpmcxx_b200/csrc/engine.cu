@@ -156,7 +156,7 @@ struct mpmc_engine {
 	DevBuf<KVec> d_kvec;
 	DevBuf<PairPartial> d_partials;
 	DevBuf<double2> d_sk_part, d_S_mobile, d_S_frozen, d_S_all;
-	DevBuf<double> d_efs, d_efi, d_efic, d_mu, d_new_mu, d_old_mu, d_rrms, d_rank, d_acc, d_dmu, d_tri, d_com, d_mol_mass, d_chain;
+	DevBuf<double> d_efs, d_efi, d_efic, d_mu, d_new_mu, d_old_mu, d_rrms, d_rank, d_acc, d_dmu, d_tri, d_near, d_com, d_mol_mass, d_chain;
 	DevBuf<int> d_gsctl, d_gmeta, d_nplist;
 	DevBuf<double4> d_gpq;
 	DevBuf<double> d_cparts, d_field_tab;
@@ -877,7 +877,7 @@ static int run_polar(mpmc_engine *e) {
 			// Gauss-Seidel pipeline (kernels_gs.cuh).  First sweep in list order (ranked_array = identity, :3463); from the second
 			// sweep on in rank order when polar_gs_ranked (update_ranking after the first pass, :3522-3523).
 			const int nblk = (np + kGsB - 1) / kGsB, nchunks = (np + kGsRows - 1) / kGsRows;
-			if ((rc = e->d_acc.ensure(len)) || (rc = e->d_dmu.ensure((size_t)np * 3)) || (rc = e->d_tri.ensure((size_t)nblk * kGsMat)) ||
+			if ((rc = e->d_acc.ensure(len)) || (rc = e->d_dmu.ensure((size_t)np * 3)) || (rc = e->d_tri.ensure((size_t)nblk * kGsMat)) || (rc = e->d_near.ensure((size_t)nblk * kGsNearPerBlock)) ||
 			    (rc = e->d_gsctl.ensure(sizeof(GsCtl) / sizeof(int) + nchunks)) || (rc = e->d_gpq.ensure(np)) || (rc = e->d_gmeta.ensure(np))) return rc;
 			if (it == 1 || acc_stale) {
 				Timed _t(e, MPMC_K_DIPOLE_SWEEP);
@@ -893,8 +893,9 @@ static int run_polar(mpmc_engine *e) {
 				}
 				Timed _t(e, MPMC_K_GS_SWEEP);
 				k_gs_gather<<<(np + 255) / 256, 256, 0, e->stream>>>(e->d_posq.p, e->d_alpha.p, e->d_meta.p, gs_order, np, e->d_gpq.p, e->d_gmeta.p);
-				k_gs_tensors<ORTHO><<<nblk, kGsThreads, 0, e->stream>>>(e->d_gpq.p, e->d_gmeta.p, np, e->cell, pd, e->d_tri.p);
-				e->launches += 2;
+				k_gs_inverse<ORTHO><<<nblk, kGsThreads, kGsInverseSmemBytes, e->stream>>>(e->d_gpq.p, e->d_gmeta.p, np, e->cell, pd, e->d_tri.p);
+				k_gs_near<ORTHO><<<nblk, kGsPipeThreads, 0, e->stream>>>(e->d_gpq.p, e->d_gmeta.p, np, e->cell, pd, e->d_near.p);
+				e->launches += 3;
 			}
 			int ns = 1;
 			if (!need_old && !want_check && cf.polar_precision == 0.0) ns = (ranked && it == 1) ? 1 : (cf.polar_max_iter - it + 1);
@@ -911,10 +912,10 @@ static int run_polar(mpmc_engine *e) {
 					CK(cudaMemsetAsync(e->d_gsctl.p, 0, sizeof(int) * (sizeof(GsCtl) / sizeof(int) + nchunks), e->stream));
 					const int token = ++e->gs_token;
 					const int sgrid = e->gs_fused ? e->gs_fused_grid : kGsCluster;
-					if (expd) k_gs_pipeline<ORTHO, true><<<sgrid, kGsThreads, kGsSmemBytes, e->stream>>>(e->d_gpq.p, e->d_gmeta.p, gs_order, np, e->cell, pd, e->d_efs.p,
-					        e->d_mu.p, e->d_efi.p, e->d_new_mu.p, e->d_acc.p, e->d_dmu.p, e->d_tri.p, (GsCtl *)e->d_gsctl.p, sw == 0 ? prof : nullptr, e->d_started, token);
-					else k_gs_pipeline<ORTHO, false><<<sgrid, kGsThreads, kGsSmemBytes, e->stream>>>(e->d_gpq.p, e->d_gmeta.p, gs_order, np, e->cell, pd, e->d_efs.p,
-					        e->d_mu.p, e->d_efi.p, e->d_new_mu.p, e->d_acc.p, e->d_dmu.p, e->d_tri.p, (GsCtl *)e->d_gsctl.p, sw == 0 ? prof : nullptr, e->d_started, token);
+					if (expd) k_gs_pipeline<ORTHO, true><<<sgrid, kGsPipeThreads, kGsSmemBytes, e->stream>>>(e->d_gpq.p, e->d_gmeta.p, gs_order, np, e->cell, pd, e->d_efs.p,
+					        e->d_mu.p, e->d_efi.p, e->d_new_mu.p, e->d_acc.p, e->d_dmu.p, e->d_tri.p, e->d_near.p, (GsCtl *)e->d_gsctl.p, sw == 0 ? prof : nullptr, e->d_started, token);
+					else k_gs_pipeline<ORTHO, false><<<sgrid, kGsPipeThreads, kGsSmemBytes, e->stream>>>(e->d_gpq.p, e->d_gmeta.p, gs_order, np, e->cell, pd, e->d_efs.p,
+					        e->d_mu.p, e->d_efi.p, e->d_new_mu.p, e->d_acc.p, e->d_dmu.p, e->d_tri.p, e->d_near.p, (GsCtl *)e->d_gsctl.p, sw == 0 ? prof : nullptr, e->d_started, token);
 					CK(cudaGetLastError());
 					if (e->gs_fused) { LAUNCHED(e); continue; }
 					// The updaters must not take the SMs the cluster needs (its CTAs want a whole SM's shared memory each): wait until the
@@ -934,6 +935,8 @@ static int run_polar(mpmc_engine *e) {
 				}
 				CK(cudaGetLastError());
 				CK(cudaMemcpyAsync(e->h_gs_abort, e->d_gsctl.p + 1, sizeof(int), cudaMemcpyDeviceToHost, e->stream));
+				k_gs_efi<<<(np * 3 + eb - 1) / eb, eb, 0, e->stream>>>(e->d_plist.p, np, e->d_mu.p, e->d_alpha.p, e->d_efs.p, e->d_efi.p);
+				LAUNCHED(e);
 				e->gs_ran = true;
 			}
 			it += ns - 1;
@@ -1076,6 +1079,7 @@ int mpmc_create(const mpmc_config *cfg, mpmc_engine **out) {
 	{
 		const size_t fmax = 96 * 1024;
 		if ((rc = set_smem(k_field_parts<true, true>, fmax)) || (rc = set_smem(k_field_parts<false, true>, fmax))) { mpmc_destroy(e); return rc; }
+		if ((rc = set_smem(k_gs_inverse<true>, kGsInverseSmemBytes)) || (rc = set_smem(k_gs_inverse<false>, kGsInverseSmemBytes))) { mpmc_destroy(e); return rc; }
 		if ((rc = set_smem(k_gs_pipeline<true, true>, kGsSmemBytes)) || (rc = set_smem(k_gs_pipeline<false, true>, kGsSmemBytes)) ||
 		    (rc = set_smem(k_gs_pipeline<true, false>, kGsSmemBytes)) || (rc = set_smem(k_gs_pipeline<false, false>, kGsSmemBytes))) { mpmc_destroy(e); return rc; }
 	}
@@ -1099,11 +1103,11 @@ int mpmc_create(const mpmc_config *cfg, mpmc_engine **out) {
 		    (rc = set_smem(k_gs_updaters<true, false>, kGsUpdaterSmemBytes)) || (rc = set_smem(k_gs_updaters<false, false>, kGsUpdaterSmemBytes))) { mpmc_destroy(e); return rc; }
 		int occ = 0;
 		CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_gs_updaters<true, true>, kGsThreads, kGsUpdaterSmemBytes));
-		e->gs_upd_grid = std::max(1, e->num_sms - kGsCluster) * std::max(1, std::min(occ, 2));
+		e->gs_upd_grid = std::max(1, e->num_sms - kGsCluster) * std::max(1, std::min(occ, kGsUpdCtas));
 		e->gs_grid = kGsCluster;
 		// single-launch fallback: as many clusters as the device holds at one CTA per SM
 		cudaLaunchConfig_t lc = {};
-		lc.gridDim = dim3(e->num_sms / kGsCluster * kGsCluster); lc.blockDim = dim3(kGsThreads); lc.dynamicSmemBytes = kGsSmemBytes;
+		lc.gridDim = dim3(e->num_sms / kGsCluster * kGsCluster); lc.blockDim = dim3(kGsPipeThreads); lc.dynamicSmemBytes = kGsSmemBytes;
 		cudaLaunchAttribute at[1];
 		at[0].id = cudaLaunchAttributeClusterDimension; at[0].val.clusterDim.x = kGsCluster; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
 		lc.attrs = at; lc.numAttrs = 1;
@@ -1128,7 +1132,7 @@ int mpmc_destroy(mpmc_engine *e) {
 	e->d_segs.release(); e->d_item_seg.release(); e->d_item_col.release(); e->d_item_ctr.release(); e->d_pmeta.release(); e->d_perm.release(); e->d_slj.release(); e->d_spq.release(); e->d_stage.release(); e->d_erf_tab.release(); e->d_mol_mobile.release(); e->d_kvec.release(); e->d_partials.release();
 	e->d_sk_part.release(); e->d_S_mobile.release(); e->d_S_frozen.release(); e->d_S_all.release();
 	e->d_efs.release(); e->d_efi.release(); e->d_efic.release(); e->d_mu.release(); e->d_new_mu.release(); e->d_old_mu.release();
-	e->d_rrms.release(); e->d_rank.release(); e->d_acc.release(); e->d_dmu.release(); e->d_tri.release(); e->d_gsctl.release(); e->d_gmeta.release(); e->d_nplist.release(); e->d_gpq.release(); e->d_cparts.release(); e->d_field_tab.release(); e->d_fp_list.release(); e->d_mp_list.release(); e->d_recount.release(); e->d_r2min_ff.release(); e->d_t2.release(); e->d_t2_cached.release(); e->d_cnt_ff.release(); e->d_mobile_sites.release(); e->d_frozen_sites.release(); e->d_allq.release(); e->d_com.release(); e->d_mol_mass.release(); e->d_chain.release();
+	e->d_rrms.release(); e->d_rank.release(); e->d_acc.release(); e->d_dmu.release(); e->d_tri.release(); e->d_near.release(); e->d_gsctl.release(); e->d_gmeta.release(); e->d_nplist.release(); e->d_gpq.release(); e->d_cparts.release(); e->d_field_tab.release(); e->d_fp_list.release(); e->d_mp_list.release(); e->d_recount.release(); e->d_r2min_ff.release(); e->d_t2.release(); e->d_t2_cached.release(); e->d_cnt_ff.release(); e->d_mobile_sites.release(); e->d_frozen_sites.release(); e->d_allq.release(); e->d_com.release(); e->d_mol_mass.release(); e->d_chain.release();
 	e->d_rmin.release(); e->d_result.release();
 	if (e->h_stage) cudaFreeHost(e->h_stage);
 	if (e->h_result) cudaFreeHost(e->h_result);

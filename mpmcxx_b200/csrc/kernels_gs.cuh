@@ -32,19 +32,28 @@
 namespace mpmc {
 
 constexpr int kGsB = 64;                  // sites per solver block
-constexpr int kGsRows = 8;                // rows per updater chunk (one warp: 8 rows x 4 column lanes)
+constexpr int kGsRows = 4;                // rows per updater chunk (one warp: 4 rows x 8 column lanes)
+constexpr int kGsColLanes = 32 / kGsRows;
+constexpr int kGsUpdCtas = 4;             // updater CTAs per SM the kernel is compiled for
 constexpr int kGsThreads = 256;
 constexpr int kGsWarps = kGsThreads / 32;
-constexpr int kGsMat = kGsB * kGsB * 6;   // doubles of one block's tensor matrix: [column k][row m][xx yy zz xy xz yz]
+constexpr int kGsPipeThreads = 512;       // the solver/helper cluster: 192 x 2 threads walk, 512 per helper push
+constexpr int kGsN = 3 * kGsB;            // components per block
+constexpr int kGsInv = 9 * (kGsB * (kGsB - 1) / 2);   // 18144 doubles: one block's strictly lower inverse (k_gs_inverse)
+__host__ __device__ constexpr int gs_inv_rows(int j) { return kGsN - 3 * (j + 1); }
+__host__ __device__ constexpr int gs_inv_off(int j) { return 3 * (kGsN - 3) * j - 9 * (j * (j - 1) / 2); }
+constexpr int kGsMat = kGsInv;            // doubles of the solver's matrix buffer
 
 // shared memory (doubles).  Solver: the block's tensor matrix, two site-column buffers, pending push (3 slices + sum), two row
 // buffers, panel dmu, the walk's results, ints.  Updaters: per warp the panel's columns and dmu.
 constexpr int kGsSiteCols = 10;           // 0 alpha, 1-3 mu_old, 4-6 E_static, 7-9 acc
-constexpr int kGsAhead = 3;               // the cluster pushes a panel into this many following blocks itself; the updaters take the rest
-constexpr int kGsHelpers = 3, kGsCluster = 1 + kGsHelpers;
+constexpr int kGsAhead = 4;               // the cluster pushes a panel into this many following blocks itself; the updaters take the rest
+constexpr int kGsHelpers = 7, kGsCluster = 1 + kGsHelpers;
 constexpr int kGsSlots = kGsAhead + 1;    // ring of per-block buffers
-constexpr size_t kGsSolverDoubles = (size_t)kGsMat + kGsSiteCols * kGsB + kGsHelpers * (kGsAhead * kGsB * 3) + kGsSlots * 3 * kGsB + 4 * kGsB + 2 * kGsB + 16;
+constexpr size_t kGsSolverDoubles = (size_t)kGsMat + 2 * kGsSiteCols * kGsB + kGsHelpers * (kGsAhead * kGsB * 3) + kGsSlots * 3 * kGsB + 4 * kGsB + 4 * kGsB + kGsN + 2 * kGsB + 16;
 constexpr size_t kGsUpdaterDoubles = (size_t)kGsWarps * 8 * kGsB;
+constexpr int kGsHelperOutOffset = 4 * kGsB;      // doubles: a helper's delivery buffer inside its shared memory (after h_dm)
+static_assert(kGsSolverDoubles >= (size_t)(kGsPipeThreads / 32) * 8 * kGsB, "the fused fallback runs the updaters inside the pipeline kernel");
 constexpr size_t kGsSmemBytes = sizeof(double) * kGsSolverDoubles;
 constexpr size_t kGsUpdaterSmemBytes = sizeof(double) * kGsUpdaterDoubles;
 
@@ -54,6 +63,11 @@ struct GsCtl { int solved; int abort; int pad[30]; };   // followed in memory by
 // tool that serialises launches).  Everybody then stops waiting, the sweep's result is meaningless and the host reports it.
 constexpr int kGsWaitLimit = 20000000;
 
+__device__ __forceinline__ long long gtime() { long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; }
+// clock read that cannot run ahead of a preceding barrier (BAR.SYNC.DEFER_BLOCKING lets register-only instructions pass): it
+// depends on a shared-memory load issued after the barrier
+__device__ __forceinline__ long long clock_after(const volatile int *p) { const int x = *p; long long t; asm volatile("mov.u64 %0, %%clock64;" : "=l"(t) : "r"(x)); return t; }
+__device__ __forceinline__ int ld_acquire(const int *p) { int v; asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory"); return v; }
 __device__ __forceinline__ int ld_flag(const int *p) { return *(const volatile int *)p; }
 __device__ __forceinline__ void st_flag(int *p, int v) { *(volatile int *)p = v; }
 
@@ -79,36 +93,116 @@ __device__ __forceinline__ void gs_contract(const CellDev &c, const PolarDev &p,
 	}
 }
 
-// in-block tensors for every block of the sweep order, as a full matrix so that the walk reads column k with unit stride:
-// mat[blk][k][m][6] = xx yy zz xy xz yz of T_mk (zero on the diagonal and for rows/columns past the end)
+// The walk of a block is a forward substitution: with a = the running contraction of the block's rows when the block starts,
+//       (I + diag(alpha) T_L) dmu = alpha E_s - mu_old - alpha a,        T_L = the strictly lower (earlier-site) part of the block's T,
+// 64 sequential steps if done site by site (the first version of this pipeline: ~160 cycles per site on the one warp the whole sweep
+// waits for).  The matrix depends on the geometry and the sweep order only — not on the dipoles — so its inverse is computed ONCE
+// per energy() and sweep order, for all blocks in parallel (k_gs_inverse), and the walk becomes one 192 x 192 triangular
+// matrix-vector product spread over 192 threads.  Layout of the strictly lower inverse X (unit diagonal and the identity 3x3
+// diagonal blocks are implied):  inv[blk][gs_inv_off(j) + q * gs_inv_rows(j) + (r - 3 (j + 1))] = X[r][3 j + q]  for column site j,
+// column component q, row component r >= 3 (j + 1): thread r of the walk reads unit-stride.
+constexpr size_t kGsInverseSmemBytes = sizeof(double) * (kGsInv + 6 * kGsB) + sizeof(double4) * kGsB + sizeof(int) * kGsB;
+
 template <bool ORTHO>
 __global__ void __launch_bounds__(kGsThreads)
-k_gs_tensors(const double4 *__restrict__ gpq, const int *__restrict__ gmeta, int np, CellDev c, PolarDev p, double *__restrict__ mat) {
-	__shared__ double4 s_pq[kGsB];
-	__shared__ int     s_met[kGsB];
+k_gs_inverse(const double4 *__restrict__ gpq, const int *__restrict__ gmeta, int np, CellDev c, PolarDev p, double *__restrict__ inv) {
+	extern __shared__ __align__(16) double s_w[];                 // X by rows: row component r holds its 3 (r / 3) entries at row_off(r)
+	double *s_L = s_w + kGsInv;                                    // alpha_i T_ij of the row being eliminated: [j][xx yy zz xy xz yz]
+	double4 *s_pq = (double4 *)(s_L + 6 * kGsB);
+	int *s_met = (int *)(s_pq + kGsB);
 	const int blk = blockIdx.x, base = blk * kGsB, cnt = min(kGsB, np - base), tid = threadIdx.x;
-	if (tid < cnt) { s_pq[tid] = gpq[base + tid]; s_met[tid] = gmeta[base + tid]; }
+	if (tid < kGsB) { s_pq[tid] = tid < cnt ? gpq[base + tid] : make_double4(0, 0, 0, 0); s_met[tid] = tid < cnt ? gmeta[base + tid] : 0; }
 	__syncthreads();
-	double *out = mat + (size_t)blk * kGsMat;
+	auto row_off = [](int r) { const int i = r / 3; return 9 * (i * (i - 1) / 2) + (r - 3 * i) * 3 * i; };
+	// phase 1: alpha_i T_ij for every pair j < i, parked at the top of the buffer; row i lives at t_off(i) and is taken out before
+	// X's rows (growing from the bottom) reach it:  9 i (i + 1) / 2  <=  t_off(i + 1)  for every i
+	auto t_off = [](int i) { return kGsInv - 3 * (kGsB * (kGsB - 1) - i * (i - 1)); };
 	for (int q = tid; q < kGsB * kGsB; q += kGsThreads) {
-		const int a = q / kGsB, b = q % kGsB;
-		if (a > b) continue;
+		const int i = q / kGsB, j = q % kGsB;
+		if (j >= i) continue;
 		double xx = 0, xy = 0, xz = 0, yy = 0, yz = 0, zz = 0, t0 = 0, t1 = 0;
-		if (a < b && b < cnt) {
+		if (i < cnt) {
 			// the tensor itself = the contraction applied to the three unit dipoles (columns of T)
 			if (p.damp_type == 2) {
-				gs_contract<ORTHO, true>(c, p, s_pq[a], s_met[a], s_pq[b], s_met[b], make_double4(1, 0, 0, 0), xx, xy, xz);
-				gs_contract<ORTHO, true>(c, p, s_pq[a], s_met[a], s_pq[b], s_met[b], make_double4(0, 1, 0, 0), t0, yy, yz);
-				gs_contract<ORTHO, true>(c, p, s_pq[a], s_met[a], s_pq[b], s_met[b], make_double4(0, 0, 1, 0), t0, t1, zz);
+				gs_contract<ORTHO, true>(c, p, s_pq[i], s_met[i], s_pq[j], s_met[j], make_double4(1, 0, 0, 0), xx, xy, xz);
+				gs_contract<ORTHO, true>(c, p, s_pq[i], s_met[i], s_pq[j], s_met[j], make_double4(0, 1, 0, 0), t0, yy, yz);
+				gs_contract<ORTHO, true>(c, p, s_pq[i], s_met[i], s_pq[j], s_met[j], make_double4(0, 0, 1, 0), t0, t1, zz);
 			} else {
-				gs_contract<ORTHO, false>(c, p, s_pq[a], s_met[a], s_pq[b], s_met[b], make_double4(1, 0, 0, 0), xx, xy, xz);
-				gs_contract<ORTHO, false>(c, p, s_pq[a], s_met[a], s_pq[b], s_met[b], make_double4(0, 1, 0, 0), t0, yy, yz);
-				gs_contract<ORTHO, false>(c, p, s_pq[a], s_met[a], s_pq[b], s_met[b], make_double4(0, 0, 1, 0), t0, t1, zz);
+				gs_contract<ORTHO, false>(c, p, s_pq[i], s_met[i], s_pq[j], s_met[j], make_double4(1, 0, 0, 0), xx, xy, xz);
+				gs_contract<ORTHO, false>(c, p, s_pq[i], s_met[i], s_pq[j], s_met[j], make_double4(0, 1, 0, 0), t0, yy, yz);
+				gs_contract<ORTHO, false>(c, p, s_pq[i], s_met[i], s_pq[j], s_met[j], make_double4(0, 0, 1, 0), t0, t1, zz);
 			}
 		}
-		double *u = out + ((size_t)a * kGsB + b) * 6, *l = out + ((size_t)b * kGsB + a) * 6;
-		u[0] = xx; u[1] = yy; u[2] = zz; u[3] = xy; u[4] = xz; u[5] = yz;
-		l[0] = xx; l[1] = yy; l[2] = zz; l[3] = xy; l[4] = xz; l[5] = yz;
+		const double al = s_pq[i].w;
+		double *t = s_w + t_off(i) + 6 * j;
+		t[0] = al * xx; t[1] = al * yy; t[2] = al * zz; t[3] = al * xy; t[4] = al * xz; t[5] = al * yz;
+	}
+	__syncthreads();
+	// phase 2: forward substitution by row sites.  Thread cc owns column component cc = 3 jc + q of X:
+	//   X[i][cc] = - sum_{jc <= j < i} L_ij X[j][cc],   X[jc][cc] = e_q
+	for (int i = 1; i < kGsB; i++) {
+		for (int q = tid; q < 6 * i; q += kGsThreads) s_L[q] = s_w[t_off(i) + q];
+		__syncthreads();
+		if (tid < 3 * i) {
+			const int jc = tid / 3, q = tid - 3 * jc;
+			const double *l = s_L + 6 * jc;
+			// - (column q of L_i,jc):  L = [xx xy xz; xy yy yz; xz yz zz]
+			double x0 = q == 0 ? -l[0] : q == 1 ? -l[3] : -l[4];
+			double x1 = q == 0 ? -l[3] : q == 1 ? -l[1] : -l[5];
+			double x2 = q == 0 ? -l[4] : q == 1 ? -l[5] : -l[2];
+			for (int j = jc + 1; j < i; j++) {
+				const double v0 = s_w[row_off(3 * j) + tid], v1 = s_w[row_off(3 * j + 1) + tid], v2 = s_w[row_off(3 * j + 2) + tid];
+				const double *m = s_L + 6 * j;
+				x0 = fma(-m[0], v0, fma(-m[3], v1, fma(-m[4], v2, x0)));
+				x1 = fma(-m[3], v0, fma(-m[1], v1, fma(-m[5], v2, x1)));
+				x2 = fma(-m[4], v0, fma(-m[5], v1, fma(-m[2], v2, x2)));
+			}
+			s_w[row_off(3 * i) + tid] = x0; s_w[row_off(3 * i + 1) + tid] = x1; s_w[row_off(3 * i + 2) + tid] = x2;
+		}
+		__syncthreads();
+	}
+	// the walk's layout
+	double *out = inv + (size_t)blk * kGsInv;
+	for (int r = 3; r < kGsN; r++) {
+		const int ncol = 3 * (r / 3);
+		if (tid < ncol) {
+			const int j = tid / 3, q = tid - 3 * j;
+			out[gs_inv_off(j) + q * gs_inv_rows(j) + (r - 3 * (j + 1))] = s_w[row_off(r) + tid];
+		}
+	}
+}
+
+// The cluster's own pushes (a panel into the rows of the next kGsAhead blocks) need the tensors between every site and the
+// kGsAhead * 64 sites that follow its block in the sweep order.  Like the inverse they depend on geometry and order only, so they
+// are computed once per energy() and order and then only READ by the helpers in every sweep (48 bytes and 9 FMAs per pair instead
+// of ~70 FP64 instructions):  near[((blk * 64 + k) * kGsAhead + j) * 64 + r][6] = xx yy zz xy xz yz of T(row r of block blk+1+j, column k of block blk).
+constexpr size_t kGsNearPerBlock = (size_t)kGsB * kGsAhead * kGsB * 6;
+template <bool ORTHO>
+__global__ void __launch_bounds__(kGsPipeThreads)
+k_gs_near(const double4 *__restrict__ gpq, const int *__restrict__ gmeta, int np, CellDev c, PolarDev p, double *__restrict__ near) {
+	__shared__ double4 s_col[kGsB], s_row[kGsAhead * kGsB];
+	__shared__ int s_cm[kGsB], s_rm[kGsAhead * kGsB];
+	const int blk = blockIdx.x, tid = threadIdx.x;
+	if (tid < kGsB) { const int pos = blk * kGsB + tid; s_col[tid] = pos < np ? gpq[pos] : make_double4(0, 0, 0, 0); s_cm[tid] = pos < np ? gmeta[pos] : -1; }
+	if (tid < kGsAhead * kGsB) { const int pos = (blk + 1) * kGsB + tid; s_row[tid] = pos < np ? gpq[pos] : make_double4(0, 0, 0, 0); s_rm[tid] = pos < np ? gmeta[pos] : -1; }
+	__syncthreads();
+	double *out = near + (size_t)blk * kGsNearPerBlock;
+	for (int q = tid; q < kGsB * kGsAhead * kGsB; q += kGsPipeThreads) {
+		const int k = q / (kGsAhead * kGsB), jr = q % (kGsAhead * kGsB);          // jr = j * 64 + r
+		double xx = 0, xy = 0, xz = 0, yy = 0, yz = 0, zz = 0, t0 = 0, t1 = 0;
+		if (blk * kGsB + k < np && (blk + 1) * kGsB + jr < np) {
+			if (p.damp_type == 2) {
+				gs_contract<ORTHO, true>(c, p, s_row[jr], s_rm[jr], s_col[k], s_cm[k], make_double4(1, 0, 0, 0), xx, xy, xz);
+				gs_contract<ORTHO, true>(c, p, s_row[jr], s_rm[jr], s_col[k], s_cm[k], make_double4(0, 1, 0, 0), t0, yy, yz);
+				gs_contract<ORTHO, true>(c, p, s_row[jr], s_rm[jr], s_col[k], s_cm[k], make_double4(0, 0, 1, 0), t0, t1, zz);
+			} else {
+				gs_contract<ORTHO, false>(c, p, s_row[jr], s_rm[jr], s_col[k], s_cm[k], make_double4(1, 0, 0, 0), xx, xy, xz);
+				gs_contract<ORTHO, false>(c, p, s_row[jr], s_rm[jr], s_col[k], s_cm[k], make_double4(0, 1, 0, 0), t0, yy, yz);
+				gs_contract<ORTHO, false>(c, p, s_row[jr], s_rm[jr], s_col[k], s_cm[k], make_double4(0, 0, 1, 0), t0, t1, zz);
+			}
+		}
+		double2 *o = reinterpret_cast<double2 *>(out + (size_t)q * 6);
+		o[0] = make_double2(xx, yy); o[1] = make_double2(zz, xy); o[2] = make_double2(xz, yz);
 	}
 }
 
@@ -128,12 +222,13 @@ __device__ __forceinline__ void gs_updater_body(double *s_raw, int cta, int U, c
 		double4 *w_dm = w_col + kGsB;
 		// (warp-major numbering: when there are more chunks than warps, the second chunks go one to each CTA instead of eight to a
 		// few CTAs — an SM with twice the work falls behind by a few thousand cycles per panel and stalls the solver at the end)
-		const int GW = U * kGsWarps, gwid = warp * U + cta;
-		const int r = lane & 7, cl = lane >> 3;             // row of the chunk, column lane
+		const int GW = U * (int)(blockDim.x >> 5), gwid = warp * U + cta;
+		const int r = lane & (kGsRows - 1), cl = lane / kGsRows;   // row of the chunk, column lane
 		for (int blk = 0; blk < nblk; blk++) {
 			const int base = blk * kGsB, cnt = min(kGsB, np - base);
-			// the panel's own rows and the rows of the next kGsAhead blocks belong to the cluster
-			const int skip0 = blk * kChunksPerBlk, skip1 = min(blk + 1 + kGsAhead, nblk) * kChunksPerBlk;
+			// the rows of the next kGsAhead blocks belong to the cluster (the panel's own rows do not: the solver writes them back
+			// before it publishes the panel, without the panel's own contribution)
+			const int skip0 = (blk + 1) * kChunksPerBlk, skip1 = min(blk + 1 + kGsAhead, nblk) * kChunksPerBlk;
 			const int first = gwid;
 			bool any = false;
 			for (int ch = first; ch < nchunks; ch += GW) any = any || !(ch >= skip0 && ch < skip1);
@@ -177,7 +272,7 @@ __device__ __forceinline__ void gs_updater_body(double *s_raw, int cta, int U, c
 					double ax = 0, ay = 0, az = 0;
 					if (on) {
 #pragma unroll 4
-						for (int cc = cl; cc < cnt; cc += 4) {
+						for (int cc = cl; cc < cnt; cc += kGsColLanes) {
 							double4 pc = w_col[cc];
 							const double4 dm = w_dm[cc];
 							const int mc = __double2loint(pc.w);
@@ -185,6 +280,7 @@ __device__ __forceinline__ void gs_updater_body(double *s_raw, int cta, int U, c
 							gs_contract<ORTHO, EXPD>(c, p, pr, mr, pc, mc, dm, ax, ay, az);
 						}
 					}
+					ax += __shfl_xor_sync(0xffffffffu, ax, 4); ay += __shfl_xor_sync(0xffffffffu, ay, 4); az += __shfl_xor_sync(0xffffffffu, az, 4);
 					ax += __shfl_xor_sync(0xffffffffu, ax, 8); ay += __shfl_xor_sync(0xffffffffu, ay, 8); az += __shfl_xor_sync(0xffffffffu, az, 8);
 					ax += __shfl_xor_sync(0xffffffffu, ax, 16); ay += __shfl_xor_sync(0xffffffffu, ay, 16); az += __shfl_xor_sync(0xffffffffu, az, 16);
 					sx[w] = ax; sy[w] = ay; sz[w] = az;
@@ -208,13 +304,13 @@ __device__ __forceinline__ void gs_updater_body(double *s_raw, int cta, int U, c
 }
 
 // what the cluster shares: the solver's shared-memory words the helpers read (progress, dmu) and write (partial pushes, done)
-struct GsShared { int prog; int loaded; int folded; int pad; int done[4]; };
+struct GsShared { int prog; int loaded; int folded; int pad; int done[8]; };
 
 template <bool ORTHO, bool EXPD>
-__global__ void __cluster_dims__(kGsCluster, 1, 1) __launch_bounds__(kGsThreads, 1)
+__global__ void __cluster_dims__(kGsCluster, 1, 1) __launch_bounds__(kGsPipeThreads, 1)
 k_gs_pipeline(const double4 *__restrict__ gpq, const int *__restrict__ gmeta, const int *__restrict__ order, int np, CellDev c, PolarDev p,
               const double *__restrict__ efs, double *mu, double *efi, double *new_mu, double *acc, double *dmu,
-              const double *__restrict__ tri, GsCtl *ctl, long long *prof, volatile int *started, int token) {
+              const double *__restrict__ tri, const double *__restrict__ near, GsCtl *ctl, long long *prof, volatile int *started, int token) {
 	cg::cluster_group cluster = cg::this_cluster();
 	if (blockIdx.x == 0 && threadIdx.x == 0) { *started = token; __threadfence_system(); }   // tells the host that the cluster holds its SMs
 	extern __shared__ __align__(16) double s_raw[];
@@ -225,11 +321,13 @@ k_gs_pipeline(const double4 *__restrict__ gpq, const int *__restrict__ gmeta, co
 	constexpr int kChunksPerBlk = kGsB / kGsRows;
 	// the solver's layout (helpers address the shared part of it through the cluster)
 	double *s_mat = s_raw;                                         // [kGsB columns][kGsB rows][6], rolled: column k of the next block replaces column k once the walk has passed it
-	double *s_site = s_mat + kGsMat;                               // [kGsSiteCols][kGsB]
-	double *s_pendp = s_site + kGsSiteCols * kGsB;                 // [kGsHelpers][kGsAhead * kGsB][3] the helpers' pushes of the last panel
+	double *s_site0 = s_mat + kGsMat;                              // [2][kGsSiteCols][kGsB], buffer = block & 1
+	double *s_pendp = s_site0 + 2 * kGsSiteCols * kGsB;                 // [kGsHelpers][kGsAhead * kGsB][3] the helpers' pushes of the last panel
 	double *s_pend = s_pendp + kGsHelpers * (kGsAhead * kGsB * 3); // [kGsSlots][kGsB][3] pushes already made into the rows of blocks b .. b+kGsAhead (slot = block % kGsSlots)
 	double4 *s_dm = (double4 *)(s_pend + kGsSlots * 3 * kGsB);     // [kGsB] dmu of the block being walked
-	int *s_idx = (int *)(s_dm + kGsB);                             // [2][kGsB] site ids of this block / the next block
+	double4 *s_rhs = s_dm + kGsB;                                  // [kGsB] right-hand side of the block being walked
+	double *s_wpart = (double *)(s_rhs + kGsB);                    // [kGsN] second half of the walk's dot products
+	int *s_idx = (int *)(s_wpart + kGsN);                          // [2][kGsB] site ids of this block / the next block
 	GsShared *s_sh = (GsShared *)(s_idx + 2 * kGsB);
 
 	if (cta == 0) {
@@ -237,11 +335,13 @@ k_gs_pipeline(const double4 *__restrict__ gpq, const int *__restrict__ gmeta, co
 		volatile int *s_prog = &s_sh->prog;                        // blk * kGsB + columns of the walk that are final
 		volatile int *s_done = s_sh->done;                         // per helper: panels delivered
 		volatile int *s_folded = &s_sh->folded;                    // panels whose deliveries have been folded (their buffers are free again)
-		volatile int *s_loaded = &s_sh->loaded;                    // blocks whose site columns the walker has taken into registers
+		constexpr int kPublisherWarp = 12, kLoaderWarp = 13;       // warps 0..11 walk; 14, 15 only copy
+		volatile int *s_loaded = &s_sh->loaded;
 		auto load_cols = [&](int blk, int m) {                     // site id and site columns of row m (all but the running contraction)
 			const int pos = blk * kGsB + m;
 			const bool on = pos < np;
 			const int s = on ? order[pos] : 0;
+			double *s_site = s_site0 + (blk & 1) * kGsSiteCols * kGsB;
 			s_idx[(blk & 1) * kGsB + m] = s;
 			s_site[m] = on ? gpq[pos].w : 0.0;
 			for (int q = 0; q < 3; q++) {
@@ -252,34 +352,43 @@ k_gs_pipeline(const double4 *__restrict__ gpq, const int *__restrict__ gmeta, co
 		auto load_acc = [&](int blk, int m) {                      // running contraction of row m as the updaters left it
 			const bool on = blk * kGsB + m < np;
 			const int s = s_idx[(blk & 1) * kGsB + m];
+			double *s_site = s_site0 + (blk & 1) * kGsSiteCols * kGsB;
 			for (int q = 0; q < 3; q++) s_site[(7 + q) * kGsB + m] = on ? __ldcg(acc + 3 * s + q) : 0.0;
 		};
-		for (int q = tid; q < kGsSlots * 3 * kGsB; q += kGsThreads) s_pend[q] = 0.0;
+		// the helpers keep their sums in their own shared memory (same offset in every helper CTA); the solver pulls them
+		const double *h_out_of[kGsHelpers];
+#pragma unroll
+		for (int h = 0; h < kGsHelpers; h++) h_out_of[h] = cluster.map_shared_rank(s_raw + kGsHelperOutOffset, h + 1);
+		for (int q = tid; q < kGsSlots * 3 * kGsB; q += kGsPipeThreads) s_pend[q] = 0.0;
 		{
 			const double2 *src = (const double2 *)tri;
 			double2 *dst = (double2 *)s_mat;
-			for (int q = tid; q < kGsMat / 2; q += kGsThreads) __pipeline_memcpy_async(dst + q, src + q, sizeof(double2));
+			for (int q = tid; q < kGsMat / 2; q += kGsPipeThreads) __pipeline_memcpy_async(dst + q, src + q, sizeof(double2));
 			__pipeline_commit();
 		}
 		if (tid < kGsB) { load_cols(0, tid); load_acc(0, tid); }
-		if (tid == 0) { *s_prog = 0; *s_loaded = 0; *s_folded = 0; for (int h = 0; h < 4; h++) s_done[h] = 0; }
+		if (tid == 0) { *s_prog = 0; *s_loaded = 0; *s_folded = 0; for (int h = 0; h < 8; h++) s_done[h] = 0; }
 		cluster.sync();                                            // the helpers may look at prog / done from here on
 		for (int blk = 0; blk < nblk; blk++) {
 			const int base = blk * kGsB, cnt = min(kGsB, np - base);
-			if (prof && tid == 0) prof[blk * 8 + 0] = clock64();
+			double *s_site = s_site0 + (blk & 1) * kGsSiteCols * kGsB;
+			if (prof && tid == 0) prof[blk * 8 + 0] = clock_after(s_prog);
 			// (A) fold the helpers' pushes of the previous panel into the pending sums (fixed order), then the running contraction
 			//     of this block's rows = what the updaters left (fetched during the previous walk) + the cluster's own pushes
 			if (blk > 0) {
 				if (tid < kGsHelpers) while (s_done[tid] < blk) { }         // every helper has delivered panel blk-1
 				__syncthreads();
-				asm volatile("fence.acq_rel.cluster;" ::: "memory");
-				if (tid < kGsAhead * kGsB) {
-					const int j = tid / kGsB, row = tid % kGsB;         // target block blk + j
-					double *dst = s_pend + (((blk + j) % kGsSlots) * kGsB + row) * 3;
-					for (int q = 0; q < 3; q++) {
-						const double v = (s_pendp[(0 * kGsAhead * kGsB + tid) * 3 + q] + s_pendp[(1 * kGsAhead * kGsB + tid) * 3 + q]) + s_pendp[(2 * kGsAhead * kGsB + tid) * 3 + q];
-						dst[q] = (j < kGsAhead - 1 ? dst[q] : 0.0) + v;     // the farthest target starts here; the nearer ones already hold earlier panels
-					}
+				if (prof && tid == 0) prof[blk * 8 + 4] = clock_after(s_prog);
+				// the part of panel blk-1 that went into THIS block's rows (the rest is taken after the walk, off the critical path)
+				if (tid < kGsN) {
+					const int par = ((blk - 1) & 1) * (kGsAhead * kGsB * 3);
+					double pv[kGsHelpers];                              // all remote loads in flight at once
+#pragma unroll
+					for (int h = 0; h < kGsHelpers; h++) pv[h] = h_out_of[h][par + tid];
+					double v = pv[0];
+#pragma unroll
+					for (int h = 1; h < kGsHelpers; h++) v += pv[h];
+					s_pend[(blk % kGsSlots) * kGsB * 3 + tid] += v;
 				}
 			}
 			__pipeline_wait_prior(0);
@@ -288,209 +397,180 @@ k_gs_pipeline(const double4 *__restrict__ gpq, const int *__restrict__ gmeta, co
 			                                                               // no column in a short last block would otherwise run ahead)
 			if (tid < kGsB) for (int q = 0; q < 3; q++) s_site[(7 + q) * kGsB + tid] += s_pend[((blk % kGsSlots) * kGsB + tid) * 3 + q];
 			__syncthreads();
-			if (prof && tid == 0) prof[blk * 8 + 1] = clock64();
-			// (B)
-			if (warp == 0) {
-				// lane owns rows lane (slot 0) and lane+32 (slot 1); everything a row needs lives in registers during the walk.
-				// With c = alpha E_s - mu_old the change of a dipole is a single FMA:  dmu = c - alpha acc.
-				double al[2], cx[2], cy[2], cz[2], ax[2], ay[2], az[2], ex[2], ey[2], ez[2], sx[2], sy[2], sz[2];
-#pragma unroll
-				for (int h = 0; h < 2; h++) {
-					const int m = lane + 32 * h;
-					al[h] = s_site[m];
-					sx[h] = s_site[4 * kGsB + m]; sy[h] = s_site[5 * kGsB + m]; sz[h] = s_site[6 * kGsB + m];
-					cx[h] = al[h] * sx[h] - s_site[1 * kGsB + m];
-					cy[h] = al[h] * sy[h] - s_site[2 * kGsB + m];
-					cz[h] = al[h] * sz[h] - s_site[3 * kGsB + m];
-					ax[h] = s_site[7 * kGsB + m]; ay[h] = s_site[8 * kGsB + m]; az[h] = s_site[9 * kGsB + m];
-					ex[h] = ey[h] = ez[h] = 0;
-				}
-				__syncwarp();
-				if (lane == 0) { *s_prog = base; *s_loaded = blk + 1; }     // the site columns are in registers: warp 1 may refill them
-				// tensor entries of column k for my two rows: (xx yy) (zz xy) (xz yz); always one column ahead of the dependent chain.
-				// Two register sets used alternately (the loop is unrolled by hand: a copy would cost 24 moves per step on the
-				// one warp the whole sweep waits for).
-				const double2 *tcol = (const double2 *)s_mat + lane * 3;
-				double2 ta[2][3], tb[2][3];
-#pragma unroll
-				for (int hh = 0; hh < 2; hh++) { ta[hh][0] = tcol[hh * 96]; ta[hh][1] = tcol[hh * 96 + 1]; ta[hh][2] = tcol[hh * 96 + 2]; }
-				const unsigned tcol_s = (unsigned)__cvta_generic_to_shared(tcol);
-				auto step = [&](const int half, const int kk, double2 (&tc)[2][3], double2 (&tn)[2][3]) {
-					const int k = kk + 32 * half;
-					// every lane forms the candidate change of its own slot-`half` row; the owner's is the real one
-					const double dxc = fma(-al[half], ax[half], cx[half]), dyc = fma(-al[half], ay[half], cy[half]), dzc = fma(-al[half], az[half], cz[half]);
-					const double dx = __shfl_sync(0xffffffffu, dxc, kk), dy = __shfl_sync(0xffffffffu, dyc, kk), dz = __shfl_sync(0xffffffffu, dzc, kk);
-					if (lane == kk) { ex[half] = ax[half]; ey[half] = ay[half]; ez[half] = az[half]; }   // acc at the moment of the update
-					// hand the finished column to the other warps and CTAs.  No fence: both are volatile shared-memory stores of one
-					// thread, which the LSU performs in program order (a MEMBAR here costs more than the whole step); every lane
-					// stores the same values, so the walk has no divergent region
-					volatile double *vd = (volatile double *)(s_dm + k);
-					vd[0] = dx; vd[1] = dy; vd[2] = dz;
-					*s_prog = base + k + 1;
-					// the next column into the register set the previous step has finished with.  Volatile (ordered after the stores
-					// above) so that the compiler does not hoist these loads over the previous step's FMAs, which would cost it a third
-					// register set and 24 moves per step
-					const unsigned tnext = tcol_s + (unsigned)(min(k + 1, kGsB - 1) * (kGsB * 3) * sizeof(double2));
-#pragma unroll
-					for (int hh = 0; hh < 2; hh++)
-#pragma unroll
-						for (int q = 0; q < 3; q++)
-							asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(tn[hh][q].x), "=d"(tn[hh][q].y) : "r"(tnext + (unsigned)((hh * 96 + q) * sizeof(double2))));
-#pragma unroll
-					for (int hh = 0; hh < 2; hh++) {                      // the diagonal entry is zero: a row does not move itself
-						ax[hh] = fma(tc[hh][0].x, dx, fma(tc[hh][1].y, dy, fma(tc[hh][2].x, dz, ax[hh])));
-						ay[hh] = fma(tc[hh][1].y, dx, fma(tc[hh][0].y, dy, fma(tc[hh][2].y, dz, ay[hh])));
-						az[hh] = fma(tc[hh][2].x, dx, fma(tc[hh][2].y, dy, fma(tc[hh][1].x, dz, az[hh])));
-					}
-				};
-#pragma unroll
-				for (int half = 0; half < 2; half++) {
-					const int kend = min(32, cnt - 32 * half);
-					int kk = 0;
-					for (; kk + 1 < kend; kk += 2) { step(half, kk, ta, tb); step(half, kk + 1, tb, ta); }
-					if (kk < kend) step(half, kk, ta, tb);                    // an odd count: always the last step of the block
-				}
-				if (prof && tid == 0) prof[blk * 8 + 2] = clock64();
-				// contract_dipoles: ef_induced = -acc at the moment of the update, mu = alpha (E_s + ef_induced)  (:3583-3592)
-#pragma unroll
-				for (int hh = 0; hh < 2; hh++) {
-					const int m = lane + 32 * hh;
-					if (m < cnt) {
-						const int s = s_idx[(blk & 1) * kGsB + m];
-						const double nx = al[hh] * (sx[hh] - ex[hh]), ny = al[hh] * (sy[hh] - ey[hh]), nz = al[hh] * (sz[hh] - ez[hh]);
-						__stcg(mu + 3 * s, nx); __stcg(mu + 3 * s + 1, ny); __stcg(mu + 3 * s + 2, nz);
-						new_mu[3 * s] = nx; new_mu[3 * s + 1] = ny; new_mu[3 * s + 2] = nz;
-						efi[3 * s] = -ex[hh]; efi[3 * s + 1] = -ey[hh]; efi[3 * s + 2] = -ez[hh];
-						__stcg(acc + 3 * s, ax[hh]); __stcg(acc + 3 * s + 1, ay[hh]); __stcg(acc + 3 * s + 2, az[hh]);
-					}
-				}
-				asm volatile("bar.sync 1, 96;" ::: "memory");
-			} else if (warp == 1) {
-				// the next block: site columns (once the walker has taken its own into registers), tensors rolled in behind the walk
-				// (column k is dead once column k+1 has been fetched), running contraction once the updaters have delivered
+			if (prof && tid == 0) prof[blk * 8 + 1] = clock_after(s_prog);
+			if (warp == kLoaderWarp) {
+				// the NEXT block's site columns and running contraction, fetched while this block is walked (nothing of it depends
+				// on this walk: the rows' dipoles are still the old ones, and no updater touches these rows between panel
+				// blk-kGsAhead and the solver's own write-back).  This warp skips the walk's barriers and waits at the next block's.
 				if (blk + 1 < nblk) {
-					while (*s_loaded <= blk) __nanosleep(100);
 					load_cols(blk + 1, lane); load_cols(blk + 1, lane + 32);
-					// (no updater touches these rows between panel blk-kGsAhead and my own write-back: safe to fetch now)
-					const int c0 = (base + kGsB) / kGsRows, c1 = min(nchunks, c0 + kChunksPerBlk);
-					if (blk >= kGsAhead && lane < c1 - c0) {
-						int spins = 0;
-						while (ld_flag(applied + c0 + lane) < blk + 1 - kGsAhead && !ld_flag(&ctl->abort)) {
-							__nanosleep(100);
-							if (++spins > kGsWaitLimit) st_flag(&ctl->abort, 1);
+					// every lane acquires the flags of the two chunks its rows (lane, lane + 32) belong to: no fence — a MEMBAR in this
+					// warp stalls the shared-memory traffic of the walk next to it
+					const int c0 = (base + kGsB) / kGsRows;
+					if (blk >= kGsAhead) {
+#pragma unroll
+						for (int h = 0; h < 2; h++) {
+							const int ch = c0 + (lane + 32 * h) / kGsRows;
+							if (ch >= nchunks) continue;
+							int spins = 0;
+							while (ld_acquire(applied + ch) < blk + 1 - kGsAhead && !ld_flag(&ctl->abort)) {
+								__nanosleep(100);
+								if (++spins > kGsWaitLimit) st_flag(&ctl->abort, 1);
+							}
 						}
 					}
 					__syncwarp();
-					__threadfence();
 					load_acc(blk + 1, lane); load_acc(blk + 1, lane + 32);
-					const double2 *src = (const double2 *)(tri + (size_t)(blk + 1) * kGsMat);
-					double2 *dst = (double2 *)s_mat;
-					int done = 0;
-					while (done < kGsB && !(g_gs_debug & 4)) {
-						int pg = max(*s_prog - base, 0);
-						if (pg >= cnt) pg = kGsB;                               // the walk is over: the remaining (unused) columns too
-						if (pg <= done) { __nanosleep(200); continue; }
-						for (int q = done * (kGsB * 3) + lane; q < pg * (kGsB * 3); q += 32) __pipeline_memcpy_async(dst + q, src + q, sizeof(double2));
-						done = pg;
-					}
-					__pipeline_commit();
-					__pipeline_wait_prior(0);
 				}
-				asm volatile("bar.sync 1, 96;" ::: "memory");                   // walker + this warp + the publisher have what the next block needs
-			} else if (warp == 2) {
-				// publish the panel for the updaters: the change of every dipole of the block, then the flag
-				while (*s_prog < base + cnt) __nanosleep(100);
-				double d[2][3];
+				continue;
+			}
+			// (B) the walk: rhs = alpha E_s - mu_old - alpha acc, dmu = rhs + X rhs (k_gs_inverse), one row component per thread
+			double rhs_r = 0.0, al_r = 0.0, mo_r = 0.0, es_r = 0.0, a_r = 0.0;
+			const int wm = tid / 3, wq = tid - 3 * wm;                     // my site of the block and component (threads 0..191)
+			if (tid < kGsN) {
+				al_r = s_site[wm]; mo_r = s_site[(1 + wq) * kGsB + wm]; es_r = s_site[(4 + wq) * kGsB + wm]; a_r = s_site[(7 + wq) * kGsB + wm];
+				rhs_r = fma(-al_r, a_r, fma(al_r, es_r, -mo_r));
+				reinterpret_cast<double *>(s_rhs)[4 * wm + wq] = rhs_r;
+			}
+			asm volatile("bar.sync 1, %0;" :: "n"(kGsPipeThreads - 32) : "memory");
+			if (prof && tid == 0) prof[blk * 8 + 5] = clock_after(s_prog);
+			if (tid < 2 * kGsN) {
+				// two threads per row: column sites of one parity each
+				const int half = tid >= kGsN, r = tid - half * kGsN, rm = r / 3;
+				double d0 = half ? 0.0 : rhs_r, d1 = 0.0, d2 = 0.0;
+				// row r of column site j sits at gs_inv_off(j) + q rows(j) + r - 3 (j + 1)
+				const double *xj = s_mat + (r - 3) + (half ? 3 * (kGsN - 3) - 3 : 0);
+				int nr = kGsN - 3 - 3 * half;
+				if (prof && tid == 191) prof[blk * 8 + 3] = clock64();
+#pragma unroll 4
+				for (int j = half; j < rm; j += 2) {
+					const double4 rj = s_rhs[j];
+					d0 = fma(xj[0], rj.x, d0); d1 = fma(xj[nr], rj.y, d1); d2 = fma(xj[2 * nr], rj.z, d2);
+					xj += 6 * nr - 15; nr -= 6;
+				}
+				const double dh = d0 + (d1 + d2);
+				if (half) s_wpart[r] = dh; else rhs_r = dh;
+				if (prof && tid == 191) prof[blk * 8 + 6] = clock64();
+			}
+			asm volatile("bar.sync 1, %0;" :: "n"(kGsPipeThreads - 32) : "memory");
+			if (prof && tid == 0) prof[blk * 8 + 7] = clock_after(s_prog);
+			if (tid < kGsN) {
+				const double d = rhs_r + s_wpart[tid];
+				reinterpret_cast<volatile double *>(s_dm)[4 * wm + wq] = d;
+				// contract_dipoles: mu = alpha (E_s + ef_induced), ef_induced = -acc at the moment of the update  (:3583-3592):
+				// mu = mu_old + dmu; ef_induced is recovered from mu after the sweep (k_gs_efi)
+				if (wm < cnt) {
+					const int sidx = s_idx[(blk & 1) * kGsB + wm];
+					const double nm = mo_r + d;
+					__stcg(mu + 3 * sidx + wq, nm);
+					new_mu[3 * sidx + wq] = nm;
+					__stcg(acc + 3 * sidx + wq, a_r);                      // what the cluster knows of this row; the updaters add the panel itself
+				}
+			}
+			asm volatile("bar.sync 1, %0;" :: "n"(kGsPipeThreads - 32) : "memory");
+			if (tid == 0) *s_prog = base + cnt;                            // the helpers may take the panel
+			if (prof && tid == 0) prof[blk * 8 + 2] = clock_after(s_prog);
+			if (blk > 0 && tid < kGsN) {
+				// what panel blk-1 pushed into the rows of blocks blk+1 .. blk+3, while the helpers work on panel blk (they write the
+				// other half of their delivery buffer)
+				const int par = ((blk - 1) & 1) * (kGsAhead * kGsB * 3);
 #pragma unroll
-				for (int h = 0; h < 2; h++) {
-					const volatile double *vd = (const volatile double *)(s_dm + min(lane + 32 * h, kGsB - 1));
-					d[h][0] = vd[0]; d[h][1] = vd[1]; d[h][2] = vd[2];
+				for (int j = 1; j < kGsAhead; j++) {
+					double pv[kGsHelpers];
+#pragma unroll
+					for (int h = 0; h < kGsHelpers; h++) pv[h] = h_out_of[h][par + j * kGsB * 3 + tid];
+					double v = pv[0];
+#pragma unroll
+					for (int h = 1; h < kGsHelpers; h++) v += pv[h];
+					double *dst = s_pend + ((blk + j) % kGsSlots) * kGsB * 3 + tid;
+					*dst = (j < kGsAhead - 1 ? *dst : 0.0) + v;         // the farthest target starts here; the nearer ones already hold earlier panels
 				}
-				asm volatile("bar.sync 1, 96;" ::: "memory");                   // s_dm may be overwritten by the next walk from here on
+			}
+			if (warp == kPublisherWarp) {
+				// publish the panel for the updaters: the change of every dipole of the block, then the flag (after the write-back
+				// of the block's rows above: the updaters add this panel to those rows too)
 #pragma unroll
 				for (int h = 0; h < 2; h++) {
 					const int k = lane + 32 * h;
-					if (k < cnt) { __stcg(dmu + 3 * (base + k), d[h][0]); __stcg(dmu + 3 * (base + k) + 1, d[h][1]); __stcg(dmu + 3 * (base + k) + 2, d[h][2]); }
+					const double4 d = s_dm[min(k, kGsB - 1)];
+					if (k < cnt) { __stcg(dmu + 3 * (base + k), d.x); __stcg(dmu + 3 * (base + k) + 1, d.y); __stcg(dmu + 3 * (base + k) + 2, d.z); }
 				}
 				__threadfence();
 				__syncwarp();
 				if (lane == 0) st_flag(&ctl->solved, blk + 1);
+			} else if (blk + 1 < nblk && !(g_gs_debug & 4)) {
+				// the next block's inverse, asynchronous copies by every other warp (the matrix-vector product above is done with this one)
+				const double2 *src = (const double2 *)(tri + (size_t)(blk + 1) * kGsInv);
+				double2 *dst = (double2 *)s_mat;
+				for (int q = tid < kPublisherWarp * 32 ? tid : tid - 64; q < kGsInv / 2; q += kGsPipeThreads - 64) __pipeline_memcpy_async(dst + q, src + q, sizeof(double2));
+				__pipeline_commit();
 			}
-			if (prof && tid == 0) prof[blk * 8 + 3] = clock64();
 		}
 		__syncthreads();
 		cluster.sync();                                            // the helpers are done with my shared memory
 	} else if (cta < kGsCluster) {
 		// ------------------------------------------------ helpers -----------------------------------------------
-		// helper hj takes the columns k = hj mod 3 of every panel, for all rows of the next kGsAhead blocks
+		// a panel = 64 columns x the 64 rows of each of the next kGsAhead blocks.  Thread = (row r, target block j, column slice cs);
+		// helper hj's two slices are 2 hj and 2 hj + 1 of 2 kGsHelpers: at most 5 columns per thread, whose tensors (k_gs_near)
+		// are fetched into registers BEFORE the panel is ready — when the walk publishes it, 45 FMAs per thread remain
 		const int hj = cta - 1;
-		double4 *h_rows = (double4 *)s_raw;                        // [kGsSlots][kGsB] x y z alpha, slot = block % kGsSlots
-		int *h_meta = (int *)(h_rows + kGsSlots * kGsB);           // [kGsSlots][kGsB]
-		double *h_part = (double *)(h_meta + kGsSlots * kGsB);     // [4 column sub-slices][kGsAhead * kGsB][3]
+		double4 *h_dm = (double4 *)s_raw;                          // [kGsB] the panel's dipole changes
+		double *h_out = s_raw + kGsHelperOutOffset;                // [kGsAhead * kGsB][3] what this helper delivers: the solver reads it from here
+		double *h_part = h_out + 2 * kGsAhead * kGsB * 3;          // [2 column slices][kGsAhead * kGsB][3]   (h_out: two buffers, panel & 1)
 		const volatile int *r_prog = &cluster.map_shared_rank(s_sh, 0)->prog;
 		int *r_done = cluster.map_shared_rank(s_sh, 0)->done + hj;
 		const volatile int *r_folded = &cluster.map_shared_rank(s_sh, 0)->folded;
-		const volatile double *r_dm = (const volatile double *)cluster.map_shared_rank(s_dm, 0);
-		double *r_pendp = cluster.map_shared_rank(s_pendp, 0) + hj * (kGsAhead * kGsB * 3);
-		auto load_rows = [&](int blk) {
-			if (tid < kGsB) {
-				const int pos = blk * kGsB + tid;
-				const bool on = pos < np;
-				h_rows[(blk % kGsSlots) * kGsB + tid] = on ? gpq[pos] : make_double4(0, 0, 0, 0);
-				h_meta[(blk % kGsSlots) * kGsB + tid] = on ? gmeta[pos] : 0;
-			}
-		};
-		for (int b = 0; b < kGsAhead; b++) load_rows(b);
+		const double4 *r_dm = cluster.map_shared_rank(s_dm, 0);
 		cluster.sync();
-		const int r = tid & (kGsB - 1), s4 = tid >> 6;            // my row of each target block; my column sub-slice
+		const int r = tid & (kGsB - 1), j = (tid >> 6) & (kGsAhead - 1), cs = tid >> 8;
+		static_assert(kGsAhead == 4 && kGsPipeThreads == 2 * kGsAhead * kGsB, "thread = (row, target block, column slice)");
+		constexpr int kCols = (kGsB + 2 * kGsHelpers - 1) / (2 * kGsHelpers);   // 5
 		for (int blk = 0; blk < nblk; blk++) {
 			const int base = blk * kGsB, cnt = min(kGsB, np - base);
-			load_rows(blk + kGsAhead);
-			__syncthreads();
-			double4 pr[kGsAhead]; int mr[kGsAhead]; bool on[kGsAhead];
-			double ax[kGsAhead], ay[kGsAhead], az[kGsAhead];
+			const int tb = blk + 1 + j;
+			const bool on = tb < nblk && tb * kGsB + r < np;
+			double2 t[kCols][3];
 #pragma unroll
-			for (int j = 0; j < kGsAhead; j++) {
-				const int tb = blk + 1 + j;
-				pr[j] = h_rows[(tb % kGsSlots) * kGsB + r];
-				mr[j] = h_meta[(tb % kGsSlots) * kGsB + r];
-				on[j] = tb < nblk && tb * kGsB + r < np;
-				ax[j] = ay[j] = az[j] = 0.0;
-			}
-			for (int k = hj + kGsHelpers * s4; k < cnt; k += kGsHelpers * 4) {
-				if (lane == 0) {
-					// a column takes the walk ~180 cycles (~95 ns): sleep about as long as the columns still to come need, so that
-					// 24 helper warps do not keep reading the solver's shared memory while it walks
-					int pg;
-					while ((pg = *r_prog) < base + k + 1) __nanosleep(min(2000, 40 + 80 * (base + k - pg)));
+			for (int m = 0; m < kCols; m++) {
+				const int k = 2 * hj + cs + 2 * kGsHelpers * m;
+				t[m][0] = t[m][1] = t[m][2] = make_double2(0.0, 0.0);
+				if (on && k < cnt) {
+					const double2 *src = reinterpret_cast<const double2 *>(near + (size_t)blk * kGsNearPerBlock + ((size_t)(k * kGsAhead + j) * kGsB + r) * 6);
+					t[m][0] = __ldg(src); t[m][1] = __ldg(src + 1); t[m][2] = __ldg(src + 2);
 				}
-				__syncwarp();
-				const double4 dm = make_double4(r_dm[4 * k], r_dm[4 * k + 1], r_dm[4 * k + 2], 0.0);
-				const double4 pc = h_rows[(blk % kGsSlots) * kGsB + k];
-				const int mc = h_meta[(blk % kGsSlots) * kGsB + k];
-#pragma unroll
-				for (int j = 0; j < kGsAhead; j++)
-					if (on[j]) gs_contract<ORTHO, EXPD>(c, p, pr[j], mr[j], pc, mc, dm, ax[j], ay[j], az[j]);
 			}
-#pragma unroll
-			for (int j = 0; j < kGsAhead; j++) {
-				double *o = h_part + ((s4 * kGsAhead + j) * kGsB + r) * 3;
-				o[0] = ax[j]; o[1] = ay[j]; o[2] = az[j];
-			}
-			// my previous delivery must have been folded before its buffer is written again (true by construction whenever this
-			// helper had a column to wait for; not in a last block shorter than the number of helpers)
-			if (tid == 0) while (*r_folded < blk) __nanosleep(100);
+			// one thread watches the solver's progress word (the walk publishes the whole panel at once)
+			if (tid == 0) while (*r_prog < base + cnt) __nanosleep(64);
+			const bool hp = prof && hj == 0 && tid == 0;
+			if (hp) prof[(nblk + blk) * 8 + 4] = gtime();
 			__syncthreads();
-			// sub-slices summed in a fixed order, straight into the solver's shared memory
-			if (tid < kGsAhead * kGsB) {
-				for (int q = 0; q < 3; q++)
-					r_pendp[tid * 3 + q] = (h_part[((0 * kGsAhead * kGsB) + tid) * 3 + q] + h_part[((1 * kGsAhead * kGsB) + tid) * 3 + q]) +
-					                       (h_part[((2 * kGsAhead * kGsB) + tid) * 3 + q] + h_part[((3 * kGsAhead * kGsB) + tid) * 3 + q]);
+			if (tid < kGsB) h_dm[tid] = r_dm[tid];
+			__syncthreads();
+			if (hp) prof[(nblk + blk) * 8 + 5] = gtime();
+			double ax = 0.0, ay = 0.0, az = 0.0;
+#pragma unroll
+			for (int m = 0; m < kCols; m++) {
+				const double4 d = h_dm[min(2 * hj + cs + 2 * kGsHelpers * m, kGsB - 1)];      // (xx yy) (zz xy) (xz yz); zero tensor where there is no column
+				ax = fma(t[m][0].x, d.x, fma(t[m][1].y, d.y, fma(t[m][2].x, d.z, ax)));
+				ay = fma(t[m][1].y, d.x, fma(t[m][0].y, d.y, fma(t[m][2].y, d.z, ay)));
+				az = fma(t[m][2].x, d.x, fma(t[m][2].y, d.y, fma(t[m][1].x, d.z, az)));
 			}
-			asm volatile("fence.acq_rel.cluster;" ::: "memory");
+			{
+				double *o = h_part + ((cs * kGsAhead + j) * kGsB + r) * 3;
+				o[0] = ax; o[1] = ay; o[2] = az;
+			}
+			__syncthreads();
+			if (hp) prof[(nblk + blk) * 8 + 6] = gtime();
+			// the two slices summed in a fixed order; the sums stay HERE and only the flag travels: like the panel in the other
+			// direction, the reader comes to the data, which costs neither remote stores nor a cluster-wide fence (2 us per panel,
+			// measured).  h_out is rewritten only after the solver has published the next panel, i.e. after it has folded this one.
+			if (tid < kGsAhead * kGsB) {
+				for (int q = 0; q < 3; q++) h_out[(blk & 1) * (kGsAhead * kGsB * 3) + tid * 3 + q] = h_part[tid * 3 + q] + h_part[(kGsAhead * kGsB + tid) * 3 + q];
+			}
 			__syncthreads();
 			if (tid == 0) *(volatile int *)r_done = blk + 1;
-			// the solver folds these sums before it starts the next walk, and only then publishes columns of the next panel:
+			if (hp) prof[(nblk + blk) * 8 + 7] = gtime();
+			// the solver folds these sums before it starts the next walk, and only then publishes the next panel:
 			// r_pendp is free again by the time this helper writes it
 		}
 		cluster.sync();
@@ -504,11 +584,20 @@ k_gs_pipeline(const double4 *__restrict__ gpq, const int *__restrict__ gmeta, co
 // The updaters as their own kernel (2 CTAs per SM on every SM the solver's cluster leaves free — the solver needs a whole SM's shared
 // memory, the updaters need latency hiding), launched right after the solver kernel on a second stream.
 template <bool ORTHO, bool EXPD>
-__global__ void __launch_bounds__(kGsThreads, 2)
+__global__ void __launch_bounds__(kGsThreads, kGsUpdCtas)
 k_gs_updaters(const double4 *__restrict__ gpq, const int *__restrict__ gmeta, const int *__restrict__ order, int np, CellDev c, PolarDev p,
               double *acc, const double *dmu, GsCtl *ctl, long long *prof) {
 	extern __shared__ __align__(16) double s_raw[];
 	gs_updater_body<ORTHO, EXPD>(s_raw, blockIdx.x, gridDim.x, gpq, gmeta, order, np, c, p, acc, dmu, ctl, prof);
+}
+
+// ef_induced of the polarizable sites after a Gauss-Seidel sweep: mu = alpha (E_s + ef_induced)  =>  ef_induced = mu / alpha - E_s
+__global__ void k_gs_efi(const int *__restrict__ plist, int np, const double *__restrict__ mu, const double *__restrict__ alpha,
+                         const double *__restrict__ efs, double *__restrict__ efi) {
+	const int t = blockIdx.x * blockDim.x + threadIdx.x;
+	if (t >= np * 3) return;
+	const int i = plist[t / 3], o = 3 * i + t % 3;
+	efi[o] = mu[o] / alpha[i] - efs[o];
 }
 
 // Palmo after Gauss-Seidel: efic_i = -efi_i - acc_i for the polarizable sites (acc is the final running contraction)

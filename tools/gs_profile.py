@@ -28,7 +28,7 @@ for i, nme in enumerate(names):
 per_blk = np.diff(sol[:, 0])
 print("  block period             mean %8.0f cycles" % per_blk.mean())
 for b in (1, 2, 50, 100):
-    print(" blk", b, "solver", (sol[b, :7] - sol[b, 0]).tolist(), "next start", int(sol[b + 1, 0] - sol[b, 0]))
+    print(" blk", b, "solver clk", (sol[b, [0, 4, 1, 5, 3, 6, 7, 2]] - sol[b, 0]).tolist(), "(start, helpers in, fold done, rhs done, thread 191 matvec start, end, matvec barrier, walk end) next start", int(sol[b + 1, 0] - sol[b, 0]))
 per = np.diff(sol[:, 0])
 worst = np.argsort(per)[-5:][::-1]
 print("longest block periods:", [(int(b), int(per[b])) for b in worst], " total sweep cycles (first..last block start):", int(sol[nb - 1, 0] - sol[0, 0]))
@@ -37,3 +37,4 @@ ok = (u[:, 3] > 0) & (u[:, 0] > 0)
 du = np.diff(u[ok], axis=1)
 print("updater warp (cta %d warp 0): wait for panel %.0f, dmu load + compute %.0f, ordering wait + atomics + fence + flag %.0f cycles (mean over %d panels); its period %.0f" % (
     4, du[:, 0].mean(), du[:, 1].mean(), du[:, 2].mean(), ok.sum(), np.diff(u[ok][:, 0]).mean()))
+
