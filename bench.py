@@ -326,9 +326,9 @@ def run_ours(args):
         ach = flops / (ms_per_launch * 1e-3) / 1e12
         bytes_alg = BYTES_PER_SITE_SWEEP * s.n
         # dram__bytes_read.sum + dram__bytes_write.sum per launch from the `ncu --set full` capture of this command (profiles/r01b_ncu_summary.md)
-        ncu_traffic = {"gs_sweep": 29.47e6 + 0.5e3, "dipole_sweep": 0.61e6, "pair": 0.65e6}
+        ncu_traffic = {"gs_sweep": 133.2e6 + 5.3e6, "dipole_sweep": 0.61e6, "pair": 0.73e6}   # profiles/r01c_ncu_summary.md
         roof = {"kernel": dom, "bound": "fp64", "achieved": ach, "peak": peak_tflops, "unit": "TFLOP/s", "frac": ach / peak_tflops,
-                "traffic": ncu_traffic.get(dom), "traffic_note": "bytes per launch from the round's ncu capture (the Gauss-Seidel sweep reads its 28 MB of precomputed block tensors once); the roofline is the FP64 pipe, not HBM", "ms_per_launch": ms_per_launch, "launches_timed": cands[dom][1], "work_per_launch": work,
+                "traffic": ncu_traffic.get(dom), "traffic_note": "bytes per launch from the round's ncu capture (a Gauss-Seidel sweep streams its precomputed tensors once: 113 MB between each block and the 4 blocks after it + 21 MB of block inverses, 0.12 TB/s); the roofline is the FP64 pipe, not HBM", "ms_per_launch": ms_per_launch, "launches_timed": cands[dom][1], "work_per_launch": work,
                 "peak_source": "measured in this run: register-resident DFMA loop on all SMs (MEASURED_PEAKS.json has no FP64 entry)",
                 "share_of_step": cands[dom][0] / max(timing["energy_total"][0], 1e-9),
                 "hbm_view": {"algorithmic_bytes": bytes_alg, "achieved_gbs": bytes_alg / (ms_per_launch * 1e-3) / 1e9,

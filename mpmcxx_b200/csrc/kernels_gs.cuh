@@ -4,27 +4,30 @@
 // as it is computed, so site i sees the NEW dipoles of every site swept before it and the OLD dipoles of the rest: a dense
 // triangular solve with N sequential steps.  The engine keeps, for every polarizable site, the running contraction
 //       acc_i = sum_{j != i} T_ij mu_j(current)
-// so that a site's update is just  mu_i = alpha_i (E_s,i - acc_i),  and the change  dmu_i = mu_i(new) - mu_i(old)  is pushed
-// into every other row:  acc_m += T_mi dmu_i.  Sites are processed in blocks of kGsB = 64 in sweep order ("panels"):
-//   * the SOLVER CTA (block 0) owns the critical path and keeps its SM quiet: one warp walks a block (two rows per lane in
-//     registers, the block's tensor matrix in shared memory, tensor loads one column ahead of the dependent chain; ~135
-//     cycles per site on B200, see tools/ubench/walk_ubench.cu), a second warp rolls the next block's tensors into the columns
-//     the walk has left behind and fetches the next block's site columns, a third publishes the panel.
-//   * three HELPER CTAs share a thread-block cluster with the solver.  They read every finished column straight out of the
-//     solver's shared memory (distributed shared memory: no trip through L2, no flag round trip) and push it into the rows
-//     of the next kGsAhead = 3 blocks, then drop their sums into the solver's shared memory.  Those are the rows the walk
-//     needs next; doing them inside the cluster costs the critical path only the tail of the last few columns.
-//   * the UPDATER CTAs (every other SM) push each published panel into all remaining rows — 8 rows per warp, 4 column lanes
-//     per row, every warp on its own — in panel order, and flag each 8-row chunk when it has received a panel.  An updater
-//     has kGsAhead block periods (~20 us) to deliver, several times what a flag - fence - load - compute - fence - flag round
-//     trip across the chip takes (~10 us measured), so that latency never reaches the solver.
+// so that a site's update is  mu_i = alpha_i (E_s,i - acc_i),  and the change  dmu_i = mu_i(new) - mu_i(old)  is pushed
+// into every other row:  acc_m += T_mi dmu_i.  Sites are processed in blocks of kGsB = 64 in sweep order ("panels").
+// Everything that depends on geometry and sweep order only is computed ONCE per energy() and order, in parallel over blocks,
+// and reused by all sweeps: the inverse of each block's triangular system (k_gs_inverse) and the tensors between a block and
+// the kGsAhead blocks that follow it (k_gs_near).  One sweep is then:
+//   * the SOLVER CTA (rank 0 of an 8-CTA cluster) owns the critical path.  Per block: fold what the cluster pushed into the
+//     block's rows, form the right-hand side, one 192 x 192 triangular matrix-vector product (two threads per row, the matrix
+//     in shared memory), write mu and the rows' running contraction back, publish the panel of dipole changes.  A dedicated
+//     warp fetches the next block's site data during the walk, the others copy the next inverse into shared memory after it.
+//   * seven HELPER CTAs share the cluster.  They push each panel into the rows of the next kGsAhead = 4 blocks — the rows
+//     the solver needs before any updater could deliver: tensors prefetched into registers before the panel exists, the panel
+//     read from the solver's shared memory (distributed shared memory), 45 FMAs per thread, and the sums stay in the helper's
+//     own shared memory where the solver reads them: only flags travel, no remote stores, no cluster-wide fences (the first
+//     version's push + fence cost 2 us per panel).  The part for the very next block is folded before the walk, the rest after.
+//   * the UPDATER CTAs (every other SM, 4 per SM) push each published panel into all remaining rows, including the panel's own
+//     block — 4 rows per warp, 8 column lanes per row, every warp on its own, tensors on the fly — in panel order, and flag
+//     each 4-row chunk when it has received a panel.  An updater has kGsAhead block periods to deliver.
 //   * the solver may start block b when its rows have received panels 0..b-1-kGsAhead from the updaters; the later panels
 //     are the cluster's own pushes.
 // Every row receives its updates in a fixed order, so the result does not depend on timing.  Pushing panels into rows that
 // were already swept prepares acc for the next sweep, and after the last sweep acc_i is exactly the contraction
-// palmo_contraction() needs (:3602-3627), so Palmo costs no extra sweep.
+// palmo_contraction() needs (:3602-3627), so Palmo costs no extra sweep.  ef_induced follows from mu after the sweep (k_gs_efi).
 // One launch = one sweep; every CTA must be resident (the grid is sized from cudaOccupancyMaxActiveClusters), which makes the
-// flag waits safe.
+// flag waits safe.  What was tried on the way is in profiles/r01b_gs_pipeline.md.
 #pragma once
 #include <cuda_pipeline.h>
 #include "kernels_polar2.cuh"
@@ -50,7 +53,7 @@ constexpr int kGsSiteCols = 10;           // 0 alpha, 1-3 mu_old, 4-6 E_static, 
 constexpr int kGsAhead = 4;               // the cluster pushes a panel into this many following blocks itself; the updaters take the rest
 constexpr int kGsHelpers = 7, kGsCluster = 1 + kGsHelpers;
 constexpr int kGsSlots = kGsAhead + 1;    // ring of per-block buffers
-constexpr size_t kGsSolverDoubles = (size_t)kGsMat + 2 * kGsSiteCols * kGsB + kGsHelpers * (kGsAhead * kGsB * 3) + kGsSlots * 3 * kGsB + 4 * kGsB + 4 * kGsB + kGsN + 2 * kGsB + 16;
+constexpr size_t kGsSolverDoubles = (size_t)kGsMat + 2 * kGsSiteCols * kGsB + kGsSlots * 3 * kGsB + 4 * kGsB + 4 * kGsB + kGsN + 2 * kGsB + 16;
 constexpr size_t kGsUpdaterDoubles = (size_t)kGsWarps * 8 * kGsB;
 constexpr int kGsHelperOutOffset = 4 * kGsB;      // doubles: a helper's delivery buffer inside its shared memory (after h_dm)
 static_assert(kGsSolverDoubles >= (size_t)(kGsPipeThreads / 32) * 8 * kGsB, "the fused fallback runs the updaters inside the pipeline kernel");
@@ -318,12 +321,10 @@ k_gs_pipeline(const double4 *__restrict__ gpq, const int *__restrict__ gmeta, co
 	const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 	const int cta = blockIdx.x;
 	const int nblk = (np + kGsB - 1) / kGsB, nchunks = (np + kGsRows - 1) / kGsRows;
-	constexpr int kChunksPerBlk = kGsB / kGsRows;
 	// the solver's layout (helpers address the shared part of it through the cluster)
 	double *s_mat = s_raw;                                         // [kGsB columns][kGsB rows][6], rolled: column k of the next block replaces column k once the walk has passed it
 	double *s_site0 = s_mat + kGsMat;                              // [2][kGsSiteCols][kGsB], buffer = block & 1
-	double *s_pendp = s_site0 + 2 * kGsSiteCols * kGsB;                 // [kGsHelpers][kGsAhead * kGsB][3] the helpers' pushes of the last panel
-	double *s_pend = s_pendp + kGsHelpers * (kGsAhead * kGsB * 3); // [kGsSlots][kGsB][3] pushes already made into the rows of blocks b .. b+kGsAhead (slot = block % kGsSlots)
+	double *s_pend = s_site0 + 2 * kGsSiteCols * kGsB;             // [kGsSlots][kGsB][3] pushes already made into the rows of blocks b .. b+kGsAhead (slot = block % kGsSlots)
 	double4 *s_dm = (double4 *)(s_pend + kGsSlots * 3 * kGsB);     // [kGsB] dmu of the block being walked
 	double4 *s_rhs = s_dm + kGsB;                                  // [kGsB] right-hand side of the block being walked
 	double *s_wpart = (double *)(s_rhs + kGsB);                    // [kGsN] second half of the walk's dot products
@@ -334,9 +335,7 @@ k_gs_pipeline(const double4 *__restrict__ gpq, const int *__restrict__ gmeta, co
 		// ------------------------------------------------ solver ------------------------------------------------
 		volatile int *s_prog = &s_sh->prog;                        // blk * kGsB + columns of the walk that are final
 		volatile int *s_done = s_sh->done;                         // per helper: panels delivered
-		volatile int *s_folded = &s_sh->folded;                    // panels whose deliveries have been folded (their buffers are free again)
 		constexpr int kPublisherWarp = 12, kLoaderWarp = 13;       // warps 0..11 walk; 14, 15 only copy
-		volatile int *s_loaded = &s_sh->loaded;
 		auto load_cols = [&](int blk, int m) {                     // site id and site columns of row m (all but the running contraction)
 			const int pos = blk * kGsB + m;
 			const bool on = pos < np;
@@ -367,7 +366,7 @@ k_gs_pipeline(const double4 *__restrict__ gpq, const int *__restrict__ gmeta, co
 			__pipeline_commit();
 		}
 		if (tid < kGsB) { load_cols(0, tid); load_acc(0, tid); }
-		if (tid == 0) { *s_prog = 0; *s_loaded = 0; *s_folded = 0; for (int h = 0; h < 8; h++) s_done[h] = 0; }
+		if (tid == 0) { *s_prog = 0; for (int h = 0; h < 8; h++) s_done[h] = 0; }
 		cluster.sync();                                            // the helpers may look at prog / done from here on
 		for (int blk = 0; blk < nblk; blk++) {
 			const int base = blk * kGsB, cnt = min(kGsB, np - base);
@@ -393,8 +392,6 @@ k_gs_pipeline(const double4 *__restrict__ gpq, const int *__restrict__ gmeta, co
 			}
 			__pipeline_wait_prior(0);
 			__syncthreads();
-			if (tid == 0) *s_folded = blk;                                 // the helpers may overwrite their delivery buffers (a helper with
-			                                                               // no column in a short last block would otherwise run ahead)
 			if (tid < kGsB) for (int q = 0; q < 3; q++) s_site[(7 + q) * kGsB + tid] += s_pend[((blk % kGsSlots) * kGsB + tid) * 3 + q];
 			__syncthreads();
 			if (prof && tid == 0) prof[blk * 8 + 1] = clock_after(s_prog);
@@ -442,10 +439,12 @@ k_gs_pipeline(const double4 *__restrict__ gpq, const int *__restrict__ gmeta, co
 				const double *xj = s_mat + (r - 3) + (half ? 3 * (kGsN - 3) - 3 : 0);
 				int nr = kGsN - 3 - 3 * half;
 				if (prof && tid == 191) prof[blk * 8 + 3] = clock64();
+				// warp-uniform trip count (the rows of a warp span 11 sites), the surplus iterations predicated off
+				const int rmw = __shfl_sync(0xffffffffu, rm, 31);
 #pragma unroll 4
-				for (int j = half; j < rm; j += 2) {
+				for (int j = half; j < rmw; j += 2) {
 					const double4 rj = s_rhs[j];
-					d0 = fma(xj[0], rj.x, d0); d1 = fma(xj[nr], rj.y, d1); d2 = fma(xj[2 * nr], rj.z, d2);
+					if (j < rm) { d0 = fma(xj[0], rj.x, d0); d1 = fma(xj[nr], rj.y, d1); d2 = fma(xj[2 * nr], rj.z, d2); }
 					xj += 6 * nr - 15; nr -= 6;
 				}
 				const double dh = d0 + (d1 + d2);
@@ -519,7 +518,6 @@ k_gs_pipeline(const double4 *__restrict__ gpq, const int *__restrict__ gmeta, co
 		double *h_part = h_out + 2 * kGsAhead * kGsB * 3;          // [2 column slices][kGsAhead * kGsB][3]   (h_out: two buffers, panel & 1)
 		const volatile int *r_prog = &cluster.map_shared_rank(s_sh, 0)->prog;
 		int *r_done = cluster.map_shared_rank(s_sh, 0)->done + hj;
-		const volatile int *r_folded = &cluster.map_shared_rank(s_sh, 0)->folded;
 		const double4 *r_dm = cluster.map_shared_rank(s_dm, 0);
 		cluster.sync();
 		const int r = tid & (kGsB - 1), j = (tid >> 6) & (kGsAhead - 1), cs = tid >> 8;
