@@ -47,8 +47,8 @@ __host__ __device__ constexpr int gs_inv_rows(int j) { return kGsN - 3 * (j + 1)
 __host__ __device__ constexpr int gs_inv_off(int j) { return 3 * (kGsN - 3) * j - 9 * (j * (j - 1) / 2); }
 constexpr int kGsMat = kGsInv;            // doubles of the solver's matrix buffer
 
-// shared memory (doubles).  Solver: the block's tensor matrix, two site-column buffers, pending push (3 slices + sum), two row
-// buffers, panel dmu, the walk's results, ints.  Updaters: per warp the panel's columns and dmu.
+// shared memory (doubles).  Solver: the block's inverse, two site-column buffers, the pending pushes of the next blocks, panel dmu,
+// right-hand side, second halves of the dot products, site ids.  Updaters: per warp the panel's columns and dmu.
 constexpr int kGsSiteCols = 10;           // 0 alpha, 1-3 mu_old, 4-6 E_static, 7-9 acc
 constexpr int kGsAhead = 4;               // the cluster pushes a panel into this many following blocks itself; the updaters take the rest
 constexpr int kGsHelpers = 7, kGsCluster = 1 + kGsHelpers;
@@ -568,8 +568,6 @@ k_gs_pipeline(const double4 *__restrict__ gpq, const int *__restrict__ gmeta, co
 			__syncthreads();
 			if (tid == 0) *(volatile int *)r_done = blk + 1;
 			if (hp) prof[(nblk + blk) * 8 + 7] = gtime();
-			// the solver folds these sums before it starts the next walk, and only then publishes the next panel:
-			// r_pendp is free again by the time this helper writes it
 		}
 		cluster.sync();
 	} else {

@@ -5,10 +5,10 @@
 // scheduler issues nothing else: cost of a pair ~ 2 x FP64 instructions + other instructions, tools/ubench/fp64_ubench.cu and the
 // instruction counts of the ncu source page).  So the kernel is built to issue as few instructions per pair as the reference's
 // semantics allow:
-//   * geometry.  The pair energies need r^2 only.  In an orthorhombic cell the sites are folded into the cell while they are staged
-//     (once per site and chunk, not per pair; into the cell centred on the origin), after which |d_img| = L/2 - | |dx| - L/2 | per axis: 3 adds per axis with the absolute
-//     values as operand modifiers, 12 FP64 instructions per pair with the sum of squares (the rint form needs 15).  A triclinic cell
-//     keeps the general FMA form.
+//   * geometry.  The pair energies need r^2 only.  In an orthorhombic cell the sites are folded into the cell centred on the origin
+//     while they are staged (once per site and chunk, not per pair), after which |d_img| = L/2 - | |dx| - L/2 | per axis: 3 adds per
+//     axis with the absolute values as operand modifiers, 12 FP64 instructions per pair with the sum of squares (the rint form needs
+//     15).  A triclinic cell keeps the general FMA form.
 //   * the reference's cutoff tests act on the last bit of rimg = sqrt(r^2) computed WITHOUT FMA; sqrt and the subtraction of 1e-12 are
 //     monotone, so each test is equivalent to r2_exact <= T for a double T the host finds by bisection (prepare_pair_sweep()).  The
 //     fast r^2 differs from the exact one by < 1e-13 relative, and the tests are done on the HIGH WORD of r^2 with integer compares

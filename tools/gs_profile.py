@@ -1,5 +1,6 @@
-"""Developer tool: where does a Gauss-Seidel sweep spend its time?  Prints per-block SM-clock deltas of the solver CTA and
-of updater CTA 1 for the first sweep of one energy() on config 4 (run on the GPU box)."""
+"""Developer tool: where does a Gauss-Seidel sweep spend its time?  Prints per-block SM-clock stamps of the solver CTA (start,
+helpers delivered, fold done, right-hand side done, matrix-vector product of thread 191 start / end, barrier after it, panel
+published) and the phases of one updater warp for the first sweep of one energy() on config 4 (run on the GPU box)."""
 import ctypes as C
 import sys, os
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
@@ -20,11 +21,12 @@ L.mpmc_debug_gs_profile(e.h, 0 | DBG, buf.ctypes.data_as(C.c_void_p), MAXB, C.by
 nb = nb.value
 sol = buf[:8 * MAXB].reshape(MAXB, 8)[:nb]
 upd = buf[8 * MAXB:].reshape(MAXB, 8)[:nb]
-names = ["flag wait + acc load", "walk (pushes overlap)", "write-back + push tail", "pending sum"]
-d = np.diff(np.concatenate([sol[:, :4], np.concatenate([sol[1:, :1], sol[-1:, 3:4]])], axis=1), axis=1)
-print("solver: cycles per phase, mean over %d blocks (SM clock ~1.9 GHz)" % nb)
-for i, nme in enumerate(names):
-    print("  %-24s mean %8.0f  median %8.0f  max %8.0f" % (nme, d[:-1, i].mean(), np.median(d[:-1, i]), d[:-1, i].max()))
+cols = [0, 4, 1, 5, 3, 6, 7, 2]
+labels = ["start", "helpers in", "fold done", "rhs done", "matvec start (thread 191)", "matvec end (thread 191)", "matvec barrier", "panel published"]
+rel = (sol[1:-1][:, cols] - sol[1:-1, :1]).astype(np.float64)
+print("solver: SM-clock cycles after the start of the block, median over %d blocks (~1.9 GHz)" % (nb - 2))
+for i, nme in enumerate(labels):
+    print("  %-28s %8.0f" % (nme, np.median(rel[:, i])))
 per_blk = np.diff(sol[:, 0])
 print("  block period             mean %8.0f cycles" % per_blk.mean())
 for b in (1, 2, 50, 100):
