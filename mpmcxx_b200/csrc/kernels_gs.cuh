@@ -153,12 +153,18 @@ k_gs_inverse(const double4 *__restrict__ gpq, const int *__restrict__ gmeta, int
 			double x0 = q == 0 ? -l[0] : q == 1 ? -l[3] : -l[4];
 			double x1 = q == 0 ? -l[3] : q == 1 ? -l[1] : -l[5];
 			double x2 = q == 0 ? -l[4] : q == 1 ? -l[5] : -l[2];
+			// (unrolled so that the shared-memory loads of four steps are in flight together: with 6 warps on the SM nothing else
+			// hides their latency; the order of the operations of each sum is unchanged)
+			const double *w = s_w + row_off(3 * (jc + 1)) + tid;          // rows 3j, 3j+1, 3j+2 of site j are 3j doubles apart
+#pragma unroll 4
 			for (int j = jc + 1; j < i; j++) {
-				const double v0 = s_w[row_off(3 * j) + tid], v1 = s_w[row_off(3 * j + 1) + tid], v2 = s_w[row_off(3 * j + 2) + tid];
-				const double *m = s_L + 6 * j;
-				x0 = fma(-m[0], v0, fma(-m[3], v1, fma(-m[4], v2, x0)));
-				x1 = fma(-m[3], v0, fma(-m[1], v1, fma(-m[5], v2, x1)));
-				x2 = fma(-m[4], v0, fma(-m[5], v1, fma(-m[2], v2, x2)));
+				const double v0 = w[0], v1 = w[3 * j], v2 = w[6 * j];
+				const double2 *m = reinterpret_cast<const double2 *>(s_L + 6 * j);   // (xx yy) (zz xy) (xz yz)
+				const double2 m01 = m[0], m23 = m[1], m45 = m[2];
+				x0 = fma(-m01.x, v0, fma(-m23.y, v1, fma(-m45.x, v2, x0)));
+				x1 = fma(-m23.y, v0, fma(-m01.y, v1, fma(-m45.y, v2, x1)));
+				x2 = fma(-m45.x, v0, fma(-m45.y, v1, fma(-m23.x, v2, x2)));
+				w += 9 * j;
 			}
 			s_w[row_off(3 * i) + tid] = x0; s_w[row_off(3 * i + 1) + tid] = x1; s_w[row_off(3 * i + 2) + tid] = x2;
 		}
