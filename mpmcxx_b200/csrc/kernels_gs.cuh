@@ -445,13 +445,26 @@ k_gs_pipeline(const double4 *__restrict__ gpq, const int *__restrict__ gmeta, co
 				const double *xj = s_mat + (r - 3) + (half ? 3 * (kGsN - 3) - 3 : 0);
 				int nr = kGsN - 3 - 3 * half;
 				if (prof && tid == 191) prof[blk * 8 + 3] = clock64();
-				// warp-uniform trip count (the rows of a warp span 11 sites), the surplus iterations predicated off
+				// warp-uniform trip count (the rows of a warp span 11 sites), four column sites per trip: all their loads first, then
+				// the FMAs, no branch inside — a surplus step (column site past the row's own) reads valid entries and a zeroed
+				// right-hand side.  (With a branch per step the loads of a step waited for the FMAs of the one before: 115 cycles each.)
 				const int rmw = __shfl_sync(0xffffffffu, rm, 31);
-#pragma unroll 4
-				for (int j = half; j < rmw; j += 2) {
-					const double4 rj = s_rhs[j];
-					if (j < rm) { d0 = fma(xj[0], rj.x, d0); d1 = fma(xj[nr], rj.y, d1); d2 = fma(xj[2 * nr], rj.z, d2); }
-					xj += 6 * nr - 15; nr -= 6;
+				for (int j = half; j < rmw; j += 8) {
+					double xa[4][3];
+					double4 ra[4];
+#pragma unroll
+					for (int u = 0; u < 4; u++) {
+						const int ju = j + 2 * u;
+						const bool ok = ju < rm;
+						const double *xp = ok ? xj : s_mat;
+						const int n1 = ok ? nr : 0;
+						xa[u][0] = xp[0]; xa[u][1] = xp[n1]; xa[u][2] = xp[2 * n1];
+						const double4 rj = s_rhs[min(ju, kGsB - 1)];
+						ra[u] = ok ? rj : make_double4(0.0, 0.0, 0.0, 0.0);
+						xj += 6 * nr - 15; nr -= 6;
+					}
+#pragma unroll
+					for (int u = 0; u < 4; u++) { d0 = fma(xa[u][0], ra[u].x, d0); d1 = fma(xa[u][1], ra[u].y, d1); d2 = fma(xa[u][2], ra[u].z, d2); }
 				}
 				const double dh = d0 + (d1 + d2);
 				if (half) s_wpart[r] = dh; else rhs_r = dh;
