@@ -252,7 +252,7 @@ __device__ __forceinline__ void gs_updater_body(double *s_raw, int cta, int U, c
 			if (lane == 0) {
 				int spins = 0;
 				while (ld_flag(&ctl->solved) <= blk && !ld_flag(&ctl->abort)) {
-					__nanosleep(32);
+					__nanosleep(256);          // ~2300 warps watch this word: short sleeps saturate its L2 slice (the flags live next to it)
 					if (++spins > 3 * kGsWaitLimit) st_flag(&ctl->abort, 1);
 				}
 			}
