@@ -51,4 +51,30 @@ int mpmc_host_energy(const char *input_file, double *out) {
 	return 0;
 }
 
+// What the mirror's readers make of an input file + PQR, without any device work: the flat site table in list order (the
+// engine's upload layout, System::flatten) and the cell.  cell[22] = basis (9), reciprocal basis (9), volume, cutoff, ewald alpha,
+// polar ewald alpha.  For pi_nvt (P > 0) the first bead system is described.  *n = number of sites; arrays hold `capacity` sites.
+int mpmc_host_describe(const char *input_file, int P, int capacity, int *n, double *pos, double *q, double *alpha, double *eps, double *sigma,
+                       double *mass, int *mol, int *frozen, double *cell) {
+	try {
+		SimulationControl sc(input_file, P);
+		sc.initializeSimulationObjects();
+		const System &s = sc.systems.empty() ? sc.sys : *sc.systems[0];
+		std::vector<double> vp, vq, va, ve, vs, vm;
+		std::vector<int> vmol, vfz;
+		s.flatten(vp, vq, va, ve, vs, vm, vmol, vfz);
+		*n = (int)vq.size();
+		if (*n > capacity) return invalid_input;
+		memcpy(pos, vp.data(), vp.size() * sizeof(double)); memcpy(q, vq.data(), vq.size() * sizeof(double));
+		memcpy(alpha, va.data(), va.size() * sizeof(double)); memcpy(eps, ve.data(), ve.size() * sizeof(double));
+		memcpy(sigma, vs.data(), vs.size() * sizeof(double)); memcpy(mass, vm.data(), vm.size() * sizeof(double));
+		memcpy(mol, vmol.data(), vmol.size() * sizeof(int)); memcpy(frozen, vfz.data(), vfz.size() * sizeof(int));
+		for (int i = 0; i < 3; i++) for (int j = 0; j < 3; j++) { cell[3 * i + j] = s.pbc.basis[i][j]; cell[9 + 3 * i + j] = s.pbc.reciprocal_basis[i][j]; }
+		cell[18] = s.pbc.volume; cell[19] = s.pbc.cutoff; cell[20] = s.ewald_alpha; cell[21] = s.polar_ewald_alpha;
+	} catch (int e) {
+		return e ? e : internal_error;
+	}
+	return 0;
+}
+
 } // extern "C"

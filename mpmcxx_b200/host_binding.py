@@ -18,6 +18,7 @@ def lib():
         L = C.CDLL(path)
         L.mpmc_host_run.argtypes = [C.c_char_p, C.c_int, C.c_int, C.c_void_p, C.c_int, C.POINTER(C.c_int), C.c_void_p]
         L.mpmc_host_energy.argtypes = [C.c_char_p, C.c_void_p]
+        L.mpmc_host_describe.argtypes = [C.c_char_p, C.c_int, C.c_int, C.POINTER(C.c_int)] + [C.c_void_p] * 9
         _lib = L
     return _lib
 
@@ -50,3 +51,23 @@ def energy(input_file: str):
     if rc:
         raise RuntimeError("host energy failed with code %d" % rc)
     return dict(energy=out[0], rd=out[1], coulombic=out[2], polar=out[3], iterations=int(out[4]))
+
+
+def describe(input_file: str, P: int = 0, capacity: int = 200000):
+    """What the mirror's readers make of an input file + PQR (no GPU needed): the flat site table and the cell."""
+    pos = np.zeros(3 * capacity); q = np.zeros(capacity); al = np.zeros(capacity); ep = np.zeros(capacity); sg = np.zeros(capacity)
+    ms = np.zeros(capacity); mol = np.zeros(capacity, np.int32); fz = np.zeros(capacity, np.int32); cell = np.zeros(22)
+    n = C.c_int()
+    cwd = os.getcwd()
+    os.chdir(os.path.dirname(os.path.abspath(input_file)))
+    try:
+        rc = lib().mpmc_host_describe(os.path.basename(input_file).encode(), P, capacity, C.byref(n),
+                                      *[a.ctypes.data_as(C.c_void_p) for a in (pos, q, al, ep, sg, ms, mol, fz, cell)])
+    finally:
+        os.chdir(cwd)
+    if rc:
+        raise RuntimeError("host describe failed with code %d" % rc)
+    k = n.value
+    return dict(pos=pos[:3 * k].reshape(k, 3).copy(), charge=q[:k].copy(), alpha=al[:k].copy(), eps=ep[:k].copy(), sigma=sg[:k].copy(),
+                mass=ms[:k].copy(), mol=mol[:k].copy(), frozen=fz[:k].copy(), basis=cell[:9].reshape(3, 3).copy(),
+                recip=cell[9:18].reshape(3, 3).copy(), volume=cell[18], cutoff=cell[19], ewald_alpha=cell[20], polar_ewald_alpha=cell[21])

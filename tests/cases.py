@@ -90,6 +90,16 @@ TRAJ = {
 }
 
 
+# jobs whose parse (input file + PQR -> flat site table + cell) is pinned against the reference's own readers: (builder, Trotter number)
+PARSED = {
+    "lj_lattice_4": (lambda: W.lj_lattice(4, 20.0), 0),
+    "tri_gs_ranked_palmo": (lambda: W.triclinic_mix(solver=W.SOLVER_GS_RANKED_PALMO), 0),
+    "h2fw_6_jacobi10": (lambda: W.h2_framework(ncell=6, n_h2=20, solver=W.SOLVER_JACOBI10, ensemble="nvt"), 0),
+    "tri_alpha_set": (lambda: _with(W.triclinic_mix(), ewald_alpha="0.31", polar_ewald_alpha="0.27", ewald_kmax="5"), 0),
+    "pi_h2_five_8x4": (lambda: W.pi_h2_cluster(n_side=2, P=4, L=30.0, five_site=True)[0], 4),
+}
+
+
 def displaced(s, seed=99):
     """Move the last mobile molecule rigidly (a displace move, System.MonteCarlo.cpp:875) — deterministic."""
     rs = np.random.RandomState(seed)

@@ -64,6 +64,23 @@ def main(only=None):
         print("%-22s P=%d n=%4d  U=%.15g  K=%.15g" % (name, P, tmpl.n, e["potential"], e["kinetic"]))
 
 
+def parsed():
+    """What the reference's own readers (input file + PQR) make of a job: the flat site table and the cell, with the job's text —
+    the CPU-side yardstick for the host mirror's readers (tests/test_host_cpu.py)."""
+    import tempfile
+    from mpmcxx_b200 import workloads
+    for name, (build, P) in cases.PARSED.items():
+        s = build()
+        with tempfile.TemporaryDirectory(prefix="mref_parsed_") as d:
+            r = ref.RefSystem(s, P=P, workdir=d)
+            out = {"input_in": np.array(open(os.path.join(d, "input.in")).read()), "input_pqr": np.array(open(os.path.join(d, "input.pqr")).read()),
+                   "P": np.int32(P)}
+            out.update({"ref_" + k: v for k, v in r.sites(0 if P else -1).items()})
+            out.update({"cell_" + k: v for k, v in r.cell(0 if P else -1).items()})
+        np.savez_compressed(os.path.join(HERE, "parsed_" + name + ".npz"), **out)
+        print("parsed_%-20s n=%d" % (name, len(out["ref_charge"])))
+
+
 def one_trajectory(name):
     build, P, steps = cases.TRAJ[name]
     s = build()
@@ -89,6 +106,9 @@ if __name__ == "__main__":
     if len(sys.argv) > 2 and sys.argv[1] == "traj1":
         one_trajectory(sys.argv[2])
         sys.exit(0)
+    if len(sys.argv) > 1 and sys.argv[1] == "parsed":
+        parsed()
+        sys.exit(0)
     if len(sys.argv) > 1 and sys.argv[1] == "traj":
         trajectories()
         sys.exit(0)
@@ -96,4 +116,5 @@ if __name__ == "__main__":
         main(set(sys.argv[2:]))
         sys.exit(0)
     main()
+    parsed()
     trajectories()
