@@ -1,0 +1,71 @@
+"""Trajectory parity of the C++ host mirror WITHOUT a GPU: the mirror's Monte Carlo drivers (System::mc, SimulationControl::PI_nvt_mc:
+move generation, RNG order, Boltzmann factors, accept/reject, restore, uVT insert/remove, bead moves) linked against a test-only
+shim that answers the engine's C-ABI from the CPU oracle (tests/shim/oracle_engine.c), compared with the reference's golden
+trajectories step by step.  The GPU tests (tests/test_gpu_trajectory.py) run the same drivers over the real engine."""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from mpmcxx_b200 import workloads as W
+from tests import cases
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+HOST = os.path.join(ROOT, "mpmcxx_b200", "host")
+
+
+@pytest.fixture(scope="module")
+def host_cpu(tmp_path_factory):
+    d = str(tmp_path_factory.mktemp("host_cpu"))
+    inc = ["-I" + os.path.join(ROOT, "include"), "-I" + os.path.join(ROOT, "oracle")]
+    cflags = ["-O2", "-std=c11", "-fPIC", "-fopenmp", "-ffp-contract=off"]
+    subprocess.run(["gcc"] + cflags + inc + ["-c", os.path.join(ROOT, "oracle", "oracle.c"), "-o", os.path.join(d, "oracle.o")], check=True)
+    subprocess.run(["gcc"] + cflags + inc + ["-c", os.path.join(ROOT, "tests", "shim", "oracle_engine.c"), "-o", os.path.join(d, "shim.o")], check=True)
+    lib = os.path.join(d, "libmpmc_host_cpu.so")
+    srcs = [os.path.join(HOST, f) for f in ("host.cpp", "sim_control.cpp", "host_capi.cpp")]
+    subprocess.run(["g++", "-O2", "-std=c++17", "-ffp-contract=off", "-fPIC", "-shared", "-fopenmp"] + inc + ["-o", lib] + srcs +
+                   [os.path.join(d, "shim.o"), os.path.join(d, "oracle.o"), "-lm"], check=True)
+    L = C.CDLL(lib)
+    L.mpmc_host_run.argtypes = [C.c_char_p, C.c_int, C.c_int, C.c_void_p, C.c_int, C.POINTER(C.c_int), C.c_void_p]
+    return L
+
+
+def _run(L, inp, P, steps):
+    log = np.zeros((steps, 5))
+    summary = np.zeros(8)
+    n = C.c_int()
+    cwd = os.getcwd()
+    os.chdir(os.path.dirname(inp))
+    try:
+        rc = L.mpmc_host_run(os.path.basename(inp).encode(), P, steps, log.ctypes.data_as(C.c_void_p), steps, C.byref(n), summary.ctypes.data_as(C.c_void_p))
+    finally:
+        os.chdir(cwd)
+    assert rc == 0, rc
+    return log[: n.value], summary
+
+
+# steps replayed on the CPU (the oracle is O(N^2) per energy): enough to go through every move type many times
+STEPS = {"traj_nvt_lj216": 3000, "traj_nvt_kat_gs_ranked": 1500, "traj_uvt_pore": 1500, "traj_pi_argon_dimer": 10000, "traj_pi_h2_27x8": 3000}
+
+
+@pytest.mark.parametrize("name", sorted(cases.TRAJ))
+def test_host_drivers_reproduce_reference_trajectory_on_cpu(host_cpu, name, tmp_path):
+    s, r = cases.load_golden_traj(name)
+    P = int(r["P"])
+    ref = r["traj"][: STEPS[name]]
+    inp = W.write_reference_job(s, str(tmp_path))
+    log, summary = _run(host_cpu, inp, P, len(ref))
+    assert len(log) == len(ref)
+    same = (log[:, 0] == ref[:, 0]) & (log[:, 3] == ref[:, 3])
+    first_bad = -1 if same.all() else int(np.argmin(same))
+    assert first_bad == -1, "trajectory diverges at step %d: ours %s reference %s" % (first_bad, log[first_bad], ref[first_bad])
+    fin = np.isfinite(ref[:, 1]) & (np.abs(ref[:, 1]) < 1e30)
+    scale = np.maximum(np.abs(ref[fin, 1]), 1.0)
+    tol = 1e-10 if s.opts.get("polarization") != "on" else 5e-8     # the classic total cancels ~1e5 K of Ewald sub-terms
+    assert (np.abs(log[fin, 1] - ref[fin, 1]) / scale).max() < tol
+    assert (np.abs(log[:, 2] - ref[:, 2]) / np.maximum(np.abs(ref[:, 2]), 1e-300) < 1e-6).all()
+    assert summary[6] == ref[:, 3].sum() and summary[7] == len(ref) - ref[:, 3].sum()
+    if P:
+        assert np.allclose(log[:, 4], ref[:, 4], rtol=1e-10, atol=0)
