@@ -481,7 +481,7 @@ def run_pi(args, embedded=False):
     ach = flop / (kms * 1e-3) / 1e12 if kms > 0 else float("nan")
     res = {"metric": "mc_moves_per_sec", "value": args.steps / t_dev, "unit": "moves/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
            "ms_per_step": 1e3 * t_dev / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-           "config": {"workload": "config5: path-integral H2 cluster, 512 molecules x %d beads, %s, beads sharded %d per GPU, one NCCL all-reduce of 4 doubles per sweep"
+           "config": {"workload": "config5: path-integral H2 cluster, 512 molecules x %d beads, %s, beads sharded %d per GPU, one all-reduce of 4 doubles per sweep (see `collective`)"
                                   % (P, "five-site H2 + Ewald (N=2560 per bead)" if five else "single-site H2, rd_only (N=512 per bead)", hi - lo),
                       "l2": "inputs are < 1 MB per rank and L2-resident by nature; no flush (latency-bound path)", "pair_evals_per_sweep": pairs_per_sweep,
                       "collective": collective,

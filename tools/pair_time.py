@@ -21,7 +21,7 @@ def timed(s, beads, reps=20):
 
 
 peak, _ = engine.probe_fp64_peak(0)
-print("FP64 peak %.2f TFLOP/s" % peak)
+print("FP64 peak %.2f TFLOP/s   (the percentages count the REFERENCE's flops per pair it visits: 54 LJ, 82 LJ + Coulomb; the per-kind\n loops of a five-site model issue about half of that, so the figure can exceed what the FP64 pipe itself shows in ncu)" % peak)
 s4 = W.h2_framework(solver={"polar_max_iter": "1"})
 s4.opts["polarization"] = "off"
 t, b = W.pi_h2_cluster(P=64, five_site=True)
