@@ -64,3 +64,22 @@ def test_sources_do_not_use_the_oracle():
                 text = open(os.path.join(dirpath, f)).read()
                 assert not bad.search(text), os.path.join(dirpath, f)
     assert os.path.exists(build.LIB)
+
+
+def test_product_libraries_do_not_contain_or_link_the_oracle():
+    """The oracle is test infrastructure: neither shipped library may define, import or depend on anything of it."""
+    import shutil
+    import subprocess
+    if not shutil.which("nm") or not shutil.which("readelf"):
+        import pytest
+        pytest.skip("binutils not available")
+    for lib in (build.build_library(), build.build_host()):
+        syms = subprocess.run(["nm", "-D", lib], capture_output=True, text=True, check=True).stdout
+        assert not re.search(r"\borc_[a-z_]+", syms), lib
+        needed = subprocess.run(["readelf", "-d", lib], capture_output=True, text=True, check=True).stdout
+        assert "oracle" not in needed and "mpmc_ref" not in needed, lib
+    for root, _, files in os.walk(os.path.join(ROOT, "mpmcxx_b200")):
+        for f in files:
+            if f.endswith((".cu", ".cuh", ".cpp", ".h", ".py")):
+                text = open(os.path.join(root, f), errors="ignore").read()
+                assert "oracle.h" not in text and "liboracle" not in text and not re.search(r"^\s*(from|import)\s+oracle\b", text, flags=re.M), f
