@@ -136,14 +136,14 @@ static inline double lrc_formula(double eps, double sigma, double cutoff, double
 }
 
 /* lj(): System.Energy.cpp:897-1032; coulombic_real(): :1466-1517.  One triangular sweep for both. */
-static void pair_energies(const sys_t *s, double *rd, double *lrc_pair, double *es_real, double *es_intra, double *n_in) {
+static void pair_energies(const sys_t *s, double *rd, double *lrc_pair, double *es_real, double *es_intra, double *n_in, double *abs_sums) {
 	const int n = s->n;
 	const double cutoff = s->cell.cutoff, a = s->cell.ewald_alpha;
 	const int do_es = !s->iopt[ORC_RD_ONLY], polar = s->iopt[ORC_POLARIZATION], do_lrc = s->iopt[ORC_RD_LRC];
-	double *acc = (double *)calloc((size_t)n * 5, sizeof(double));
+	double *acc = (double *)calloc((size_t)n * 8, sizeof(double));
 #pragma omp parallel for schedule(dynamic, 16)
 	for (int i = 0; i < n - 1; i++) {
-		double a_rd = 0, a_lrc = 0, a_re = 0, a_in = 0, a_cnt = 0;
+		double a_rd = 0, a_lrc = 0, a_re = 0, a_in = 0, a_cnt = 0, b_rd = 0, b_re = 0, b_in = 0;   /* b_*: sums of |term| (scale of the rounding noise; not a reference quantity) */
 		for (int j = i + 1; j < n; j++) {
 			int rdx, esx, fz; double e, sg;
 			pair_mix(s, i, j, &rdx, &esx, &fz, &e, &sg);
@@ -157,17 +157,23 @@ static void pair_energies(const sys_t *s, double *rd, double *lrc_pair, double *
 				double s6 = sor * sor * sor; s6 *= s6;
 				double s12 = s6 * s6;
 				a_rd += 4.0 * e * (s12 - s6);
+				b_rd += fabs(4.0 * e * s12) + fabs(4.0 * e * s6);
 				a_cnt += 1;
 			}
 			if (do_es && !fz) {
-				if (!((rimg > cutoff) || esx)) a_re += s->q[i] * s->q[j] * erfc(a * rimg) / rimg;          /* :1490-1497 */
-				else if (esx) a_in += s->q[i] * s->q[j] * erf(a * r) / r;                                   /* :1503-1504, un-imaged r */
+				if (!((rimg > cutoff) || esx)) { const double t = s->q[i] * s->q[j] * erfc(a * rimg) / rimg; a_re += t; b_re += fabs(t); }   /* :1490-1497 */
+				else if (esx) { const double t = s->q[i] * s->q[j] * erf(a * r) / r; a_in += t; b_in += fabs(t); }                            /* :1503-1504, un-imaged r */
 			}
 		}
-		acc[5 * i] = a_rd; acc[5 * i + 1] = a_lrc; acc[5 * i + 2] = a_re; acc[5 * i + 3] = a_in; acc[5 * i + 4] = a_cnt;
+		acc[8 * i] = a_rd; acc[8 * i + 1] = a_lrc; acc[8 * i + 2] = a_re; acc[8 * i + 3] = a_in; acc[8 * i + 4] = a_cnt;
+		acc[8 * i + 5] = b_rd; acc[8 * i + 6] = b_re; acc[8 * i + 7] = b_in;
 	}
 	*rd = *lrc_pair = *es_real = *es_intra = *n_in = 0;
-	for (int i = 0; i < n; i++) { *rd += acc[5 * i]; *lrc_pair += acc[5 * i + 1]; *es_real += acc[5 * i + 2]; *es_intra += acc[5 * i + 3]; *n_in += acc[5 * i + 4]; }
+	abs_sums[0] = abs_sums[1] = abs_sums[2] = 0;
+	for (int i = 0; i < n; i++) {
+		*rd += acc[8 * i]; *lrc_pair += acc[8 * i + 1]; *es_real += acc[8 * i + 2]; *es_intra += acc[8 * i + 3]; *n_in += acc[8 * i + 4];
+		for (int q = 0; q < 3; q++) abs_sums[q] += acc[8 * i + 5 + q];
+	}
 	free(acc);
 }
 
@@ -494,7 +500,8 @@ int orc_energy(int n, const double *pos, const double *charge, const double *alp
 	double *kv = NULL;
 	int nk = kvectors(&s.cell, iopt[ORC_EWALD_KMAX], &kv);
 	double rd, lrcp, esr, esi, nin;
-	pair_energies(&s, &rd, &lrcp, &esr, &esi, &nin);
+	double abs_sums[3];
+	pair_energies(&s, &rd, &lrcp, &esr, &esi, &nin, abs_sums);
 	double lrcs = 0;
 	if (iopt[ORC_RD_LRC])
 		for (int i = 0; i < n; i++)
@@ -522,6 +529,7 @@ int orc_energy(int n, const double *pos, const double *charge, const double *alp
 	out[ORC_O_VOLUME] = s.cell.volume; out[ORC_O_CUTOFF] = s.cell.cutoff;
 	out[ORC_O_EWALD_ALPHA] = s.cell.ewald_alpha; out[ORC_O_POLAR_EWALD_ALPHA] = s.cell.polar_ewald_alpha;
 	out[ORC_O_NKVEC] = nk; out[ORC_O_NPAIR_IN_CUTOFF] = nin;
+	out[ORC_O_RD_ABS] = abs_sums[0]; out[ORC_O_ES_REAL_ABS] = abs_sums[1]; out[ORC_O_ES_INTRA_ABS] = abs_sums[2];
 	free(kv);
 	return 0;
 }

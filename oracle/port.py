@@ -18,7 +18,7 @@ IOPT = ["rd_lrc", "rd_only", "polarization", "damp_type", "polar_ewald", "polar_
 DOPT = ["polar_damp", "polar_gamma", "polar_precision", "ewald_alpha", "polar_ewald_alpha"]
 OUT = ["energy", "rd_total", "coulombic", "polar", "rd", "lrc_pair", "lrc_self", "es_real", "es_self_intra", "es_recip",
        "es_self", "iterations", "dipole_rrms", "iterator_failed", "volume", "cutoff", "ewald_alpha", "polar_ewald_alpha",
-       "n_kvec", "n_pairs_in_cutoff"]
+       "n_kvec", "n_pairs_in_cutoff", "rd_abs", "es_real_abs", "es_intra_abs"]
 
 
 def build() -> None:

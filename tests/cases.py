@@ -48,6 +48,12 @@ CLASSIC = {
     # scaled-down config 4: frozen framework + randomly oriented five-site H2
     "h2fw_6_gs_ranked_palmo": lambda: W.h2_framework(ncell=6, n_h2=20, solver=W.SOLVER_GS_RANKED_PALMO, ensemble="nvt"),
     "h2fw_6_jacobi10": lambda: W.h2_framework(ncell=6, n_h2=20, solver=W.SOLVER_JACOBI10, ensemble="nvt"),
+    # 879 polarizable sites = 13.7 Gauss-Seidel blocks of 64: beyond the cluster's lookahead, so the updaters' flags, the far rows and
+    # the wrapped (already swept) rows all take part; not a multiple of 64
+    "h2fw_9_gs_ranked_palmo": lambda: W.h2_framework(ncell=9, n_h2=50, solver=W.SOLVER_GS_RANKED_PALMO, ensemble="nvt"),
+    # the 128-iteration fail-out of thole_iterative (src/System.Energy.cpp:3483-3494): over-relaxed SOR diverges, precision mode
+    # never converges -> mu = alpha E_static, ef_induced_change = 0, iterator_failed = 1
+    "tri_sor_failed": lambda: W.triclinic_mix(solver={"polar_sor": "on", "polar_gamma": "2.2", "polar_precision": "1e-6"}),
 }
 
 PI = {
