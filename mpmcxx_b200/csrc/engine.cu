@@ -167,9 +167,9 @@ struct mpmc_engine {
 	bool rank_ff_dirty = true;
 	// Gauss-Seidel pipeline: the updater kernel runs beside the solver cluster on a second stream
 	cudaStream_t stream2 = nullptr;
-	cudaEvent_t ev_upd = nullptr, ev_fork = nullptr, ev_sk = nullptr;
-	int *h_started = nullptr, *d_started = nullptr;   // mapped pinned word the solver kernel stamps when it is running
-	int gs_token = 0, gs_upd_grid = 0, gs_fused_grid = 0;
+	cudaEvent_t ev_fork = nullptr, ev_sk = nullptr;
+	int gs_gen = 0, gs_upd_grid = 0, gs_fused_grid = 0;   // gs_gen: generation of the pipeline's flag words (kernels_gs.cuh)
+	size_t gs_ctl_len = 0;
 	int *h_gs_abort = nullptr;      // pinned copy of GsCtl::abort after the last sweep of an energy()
 	bool gs_ran = false;
 	bool gs_fused = false;          // MPMC_GS_FUSED=1: updaters inside the solver's launch (for tools that serialise kernel launches)
@@ -909,28 +909,35 @@ static int run_polar(mpmc_engine *e) {
 			{
 				Timed _t(e, MPMC_K_GS_SWEEP);
 				for (int sw = 0; sw < ns; sw++) {   // one launch per sweep: the kernel boundary is the barrier between sweeps
-					CK(cudaMemsetAsync(e->d_gsctl.p, 0, sizeof(int) * (sizeof(GsCtl) / sizeof(int) + nchunks), e->stream));
-					const int token = ++e->gs_token;
+					// flags count from generation << 16, so nothing is cleared between sweeps (kernels_gs.cuh); zero them when the generation wraps
+					if (e->gs_gen == 0 || e->gs_gen >= (1 << (30 - kGsGenShift)) || e->gs_ctl_len != sizeof(GsCtl) / sizeof(int) + (size_t)nchunks) {
+						e->gs_ctl_len = sizeof(GsCtl) / sizeof(int) + (size_t)nchunks;
+						CK(cudaMemsetAsync(e->d_gsctl.p, 0, sizeof(int) * e->gs_ctl_len, e->stream));
+						e->gs_gen = 0;
+					}
+					if (nblk >= (1 << kGsGenShift) - kGsAhead - 2) FAIL(MPMC_ERR_UNSUPPORTED, "Gauss-Seidel pipeline: too many polarizable sites (%d)", np);
+					const int gbase = ++e->gs_gen << kGsGenShift;
 					const int sgrid = e->gs_fused ? e->gs_fused_grid : kGsCluster;
 					if (expd) k_gs_pipeline<ORTHO, true><<<sgrid, kGsPipeThreads, kGsSmemBytes, e->stream>>>(e->d_gpq.p, e->d_gmeta.p, gs_order, np, e->cell, pd, e->d_efs.p,
-					        e->d_mu.p, e->d_efi.p, e->d_new_mu.p, e->d_acc.p, e->d_dmu.p, e->d_tri.p, e->d_near.p, (GsCtl *)e->d_gsctl.p, sw == 0 ? prof : nullptr, e->d_started, token);
+					        e->d_mu.p, e->d_efi.p, e->d_new_mu.p, e->d_acc.p, e->d_dmu.p, e->d_tri.p, e->d_near.p, (GsCtl *)e->d_gsctl.p, sw == 0 ? prof : nullptr, gbase);
 					else k_gs_pipeline<ORTHO, false><<<sgrid, kGsPipeThreads, kGsSmemBytes, e->stream>>>(e->d_gpq.p, e->d_gmeta.p, gs_order, np, e->cell, pd, e->d_efs.p,
-					        e->d_mu.p, e->d_efi.p, e->d_new_mu.p, e->d_acc.p, e->d_dmu.p, e->d_tri.p, e->d_near.p, (GsCtl *)e->d_gsctl.p, sw == 0 ? prof : nullptr, e->d_started, token);
+					        e->d_mu.p, e->d_efi.p, e->d_new_mu.p, e->d_acc.p, e->d_dmu.p, e->d_tri.p, e->d_near.p, (GsCtl *)e->d_gsctl.p, sw == 0 ? prof : nullptr, gbase);
 					CK(cudaGetLastError());
-					if (e->gs_fused) { LAUNCHED(e); continue; }
-					// The updaters must not take the SMs the cluster needs (its CTAs want a whole SM's shared memory each): wait until the
-					// solver kernel is running — it stamps a mapped host word first thing — then fill the rest of the machine.
-					for (long long spin = 0; *(volatile int *)e->h_started != token; spin++) {
-						if (spin > 2000000000ll) FAIL(MPMC_ERR_CUDA, "Gauss-Seidel solver kernel did not start");
-						if ((spin & 0xfffff) == 0xfffff && cudaStreamQuery(e->stream) != cudaErrorNotReady) break;   // it already finished (tiny system) or failed
-					}
-					if (expd) k_gs_updaters<ORTHO, true><<<e->gs_upd_grid, kGsThreads, kGsUpdaterSmemBytes, e->stream2>>>(e->d_gpq.p, e->d_gmeta.p, gs_order, np, e->cell, pd,
-					        e->d_acc.p, e->d_dmu.p, (GsCtl *)e->d_gsctl.p, sw == 0 ? prof : nullptr);
-					else k_gs_updaters<ORTHO, false><<<e->gs_upd_grid, kGsThreads, kGsUpdaterSmemBytes, e->stream2>>>(e->d_gpq.p, e->d_gmeta.p, gs_order, np, e->cell, pd,
-					        e->d_acc.p, e->d_dmu.p, (GsCtl *)e->d_gsctl.p, sw == 0 ? prof : nullptr);
-					CK(cudaEventRecord(e->ev_upd, e->stream2));
-					CK(cudaStreamWaitEvent(e->stream, e->ev_upd, 0));
-					e->launches++;
+					LAUNCHED(e);
+					if (e->gs_fused) continue;
+					// The updaters must not take the SMs the cluster needs (its CTAs want a whole SM's shared memory each): they are launched
+					// as the solver kernel's programmatic dependent — same stream, eligible as soon as every CTA of the cluster has executed
+					// griddepcontrol.launch_dependents, i.e. is resident.  No host wait, no second stream; the next operation in the stream
+					// waits for both kernels.
+					cudaLaunchConfig_t lc = {};
+					lc.gridDim = dim3(e->gs_upd_grid); lc.blockDim = dim3(kGsThreads); lc.dynamicSmemBytes = kGsUpdaterSmemBytes; lc.stream = e->stream;
+					cudaLaunchAttribute at[1];
+					at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization; at[0].val.programmaticStreamSerializationAllowed = 1;
+					lc.attrs = at; lc.numAttrs = 1;
+					const double4 *a_gpq = e->d_gpq.p; const int *a_gmeta = e->d_gmeta.p; double *a_acc = e->d_acc.p; const double *a_dmu = e->d_dmu.p;
+					GsCtl *a_ctl = (GsCtl *)e->d_gsctl.p; long long *a_prof = sw == 0 ? prof : nullptr;
+					if (expd) CK(cudaLaunchKernelEx(&lc, k_gs_updaters<ORTHO, true>, a_gpq, a_gmeta, gs_order, np, e->cell, pd, a_acc, a_dmu, a_ctl, a_prof, gbase));
+					else CK(cudaLaunchKernelEx(&lc, k_gs_updaters<ORTHO, false>, a_gpq, a_gmeta, gs_order, np, e->cell, pd, a_acc, a_dmu, a_ctl, a_prof, gbase));
 					LAUNCHED(e);
 				}
 				CK(cudaGetLastError());
@@ -1091,14 +1098,10 @@ int mpmc_create(const mpmc_config *cfg, mpmc_engine **out) {
 	{
 		// the Gauss-Seidel pipeline: one cluster (solver + helpers) and an updater kernel on every other SM, 2 CTAs each
 		CK(cudaStreamCreateWithFlags(&e->stream2, cudaStreamNonBlocking));
-		CK(cudaEventCreateWithFlags(&e->ev_upd, cudaEventDisableTiming));
 		CK(cudaEventCreateWithFlags(&e->ev_fork, cudaEventDisableTiming));
 		CK(cudaEventCreateWithFlags(&e->ev_sk, cudaEventDisableTiming));
-		CK(cudaHostAlloc(&e->h_started, sizeof(int), cudaHostAllocMapped));
-		*e->h_started = 0;
 		CK(cudaMallocHost(&e->h_gs_abort, sizeof(int)));
 		*e->h_gs_abort = 0;
-		CK(cudaHostGetDevicePointer(&e->d_started, e->h_started, 0));
 		if ((rc = set_smem(k_gs_updaters<true, true>, kGsUpdaterSmemBytes)) || (rc = set_smem(k_gs_updaters<false, true>, kGsUpdaterSmemBytes)) ||
 		    (rc = set_smem(k_gs_updaters<true, false>, kGsUpdaterSmemBytes)) || (rc = set_smem(k_gs_updaters<false, false>, kGsUpdaterSmemBytes))) { mpmc_destroy(e); return rc; }
 		int occ = 0;
@@ -1139,10 +1142,8 @@ int mpmc_destroy(mpmc_engine *e) {
 	if (e->h_flags) cudaFreeHost(e->h_flags);
 	drop_pi_graph(e);
 	if (e->stream2) { cudaStreamSynchronize(e->stream2); cudaStreamDestroy(e->stream2); }
-	if (e->ev_upd) cudaEventDestroy(e->ev_upd);
 	if (e->ev_fork) cudaEventDestroy(e->ev_fork);
 	if (e->ev_sk) cudaEventDestroy(e->ev_sk);
-	if (e->h_started) cudaFreeHost(e->h_started);
 	if (e->h_gs_abort) cudaFreeHost(e->h_gs_abort);
 	for (int r = 0; r < (int)e->peer_mbox.size(); r++) if (r != e->rank && e->peer_mbox[r]) cudaIpcCloseMemHandle(e->peer_mbox[r]);
 	if (e->d_mbox) cudaFree(e->d_mbox);
@@ -1264,6 +1265,7 @@ int mpmc_energy_fetch(mpmc_engine *e, mpmc_energy_out *out) {
 			// the solver and updater kernels were not run side by side (a tool that serialises kernel launches): the result of this
 			// evaluation is meaningless.  Switch this engine to the single-launch pipeline for good and evaluate again.
 			*e->h_gs_abort = 0;
+			e->gs_gen = 0;                                  // the sticky abort word is zeroed with the other flags before the next sweep
 			if (e->gs_fused) FAIL(MPMC_ERR_CUDA, "the Gauss-Seidel pipeline timed out waiting for its own CTAs");
 			e->gs_fused = true;
 			int rc = mpmc_energy_enqueue(e);

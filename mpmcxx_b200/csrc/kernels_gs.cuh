@@ -37,7 +37,7 @@ namespace mpmc {
 constexpr int kGsB = 64;                  // sites per solver block
 constexpr int kGsRows = 4;                // rows per updater chunk (one warp: 4 rows x 8 column lanes)
 constexpr int kGsColLanes = 32 / kGsRows;
-constexpr int kGsUpdCtas = 4;             // updater CTAs per SM the kernel is compiled for
+constexpr int kGsUpdCtas = 3;             // updater CTAs per SM the kernel is compiled for (85 registers: the row sums live in registers)
 constexpr int kGsThreads = 256;
 constexpr int kGsWarps = kGsThreads / 32;
 constexpr int kGsPipeThreads = 512;       // the solver/helper cluster: 192 x 2 threads walk, 512 per helper push
@@ -45,7 +45,12 @@ constexpr int kGsN = 3 * kGsB;            // components per block
 constexpr int kGsInv = 9 * (kGsB * (kGsB - 1) / 2);   // 18144 doubles: one block's strictly lower inverse (k_gs_inverse)
 __host__ __device__ constexpr int gs_inv_rows(int j) { return kGsN - 3 * (j + 1); }
 __host__ __device__ constexpr int gs_inv_off(int j) { return 3 * (kGsN - 3) * j - 9 * (j * (j - 1) / 2); }
-constexpr int kGsMat = kGsInv;            // doubles of the solver's matrix buffer
+// The solver reads a block's inverse as 32 x 32 tiles: tile (I, J), J <= I, of the 192 x 192 strictly (by site) lower matrix X sits at
+// gs_tile(I, J) * 1024 + c * 32 + r  (column-major inside the tile: a warp reads one column with consecutive lanes); the entries of the
+// diagonal tiles that are not strictly lower by site are stored as zeros.
+constexpr int kGsTileDim = 32, kGsTilesPerSide = kGsN / kGsTileDim, kGsTiles = kGsTilesPerSide * (kGsTilesPerSide + 1) / 2;   // 6, 21
+__host__ __device__ constexpr int gs_tile(int I, int J) { return I * (I + 1) / 2 + J; }
+constexpr int kGsMat = kGsTiles * kGsTileDim * kGsTileDim;   // 21504 doubles of the solver's matrix buffer (172 KB)
 
 // shared memory (doubles).  Solver: the block's inverse, two site-column buffers, the pending pushes of the next blocks, panel dmu,
 // right-hand side, second halves of the dot products, site ids.  Updaters: per warp the panel's columns and dmu.
@@ -53,7 +58,7 @@ constexpr int kGsSiteCols = 10;           // 0 alpha, 1-3 mu_old, 4-6 E_static, 
 constexpr int kGsAhead = 4;               // the cluster pushes a panel into this many following blocks itself; the updaters take the rest
 constexpr int kGsHelpers = 7, kGsCluster = 1 + kGsHelpers;
 constexpr int kGsSlots = kGsAhead + 1;    // ring of per-block buffers
-constexpr size_t kGsSolverDoubles = (size_t)kGsMat + 2 * kGsSiteCols * kGsB + kGsSlots * 3 * kGsB + 4 * kGsB + 4 * kGsB + kGsN + 2 * kGsB + 16;
+constexpr size_t kGsSolverDoubles = (size_t)kGsMat + 2 * kGsSiteCols * kGsB + kGsSlots * 3 * kGsB + 4 * kGsB + kGsN + kGsTiles * kGsTileDim + 2 * kGsB + 16;
 constexpr size_t kGsUpdaterDoubles = (size_t)kGsWarps * 8 * kGsB;
 constexpr int kGsHelperOutOffset = 4 * kGsB;      // doubles: a helper's delivery buffer inside its shared memory (after h_dm)
 static_assert(kGsSolverDoubles >= (size_t)(kGsPipeThreads / 32) * 8 * kGsB, "the fused fallback runs the updaters inside the pipeline kernel");
@@ -62,6 +67,10 @@ constexpr size_t kGsUpdaterSmemBytes = sizeof(double) * kGsUpdaterDoubles;
 
 __device__ int g_gs_debug = 0;            // developer switch (mpmc_debug_gs_profile enable bits 1..): 2 = pushers idle, 4 = no rolling copy
 struct GsCtl { int solved; int abort; int pad[30]; };   // followed in memory by int applied[nchunks]
+// The flags are never cleared between sweeps: every launch gets a generation number and counts from `gbase` = generation << 16
+// (solved = gbase + blocks solved, applied[chunk] = gbase + panels in memory), so whatever the previous sweep left compares as "not
+// yet".  The host zeroes the words when the generation wraps.  `abort` is sticky until the host has looked at it.
+constexpr int kGsGenShift = 16;
 // `abort`: set when a CTA has waited ~2 s for the other kernel of the pipeline — the two kernels were not run side by side (a
 // tool that serialises launches).  Everybody then stops waiting, the sweep's result is meaningless and the host reports it.
 constexpr int kGsWaitLimit = 20000000;
@@ -73,6 +82,20 @@ __device__ __forceinline__ long long clock_after(const volatile int *p) { const 
 __device__ __forceinline__ int ld_acquire(const int *p) { int v; asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory"); return v; }
 __device__ __forceinline__ int ld_flag(const int *p) { return *(const volatile int *)p; }
 __device__ __forceinline__ void st_flag(int *p, int v) { *(volatile int *)p = v; }
+// mbarrier + bulk asynchronous copy (TMA engine, no tensor map): one thread moves a block's inverse into shared memory with a few
+// instructions; the waiters sleep on the barrier's phase instead of issuing 40 cp.async each
+__device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned bar, unsigned count) { asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory"); }
+__device__ __forceinline__ void mbar_expect_tx(unsigned bar, unsigned bytes) { asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory"); }
+__device__ __forceinline__ void bulk_g2s(unsigned dst, const void *src, unsigned bytes, unsigned bar) {
+	asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned bar, unsigned parity) {
+	unsigned ok;
+	do {
+		asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }" : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+	} while (!ok);
+}
 
 // sweep-order copies of what the pipeline reads per site: gpq[pos] = x, y, z, alpha; gmeta[pos] = molecule | charged<<30
 __global__ void k_gs_gather(const double4 *__restrict__ pq, const double *__restrict__ alpha, const int *__restrict__ meta,
@@ -170,14 +193,14 @@ k_gs_inverse(const double4 *__restrict__ gpq, const int *__restrict__ gmeta, int
 		}
 		__syncthreads();
 	}
-	// the walk's layout
-	double *out = inv + (size_t)blk * kGsInv;
-	for (int r = 3; r < kGsN; r++) {
-		const int ncol = 3 * (r / 3);
-		if (tid < ncol) {
-			const int j = tid / 3, q = tid - 3 * j;
-			out[gs_inv_off(j) + q * gs_inv_rows(j) + (r - 3 * (j + 1))] = s_w[row_off(r) + tid];
-		}
+	// the solver's layout: 32 x 32 tiles, zeros where the matrix is not strictly lower by site
+	double *out = inv + (size_t)blk * kGsMat;
+	for (int q = tid; q < kGsMat; q += kGsThreads) {
+		const int t = q / (kGsTileDim * kGsTileDim), cl = (q / kGsTileDim) % kGsTileDim, rl = q % kGsTileDim;
+		int I = 0;
+		while (gs_tile(I + 1, 0) <= t) I++;
+		const int J = t - gs_tile(I, 0), r = kGsTileDim * I + rl, cc = kGsTileDim * J + cl;
+		out[q] = cc < 3 * (r / 3) ? s_w[row_off(r) + cc] : 0.0;
 	}
 }
 
@@ -216,125 +239,181 @@ k_gs_near(const double4 *__restrict__ gpq, const int *__restrict__ gmeta, int np
 }
 
 // The updaters' work, shared by the updater kernel and by the single-launch fallback of the pipeline kernel: CTA `cta` of `U`.
+// Warps work independently.  A warp owns up to kGsOwn chunks of kGsRows consecutive rows of the sweep order (lane = row x column
+// lane) and keeps what it pushes into them IN REGISTERS from panel to panel — a row's sum only has to reach memory twice per sweep:
+//   * when the solver is about to take the row over: the rows of block c belong to the cluster for panels c-kGsAhead .. c-1, so
+//     after panel c-kGsAhead-1 the chunk's sums are reduced over the column lanes, added to acc, fenced and flagged
+//     (applied[chunk] = number of panels that have reached memory);
+//   * at the end of the sweep, with everything pushed since the solver wrote the row back (panels c .. nblk-1, which prepare acc
+//     for the next sweep / are the Palmo contraction).
+// (The first version added every panel to acc with atomics and paid a fence + flag per panel and chunk: 2.2 k of the 7.9 k
+// cycles a warp spent per panel, and a latency the solver ran into several times per sweep.)  Each row has one writer and
+// receives its panels in a fixed order, so the result does not depend on timing.  Chunks beyond kGsOwn per warp (systems with
+// more than kGsOwn x kGsRows x resident-warps polarizable sites) take the per-panel path of the first version.
+constexpr int kGsOwn = 2;
 template <bool ORTHO, bool EXPD>
 __device__ __forceinline__ void gs_updater_body(double *s_raw, int cta, int U, const double4 *__restrict__ gpq, const int *__restrict__ gmeta,
                                                 const int *__restrict__ order, int np, const CellDev &c, const PolarDev &p, double *acc,
-                                                const double *dmu, GsCtl *ctl, long long *prof) {
+                                                const double *dmu, GsCtl *ctl, long long *prof, int gbase) {
 	int *applied = (int *)(ctl + 1);
 	const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 	const int nblk = (np + kGsB - 1) / kGsB, nchunks = (np + kGsRows - 1) / kGsRows;
 	constexpr int kChunksPerBlk = kGsB / kGsRows;
-	{
-		// warps work independently: global warp gwid owns the chunks ch = gwid, gwid + GW, ...  (8 consecutive rows of the
-		// sweep order each) and keeps its own copy of the panel in shared memory
-		double4 *w_col = (double4 *)s_raw + warp * 2 * kGsB;
-		double4 *w_dm = w_col + kGsB;
-		// (warp-major numbering: when there are more chunks than warps, the second chunks go one to each CTA instead of eight to a
-		// few CTAs — an SM with twice the work falls behind by a few thousand cycles per panel and stalls the solver at the end)
-		const int GW = U * (int)(blockDim.x >> 5), gwid = warp * U + cta;
-		const int r = lane & (kGsRows - 1), cl = lane / kGsRows;   // row of the chunk, column lane
-		for (int blk = 0; blk < nblk; blk++) {
-			const int base = blk * kGsB, cnt = min(kGsB, np - base);
-			// the rows of the next kGsAhead blocks belong to the cluster (the panel's own rows do not: the solver writes them back
-			// before it publishes the panel, without the panel's own contribution)
-			const int skip0 = (blk + 1) * kChunksPerBlk, skip1 = min(blk + 1 + kGsAhead, nblk) * kChunksPerBlk;
-			const int first = gwid;
-			bool any = false;
-			for (int ch = first; ch < nchunks; ch += GW) any = any || !(ch >= skip0 && ch < skip1);
-			if (!any) continue;
-			__syncwarp();
-			for (int cc = lane; cc < cnt; cc += 32) {
-				const double4 g = gpq[base + cc];
-				w_col[cc] = make_double4(g.x, g.y, g.z, __longlong_as_double((long long)gmeta[base + cc]));   // alpha travels in w_dm.w
-			}
-			const bool pw = prof && cta == 0 && warp == 0 && lane == 0;
-			if (pw) prof[(nblk + blk) * 8 + 0] = clock64();
-			if (lane == 0) {
-				int spins = 0;
-				while (ld_flag(&ctl->solved) <= blk && !ld_flag(&ctl->abort)) {
-					__nanosleep(256);          // ~2300 warps watch this word: short sleeps saturate its L2 slice (the flags live next to it)
-					if (++spins > 3 * kGsWaitLimit) st_flag(&ctl->abort, 1);
-				}
-			}
-			if (__shfl_sync(0xffffffffu, ld_flag(&ctl->abort), 0)) return;
-			__syncwarp();
-			__threadfence();
-			if (pw) prof[(nblk + blk) * 8 + 1] = clock64();
-			for (int cc = lane; cc < cnt; cc += 32)
-				w_dm[cc] = make_double4(__ldcg(dmu + 3 * (base + cc)), __ldcg(dmu + 3 * (base + cc) + 1), __ldcg(dmu + 3 * (base + cc) + 2), EXPD ? 0.0 : gpq[base + cc].w);
-			__syncwarp();
-			// all my chunks of this panel first, then their running contractions (each row has exactly one writer, so the atomic adds
-			// are ordered and the result deterministic), ONE fence, then the flags: a warp that owns two chunks must not pay two fences
-			for (int ch0 = first; ch0 < nchunks; ch0 += 2 * GW) {
-				double sx[2], sy[2], sz[2];
-				int chs[2];
+	double4 *w_col = (double4 *)s_raw + warp * 2 * kGsB;
+	double4 *w_dm = w_col + kGsB;
+	// (warp-major numbering: when there are more chunks than warps, the second chunks go one to each CTA instead of eight to a
+	// few CTAs — an SM with twice the work falls behind by a few thousand cycles per panel and stalls the solver at the end)
+	const int GW = U * (int)(blockDim.x >> 5), gwid = warp * U + cta;
+	const int r = lane & (kGsRows - 1), cl = lane / kGsRows;   // row of the chunk, column lane
+	if (gwid >= nchunks) return;
+	// my rows (constant over the sweep) and their sums
+	double4 pr[kGsOwn];
+	int mr[kGsOwn], chs[kGsOwn], cblk[kGsOwn];
+	double sx[kGsOwn], sy[kGsOwn], sz[kGsOwn];
 #pragma unroll
-				for (int w = 0; w < 2; w++) {
-					const int ch = ch0 + w * GW;
-					chs[w] = (ch < nchunks && !(ch >= skip0 && ch < skip1)) ? ch : -1;
-					sx[w] = sy[w] = sz[w] = 0.0;
-					if (chs[w] < 0) continue;
-					const int pos = ch * kGsRows + r;
-					const bool on = pos < np;
-					const double4 pr = on ? gpq[pos] : make_double4(0, 0, 0, 0);
-					const int mr = on ? gmeta[pos] : 0;
-					double ax = 0, ay = 0, az = 0;
-					if (on) {
+	for (int w = 0; w < kGsOwn; w++) {
+		const int ch = gwid + w * GW;
+		chs[w] = ch < nchunks ? ch : -1;
+		cblk[w] = ch / kChunksPerBlk;
+		const int pos = ch * kGsRows + r;
+		const bool on = chs[w] >= 0 && pos < np;
+		pr[w] = on ? gpq[pos] : make_double4(0, 0, 0, 0);
+		mr[w] = on ? gmeta[pos] : 0;
+		if (!on && chs[w] >= 0) mr[w] = -1;                 // a row past the end of a last, partial chunk
+		sx[w] = sy[w] = sz[w] = 0.0;
+	}
+	const bool more = gwid + kGsOwn * GW < nchunks;
+	// reduce a chunk's sums over the column lanes and add them to acc (one writer per row: a plain read-modify-write)
+	auto flush = [&](int w) {
+		double ax = sx[w], ay = sy[w], az = sz[w];
+		ax += __shfl_xor_sync(0xffffffffu, ax, 4); ay += __shfl_xor_sync(0xffffffffu, ay, 4); az += __shfl_xor_sync(0xffffffffu, az, 4);
+		ax += __shfl_xor_sync(0xffffffffu, ax, 8); ay += __shfl_xor_sync(0xffffffffu, ay, 8); az += __shfl_xor_sync(0xffffffffu, az, 8);
+		ax += __shfl_xor_sync(0xffffffffu, ax, 16); ay += __shfl_xor_sync(0xffffffffu, ay, 16); az += __shfl_xor_sync(0xffffffffu, az, 16);
+		const int pos = chs[w] * kGsRows + r;
+		if (cl == 0 && pos < np) {
+			double *a = acc + 3 * order[pos];
+			__stcg(a, __ldcg(a) + ax); __stcg(a + 1, __ldcg(a + 1) + ay); __stcg(a + 2, __ldcg(a + 2) + az);
+		}
+		sx[w] = sy[w] = sz[w] = 0.0;
+	};
+	for (int blk = 0; blk < nblk; blk++) {
+		const int base = blk * kGsB, cnt = min(kGsB, np - base);
+		// the rows of the next kGsAhead blocks belong to the cluster (the panel's own rows do not: the solver writes them back
+		// before it publishes the panel, without the panel's own contribution)
+		const int skip0 = (blk + 1) * kChunksPerBlk, skip1 = min(blk + 1 + kGsAhead, nblk) * kChunksPerBlk;
+		bool any = more;
+#pragma unroll
+		for (int w = 0; w < kGsOwn; w++) any = any || (chs[w] >= 0 && !(chs[w] >= skip0 && chs[w] < skip1));
+		if (!any) continue;
+		__syncwarp();
+		for (int cc = lane; cc < cnt; cc += 32) {
+			const double4 g = gpq[base + cc];
+			w_col[cc] = make_double4(g.x, g.y, g.z, __longlong_as_double((long long)gmeta[base + cc]));   // alpha travels in w_dm.w
+		}
+		const bool pw = prof && cta == 0 && warp == 0 && lane == 0;
+		if (pw) prof[(nblk + blk) * 8 + 0] = clock64();
+		if (lane == 0) {
+			int spins = 0;
+			while (ld_flag(&ctl->solved) <= gbase + blk && !ld_flag(&ctl->abort)) {
+				__nanosleep(256);          // ~2300 warps watch this word: short sleeps saturate its L2 slice (the flags live next to it)
+				if (++spins > 3 * kGsWaitLimit) st_flag(&ctl->abort, 1);
+			}
+		}
+		if (__shfl_sync(0xffffffffu, ld_flag(&ctl->abort), 0)) return;
+		__syncwarp();
+		__threadfence();
+		if (pw) prof[(nblk + blk) * 8 + 1] = clock64();
+		for (int cc = lane; cc < cnt; cc += 32)
+			w_dm[cc] = make_double4(__ldcg(dmu + 3 * (base + cc)), __ldcg(dmu + 3 * (base + cc) + 1), __ldcg(dmu + 3 * (base + cc) + 2), EXPD ? 0.0 : gpq[base + cc].w);
+		__syncwarp();
+#pragma unroll
+		for (int w = 0; w < kGsOwn; w++) {
+			if (chs[w] < 0 || (chs[w] >= skip0 && chs[w] < skip1)) continue;       // warp-uniform
+			if (mr[w] != -1) {
+				double ax = 0, ay = 0, az = 0;
 #pragma unroll 4
-						for (int cc = cl; cc < cnt; cc += kGsColLanes) {
-							double4 pc = w_col[cc];
-							const double4 dm = w_dm[cc];
-							const int mc = __double2loint(pc.w);
-							if (!EXPD) pc.w = dm.w;                           // alpha of the column (linear damping)
-							gs_contract<ORTHO, EXPD>(c, p, pr, mr, pc, mc, dm, ax, ay, az);
-						}
-					}
-					ax += __shfl_xor_sync(0xffffffffu, ax, 4); ay += __shfl_xor_sync(0xffffffffu, ay, 4); az += __shfl_xor_sync(0xffffffffu, az, 4);
-					ax += __shfl_xor_sync(0xffffffffu, ax, 8); ay += __shfl_xor_sync(0xffffffffu, ay, 8); az += __shfl_xor_sync(0xffffffffu, az, 8);
-					ax += __shfl_xor_sync(0xffffffffu, ax, 16); ay += __shfl_xor_sync(0xffffffffu, ay, 16); az += __shfl_xor_sync(0xffffffffu, az, 16);
-					sx[w] = ax; sy[w] = ay; sz[w] = az;
+				for (int cc = cl; cc < cnt; cc += kGsColLanes) {
+					double4 pc = w_col[cc];
+					const double4 dm = w_dm[cc];
+					const int mc = __double2loint(pc.w);
+					if (!EXPD) pc.w = dm.w;                           // alpha of the column (linear damping)
+					gs_contract<ORTHO, EXPD>(c, p, pr[w], mr[w], pc, mc, dm, ax, ay, az);
 				}
-				if (pw) prof[(nblk + blk) * 8 + 2] = clock64();
-#pragma unroll
-				for (int w = 0; w < 2; w++) {
-					const int pos = chs[w] * kGsRows + r;
-					if (chs[w] >= 0 && cl == 0 && pos < np) {
-						const int i = order[pos];
-						atomicAdd(acc + 3 * i, sx[w]); atomicAdd(acc + 3 * i + 1, sy[w]); atomicAdd(acc + 3 * i + 2, sz[w]);
+				sx[w] += ax; sy[w] += ay; sz[w] += az;
+			}
+			// the last panel before the cluster takes these rows over: to memory, then the flag
+			if (blk == cblk[w] - kGsAhead - 1) {
+				flush(w);
+				__threadfence();
+				__syncwarp();
+				if (lane == 0) st_flag(applied + chs[w], gbase + blk + 1);
+			}
+		}
+		if (pw) prof[(nblk + blk) * 8 + 2] = clock64();
+		if (more) {
+			// per-panel path for the chunks this warp cannot keep in registers
+			for (int ch = gwid + kGsOwn * GW; ch < nchunks; ch += GW) {
+				if (ch >= skip0 && ch < skip1) continue;
+				const int pos = ch * kGsRows + r;
+				const bool on = pos < np;
+				const double4 prr = on ? gpq[pos] : make_double4(0, 0, 0, 0);
+				const int mrr = on ? gmeta[pos] : 0;
+				double ax = 0, ay = 0, az = 0;
+				if (on) {
+#pragma unroll 4
+					for (int cc = cl; cc < cnt; cc += kGsColLanes) {
+						double4 pc = w_col[cc];
+						const double4 dm = w_dm[cc];
+						const int mc = __double2loint(pc.w);
+						if (!EXPD) pc.w = dm.w;
+						gs_contract<ORTHO, EXPD>(c, p, prr, mrr, pc, mc, dm, ax, ay, az);
 					}
+				}
+				ax += __shfl_xor_sync(0xffffffffu, ax, 4); ay += __shfl_xor_sync(0xffffffffu, ay, 4); az += __shfl_xor_sync(0xffffffffu, az, 4);
+				ax += __shfl_xor_sync(0xffffffffu, ax, 8); ay += __shfl_xor_sync(0xffffffffu, ay, 8); az += __shfl_xor_sync(0xffffffffu, az, 8);
+				ax += __shfl_xor_sync(0xffffffffu, ax, 16); ay += __shfl_xor_sync(0xffffffffu, ay, 16); az += __shfl_xor_sync(0xffffffffu, az, 16);
+				if (cl == 0 && on) {
+					const int i = order[pos];
+					atomicAdd(acc + 3 * i, ax); atomicAdd(acc + 3 * i + 1, ay); atomicAdd(acc + 3 * i + 2, az);
 				}
 				__threadfence();
 				__syncwarp();
-				if (lane < 2 && chs[lane] >= 0) st_flag(applied + chs[lane], blk + 1);
-				if (pw) prof[(nblk + blk) * 8 + 3] = clock64();
+				if (lane == 0) st_flag(applied + ch, gbase + blk + 1);
 			}
 		}
+		if (pw) prof[(nblk + blk) * 8 + 3] = clock64();
 	}
+	// what was pushed since the solver wrote the rows back
+#pragma unroll
+	for (int w = 0; w < kGsOwn; w++) if (chs[w] >= 0) flush(w);
 }
 
 // what the cluster shares: the solver's shared-memory words the helpers read (progress, dmu) and write (partial pushes, done)
-struct GsShared { int prog; int loaded; int folded; int pad; int done[8]; };
+struct GsShared { int prog; int loaded; int folded; int pad; int done[8]; unsigned long long mbar; };
 
 template <bool ORTHO, bool EXPD>
 __global__ void __cluster_dims__(kGsCluster, 1, 1) __launch_bounds__(kGsPipeThreads, 1)
 k_gs_pipeline(const double4 *__restrict__ gpq, const int *__restrict__ gmeta, const int *__restrict__ order, int np, CellDev c, PolarDev p,
               const double *__restrict__ efs, double *mu, double *efi, double *new_mu, double *acc, double *dmu,
-              const double *__restrict__ tri, const double *__restrict__ near, GsCtl *ctl, long long *prof, volatile int *started, int token) {
+              const double *__restrict__ tri, const double *__restrict__ near, GsCtl *ctl, long long *prof, int gbase) {
 	cg::cluster_group cluster = cg::this_cluster();
-	if (blockIdx.x == 0 && threadIdx.x == 0) { *started = token; __threadfence_system(); }   // tells the host that the cluster holds its SMs
+	// Programmatic dependent launch: the updater kernel follows in the same stream and may start as soon as every CTA of this grid
+	// has executed this — i.e. once the cluster holds its SMs (its CTAs want a whole SM's shared memory each, so the updaters must
+	// not be placed first).  No host round trip between the two launches.
+	asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
 	extern __shared__ __align__(16) double s_raw[];
 	int *applied = (int *)(ctl + 1);
 	const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 	const int cta = blockIdx.x;
 	const int nblk = (np + kGsB - 1) / kGsB, nchunks = (np + kGsRows - 1) / kGsRows;
 	// the solver's layout (helpers address the shared part of it through the cluster)
-	double *s_mat = s_raw;                                         // [kGsB columns][kGsB rows][6], rolled: column k of the next block replaces column k once the walk has passed it
+	double *s_mat = s_raw;                                         // [kGsTiles][32 columns][32 rows]: the block's inverse (k_gs_inverse)
 	double *s_site0 = s_mat + kGsMat;                              // [2][kGsSiteCols][kGsB], buffer = block & 1
 	double *s_pend = s_site0 + 2 * kGsSiteCols * kGsB;             // [kGsSlots][kGsB][3] pushes already made into the rows of blocks b .. b+kGsAhead (slot = block % kGsSlots)
 	double4 *s_dm = (double4 *)(s_pend + kGsSlots * 3 * kGsB);     // [kGsB] dmu of the block being walked
-	double4 *s_rhs = s_dm + kGsB;                                  // [kGsB] right-hand side of the block being walked
-	double *s_wpart = (double *)(s_rhs + kGsB);                    // [kGsN] second half of the walk's dot products
-	int *s_idx = (int *)(s_wpart + kGsN);                          // [2][kGsB] site ids of this block / the next block
+	double *s_rho = (double *)(s_dm + kGsB);                       // [kGsN] right-hand side of the block being walked
+	double *s_tpart = s_rho + kGsN;                                // [kGsTiles][32] per-tile partial dot products
+	int *s_idx = (int *)(s_tpart + kGsTiles * kGsTileDim);         // [2][kGsB] site ids of this block / the next block
 	GsShared *s_sh = (GsShared *)(s_idx + 2 * kGsB);
 
 	if (cta == 0) {
@@ -365,15 +444,22 @@ k_gs_pipeline(const double4 *__restrict__ gpq, const int *__restrict__ gmeta, co
 #pragma unroll
 		for (int h = 0; h < kGsHelpers; h++) h_out_of[h] = cluster.map_shared_rank(s_raw + kGsHelperOutOffset, h + 1);
 		for (int q = tid; q < kGsSlots * 3 * kGsB; q += kGsPipeThreads) s_pend[q] = 0.0;
-		{
-			const double2 *src = (const double2 *)tri;
-			double2 *dst = (double2 *)s_mat;
-			for (int q = tid; q < kGsMat / 2; q += kGsPipeThreads) __pipeline_memcpy_async(dst + q, src + q, sizeof(double2));
-			__pipeline_commit();
+		const unsigned bar = smem_u32(&s_sh->mbar);
+		constexpr unsigned kMatBytes = sizeof(double) * kGsMat, kMatPiece = kMatBytes / 3;
+		static_assert(kMatPiece % 16 == 0, "bulk copies move multiples of 16 bytes");
+		auto fetch_inverse = [&](int blk) {                        // one thread: the whole inverse of block blk -> s_mat, completion on the barrier
+			mbar_expect_tx(bar, kMatBytes);
+			const char *src = (const char *)(tri + (size_t)blk * kGsMat);
+			for (int q = 0; q < 3; q++) bulk_g2s(smem_u32(s_mat) + q * kMatPiece, src + q * kMatPiece, kMatPiece, bar);
+		};
+		if (tid == 0) {
+			mbar_init(bar, 1);
+			asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+			*s_prog = 0; for (int h = 0; h < 8; h++) s_done[h] = 0;
 		}
 		if (tid < kGsB) { load_cols(0, tid); load_acc(0, tid); }
-		if (tid == 0) { *s_prog = 0; for (int h = 0; h < 8; h++) s_done[h] = 0; }
 		cluster.sync();                                            // the helpers may look at prog / done from here on
+		if (tid == 0) fetch_inverse(0);
 		for (int blk = 0; blk < nblk; blk++) {
 			const int base = blk * kGsB, cnt = min(kGsB, np - base);
 			double *s_site = s_site0 + (blk & 1) * kGsSiteCols * kGsB;
@@ -396,7 +482,6 @@ k_gs_pipeline(const double4 *__restrict__ gpq, const int *__restrict__ gmeta, co
 					s_pend[(blk % kGsSlots) * kGsB * 3 + tid] += v;
 				}
 			}
-			__pipeline_wait_prior(0);
 			__syncthreads();
 			if (tid < kGsB) for (int q = 0; q < 3; q++) s_site[(7 + q) * kGsB + tid] += s_pend[((blk % kGsSlots) * kGsB + tid) * 3 + q];
 			__syncthreads();
@@ -416,7 +501,7 @@ k_gs_pipeline(const double4 *__restrict__ gpq, const int *__restrict__ gmeta, co
 							const int ch = c0 + (lane + 32 * h) / kGsRows;
 							if (ch >= nchunks) continue;
 							int spins = 0;
-							while (ld_acquire(applied + ch) < blk + 1 - kGsAhead && !ld_flag(&ctl->abort)) {
+							while (ld_acquire(applied + ch) < gbase + blk + 1 - kGsAhead && !ld_flag(&ctl->abort)) {
 								__nanosleep(100);
 								if (++spins > kGsWaitLimit) st_flag(&ctl->abort, 1);
 							}
@@ -427,53 +512,48 @@ k_gs_pipeline(const double4 *__restrict__ gpq, const int *__restrict__ gmeta, co
 				}
 				continue;
 			}
-			// (B) the walk: rhs = alpha E_s - mu_old - alpha acc, dmu = rhs + X rhs (k_gs_inverse), one row component per thread
+			// (B) the walk: rhs = alpha E_s - mu_old - alpha acc, dmu = rhs + X rhs (k_gs_inverse): a 192 x 192 triangular matrix-vector
+			// product cut in 21 tiles of 32 x 32, one or two tiles per warp, lane = row; every load has a compile-time offset (the
+			// first version walked the packed triangle with ~100 instructions of address arithmetic per 12 FMAs: 3 000 cycles)
 			double rhs_r = 0.0, al_r = 0.0, mo_r = 0.0, es_r = 0.0, a_r = 0.0;
 			const int wm = tid / 3, wq = tid - 3 * wm;                     // my site of the block and component (threads 0..191)
 			if (tid < kGsN) {
 				al_r = s_site[wm]; mo_r = s_site[(1 + wq) * kGsB + wm]; es_r = s_site[(4 + wq) * kGsB + wm]; a_r = s_site[(7 + wq) * kGsB + wm];
 				rhs_r = fma(-al_r, a_r, fma(al_r, es_r, -mo_r));
-				reinterpret_cast<double *>(s_rhs)[4 * wm + wq] = rhs_r;
+				s_rho[tid] = rhs_r;
 			}
+			mbar_wait(bar, blk & 1);                                       // the inverse has landed (every reader observes the phase itself)
 			asm volatile("bar.sync 1, %0;" :: "n"(kGsPipeThreads - 32) : "memory");
 			if (prof && tid == 0) prof[blk * 8 + 5] = clock_after(s_prog);
-			if (tid < 2 * kGsN) {
-				// two threads per row: column sites of one parity each
-				const int half = tid >= kGsN, r = tid - half * kGsN, rm = r / 3;
-				double d0 = half ? 0.0 : rhs_r, d1 = 0.0, d2 = 0.0;
-				// row r of column site j sits at gs_inv_off(j) + q rows(j) + r - 3 (j + 1)
-				const double *xj = s_mat + (r - 3) + (half ? 3 * (kGsN - 3) - 3 : 0);
-				int nr = kGsN - 3 - 3 * half;
+			{
 				if (prof && tid == 191) prof[blk * 8 + 3] = clock64();
-				// warp-uniform trip count (the rows of a warp span 11 sites), four column sites per trip: all their loads first, then
-				// the FMAs, no branch inside — a surplus step (column site past the row's own) reads valid entries and a zeroed
-				// right-hand side.  (With a branch per step the loads of a step waited for the FMAs of the one before: 115 cycles each.)
-				const int rmw = __shfl_sync(0xffffffffu, rm, 31);
-				for (int j = half; j < rmw; j += 8) {
-					double xa[4][3];
-					double4 ra[4];
+				const int wslot = warp < kLoaderWarp ? warp : warp - 1;    // 15 warps take part (the loader does not)
+				for (int t = wslot; t < kGsTiles; t += kGsPipeThreads / 32 - 1) {
+					int I = 0;
+					while (gs_tile(I + 1, 0) <= t) I++;
+					const int J = t - gs_tile(I, 0);
+					const double *xt = s_mat + t * (kGsTileDim * kGsTileDim) + lane;
+					const double2 *rh = reinterpret_cast<const double2 *>(s_rho + kGsTileDim * J);
+					double d0 = 0.0, d1 = 0.0, d2 = 0.0, d3 = 0.0;
 #pragma unroll
-					for (int u = 0; u < 4; u++) {
-						const int ju = j + 2 * u;
-						const bool ok = ju < rm;
-						const double *xp = ok ? xj : s_mat;
-						const int n1 = ok ? nr : 0;
-						xa[u][0] = xp[0]; xa[u][1] = xp[n1]; xa[u][2] = xp[2 * n1];
-						const double4 rj = s_rhs[min(ju, kGsB - 1)];
-						ra[u] = ok ? rj : make_double4(0.0, 0.0, 0.0, 0.0);
-						xj += 6 * nr - 15; nr -= 6;
+					for (int cc = 0; cc < kGsTileDim; cc += 4) {
+						const double2 r01 = rh[cc / 2], r23 = rh[cc / 2 + 1];
+						d0 = fma(xt[cc * kGsTileDim], r01.x, d0);
+						d1 = fma(xt[(cc + 1) * kGsTileDim], r01.y, d1);
+						d2 = fma(xt[(cc + 2) * kGsTileDim], r23.x, d2);
+						d3 = fma(xt[(cc + 3) * kGsTileDim], r23.y, d3);
 					}
-#pragma unroll
-					for (int u = 0; u < 4; u++) { d0 = fma(xa[u][0], ra[u].x, d0); d1 = fma(xa[u][1], ra[u].y, d1); d2 = fma(xa[u][2], ra[u].z, d2); }
+					s_tpart[t * kGsTileDim + lane] = (d0 + d1) + (d2 + d3);
 				}
-				const double dh = d0 + (d1 + d2);
-				if (half) s_wpart[r] = dh; else rhs_r = dh;
 				if (prof && tid == 191) prof[blk * 8 + 6] = clock64();
 			}
 			asm volatile("bar.sync 1, %0;" :: "n"(kGsPipeThreads - 32) : "memory");
 			if (prof && tid == 0) prof[blk * 8 + 7] = clock_after(s_prog);
+			if (tid == (kLoaderWarp + 1) * 32 && blk + 1 < nblk) fetch_inverse(blk + 1);   // s_mat is free: every warp is past the product
 			if (tid < kGsN) {
-				const double d = rhs_r + s_wpart[tid];
+				double d = rhs_r;                                              // + (X rhs)_row: the row block's tiles in a fixed order
+				const int I = tid / kGsTileDim;
+				for (int J = 0; J <= I; J++) d += s_tpart[gs_tile(I, J) * kGsTileDim + (tid & (kGsTileDim - 1))];
 				reinterpret_cast<volatile double *>(s_dm)[4 * wm + wq] = d;
 				// contract_dipoles: mu = alpha (E_s + ef_induced), ef_induced = -acc at the moment of the update  (:3583-3592):
 				// mu = mu_old + dmu; ef_induced is recovered from mu after the sweep (k_gs_efi)
@@ -515,13 +595,7 @@ k_gs_pipeline(const double4 *__restrict__ gpq, const int *__restrict__ gmeta, co
 				}
 				__threadfence();
 				__syncwarp();
-				if (lane == 0) st_flag(&ctl->solved, blk + 1);
-			} else if (blk + 1 < nblk && !(g_gs_debug & 4)) {
-				// the next block's inverse, asynchronous copies by every other warp (the matrix-vector product above is done with this one)
-				const double2 *src = (const double2 *)(tri + (size_t)(blk + 1) * kGsInv);
-				double2 *dst = (double2 *)s_mat;
-				for (int q = tid < kPublisherWarp * 32 ? tid : tid - 64; q < kGsInv / 2; q += kGsPipeThreads - 64) __pipeline_memcpy_async(dst + q, src + q, sizeof(double2));
-				__pipeline_commit();
+				if (lane == 0) st_flag(&ctl->solved, gbase + blk + 1);
 			}
 		}
 		__syncthreads();
@@ -592,18 +666,20 @@ k_gs_pipeline(const double4 *__restrict__ gpq, const int *__restrict__ gmeta, co
 	} else {
 		// single-launch fallback (MPMC_GS_FUSED=1: for tools that serialise kernel launches, e.g. ncu): the CTAs beyond the
 		// cluster do the updaters' work, one CTA per SM
-		gs_updater_body<ORTHO, EXPD>(s_raw, cta - kGsCluster, gridDim.x - kGsCluster, gpq, gmeta, order, np, c, p, acc, dmu, ctl, prof);
+		gs_updater_body<ORTHO, EXPD>(s_raw, cta - kGsCluster, gridDim.x - kGsCluster, gpq, gmeta, order, np, c, p, acc, dmu, ctl, prof, gbase);
 	}
 }
 
-// The updaters as their own kernel (2 CTAs per SM on every SM the solver's cluster leaves free — the solver needs a whole SM's shared
-// memory, the updaters need latency hiding), launched right after the solver kernel on a second stream.
+// The updaters as their own kernel (kGsUpdCtas CTAs per SM on every SM the solver's cluster leaves free — the solver needs a whole SM's
+// shared memory, the updaters need latency hiding), launched right after the solver kernel in the same stream as its programmatic
+// dependent (cudaLaunchAttributeProgrammaticStreamSerialization): it starts when the cluster is resident and never calls
+// griddepcontrol.wait — the two kernels synchronise through their own flags.
 template <bool ORTHO, bool EXPD>
 __global__ void __launch_bounds__(kGsThreads, kGsUpdCtas)
 k_gs_updaters(const double4 *__restrict__ gpq, const int *__restrict__ gmeta, const int *__restrict__ order, int np, CellDev c, PolarDev p,
-              double *acc, const double *dmu, GsCtl *ctl, long long *prof) {
+              double *acc, const double *dmu, GsCtl *ctl, long long *prof, int gbase) {
 	extern __shared__ __align__(16) double s_raw[];
-	gs_updater_body<ORTHO, EXPD>(s_raw, blockIdx.x, gridDim.x, gpq, gmeta, order, np, c, p, acc, dmu, ctl, prof);
+	gs_updater_body<ORTHO, EXPD>(s_raw, blockIdx.x, gridDim.x, gpq, gmeta, order, np, c, p, acc, dmu, ctl, prof, gbase);
 }
 
 // ef_induced of the polarizable sites after a Gauss-Seidel sweep: mu = alpha (E_s + ef_induced)  =>  ef_induced = mu / alpha - E_s

@@ -73,6 +73,23 @@ class RefSystem:
             raise RuntimeError("reference refused the input: error code %d" % lib().mref_last_error())
         self.P = lib().mref_nsys(self.h)
 
+    @classmethod
+    def from_directory(cls, directory: str, input_name: str, P: int = 0):
+        """A reference SimulationControl opened on an existing job directory exactly as it is (e.g. a copy of one of the
+        reference's shipped sample-input directories)."""
+        self = cls.__new__(cls)
+        self._tmp = None
+        cwd = os.getcwd()
+        os.chdir(directory)
+        try:
+            self.h = lib().mref_open(input_name.encode(), P)
+        finally:
+            os.chdir(cwd)
+        if not self.h:
+            raise RuntimeError("reference refused the input: error code %d" % lib().mref_last_error())
+        self.P = lib().mref_nsys(self.h)
+        return self
+
     def natoms(self, s: int = -1) -> int:
         return lib().mref_natoms(self.h, s)
 

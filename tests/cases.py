@@ -96,6 +96,31 @@ TRAJ = {
 }
 
 
+# sample directories shipped with the reference, run UNMODIFIED (file texts are stored in the golden next to the reference's trajectory):
+# name -> (directory under sample-input/, files the job reads, input file, Trotter number, steps)
+SHIPPED = {
+    # BASELINE config 1: two free argon atoms (eps = 0) at 2 K, potential == 0 -> the kinetic-energy series of the bead-spring path
+    # (src/SimulationControl.PathIntegral.cpp:810-828) and the host loop; PQR with CRYST1 / BOX pseudo-molecule / CONECT records
+    "shipped_pi000_free_argon": ("pi000-free-argon-2K", ["equilibrate.in", "Ar.pqr"], "equilibrate.in", 8, 10000),
+    # BASELINE config 2: the argon dimer (LJ pair + bead springs), as shipped
+    "shipped_pi001_argon_dimer": ("pi001-argon-dimer-2K", ["equilibrate.in", "Ar-Ar-4A.pqr"], "equilibrate.in", 8, 10000),
+}
+
+
+def load_shipped(name):
+    """-> ({file name: text}, input file name, P, reference trajectory [steps, 5])"""
+    z = np.load(os.path.join(GOLDEN_DIR, name + ".npz"))
+    files = {str(k): str(v) for k, v in zip(z["file_names"], z["file_texts"])}
+    return files, str(z["input_name"]), int(z["P"]), z["traj"]
+
+
+def write_shipped(files, directory):
+    os.makedirs(directory, exist_ok=True)
+    for k, v in files.items():
+        with open(os.path.join(directory, k), "w") as fp:
+            fp.write(v)
+
+
 # jobs whose parse (input file + PQR -> flat site table + cell) is pinned against the reference's own readers: (builder, Trotter number)
 PARSED = {
     "lj_lattice_4": (lambda: W.lj_lattice(4, 20.0), 0),

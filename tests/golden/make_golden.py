@@ -102,7 +102,36 @@ def trajectories():
         subprocess.run([sys.executable, os.path.abspath(__file__), "traj1", name], check=True)
 
 
+def one_shipped(name):
+    """A sample directory shipped with the reference, copied as it is and run by the reference itself (fresh process, see trajectories())."""
+    import shutil
+    import tempfile
+    sub, names, inp, P, steps = cases.SHIPPED[name]
+    src = os.path.join("/root/reference/sample-input", sub)
+    with tempfile.TemporaryDirectory(prefix="mref_shipped_") as d:
+        for f in names:
+            shutil.copy(os.path.join(src, f), os.path.join(d, f))
+        r = ref.RefSystem.from_directory(d, inp, P)
+        traj = r.pi_trajectory(steps) if P else r.mc_trajectory(steps)
+    texts = [open(os.path.join(src, f)).read() for f in names]
+    np.savez_compressed(os.path.join(HERE, name + ".npz"), file_names=np.array(names), file_texts=np.array(texts), input_name=np.array(inp),
+                        P=np.int32(P), traj=traj)
+    print("%-28s steps=%d acceptance=%.3f kinetic[0..2]=%s" % (name, steps, traj[:, 3].mean(), traj[:3, 4].tolist()), flush=True)
+
+
+def shipped():
+    import subprocess
+    for name in cases.SHIPPED:
+        subprocess.run([sys.executable, os.path.abspath(__file__), "shipped1", name], check=True)
+
+
 if __name__ == "__main__":
+    if len(sys.argv) > 2 and sys.argv[1] == "shipped1":
+        one_shipped(sys.argv[2])
+        sys.exit(0)
+    if len(sys.argv) > 1 and sys.argv[1] == "shipped":
+        shipped()
+        sys.exit(0)
     if len(sys.argv) > 2 and sys.argv[1] == "traj1":
         one_trajectory(sys.argv[2])
         sys.exit(0)
@@ -118,3 +147,4 @@ if __name__ == "__main__":
     main()
     parsed()
     trajectories()
+    shipped()

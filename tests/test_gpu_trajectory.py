@@ -45,3 +45,20 @@ def test_host_reader_and_energy_match_reference_fixture(tmp_path):
     e = r["ref_energy_cold"]
     assert abs(o["rd"] - e[1]) < 1e-10 * abs(e[1]) and abs(o["polar"] - e[3]) < 1e-10 * abs(e[3])
     assert o["iterations"] == int(r["ref_iterations"])
+
+
+@pytest.mark.parametrize("name", sorted(cases.SHIPPED))
+def test_shipped_sample_directory_runs_unmodified(name, tmp_path):
+    """BASELINE config 1 (sample-input/pi000-free-argon-2K, `-P 8 equilibrate.in`) with the files as shipped, through the mirror's
+    readers and the GPU engine: accept/reject decisions and the kinetic-energy series of the reference for 10^4 steps."""
+    import os
+    from mpmcxx_b200 import host_binding
+    files, inp, P, ref = cases.load_shipped(name)
+    cases.write_shipped(files, str(tmp_path))
+    log, summary = host_binding.run(os.path.join(str(tmp_path), inp), P=P, max_steps=len(ref), capacity=len(ref))
+    assert len(log) == len(ref)
+    same = (log[:, 0] == ref[:, 0]) & (log[:, 3] == ref[:, 3])
+    assert same.all(), "trajectory diverges at step %d" % int(np.argmin(same))
+    assert np.allclose(log[:, 4], ref[:, 4], rtol=1e-10, atol=0)
+    assert (np.abs(log[:, 1] - ref[:, 1]) <= 1e-10 * np.maximum(np.abs(ref[:, 1]), 1.0)).all()
+    assert summary[6] == ref[:, 3].sum()

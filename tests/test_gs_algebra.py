@@ -27,10 +27,16 @@ def t_off(i):
 
 
 def test_packed_layouts():
-    # the walk's layout: column sites back to back, 3 components x rows below the site
-    assert inv_off(0) == 0 and inv_off(B - 1) + 3 * inv_rows(B - 1) == KINV
-    for j in range(B - 1):
-        assert inv_off(j + 1) == inv_off(j) + 3 * inv_rows(j)
+    # the solver's layout: 21 tiles of 32 x 32 covering the lower triangle of the 192 x 192 inverse, tile (I, J) at I (I + 1) / 2 + J
+    tiles = sorted(I * (I + 1) // 2 + J for I in range(N // 32) for J in range(I + 1))
+    assert tiles == list(range(21)) and 21 * 32 * 32 * 8 == 172032 and (21 * 32 * 32 * 8 // 3) % 16 == 0
+    # every strictly-lower-by-site entry (r, c), c < 3 (r // 3), falls in exactly one stored tile
+    covered = np.zeros((N, N), bool)
+    for I in range(N // 32):
+        for J in range(I + 1):
+            covered[32 * I:32 * I + 32, 32 * J:32 * J + 32] = True
+    rr, cc = np.meshgrid(np.arange(N), np.arange(N), indexing="ij")
+    assert covered[cc < 3 * (rr // 3)].all()
     # the scratch layout of the substitution: rows back to back, 3 (r // 3) entries each
     assert row_off(0) == 0 and row_off(N - 1) + 3 * (B - 1) == KINV
     for r in range(N - 1):
@@ -40,13 +46,6 @@ def test_packed_layouts():
     for i in range(1, B - 1):
         assert t_off(i + 1) == t_off(i) + 6 * i
         assert row_off(3 * i) + 9 * i <= t_off(i + 1)          # X rows of site i end below tensor row i + 1
-    # pointer stepping of the walk: two threads per row, column sites of one parity each
-    for half in (0, 1):
-        x, nr = (3 * (N - 3) - 3 if half else 0), N - 3 - 3 * half
-        for j in range(half, B - 1, 2):
-            assert x == inv_off(j) - 3 * j and nr == inv_rows(j)
-            x += 6 * nr - 15
-            nr -= 6
 
 
 def _random_block(rs, n):

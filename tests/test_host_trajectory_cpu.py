@@ -69,3 +69,21 @@ def test_host_drivers_reproduce_reference_trajectory_on_cpu(host_cpu, name, tmp_
     assert summary[6] == ref[:, 3].sum() and summary[7] == len(ref) - ref[:, 3].sum()
     if P:
         assert np.allclose(log[:, 4], ref[:, 4], rtol=1e-10, atol=0)
+
+
+@pytest.mark.parametrize("name", sorted(cases.SHIPPED))
+def test_shipped_sample_directory_runs_unmodified_on_cpu(host_cpu, name, tmp_path):
+    """A sample directory shipped with the reference (BASELINE config 1: sample-input/pi000-free-argon-2K, `-P 8 equilibrate.in`), files
+    byte for byte as shipped — CRYST1 / BOX pseudo-molecule / CONECT records in the PQR, blank lines in the input file — through the
+    mirror's own readers and its path-integral driver: every decision and the kinetic-energy series of the reference
+    (src/SimulationControl.PathIntegral.cpp:810-828)."""
+    files, inp, P, ref = cases.load_shipped(name)
+    cases.write_shipped(files, str(tmp_path))
+    log, summary = _run(host_cpu, os.path.join(str(tmp_path), inp), P, len(ref))
+    assert len(log) == len(ref)
+    same = (log[:, 0] == ref[:, 0]) & (log[:, 3] == ref[:, 3])
+    assert same.all(), "trajectory diverges at step %d" % int(np.argmin(same))
+    assert np.allclose(log[:, 4], ref[:, 4], rtol=1e-10, atol=0)          # kinetic energy after every step
+    assert (np.abs(log[:, 1] - ref[:, 1]) <= 1e-10 * np.maximum(np.abs(ref[:, 1]), 1.0)).all()     # potential (identically 0 for free argon)
+    assert (np.abs(log[:, 2] - ref[:, 2]) <= 1e-9 * np.maximum(np.abs(ref[:, 2]), 1e-300)).all()
+    assert summary[6] == ref[:, 3].sum()
