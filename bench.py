@@ -451,13 +451,15 @@ def run_ours(args):
     if rank == 0 and world == 1 and not args.no_extra:
         out["extra"] = extra_workloads(engine, local, peak_tflops)
     if not args.no_extra:
-        # BASELINE config 5, the bead-sharded path-integral workload (STRONG scaling over the same N GPUs; one NCCL all-reduce per sweep)
+        # BASELINE config 5, the bead-sharded path-integral workloads (STRONG scaling over the same N GPUs; one exchange of 4 doubles per
+        # sweep): the five-site + Ewald variant (enough work per GPU for the scaling target) and the primary single-site variant
         import copy
-        a2 = copy.copy(args)
-        a2.workload, a2.steps, a2.warmup = "pi_h2_five", 100, 10
-        pi_res = run_pi(a2, embedded=True)
-        if rank == 0:
-            out.setdefault("extra", {})["pi_h2_five_bead_sharded"] = {k: pi_res[k] for k in ("value", "unit", "n_gpus", "ms_per_step", "scaling", "config", "e2e", "pair_evals_per_sec")}
+        for key, wl in (("pi_h2_five_bead_sharded", "pi_h2_five"), ("pi_h2_single_bead_sharded", "pi_h2")):
+            a2 = copy.copy(args)
+            a2.workload, a2.steps, a2.warmup = wl, 200, 20
+            pi_res = run_pi(a2, embedded=True)
+            if rank == 0:
+                out[key] = {k: pi_res[k] for k in ("value", "unit", "n_gpus", "ms_per_step", "scaling", "config", "e2e", "pair_evals_per_sec", "roofline")}
     if rank == 0:
         print(json.dumps(out, default=_np_default))
     if world > 1:
@@ -466,12 +468,17 @@ def run_ours(args):
 
 def run_pi(args, embedded=False):
     """BASELINE config 5: path-integral H2 cluster, 512 molecules x P=64 beads, beads sharded over the GPUs (strong scaling).
-    One move = bead-chain perturbation or rigid displacement of one molecule in every bead system -> mpmc_update_sites_all_beads ->
-    mpmc_pi_potential_allreduce (local sweep + ONE ncclAllReduce of 4 doubles) -> bead-spring term of the moved molecule on the host ->
-    PI_NVT_boltzmann_factor accept/reject.  Every rank replays the same RNG stream, as the reference's MPI ranks do."""
+      value : potential sweeps per second with the beads resident in HBM: K calls of mpmc_pi_potential_allreduce (structure factor of the
+              moved chunk, pair sweep over the local beads, reductions + per-bead assembly + cross-GPU exchange in one kernel, result
+              copy — one CUDA graph) timed with CUDA events on the engine's stream, max over ranks.
+      e2e   : MC moves per second through the C++ host mirror (SimulationControl::PI_nvt_mc over mpmc_host_run_sharded, one process per
+              GPU, every rank replaying the same Rando stream as the reference's MPI ranks do): move generation on the host, coordinates
+              host->device, sweep, sums device->host, PI_NVT_boltzmann_factor accept/reject, restore — wall clock of the step loop in
+              C++.  An accepted move costs a second sweep (PathIntegral.cpp:148), so e2e also reports sweeps/s."""
+    import tempfile
     import torch
     import torch.distributed as dist
-    from mpmcxx_b200 import engine, pi
+    from mpmcxx_b200 import engine, pi, host_binding
 
     rank, world, local = env_int("RANK", 0), env_int("WORLD_SIZE", 1), env_int("LOCAL_RANK", 0)
     torch.cuda.set_device(local)
@@ -490,106 +497,106 @@ def run_pi(args, embedded=False):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
 
+    def shared_uid():
+        uid = [engine.nccl_unique_id() if rank == 0 else None]
+        if world > 1:
+            dist.broadcast_object_list(uid, src=0)
+        return uid[0]
+
     P = args.beads
     five = args.workload == "pi_h2_five"
     tmpl, beads = W.pi_h2_cluster(n_side=8, P=P, five_site=five)
     lo, hi = pi.bead_range(P, rank, world)
     eng = engine.Engine(tmpl, beads=np.ascontiguousarray(beads[lo:hi]), device=local)
     if world > 1:
-        uid = [engine.nccl_unique_id() if rank == 0 else None]
-        dist.broadcast_object_list(uid, src=0)
-        eng.nccl_init(uid[0], rank, world)
+        eng.nccl_init(shared_uid(), rank, world)
     ext = torch.cuda.ExternalStream(eng.stream(), device=torch.device("cuda", local))
     rs = np.random.RandomState(4242)            # the same stream on every rank
-    T = float(tmpl.opts["temperature"])
     starts = np.nonzero(np.diff(np.concatenate([[-1], tmpl.mol])))[0]
     ends = np.concatenate([starts[1:], [tmpl.n]])
-    nchain = int(tmpl.opts["PI_trial_chain_length"])
-    pos = beads.copy()                           # every rank keeps all P geometries on the host (as the reference does)
-    u_cur, _ = eng.pi_potential_allreduce(P)
-    u_first = u_cur
+    pos = beads.copy()
+    u_first, _ = eng.pi_potential_allreduce(P)
     collective = eng.pi_collective()
-    nacc = 0
 
-    def step():
-        nonlocal u_cur, nacc
+    def move_and_sweep():
+        """one molecule moves in every bead system (what a step changes on the device), then the sweep"""
         m = rs.randint(len(starts))
         a, b = int(starts[m]), int(ends[m])
-        old = pos[:, a:b, :].copy()
-        mass = tmpl.mass[a:b]
-        com_old = (old * mass[None, :, None]).sum(1) / mass.sum()
-        if rs.random_sample() < 0.5:             # bead_perturb_probability 0.5
-            s0 = rs.randint(P)
-            idx = (s0 + np.arange(nchain)) % P
-            pos[idx, a:b, :] += rs.normal(scale=0.05, size=(nchain, 1, 3))
-            perturb = True
-        else:
-            pos[:, a:b, :] += (rs.random_sample(3) * 2 - 1) * 0.3
-            perturb = False
+        pos[:, a:b, :] += rs.normal(scale=0.02, size=(P, 1, 3))
         eng.update_sites_all_beads(a, pos[lo:hi, a:b, :])
-        u_new, _ = eng.pi_potential_allreduce(P)
-        if perturb:
-            com_new = (pos[:, a:b, :] * mass[None, :, None]).sum(1) / mass.sum()
-            dchain = pi.chain_mass_len2(com_new, float(mass.sum())) - pi.chain_mass_len2(com_old, float(mass.sum()))
-            bf = pi.bead_perturb_boltzmann(u_new - u_cur, dchain, P, T)
-        else:
-            bf = float(np.exp(min(0.0, -(u_new - u_cur) / T)))
-        if np.isfinite(u_new) and rs.random_sample() < bf:
-            u_cur = u_new
-            nacc += 1
-        else:
-            pos[:, a:b, :] = old
-            eng.update_sites_all_beads(a, pos[lo:hi, a:b, :])
-        return u_new
+        return eng.pi_potential_allreduce(P)[0]
 
     peak_tflops, _ = engine.probe_fp64_peak(local)
     for _ in range(args.warmup):
-        step()
+        move_and_sweep()
     clocks = ClockSampler(local)
     barrier()
     clocks.start()
     l0 = eng.launches()
-    eng.set_timing(True)
-    t0 = time.perf_counter()
+    # device-resident: K sweeps (each after a one-molecule move, so that the incremental structure factor does its real work: the
+    # coordinate upload itself is outside the events), CUDA events on the engine's stream
+    t_dev_ms = 0.0
     for _ in range(args.steps):
-        step()
+        m = rs.randint(len(starts))
+        a, b = int(starts[m]), int(ends[m])
+        pos[:, a:b, :] += rs.normal(scale=0.02, size=(P, 1, 3))
+        eng.update_sites_all_beads(a, pos[lo:hi, a:b, :])
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(ext)
+        u_last = eng.pi_potential_allreduce(P)[0]
+        e1.record(ext)
+        e1.synchronize()
+        t_dev_ms += e0.elapsed_time(e1)
     barrier()
-    t_wall = max_over_ranks(time.perf_counter() - t0)
+    t_dev = max_over_ranks(t_dev_ms * 1e-3)
+    launches = eng.launches() - l0
+    # per-kernel-class durations (their own pass: event pairs disable the graph)
+    eng.set_timing(True)
+    for _ in range(args.steps):
+        move_and_sweep()
     timing = eng.timing()
     eng.set_timing(False)
-    # device-resident: K sweeps + all-reduce, CUDA events on the engine's stream
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    barrier()
-    e0.record(ext)
-    for _ in range(args.steps):
-        eng.pi_potential_allreduce(P)
-    e1.record(ext)
-    e1.synchronize()
-    barrier()
-    t_dev = max_over_ranks(e0.elapsed_time(e1) * 1e-3)
-    clk = clocks.stop()
-    launches = eng.launches() - l0
     out1 = eng.energy_all()[0]
+    eng.close()
+    # ---- e2e through the C++ mirror -----------------------------------------------------------------------------------
+    e2e_steps = max(args.steps, 200)
+    t = tmpl.copy()
+    t.opts.update({"seed": "1", "numsteps": str(e2e_steps + 50), "corrtime": "1000000"})
+    d = tempfile.mkdtemp(prefix="mpmc_pi_bench_")
+    inp = W.write_reference_job(t, d)
+    uid2 = shared_uid()
+    barrier()
+    host_binding.run_sharded(inp, P, rank, world, local, uid2, max_steps=50, capacity=50)          # warm-up run (graph capture, allocations)
+    barrier()
+    log, summary = host_binding.run_sharded(inp, P, rank, world, local, shared_uid(), max_steps=e2e_steps, capacity=e2e_steps)
+    loop_s, loop_sweeps = host_binding.last_stats()
+    barrier()
+    clk = clocks.stop()
+    t_wall = max_over_ranks(loop_s)
+    acc = float(log[:, 3].mean())
     pairs_per_sweep = out1["n_pair_evals"] * P
     pk = timing["pair"]
     kms = pk[0] / max(pk[1], 1)
     flop = (FLOP_PER_ES_PAIR if five else FLOP_PER_LJ_PAIR) * out1["n_pair_evals"] * (hi - lo)
     ach = flop / (kms * 1e-3) / 1e12 if kms > 0 else float("nan")
-    res = {"metric": "mc_moves_per_sec", "value": args.steps / t_dev, "unit": "moves/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+    res = {"metric": "mc_moves_per_sec", "value": args.steps / t_dev, "unit": "sweeps/s (one potential sweep over all beads; a rejected move costs one, an accepted move two)",
+           "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
            "ms_per_step": 1e3 * t_dev / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-           "config": {"workload": "config5: path-integral H2 cluster, 512 molecules x %d beads, %s, beads sharded %d per GPU, one all-reduce of 4 doubles per sweep (see `collective`)"
+           "config": {"workload": "config5: path-integral H2 cluster, 512 molecules x %d beads, %s, beads sharded %d per GPU, one exchange of 4 doubles per sweep (see `collective`)"
                                   % (P, "five-site H2 + Ewald (N=2560 per bead)" if five else "single-site H2, rd_only (N=512 per bead)", hi - lo),
                       "l2": "inputs are < 1 MB per rank and L2-resident by nature; no flush (latency-bound path)", "pair_evals_per_sweep": pairs_per_sweep,
                       "collective": collective,
-                      "potential_of_start_configuration_K": u_first, "potential_after_run_K": u_cur},
+                      "potential_of_start_configuration_K": u_first, "potential_after_run_K": u_last},
            "clocks": clk,
-           "e2e": {"value": args.steps / t_wall, "unit": "moves/s", "h2d_bytes_per_step": 32 * (ends[0] - starts[0]) * (hi - lo), "d2h_bytes_per_step": 32,
-                   "ms_per_step": 1e3 * t_wall / args.steps, "acceptance": nacc / (args.steps + args.warmup)},
+           "e2e": {"value": e2e_steps / t_wall, "unit": "moves/s", "sweeps_per_s": loop_sweeps / t_wall, "sweeps_per_move": loop_sweeps / e2e_steps,
+                   "h2d_bytes_per_step": 32 * int(ends[0] - starts[0]) * (hi - lo) * (2 - acc), "d2h_bytes_per_step": 48 * loop_sweeps / e2e_steps,
+                   "ms_per_step": 1e3 * t_wall / e2e_steps, "acceptance": acc, "steps": e2e_steps,
+                   "through": "C++ host mirror: SimulationControl::PI_nvt_mc via mpmc_host_run_sharded, one process per GPU"},
            "gpu_launches": int(launches), "pair_evals_per_sec": pairs_per_sweep * args.steps / t_dev,
            "roofline": {"kernel": "pair", "bound": "fp64", "achieved": ach, "peak": peak_tflops, "unit": "TFLOP/s", "frac": ach / peak_tflops, "traffic": None,
                         "ms_per_launch": kms, "peak_source": "measured in this run (DFMA probe)",
                         "kernel_ms_per_step": {k: v[0] / args.steps for k, v in timing.items() if v[1]}}}
-    eng.close()
     if embedded:
         return res
     if rank == 0:

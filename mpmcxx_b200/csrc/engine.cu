@@ -29,6 +29,7 @@
 #include "kernels_polar.cuh"
 #include "kernels_polar2.cuh"
 #include "kernels_recip.cuh"
+#include "kernels_pi.cuh"
 
 using namespace mpmc;
 
@@ -149,7 +150,14 @@ struct mpmc_engine {
 	int pair_ctr_start = 0;
 	DevBuf<double2> d_slj;
 	DevBuf<double4> d_spq, d_stage;
-	bool perm_identity = true;
+	DevBuf<int> d_iperm;             // site -> position in the class-sorted table (k_scatter_sites keeps d_spq current)
+	bool perm_identity = true, spq_valid = false;
+	// mobile structure factor: the chunk partials stay valid between evaluations; only chunks holding a moved site are recomputed
+	bool sk_valid = false;
+	std::vector<int> sk_dirty;
+	DevBuf<int> d_sk_dirty, d_pi_done;
+	int *h_sk_dirty = nullptr;
+	long long xchg_timeout_cycles = 0;
 	DevBuf<double> d_erf_tab;
 	int pair_grid = 0;
 	DevBuf<unsigned char> d_mol_mobile;
@@ -183,11 +191,14 @@ struct mpmc_engine {
 	DevBuf<unsigned long long> d_rmin;
 	DevBuf<double> d_result;
 	// pinned staging
-	double4 *h_stage = nullptr; size_t stage_cap = 0;
+	double4 *h_stage[2] = {nullptr, nullptr}; size_t stage_cap[2] = {0, 0};   // two slots: a restore and the next move may both be in flight
+	bool stage_busy[2] = {false, false};
+	int stage_next = 0;
 	double *h_result = nullptr;
 	int *h_flags = nullptr;
 	// polarization bookkeeping of the last energy()
 	int last_iterations = 0;
+	std::vector<int> last_iters;    // per bead system
 	std::vector<int> last_failed;
 	bool enqueued = false;
 	int gs_grid = 0;
@@ -203,7 +214,7 @@ struct mpmc_engine {
 	DevBuf<long long> d_step;
 	// the path-integral sweep (kernels + all-reduce + result copy) as a CUDA graph: one launch per Monte Carlo move
 	cudaGraphExec_t pi_graph = nullptr;
-	bool pi_graph_off = false;
+	bool pi_graph_off = false, pi_warm = false;   // pi_warm: one sweep has run outside a capture (every buffer it needs exists)
 	long long pi_graph_launches = 0;
 	double *h_pisums = nullptr;
 	// optional per-kernel-class timing with CUDA events on the engine's stream (mpmc_set_timing)
@@ -247,6 +258,8 @@ void collect_timing(mpmc_engine *e) {   // call after a stream synchronize
 // host helpers
 // ------------------------------------------------------------------------------------------------------------
 namespace {
+
+int sync_stream(mpmc_engine *e);
 
 // PeriodicBoundary::update (src/PeriodicBoundary.cpp:31-101) + update_pbc alphas (src/System.cpp:871-874)
 int compute_cell(mpmc_engine *e, const double basis[9]) {
@@ -306,8 +319,9 @@ int compute_cell(mpmc_engine *e, const double basis[9]) {
 	int rc = e->d_kvec.ensure(e->kvec.size());
 	if (rc) return rc;
 	if (!e->kvec.empty()) CK(cudaMemcpyAsync(e->d_kvec.p, e->kvec.data(), e->kvec.size() * sizeof(KVec), cudaMemcpyHostToDevice, e->stream));
-	CK(cudaStreamSynchronize(e->stream));
+	{ int _rc = sync_stream(e); if (_rc) return _rc; }
 	e->frozen_sk_dirty = true;
+	e->sk_valid = false;
 	e->topo_dirty = true;   // LRC and self terms depend on volume / cutoff / alpha
 	return MPMC_OK;
 }
@@ -364,7 +378,7 @@ int rebuild_topology(mpmc_engine *e) {
 	if ((rc = up(e->d_plist, e->plist)) || (rc = up(e->d_mobile_q, e->mobile_q)) ||
 	    (rc = up(e->d_frozen_q, e->frozen_q)) || (rc = up(e->d_mol_start, e->mol_start)) ||
 	    (rc = up(e->d_mol_mobile, e->mol_mobile))) return rc;
-	CK(cudaStreamSynchronize(e->stream));   // the std::vectors above go out of scope / may be rebuilt
+	{ int _rc = sync_stream(e); if (_rc) return _rc; }   // the std::vectors above go out of scope / may be rebuilt
 	if ((rc = prepare_pair_sweep(e))) return rc;
 	if ((rc = prepare_polar(e))) return rc;
 
@@ -397,6 +411,7 @@ int rebuild_topology(mpmc_engine *e) {
 			if (!e->h_frozen[i]) e->es_self -= c.ewald_alpha * e->h_q[i] * e->h_q[i] / std::sqrt(kPi);   // System.Energy.cpp:1626-1643
 	e->topo_dirty = false;
 	e->frozen_sk_dirty = true;
+	e->sk_valid = false;
 	return MPMC_OK;
 }
 
@@ -448,7 +463,9 @@ int prepare_pair_sweep(mpmc_engine *e) {
 	std::stable_sort(perm.begin(), perm.end(), [&](int a, int b) { return cls[a] < cls[b]; });
 	e->perm_identity = true;
 	for (int k = 0; k < n; k++) e->perm_identity = e->perm_identity && perm[k] == k;
-	std::vector<int> pm(n);
+	std::vector<int> pm(n), iperm(n);
+	for (int k = 0; k < n; k++) iperm[perm[k]] = k;
+	e->spq_valid = false;
 	std::vector<double2> slj(n);
 	int cbeg[9];
 	{
@@ -536,13 +553,14 @@ int prepare_pair_sweep(mpmc_engine *e) {
 	CK(cudaMemcpyAsync(e->d_item_col.p, item_col.data(), (K + 1) * sizeof(int), cudaMemcpyHostToDevice, e->stream));
 	e->pair_ctr_start = e->pair_grid * pair_warps(es);
 	CK(cudaMemcpyAsync(e->d_item_ctr.p, &e->pair_ctr_start, sizeof(int), cudaMemcpyHostToDevice, e->stream));
-	if ((rc2 = e->d_pmeta.ensure(std::max(n, 1))) || (rc2 = e->d_segs.ensure(std::max<size_t>(e->segs.size(), 1))) || (rc2 = e->d_perm.ensure(std::max(n, 1))) ||
+	if ((rc2 = e->d_pmeta.ensure(std::max(n, 1))) || (rc2 = e->d_segs.ensure(std::max<size_t>(e->segs.size(), 1))) || (rc2 = e->d_perm.ensure(std::max(n, 1))) || (rc2 = e->d_iperm.ensure(std::max(n, 1))) ||
 	    (rc2 = e->d_slj.ensure(std::max(n, 1))) || (rc2 = e->d_spq.ensure((size_t)e->B * e->cap))) return rc2;
 	CK(cudaMemcpyAsync(e->d_pmeta.p, pm.data(), n * sizeof(int), cudaMemcpyHostToDevice, e->stream));
 	CK(cudaMemcpyAsync(e->d_perm.p, perm.data(), n * sizeof(int), cudaMemcpyHostToDevice, e->stream));
+	CK(cudaMemcpyAsync(e->d_iperm.p, iperm.data(), n * sizeof(int), cudaMemcpyHostToDevice, e->stream));
 	CK(cudaMemcpyAsync(e->d_slj.p, slj.data(), n * sizeof(double2), cudaMemcpyHostToDevice, e->stream));
 	if (!e->segs.empty()) CK(cudaMemcpyAsync(e->d_segs.p, e->segs.data(), e->segs.size() * sizeof(PairSeg), cudaMemcpyHostToDevice, e->stream));
-	CK(cudaStreamSynchronize(e->stream));
+	{ int _rc = sync_stream(e); if (_rc) return _rc; }
 	return MPMC_OK;
 }
 
@@ -600,43 +618,66 @@ int prepare_polar(mpmc_engine *e) {
 			CK(cudaMemcpyAsync(e->d_field_tab.p, e->field_tab.rows.data(), e->field_tab.rows.size() * sizeof(double), cudaMemcpyHostToDevice, e->stream));
 		}
 	}
+	{ int _rc = sync_stream(e); if (_rc) return _rc; }
+	return MPMC_OK;
+}
+
+constexpr int kSkMaxDirty = 8;   // chunks of the mobile structure factor recomputed per evaluation before a full pass is cheaper
+
+// every cudaStreamSynchronize of the engine's stream goes through here: whatever was staged has been consumed
+int sync_stream(mpmc_engine *e) {
 	CK(cudaStreamSynchronize(e->stream));
+	e->stage_busy[0] = e->stage_busy[1] = false;
 	return MPMC_OK;
 }
 
-int ensure_stage(mpmc_engine *e, size_t count) {
-	if (count <= e->stage_cap) return MPMC_OK;
-	if (e->h_stage) cudaFreeHost(e->h_stage);
-	e->h_stage = nullptr; e->stage_cap = 0;
+int ensure_stage(mpmc_engine *e, int slot, size_t count) {
+	if (count <= e->stage_cap[slot]) return MPMC_OK;
+	if (e->stage_busy[0] || e->stage_busy[1]) { int rc = sync_stream(e); if (rc) return rc; }
+	if (e->h_stage[slot]) cudaFreeHost(e->h_stage[slot]);
+	e->h_stage[slot] = nullptr; e->stage_cap[slot] = 0;
 	size_t want = std::max<size_t>(count, 1024);
-	CK(cudaMallocHost(&e->h_stage, want * sizeof(double4)));
-	e->stage_cap = want;
+	CK(cudaMallocHost(&e->h_stage[slot], want * sizeof(double4)));
+	e->stage_cap[slot] = want;
 	return MPMC_OK;
 }
 
-// copy sites [first, first+count) of every bead (or one bead) from the shadow to the device posq array
+// the chunks of the mobile structure factor that hold sites [first, first + count)
+void mark_moved(mpmc_engine *e, int first, int count) {
+	if (!e->sk_valid) return;
+	const auto lo = std::lower_bound(e->mobile_q.begin(), e->mobile_q.end(), first) - e->mobile_q.begin();
+	const auto hi = std::lower_bound(e->mobile_q.begin(), e->mobile_q.end(), first + count) - e->mobile_q.begin();
+	if (hi <= lo) return;
+	for (int c = (int)lo / kSkSites; c <= (int)(hi - 1) / kSkSites; c++)
+		if (std::find(e->sk_dirty.begin(), e->sk_dirty.end(), c) == e->sk_dirty.end()) e->sk_dirty.push_back(c);
+	if ((int)e->sk_dirty.size() > kSkMaxDirty) { e->sk_valid = false; e->sk_dirty.clear(); }
+}
+
+// copy sites [first, first+count) of every bead (or one bead) from the shadow to the device: one pinned staging slot, one
+// host-to-device copy, one scatter into posq (and into the class-sorted copy the pair sweep reads).  No stream synchronisation
+// unless both slots are still in flight.
 int push_positions(mpmc_engine *e, int bead_lo, int bead_hi, int first, int count) {
 	if (count <= 0) return MPMC_OK;
 	const int nb = bead_hi - bead_lo;
-	int rc = ensure_stage(e, (size_t)nb * count);
-	if (rc) return rc;
-	CK(cudaStreamSynchronize(e->stream));   // the staging buffer may still be in flight from the previous move
+	const int slot = e->stage_next;
+	e->stage_next ^= 1;
+	int rc;
+	if (e->stage_busy[slot] && (rc = sync_stream(e))) return rc;   // the slot may still be in flight from two updates ago
+	if ((rc = ensure_stage(e, slot, (size_t)nb * count))) return rc;
+	double4 *hs = e->h_stage[slot];
 	for (int b = 0; b < nb; b++)
 		for (int i = 0; i < count; i++) {
 			const double *p = &e->h_pos[((size_t)(bead_lo + b) * e->n + first + i) * 3];
-			e->h_stage[(size_t)b * count + i] = make_double4(p[0], p[1], p[2], e->h_q[first + i]);
+			hs[(size_t)b * count + i] = make_double4(p[0], p[1], p[2], e->h_q[first + i]);
 		}
-	if (nb == 1) {
-		CK(cudaMemcpyAsync(e->d_posq.p + (size_t)bead_lo * e->cap + first, e->h_stage, count * sizeof(double4), cudaMemcpyHostToDevice, e->stream));
-	} else {
-		// one copy for all bead systems, then a scatter into the per-bead rows of posq
-		int rc2 = e->d_stage.ensure((size_t)nb * count);
-		if (rc2) return rc2;
-		CK(cudaMemcpyAsync(e->d_stage.p, e->h_stage, (size_t)nb * count * sizeof(double4), cudaMemcpyHostToDevice, e->stream));
-		k_scatter_sites<<<(nb * count + 127) / 128, 128, 0, e->stream>>>(e->d_stage.p, e->d_posq.p, e->cap, bead_lo, nb, first, count);
-		e->launches++;
-		CK(cudaGetLastError());
-	}
+	if ((rc = e->d_stage.ensure((size_t)nb * count))) return rc;
+	CK(cudaMemcpyAsync(e->d_stage.p, hs, (size_t)nb * count * sizeof(double4), cudaMemcpyHostToDevice, e->stream));
+	e->stage_busy[slot] = true;
+	const bool sorted_copy = !e->perm_identity && e->d_iperm.p && e->d_spq.p;
+	k_scatter_sites<<<(nb * count + 127) / 128, 128, 0, e->stream>>>(e->d_stage.p, e->d_posq.p, e->cap, bead_lo, nb, first, count,
+	                                                                 sorted_copy ? e->d_iperm.p : nullptr, sorted_copy ? e->d_spq.p : nullptr);
+	e->launches++;
+	CK(cudaGetLastError());
 	return MPMC_OK;
 }
 
@@ -666,6 +707,7 @@ template <class K> int set_smem(K kernel, size_t bytes) {
 
 static void drop_pi_graph(mpmc_engine *e) {
 	if (e->pi_graph) { cudaGraphExecDestroy(e->pi_graph); e->pi_graph = nullptr; }
+	e->pi_warm = false;
 }
 
 static int adopt_table(mpmc_engine *e) {
@@ -685,23 +727,49 @@ static int adopt_table(mpmc_engine *e) {
 // ---- energy ----------------------------------------------------------------------------------------------
 #define LAUNCHED(e) ((e)->launches++)
 
-static int run_structure(mpmc_engine *e, DevBuf<int> &list, int nlist, DevBuf<double2> &S, const double2 *addend, cudaStream_t stream = nullptr) {
+// chunk partials of a structure factor (all chunks, or only those listed in d_sk_dirty) and, unless `reduce` is false, their sum
+static int run_structure(mpmc_engine *e, DevBuf<int> &list, int nlist, DevBuf<double2> &S, const double2 *addend, cudaStream_t stream = nullptr,
+                         bool dirty_only = false, bool reduce = true) {
 	if (!stream) stream = e->stream;
 	const int nk = (int)e->kvec.size(), kmax = e->cfg.ewald_kmax, B = e->B;
 	int rc;
 	if ((rc = S.ensure((size_t)B * nk))) return rc;
 	const int nchunks = (nlist + kSkSites - 1) / kSkSites;
 	if (nchunks > 0) {
+		if (e->d_sk_part.cap < (size_t)B * nchunks * nk) { e->sk_valid = false; dirty_only = false; }
 		if ((rc = e->d_sk_part.ensure((size_t)B * nchunks * nk))) return rc;
 		const size_t smem = sizeof(double2) * kSkSites * 3 * (kmax + 1);
-{ Timed _t(e, MPMC_K_STRUCTURE);
-		k_structure_partial<<<dim3(nchunks, B), kSkThreads, smem, stream>>>(e->d_posq.p, e->cap, list.p, nlist, e->d_kvec.p, nk, kmax, e->cell,
-		                                                                        e->d_sk_part.p, nchunks);
+		Timed _t(e, MPMC_K_STRUCTURE);
+		if (dirty_only)
+			k_structure_partial<<<dim3(std::min(kSkMaxDirty, nchunks), B), kSkThreads, smem, stream>>>(e->d_posq.p, e->cap, list.p, nlist, e->d_kvec.p, nk, kmax, e->cell,
+			                                                                                        e->d_sk_part.p, nchunks, e->d_sk_dirty.p);
+		else
+			k_structure_partial<<<dim3(nchunks, B), kSkThreads, smem, stream>>>(e->d_posq.p, e->cap, list.p, nlist, e->d_kvec.p, nk, kmax, e->cell,
+			                                                                        e->d_sk_part.p, nchunks, nullptr);
 		LAUNCHED(e);
- }	}
-	k_structure_reduce<<<dim3((nk + 127) / 128, B), 128, 0, stream>>>(e->d_sk_part.p, nchunks, nk, S.p, addend);
-	LAUNCHED(e);
+	}
+	if (reduce) {
+		k_structure_reduce<<<dim3((nk + 127) / 128, B), 128, 0, stream>>>(e->d_sk_part.p, nchunks, nk, S.p, addend);
+		LAUNCHED(e);
+	}
 	CK(cudaGetLastError());
+	return MPMC_OK;
+}
+
+// the mobile sites' structure factor: only the chunks that hold a moved site when the stored partials are still valid (the list of
+// dirty chunks travels in a pinned word array, so the same launch can sit in a CUDA graph)
+static int run_structure_mobile(mpmc_engine *e, cudaStream_t stream, bool reduce) {
+	const int nlist = (int)e->mobile_q.size();
+	const bool inc = e->sk_valid && nlist > 0;
+	if (inc) {
+		e->h_sk_dirty[0] = (int)e->sk_dirty.size();
+		for (size_t i = 0; i < e->sk_dirty.size(); i++) e->h_sk_dirty[1 + i] = e->sk_dirty[i];
+		CK(cudaMemcpyAsync(e->d_sk_dirty.p, e->h_sk_dirty, sizeof(int) * (1 + kSkMaxDirty), cudaMemcpyHostToDevice, stream ? stream : e->stream));
+	}
+	int rc = run_structure(e, e->d_mobile_q, nlist, e->d_S_mobile, nullptr, stream, inc, reduce);
+	if (rc) return rc;
+	e->sk_valid = nlist > 0;
+	e->sk_dirty.clear();
 	return MPMC_OK;
 }
 
@@ -831,159 +899,179 @@ static int run_polar(mpmc_engine *e) {
 	} else CK(cudaMemsetAsync(e->d_rank.p, 0, sizeof(double) * (size_t)B * n, e->stream));
 
 	e->last_iterations = 0;
+	e->last_iters.assign(B, 0);
 	std::fill(e->last_failed.begin(), e->last_failed.end(), 0);
 	if (cf.polar_zodid || np == 0) return MPMC_OK;
-	if (pd.gs && B != 1) FAIL(MPMC_ERR_UNSUPPORTED, "Gauss-Seidel polarization with n_beads > 1 is not supported yet");
 
 	const bool need_old = cf.polar_rrms || cf.polar_precision > 0 || cf.polar_sor || cf.polar_esor;
 	const bool want_check = cf.polar_rrms || cf.polar_precision > 0;
 	const bool expd = cf.damp_type == MPMC_DAMPING_EXPONENTIAL;
-	// one contraction sweep acc_i = sum_j T_ij mu_j over a row list, then the epilogue of `mode`
-	auto contract = [&](int mode, const int *rowlist, int nrows, double *out_acc) -> int {
-		if (nrows <= 0) return MPMC_OK;
-		const dim3 grid((nrows + kOrdI - 1) / kOrdI, e->ct_parts, B);
-		if (expd) k_contract_parts<ORTHO, true><<<grid, kOrdThreads, 0, e->stream>>>(e->d_posq.p, e->d_alpha.p, e->d_meta.p, e->d_plist.p, np, e->ct_part_len,
-		                                                                         rowlist, nrows, n, e->cap, e->cell, pd, e->d_mu.p, e->d_cparts.p);
-		else k_contract_parts<ORTHO, false><<<grid, kOrdThreads, 0, e->stream>>>(e->d_posq.p, e->d_alpha.p, e->d_meta.p, e->d_plist.p, np, e->ct_part_len,
-		                                                                        rowlist, nrows, n, e->cap, e->cell, pd, e->d_mu.p, e->d_cparts.p);
-		const int fb = 128, fg = (nrows * B + fb - 1) / fb;
-#define FINISH(M) k_contract_finish<M><<<fg, fb, 0, e->stream>>>(e->d_cparts.p, e->ct_parts, rowlist, nrows, n, B, e->d_alpha.p, e->d_efs.p, e->d_efi.p, e->d_new_mu.p, e->d_efic.p, out_acc)
-		if (mode == SWEEP_JACOBI) FINISH(SWEEP_JACOBI);
-		else if (mode == SWEEP_ACC) FINISH(SWEEP_ACC);
-		else FINISH(SWEEP_PALMO);
+	if (pd.gs && (rc = e->d_acc.ensure(len))) return rc;
+
+	// thole_iterative() (:3450-3543) for the bead systems [b0, b0 + nb).  The reference runs it per bead system, each with its own
+	// iteration count and failure flag (PathIntegral.cpp:770-780): bead systems are solved together only where that cannot change a
+	// result — a fixed iteration count without Gauss-Seidel ordering.  With polar_precision, or with the Gauss-Seidel pipeline (one
+	// cluster walks one system's sweep order), they are solved one after the other (nb = 1).
+	auto solve = [&](int b0, int nb) -> int {
+		const size_t o3 = (size_t)b0 * n * 3, o1 = (size_t)b0 * n, blen = (size_t)nb * n * 3;
+		const double4 *posq = e->d_posq.p + (size_t)b0 * e->cap;
+		double *mu = e->d_mu.p + o3, *new_mu = e->d_new_mu.p + o3, *old_mu = e->d_old_mu.p + o3, *efs = e->d_efs.p + o3, *efi = e->d_efi.p + o3,
+		       *efic = e->d_efic.p + o3, *rrms = e->d_rrms.p + o1, *rank = e->d_rank.p + o1;
+		double *acc = pd.gs ? e->d_acc.p + o3 : nullptr;
+		// one contraction sweep acc_i = sum_j T_ij mu_j over a row list, then the epilogue of `mode`
+		auto contract = [&](int mode, const int *rowlist, int nrows, double *out_acc) -> int {
+			if (nrows <= 0) return MPMC_OK;
+			const dim3 grid((nrows + kOrdI - 1) / kOrdI, e->ct_parts, nb);
+			if (expd) k_contract_parts<ORTHO, true><<<grid, kOrdThreads, 0, e->stream>>>(posq, e->d_alpha.p, e->d_meta.p, e->d_plist.p, np, e->ct_part_len,
+			                                                                         rowlist, nrows, n, e->cap, e->cell, pd, mu, e->d_cparts.p);
+			else k_contract_parts<ORTHO, false><<<grid, kOrdThreads, 0, e->stream>>>(posq, e->d_alpha.p, e->d_meta.p, e->d_plist.p, np, e->ct_part_len,
+			                                                                        rowlist, nrows, n, e->cap, e->cell, pd, mu, e->d_cparts.p);
+			const int fb = 128, fg = (nrows * nb + fb - 1) / fb;
+#define FINISH(M) k_contract_finish<M><<<fg, fb, 0, e->stream>>>(e->d_cparts.p, e->ct_parts, rowlist, nrows, n, nb, e->d_alpha.p, efs, efi, new_mu, efic, out_acc)
+			if (mode == SWEEP_JACOBI) FINISH(SWEEP_JACOBI);
+			else if (mode == SWEEP_ACC) FINISH(SWEEP_ACC);
+			else FINISH(SWEEP_PALMO);
 #undef FINISH
-		e->launches += 2;
-		CK(cudaGetLastError());
+			e->launches += 2;
+			CK(cudaGetLastError());
+			return MPMC_OK;
+		};
+		int it = 0;
+		bool keep = true, acc_stale = false;
+		const int *gs_order = e->d_plist.p;
+		while (keep) {
+			it++;
+			if (it >= 128 && cf.polar_precision > 0) {   // MAX_ITERATION_COUNT (constants.h:52), System.Energy.cpp:3483-3494
+				for (int b = b0; b < b0 + nb; b++) {
+					k_dipole_fail<<<(n * 3 + eb - 1) / eb, eb, 0, e->stream>>>(e->d_alpha.p, e->d_efs.p, n, (size_t)b * n * 3, e->d_mu.p, e->d_efic.p);
+					LAUNCHED(e);
+					e->last_failed[b] = 1;
+				}
+				break;
+			}
+			if (need_old) CK(cudaMemcpyAsync(old_mu, mu, blen * sizeof(double), cudaMemcpyDeviceToDevice, e->stream));
+			if (!pd.gs) {
+				Timed _t(e, MPMC_K_DIPOLE_SWEEP);
+				if ((rc = contract(SWEEP_JACOBI, e->d_plist.p, np, nullptr))) return rc;
+			} else {
+				// Gauss-Seidel pipeline (kernels_gs.cuh).  First sweep in list order (ranked_array = identity, :3463); from the second
+				// sweep on in rank order when polar_gs_ranked (update_ranking after the first pass, :3522-3523).
+				const int nblk = (np + kGsB - 1) / kGsB, nchunks = (np + kGsRows - 1) / kGsRows;
+				if ((rc = e->d_dmu.ensure((size_t)np * 3)) || (rc = e->d_tri.ensure((size_t)nblk * kGsMat)) || (rc = e->d_near.ensure((size_t)nblk * kGsNearPerBlock)) ||
+				    (rc = e->d_gsctl.ensure(sizeof(GsCtl) / sizeof(int) + nchunks)) || (rc = e->d_gpq.ensure(np)) || (rc = e->d_gmeta.ensure(np))) return rc;
+				if (it == 1 || acc_stale) {
+					Timed _t(e, MPMC_K_DIPOLE_SWEEP);
+					if ((rc = contract(SWEEP_ACC, e->d_plist.p, np, acc))) return rc;
+					acc_stale = false;
+				}
+				if (it == 1 || (ranked && it == 2)) {
+					gs_order = e->d_plist.p;
+					if (ranked && it == 2) {
+						k_rank_order_plist<<<(np + kOrdI - 1) / kOrdI, kOrdThreads, 0, e->stream>>>(rank, e->d_plist.p, np, e->d_order.p);
+						LAUNCHED(e);
+						gs_order = e->d_order.p;
+					}
+					Timed _t(e, MPMC_K_GS_SWEEP);
+					k_gs_gather<<<(np + 255) / 256, 256, 0, e->stream>>>(posq, e->d_alpha.p, e->d_meta.p, gs_order, np, e->d_gpq.p, e->d_gmeta.p);
+					k_gs_inverse<ORTHO><<<nblk, kGsThreads, kGsInverseSmemBytes, e->stream>>>(e->d_gpq.p, e->d_gmeta.p, np, e->cell, pd, e->d_tri.p);
+					k_gs_near<ORTHO><<<nblk, kGsPipeThreads, 0, e->stream>>>(e->d_gpq.p, e->d_gmeta.p, np, e->cell, pd, e->d_near.p);
+					e->launches += 3;
+				}
+				int ns = 1;
+				if (!need_old && !want_check && cf.polar_precision == 0.0) ns = (ranked && it == 1) ? 1 : (cf.polar_max_iter - it + 1);
+				long long *prof = nullptr;
+				if (e->gs_prof_enabled) {
+					if ((rc = e->d_gsprof.ensure((size_t)nblk * 16))) return rc;
+					CK(cudaMemsetAsync(e->d_gsprof.p, 0, sizeof(long long) * nblk * 16, e->stream));
+					prof = e->d_gsprof.p;
+					e->gs_prof_nblk = nblk;
+				}
+				{
+					Timed _t(e, MPMC_K_GS_SWEEP);
+					for (int sw = 0; sw < ns; sw++) {   // one launch per sweep: the kernel boundary is the barrier between sweeps
+						// flags count from generation << 16, so nothing is cleared between sweeps (kernels_gs.cuh); zero them when the generation wraps
+						if (e->gs_gen == 0 || e->gs_gen >= (1 << (30 - kGsGenShift)) || e->gs_ctl_len != sizeof(GsCtl) / sizeof(int) + (size_t)nchunks) {
+							e->gs_ctl_len = sizeof(GsCtl) / sizeof(int) + (size_t)nchunks;
+							CK(cudaMemsetAsync(e->d_gsctl.p, 0, sizeof(int) * e->gs_ctl_len, e->stream));
+							e->gs_gen = 0;
+						}
+						if (nblk >= (1 << kGsGenShift) - kGsAhead - 2) FAIL(MPMC_ERR_UNSUPPORTED, "Gauss-Seidel pipeline: too many polarizable sites (%d)", np);
+						const int gbase = ++e->gs_gen << kGsGenShift;
+						const int sgrid = e->gs_fused ? e->gs_fused_grid : kGsCluster;
+						if (expd) k_gs_pipeline<ORTHO, true><<<sgrid, kGsPipeThreads, kGsSmemBytes, e->stream>>>(e->d_gpq.p, e->d_gmeta.p, gs_order, np, e->cell, pd, efs,
+						        mu, efi, new_mu, acc, e->d_dmu.p, e->d_tri.p, e->d_near.p, (GsCtl *)e->d_gsctl.p, sw == 0 ? prof : nullptr, gbase);
+						else k_gs_pipeline<ORTHO, false><<<sgrid, kGsPipeThreads, kGsSmemBytes, e->stream>>>(e->d_gpq.p, e->d_gmeta.p, gs_order, np, e->cell, pd, efs,
+						        mu, efi, new_mu, acc, e->d_dmu.p, e->d_tri.p, e->d_near.p, (GsCtl *)e->d_gsctl.p, sw == 0 ? prof : nullptr, gbase);
+						CK(cudaGetLastError());
+						LAUNCHED(e);
+						if (e->gs_fused) continue;
+						// The updaters must not take the SMs the cluster needs (its CTAs want a whole SM's shared memory each): they are launched
+						// as the solver kernel's programmatic dependent — same stream, eligible as soon as every CTA of the cluster has executed
+						// griddepcontrol.launch_dependents, i.e. is resident.  No host wait, no second stream; the next operation in the stream
+						// waits for both kernels.
+						cudaLaunchConfig_t lc = {};
+						lc.gridDim = dim3(e->gs_upd_grid); lc.blockDim = dim3(kGsThreads); lc.dynamicSmemBytes = kGsUpdaterSmemBytes; lc.stream = e->stream;
+						cudaLaunchAttribute at[1];
+						at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization; at[0].val.programmaticStreamSerializationAllowed = 1;
+						lc.attrs = at; lc.numAttrs = 1;
+						const double4 *a_gpq = e->d_gpq.p; const int *a_gmeta = e->d_gmeta.p; double *a_acc = acc; const double *a_dmu = e->d_dmu.p;
+						GsCtl *a_ctl = (GsCtl *)e->d_gsctl.p; long long *a_prof = sw == 0 ? prof : nullptr;
+						if (expd) CK(cudaLaunchKernelEx(&lc, k_gs_updaters<ORTHO, true>, a_gpq, a_gmeta, gs_order, np, e->cell, pd, a_acc, a_dmu, a_ctl, a_prof, gbase));
+						else CK(cudaLaunchKernelEx(&lc, k_gs_updaters<ORTHO, false>, a_gpq, a_gmeta, gs_order, np, e->cell, pd, a_acc, a_dmu, a_ctl, a_prof, gbase));
+						LAUNCHED(e);
+					}
+					CK(cudaGetLastError());
+					CK(cudaMemcpyAsync(e->h_gs_abort, e->d_gsctl.p + 1, sizeof(int), cudaMemcpyDeviceToHost, e->stream));
+					k_gs_efi<<<(np * 3 + eb - 1) / eb, eb, 0, e->stream>>>(e->d_plist.p, np, mu, e->d_alpha.p, efs, efi);
+					LAUNCHED(e);
+					e->gs_ran = true;
+				}
+				it += ns - 1;
+			}
+			if (want_check) {
+				CK(cudaMemsetAsync(e->d_flags.p + b0, 0, sizeof(int) * nb, e->stream));
+				k_dipole_check<<<(nb * n + eb - 1) / eb, eb, 0, e->stream>>>(new_mu, old_mu, n, nb, 1, pd.allowed_sqerr, rrms, e->d_flags.p + b0);
+				LAUNCHED(e);
+			}
+			if (cf.polar_precision == 0.0) keep = (it != cf.polar_max_iter);     // are_we_done_yet, fixed-iteration branch (:3222-3225)
+			else {
+				CK(cudaMemcpyAsync(e->h_flags + b0, e->d_flags.p + b0, sizeof(int) * nb, cudaMemcpyDeviceToHost, e->stream));
+				{ int _rc = sync_stream(e); if (_rc) return _rc; }
+				keep = false;
+				for (int b = b0; b < b0 + nb; b++) keep = keep || e->h_flags[b];
+			}
+			if (cf.polar_palmo && !keep) {                                       // :3518-3519
+				Timed _t(e, MPMC_K_PALMO);
+				if (pd.gs) {   // the running contraction already is sum_j T_ij mu_j for the polarizable rows
+					k_gs_palmo<<<(np * 3 + eb - 1) / eb, eb, 0, e->stream>>>(e->d_plist.p, np, efi, acc, efic);
+					LAUNCHED(e);
+					if ((rc = contract(SWEEP_PALMO_NONPOLAR, e->d_nplist.p, (int)e->nplist.size(), nullptr))) return rc;
+				} else {
+					if ((rc = contract(SWEEP_PALMO, nullptr, n, nullptr))) return rc;
+				}
+			}
+			if (!pd.gs || cf.polar_sor || cf.polar_esor) {                       // :3526-3536 (plain GS already has mu == new_mu)
+				k_mu_update<<<(unsigned)((blen + eb - 1) / eb), eb, 0, e->stream>>>(new_mu, old_mu, blen, cf.polar_sor, cf.polar_esor, cf.polar_gamma,
+				                                                                   std::exp(-cf.polar_gamma * it), mu);
+				LAUNCHED(e);
+				if (pd.gs) acc_stale = true;                                     // relaxation moved mu: the running contraction must be rebuilt
+			}
+		}
+		for (int b = b0; b < b0 + nb; b++) e->last_iters[b] = it;
 		return MPMC_OK;
 	};
-	int it = 0;
-	bool keep = true, acc_stale = false;
-	const int *gs_order = e->d_plist.p;
-	while (keep) {
-		it++;
-		if (it >= 128 && cf.polar_precision > 0) {   // MAX_ITERATION_COUNT (constants.h:52), System.Energy.cpp:3483-3494
-			for (int b = 0; b < B; b++) {
-				k_dipole_fail<<<(n * 3 + eb - 1) / eb, eb, 0, e->stream>>>(e->d_alpha.p, e->d_efs.p, n, (size_t)b * n * 3, e->d_mu.p, e->d_efic.p);
-				LAUNCHED(e);
-				e->last_failed[b] = 1;
-			}
-			break;
-		}
-		if (need_old) CK(cudaMemcpyAsync(e->d_old_mu.p, e->d_mu.p, len * sizeof(double), cudaMemcpyDeviceToDevice, e->stream));
-		if (!pd.gs) {
-			Timed _t(e, MPMC_K_DIPOLE_SWEEP);
-			if ((rc = contract(SWEEP_JACOBI, e->d_plist.p, np, nullptr))) return rc;
-		} else {
-			// Gauss-Seidel pipeline (kernels_gs.cuh).  First sweep in list order (ranked_array = identity, :3463); from the second
-			// sweep on in rank order when polar_gs_ranked (update_ranking after the first pass, :3522-3523).
-			const int nblk = (np + kGsB - 1) / kGsB, nchunks = (np + kGsRows - 1) / kGsRows;
-			if ((rc = e->d_acc.ensure(len)) || (rc = e->d_dmu.ensure((size_t)np * 3)) || (rc = e->d_tri.ensure((size_t)nblk * kGsMat)) || (rc = e->d_near.ensure((size_t)nblk * kGsNearPerBlock)) ||
-			    (rc = e->d_gsctl.ensure(sizeof(GsCtl) / sizeof(int) + nchunks)) || (rc = e->d_gpq.ensure(np)) || (rc = e->d_gmeta.ensure(np))) return rc;
-			if (it == 1 || acc_stale) {
-				Timed _t(e, MPMC_K_DIPOLE_SWEEP);
-				if ((rc = contract(SWEEP_ACC, e->d_plist.p, np, e->d_acc.p))) return rc;
-				acc_stale = false;
-			}
-			if (it == 1 || (ranked && it == 2)) {
-				gs_order = e->d_plist.p;
-				if (ranked && it == 2) {
-					k_rank_order_plist<<<(np + kOrdI - 1) / kOrdI, kOrdThreads, 0, e->stream>>>(e->d_rank.p, e->d_plist.p, np, e->d_order.p);
-					LAUNCHED(e);
-					gs_order = e->d_order.p;
-				}
-				Timed _t(e, MPMC_K_GS_SWEEP);
-				k_gs_gather<<<(np + 255) / 256, 256, 0, e->stream>>>(e->d_posq.p, e->d_alpha.p, e->d_meta.p, gs_order, np, e->d_gpq.p, e->d_gmeta.p);
-				k_gs_inverse<ORTHO><<<nblk, kGsThreads, kGsInverseSmemBytes, e->stream>>>(e->d_gpq.p, e->d_gmeta.p, np, e->cell, pd, e->d_tri.p);
-				k_gs_near<ORTHO><<<nblk, kGsPipeThreads, 0, e->stream>>>(e->d_gpq.p, e->d_gmeta.p, np, e->cell, pd, e->d_near.p);
-				e->launches += 3;
-			}
-			int ns = 1;
-			if (!need_old && !want_check && cf.polar_precision == 0.0) ns = (ranked && it == 1) ? 1 : (cf.polar_max_iter - it + 1);
-			long long *prof = nullptr;
-			if (e->gs_prof_enabled) {
-				if ((rc = e->d_gsprof.ensure((size_t)nblk * 16))) return rc;
-				CK(cudaMemsetAsync(e->d_gsprof.p, 0, sizeof(long long) * nblk * 16, e->stream));
-				prof = e->d_gsprof.p;
-				e->gs_prof_nblk = nblk;
-			}
-			{
-				Timed _t(e, MPMC_K_GS_SWEEP);
-				for (int sw = 0; sw < ns; sw++) {   // one launch per sweep: the kernel boundary is the barrier between sweeps
-					// flags count from generation << 16, so nothing is cleared between sweeps (kernels_gs.cuh); zero them when the generation wraps
-					if (e->gs_gen == 0 || e->gs_gen >= (1 << (30 - kGsGenShift)) || e->gs_ctl_len != sizeof(GsCtl) / sizeof(int) + (size_t)nchunks) {
-						e->gs_ctl_len = sizeof(GsCtl) / sizeof(int) + (size_t)nchunks;
-						CK(cudaMemsetAsync(e->d_gsctl.p, 0, sizeof(int) * e->gs_ctl_len, e->stream));
-						e->gs_gen = 0;
-					}
-					if (nblk >= (1 << kGsGenShift) - kGsAhead - 2) FAIL(MPMC_ERR_UNSUPPORTED, "Gauss-Seidel pipeline: too many polarizable sites (%d)", np);
-					const int gbase = ++e->gs_gen << kGsGenShift;
-					const int sgrid = e->gs_fused ? e->gs_fused_grid : kGsCluster;
-					if (expd) k_gs_pipeline<ORTHO, true><<<sgrid, kGsPipeThreads, kGsSmemBytes, e->stream>>>(e->d_gpq.p, e->d_gmeta.p, gs_order, np, e->cell, pd, e->d_efs.p,
-					        e->d_mu.p, e->d_efi.p, e->d_new_mu.p, e->d_acc.p, e->d_dmu.p, e->d_tri.p, e->d_near.p, (GsCtl *)e->d_gsctl.p, sw == 0 ? prof : nullptr, gbase);
-					else k_gs_pipeline<ORTHO, false><<<sgrid, kGsPipeThreads, kGsSmemBytes, e->stream>>>(e->d_gpq.p, e->d_gmeta.p, gs_order, np, e->cell, pd, e->d_efs.p,
-					        e->d_mu.p, e->d_efi.p, e->d_new_mu.p, e->d_acc.p, e->d_dmu.p, e->d_tri.p, e->d_near.p, (GsCtl *)e->d_gsctl.p, sw == 0 ? prof : nullptr, gbase);
-					CK(cudaGetLastError());
-					LAUNCHED(e);
-					if (e->gs_fused) continue;
-					// The updaters must not take the SMs the cluster needs (its CTAs want a whole SM's shared memory each): they are launched
-					// as the solver kernel's programmatic dependent — same stream, eligible as soon as every CTA of the cluster has executed
-					// griddepcontrol.launch_dependents, i.e. is resident.  No host wait, no second stream; the next operation in the stream
-					// waits for both kernels.
-					cudaLaunchConfig_t lc = {};
-					lc.gridDim = dim3(e->gs_upd_grid); lc.blockDim = dim3(kGsThreads); lc.dynamicSmemBytes = kGsUpdaterSmemBytes; lc.stream = e->stream;
-					cudaLaunchAttribute at[1];
-					at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization; at[0].val.programmaticStreamSerializationAllowed = 1;
-					lc.attrs = at; lc.numAttrs = 1;
-					const double4 *a_gpq = e->d_gpq.p; const int *a_gmeta = e->d_gmeta.p; double *a_acc = e->d_acc.p; const double *a_dmu = e->d_dmu.p;
-					GsCtl *a_ctl = (GsCtl *)e->d_gsctl.p; long long *a_prof = sw == 0 ? prof : nullptr;
-					if (expd) CK(cudaLaunchKernelEx(&lc, k_gs_updaters<ORTHO, true>, a_gpq, a_gmeta, gs_order, np, e->cell, pd, a_acc, a_dmu, a_ctl, a_prof, gbase));
-					else CK(cudaLaunchKernelEx(&lc, k_gs_updaters<ORTHO, false>, a_gpq, a_gmeta, gs_order, np, e->cell, pd, a_acc, a_dmu, a_ctl, a_prof, gbase));
-					LAUNCHED(e);
-				}
-				CK(cudaGetLastError());
-				CK(cudaMemcpyAsync(e->h_gs_abort, e->d_gsctl.p + 1, sizeof(int), cudaMemcpyDeviceToHost, e->stream));
-				k_gs_efi<<<(np * 3 + eb - 1) / eb, eb, 0, e->stream>>>(e->d_plist.p, np, e->d_mu.p, e->d_alpha.p, e->d_efs.p, e->d_efi.p);
-				LAUNCHED(e);
-				e->gs_ran = true;
-			}
-			it += ns - 1;
-		}
-		if (want_check) {
-			CK(cudaMemsetAsync(e->d_flags.p, 0, sizeof(int) * B, e->stream));
-			k_dipole_check<<<(B * n + eb - 1) / eb, eb, 0, e->stream>>>(e->d_new_mu.p, e->d_old_mu.p, n, B, 1, pd.allowed_sqerr, e->d_rrms.p, e->d_flags.p);
-			LAUNCHED(e);
-		}
-		if (cf.polar_precision == 0.0) keep = (it != cf.polar_max_iter);     // are_we_done_yet, fixed-iteration branch (:3222-3225)
-		else {
-			CK(cudaMemcpyAsync(e->h_flags, e->d_flags.p, sizeof(int) * B, cudaMemcpyDeviceToHost, e->stream));
-			CK(cudaStreamSynchronize(e->stream));
-			keep = false;
-			for (int b = 0; b < B; b++) keep = keep || e->h_flags[b];        // bead systems iterate in lock-step until all have converged
-		}
-		if (cf.polar_palmo && !keep) {                                       // :3518-3519
-			Timed _t(e, MPMC_K_PALMO);
-			if (pd.gs) {   // the running contraction already is sum_j T_ij mu_j for the polarizable rows
-				k_gs_palmo<<<(np * 3 + eb - 1) / eb, eb, 0, e->stream>>>(e->d_plist.p, np, e->d_efi.p, e->d_acc.p, e->d_efic.p);
-				LAUNCHED(e);
-				if ((rc = contract(SWEEP_PALMO_NONPOLAR, e->d_nplist.p, (int)e->nplist.size(), nullptr))) return rc;
-			} else {
-				if ((rc = contract(SWEEP_PALMO, nullptr, n, nullptr))) return rc;
-			}
-		}
-		if (!pd.gs || cf.polar_sor || cf.polar_esor) {                       // :3526-3536 (plain GS already has mu == new_mu)
-			k_mu_update<<<(unsigned)((len + eb - 1) / eb), eb, 0, e->stream>>>(e->d_new_mu.p, e->d_old_mu.p, len, cf.polar_sor, cf.polar_esor, cf.polar_gamma,
-			                                                                  std::exp(-cf.polar_gamma * it), e->d_mu.p);
-			LAUNCHED(e);
-			if (pd.gs) acc_stale = true;                                     // relaxation moved mu: the running contraction must be rebuilt
-		}
-	}
-	e->last_iterations = it;
+	if (B > 1 && (pd.gs || cf.polar_precision > 0)) {
+		for (int b = 0; b < B; b++) if ((rc = solve(b, 1))) return rc;
+	} else if ((rc = solve(0, B))) return rc;
+	e->last_iterations = e->last_iters[0];
 	CK(cudaGetLastError());
 	return MPMC_OK;
 }
 
+// pi_fused: the path-integral aggregate is wanted, not the per-bead records — the reductions, the reciprocal energy, the per-bead
+// assembly and the cross-GPU exchange run as one kernel (k_pi_finish) and the per-bead result copy is skipped
 template <bool ORTHO>
-static int enqueue_energy(mpmc_engine *e) {
+static int enqueue_energy(mpmc_engine *e, bool pi_fused = false) {
 	const int n = e->n, B = e->B;
 	const mpmc_config &cf = e->cfg;
 	int rc;
@@ -995,14 +1083,16 @@ static int enqueue_energy(mpmc_engine *e) {
 	// sites': on the second stream, beside the pair sweep — it needs the coordinates only, and the sweep (whose items are dealt through
 	// a counter) takes whatever the structure-factor CTAs leave free, so its ramp-up and tail are no longer idle time.
 	const bool sk_side = es && !e->timing && e->stream2 && e->ev_fork && e->ev_sk;
+	pi_fused = pi_fused && !cf.polarization;
 	if (es && e->frozen_sk_dirty) {
 		if ((rc = run_structure(e, e->d_frozen_q, (int)e->frozen_q.size(), e->d_S_frozen, nullptr))) return rc;
 		e->frozen_sk_dirty = false;
+		e->sk_valid = false;                 // the framework pass used the same scratch for its chunk partials
 	}
 	if (sk_side) {
 		CK(cudaEventRecord(e->ev_fork, e->stream));
 		CK(cudaStreamWaitEvent(e->stream2, e->ev_fork, 0));
-		if ((rc = run_structure(e, e->d_mobile_q, (int)e->mobile_q.size(), e->d_S_mobile, nullptr, e->stream2))) return rc;
+		if ((rc = run_structure_mobile(e, e->stream2, !pi_fused))) return rc;
 		CK(cudaEventRecord(e->ev_sk, e->stream2));
 	}
 	// pair sweep: lj() + coulombic_real()
@@ -1013,20 +1103,40 @@ static int enqueue_energy(mpmc_engine *e) {
 		Timed _t(e, MPMC_K_PAIR);
 		const double4 *spq = e->d_posq.p;        // one class in list order (bulk LJ, single-site models): the table already is sorted
 		if (!e->perm_identity) {
-			k_pair_gather<<<(unsigned)(((size_t)B * n + 255) / 256), 256, 0, e->stream>>>(e->d_posq.p, e->d_perm.p, n, e->cap, B, e->d_spq.p);
-			LAUNCHED(e);
+			if (!e->spq_valid) {             // after a topology change; moves keep the copy current (k_scatter_sites)
+				k_pair_gather<<<(unsigned)(((size_t)B * n + 255) / 256), 256, 0, e->stream>>>(e->d_posq.p, e->d_perm.p, n, e->cap, B, e->d_spq.p);
+				LAUNCHED(e);
+				e->spq_valid = true;
+			}
 			spq = e->d_spq.p;
 		}
 		if (es) k_pair_sweep<ORTHO, true><<<e->pair_grid, pair_warps(true) * 32, smem, e->stream>>>(spq, e->d_slj.p, e->d_pmeta.p, e->cap, B, e->d_segs.p, e->d_item_seg.p, e->d_item_col.p, e->pp, e->cell, e->d_erf_tab.p, e->d_partials.p, e->d_item_ctr.p);
 		else k_pair_sweep<ORTHO, false><<<e->pair_grid, pair_warps(false) * 32, smem, e->stream>>>(spq, e->d_slj.p, e->d_pmeta.p, e->cap, B, e->d_segs.p, e->d_item_seg.p, e->d_item_col.p, e->pp, e->cell, nullptr, e->d_partials.p, e->d_item_ctr.p);
 		LAUNCHED(e);
 	}
+	if (pi_fused) {
+		const int nk = (int)e->kvec.size();
+		if (es) {
+			if (sk_side) CK(cudaStreamWaitEvent(e->stream, e->ev_sk, 0));
+			else if ((rc = run_structure_mobile(e, nullptr, false))) return rc;
+		}
+		if ((rc = e->d_pisums.ensure(8 + 4 * (size_t)B)) || (rc = e->d_pi_done.ensure(1))) return rc;
+		const bool xchg = e->p2p;
+		k_pi_finish<<<B, 256, 0, e->stream>>>(e->d_partials.p, nitems, e->d_item_ctr.p, e->pair_ctr_start, e->d_sk_part.p,
+		                                      ((int)e->mobile_q.size() + kSkSites - 1) / kSkSites, e->d_kvec.p, nk, 4.0 * kPi / e->cell.volume, e->d_S_mobile.p,
+		                                      e->d_result.p, B, e->lrc_pair + e->lrc_self, e->es_self, es ? 1 : 0, e->d_pisums.p,
+		                                      xchg ? e->d_peers.p : nullptr, e->rank, e->nranks, xchg ? e->d_step.p : nullptr, e->xchg_timeout_cycles, e->d_pi_done.p);
+		LAUNCHED(e);
+		CK(cudaGetLastError());
+		e->enqueued = true;
+		return MPMC_OK;
+	}
 	k_reduce_partials<<<B, 256, 0, e->stream>>>(e->d_partials.p, nitems, e->d_result.p, e->d_item_ctr.p, e->pair_ctr_start);
 	LAUNCHED(e);
 	if (es) {
 		const int nk = (int)e->kvec.size();
 		if (sk_side) CK(cudaStreamWaitEvent(e->stream, e->ev_sk, 0));
-		else if ((rc = run_structure(e, e->d_mobile_q, (int)e->mobile_q.size(), e->d_S_mobile, nullptr))) return rc;
+		else if ((rc = run_structure_mobile(e, nullptr, true))) return rc;
 		k_recip_energy<<<B, 256, 0, e->stream>>>(e->d_S_mobile.p, e->d_kvec.p, nk, 4.0 * kPi / e->cell.volume, e->d_result.p);
 		LAUNCHED(e);
 		if (cf.polarization) {
@@ -1079,6 +1189,15 @@ int mpmc_create(const mpmc_config *cfg, mpmc_engine **out) {
 	CK(cudaMallocHost(&e->h_flags, sizeof(int) * e->B));
 	if ((rc = e->d_result.ensure(res_len(e->B))) || (rc = e->d_flags.ensure(e->B)) || (rc = e->d_rmin.ensure(e->B))) { mpmc_destroy(e); return rc; }
 	e->last_failed.assign(e->B, 0);
+	CK(cudaMallocHost(&e->h_sk_dirty, sizeof(int) * (1 + kSkMaxDirty)));
+	if ((rc = e->d_sk_dirty.ensure(1 + kSkMaxDirty)) || (rc = e->d_pi_done.ensure(1)) || (rc = e->d_pisums.ensure(8 + 4 * (size_t)e->B))) { mpmc_destroy(e); return rc; }
+	CK(cudaMemset(e->d_pi_done.p, 0, sizeof(int)));
+	CK(cudaMemset(e->d_pisums.p, 0, sizeof(double) * 8));
+	{
+		const char *ts = getenv("MPMC_PI_XCHG_TIMEOUT_S");
+		const double sec = ts ? atof(ts) : 60.0;
+		e->xchg_timeout_cycles = (long long)(std::max(sec, 0.001) * 1.0e3 * prop.clockRate);     // clockRate is in kHz
+	}
 	// shared-memory opt-ins
 	if ((rc = set_smem(k_structure_partial, sizeof(double2) * kSkSites * 3 * (kMaxKmax + 1))) ||
 	    (rc = set_smem(k_field_recip, sizeof(double2) * kFrSites * 3 * (kMaxKmax + 1))) ||
@@ -1137,7 +1256,9 @@ int mpmc_destroy(mpmc_engine *e) {
 	e->d_efs.release(); e->d_efi.release(); e->d_efic.release(); e->d_mu.release(); e->d_new_mu.release(); e->d_old_mu.release();
 	e->d_rrms.release(); e->d_rank.release(); e->d_acc.release(); e->d_dmu.release(); e->d_tri.release(); e->d_near.release(); e->d_gsctl.release(); e->d_gmeta.release(); e->d_nplist.release(); e->d_gpq.release(); e->d_cparts.release(); e->d_field_tab.release(); e->d_fp_list.release(); e->d_mp_list.release(); e->d_recount.release(); e->d_r2min_ff.release(); e->d_t2.release(); e->d_t2_cached.release(); e->d_cnt_ff.release(); e->d_mobile_sites.release(); e->d_frozen_sites.release(); e->d_allq.release(); e->d_com.release(); e->d_mol_mass.release(); e->d_chain.release();
 	e->d_rmin.release(); e->d_result.release();
-	if (e->h_stage) cudaFreeHost(e->h_stage);
+	for (int q = 0; q < 2; q++) if (e->h_stage[q]) cudaFreeHost(e->h_stage[q]);
+	if (e->h_sk_dirty) cudaFreeHost(e->h_sk_dirty);
+	e->d_iperm.release(); e->d_sk_dirty.release(); e->d_pi_done.release();
 	if (e->h_result) cudaFreeHost(e->h_result);
 	if (e->h_flags) cudaFreeHost(e->h_flags);
 	drop_pi_graph(e);
@@ -1192,6 +1313,7 @@ int mpmc_update_sites(mpmc_engine *e, int bead, int first, int count, const doub
 	if (bead < 0 || bead >= e->B || first < 0 || count < 0 || first + count > e->n) FAIL(MPMC_ERR_INVALID_INPUT, "update_sites: range out of bounds");
 	memcpy(&e->h_pos[((size_t)bead * e->n + first) * 3], pos, sizeof(double) * 3 * count);
 	for (int i = first; i < first + count; i++) if (e->h_frozen[i]) { e->rank_ff_dirty = true; if (e->h_q[i] != 0.0) e->frozen_sk_dirty = true; }
+	mark_moved(e, first, count);
 	return push_positions(e, bead, bead + 1, first, count);
 }
 
@@ -1200,6 +1322,7 @@ int mpmc_update_sites_all_beads(mpmc_engine *e, int first, int count, const doub
 	if (first < 0 || count < 0 || first + count > e->n) FAIL(MPMC_ERR_INVALID_INPUT, "update_sites: range out of bounds");
 	for (int b = 0; b < e->B; b++) memcpy(&e->h_pos[((size_t)b * e->n + first) * 3], pos + (size_t)b * count * 3, sizeof(double) * 3 * count);
 	for (int i = first; i < first + count; i++) if (e->h_frozen[i]) { e->rank_ff_dirty = true; if (e->h_q[i] != 0.0) e->frozen_sk_dirty = true; }
+	mark_moved(e, first, count);
 	return push_positions(e, 0, e->B, first, count);
 }
 
@@ -1256,7 +1379,7 @@ int mpmc_energy_enqueue(mpmc_engine *e) {
 int mpmc_energy_fetch(mpmc_engine *e, mpmc_energy_out *out) {
 	if (!e->enqueued) FAIL(MPMC_ERR_INTERNAL, "energy_fetch without energy_enqueue");
 	CK(cudaSetDevice(e->dev));
-	CK(cudaStreamSynchronize(e->stream));
+	{ int _rc = sync_stream(e); if (_rc) return _rc; }
 	e->enqueued = false;
 	if (e->timing) collect_timing(e);
 	if (e->gs_ran) {
@@ -1292,7 +1415,7 @@ int mpmc_energy_fetch(mpmc_engine *e, mpmc_energy_out *out) {
 				if (cf.polar_palmo) pot += pr[1];
 				o.polarization_energy = -0.5 * pot;                           // :2609-2618
 				o.dipole_rrms = pr[2] / e->n;               // :2639-2657
-				o.polarization_iterations = e->last_iterations;
+				o.polarization_iterations = b < (int)e->last_iters.size() ? e->last_iters[b] : e->last_iterations;
 				o.iterator_failed = e->last_failed[b];
 			}
 		}
@@ -1312,7 +1435,7 @@ int mpmc_download_dipoles(mpmc_engine *e, int bead, double *mu, double *ef_stati
 	if (bead < 0 || bead >= e->B) FAIL(MPMC_ERR_INVALID_INPUT, "bead out of range");
 	if (!e->d_mu.p) FAIL(MPMC_ERR_INVALID_SETTING, "polarization has not been evaluated");
 	const size_t len = (size_t)e->n * 3, off = (size_t)bead * len;
-	CK(cudaStreamSynchronize(e->stream));
+	{ int _rc = sync_stream(e); if (_rc) return _rc; }
 	if (mu) CK(cudaMemcpy(mu, e->d_mu.p + off, len * sizeof(double), cudaMemcpyDeviceToHost));
 	if (ef_static) CK(cudaMemcpy(ef_static, e->d_efs.p + off, len * sizeof(double), cudaMemcpyDeviceToHost));
 	if (ef_induced) CK(cudaMemcpy(ef_induced, e->d_efi.p + off, len * sizeof(double), cudaMemcpyDeviceToHost));
@@ -1324,21 +1447,26 @@ int mpmc_download_rank_metric(mpmc_engine *e, int bead, double *rank_metric) {
 	CK(cudaSetDevice(e->dev));
 	if (bead < 0 || bead >= e->B) FAIL(MPMC_ERR_INVALID_INPUT, "bead out of range");
 	if (!e->d_rank.p) FAIL(MPMC_ERR_INVALID_SETTING, "polarization has not been evaluated");
-	CK(cudaStreamSynchronize(e->stream));
+	{ int _rc = sync_stream(e); if (_rc) return _rc; }
 	CK(cudaMemcpy(rank_metric, e->d_rank.p + (size_t)bead * e->n, e->n * sizeof(double), cudaMemcpyDeviceToHost));
 	return MPMC_OK;
 }
 
 // enqueue one sweep over the local bead systems and leave {sum rd, sum coulombic, sum polarization, sum vdw} in d_pisums[0..3]
-static int pi_sums_enqueue(mpmc_engine *e, double *d_per_bead, bool xchg = false) {
-	int rc = mpmc_energy_enqueue(e);
-	if (rc) return rc;
-	if ((rc = e->d_pisums.ensure(8 + 4 * (size_t)e->B))) return rc;
+// `fused` (the all-reduce path): one kernel does the reductions, the assembly and the exchange (k_pi_finish); polarizable systems
+// and the per-bead API keep the separate kernels.
+static int pi_sums_enqueue(mpmc_engine *e, double *d_per_bead, bool xchg = false, bool fused = false) {
 	if (!e->h_pisums) CK(cudaMallocHost(&e->h_pisums, sizeof(double) * (8 + 4 * (size_t)e->B)));
 	const mpmc_config &cf = e->cfg;
+	if (fused && !cf.polarization) {
+		CK(cudaSetDevice(e->dev));
+		return e->ortho ? enqueue_energy<true>(e, true) : enqueue_energy<false>(e, true);
+	}
+	int rc = mpmc_energy_enqueue(e);
+	if (rc) return rc;
 	if (e->p2p && xchg)
 		k_pi_sums_xchg<<<1, 32, 0, e->stream>>>(e->d_result.p, e->B, e->lrc_pair + e->lrc_self, e->es_self, !cf.rd_only, cf.polarization, cf.polar_palmo,
-		                                        e->d_pisums.p, e->d_peers.p, e->rank, e->nranks, e->d_step.p);
+		                                        e->d_pisums.p, e->d_peers.p, e->rank, e->nranks, e->d_step.p, e->xchg_timeout_cycles);
 	else
 		k_pi_sums<<<1, 32, 0, e->stream>>>(e->d_result.p, e->B, e->lrc_pair + e->lrc_self, e->es_self, !cf.rd_only, cf.polarization, cf.polar_palmo,
 		                                   d_per_bead, e->d_pisums.p);
@@ -1435,44 +1563,66 @@ int mpmc_pi_potential_allreduce(mpmc_engine *e, int P_global, double means[4], d
 	CK(cudaSetDevice(e->dev));
 	if (P_global < e->B) FAIL(MPMC_ERR_BEADS, "P_global (%d) smaller than the local bead count (%d)", P_global, e->B);
 	int rc;
-	// Steady state (same topology, no framework move pending, no per-kernel timing, no polarization loop with host decisions):
-	// the whole sweep — gather, pair sweep, reductions, structure factor, per-bead assembly, all-reduce, result copy — is one
-	// CUDA graph, captured on the second call and replayed afterwards.  At 8 beads per GPU the sweep is ~150 us of kernels: ten
-	// separate launches would leave the GPU idle for a third of that.
-	const bool graphable = !e->pi_graph_off && !e->timing && !e->cfg.polarization && !e->topo_dirty && !e->frozen_sk_dirty && e->d_pisums.p && e->h_pisums;
+	if (!e->h_pisums) CK(cudaMallocHost(&e->h_pisums, sizeof(double) * (8 + 4 * (size_t)e->B)));
+	// Steady state (same topology, no framework move pending, no per-kernel timing, no polarization loop with host decisions, the
+	// structure-factor partials valid so that only the moved chunks are redone): the whole sweep — dirty-chunk list, structure
+	// factor, pair sweep, finish (reductions + assembly + exchange), result copy — is one CUDA graph, captured on the second call and
+	// replayed afterwards.  At 8 beads per GPU the sweep is ~100 us of kernels: separate launches would leave the GPU idle for a
+	// third of that.
+	const bool es = !e->cfg.rd_only;
+	const bool graphable = e->pi_warm && !e->pi_graph_off && !e->timing && !e->cfg.polarization && !e->topo_dirty && !e->frozen_sk_dirty && (!es || e->sk_valid);
+	auto copy_back = [&]() { return cudaMemcpyAsync(e->h_pisums, e->d_pisums.p, sizeof(double) * 6, cudaMemcpyDeviceToHost, e->stream); };
 	if (graphable && e->pi_graph) {
+		// what run_structure_mobile does on the host when it is not replayed from a graph
+		e->h_sk_dirty[0] = (int)e->sk_dirty.size();
+		for (size_t i = 0; i < e->sk_dirty.size(); i++) e->h_sk_dirty[1 + i] = e->sk_dirty[i];
+		e->sk_dirty.clear();
 		CK(cudaGraphLaunch(e->pi_graph, e->stream));
 		e->launches += e->pi_graph_launches;
 	} else if (graphable) {
 		const long long l0 = e->launches;
+		const std::vector<int> dirty0 = e->sk_dirty;
 		cudaGraph_t g = nullptr;
 		CK(cudaStreamBeginCapture(e->stream, cudaStreamCaptureModeThreadLocal));
-		rc = pi_sums_enqueue(e, nullptr, true);
+		rc = pi_sums_enqueue(e, nullptr, true, true);
 		int nrc = 0;
 		if (!rc && e->comm && !e->p2p) nrc = g_nccl.AllReduce(e->d_pisums.p, e->d_pisums.p, 4, kNcclFloat64, kNcclSum, e->comm, e->stream);
-		cudaError_t ce = (!rc && !nrc) ? cudaMemcpyAsync(e->h_pisums, e->d_pisums.p, sizeof(double) * 4, cudaMemcpyDeviceToHost, e->stream) : cudaSuccess;
+		cudaError_t ce = (!rc && !nrc) ? copy_back() : cudaSuccess;
 		cudaError_t ee = cudaStreamEndCapture(e->stream, &g);
 		if (rc || nrc || ce != cudaSuccess || ee != cudaSuccess || !g || cudaGraphInstantiate(&e->pi_graph, g, 0) != cudaSuccess) {
 			cudaGetLastError();
 			if (g) cudaGraphDestroy(g);
 			e->pi_graph = nullptr; e->pi_graph_off = true;      // fall back to plain launches for the rest of this engine's life
 			e->launches = l0;
-			if ((rc = pi_sums_enqueue(e, nullptr, true))) return rc;
+			e->sk_valid = false;                                // nothing was executed: redo the structure factor in full
+			if ((rc = pi_sums_enqueue(e, nullptr, true, true))) return rc;
 			if (e->comm && !e->p2p) NK(g_nccl.AllReduce(e->d_pisums.p, e->d_pisums.p, 4, kNcclFloat64, kNcclSum, e->comm, e->stream));
-			CK(cudaMemcpyAsync(e->h_pisums, e->d_pisums.p, sizeof(double) * 4, cudaMemcpyDeviceToHost, e->stream));
+			CK(copy_back());
 		} else {
 			cudaGraphDestroy(g);
 			e->pi_graph_launches = e->launches - l0;
+			// capture recorded the work without running it: the pinned dirty list the graph reads is the one staged during capture
+			e->h_sk_dirty[0] = (int)dirty0.size();
+			for (size_t i = 0; i < dirty0.size(); i++) e->h_sk_dirty[1 + i] = dirty0[i];
 			CK(cudaGraphLaunch(e->pi_graph, e->stream));
 		}
 	} else {
-		if ((rc = pi_sums_enqueue(e, nullptr, true))) return rc;
+		if ((rc = pi_sums_enqueue(e, nullptr, true, true))) return rc;
 		if (e->comm && !e->p2p) NK(g_nccl.AllReduce(e->d_pisums.p, e->d_pisums.p, 4, kNcclFloat64, kNcclSum, e->comm, e->stream));
-		CK(cudaMemcpyAsync(e->h_pisums, e->d_pisums.p, sizeof(double) * 4, cudaMemcpyDeviceToHost, e->stream));
+		CK(copy_back());
 	}
-	CK(cudaStreamSynchronize(e->stream));
+	{ int _rc = sync_stream(e); if (_rc) return _rc; }
 	e->enqueued = false;
+	e->pi_warm = true;
 	if (e->timing) collect_timing(e);
+	if (e->h_pisums[5] != 0.0) {
+		FAIL(MPMC_ERR_CUDA, "path-integral exchange failed: a peer rank did not deliver its bead sums within the time limit (MPMC_PI_XCHG_TIMEOUT_S) or has stopped; "
+		                    "every rank of the group reports this error");
+	}
+	if (e->gs_ran) {                                          // a polarizable bead system solved with the Gauss-Seidel pipeline
+		e->gs_ran = false;
+		if (*e->h_gs_abort) { *e->h_gs_abort = 0; e->gs_gen = 0; FAIL(MPMC_ERR_CUDA, "the Gauss-Seidel pipeline timed out waiting for its own CTAs"); }
+	}
 	for (int q = 0; q < 4; q++) means[q] = e->h_pisums[q] / P_global;          // PathIntegral.cpp:798-801
 	if (potential) *potential = means[0] + means[1] + means[3] + means[2];     // :803-804
 	return MPMC_OK;
@@ -1503,7 +1653,7 @@ int mpmc_pi_chain_allreduce(mpmc_engine *e, double *chain_mass_len2) {
 	e->launches++;
 	if (e->comm) NK(g_nccl.AllReduce(e->d_pisums.p + 4, e->d_pisums.p + 4, 1, kNcclFloat64, kNcclSum, e->comm, e->stream));
 	CK(cudaMemcpyAsync(e->h_pisums + 4, e->d_pisums.p + 4, sizeof(double), cudaMemcpyDeviceToHost, e->stream));
-	CK(cudaStreamSynchronize(e->stream));
+	{ int _rc = sync_stream(e); if (_rc) return _rc; }
 	*chain_mass_len2 = e->h_pisums[4];
 	return MPMC_OK;
 }
@@ -1521,7 +1671,7 @@ int mpmc_pi_chain(mpmc_engine *e, int closed, double *chain_mass_len2, double *c
 	CK(cudaMemcpyAsync(per.data(), e->d_chain.p, sizeof(double) * nmol, cudaMemcpyDeviceToHost, e->stream));
 	if (com) CK(cudaMemcpyAsync(com, e->d_com.p, sizeof(double) * (size_t)B * nmol * 3, cudaMemcpyDeviceToHost, e->stream));
 	if (mol_mass) CK(cudaMemcpyAsync(mol_mass, e->d_mol_mass.p, sizeof(double) * nmol, cudaMemcpyDeviceToHost, e->stream));
-	CK(cudaStreamSynchronize(e->stream));
+	{ int _rc = sync_stream(e); if (_rc) return _rc; }
 	double s = 0;
 	for (int m = 0; m < nmol; m++) s += per[m];      // PathIntegral.cpp:880-901, molecule order
 	*chain_mass_len2 = s;
@@ -1536,7 +1686,7 @@ int mpmc_debug_gs_profile(mpmc_engine *e, int enable, long long *out, int max_bl
 	{ const int dbg = enable & ~1; CK(cudaMemcpyToSymbol(g_gs_debug, &dbg, sizeof(int))); }
 	if (nblk) *nblk = e->gs_grid;
 	if (out && e->d_gsprof.p && e->gs_prof_nblk) {
-		CK(cudaStreamSynchronize(e->stream));
+		{ int _rc = sync_stream(e); if (_rc) return _rc; }
 		const int nb = std::min(max_blocks, e->gs_prof_nblk);
 		CK(cudaMemcpy(out, e->d_gsprof.p, sizeof(long long) * 8 * nb, cudaMemcpyDeviceToHost));
 		CK(cudaMemcpy(out + (size_t)8 * max_blocks, e->d_gsprof.p + (size_t)8 * e->gs_prof_nblk, sizeof(long long) * 8 * nb, cudaMemcpyDeviceToHost));
@@ -1572,7 +1722,7 @@ int mpmc_debug_cutoff_thresholds(double cutoff, double out[2]) {
 
 int mpmc_set_timing(mpmc_engine *e, int on) {
 	CK(cudaSetDevice(e->dev));
-	CK(cudaStreamSynchronize(e->stream));
+	{ int _rc = sync_stream(e); if (_rc) return _rc; }
 	e->timing = on != 0;
 	e->ev_used = 0;
 	for (int i = 0; i < MPMC_NUM_KERNEL_CLASSES; i++) { e->t_ms[i] = 0; e->t_count[i] = 0; }

@@ -62,8 +62,52 @@ __global__ void k_pi_sums(const double *__restrict__ res, int nbeads, double rd_
 // order on every rank, so all ranks hold bit-identical sums.  One kernel, no host round trip, ~3 us instead of the ~70 us the
 // 8-rank collective cost inside a 250 us step.  Two parities suffice: a rank can only be one step ahead of the slowest reader.
 struct PiMailSlot { double v[4]; long long seq; long long pad[3]; };   // 64 bytes
+// A peer that does not show up within `timeout_cycles` (default ~60 s: rank-0 I/O, a topology rebuild or a debugger can hold a rank
+// for seconds) makes the exchange FAIL ON EVERY RANK: the waiting rank raises its sticky error word (sums[5], copied back with the
+// sums: the host call returns MPMC_ERR_CUDA) and poisons its slot in every peer's mailbox (seq = -1, both parities), so that a
+// late peer — which may still complete the step it is in from the stamps already posted — fails at its next exchange instead of
+// carrying on with a partner that has stopped.  No rank ever returns success with sums another rank does not hold.
+constexpr long long kPiPoison = -1;
+__device__ __forceinline__ void pi_exchange(const double *s_loc, double (*s_in)[4], double *__restrict__ sums, PiMailSlot *const *__restrict__ peers,
+                                            int rank, int nranks, long long step, long long timeout_cycles) {
+	const int t = threadIdx.x;
+	const int par = (int)(step & 1);
+	__shared__ int s_fail;
+	if (t == 0) s_fail = 0;
+	__syncthreads();
+	if (t < nranks) {
+		volatile PiMailSlot *dst = peers[t] + par * nranks + rank;
+		for (int q = 0; q < 4; q++) dst->v[q] = s_loc[q];
+		__threadfence_system();
+		dst->seq = step;
+		volatile PiMailSlot *src = peers[rank] + par * nranks + t;
+		const long long t0 = clock64();
+		bool ok = true;
+		for (;;) {
+			const long long sq = src->seq;
+			if (sq == step) break;
+			if (sq == kPiPoison || clock64() - t0 > timeout_cycles) { ok = false; break; }
+		}
+		__threadfence_system();
+		for (int q = 0; q < 4; q++) s_in[t][q] = ok ? src->v[q] : __longlong_as_double(0x7ff8000000000000ll);
+		if (!ok) s_fail = 1;
+	}
+	__syncthreads();
+	if (s_fail && t < nranks) {
+		for (int pp = 0; pp < 2; pp++) { volatile PiMailSlot *dst = peers[t] + pp * nranks + rank; dst->seq = kPiPoison; }
+		__threadfence_system();
+	}
+	if (t < 4) {
+		double a = 0;
+		for (int r = 0; r < nranks; r++) a += s_in[r][t];
+		sums[t] = a;
+	}
+	if (t == 0 && s_fail) sums[5] = 1.0;       // sticky: only the host clears it
+}
+
 __global__ void k_pi_sums_xchg(const double *__restrict__ res, int nbeads, double rd_const, double es_self, int es_on, int polar_on, int palmo,
-                               double *__restrict__ sums, PiMailSlot *const *__restrict__ peers, int rank, int nranks, long long *step_counter) {
+                               double *__restrict__ sums, PiMailSlot *const *__restrict__ peers, int rank, int nranks, long long *step_counter,
+                               long long timeout_cycles) {
 	__shared__ double s_loc[4];
 	__shared__ double s_in[32][4];
 	__shared__ long long s_step;
@@ -80,26 +124,7 @@ __global__ void k_pi_sums_xchg(const double *__restrict__ res, int nbeads, doubl
 		s_step = ++(*step_counter);
 	}
 	__syncthreads();
-	const long long step = s_step;
-	const int par = (int)(step & 1);
-	if (t < nranks) {
-		volatile PiMailSlot *dst = peers[t] + par * nranks + rank;
-		for (int q = 0; q < 4; q++) dst->v[q] = s_loc[q];
-		__threadfence_system();
-		dst->seq = step;
-		volatile PiMailSlot *src = peers[rank] + par * nranks + t;
-		const long long t0 = clock64();
-		bool ok = true;
-		while (src->seq != step) { if (clock64() - t0 > 8000000000ll) { ok = false; break; } }   // ~4 s: a peer died; fail loudly with NaN
-		__threadfence_system();
-		for (int q = 0; q < 4; q++) s_in[t][q] = ok ? src->v[q] : __longlong_as_double(0x7ff8000000000000ll);
-	}
-	__syncthreads();
-	if (t < 4) {
-		double a = 0;
-		for (int r = 0; r < nranks; r++) a += s_in[r][t];
-		sums[t] = a;
-	}
+	pi_exchange(s_loc, s_in, sums, peers, rank, nranks, s_step, timeout_cycles);
 }
 
 // ---------------------------------------------------------------------------------------------------------

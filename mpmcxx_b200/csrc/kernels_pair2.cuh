@@ -131,12 +131,16 @@ __global__ void k_pair_gather(const double4 *__restrict__ posq, const int *__res
 	spq[(size_t)bead * stride + k] = posq[(size_t)bead * stride + perm[k]];
 }
 
-// a move of `count` consecutive sites in every bead system: stage[b][k] -> posq[bead_lo + b][first + k]
-__global__ void k_scatter_sites(const double4 *__restrict__ stage, double4 *__restrict__ posq, int stride, int bead_lo, int nb, int first, int count) {
+// a move of `count` consecutive sites in every bead system: stage[b][k] -> posq[bead_lo + b][first + k], and — where the pair sweep
+// reads a class-sorted copy — the same site in spq (iperm = site -> sorted position), so the copy never has to be re-gathered
+__global__ void k_scatter_sites(const double4 *__restrict__ stage, double4 *__restrict__ posq, int stride, int bead_lo, int nb, int first, int count,
+                                const int *__restrict__ iperm, double4 *__restrict__ spq) {
 	const int t = blockIdx.x * blockDim.x + threadIdx.x;
 	if (t >= nb * count) return;
 	const int b = t / count, k = t - b * count;
-	posq[(size_t)(bead_lo + b) * stride + first + k] = stage[t];
+	const double4 v = stage[t];
+	posq[(size_t)(bead_lo + b) * stride + first + k] = v;
+	if (spq) spq[(size_t)(bead_lo + b) * stride + iperm[first + k]] = v;
 }
 
 // folds a site into the cell centred on the origin along each axis of an orthorhombic cell (coordinates end up in [-L/2, L/2] up to

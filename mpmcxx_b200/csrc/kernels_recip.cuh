@@ -49,10 +49,13 @@ __device__ __forceinline__ double2 tab_at(const double2 *tab, int kmax, int ld, 
 // [site][row] so that lanes with different l hit different banks.
 __global__ void __launch_bounds__(kSkThreads)
 k_structure_partial(const double4 *__restrict__ posq, int stride, const int *__restrict__ list, int nlist,
-                    const KVec *__restrict__ kv, int nk, int kmax, CellDev c, double2 *__restrict__ part, int nchunks) {
+                    const KVec *__restrict__ kv, int nk, int kmax, CellDev c, double2 *__restrict__ part, int nchunks, const int *__restrict__ dirty) {
 	extern __shared__ double2 s_tab[];               // [kSkSites][3*(kmax+1)]
 	__shared__ double s_q[kSkSites];
-	const int bead = blockIdx.y, chunk = blockIdx.x;
+	// `dirty` (may be null): { count, chunk indices ... } — only the chunks that hold a site moved since the partials were last
+	// computed; the others are still valid, and summing all of them in chunk order gives the bits of a full evaluation
+	if (dirty && (int)blockIdx.x >= dirty[0]) return;
+	const int bead = blockIdx.y, chunk = dirty ? dirty[1 + blockIdx.x] : blockIdx.x;
 	const double4 *pq = posq + (size_t)bead * stride;
 	const int rows = 3 * (kmax + 1);
 	const int base = chunk * kSkSites;

@@ -6,7 +6,12 @@
 
 using namespace mpmc_host;
 
+static double g_last_loop_seconds = 0, g_last_loop_sweeps = 0;
+
 extern "C" {
+
+// wall seconds of the last run's step loop (set-up and initial energy excluded) and the potential sweeps it made (path integrals)
+void mpmc_host_last_stats(double out[2]) { out[0] = g_last_loop_seconds; out[1] = g_last_loop_sweeps; }
 
 // Run the simulation an input file describes (ensemble nvt | uvt | pi_nvt), with `P` beads for pi_nvt, for at most max_steps
 // steps (0 = numsteps from the file).  log receives 5 doubles per step: move type, trial energy (potential for pi_nvt),
@@ -19,6 +24,39 @@ int mpmc_host_run(const char *input_file, int P, int max_steps, double *log, int
 		sc.initializeSimulationObjects();
 		std::vector<System::step_record> rec;
 		sc.runSimulation(&rec);
+		g_last_loop_seconds = sc.loop_seconds; g_last_loop_sweeps = (double)sc.loop_sweeps;
+		const int n = (int)std::min<size_t>(rec.size(), (size_t)log_capacity);
+		for (int i = 0; i < n; i++) {
+			log[5 * i] = rec[i].movetype; log[5 * i + 1] = rec[i].final_energy; log[5 * i + 2] = rec[i].boltzmann_factor;
+			log[5 * i + 3] = rec[i].accepted; log[5 * i + 4] = rec[i].N;
+		}
+		if (n_logged) *n_logged = n;
+		if (summary) {
+			const System::observables_t &o = *sc.sys.observables;
+			summary[0] = o.energy; summary[1] = o.rd_energy; summary[2] = o.coulombic_energy; summary[3] = o.polarization_energy;
+			summary[4] = o.kinetic_energy; summary[5] = o.N; summary[6] = sc.sys.nodestats->accept; summary[7] = sc.sys.nodestats->reject;
+		}
+	} catch (int e) {
+		return e ? e : internal_error;
+	}
+	return 0;
+}
+
+// The same for a path-integral run whose bead systems are sharded over `nranks` processes, one GPU each (launched e.g. by torchrun):
+// every rank calls this with its rank, the device it owns and the 128-byte NCCL id rank 0 obtained from mpmc_nccl_get_unique_id().
+// All ranks replay the same random stream and return the same log.
+int mpmc_host_run_sharded(const char *input_file, int P, int max_steps, int rank, int nranks, int device, const char *nccl_id,
+                          double *log, int log_capacity, int *n_logged, double *summary) {
+	try {
+		SimulationControl sc(input_file, P);
+		if (sc.sys.ensemble != ENSEMBLE_PATH_INTEGRAL_NVT) return invalid_ensemble;
+		if (max_steps > 0) sc.sys.numsteps = (uint32_t)max_steps;
+		sc.sys.gpu_device = device;
+		sc.set_sharding(rank, nranks, nccl_id);
+		sc.initializeSimulationObjects();
+		std::vector<System::step_record> rec;
+		sc.runSimulation(&rec);
+		g_last_loop_seconds = sc.loop_seconds; g_last_loop_sweeps = (double)sc.loop_sweeps;
 		const int n = (int)std::min<size_t>(rec.size(), (size_t)log_capacity);
 		for (int i = 0; i < n; i++) {
 			log[5 * i] = rec[i].movetype; log[5 * i + 1] = rec[i].final_energy; log[5 * i + 2] = rec[i].boltzmann_factor;

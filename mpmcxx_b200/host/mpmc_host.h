@@ -8,8 +8,10 @@
 // global Rando) are consumed in the reference's order with libstdc++'s own distributions, and the
 // move arithmetic rounds like the reference's (-ffp-contract=off).
 #pragma once
+#include <chrono>
 #include <cstdint>
 #include <cstdio>
+#include <cstring>
 #include <random>
 #include <string>
 #include <vector>
@@ -171,6 +173,13 @@ public:
 	int nSys = 0;                    // Trotter number
 	int PI_trial_chain_length = 0;
 	std::vector<System *> systems;   // one per bead
+	// bead sharding over GPUs (one process per GPU): this process evaluates beads [P rank / nranks, P (rank + 1) / nranks)
+	int rank = 0, nranks = 1;
+	char nccl_id[128] = {0};
+	// what the last run cost: wall seconds of the step loop alone (set-up and the initial energy excluded) and potential sweeps in it
+	double loop_seconds = 0;
+	long long loop_sweeps = 0, pi_sweeps = 0;
+	void set_sharding(int r, int nr, const char id[128]) { rank = r; nranks = nr; memcpy(nccl_id, id, 128); }
 
 	// path integrals (src/SimulationControl.PathIntegral.cpp)
 	bool PI_nvt_mc(std::vector<System::step_record> *log = nullptr);
@@ -196,8 +205,10 @@ private:
 	void check_system();
 	void initialize_PI_NVT_Systems();
 	int starterBead = 0;             // the function-static of PI_perturb_bead_COMs(int) (PathIntegral.cpp:1480)
-	mpmc_engine *pi_gpu = nullptr;   // one batched engine for all bead systems
-	std::vector<double> pi_gpu_pos;
+	mpmc_engine *pi_gpu = nullptr;   // one batched engine for this rank's bead systems
+	std::vector<int> pi_mol_first;   // list position of a molecule -> its first site (+ total at the end)
+	std::vector<int> pi_dirty;       // list positions whose coordinates changed since the device last saw them
+	int pi_target_pos = 0;
 };
 
 } // namespace mpmc_host

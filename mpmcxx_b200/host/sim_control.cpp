@@ -165,40 +165,60 @@ void SimulationControl::initialize_PI_NVT_Systems() {        // PathIntegral.cpp
 	sys.pbc = systems[0]->pbc;
 }
 
-// energy() of every bead system in one batched engine call; means over beads (PathIntegral.cpp:752-805)
+// energy() of every bead system in one batched engine call; means over beads (PathIntegral.cpp:752-805).  With nranks > 1 the bead
+// systems are sharded over the ranks' GPUs (every rank keeps all P systems on the host and replays the same random stream, as the
+// reference's MPI ranks do); the engine sums the per-bead energies across ranks (replaces MPI_Allgather x 4, :763-766).
+// Only what moved since the last call is sent: the Markov chain alters one molecule (the same list position in every bead system)
+// per step, so the driver records the list positions it touched (pi_dirty) instead of flattening and comparing P x N sites.
 double SimulationControl::PI_calculate_potential() {
-	const int P = nSys, n = systems[0]->countNatoms();
-	std::vector<double> pos;
-	pos.reserve((size_t)P * n * 3);
+	const int P = nSys;
+	const int b_lo = (int)((long long)P * rank / nranks), b_hi = (int)((long long)P * (rank + 1) / nranks), PL = b_hi - b_lo;
+	if (PL < 1) throw invalid_MPI_size_for_PI;
 	int rc;
-	std::vector<double> q, al, ep, sg, ms;
-	std::vector<int> mol, fz;
-	for (int s = 0; s < P; s++) {
-		std::vector<double> q1, a1, e1, s1, m1;
-		std::vector<int> mo1, f1;
-		systems[s]->flatten(pos, q1, a1, e1, s1, m1, mo1, f1);
-		if (s == 0) { q.swap(q1); al.swap(a1); ep.swap(e1); sg.swap(s1); ms.swap(m1); mol.swap(mo1); fz.swap(f1); }
-		else if ((int)q1.size() != n) throw 6005;          // incongruent_bead_states
-	}
 	if (!pi_gpu) {
+		const int n = systems[0]->countNatoms();
+		std::vector<double> pos, q, al, ep, sg, ms;
+		std::vector<int> mol, fz;
+		pos.reserve((size_t)PL * n * 3);
+		for (int s = 0; s < P; s++) {
+			std::vector<double> p1, q1, a1, e1, s1, m1;
+			std::vector<int> mo1, f1;
+			systems[s]->flatten(s >= b_lo && s < b_hi ? pos : p1, q1, a1, e1, s1, m1, mo1, f1);
+			if (s == 0) { q.swap(q1); al.swap(a1); ep.swap(e1); sg.swap(s1); ms.swap(m1); mol.swap(mo1); fz.swap(f1); }
+			else if ((int)q1.size() != n) throw 6005;          // incongruent_bead_states
+		}
+		// list position -> first site, once (path-integral runs neither insert nor remove molecules)
+		pi_mol_first.clear();
+		int at = 0;
+		for (Molecule *m = systems[0]->molecules; m; m = m->next) { pi_mol_first.push_back(at); at += m->natoms(); }
+		pi_mol_first.push_back(at);
 		mpmc_config c;
-		systems[0]->fill_config(c, P);
+		systems[0]->fill_config(c, PL);
 		if ((rc = mpmc_create(&c, &pi_gpu))) throw rc;
 		if ((rc = mpmc_upload_sites(pi_gpu, n, pos.data(), q.data(), al.data(), ep.data(), sg.data(), ms.data(), mol.data(), fz.data()))) throw rc;
+		if (nranks > 1 && (rc = mpmc_nccl_init(pi_gpu, nccl_id, rank, nranks))) throw rc;
+		pi_dirty.clear();
 	} else {
-		int lo = n, hi = -1;                                // the moved molecule is the same contiguous run of sites in every bead system
-		for (int s = 0; s < P; s++)
-			for (int i = 0; i < n; i++)
-				if (memcmp(&pos[((size_t)s * n + i) * 3], &pi_gpu_pos[((size_t)s * n + i) * 3], 3 * sizeof(double))) { lo = std::min(lo, i); hi = std::max(hi, i); }
-		if (hi >= lo) {
-			const int cnt = hi - lo + 1;
-			std::vector<double> seg((size_t)P * cnt * 3);
-			for (int s = 0; s < P; s++) memcpy(&seg[(size_t)s * cnt * 3], &pos[((size_t)s * n + lo) * 3], sizeof(double) * 3 * cnt);
-			if ((rc = mpmc_update_sites_all_beads(pi_gpu, lo, cnt, seg.data()))) throw rc;
+		std::sort(pi_dirty.begin(), pi_dirty.end());
+		pi_dirty.erase(std::unique(pi_dirty.begin(), pi_dirty.end()), pi_dirty.end());
+		for (int lp : pi_dirty) {
+			const int first = pi_mol_first[lp], cnt = pi_mol_first[lp + 1] - first;
+			std::vector<double> seg((size_t)PL * cnt * 3);
+			for (int s = b_lo; s < b_hi; s++) {
+				Molecule *m = systems[s]->molecules;
+				for (int k = 0; k < lp && m; k++) m = m->next;
+				if (!m) throw internal_error;
+				double *o = &seg[(size_t)(s - b_lo) * cnt * 3];
+				int k = 0;
+				for (Atom *a = m->atoms; a; a = a->next, k++) { if (k >= cnt) throw internal_error; o[3 * k] = a->pos[0]; o[3 * k + 1] = a->pos[1]; o[3 * k + 2] = a->pos[2]; }
+				if (k != cnt) throw internal_error;
+			}
+			if ((rc = mpmc_update_sites_all_beads(pi_gpu, first, cnt, seg.data()))) throw rc;
 		}
+		pi_dirty.clear();
 	}
-	pi_gpu_pos.swap(pos);
 	double means[4], U;
+	pi_sweeps++;
 	if ((rc = mpmc_pi_potential_allreduce(pi_gpu, P, means, &U))) throw rc;
 	System::observables_t *obs = sys.observables;
 	obs->rd_energy = means[0]; obs->coulombic_energy = means[1]; obs->polarization_energy = means[2]; obs->vdw_energy = means[3];
@@ -270,6 +290,12 @@ int SimulationControl::PI_pick_NVT_move() {
 		if (cand.empty()) throw no_molecules_in_system;
 		const int target = (int)std::floor(cand.size() * dice_target);
 		S->checkpoint->molecule_altered = cand[target];
+		if (s == 0) {                                   // list position of the molecule this step alters (and restore() may put back)
+			int lp = 0;
+			for (Molecule *m = S->molecules; m && m != cand[target]; m = m->next) lp++;
+			pi_target_pos = lp;
+			pi_dirty.push_back(lp);
+		}
 		S->checkpoint->movetype = (dice_move < sys.bead_perturb_probability) ? MOVETYPE_PERTURB_BEADS : MOVETYPE_DISPLACE;
 		Molecule *prev = nullptr;
 		for (Molecule *m = S->molecules; m; m = m->next) {
@@ -355,6 +381,7 @@ void SimulationControl::PI_perturb_bead_COMs_ENTIRE_SYSTEM() {      // :1402-144
 		for (int s = 0; s < nSys; s++) ptr[s] = ptr[s]->next;
 	}
 	for (int s = 0; s < nSys; s++) systems[s]->checkpoint->molecule_altered = backup[s];
+	if (pi_gpu) for (int lp = 0; lp + 1 < (int)pi_mol_first.size(); lp++) pi_dirty.push_back(lp);
 }
 
 void SimulationControl::PI_perturb_bead_COMs() { PI_perturb_bead_COMs(PI_trial_chain_length); }
@@ -400,6 +427,7 @@ void SimulationControl::PI_perturb_bead_COMs(int n) {
 
 void SimulationControl::restore_PI_systems() {
 	for (System *S : systems) { S->iterator_failed = 0; S->restore(); }
+	pi_dirty.push_back(pi_target_pos);                  // the device still holds the rejected coordinates
 }
 
 double SimulationControl::PI_NVT_boltzmann_factor(double d_potential, double d_chain, int movetype) {   // :490-547
@@ -420,6 +448,8 @@ bool SimulationControl::PI_nvt_mc(std::vector<System::step_record> *log) {     /
 	System::observables_t saved = *sys.observables;
 	double pot_current = sys.observables->potential();
 	if (!std::isfinite(pot_current)) sys.observables->energy = pot_current = MAXVALUE;
+	const auto t_loop = std::chrono::steady_clock::now();
+	const long long sweeps0 = pi_sweeps;
 	for (sys.step = 1; sys.step <= sys.numsteps; sys.step++) {
 		const double pot_init = pot_current;
 		const double chain_init = (move == MOVETYPE_PERTURB_BEADS) ? PI_chain_mass_length2() : 0;
@@ -446,6 +476,8 @@ bool SimulationControl::PI_nvt_mc(std::vector<System::step_record> *log) {     /
 		if (log) log->push_back({move, pot_trial, bf, accepted, sys.observables->kinetic_energy});
 		move = PI_pick_NVT_move();
 	}
+	loop_seconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - t_loop).count();
+	loop_sweeps = pi_sweeps - sweeps0;
 	return true;
 }
 

@@ -17,6 +17,9 @@ def lib():
         path = _build.build_host()
         L = C.CDLL(path)
         L.mpmc_host_run.argtypes = [C.c_char_p, C.c_int, C.c_int, C.c_void_p, C.c_int, C.POINTER(C.c_int), C.c_void_p]
+        L.mpmc_host_run_sharded.argtypes = [C.c_char_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_char_p, C.c_void_p, C.c_int, C.POINTER(C.c_int), C.c_void_p]
+        L.mpmc_host_last_stats.argtypes = [C.c_void_p]
+        L.mpmc_host_last_stats.restype = None
         L.mpmc_host_energy.argtypes = [C.c_char_p, C.c_void_p]
         L.mpmc_host_describe.argtypes = [C.c_char_p, C.c_int, C.c_int, C.POINTER(C.c_int)] + [C.c_void_p] * 9
         _lib = L
@@ -38,6 +41,31 @@ def run(input_file: str, P: int = 0, max_steps: int = 0, capacity: int = 20000):
     if rc:
         raise RuntimeError("host run failed with code %d" % rc)
     return log[: n.value].copy(), summary
+
+
+def run_sharded(input_file: str, P: int, rank: int, nranks: int, device: int, nccl_id: bytes, max_steps: int = 0, capacity: int = 20000):
+    """A path-integral run with the bead systems sharded over `nranks` processes (one GPU each); call from every rank with the same
+    128-byte id (mpmcxx_b200.engine.nccl_unique_id() of rank 0).  Returns (log[n,5], summary[8]), identical on every rank."""
+    log = np.zeros((capacity, 5))
+    summary = np.zeros(8)
+    n = C.c_int()
+    cwd = os.getcwd()
+    os.chdir(os.path.dirname(os.path.abspath(input_file)))
+    try:
+        rc = lib().mpmc_host_run_sharded(os.path.basename(input_file).encode(), P, max_steps, rank, nranks, device, nccl_id,
+                                         log.ctypes.data_as(C.c_void_p), capacity, C.byref(n), summary.ctypes.data_as(C.c_void_p))
+    finally:
+        os.chdir(cwd)
+    if rc:
+        raise RuntimeError("sharded host run failed with code %d" % rc)
+    return log[: n.value].copy(), summary
+
+
+def last_stats():
+    """(wall seconds of the last run's step loop, potential sweeps made in it)"""
+    o = np.zeros(2)
+    lib().mpmc_host_last_stats(o.ctypes.data_as(C.c_void_p))
+    return float(o[0]), float(o[1])
 
 
 def energy(input_file: str):

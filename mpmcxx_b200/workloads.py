@@ -287,7 +287,7 @@ H2_SINGLE = dict(eps=34.2, sigma=2.96, mass=2.016)
 
 
 def pi_h2_cluster(n_side: int = 8, P: int = 64, a: float = 3.8, L: float = 100.0, five_site: bool = False,
-                  seed: int = 1, bead_sigma: float = 0.25):
+                  seed: int = 1, bead_sigma: float = 0.25, polarizable: bool = False, solver: dict | None = None):
     """Config 5: n_side^3 H2 molecules on a centred cubic lattice, P beads each.  Returns (template, beads) where
     `template` is the SiteSystem of bead 0's centroid geometry and `beads` is a (P, n, 3) array of per-bead site
     positions (centroid + one gaussian COM offset per molecule per bead; rigid molecules keep their orientation)."""
@@ -309,10 +309,13 @@ def pi_h2_cluster(n_side: int = 8, P: int = 64, a: float = 3.8, L: float = 100.0
         pos = []; q = []; alpha = []; eps = []; sig = []; mass = []; mol = []; at = []
         for m in range(M):
             for (name, off, qq, al, ee, ss, ms) in H2_SITES:
-                pos.append(centres[m] + off * axes[m]); q.append(qq); alpha.append(0.0); eps.append(ee); sig.append(ss)
+                pos.append(centres[m] + off * axes[m]); q.append(qq); alpha.append(al if polarizable else 0.0); eps.append(ee); sig.append(ss)
                 mass.append(ms); mol.append(m); at.append(name)
         n = len(q)
         opts["ewald_kmax"] = "7"
+        if polarizable:     # every bead system is polarized on its own (src/SimulationControl.PathIntegral.cpp:770-780)
+            opts.update(POLAR_OPTS)
+            opts.update(solver if solver is not None else SOLVER_GS_RANKED_PALMO)
         tmpl = _mk(np.eye(3) * L, np.array(pos), q, alpha, eps, sig, mass, mol, np.zeros(n), at, ["H2"] * n, opts)
     off = rs.normal(scale=bead_sigma, size=(P, M, 3))
     beads = tmpl.pos[None, :, :] + off[:, tmpl.mol, :]

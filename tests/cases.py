@@ -59,6 +59,10 @@ CLASSIC = {
 PI = {
     "pi_h2_single_27x8": lambda: W.pi_h2_cluster(n_side=3, P=8, L=40.0),
     "pi_h2_five_8x4": lambda: W.pi_h2_cluster(n_side=2, P=4, L=30.0, five_site=True),
+    # polarizable bead systems: Gauss-Seidel ranked + Palmo per bead (81 polarizable sites = 2 blocks), and a precision-controlled
+    # Jacobi solve whose beads converge after different numbers of iterations
+    "pi_h2_polar_gs_27x4": lambda: W.pi_h2_cluster(n_side=3, P=4, L=30.0, five_site=True, polarizable=True, solver=W.SOLVER_GS_RANKED_PALMO),
+    "pi_h2_polar_prec_8x4": lambda: W.pi_h2_cluster(n_side=2, P=4, L=30.0, five_site=True, polarizable=True, solver={"polar_precision": "1e-8"}, bead_sigma=0.5),
 }
 
 

@@ -128,3 +128,10 @@ int mpmc_pi_potential_allreduce(mpmc_engine *e, int P_global, double means[4], d
 	if (potential) *potential = means[0] + means[1] + means[3] + means[2];
 	return MPMC_OK;
 }
+
+/* bead sharding needs GPUs and NCCL: the CPU shim only ever runs single-rank */
+int mpmc_nccl_init(mpmc_engine *e, const char id[128], int rank, int nranks) {
+	(void)e; (void)id; (void)rank; (void)nranks;
+	g_err = "the CPU test shim has no collective";
+	return MPMC_ERR_UNSUPPORTED;
+}

@@ -116,6 +116,18 @@ def test_pi_matches_reference_golden(name):
         outs = e.energy_all()
         scale = np.mean([abs(o["es_real"]) + abs(o["es_self_intra"]) + abs(o["es_reciprocal"]) + abs(o["es_self"]) for o in outs])
         assert abs(es - float(r["ref_pi_coulombic"])) <= RTOL * scale
+    if float(r["ref_pi_polar"]) != 0.0:
+        # polarizable bead systems (src/SimulationControl.PathIntegral.cpp:770-780): the mean against the reference, and every bead's
+        # energy, iteration count and failure flag against the oracle's per-bead solve (beads converge independently)
+        from oracle import port
+        assert _rel(sums[2] / P, float(r["ref_pi_polar"])) < RTOL
+        outs = e.energy_all()
+        for b in range(P):
+            p = port.energy(s, pos=beads[b], want_sites=False)
+            assert _rel(outs[b]["polarization_energy"], p["polar"]) < RTOL, (b, outs[b]["polarization_energy"], p["polar"])
+            assert outs[b]["polarization_iterations"] == int(p["iterations"]) and outs[b]["iterator_failed"] == int(p["iterator_failed"])
+        pot, means = e.pi_potential_allreduce(P)
+        assert _rel(means[2], float(r["ref_pi_polar"])) < RTOL
     chain, com, mm = e.pi_chain(closed=True)
     assert _rel(chain, float(r["ref_pi_chain_mass_len2"])) < 1e-12
     e.close()

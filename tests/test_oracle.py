@@ -66,6 +66,8 @@ def test_port_pi_matches_golden(name):
     assert _rel(o["chain_mass_len2"], float(r["ref_pi_chain_mass_len2"])) < 1e-13
     assert _rel(o["kinetic"], float(r["ref_pi_kinetic"])) < 1e-12
     assert abs(o["potential"] - float(r["ref_pi_potential"])) < 1e-9 * max(1.0, abs(float(r["ref_pi_potential"])))
+    if float(r["ref_pi_polar"]) != 0.0:
+        assert _rel(o["polar"], float(r["ref_pi_polar"])) < RTOL
 
 
 def test_survey_known_answers():
