@@ -125,6 +125,29 @@ def write_shipped(files, directory):
             fp.write(v)
 
 
+# ensemble averages (north_star's third criterion): name -> (builder, P, steps, seeds run by the reference for the golden, seeds the
+# engine's chains use in the test).  Different seeds on the two sides: the chains are statistically independent, and the means of
+# energy / N (uVT) and of the potential / kinetic energy (pi_nvt: kinetic = const - 1/2 omega^2 sum m <r^2> of the bead chains,
+# src/SimulationControl.PathIntegral.cpp:810-828) must agree within the combined standard error.
+def _avg_uvt():
+    s = W.uvt_pore()
+    s.opts.update({"numsteps": "6000"})
+    return s
+
+
+def _avg_pi():
+    tmpl, _ = W.pi_h2_cluster(n_side=3, P=8, L=40.0)
+    tmpl.opts.update({"numsteps": "6000", "PI_trial_chain_length": "3"})
+    return tmpl
+
+
+AVERAGES = {
+    "avg_uvt_pore": (_avg_uvt, 0, 6000, (101, 102, 103, 104), (201, 202, 203, 204)),
+    "avg_pi_h2_27x8": (_avg_pi, 8, 6000, (101, 102, 103, 104), (201, 202, 203, 204)),
+}
+AVG_BLOCKS = 6
+
+
 # jobs whose parse (input file + PQR -> flat site table + cell) is pinned against the reference's own readers: (builder, Trotter number)
 PARSED = {
     "lj_lattice_4": (lambda: W.lj_lattice(4, 20.0), 0),

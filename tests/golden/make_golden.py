@@ -119,6 +119,38 @@ def one_shipped(name):
     print("%-28s steps=%d acceptance=%.3f kinetic[0..2]=%s" % (name, steps, traj[:, 3].mean(), traj[:3, 4].tolist()), flush=True)
 
 
+def one_average(name, seed):
+    """One chain of the reference for the ensemble-average comparison: block means of the current-state series."""
+    from mpmcxx_b200 import averages
+    build, P, steps, _, _ = cases.AVERAGES[name]
+    s = build()
+    s.opts["seed"] = str(seed)
+    r = ref.RefSystem(s, P=P)
+    first = r.pi_potential() if P else r.energy()["energy"]
+    r2 = ref.RefSystem(s, P=P)          # the trajectory replay starts from its own fresh state
+    traj = r2.pi_trajectory(steps) if P else r2.mc_trajectory(steps)
+    ser = averages.chain_series(traj, first)
+    out = {"energy": averages.block_means(ser["energy"], cases.AVG_BLOCKS), "aux": averages.block_means(ser["aux"], cases.AVG_BLOCKS),
+           "acceptance": np.float64(ser["accepted"].mean())}
+    np.savez(os.path.join(HERE, "_avg_%s_%d.npz" % (name, seed)), **out)
+
+
+def averages_golden():
+    """Per chain a fresh process (Rando's cached normal, see trajectories()); the per-seed pieces are merged into one small fixture."""
+    import subprocess
+    for name, (build, P, steps, ref_seeds, _) in cases.AVERAGES.items():
+        for seed in ref_seeds:
+            subprocess.run([sys.executable, os.path.abspath(__file__), "avg1", name, str(seed)], check=True)
+        parts = [np.load(os.path.join(HERE, "_avg_%s_%d.npz" % (name, seed))) for seed in ref_seeds]
+        np.savez_compressed(os.path.join(HERE, name + ".npz"), seeds=np.array(ref_seeds), energy=np.stack([p["energy"] for p in parts]),
+                            aux=np.stack([p["aux"] for p in parts]), acceptance=np.array([p["acceptance"] for p in parts]), steps=np.int32(steps))
+        for seed in ref_seeds:
+            os.remove(os.path.join(HERE, "_avg_%s_%d.npz" % (name, seed)))
+        z = np.load(os.path.join(HERE, name + ".npz"))
+        print("%-18s <E> %.6g +- %.3g   <aux> %.6g +- %.3g   acceptance %s" % (name, z["energy"].mean(), z["energy"].std(ddof=1) / np.sqrt(z["energy"].size),
+              z["aux"].mean(), z["aux"].std(ddof=1) / np.sqrt(z["aux"].size), z["acceptance"].round(3).tolist()), flush=True)
+
+
 def shipped():
     import subprocess
     for name in cases.SHIPPED:
@@ -126,6 +158,12 @@ def shipped():
 
 
 if __name__ == "__main__":
+    if len(sys.argv) > 3 and sys.argv[1] == "avg1":
+        one_average(sys.argv[2], int(sys.argv[3]))
+        sys.exit(0)
+    if len(sys.argv) > 1 and sys.argv[1] == "averages":
+        averages_golden()
+        sys.exit(0)
     if len(sys.argv) > 2 and sys.argv[1] == "shipped1":
         one_shipped(sys.argv[2])
         sys.exit(0)
@@ -148,3 +186,4 @@ if __name__ == "__main__":
     parsed()
     trajectories()
     shipped()
+    averages_golden()
