@@ -181,6 +181,77 @@ __device__ __forceinline__ void tensor_contract_exp(const CellDev &c, double lam
 	az = fma(-bd, dz, fma(a, mz, az));
 }
 
+// ---- branch-free building blocks for the contraction sweeps ---------------------------------------------------------------
+// The library rsqrt() and exp() each carry a rare-case branch; with one of each per pair the compiler emits every contraction as
+// its own sequence of divergence regions and cannot interleave two of them: a warp then runs its contractions back to back, one
+// dependent chain at a time (~150 instructions, ~700 cycles each at 4 warps per scheduler), and the FP64 pipe idles half the
+// time.  These forms have no branches, so two contractions can be issued as one interleaved stream.
+
+// 1/sqrt(u) for normal positive u: hardware seed (2^-23) + two Newton steps; <= 1 ulp
+__device__ __forceinline__ double rsqrt_nr(double u) {
+	double y;
+	asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(u));
+	const double h = 0.5 * u;
+	double e = fma(-(h * y), y, 0.5);
+	y = fma(y, e, y);
+	e = fma(-(h * y), y, 0.5);
+	return fma(y, e, y);
+}
+
+// e^x for x in [-700, 0]: x = k ln2 + r, |r| <= ln2 / 2, degree-13 Taylor polynomial (truncation 4e-18), 2^k through the exponent field; <= 2 ulp
+__device__ __forceinline__ double exp_nonpos(double x) {
+	const double kMagic = 6755399441055744.0;
+	double t = fma(x, 1.4426950408889634074, kMagic);
+	const int k = __double2loint(t);
+	t -= kMagic;
+	double r = fma(-t, 6.93147180369123816490e-01, x);
+	r = fma(-t, 1.90821492927058770002e-10, r);
+	double p = 1.6059043836821613e-10;                 // 1/13!
+	p = fma(p, r, 2.0876756987868100e-09);            // 1/12!
+	p = fma(p, r, 2.5052108385441720e-08);            // 1/11!
+	p = fma(p, r, 2.7557319223985888e-07);            // 1/10!
+	p = fma(p, r, 2.7557319223985893e-06);            // 1/9!
+	p = fma(p, r, 2.4801587301587302e-05);            // 1/8!
+	p = fma(p, r, 1.9841269841269841e-04);            // 1/7!
+	p = fma(p, r, 1.3888888888888889e-03);            // 1/6!
+	p = fma(p, r, 8.3333333333333332e-03);            // 1/5!
+	p = fma(p, r, 4.1666666666666664e-02);            // 1/4!
+	p = fma(p, r, 1.6666666666666666e-01);            // 1/3!
+	p = fma(p, r, 0.5);
+	p = fma(p, r, 1.0);
+	p = fma(p, r, 1.0);
+	return __hiloint2double(__double2hiint(p) + (k << 20), __double2loint(p));
+}
+
+// acc += T_i,j0 mu_j0 + T_i,j1 mu_j1 (exponential damping), the two contractions as ONE branch-free stream apart from a single test:
+// the damping factors are evaluated for BOTH columns when either needs them (for lambda r >= 50 they come out as exactly 1, as
+// tensor_contract_exp skips them).  The sums are taken in the order j0, j1, like two calls of tensor_contract_exp.
+template <bool ORTHO>
+__device__ __forceinline__ void tensor_contract_exp_x2(const CellDev &c, double lambda, double u_damp, double xi, double yi, double zi,
+                                                       double x0, double y0, double z0, double m0x, double m0y, double m0z,
+                                                       double x1, double y1, double z1, double m1x, double m1y, double m1z,
+                                                       double &ax, double &ay, double &az) {
+	double d0x, d0y, d0z, d1x, d1y, d1z;
+	min_image_fast<ORTHO>(c, __dsub_rn(xi, x0), __dsub_rn(yi, y0), __dsub_rn(zi, z0), d0x, d0y, d0z);
+	min_image_fast<ORTHO>(c, __dsub_rn(xi, x1), __dsub_rn(yi, y1), __dsub_rn(zi, z1), d1x, d1y, d1z);
+	const double u0 = fma(d0z, d0z, fma(d0y, d0y, d0x * d0x)), u1 = fma(d1z, d1z, fma(d1y, d1y, d1x * d1x));
+	// coincident sites (and the i == j column): the reference multiplies MAXVALUE by damping factors that are exactly 0 (:2704-2705)
+	const double ir0 = u0 > 0.0 ? rsqrt_nr(u0 > 0.0 ? u0 : 1.0) : 0.0, ir1 = u1 > 0.0 ? rsqrt_nr(u1 > 0.0 ? u1 : 1.0) : 0.0;
+	const double i20 = ir0 * ir0, i21 = ir1 * ir1, i30 = i20 * ir0, i31 = i21 * ir1;
+	double a0 = i30, b0 = 3.0 * i30 * i20, a1 = i31, b1 = 3.0 * i31 * i21;
+	if (u0 < u_damp || u1 < u_damp) {
+		const double l0 = lambda * (u0 * ir0), l1 = lambda * (u1 * ir1);
+		const double e0 = exp_nonpos(-l0), e1 = exp_nonpos(-l1);
+		const double g0 = fma(-e0, fma(0.5 * l0, l0, l0) + 1.0, 1.0), g1 = fma(-e1, fma(0.5 * l1, l1, l1) + 1.0, 1.0);   // 1 - e (l^2 r^2 / 2 + l r + 1)
+		const double h0 = fma(-e0, l0 * l0 * l0 * (1.0 / 6.0), g0), h1 = fma(-e1, l1 * l1 * l1 * (1.0 / 6.0), g1);       // damp1 - e l^3 r^3 / 6
+		a0 *= g0; b0 *= h0; a1 *= g1; b1 *= h1;
+	}
+	const double q0 = b0 * fma(d0z, m0z, fma(d0y, m0y, d0x * m0x)), q1 = b1 * fma(d1z, m1z, fma(d1y, m1y, d1x * m1x));
+	ax = fma(-q1, d1x, fma(a1, m1x, fma(-q0, d0x, fma(a0, m0x, ax))));
+	ay = fma(-q1, d1y, fma(a1, m1y, fma(-q0, d0y, fma(a0, m0y, ay))));
+	az = fma(-q1, d1z, fma(a1, m1z, fma(-q0, d0z, fma(a0, m0z, az))));
+}
+
 // copy a table into shared memory (all threads of the CTA; len even, both 16-byte aligned): asynchronous 16-byte copies, all in
 // flight at once.  The caller runs stage_table_wait() and then synchronises the CTA before the first look-up.
 __device__ __forceinline__ void stage_table(double *dst, const double *__restrict__ src, int len) {

@@ -981,8 +981,8 @@ static int run_polar(mpmc_engine *e) {
 				if (!need_old && !want_check && cf.polar_precision == 0.0) ns = (ranked && it == 1) ? 1 : (cf.polar_max_iter - it + 1);
 				long long *prof = nullptr;
 				if (e->gs_prof_enabled) {
-					if ((rc = e->d_gsprof.ensure((size_t)nblk * 16))) return rc;
-					CK(cudaMemsetAsync(e->d_gsprof.p, 0, sizeof(long long) * nblk * 16, e->stream));
+					if ((rc = e->d_gsprof.ensure((size_t)nblk * 32))) return rc;
+					CK(cudaMemsetAsync(e->d_gsprof.p, 0, sizeof(long long) * (size_t)nblk * 32, e->stream));
 					prof = e->d_gsprof.p;
 					e->gs_prof_nblk = nblk;
 				}
@@ -1010,7 +1010,7 @@ static int run_polar(mpmc_engine *e) {
 						// griddepcontrol.launch_dependents, i.e. is resident.  No host wait, no second stream; the next operation in the stream
 						// waits for both kernels.
 						cudaLaunchConfig_t lc = {};
-						lc.gridDim = dim3(e->gs_upd_grid); lc.blockDim = dim3(kGsThreads); lc.dynamicSmemBytes = kGsUpdaterSmemBytes; lc.stream = e->stream;
+						lc.gridDim = dim3(e->gs_upd_grid); lc.blockDim = dim3(kGsUpdThreads); lc.dynamicSmemBytes = kGsUpdaterSmemBytes; lc.stream = e->stream;
 						cudaLaunchAttribute at[1];
 						at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization; at[0].val.programmaticStreamSerializationAllowed = 1;
 						lc.attrs = at; lc.numAttrs = 1;
@@ -1224,8 +1224,9 @@ int mpmc_create(const mpmc_config *cfg, mpmc_engine **out) {
 		if ((rc = set_smem(k_gs_updaters<true, true>, kGsUpdaterSmemBytes)) || (rc = set_smem(k_gs_updaters<false, true>, kGsUpdaterSmemBytes)) ||
 		    (rc = set_smem(k_gs_updaters<true, false>, kGsUpdaterSmemBytes)) || (rc = set_smem(k_gs_updaters<false, false>, kGsUpdaterSmemBytes))) { mpmc_destroy(e); return rc; }
 		int occ = 0;
-		CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_gs_updaters<true, true>, kGsThreads, kGsUpdaterSmemBytes));
-		e->gs_upd_grid = std::max(1, e->num_sms - kGsCluster) * std::max(1, std::min(occ, kGsUpdCtas));
+		CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_gs_updaters<true, true>, kGsUpdThreads, kGsUpdaterSmemBytes));
+		if (occ < 1) FAIL(MPMC_ERR_CUDA, "the Gauss-Seidel updater kernel does not fit an SM");
+		e->gs_upd_grid = std::max(1, e->num_sms - kGsCluster);
 		e->gs_grid = kGsCluster;
 		// single-launch fallback: as many clusters as the device holds at one CTA per SM
 		cudaLaunchConfig_t lc = {};
@@ -1690,6 +1691,8 @@ int mpmc_debug_gs_profile(mpmc_engine *e, int enable, long long *out, int max_bl
 		const int nb = std::min(max_blocks, e->gs_prof_nblk);
 		CK(cudaMemcpy(out, e->d_gsprof.p, sizeof(long long) * 8 * nb, cudaMemcpyDeviceToHost));
 		CK(cudaMemcpy(out + (size_t)8 * max_blocks, e->d_gsprof.p + (size_t)8 * e->gs_prof_nblk, sizeof(long long) * 8 * nb, cudaMemcpyDeviceToHost));
+		// (optional third part, when the caller's buffer has room for it: per-chunk hand-over stamps, 16 chunks per block)
+		if (enable & 0x100) CK(cudaMemcpy(out + (size_t)16 * max_blocks, e->d_gsprof.p + (size_t)16 * e->gs_prof_nblk, sizeof(long long) * 16 * nb, cudaMemcpyDeviceToHost));
 		if (nblk) *nblk = nb;
 	}
 	return MPMC_OK;

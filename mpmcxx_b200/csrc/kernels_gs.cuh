@@ -37,7 +37,8 @@ namespace mpmc {
 constexpr int kGsB = 64;                  // sites per solver block
 constexpr int kGsRows = 4;                // rows per updater chunk (one warp: 4 rows x 8 column lanes)
 constexpr int kGsColLanes = 32 / kGsRows;
-constexpr int kGsUpdCtas = 3;             // updater CTAs per SM the kernel is compiled for (85 registers: the row sums live in registers)
+constexpr int kGsUpdWarps = 17, kGsUpdThreads = 32 * kGsUpdWarps;   // ONE updater CTA of 17 warps per SM: 140 SMs x 17 = 2380 warps for the 2300
+                                          // four-row chunks of 9200 polarizable sites (16 or 17 busy warps on every SM; 96 registers: five warps share a scheduler's 16 K)
 constexpr int kGsThreads = 256;
 constexpr int kGsWarps = kGsThreads / 32;
 constexpr int kGsPipeThreads = 512;       // the solver/helper cluster: 192 x 2 threads walk, 512 per helper push
@@ -52,17 +53,25 @@ constexpr int kGsTileDim = 32, kGsTilesPerSide = kGsN / kGsTileDim, kGsTiles = k
 __host__ __device__ constexpr int gs_tile(int I, int J) { return I * (I + 1) / 2 + J; }
 constexpr int kGsMat = kGsTiles * kGsTileDim * kGsTileDim;   // 21504 doubles of the solver's matrix buffer (172 KB)
 
-// shared memory (doubles).  Solver: the block's inverse, two site-column buffers, the pending pushes of the next blocks, panel dmu,
-// right-hand side, second halves of the dot products, site ids.  Updaters: per warp the panel's columns and dmu.
+// shared memory (doubles).  Updaters: per warp the panel's columns and dmu.
 constexpr int kGsSiteCols = 10;           // 0 alpha, 1-3 mu_old, 4-6 E_static, 7-9 acc
 constexpr int kGsAhead = 4;               // the cluster pushes a panel into this many following blocks itself; the updaters take the rest
 constexpr int kGsHelpers = 7, kGsCluster = 1 + kGsHelpers;
-constexpr int kGsSlots = kGsAhead + 1;    // ring of per-block buffers
-constexpr size_t kGsSolverDoubles = (size_t)kGsMat + 2 * kGsSiteCols * kGsB + kGsSlots * 3 * kGsB + 4 * kGsB + kGsN + kGsTiles * kGsTileDim + 2 * kGsB + 16;
-constexpr size_t kGsUpdaterDoubles = (size_t)kGsWarps * 8 * kGsB;
-constexpr int kGsHelperOutOffset = 4 * kGsB;      // doubles: a helper's delivery buffer inside its shared memory (after h_dm)
+// Solver: the block's inverse, two site-column buffers, the helpers' deliveries for the block about to be solved, panel dmu, right-hand
+// side, per-tile partial products, site ids, barriers.  Helpers: the panel, a ring of pending sums for the next kGsAhead blocks, the two
+// column slices' partial sums, a barrier.  (Offsets in doubles from the start of dynamic shared memory; the same in every CTA, so a
+// CTA can form the address of a peer's buffer from its own.)
+constexpr int kGsHelpDm = 0;                                   // double4[kGsB]: the panel's dipole changes (written by the solver)
+constexpr int kGsHelpAcc = kGsHelpDm + 4 * kGsB;               // [kGsAhead][kGsN]: what this helper has pushed into the next blocks' rows so far
+constexpr int kGsHelpPart = kGsHelpAcc + kGsAhead * kGsN;      // [2 column slices][kGsAhead * kGsB][3]
+constexpr int kGsHelpBar = kGsHelpPart + 2 * kGsAhead * kGsB * 3;   // one mbarrier (8 bytes)
+constexpr int kGsSolIn = kGsMat + 2 * kGsSiteCols * kGsB;      // [kGsHelpers][kGsN]: the helpers' deliveries (written by the helpers)
+constexpr int kGsSolBar = kGsSolIn + kGsHelpers * kGsN;        // two mbarriers: deliveries, inverse
+constexpr size_t kGsSolverDoubles = (size_t)kGsSolBar + 2 + 4 * kGsB + kGsN + kGsTiles * kGsTileDim + 2 * kGsB + 16;
+static_assert(kGsSolverDoubles >= (size_t)kGsHelpBar + 1, "helpers use the same allocation");
 static_assert(kGsSolverDoubles >= (size_t)(kGsPipeThreads / 32) * 8 * kGsB, "the fused fallback runs the updaters inside the pipeline kernel");
 constexpr size_t kGsSmemBytes = sizeof(double) * kGsSolverDoubles;
+constexpr size_t kGsUpdaterDoubles = (size_t)kGsUpdWarps * 8 * kGsB;
 constexpr size_t kGsUpdaterSmemBytes = sizeof(double) * kGsUpdaterDoubles;
 
 __device__ int g_gs_debug = 0;            // developer switch (mpmc_debug_gs_profile enable bits 1..): 2 = pushers idle, 4 = no rolling copy
@@ -89,6 +98,18 @@ __device__ __forceinline__ void mbar_init(unsigned bar, unsigned count) { asm vo
 __device__ __forceinline__ void mbar_expect_tx(unsigned bar, unsigned bytes) { asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory"); }
 __device__ __forceinline__ void bulk_g2s(unsigned dst, const void *src, unsigned bytes, unsigned bar) {
 	asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+// address of the same shared-memory location in CTA `rank` of the cluster, and an 8-byte store into a peer's shared memory that
+// signals the peer's mbarrier when it lands (no flag, no fence, no polling over the cluster network: the reader sleeps on its own barrier)
+__device__ __forceinline__ unsigned map_to_cta(unsigned addr, unsigned rank) { unsigned r; asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank)); return r; }
+__device__ __forceinline__ void st_async_f64(unsigned remote_addr, double v, unsigned remote_bar) {
+	asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.b64 [%0], %1, [%2];" ::"r"(remote_addr), "l"(__double_as_longlong(v)), "r"(remote_bar) : "memory");
+}
+// bulk copy from my shared memory into a peer's, completion signalled on the PEER's barrier (one wide transfer instead of hundreds of
+// 8-byte stores: the cluster port handles ~1 small store per 1.5 cycles, which made 7 x 192 doubles take 1 us)
+__device__ __forceinline__ void bulk_s2peer(unsigned remote_dst, unsigned local_src, unsigned bytes, unsigned remote_bar) {
+	asm volatile("fence.proxy.async.shared::cta;" ::: "memory");     // my generic-proxy stores to the source are visible to the copy engine
+	asm volatile("cp.async.bulk.shared::cluster.shared::cta.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(remote_dst), "r"(local_src), "r"(bytes), "r"(remote_bar) : "memory");
 }
 __device__ __forceinline__ void mbar_wait(unsigned bar, unsigned parity) {
 	unsigned ok;
@@ -296,48 +317,101 @@ __device__ __forceinline__ void gs_updater_body(double *s_raw, int cta, int U, c
 		}
 		sx[w] = sy[w] = sz[w] = 0.0;
 	};
+	// Software pipeline over the panels: while a panel is contracted, the NEXT panel's columns (their positions are known in advance)
+	// and — when the solver is already past it — its dipole changes travel from L2 into registers; a warp that keeps up with the solver
+	// only ever waits for the flag, a warp that runs behind never waits for memory.
+	double4 pf_c[2];
+	int pf_m[2];
+	double pf_d[2][3];
+	bool pf_have_d = false;
+	auto fetch_cols = [&](int blk) {
+#pragma unroll
+		for (int h = 0; h < 2; h++) {
+			const int pos = blk * kGsB + lane + 32 * h;
+			const bool on = pos < np;
+			pf_c[h] = on ? gpq[pos] : make_double4(0, 0, 0, 0);
+			pf_m[h] = on ? gmeta[pos] : 0;
+		}
+	};
+	auto fetch_dmu = [&](int blk) {
+#pragma unroll
+		for (int h = 0; h < 2; h++) {
+			const int pos = blk * kGsB + lane + 32 * h;
+			const bool on = pos < np;
+#pragma unroll
+			for (int q = 0; q < 3; q++) pf_d[h][q] = on ? __ldcg(dmu + 3 * pos + q) : 0.0;     // beyond the end: zero change, contributes nothing
+		}
+	};
+	fetch_cols(0);
 	for (int blk = 0; blk < nblk; blk++) {
-		const int base = blk * kGsB, cnt = min(kGsB, np - base);
 		// the rows of the next kGsAhead blocks belong to the cluster (the panel's own rows do not: the solver writes them back
 		// before it publishes the panel, without the panel's own contribution)
 		const int skip0 = (blk + 1) * kChunksPerBlk, skip1 = min(blk + 1 + kGsAhead, nblk) * kChunksPerBlk;
-		bool any = more;
-#pragma unroll
-		for (int w = 0; w < kGsOwn; w++) any = any || (chs[w] >= 0 && !(chs[w] >= skip0 && chs[w] < skip1));
-		if (!any) continue;
 		__syncwarp();
-		for (int cc = lane; cc < cnt; cc += 32) {
-			const double4 g = gpq[base + cc];
-			w_col[cc] = make_double4(g.x, g.y, g.z, __longlong_as_double((long long)gmeta[base + cc]));   // alpha travels in w_dm.w
+#pragma unroll
+		for (int h = 0; h < 2; h++) {
+			const int cc = lane + 32 * h;
+			w_col[cc] = make_double4(pf_c[h].x, pf_c[h].y, pf_c[h].z, __longlong_as_double((long long)pf_m[h]));
+			if (!EXPD) w_dm[cc].w = pf_c[h].w;                      // alpha of the column (linear damping)
 		}
+		const bool had_d = pf_have_d;
+		if (had_d) {
+#pragma unroll
+			for (int h = 0; h < 2; h++) { double4 *d = w_dm + lane + 32 * h; d->x = pf_d[h][0]; d->y = pf_d[h][1]; d->z = pf_d[h][2]; }
+		}
+		if (blk + 1 < nblk) fetch_cols(blk + 1);
 		const bool pw = prof && cta == 0 && warp == 0 && lane == 0;
 		if (pw) prof[(nblk + blk) * 8 + 0] = clock64();
-		if (lane == 0) {
-			int spins = 0;
-			while (ld_flag(&ctl->solved) <= gbase + blk && !ld_flag(&ctl->abort)) {
-				__nanosleep(256);          // ~2300 warps watch this word: short sleeps saturate its L2 slice (the flags live next to it)
-				if (++spins > 3 * kGsWaitLimit) st_flag(&ctl->abort, 1);
+		if (!had_d) {
+			if (lane == 0) {
+				int spins = 0;
+				while (ld_flag(&ctl->solved) <= gbase + blk && !ld_flag(&ctl->abort)) {
+					__nanosleep(256);          // ~2300 warps watch this word: short sleeps saturate its L2 slice (the flags live next to it)
+					if (++spins > 3 * kGsWaitLimit) st_flag(&ctl->abort, 1);
+				}
 			}
+			if (__shfl_sync(0xffffffffu, ld_flag(&ctl->abort), 0)) return;
+			__syncwarp();
+			if (pw) prof[(nblk + blk) * 8 + 3] = clock64();
+			// every lane acquires the flag itself before it reads the panel (one load; a __threadfence() here also waits for the
+			// column prefetch in flight and cost 3.5 k cycles per panel)
+			(void)ld_acquire(&ctl->solved);
+			fetch_dmu(blk);
+#pragma unroll
+			for (int h = 0; h < 2; h++) { double4 *d = w_dm + lane + 32 * h; d->x = pf_d[h][0]; d->y = pf_d[h][1]; d->z = pf_d[h][2]; }
 		}
-		if (__shfl_sync(0xffffffffu, ld_flag(&ctl->abort), 0)) return;
-		__syncwarp();
-		__threadfence();
 		if (pw) prof[(nblk + blk) * 8 + 1] = clock64();
-		for (int cc = lane; cc < cnt; cc += 32)
-			w_dm[cc] = make_double4(__ldcg(dmu + 3 * (base + cc)), __ldcg(dmu + 3 * (base + cc) + 1), __ldcg(dmu + 3 * (base + cc) + 2), EXPD ? 0.0 : gpq[base + cc].w);
+		// is the next panel out already?  then its dipole changes come along during this panel's arithmetic
+		pf_have_d = false;
+		if (blk + 1 < nblk) {
+			const int sv = __shfl_sync(0xffffffffu, ld_acquire(&ctl->solved), 0);     // warp-uniform decision; every lane has acquired
+			if (sv > gbase + blk + 1) { fetch_dmu(blk + 1); pf_have_d = true; }
+		}
 		__syncwarp();
 #pragma unroll
 		for (int w = 0; w < kGsOwn; w++) {
 			if (chs[w] < 0 || (chs[w] >= skip0 && chs[w] < skip1)) continue;       // warp-uniform
 			if (mr[w] != -1) {
 				double ax = 0, ay = 0, az = 0;
-#pragma unroll 4
-				for (int cc = cl; cc < cnt; cc += kGsColLanes) {
-					double4 pc = w_col[cc];
-					const double4 dm = w_dm[cc];
-					const int mc = __double2loint(pc.w);
-					if (!EXPD) pc.w = dm.w;                           // alpha of the column (linear damping)
-					gs_contract<ORTHO, EXPD>(c, p, pr[w], mr[w], pc, mc, dm, ax, ay, az);
+				if (EXPD) {
+#pragma unroll
+					for (int i = 0; i < kGsB / kGsColLanes; i += 2) {    // the whole panel, no bounds: columns past the end carry a zero change
+						const int cc = cl + kGsColLanes * i;
+						const double4 p0 = w_col[cc], p1 = w_col[cc + kGsColLanes];
+						const double4 m0 = w_dm[cc], m1 = w_dm[cc + kGsColLanes];
+						tensor_contract_exp_x2<ORTHO>(c, p.damp, p.u_damp, pr[w].x, pr[w].y, pr[w].z, p0.x, p0.y, p0.z, m0.x, m0.y, m0.z,
+						                              p1.x, p1.y, p1.z, m1.x, m1.y, m1.z, ax, ay, az);
+					}
+				} else {
+#pragma unroll
+					for (int i = 0; i < kGsB / kGsColLanes; i++) {
+						const int cc = cl + kGsColLanes * i;
+						double4 pc = w_col[cc];
+						const double4 dm = w_dm[cc];
+						const int mc = __double2loint(pc.w);
+						pc.w = dm.w;
+						gs_contract<ORTHO, EXPD>(c, p, pr[w], mr[w], pc, mc, dm, ax, ay, az);
+					}
 				}
 				sx[w] += ax; sy[w] += ay; sz[w] += az;
 			}
@@ -347,6 +421,7 @@ __device__ __forceinline__ void gs_updater_body(double *s_raw, int cta, int U, c
 				__threadfence();
 				__syncwarp();
 				if (lane == 0) st_flag(applied + chs[w], gbase + blk + 1);
+				if (prof && lane == 0) prof[nblk * 16 + chs[w]] = gtime();      // when this chunk's rows were handed to the cluster
 			}
 		}
 		if (pw) prof[(nblk + blk) * 8 + 2] = clock64();
@@ -361,7 +436,7 @@ __device__ __forceinline__ void gs_updater_body(double *s_raw, int cta, int U, c
 				double ax = 0, ay = 0, az = 0;
 				if (on) {
 #pragma unroll 4
-					for (int cc = cl; cc < cnt; cc += kGsColLanes) {
+					for (int cc = cl; cc < kGsB; cc += kGsColLanes) {
 						double4 pc = w_col[cc];
 						const double4 dm = w_dm[cc];
 						const int mc = __double2loint(pc.w);
@@ -381,15 +456,14 @@ __device__ __forceinline__ void gs_updater_body(double *s_raw, int cta, int U, c
 				if (lane == 0) st_flag(applied + ch, gbase + blk + 1);
 			}
 		}
-		if (pw) prof[(nblk + blk) * 8 + 3] = clock64();
 	}
 	// what was pushed since the solver wrote the rows back
 #pragma unroll
 	for (int w = 0; w < kGsOwn; w++) if (chs[w] >= 0) flush(w);
 }
 
-// what the cluster shares: the solver's shared-memory words the helpers read (progress, dmu) and write (partial pushes, done)
-struct GsShared { int prog; int loaded; int folded; int pad; int done[8]; unsigned long long mbar; };
+// columns of a 64-site panel a helper pushes: 2 hj + cs + 14 m  (cs = 0, 1 the thread's column slice)
+__host__ __device__ constexpr int gs_helper_cols(int hj) { int n = 0; for (int k = 0; k < kGsB; k++) n += (k % (2 * kGsHelpers)) / 2 == hj; return n; }
 
 template <bool ORTHO, bool EXPD>
 __global__ void __cluster_dims__(kGsCluster, 1, 1) __launch_bounds__(kGsPipeThreads, 1)
@@ -406,21 +480,26 @@ k_gs_pipeline(const double4 *__restrict__ gpq, const int *__restrict__ gmeta, co
 	const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 	const int cta = blockIdx.x;
 	const int nblk = (np + kGsB - 1) / kGsB, nchunks = (np + kGsRows - 1) / kGsRows;
-	// the solver's layout (helpers address the shared part of it through the cluster)
-	double *s_mat = s_raw;                                         // [kGsTiles][32 columns][32 rows]: the block's inverse (k_gs_inverse)
-	double *s_site0 = s_mat + kGsMat;                              // [2][kGsSiteCols][kGsB], buffer = block & 1
-	double *s_pend = s_site0 + 2 * kGsSiteCols * kGsB;             // [kGsSlots][kGsB][3] pushes already made into the rows of blocks b .. b+kGsAhead (slot = block % kGsSlots)
-	double4 *s_dm = (double4 *)(s_pend + kGsSlots * 3 * kGsB);     // [kGsB] dmu of the block being walked
-	double *s_rho = (double *)(s_dm + kGsB);                       // [kGsN] right-hand side of the block being walked
-	double *s_tpart = s_rho + kGsN;                                // [kGsTiles][32] per-tile partial dot products
-	int *s_idx = (int *)(s_tpart + kGsTiles * kGsTileDim);         // [2][kGsB] site ids of this block / the next block
-	GsShared *s_sh = (GsShared *)(s_idx + 2 * kGsB);
-
+	// How the cluster talks (the first version had the helpers poll the solver's progress word, copy the whole panel out of its shared
+	// memory and leave their sums for the solver to pull: 57 KB per block through the solver's cluster port, which moves ~17 bytes
+	// per cycle — 3.3 k of the 8.6 k cycles a block took):
+	//   solver -> helper : each dipole change goes to the ONE helper that owns its column, as an 8-byte store that signals the helper's
+	//                      barrier (1.5 KB per block);
+	//   helper -> solver : a helper keeps what it has pushed into the next four blocks in its own shared memory and delivers only the
+	//                      sums of the block that is solved next, the same way (7 x 1.5 KB per block).
+	// Readers sleep on their own barrier; nothing is polled or pulled across the cluster.
 	if (cta == 0) {
 		// ------------------------------------------------ solver ------------------------------------------------
-		volatile int *s_prog = &s_sh->prog;                        // blk * kGsB + columns of the walk that are final
-		volatile int *s_done = s_sh->done;                         // per helper: panels delivered
-		constexpr int kPublisherWarp = 12, kLoaderWarp = 13;       // warps 0..11 walk; 14, 15 only copy
+		double *s_mat = s_raw;                                         // [kGsTiles][32 columns][32 rows]: the block's inverse (k_gs_inverse)
+		double *s_site0 = s_mat + kGsMat;                              // [2][kGsSiteCols][kGsB], buffer = block & 1
+		double *s_in = s_raw + kGsSolIn;                               // [kGsHelpers][kGsN] what the helpers pushed into the rows of the block about to be solved
+		unsigned long long *s_bars = (unsigned long long *)(s_raw + kGsSolBar);
+		double4 *s_dm = (double4 *)(s_raw + kGsSolBar + 2);            // [kGsB] dmu of the block being walked
+		double *s_rho = (double *)(s_dm + kGsB);                       // [kGsN] right-hand side of the block being walked
+		double *s_tpart = s_rho + kGsN;                                // [kGsTiles][32] per-tile partial dot products
+		int *s_idx = (int *)(s_tpart + kGsTiles * kGsTileDim);         // [2][kGsB] site ids of this block / the next block
+		volatile int *s_clk = s_idx;                                   // any shared word: anchors the profiling clock reads behind the barriers
+		constexpr int kPublisherWarp = 12, kLoaderWarp = 13;
 		auto load_cols = [&](int blk, int m) {                     // site id and site columns of row m (all but the running contraction)
 			const int pos = blk * kGsB + m;
 			const bool on = pos < np;
@@ -439,12 +518,7 @@ k_gs_pipeline(const double4 *__restrict__ gpq, const int *__restrict__ gmeta, co
 			double *s_site = s_site0 + (blk & 1) * kGsSiteCols * kGsB;
 			for (int q = 0; q < 3; q++) s_site[(7 + q) * kGsB + m] = on ? __ldcg(acc + 3 * s + q) : 0.0;
 		};
-		// the helpers keep their sums in their own shared memory (same offset in every helper CTA); the solver pulls them
-		const double *h_out_of[kGsHelpers];
-#pragma unroll
-		for (int h = 0; h < kGsHelpers; h++) h_out_of[h] = cluster.map_shared_rank(s_raw + kGsHelperOutOffset, h + 1);
-		for (int q = tid; q < kGsSlots * 3 * kGsB; q += kGsPipeThreads) s_pend[q] = 0.0;
-		const unsigned bar = smem_u32(&s_sh->mbar);
+		const unsigned bar_in = smem_u32(&s_bars[0]), bar = smem_u32(&s_bars[1]);
 		constexpr unsigned kMatBytes = sizeof(double) * kGsMat, kMatPiece = kMatBytes / 3;
 		static_assert(kMatPiece % 16 == 0, "bulk copies move multiples of 16 bytes");
 		auto fetch_inverse = [&](int blk) {                        // one thread: the whole inverse of block blk -> s_mat, completion on the barrier
@@ -452,40 +526,37 @@ k_gs_pipeline(const double4 *__restrict__ gpq, const int *__restrict__ gmeta, co
 			const char *src = (const char *)(tri + (size_t)blk * kGsMat);
 			for (int q = 0; q < 3; q++) bulk_g2s(smem_u32(s_mat) + q * kMatPiece, src + q * kMatPiece, kMatPiece, bar);
 		};
+		// my component's place in its helper's panel buffer: column site wm belongs to helper (wm % 14) / 2
+		const int wm = tid / 3, wq = tid - 3 * wm;                     // my site of the block and component (threads 0..191)
+		unsigned r_dm = 0, r_bar = 0;
+		if (tid < kGsN) {
+			const unsigned owner = 1 + (wm % (2 * kGsHelpers)) / 2;
+			r_dm = map_to_cta(smem_u32(s_raw + kGsHelpDm + 4 * wm + wq), owner);
+			r_bar = map_to_cta(smem_u32(s_raw + kGsHelpBar), owner);
+		}
 		if (tid == 0) {
-			mbar_init(bar, 1);
+			mbar_init(bar_in, 1); mbar_init(bar, 1);
 			asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-			*s_prog = 0; for (int h = 0; h < 8; h++) s_done[h] = 0;
 		}
 		if (tid < kGsB) { load_cols(0, tid); load_acc(0, tid); }
-		cluster.sync();                                            // the helpers may look at prog / done from here on
+		cluster.sync();                                            // every barrier of the cluster is initialised
 		if (tid == 0) fetch_inverse(0);
 		for (int blk = 0; blk < nblk; blk++) {
 			const int base = blk * kGsB, cnt = min(kGsB, np - base);
 			double *s_site = s_site0 + (blk & 1) * kGsSiteCols * kGsB;
-			if (prof && tid == 0) prof[blk * 8 + 0] = clock_after(s_prog);
-			// (A) fold the helpers' pushes of the previous panel into the pending sums (fixed order), then the running contraction
-			//     of this block's rows = what the updaters left (fetched during the previous walk) + the cluster's own pushes
-			if (blk > 0) {
-				if (tid < kGsHelpers) while (s_done[tid] < blk) { }         // every helper has delivered panel blk-1
-				__syncthreads();
-				if (prof && tid == 0) prof[blk * 8 + 4] = clock_after(s_prog);
-				// the part of panel blk-1 that went into THIS block's rows (the rest is taken after the walk, off the critical path)
-				if (tid < kGsN) {
-					const int par = ((blk - 1) & 1) * (kGsAhead * kGsB * 3);
-					double pv[kGsHelpers];                              // all remote loads in flight at once
-#pragma unroll
-					for (int h = 0; h < kGsHelpers; h++) pv[h] = h_out_of[h][par + tid];
-					double v = pv[0];
-#pragma unroll
-					for (int h = 1; h < kGsHelpers; h++) v += pv[h];
-					s_pend[(blk % kGsSlots) * kGsB * 3 + tid] += v;
+			if (prof && tid == 0) prof[blk * 8 + 0] = clock_after(s_clk);
+			// (A) what the cluster pushed into this block's rows (panels blk-kGsAhead .. blk-1), delivered by the helpers after panel blk-1
+			// (the publisher warp comes straight from its memory fence — several hundred cycles after the others — and owns no row:
+			// it joins at the barrier before the matrix-vector product, not here)
+			if (warp != kPublisherWarp) {
+				if (blk > 0 && warp != kLoaderWarp) {
+					if (tid == 0) mbar_expect_tx(bar_in, (unsigned)(sizeof(double) * kGsHelpers * kGsN));
+					mbar_wait(bar_in, (blk - 1) & 1);
+					if (prof && tid == 0) prof[blk * 8 + 3] = gtime();
 				}
+				asm volatile("bar.sync 2, %0;" :: "n"(kGsPipeThreads - 32) : "memory");   // the loader warp's columns of this block are in place
 			}
-			__syncthreads();
-			if (tid < kGsB) for (int q = 0; q < 3; q++) s_site[(7 + q) * kGsB + tid] += s_pend[((blk % kGsSlots) * kGsB + tid) * 3 + q];
-			__syncthreads();
-			if (prof && tid == 0) prof[blk * 8 + 1] = clock_after(s_prog);
+			if (prof && tid == 0) { prof[blk * 8 + 4] = clock_after(s_clk); prof[blk * 8 + 7] = gtime(); }
 			if (warp == kLoaderWarp) {
 				// the NEXT block's site columns and running contraction, fetched while this block is walked (nothing of it depends
 				// on this walk: the rows' dipoles are still the old ones, and no updater touches these rows between panel
@@ -495,6 +566,8 @@ k_gs_pipeline(const double4 *__restrict__ gpq, const int *__restrict__ gmeta, co
 					// every lane acquires the flags of the two chunks its rows (lane, lane + 32) belong to: no fence — a MEMBAR in this
 					// warp stalls the shared-memory traffic of the walk next to it
 					const int c0 = (base + kGsB) / kGsRows;
+					const long long tw0 = prof ? clock64() : 0;
+					long long twait = 0; int late = -1;
 					if (blk >= kGsAhead) {
 #pragma unroll
 						for (int h = 0; h < 2; h++) {
@@ -505,7 +578,14 @@ k_gs_pipeline(const double4 *__restrict__ gpq, const int *__restrict__ gmeta, co
 								__nanosleep(100);
 								if (++spins > kGsWaitLimit) st_flag(&ctl->abort, 1);
 							}
+							if (prof && spins) { twait = clock64() - tw0; late = ch; }
 						}
+					}
+					if (prof) {                                        // how long this block's rows kept the loader waiting, and for which chunk
+						long long key = (twait << 16) | (late & 0xffff);
+#pragma unroll
+						for (int o = 16; o > 0; o >>= 1) { const long long k2 = __shfl_xor_sync(0xffffffffu, key, o); key = k2 > key ? k2 : key; }
+						if (lane == 0) prof[blk * 8 + 5] = key;
 					}
 					__syncwarp();
 					load_acc(blk + 1, lane); load_acc(blk + 1, lane + 32);
@@ -515,18 +595,23 @@ k_gs_pipeline(const double4 *__restrict__ gpq, const int *__restrict__ gmeta, co
 			// (B) the walk: rhs = alpha E_s - mu_old - alpha acc, dmu = rhs + X rhs (k_gs_inverse): a 192 x 192 triangular matrix-vector
 			// product cut in 21 tiles of 32 x 32, one or two tiles per warp, lane = row; every load has a compile-time offset (the
 			// first version walked the packed triangle with ~100 instructions of address arithmetic per 12 FMAs: 3 000 cycles)
-			double rhs_r = 0.0, al_r = 0.0, mo_r = 0.0, es_r = 0.0, a_r = 0.0;
-			const int wm = tid / 3, wq = tid - 3 * wm;                     // my site of the block and component (threads 0..191)
+			double rhs_r = 0.0, mo_r = 0.0, a_r = 0.0;
 			if (tid < kGsN) {
-				al_r = s_site[wm]; mo_r = s_site[(1 + wq) * kGsB + wm]; es_r = s_site[(4 + wq) * kGsB + wm]; a_r = s_site[(7 + wq) * kGsB + wm];
+				const double al_r = s_site[wm], es_r = s_site[(4 + wq) * kGsB + wm];
+				mo_r = s_site[(1 + wq) * kGsB + wm]; a_r = s_site[(7 + wq) * kGsB + wm];
+				if (blk > 0) {                                             // the helpers' sums in a fixed order
+					double v = s_in[tid];
+#pragma unroll
+					for (int h = 1; h < kGsHelpers; h++) v += s_in[h * kGsN + tid];
+					a_r += v;
+				}
 				rhs_r = fma(-al_r, a_r, fma(al_r, es_r, -mo_r));
 				s_rho[tid] = rhs_r;
 			}
 			mbar_wait(bar, blk & 1);                                       // the inverse has landed (every reader observes the phase itself)
 			asm volatile("bar.sync 1, %0;" :: "n"(kGsPipeThreads - 32) : "memory");
-			if (prof && tid == 0) prof[blk * 8 + 5] = clock_after(s_prog);
+			if (prof && tid == 0) prof[blk * 8 + 1] = clock_after(s_clk);
 			{
-				if (prof && tid == 191) prof[blk * 8 + 3] = clock64();
 				const int wslot = warp < kLoaderWarp ? warp : warp - 1;    // 15 warps take part (the loader does not)
 				for (int t = wslot; t < kGsTiles; t += kGsPipeThreads / 32 - 1) {
 					int I = 0;
@@ -548,13 +633,14 @@ k_gs_pipeline(const double4 *__restrict__ gpq, const int *__restrict__ gmeta, co
 				if (prof && tid == 191) prof[blk * 8 + 6] = clock64();
 			}
 			asm volatile("bar.sync 1, %0;" :: "n"(kGsPipeThreads - 32) : "memory");
-			if (prof && tid == 0) prof[blk * 8 + 7] = clock_after(s_prog);
 			if (tid == (kLoaderWarp + 1) * 32 && blk + 1 < nblk) fetch_inverse(blk + 1);   // s_mat is free: every warp is past the product
 			if (tid < kGsN) {
 				double d = rhs_r;                                              // + (X rhs)_row: the row block's tiles in a fixed order
 				const int I = tid / kGsTileDim;
 				for (int J = 0; J <= I; J++) d += s_tpart[gs_tile(I, J) * kGsTileDim + (tid & (kGsTileDim - 1))];
-				reinterpret_cast<volatile double *>(s_dm)[4 * wm + wq] = d;
+				// the panel, component by component, to the helper that pushes this column (it may be waiting for it already)
+				if (blk + 1 < nblk) st_async_f64(r_dm, d, r_bar);
+				reinterpret_cast<double *>(s_dm)[4 * wm + wq] = d;
 				// contract_dipoles: mu = alpha (E_s + ef_induced), ef_induced = -acc at the moment of the update  (:3583-3592):
 				// mu = mu_old + dmu; ef_induced is recovered from mu after the sweep (k_gs_efi)
 				if (wm < cnt) {
@@ -566,24 +652,7 @@ k_gs_pipeline(const double4 *__restrict__ gpq, const int *__restrict__ gmeta, co
 				}
 			}
 			asm volatile("bar.sync 1, %0;" :: "n"(kGsPipeThreads - 32) : "memory");
-			if (tid == 0) *s_prog = base + cnt;                            // the helpers may take the panel
-			if (prof && tid == 0) prof[blk * 8 + 2] = clock_after(s_prog);
-			if (blk > 0 && tid < kGsN) {
-				// what panel blk-1 pushed into the rows of blocks blk+1 .. blk+3, while the helpers work on panel blk (they write the
-				// other half of their delivery buffer)
-				const int par = ((blk - 1) & 1) * (kGsAhead * kGsB * 3);
-#pragma unroll
-				for (int j = 1; j < kGsAhead; j++) {
-					double pv[kGsHelpers];
-#pragma unroll
-					for (int h = 0; h < kGsHelpers; h++) pv[h] = h_out_of[h][par + j * kGsB * 3 + tid];
-					double v = pv[0];
-#pragma unroll
-					for (int h = 1; h < kGsHelpers; h++) v += pv[h];
-					double *dst = s_pend + ((blk + j) % kGsSlots) * kGsB * 3 + tid;
-					*dst = (j < kGsAhead - 1 ? *dst : 0.0) + v;         // the farthest target starts here; the nearer ones already hold earlier panels
-				}
-			}
+			if (prof && tid == 0) { prof[blk * 8 + 2] = clock_after(s_clk); prof[(nblk + blk) * 8 + 6] = gtime(); }
 			if (warp == kPublisherWarp) {
 				// publish the panel for the updaters: the change of every dipole of the block, then the flag (after the write-back
 				// of the block's rows above: the updaters add this panel to those rows too)
@@ -599,24 +668,28 @@ k_gs_pipeline(const double4 *__restrict__ gpq, const int *__restrict__ gmeta, co
 			}
 		}
 		__syncthreads();
-		cluster.sync();                                            // the helpers are done with my shared memory
+		cluster.sync();                                            // nothing of the cluster is in flight towards my shared memory any more
 	} else if (cta < kGsCluster) {
 		// ------------------------------------------------ helpers -----------------------------------------------
 		// a panel = 64 columns x the 64 rows of each of the next kGsAhead blocks.  Thread = (row r, target block j, column slice cs);
 		// helper hj's two slices are 2 hj and 2 hj + 1 of 2 kGsHelpers: at most 5 columns per thread, whose tensors (k_gs_near)
-		// are fetched into registers BEFORE the panel is ready — when the walk publishes it, 45 FMAs per thread remain
+		// are fetched into registers BEFORE the panel is ready — when it arrives, 45 FMAs per thread remain.
 		const int hj = cta - 1;
-		double4 *h_dm = (double4 *)s_raw;                          // [kGsB] the panel's dipole changes
-		double *h_out = s_raw + kGsHelperOutOffset;                // [kGsAhead * kGsB][3] what this helper delivers: the solver reads it from here
-		double *h_part = h_out + 2 * kGsAhead * kGsB * 3;          // [2 column slices][kGsAhead * kGsB][3]   (h_out: two buffers, panel & 1)
-		const volatile int *r_prog = &cluster.map_shared_rank(s_sh, 0)->prog;
-		int *r_done = cluster.map_shared_rank(s_sh, 0)->done + hj;
-		const double4 *r_dm = cluster.map_shared_rank(s_dm, 0);
+		double4 *h_dm = (double4 *)(s_raw + kGsHelpDm);            // [kGsB] the panel's dipole changes (my columns only are written)
+		double *h_acc = s_raw + kGsHelpAcc;                        // [kGsAhead][kGsN] pushed so far into the rows of the blocks ahead (slot = block % kGsAhead)
+		double *h_part = s_raw + kGsHelpPart;                      // [2 column slices][kGsAhead * kGsB][3]
+		const unsigned bar_p = smem_u32(s_raw + kGsHelpBar);
+		const unsigned r_in = map_to_cta(smem_u32(s_raw + kGsSolIn + hj * kGsN), 0), r_bar_in = map_to_cta(smem_u32(s_raw + kGsSolBar), 0);
+		const unsigned panel_bytes = (unsigned)(sizeof(double) * 3 * gs_helper_cols(hj));
+		for (int q = tid; q < kGsAhead * kGsN; q += kGsPipeThreads) h_acc[q] = 0.0;
+		if (tid < kGsB) h_dm[tid] = make_double4(0.0, 0.0, 0.0, 0.0);
+		if (tid == 0) { mbar_init(bar_p, 1); asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+		__syncthreads();
 		cluster.sync();
 		const int r = tid & (kGsB - 1), j = (tid >> 6) & (kGsAhead - 1), cs = tid >> 8;
 		static_assert(kGsAhead == 4 && kGsPipeThreads == 2 * kGsAhead * kGsB, "thread = (row, target block, column slice)");
 		constexpr int kCols = (kGsB + 2 * kGsHelpers - 1) / (2 * kGsHelpers);   // 5
-		for (int blk = 0; blk < nblk; blk++) {
+		for (int blk = 0; blk + 1 < nblk; blk++) {                 // (the last panel has no rows ahead of it)
 			const int base = blk * kGsB, cnt = min(kGsB, np - base);
 			const int tb = blk + 1 + j;
 			const bool on = tb < nblk && tb * kGsB + r < np;
@@ -630,14 +703,10 @@ k_gs_pipeline(const double4 *__restrict__ gpq, const int *__restrict__ gmeta, co
 					t[m][0] = __ldg(src); t[m][1] = __ldg(src + 1); t[m][2] = __ldg(src + 2);
 				}
 			}
-			// one thread watches the solver's progress word (the walk publishes the whole panel at once)
-			if (tid == 0) while (*r_prog < base + cnt) __nanosleep(64);
+			if (tid == 0) mbar_expect_tx(bar_p, panel_bytes);
+			mbar_wait(bar_p, blk & 1);                             // my columns of the panel have arrived
 			const bool hp = prof && hj == 0 && tid == 0;
 			if (hp) prof[(nblk + blk) * 8 + 4] = gtime();
-			__syncthreads();
-			if (tid < kGsB) h_dm[tid] = r_dm[tid];
-			__syncthreads();
-			if (hp) prof[(nblk + blk) * 8 + 5] = gtime();
 			double ax = 0.0, ay = 0.0, az = 0.0;
 #pragma unroll
 			for (int m = 0; m < kCols; m++) {
@@ -651,16 +720,20 @@ k_gs_pipeline(const double4 *__restrict__ gpq, const int *__restrict__ gmeta, co
 				o[0] = ax; o[1] = ay; o[2] = az;
 			}
 			__syncthreads();
-			if (hp) prof[(nblk + blk) * 8 + 6] = gtime();
-			// the two slices summed in a fixed order; the sums stay HERE and only the flag travels: like the panel in the other
-			// direction, the reader comes to the data, which costs neither remote stores nor a cluster-wide fence (2 us per panel,
-			// measured).  h_out is rewritten only after the solver has published the next panel, i.e. after it has folded this one.
+			if (hp) prof[(nblk + blk) * 8 + 5] = gtime();
+			// the two slices in a fixed order, added to what earlier panels pushed into the same rows; the farthest target block
+			// starts its sum here.  What belongs to the block solved next goes to the solver, the rest stays here.
 			if (tid < kGsAhead * kGsB) {
-				for (int q = 0; q < 3; q++) h_out[(blk & 1) * (kGsAhead * kGsB * 3) + tid * 3 + q] = h_part[tid * 3 + q] + h_part[(kGsAhead * kGsB + tid) * 3 + q];
+				double *slot = h_acc + ((blk + 1 + j) % kGsAhead) * kGsN + 3 * r;
+#pragma unroll
+				for (int q = 0; q < 3; q++) {
+					const double v = h_part[tid * 3 + q] + h_part[(kGsAhead * kGsB + tid) * 3 + q];
+					slot[q] = (j < kGsAhead - 1 ? slot[q] : 0.0) + v;
+				}
 			}
-			__syncthreads();
-			if (tid == 0) *(volatile int *)r_done = blk + 1;
-			if (hp) prof[(nblk + blk) * 8 + 7] = gtime();
+			__syncthreads();                                       // h_part and the panel buffer are free for the next panel; the next block's slot is complete
+			if (tid == 0) bulk_s2peer(r_in, smem_u32(h_acc + ((blk + 1) % kGsAhead) * kGsN), (unsigned)(sizeof(double) * kGsN), r_bar_in);
+			if (prof && tid == 0) atomicMax((unsigned long long *)&prof[(nblk + blk) * 8 + 7], (unsigned long long)gtime());   // the LAST helper to finish
 		}
 		cluster.sync();
 	} else {
@@ -675,7 +748,7 @@ k_gs_pipeline(const double4 *__restrict__ gpq, const int *__restrict__ gmeta, co
 // dependent (cudaLaunchAttributeProgrammaticStreamSerialization): it starts when the cluster is resident and never calls
 // griddepcontrol.wait — the two kernels synchronise through their own flags.
 template <bool ORTHO, bool EXPD>
-__global__ void __launch_bounds__(kGsThreads, kGsUpdCtas)
+__global__ void __launch_bounds__(kGsUpdThreads, 1)
 k_gs_updaters(const double4 *__restrict__ gpq, const int *__restrict__ gmeta, const int *__restrict__ order, int np, CellDev c, PolarDev p,
               double *acc, const double *dmu, GsCtl *ctl, long long *prof, int gbase) {
 	extern __shared__ __align__(16) double s_raw[];
