@@ -417,10 +417,21 @@ def run_ours(args):
             flops, work = float("nan"), "n/a"
         ach = flops / (ms_per_launch * 1e-3) / 1e12
         bytes_alg = BYTES_PER_SITE_SWEEP * s.n
-        # dram__bytes_read.sum + dram__bytes_write.sum per launch from the `ncu --set full` capture of this command (profiles/r01b_ncu_summary.md)
-        ncu_traffic = {"gs_sweep": 133.2e6 + 5.3e6, "dipole_sweep": 0.61e6, "pair": 0.73e6}   # profiles/r01c_ncu_summary.md
+        # dram__bytes_read.sum + dram__bytes_write.sum per launch from the round's `ncu --set full` capture of this command (profiles/):
+        # kept in a small JSON next to the summaries so that the number in the line is the one the committed capture shows
+        ncu_traffic, traffic_src = {}, None
+        try:
+            with open(os.path.join(ROOT, "profiles", "r02_ncu_traffic.json")) as fp:
+                tj = json.load(fp)
+            ncu_traffic, traffic_src = tj.get("bytes_per_launch", {}), tj.get("source")
+        except Exception:
+            pass
         roof = {"kernel": dom, "bound": "fp64", "achieved": ach, "peak": peak_tflops, "unit": "TFLOP/s", "frac": ach / peak_tflops,
-                "traffic": ncu_traffic.get(dom), "traffic_note": "bytes per launch from the round's ncu capture (a Gauss-Seidel sweep streams its precomputed tensors once: 113 MB between each block and the 4 blocks after it + 21 MB of block inverses, 0.12 TB/s); the roofline is the FP64 pipe, not HBM", "ms_per_launch": ms_per_launch, "launches_timed": cands[dom][1], "work_per_launch": work,
+                "traffic": ncu_traffic.get(dom), "traffic_source": traffic_src,
+                "traffic_note": "a Gauss-Seidel sweep streams what was precomputed for its order once: the tensors between each 64-site block and the 4 blocks after it (113 MB) and the block inverses (25 MB); the roofline is the FP64 pipe, not HBM",
+                "ms_per_launch": ms_per_launch, "launches_timed": cands[dom][1],
+                "launch": "one Gauss-Seidel sweep = k_gs_pipeline (8-CTA cluster) + k_gs_updaters (140 CTAs) side by side" if dom == "gs_sweep" else dom,
+                "work_per_launch": work,
                 "peak_source": "measured in this run: register-resident DFMA loop on all SMs (MEASURED_PEAKS.json has no FP64 entry)",
                 "share_of_step": cands[dom][0] / max(timing["energy_total"][0], 1e-9),
                 "hbm_view": {"algorithmic_bytes": bytes_alg, "achieved_gbs": bytes_alg / (ms_per_launch * 1e-3) / 1e9,

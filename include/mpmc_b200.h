@@ -170,14 +170,15 @@ int mpmc_pi_collective(mpmc_engine *e);
  * (accumulated from mpmc_set_timing(e,1) on; read after an energy fetch). */
 enum {
 	MPMC_K_ENERGY_TOTAL = 0,  /* everything one energy() enqueues */
-	MPMC_K_PAIR,              /* k_pair_energy: lj() + coulombic_real() */
-	MPMC_K_STRUCTURE,         /* k_structure_partial: S(k) */
+	MPMC_K_PAIR,              /* k_pair_gather + k_pair_sweep: lj() + coulombic_real() */
+	MPMC_K_STRUCTURE,         /* k_structure_partial: S(k) chunk partials */
 	MPMC_K_FIELD_RECIP,       /* k_field_recip: recip_term() */
-	MPMC_K_FIELD_REAL,        /* k_field_real: real_term() */
-	MPMC_K_RANK,              /* rank metric kernels */
-	MPMC_K_DIPOLE_SWEEP,      /* k_dipole_sweep (Jacobi contract_dipoles) */
-	MPMC_K_GS_SWEEP,          /* k_gs_sweep (Gauss-Seidel contract_dipoles) */
-	MPMC_K_PALMO,             /* k_dipole_sweep<PALMO> */
+	MPMC_K_FIELD_REAL,        /* k_field_parts + k_field_finish: real_term() / thole_field_nopbc() */
+	MPMC_K_RANK,              /* k_rank_min_parts, k_rank_lim, k_rank_count_parts: the Gauss-Seidel rank metric */
+	MPMC_K_DIPOLE_SWEEP,      /* k_contract_parts + k_contract_finish: Jacobi contract_dipoles(), and the Gauss-Seidel pipeline's initial contraction */
+	MPMC_K_GS_SWEEP,          /* ONE Gauss-Seidel sweep: k_gs_pipeline (solver + helpers) with k_gs_updaters beside it; count = sweeps */
+	MPMC_K_PALMO,             /* palmo_contraction(): k_contract_parts over the needed rows / k_gs_palmo */
+	MPMC_K_GS_PRECOMPUTE,     /* per sweep order: k_gs_gather, k_gs_inverse, k_gs_near (on the second stream unless timing is on) */
 	MPMC_NUM_KERNEL_CLASSES
 };
 int mpmc_set_timing(mpmc_engine *e, int on);

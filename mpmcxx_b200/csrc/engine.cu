@@ -175,7 +175,12 @@ struct mpmc_engine {
 	bool rank_ff_dirty = true;
 	// Gauss-Seidel pipeline: the updater kernel runs beside the solver cluster on a second stream
 	cudaStream_t stream2 = nullptr;
-	cudaEvent_t ev_fork = nullptr, ev_sk = nullptr;
+	cudaEvent_t ev_fork = nullptr, ev_sk = nullptr, ev_pol = nullptr, ev_pre[2] = {nullptr, nullptr};
+	// the Gauss-Seidel precomputation of the second sweep order (rank order) has its own buffers, so that it can be built on the second
+	// stream while the first sweep runs on the first order's
+	DevBuf<double4> d_gpq2;
+	DevBuf<int> d_gmeta2;
+	DevBuf<double> d_tri2, d_near2;
 	int gs_gen = 0, gs_upd_grid = 0, gs_fused_grid = 0;   // gs_gen: generation of the pipeline's flag words (kernels_gs.cuh)
 	size_t gs_ctl_len = 0;
 	int *h_gs_abort = nullptr;      // pinned copy of GsCtl::abort after the last sweep of an energy()
@@ -809,6 +814,12 @@ static int run_polar(mpmc_engine *e) {
 	    (rc = e->d_order.ensure(1))) return rc;
 	const dim3 ogrid((n + kOrdI - 1) / kOrdI, B);
 	const int nk = (int)e->kvec.size(), kmax = cf.ewald_kmax;
+	// the second stream starts here, beside the static field (see the ranking block below)
+	const bool side = (cf.polar_gs || cf.polar_gs_ranked) && B == 1 && !e->timing && e->stream2 && np > 0 && !cf.polar_zodid;
+	if (side) {
+		CK(cudaEventRecord(e->ev_pol, e->stream));
+		CK(cudaStreamWaitEvent(e->stream2, e->ev_pol, 0));
+	}
 	// thole_field(): static field (System.Energy.cpp:3271-3296)
 	if (cf.polar_ewald) {
 		// S_all = S_frozen + S_mobile: the mobile chunk partials computed for coulombic_reciprocal() are still in d_sk_part
@@ -829,6 +840,7 @@ static int run_polar(mpmc_engine *e) {
 	PolarDev pd;
 	pd.damp = cf.polar_damp; pd.gamma = cf.polar_gamma; pd.damp_type = cf.damp_type;
 	pd.gs = cf.polar_gs || cf.polar_gs_ranked; pd.sor = cf.polar_sor; pd.esor = cf.polar_esor;
+
 	pd.allowed_sqerr = cf.polar_precision * cf.polar_precision * kDebye2Ska * kDebye2Ska;
 	pd.u_damp = cf.polar_damp > 0 ? (50.0 / cf.polar_damp) * (50.0 / cf.polar_damp) : 0.0;
 	const double gamma_init = (!cf.polar_sor && !cf.polar_esor) ? cf.polar_gamma : 1.0;
@@ -838,6 +850,11 @@ static int run_polar(mpmc_engine *e) {
 	LAUNCHED(e);
 	// GS ranking (System.cpp:1000-1029) — the metric only depends on the geometry, so both sweep orders are known up front
 	const bool ranked = cf.polar_gs_ranked && !cf.polar_zodid;
+	// Everything the Gauss-Seidel sweeps need that depends on the geometry only — the rank metric, the two sweep orders, per order the
+	// block inverses and the near tensors — is built on the SECOND stream, beside the static field, the dipole initialisation, the
+	// initial contraction and (for the second order) the first sweep: k_gs_inverse runs 144 CTAs at 11 % of the FP64 pipe and the rank
+	// kernels are short launches, so they fill what the main stream's kernels leave idle instead of standing in its way.
+	cudaStream_t rstream = side ? e->stream2 : e->stream;
 	if (ranked && np > 0) {
 		Timed _t(e, MPMC_K_RANK);
 		auto split = [&](int nrows, int ncols, int &parts, int &plen) {
@@ -852,45 +869,45 @@ static int run_polar(mpmc_engine *e) {
 		const unsigned long long inf_bits = 0x7ff0000000000000ull;
 		if (e->rank_ff_dirty) {
 			// the frozen-frozen part depends only on the frozen coordinates: once per topology / cell / framework move
-			k_fill_u64<<<1, 32, 0, e->stream>>>(e->d_r2min_ff.p, B, inf_bits);
-			k_fill_u64<<<1, 32, 0, e->stream>>>((unsigned long long *)e->d_t2_cached.p, B, 0xbff0000000000000ull);   // -1: no cached counts
-			CK(cudaMemsetAsync(e->d_cnt_ff.p, 0, sizeof(double) * (size_t)B * n, e->stream));
+			k_fill_u64<<<1, 32, 0, rstream>>>(e->d_r2min_ff.p, B, inf_bits);
+			k_fill_u64<<<1, 32, 0, rstream>>>((unsigned long long *)e->d_t2_cached.p, B, 0xbff0000000000000ull);   // -1: no cached counts
+			CK(cudaMemsetAsync(e->d_cnt_ff.p, 0, sizeof(double) * (size_t)B * n, rstream));
 			e->launches += 2;
 			if (nfp > 1) {
 				split(nfp, nfp, parts, plen);
-				k_rank_min_parts<ORTHO><<<dim3((nfp + kOrdI - 1) / kOrdI, parts, B), kOrdThreads, 0, e->stream>>>(e->d_posq.p, e->d_fp_list.p, nfp, plen, e->d_fp_list.p, nfp,
+				k_rank_min_parts<ORTHO><<<dim3((nfp + kOrdI - 1) / kOrdI, parts, B), kOrdThreads, 0, rstream>>>(e->d_posq.p, e->d_fp_list.p, nfp, plen, e->d_fp_list.p, nfp,
 				                                                                                                e->cap, e->cell, e->d_r2min_ff.p);
 				LAUNCHED(e);
 			}
 			e->rank_ff_dirty = false;
 		}
-		k_fill_u64<<<1, 32, 0, e->stream>>>(e->d_rmin.p, B, inf_bits);
+		k_fill_u64<<<1, 32, 0, rstream>>>(e->d_rmin.p, B, inf_bits);
 		LAUNCHED(e);
 		if (nmp > 0) {   // every pair with a mobile member (the frozen x mobile pairs by symmetry)
 			split(nmp, np, parts, plen);
-			k_rank_min_parts<ORTHO><<<dim3((nmp + kOrdI - 1) / kOrdI, parts, B), kOrdThreads, 0, e->stream>>>(e->d_posq.p, e->d_plist.p, np, plen, e->d_mp_list.p, nmp,
+			k_rank_min_parts<ORTHO><<<dim3((nmp + kOrdI - 1) / kOrdI, parts, B), kOrdThreads, 0, rstream>>>(e->d_posq.p, e->d_plist.p, np, plen, e->d_mp_list.p, nmp,
 			                                                                                                e->cap, e->cell, e->d_rmin.p);
 			LAUNCHED(e);
 		}
-		k_rank_lim<<<(B + 31) / 32, 32, 0, e->stream>>>(e->d_rmin.p, e->d_r2min_ff.p, B, e->d_t2.p, e->d_t2_cached.p, e->d_recount.p);
-		k_rank_clear_gated<<<(unsigned)(((size_t)B * n + 255) / 256), 256, 0, e->stream>>>(e->d_recount.p, n, B, e->d_cnt_ff.p);
+		k_rank_lim<<<(B + 31) / 32, 32, 0, rstream>>>(e->d_rmin.p, e->d_r2min_ff.p, B, e->d_t2.p, e->d_t2_cached.p, e->d_recount.p);
+		k_rank_clear_gated<<<(unsigned)(((size_t)B * n + 255) / 256), 256, 0, rstream>>>(e->d_recount.p, n, B, e->d_cnt_ff.p);
 		e->launches += 2;
 		if (nfp > 1) {   // skipped on the device unless 1.5 rmin changed
 			split(nfp, nfp, parts, plen);
-			k_rank_count_parts<<<dim3((nfp + kOrdI - 1) / kOrdI, parts, B), kOrdThreads, 0, e->stream>>>(e->d_posq.p, e->d_fp_list.p, nfp, plen, e->d_fp_list.p, nfp, n, e->cap,
+			k_rank_count_parts<<<dim3((nfp + kOrdI - 1) / kOrdI, parts, B), kOrdThreads, 0, rstream>>>(e->d_posq.p, e->d_fp_list.p, nfp, plen, e->d_fp_list.p, nfp, n, e->cap,
 			                                                                                           e->d_t2.p, e->d_recount.p, e->d_cnt_ff.p);
 			LAUNCHED(e);
 		}
-		k_rank_init<<<(unsigned)(((size_t)B * n + 255) / 256), 256, 0, e->stream>>>(e->d_cnt_ff.p, n, B, e->d_rank.p);
+		k_rank_init<<<(unsigned)(((size_t)B * n + 255) / 256), 256, 0, rstream>>>(e->d_cnt_ff.p, n, B, e->d_rank.p);
 		LAUNCHED(e);
 		if (nmp > 0) {
 			split(nmp, np, parts, plen);
-			k_rank_count_parts<<<dim3((nmp + kOrdI - 1) / kOrdI, parts, B), kOrdThreads, 0, e->stream>>>(e->d_posq.p, e->d_plist.p, np, plen, e->d_mp_list.p, nmp, n, e->cap,
+			k_rank_count_parts<<<dim3((nmp + kOrdI - 1) / kOrdI, parts, B), kOrdThreads, 0, rstream>>>(e->d_posq.p, e->d_plist.p, np, plen, e->d_mp_list.p, nmp, n, e->cap,
 			                                                                                           e->d_t2.p, nullptr, e->d_rank.p);
 			LAUNCHED(e);
 			if (nfp > 0) {
 				split(nfp, nmp, parts, plen);
-				k_rank_count_parts<<<dim3((nfp + kOrdI - 1) / kOrdI, parts, B), kOrdThreads, 0, e->stream>>>(e->d_posq.p, e->d_mp_list.p, nmp, plen, e->d_fp_list.p, nfp, n, e->cap,
+				k_rank_count_parts<<<dim3((nfp + kOrdI - 1) / kOrdI, parts, B), kOrdThreads, 0, rstream>>>(e->d_posq.p, e->d_mp_list.p, nmp, plen, e->d_fp_list.p, nfp, n, e->cap,
 				                                                                                           e->d_t2.p, nullptr, e->d_rank.p);
 				LAUNCHED(e);
 			}
@@ -938,7 +955,10 @@ static int run_polar(mpmc_engine *e) {
 		};
 		int it = 0;
 		bool keep = true, acc_stale = false;
-		const int *gs_order = e->d_plist.p;
+		struct GsPre { DevBuf<double4> *gpq; DevBuf<int> *gmeta; DevBuf<double> *tri, *near; const int *order; };
+		GsPre pre[2] = {{&e->d_gpq, &e->d_gmeta, &e->d_tri, &e->d_near, e->d_plist.p}, {&e->d_gpq2, &e->d_gmeta2, &e->d_tri2, &e->d_near2, e->d_plist.p}};
+		if (!side) pre[1] = pre[0];                                  // one after the other on one stream: one set of buffers is enough
+		int cur = 0;
 		while (keep) {
 			it++;
 			if (it >= 128 && cf.polar_precision > 0) {   // MAX_ITERATION_COUNT (constants.h:52), System.Energy.cpp:3483-3494
@@ -957,26 +977,54 @@ static int run_polar(mpmc_engine *e) {
 				// Gauss-Seidel pipeline (kernels_gs.cuh).  First sweep in list order (ranked_array = identity, :3463); from the second
 				// sweep on in rank order when polar_gs_ranked (update_ranking after the first pass, :3522-3523).
 				const int nblk = (np + kGsB - 1) / kGsB, nchunks = (np + kGsRows - 1) / kGsRows;
-				if ((rc = e->d_dmu.ensure((size_t)np * 3)) || (rc = e->d_tri.ensure((size_t)nblk * kGsMat)) || (rc = e->d_near.ensure((size_t)nblk * kGsNearPerBlock)) ||
-				    (rc = e->d_gsctl.ensure(sizeof(GsCtl) / sizeof(int) + nchunks)) || (rc = e->d_gpq.ensure(np)) || (rc = e->d_gmeta.ensure(np))) return rc;
+				if ((rc = e->d_dmu.ensure((size_t)np * 3)) || (rc = e->d_gsctl.ensure(sizeof(GsCtl) / sizeof(int) + nchunks))) return rc;
 				if (it == 1 || acc_stale) {
 					Timed _t(e, MPMC_K_DIPOLE_SWEEP);
 					if ((rc = contract(SWEEP_ACC, e->d_plist.p, np, acc))) return rc;
 					acc_stale = false;
 				}
-				if (it == 1 || (ranked && it == 2)) {
-					gs_order = e->d_plist.p;
-					if (ranked && it == 2) {
-						k_rank_order_plist<<<(np + kOrdI - 1) / kOrdI, kOrdThreads, 0, e->stream>>>(rank, e->d_plist.p, np, e->d_order.p);
+				// what the sweeps of one order need (k_gs_gather, k_gs_inverse, k_gs_near): order 0 = list order, order 1 = rank order
+				auto precompute = [&](int k, cudaStream_t st) -> int {
+					GsPre &g = pre[k];
+					int r2;
+					if ((r2 = g.gpq->ensure(np)) || (r2 = g.gmeta->ensure(np)) || (r2 = g.tri->ensure((size_t)nblk * kGsMat)) || (r2 = g.near->ensure((size_t)nblk * kGsNearPerBlock))) return r2;
+					if (k == 1) {
+						k_rank_order_plist<<<(np + kOrdI - 1) / kOrdI, kOrdThreads, 0, st>>>(rank, e->d_plist.p, np, e->d_order.p);
 						LAUNCHED(e);
-						gs_order = e->d_order.p;
 					}
-					Timed _t(e, MPMC_K_GS_SWEEP);
-					k_gs_gather<<<(np + 255) / 256, 256, 0, e->stream>>>(posq, e->d_alpha.p, e->d_meta.p, gs_order, np, e->d_gpq.p, e->d_gmeta.p);
-					k_gs_inverse<ORTHO><<<nblk, kGsThreads, kGsInverseSmemBytes, e->stream>>>(e->d_gpq.p, e->d_gmeta.p, np, e->cell, pd, e->d_tri.p);
-					k_gs_near<ORTHO><<<nblk, kGsPipeThreads, 0, e->stream>>>(e->d_gpq.p, e->d_gmeta.p, np, e->cell, pd, e->d_near.p);
+					g.order = k == 1 ? e->d_order.p : e->d_plist.p;
+					k_gs_gather<<<(np + 255) / 256, 256, 0, st>>>(posq, e->d_alpha.p, e->d_meta.p, g.order, np, g.gpq->p, g.gmeta->p);
+					k_gs_inverse<ORTHO><<<nblk, kGsThreads, kGsInverseSmemBytes, st>>>(g.gpq->p, g.gmeta->p, np, e->cell, pd, g.tri->p);
+					k_gs_near<ORTHO><<<nblk, kGsPipeThreads, 0, st>>>(g.gpq->p, g.gmeta->p, np, e->cell, pd, g.near->p);
 					e->launches += 3;
+					CK(cudaGetLastError());
+					return MPMC_OK;
+				};
+				if (it == 1) {
+					if (side) {
+						// both orders on the second stream, in the order the sweeps will want them; the main stream waits per order
+						if ((rc = precompute(0, e->stream2))) return rc;
+						CK(cudaEventRecord(e->ev_pre[0], e->stream2));
+						if (ranked) {
+							if ((rc = precompute(1, e->stream2))) return rc;
+							CK(cudaEventRecord(e->ev_pre[1], e->stream2));
+						}
+						CK(cudaStreamWaitEvent(e->stream, e->ev_pre[0], 0));
+					} else {
+						Timed _t(e, MPMC_K_GS_PRECOMPUTE);
+						if ((rc = precompute(0, e->stream))) return rc;
+					}
+					cur = 0;
+				} else if (ranked && it == 2) {
+					if (side) CK(cudaStreamWaitEvent(e->stream, e->ev_pre[1], 0));
+					else {
+						Timed _t(e, MPMC_K_GS_PRECOMPUTE);
+						if ((rc = precompute(1, e->stream))) return rc;
+					}
+					cur = 1;
 				}
+				const GsPre &G = pre[cur];
+				const int *gs_order = G.order;
 				int ns = 1;
 				if (!need_old && !want_check && cf.polar_precision == 0.0) ns = (ranked && it == 1) ? 1 : (cf.polar_max_iter - it + 1);
 				long long *prof = nullptr;
@@ -987,8 +1035,8 @@ static int run_polar(mpmc_engine *e) {
 					e->gs_prof_nblk = nblk;
 				}
 				{
-					Timed _t(e, MPMC_K_GS_SWEEP);
 					for (int sw = 0; sw < ns; sw++) {   // one launch per sweep: the kernel boundary is the barrier between sweeps
+						Timed _t(e, MPMC_K_GS_SWEEP);
 						// flags count from generation << 16, so nothing is cleared between sweeps (kernels_gs.cuh); zero them when the generation wraps
 						if (e->gs_gen == 0 || e->gs_gen >= (1 << (30 - kGsGenShift)) || e->gs_ctl_len != sizeof(GsCtl) / sizeof(int) + (size_t)nchunks) {
 							e->gs_ctl_len = sizeof(GsCtl) / sizeof(int) + (size_t)nchunks;
@@ -998,10 +1046,10 @@ static int run_polar(mpmc_engine *e) {
 						if (nblk >= (1 << kGsGenShift) - kGsAhead - 2) FAIL(MPMC_ERR_UNSUPPORTED, "Gauss-Seidel pipeline: too many polarizable sites (%d)", np);
 						const int gbase = ++e->gs_gen << kGsGenShift;
 						const int sgrid = e->gs_fused ? e->gs_fused_grid : kGsCluster;
-						if (expd) k_gs_pipeline<ORTHO, true><<<sgrid, kGsPipeThreads, kGsSmemBytes, e->stream>>>(e->d_gpq.p, e->d_gmeta.p, gs_order, np, e->cell, pd, efs,
-						        mu, efi, new_mu, acc, e->d_dmu.p, e->d_tri.p, e->d_near.p, (GsCtl *)e->d_gsctl.p, sw == 0 ? prof : nullptr, gbase);
-						else k_gs_pipeline<ORTHO, false><<<sgrid, kGsPipeThreads, kGsSmemBytes, e->stream>>>(e->d_gpq.p, e->d_gmeta.p, gs_order, np, e->cell, pd, efs,
-						        mu, efi, new_mu, acc, e->d_dmu.p, e->d_tri.p, e->d_near.p, (GsCtl *)e->d_gsctl.p, sw == 0 ? prof : nullptr, gbase);
+						if (expd) k_gs_pipeline<ORTHO, true><<<sgrid, kGsPipeThreads, kGsSmemBytes, e->stream>>>(G.gpq->p, G.gmeta->p, gs_order, np, e->cell, pd, efs,
+						        mu, efi, new_mu, acc, e->d_dmu.p, G.tri->p, G.near->p, (GsCtl *)e->d_gsctl.p, sw == 0 ? prof : nullptr, gbase);
+						else k_gs_pipeline<ORTHO, false><<<sgrid, kGsPipeThreads, kGsSmemBytes, e->stream>>>(G.gpq->p, G.gmeta->p, gs_order, np, e->cell, pd, efs,
+						        mu, efi, new_mu, acc, e->d_dmu.p, G.tri->p, G.near->p, (GsCtl *)e->d_gsctl.p, sw == 0 ? prof : nullptr, gbase);
 						CK(cudaGetLastError());
 						LAUNCHED(e);
 						if (e->gs_fused) continue;
@@ -1014,7 +1062,7 @@ static int run_polar(mpmc_engine *e) {
 						cudaLaunchAttribute at[1];
 						at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization; at[0].val.programmaticStreamSerializationAllowed = 1;
 						lc.attrs = at; lc.numAttrs = 1;
-						const double4 *a_gpq = e->d_gpq.p; const int *a_gmeta = e->d_gmeta.p; double *a_acc = acc; const double *a_dmu = e->d_dmu.p;
+						const double4 *a_gpq = G.gpq->p; const int *a_gmeta = G.gmeta->p; double *a_acc = acc; const double *a_dmu = e->d_dmu.p;
 						GsCtl *a_ctl = (GsCtl *)e->d_gsctl.p; long long *a_prof = sw == 0 ? prof : nullptr;
 						if (expd) CK(cudaLaunchKernelEx(&lc, k_gs_updaters<ORTHO, true>, a_gpq, a_gmeta, gs_order, np, e->cell, pd, a_acc, a_dmu, a_ctl, a_prof, gbase));
 						else CK(cudaLaunchKernelEx(&lc, k_gs_updaters<ORTHO, false>, a_gpq, a_gmeta, gs_order, np, e->cell, pd, a_acc, a_dmu, a_ctl, a_prof, gbase));
@@ -1219,6 +1267,9 @@ int mpmc_create(const mpmc_config *cfg, mpmc_engine **out) {
 		CK(cudaStreamCreateWithFlags(&e->stream2, cudaStreamNonBlocking));
 		CK(cudaEventCreateWithFlags(&e->ev_fork, cudaEventDisableTiming));
 		CK(cudaEventCreateWithFlags(&e->ev_sk, cudaEventDisableTiming));
+		CK(cudaEventCreateWithFlags(&e->ev_pol, cudaEventDisableTiming));
+		CK(cudaEventCreateWithFlags(&e->ev_pre[0], cudaEventDisableTiming));
+		CK(cudaEventCreateWithFlags(&e->ev_pre[1], cudaEventDisableTiming));
 		CK(cudaMallocHost(&e->h_gs_abort, sizeof(int)));
 		*e->h_gs_abort = 0;
 		if ((rc = set_smem(k_gs_updaters<true, true>, kGsUpdaterSmemBytes)) || (rc = set_smem(k_gs_updaters<false, true>, kGsUpdaterSmemBytes)) ||
@@ -1266,6 +1317,9 @@ int mpmc_destroy(mpmc_engine *e) {
 	if (e->stream2) { cudaStreamSynchronize(e->stream2); cudaStreamDestroy(e->stream2); }
 	if (e->ev_fork) cudaEventDestroy(e->ev_fork);
 	if (e->ev_sk) cudaEventDestroy(e->ev_sk);
+	if (e->ev_pol) cudaEventDestroy(e->ev_pol);
+	for (int q = 0; q < 2; q++) if (e->ev_pre[q]) cudaEventDestroy(e->ev_pre[q]);
+	e->d_gpq2.release(); e->d_gmeta2.release(); e->d_tri2.release(); e->d_near2.release();
 	if (e->h_gs_abort) cudaFreeHost(e->h_gs_abort);
 	for (int r = 0; r < (int)e->peer_mbox.size(); r++) if (r != e->rank && e->peer_mbox[r]) cudaIpcCloseMemHandle(e->peer_mbox[r]);
 	if (e->d_mbox) cudaFree(e->d_mbox);

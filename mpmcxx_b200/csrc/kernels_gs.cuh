@@ -71,7 +71,8 @@ constexpr size_t kGsSolverDoubles = (size_t)kGsSolBar + 2 + 4 * kGsB + kGsN + kG
 static_assert(kGsSolverDoubles >= (size_t)kGsHelpBar + 1, "helpers use the same allocation");
 static_assert(kGsSolverDoubles >= (size_t)(kGsPipeThreads / 32) * 8 * kGsB, "the fused fallback runs the updaters inside the pipeline kernel");
 constexpr size_t kGsSmemBytes = sizeof(double) * kGsSolverDoubles;
-constexpr size_t kGsUpdaterDoubles = (size_t)kGsUpdWarps * 8 * kGsB;
+constexpr int kGsRing = 4;                // panels an updater CTA keeps in shared memory
+constexpr size_t kGsUpdaterDoubles = (size_t)kGsRing * 8 * kGsB;
 constexpr size_t kGsUpdaterSmemBytes = sizeof(double) * kGsUpdaterDoubles;
 
 __device__ int g_gs_debug = 0;            // developer switch (mpmc_debug_gs_profile enable bits 1..): 2 = pushers idle, 4 = no rolling copy
@@ -280,12 +281,22 @@ __device__ __forceinline__ void gs_updater_body(double *s_raw, int cta, int U, c
 	const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 	const int nblk = (np + kGsB - 1) / kGsB, nchunks = (np + kGsRows - 1) / kGsRows;
 	constexpr int kChunksPerBlk = kGsB / kGsRows;
-	double4 *w_col = (double4 *)s_raw + warp * 2 * kGsB;
-	double4 *w_dm = w_col + kGsB;
+	// A panel (64 columns: position + molecule word, dipole change + alpha) is fetched ONCE per CTA into a ring of kGsRing shared
+	// buffers and read from there by all its warps.  (With a private copy per warp, 2 400 warps read the same 4 KB from L2 at the same
+	// moment: the few L2 lines that hold a panel became a hot spot and a panel took 1.5 us to arrive.)  Whichever warp first needs a
+	// panel that is not in the ring takes a token, waits for the solver's flag (the one acquire the CTA relies on), waits until every
+	// warp has finished with the buffer's previous panel, loads, and posts it; the others meanwhile work on what is already there.
+	double4 *ring = (double4 *)s_raw;                               // [kGsRing][2][kGsB]
+	__shared__ int s_ready, s_token, s_done[kGsRing];               // panels in the ring so far; loader token; warps finished with a buffer's panel
 	// (warp-major numbering: when there are more chunks than warps, the second chunks go one to each CTA instead of eight to a
 	// few CTAs — an SM with twice the work falls behind by a few thousand cycles per panel and stalls the solver at the end)
 	const int GW = U * (int)(blockDim.x >> 5), gwid = warp * U + cta;
 	const int r = lane & (kGsRows - 1), cl = lane / kGsRows;   // row of the chunk, column lane
+	int nlive = 0;                                                  // warps of this CTA that own rows
+	for (int w = 0; w < (int)(blockDim.x >> 5); w++) nlive += w * U + cta < nchunks;
+	if (tid == 0) { s_ready = 0; s_token = 0; }
+	if (tid < kGsRing) s_done[tid] = nlive;                         // every buffer starts free
+	__syncthreads();
 	if (gwid >= nchunks) return;
 	// my rows (constant over the sweep) and their sums
 	double4 pr[kGsOwn];
@@ -317,77 +328,60 @@ __device__ __forceinline__ void gs_updater_body(double *s_raw, int cta, int U, c
 		}
 		sx[w] = sy[w] = sz[w] = 0.0;
 	};
-	// Software pipeline over the panels: while a panel is contracted, the NEXT panel's columns (their positions are known in advance)
-	// and — when the solver is already past it — its dipole changes travel from L2 into registers; a warp that keeps up with the solver
-	// only ever waits for the flag, a warp that runs behind never waits for memory.
-	double4 pf_c[2];
-	int pf_m[2];
-	double pf_d[2][3];
-	bool pf_have_d = false;
-	auto fetch_cols = [&](int blk) {
-#pragma unroll
-		for (int h = 0; h < 2; h++) {
-			const int pos = blk * kGsB + lane + 32 * h;
-			const bool on = pos < np;
-			pf_c[h] = on ? gpq[pos] : make_double4(0, 0, 0, 0);
-			pf_m[h] = on ? gmeta[pos] : 0;
-		}
-	};
-	auto fetch_dmu = [&](int blk) {
-#pragma unroll
-		for (int h = 0; h < 2; h++) {
-			const int pos = blk * kGsB + lane + 32 * h;
-			const bool on = pos < np;
-#pragma unroll
-			for (int q = 0; q < 3; q++) pf_d[h][q] = on ? __ldcg(dmu + 3 * pos + q) : 0.0;     // beyond the end: zero change, contributes nothing
-		}
-	};
-	fetch_cols(0);
+	volatile int *v_ready = &s_ready, *v_token = &s_token, *v_done = s_done;
 	for (int blk = 0; blk < nblk; blk++) {
 		// the rows of the next kGsAhead blocks belong to the cluster (the panel's own rows do not: the solver writes them back
 		// before it publishes the panel, without the panel's own contribution)
 		const int skip0 = (blk + 1) * kChunksPerBlk, skip1 = min(blk + 1 + kGsAhead, nblk) * kChunksPerBlk;
-		__syncwarp();
-#pragma unroll
-		for (int h = 0; h < 2; h++) {
-			const int cc = lane + 32 * h;
-			w_col[cc] = make_double4(pf_c[h].x, pf_c[h].y, pf_c[h].z, __longlong_as_double((long long)pf_m[h]));
-			if (!EXPD) w_dm[cc].w = pf_c[h].w;                      // alpha of the column (linear damping)
-		}
-		const bool had_d = pf_have_d;
-		if (had_d) {
-#pragma unroll
-			for (int h = 0; h < 2; h++) { double4 *d = w_dm + lane + 32 * h; d->x = pf_d[h][0]; d->y = pf_d[h][1]; d->z = pf_d[h][2]; }
-		}
-		if (blk + 1 < nblk) fetch_cols(blk + 1);
 		const bool pw = prof && cta == 0 && warp == 0 && lane == 0;
-		if (pw) prof[(nblk + blk) * 8 + 0] = clock64();
-		if (!had_d) {
+		if (pw) prof[(nblk + blk) * 8 + 0] = gtime();
+		// ---- get panel blk into the ring (warp-uniform control flow: lane 0 decides, everybody follows)
+		for (;;) {
+			const int rd = __shfl_sync(0xffffffffu, *v_ready, 0);
+			if (rd > blk) break;
+			int got = 0;
+			if (lane == 0) got = atomicCAS(&s_token, 0, 1) == 0;
+			got = __shfl_sync(0xffffffffu, got, 0);
+			if (!got) { __nanosleep(20); continue; }
+			const int q = *v_ready;                                 // the next panel nobody has loaded yet (q <= blk)
+			if (q > blk) { __syncwarp(); if (lane == 0) *v_token = 0; continue; }
+			int bad = 0;
 			if (lane == 0) {
 				int spins = 0;
-				while (ld_flag(&ctl->solved) <= gbase + blk && !ld_flag(&ctl->abort)) {
-					__nanosleep(256);          // ~2300 warps watch this word: short sleeps saturate its L2 slice (the flags live next to it)
-					if (++spins > 3 * kGsWaitLimit) st_flag(&ctl->abort, 1);
+				while (ld_acquire(&ctl->solved) <= gbase + q && !(bad = ld_flag(&ctl->abort))) {
+					__nanosleep(40);
+					if (++spins > 20 * kGsWaitLimit) st_flag(&ctl->abort, 1);
+				}
+				while (!bad && v_done[q % kGsRing] < nlive) {        // the buffer's previous panel (q - kGsRing) is still being read
+					__nanosleep(20);
+					if (++spins > 20 * kGsWaitLimit) { st_flag(&ctl->abort, 1); bad = 1; }
 				}
 			}
-			if (__shfl_sync(0xffffffffu, ld_flag(&ctl->abort), 0)) return;
-			__syncwarp();
-			if (pw) prof[(nblk + blk) * 8 + 3] = clock64();
-			// every lane acquires the flag itself before it reads the panel (one load; a __threadfence() here also waits for the
-			// column prefetch in flight and cost 3.5 k cycles per panel)
-			(void)ld_acquire(&ctl->solved);
-			fetch_dmu(blk);
+			bad = __shfl_sync(0xffffffffu, bad, 0);
+			if (!bad) {
+				double4 *b_col = ring + (q % kGsRing) * 2 * kGsB, *b_dm = b_col + kGsB;
 #pragma unroll
-			for (int h = 0; h < 2; h++) { double4 *d = w_dm + lane + 32 * h; d->x = pf_d[h][0]; d->y = pf_d[h][1]; d->z = pf_d[h][2]; }
+				for (int h = 0; h < 2; h++) {
+					const int cc = lane + 32 * h, pos = q * kGsB + cc;
+					const bool on = pos < np;
+					const double4 g = on ? gpq[pos] : make_double4(0, 0, 0, 0);
+					const int gm = on ? gmeta[pos] : 0;
+					double d0 = 0, d1 = 0, d2 = 0;                         // beyond the end: zero change, contributes nothing
+					if (on) { d0 = __ldcg(dmu + 3 * pos); d1 = __ldcg(dmu + 3 * pos + 1); d2 = __ldcg(dmu + 3 * pos + 2); }
+					b_col[cc] = make_double4(g.x, g.y, g.z, __longlong_as_double((long long)gm));
+					b_dm[cc] = make_double4(d0, d1, d2, g.w);               // .w: alpha of the column (linear damping)
+				}
+				__threadfence_block();
+				__syncwarp();
+				if (lane == 0) { v_done[q % kGsRing] = 0; __threadfence_block(); *v_ready = q + 1; }
+			} else if (lane == 0) *v_ready = 0x7ffffff0;             // abort: everybody out
+			__syncwarp();
+			if (lane == 0) { __threadfence_block(); *v_token = 0; }
 		}
-		if (pw) prof[(nblk + blk) * 8 + 1] = clock64();
-		// is the next panel out already?  then its dipole changes come along during this panel's arithmetic
-		pf_have_d = false;
-		if (blk + 1 < nblk) {
-			const int sv = __shfl_sync(0xffffffffu, ld_acquire(&ctl->solved), 0);     // warp-uniform decision; every lane has acquired
-			if (sv > gbase + blk + 1) { fetch_dmu(blk + 1); pf_have_d = true; }
-		}
-		__syncwarp();
+		if (__shfl_sync(0xffffffffu, ld_flag(&ctl->abort), 0)) return;
+		__threadfence_block();                                      // the loader's stores to the buffer, posted before `ready`
+		if (pw) prof[(nblk + blk) * 8 + 1] = gtime();
+		const double4 *w_col = ring + (blk % kGsRing) * 2 * kGsB, *w_dm = w_col + kGsB;
 #pragma unroll
 		for (int w = 0; w < kGsOwn; w++) {
 			if (chs[w] < 0 || (chs[w] >= skip0 && chs[w] < skip1)) continue;       // warp-uniform
@@ -424,7 +418,7 @@ __device__ __forceinline__ void gs_updater_body(double *s_raw, int cta, int U, c
 				if (prof && lane == 0) prof[nblk * 16 + chs[w]] = gtime();      // when this chunk's rows were handed to the cluster
 			}
 		}
-		if (pw) prof[(nblk + blk) * 8 + 2] = clock64();
+		if (pw) prof[(nblk + blk) * 8 + 2] = gtime();
 		if (more) {
 			// per-panel path for the chunks this warp cannot keep in registers
 			for (int ch = gwid + kGsOwn * GW; ch < nchunks; ch += GW) {
@@ -456,6 +450,9 @@ __device__ __forceinline__ void gs_updater_body(double *s_raw, int cta, int U, c
 				if (lane == 0) st_flag(applied + ch, gbase + blk + 1);
 			}
 		}
+		// this warp is finished with the panel's buffer
+		__syncwarp();
+		if (lane == 0) { __threadfence_block(); atomicAdd(&s_done[blk % kGsRing], 1); }
 	}
 	// what was pushed since the solver wrote the rows back
 #pragma unroll
@@ -640,7 +637,7 @@ k_gs_pipeline(const double4 *__restrict__ gpq, const int *__restrict__ gmeta, co
 				for (int J = 0; J <= I; J++) d += s_tpart[gs_tile(I, J) * kGsTileDim + (tid & (kGsTileDim - 1))];
 				// the panel, component by component, to the helper that pushes this column (it may be waiting for it already)
 				if (blk + 1 < nblk) st_async_f64(r_dm, d, r_bar);
-				reinterpret_cast<double *>(s_dm)[4 * wm + wq] = d;
+				if (wm < cnt) __stcg(dmu + 3 * (base + wm) + wq, d);               // for the updaters (the publisher warp fences and raises the flag)
 				// contract_dipoles: mu = alpha (E_s + ef_induced), ef_induced = -acc at the moment of the update  (:3583-3592):
 				// mu = mu_old + dmu; ef_induced is recovered from mu after the sweep (k_gs_efi)
 				if (wm < cnt) {
@@ -656,12 +653,7 @@ k_gs_pipeline(const double4 *__restrict__ gpq, const int *__restrict__ gmeta, co
 			if (warp == kPublisherWarp) {
 				// publish the panel for the updaters: the change of every dipole of the block, then the flag (after the write-back
 				// of the block's rows above: the updaters add this panel to those rows too)
-#pragma unroll
-				for (int h = 0; h < 2; h++) {
-					const int k = lane + 32 * h;
-					const double4 d = s_dm[min(k, kGsB - 1)];
-					if (k < cnt) { __stcg(dmu + 3 * (base + k), d.x); __stcg(dmu + 3 * (base + k) + 1, d.y); __stcg(dmu + 3 * (base + k) + 2, d.z); }
-				}
+				// (the barrier above makes the row threads' stores of the panel and of the rows' write-back part of what this fence orders)
 				__threadfence();
 				__syncwarp();
 				if (lane == 0) st_flag(&ctl->solved, gbase + blk + 1);
@@ -701,6 +693,17 @@ k_gs_pipeline(const double4 *__restrict__ gpq, const int *__restrict__ gmeta, co
 				if (on && k < cnt) {
 					const double2 *src = reinterpret_cast<const double2 *>(near + (size_t)blk * kGsNearPerBlock + ((size_t)(k * kGsAhead + j) * kGsB + r) * 6);
 					t[m][0] = __ldg(src); t[m][1] = __ldg(src + 1); t[m][2] = __ldg(src + 2);
+				}
+			}
+			// the tensors of the block after next: into L2 now (they stream from HBM once per sweep), into registers one block later
+			if (blk + 2 < nblk) {
+				const int tb2 = blk + 2 + j;
+				if (tb2 < nblk && tb2 * kGsB + r < np) {
+#pragma unroll
+					for (int m = 0; m < kCols; m++) {
+						const int k = 2 * hj + cs + 2 * kGsHelpers * m;
+						if (k < kGsB) asm volatile("prefetch.global.L2 [%0];" ::"l"(near + (size_t)(blk + 1) * kGsNearPerBlock + ((size_t)(k * kGsAhead + j) * kGsB + r) * 6));
+					}
 				}
 			}
 			if (tid == 0) mbar_expect_tx(bar_p, panel_bytes);

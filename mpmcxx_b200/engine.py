@@ -52,7 +52,7 @@ EXPORTS = ["mpmc_abi_version", "mpmc_last_error", "mpmc_device_count", "mpmc_cre
            "mpmc_probe_fp64_peak", "mpmc_debug_radial_table", "mpmc_debug_cutoff_thresholds", "mpmc_pi_collective"]
 
 
-KERNEL_CLASSES = ["energy_total", "pair", "structure", "field_recip", "field_real", "rank", "dipole_sweep", "gs_sweep", "palmo"]
+KERNEL_CLASSES = ["energy_total", "pair", "structure", "field_recip", "field_real", "rank", "dipole_sweep", "gs_sweep", "palmo", "gs_precompute"]
 
 
 def lib():

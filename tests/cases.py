@@ -81,22 +81,22 @@ def _traj_kat():
 
 def _traj_uvt():
     s = W.uvt_pore()
-    s.opts.update({"seed": "11", "numsteps": "4000"})
+    s.opts.update({"seed": "11", "numsteps": "10000"})
     return s
 
 
 def _traj_pi_h2():
     tmpl, _ = W.pi_h2_cluster(n_side=3, P=8, L=40.0)
-    tmpl.opts.update({"seed": "3", "numsteps": "5000", "PI_trial_chain_length": "3"})
+    tmpl.opts.update({"seed": "3", "numsteps": "10000", "PI_trial_chain_length": "3"})
     return tmpl
 
 
 TRAJ = {
     "traj_nvt_lj216": (_traj_lj, 0, 10000),
     "traj_nvt_kat_gs_ranked": (_traj_kat, 0, 10000),
-    "traj_uvt_pore": (_traj_uvt, 0, 4000),
+    "traj_uvt_pore": (_traj_uvt, 0, 10000),
     "traj_pi_argon_dimer": (W.argon_dimer_pi, 8, 10000),
-    "traj_pi_h2_27x8": (_traj_pi_h2, 8, 5000),
+    "traj_pi_h2_27x8": (_traj_pi_h2, 8, 10000),
 }
 
 

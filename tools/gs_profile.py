@@ -38,7 +38,7 @@ print("longest block periods:", [(int(b), int(per[b])) for b in worst], " total 
 u = upd[:, :4].astype(np.float64)
 ok = (u[:, 2] > 0) & (u[:, 0] > 0)
 polled = ok & (u[:, 3] > 0)
-print("updater warp (cta 0 warp 0), cycles per panel (mean over %d panels): top -> next panel's changes in shared memory %.0f, contraction (+ hand-over when due) %.0f; its period %.0f" % (
+print("updater warp (cta 0 warp 0), NANOSECONDS per panel (mean over %d panels): top -> next panel's changes in shared memory %.0f, contraction (+ hand-over when due) %.0f; its period %.0f" % (
     ok.sum(), (u[ok, 1] - u[ok, 0]).mean(), (u[ok, 2] - u[ok, 1]).mean(), np.diff(u[ok][:, 0]).mean()))
 print("   panels it had to poll for: %d of %d; there: waiting for the flag %.0f, fence + load of the changes %.0f" % (
     polled.sum(), ok.sum(), (u[polled, 3] - u[polled, 0]).mean() if polled.any() else 0, (u[polled, 1] - u[polled, 3]).mean() if polled.any() else 0))
@@ -73,3 +73,6 @@ for cb in range(5, nb):
 print("  by warp index of the updater CTA (warp = chunk // 140; scheduler = warp % 4): " + ", ".join("%d:%.0f" % (w, np.median(v)) for w, v in sorted(bywarp.items())))
 print("  hand-over latency by block (median over its chunks, ns):", [(cb, int(np.nanmedian(lat[cb]))) for cb in list(range(5, 30)) + list(range(60, 70)) + list(range(130, nb))])
 print("  solver: ns between consecutive panel sends, blocks 0..40:", np.diff(pub[:41]).tolist())
+
+lag = u[:, 1] - pub
+print("  updater warp (cta 0 warp 0): ns between the solver sending panel b and this warp starting its contraction, panels 0..143 step 8:", [int(x) for x in lag[::8]])
