@@ -552,8 +552,8 @@ def run_pi(args, embedded=False):
         a, b = int(starts[m]), int(ends[m])
         pos[:, a:b, :] += rs.normal(scale=0.02, size=(P, 1, 3))
         eng.update_sites_all_beads(a, pos[lo:hi, a:b, :])
-        torch.cuda.synchronize()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()                                   # all ranks start the sweep together: the exchange inside it waits for the slowest rank,
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)   # and the host-side move above is not part of `value`
         e0.record(ext)
         u_last = eng.pi_potential_allreduce(P)[0]
         e1.record(ext)

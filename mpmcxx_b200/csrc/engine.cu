@@ -746,7 +746,7 @@ static int run_structure(mpmc_engine *e, DevBuf<int> &list, int nlist, DevBuf<do
 		const size_t smem = sizeof(double2) * kSkSites * 3 * (kmax + 1);
 		Timed _t(e, MPMC_K_STRUCTURE);
 		if (dirty_only)
-			k_structure_partial<<<dim3(std::min(kSkMaxDirty, nchunks), B), kSkThreads, smem, stream>>>(e->d_posq.p, e->cap, list.p, nlist, e->d_kvec.p, nk, kmax, e->cell,
+			k_structure_partial<<<dim3(std::min(kSkMaxDirty, nchunks), B, B <= 16 ? 3 : 1), kSkThreads, smem, stream>>>(e->d_posq.p, e->cap, list.p, nlist, e->d_kvec.p, nk, kmax, e->cell,
 			                                                                                        e->d_sk_part.p, nchunks, e->d_sk_dirty.p);
 		else
 			k_structure_partial<<<dim3(nchunks, B), kSkThreads, smem, stream>>>(e->d_posq.p, e->cap, list.p, nlist, e->d_kvec.p, nk, kmax, e->cell,

@@ -54,8 +54,11 @@ k_structure_partial(const double4 *__restrict__ posq, int stride, const int *__r
 	__shared__ double s_q[kSkSites];
 	// `dirty` (may be null): { count, chunk indices ... } — only the chunks that hold a site moved since the partials were last
 	// computed; the others are still valid, and summing all of them in chunk order gives the bits of a full evaluation
+	// In the dirty form the k vectors are also cut in gridDim.z slices: a move touches one or two chunks per bead system, and at 8 bead
+	// systems per GPU that would be 8 busy CTAs of 10 us each.
 	if (dirty && (int)blockIdx.x >= dirty[0]) return;
 	const int bead = blockIdx.y, chunk = dirty ? dirty[1 + blockIdx.x] : blockIdx.x;
+	const int kslices = gridDim.z, kper = (nk + kslices - 1) / kslices, k_lo = blockIdx.z * kper, k_hi = min(nk, k_lo + kper);
 	const double4 *pq = posq + (size_t)bead * stride;
 	const int rows = 3 * (kmax + 1);
 	const int base = chunk * kSkSites;
@@ -68,7 +71,7 @@ k_structure_partial(const double4 *__restrict__ posq, int stride, const int *__r
 		build_phase_table(c, p.x, p.y, p.z, kmax, s_tab + (size_t)threadIdx.x * rows, 1, 0);
 	}
 	__syncthreads();
-	for (int ik = threadIdx.x; ik < nk; ik += kSkThreads) {
+	for (int ik = k_lo + threadIdx.x; ik < k_hi; ik += kSkThreads) {
 		const KVec k = kv[ik];
 		double re = 0, im = 0;
 		for (int s = 0; s < cnt; s++) {

@@ -209,6 +209,11 @@ private:
 	std::vector<int> pi_mol_first;   // list position of a molecule -> its first site (+ total at the end)
 	std::vector<int> pi_dirty;       // list positions whose coordinates changed since the device last saw them
 	int pi_target_pos = 0;
+	std::vector<std::vector<Molecule *>> pi_mols;   // [bead system][list position]
+	std::vector<int> pi_movable;     // list positions the Markov chain may pick
+	std::vector<double> pi_chain_term;              // per molecule: PI_chain_mass_length2 of its chain, as last computed
+	std::vector<int> pi_chain_stale;                // list positions whose term must be recomputed
+	void pi_index_build();
 };
 
 } // namespace mpmc_host

@@ -204,10 +204,9 @@ double SimulationControl::PI_calculate_potential() {
 		for (int lp : pi_dirty) {
 			const int first = pi_mol_first[lp], cnt = pi_mol_first[lp + 1] - first;
 			std::vector<double> seg((size_t)PL * cnt * 3);
+			pi_index_build();
 			for (int s = b_lo; s < b_hi; s++) {
-				Molecule *m = systems[s]->molecules;
-				for (int k = 0; k < lp && m; k++) m = m->next;
-				if (!m) throw internal_error;
+				Molecule *m = pi_mols[s][lp];
 				double *o = &seg[(size_t)(s - b_lo) * cnt * 3];
 				int k = 0;
 				for (Atom *a = m->atoms; a; a = a->next, k++) { if (k >= cnt) throw internal_error; o[3 * k] = a->pos[0]; o[3 * k + 1] = a->pos[1]; o[3 * k + 2] = a->pos[2]; }
@@ -241,18 +240,41 @@ double SimulationControl::PI_calculate_energy() {             // :734-748
 	return sys.observables->energy;
 }
 
+// The sum over every mobile molecule of its chain's mass-weighted squared length (:859-904), in list order.  A molecule's term
+// depends on that molecule's bead coordinates only, so the terms are kept and only those of molecules altered since the last call
+// are recomputed: the same doubles added in the same order as the reference's full loop, without walking P x M molecules per step.
 double SimulationControl::PI_chain_mass_length2_ENTIRE_SYSTEM() {   // :859-904
-	double sum = 0;
+	pi_index_build();
+	const int M = (int)pi_mols[0].size();
+	if ((int)pi_chain_term.size() != M) { pi_chain_term.assign(M, 0.0); pi_chain_stale.clear(); for (int lp = 0; lp < M; lp++) pi_chain_stale.push_back(lp); }
+	std::sort(pi_chain_stale.begin(), pi_chain_stale.end());
+	pi_chain_stale.erase(std::unique(pi_chain_stale.begin(), pi_chain_stale.end()), pi_chain_stale.end());
 	std::vector<Molecule *> ptr(nSys);
-	for (int s = 0; s < nSys; s++) ptr[s] = systems[s]->molecules;
-	while (ptr[0]) {
-		if (!(ptr[0]->frozen || ptr[0]->adiabatic || ptr[0]->target)) {
-			for (int s = 0; s < nSys; s++) if (!ptr[s]) throw internal_error;
-			sum += PI_chain_mass_length2(ptr);
-		}
-		for (int s = 0; s < nSys; s++) ptr[s] = ptr[s]->next;
+	for (int lp : pi_chain_stale) {
+		Molecule *m0 = pi_mols[0][lp];
+		if (m0->frozen || m0->adiabatic || m0->target) { pi_chain_term[lp] = 0.0; continue; }
+		for (int s = 0; s < nSys; s++) ptr[s] = pi_mols[s][lp];
+		pi_chain_term[lp] = PI_chain_mass_length2(ptr);
+	}
+	pi_chain_stale.clear();
+	double sum = 0;
+	for (int lp = 0; lp < M; lp++) {
+		Molecule *m0 = pi_mols[0][lp];
+		if (!(m0->frozen || m0->adiabatic || m0->target)) sum += pi_chain_term[lp];
 	}
 	return sum;
+}
+
+// list position -> molecule, per bead system (path-integral runs neither insert nor remove molecules; restore() swaps one object)
+void SimulationControl::pi_index_build() {
+	if ((int)pi_mols.size() == nSys && !pi_mols[0].empty()) return;
+	pi_mols.assign(nSys, {});
+	for (int s = 0; s < nSys; s++) for (Molecule *m = systems[s]->molecules; m; m = m->next) pi_mols[s].push_back(m);
+	pi_movable.clear();
+	for (int lp = 0; lp < (int)pi_mols[0].size(); lp++) {
+		Molecule *m = pi_mols[0][lp];
+		if (!(m->frozen || m->adiabatic || m->target)) pi_movable.push_back(lp);
+	}
 }
 
 double SimulationControl::PI_chain_mass_length2() {           // :905-915
@@ -283,27 +305,21 @@ double SimulationControl::PI_chain_mass_length2(std::vector<Molecule *> &molecul
 // two uniforms from Rando: move type, then the target index (the same index in every bead system) (:1047-1116)
 int SimulationControl::PI_pick_NVT_move() {
 	const double dice_move = Rando::rand(), dice_target = Rando::rand();
+	pi_index_build();
+	if (pi_movable.empty()) throw no_molecules_in_system;
+	const int lp = pi_movable[(int)std::floor(pi_movable.size() * dice_target)];
+	pi_target_pos = lp;
+	pi_dirty.push_back(lp);
+	pi_chain_stale.push_back(lp);
 	for (int s = 0; s < nSys; s++) {
 		System *S = systems[s];
-		std::vector<Molecule *> cand;
-		for (Molecule *m = S->molecules; m; m = m->next) if (!(m->frozen || m->adiabatic || m->target)) cand.push_back(m);
-		if (cand.empty()) throw no_molecules_in_system;
-		const int target = (int)std::floor(cand.size() * dice_target);
-		S->checkpoint->molecule_altered = cand[target];
-		if (s == 0) {                                   // list position of the molecule this step alters (and restore() may put back)
-			int lp = 0;
-			for (Molecule *m = S->molecules; m && m != cand[target]; m = m->next) lp++;
-			pi_target_pos = lp;
-			pi_dirty.push_back(lp);
-		}
+		Molecule *m = pi_mols[s][lp];
+		S->checkpoint->molecule_altered = m;
 		S->checkpoint->movetype = (dice_move < sys.bead_perturb_probability) ? MOVETYPE_PERTURB_BEADS : MOVETYPE_DISPLACE;
-		Molecule *prev = nullptr;
-		for (Molecule *m = S->molecules; m; m = m->next) {
-			if (m == S->checkpoint->molecule_altered) { S->checkpoint->head = prev; S->checkpoint->tail = m->next; break; }
-			prev = m;
-		}
+		S->checkpoint->head = lp > 0 ? pi_mols[s][lp - 1] : nullptr;
+		S->checkpoint->tail = m->next;
 		delete S->checkpoint->molecule_backup;
-		S->checkpoint->molecule_backup = new Molecule(*S->checkpoint->molecule_altered);
+		S->checkpoint->molecule_backup = new Molecule(*m);
 	}
 	return systems[0]->checkpoint->movetype;
 }
@@ -382,6 +398,7 @@ void SimulationControl::PI_perturb_bead_COMs_ENTIRE_SYSTEM() {      // :1402-144
 	}
 	for (int s = 0; s < nSys; s++) systems[s]->checkpoint->molecule_altered = backup[s];
 	if (pi_gpu) for (int lp = 0; lp + 1 < (int)pi_mol_first.size(); lp++) pi_dirty.push_back(lp);
+	pi_chain_term.clear();
 }
 
 void SimulationControl::PI_perturb_bead_COMs() { PI_perturb_bead_COMs(PI_trial_chain_length); }
@@ -426,8 +443,15 @@ void SimulationControl::PI_perturb_bead_COMs(int n) {
 }
 
 void SimulationControl::restore_PI_systems() {
-	for (System *S : systems) { S->iterator_failed = 0; S->restore(); }
+	for (int s = 0; s < nSys; s++) {
+		System *S = systems[s];
+		Molecule *prev = S->checkpoint->head;
+		S->iterator_failed = 0;
+		S->restore();                                    // the backup object takes the altered one's place in the list
+		if (!pi_mols.empty()) pi_mols[s][pi_target_pos] = prev ? prev->next : S->molecules;
+	}
 	pi_dirty.push_back(pi_target_pos);                  // the device still holds the rejected coordinates
+	// (the chain terms need nothing: they were last computed for exactly the coordinates that have just been put back)
 }
 
 double SimulationControl::PI_NVT_boltzmann_factor(double d_potential, double d_chain, int movetype) {   // :490-547

@@ -17,6 +17,7 @@ def pi_energy_worker(rank, nranks, uid, name, p2p, steps, out):
         e = engine.Engine(s, beads=np.ascontiguousarray(beads[lo:hi]), device=rank)
         e.nccl_init(uid, rank, nranks)
         res = []
+        chain = e.pi_chain_allreduce()               # of the fixture's configuration
         rs = np.random.RandomState(17)               # the same moves on every rank
         pos = beads.copy()
         starts = np.nonzero(np.diff(np.concatenate([[-1], s.mol])))[0]
@@ -28,7 +29,6 @@ def pi_energy_worker(rank, nranks, uid, name, p2p, steps, out):
             a, b = int(starts[m]), int(ends[m])
             pos[:, a:b, :] += rs.normal(scale=0.05, size=(P, 1, 3))
             e.update_sites_all_beads(a, pos[lo:hi, a:b, :])
-        chain = e.pi_chain_allreduce()
         coll = e.pi_collective()
         e.close()
         out.put((rank, "ok", np.array(res), chain, coll, pos))
