@@ -515,6 +515,7 @@ int prepare_pair_sweep(mpmc_engine *e) {
 	int rounds = 1;
 	while (rounds < 6 && cols_per_warp / (1 << rounds) >= 32.0) rounds++;
 	if (cols_per_warp < 128.0) rounds = 1;
+	if (const char *ev = getenv("MPMC_PAIR_ROUNDS")) rounds = std::max(1, atoi(ev));      // developer knob (tools/pair_time.py)
 	const int per_round = std::max(1, warps / e->B);                  // items of one round in one bead system (never more items than warps)
 	int K = per_round * rounds;
 	if (K > std::max(1, (col + 15) / 16)) { K = std::max(1, (col + 15) / 16); rounds = 1; }    // at least ~16 columns per item
