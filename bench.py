@@ -364,8 +364,15 @@ def run_ours(args):
     # ---- value: device-resident, CUDA events on the engine's stream -------------------------------------------------
     t_dev_ms = 0.0
     launches1 = eng.launches()
+    def mark_one_moved():
+        """What the engine tracks between moves (the structure-factor chunks of moved sites) must be redone in a device-resident step as
+        it is after a real move: mark one H2 as moved, without a copy (mpmc_debug_mark_moved)."""
+        a, b = gen.mols[gen.rs.randint(len(gen.mols))]
+        eng.mark_moved(a, b - a)
+
     for _ in range(args.steps):
         flush_l2()
+        mark_one_moved()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record(ext)
         eng.enqueue()
@@ -381,6 +388,7 @@ def run_ours(args):
     t_prof_ms = 0.0
     for _ in range(args.steps):
         flush_l2()
+        mark_one_moved()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record(ext)
         eng.enqueue()
@@ -544,21 +552,20 @@ def run_pi(args, embedded=False):
     barrier()
     clocks.start()
     l0 = eng.launches()
-    # device-resident: K sweeps (each after a one-molecule move, so that the incremental structure factor does its real work: the
-    # coordinate upload itself is outside the events), CUDA events on the engine's stream
-    t_dev_ms = 0.0
-    for _ in range(args.steps):
-        m = rs.randint(len(starts))
-        a, b = int(starts[m]), int(ends[m])
-        pos[:, a:b, :] += rs.normal(scale=0.02, size=(P, 1, 3))
-        eng.update_sites_all_beads(a, pos[lo:hi, a:b, :])
-        barrier()                                   # all ranks start the sweep together: the exchange inside it waits for the slowest rank,
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)   # and the host-side move above is not part of `value`
-        e0.record(ext)
+    # device-resident: K sweeps back to back over the beads as they sit in HBM, one event pair around all of them on the engine's
+    # stream.  Before every sweep one molecule is marked as moved (mpmc_debug_mark_moved: no copy), so that the sweep does what it does
+    # after a real move — the structure factor of the moved chunk is recomputed — and nothing is skipped.  (Timing each sweep on
+    # its own after a host-side move measures the ranks' launch skew instead: the exchange inside a sweep waits for the slowest.)
+    marks = [(int(starts[m]), int(ends[m] - starts[m])) for m in rs.randint(len(starts), size=args.steps)]
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(ext)
+    for a, cnt in marks:
+        eng.mark_moved(a, cnt)
         u_last = eng.pi_potential_allreduce(P)[0]
-        e1.record(ext)
-        e1.synchronize()
-        t_dev_ms += e0.elapsed_time(e1)
+    e1.record(ext)
+    e1.synchronize()
+    t_dev_ms = e0.elapsed_time(e1)
     barrier()
     t_dev = max_over_ranks(t_dev_ms * 1e-3)
     launches = eng.launches() - l0

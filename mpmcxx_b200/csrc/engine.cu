@@ -1753,6 +1753,14 @@ int mpmc_debug_gs_profile(mpmc_engine *e, int enable, long long *out, int max_bl
 	return MPMC_OK;
 }
 
+// developer / bench hook: treat sites [first, first + count) as moved (their structure-factor chunks are recomputed by the next
+// evaluation) without sending coordinates — what a device-resident timing loop uses so that no part of a sweep is skipped
+int mpmc_debug_mark_moved(mpmc_engine *e, int first, int count) {
+	if (first < 0 || count < 0 || first + count > e->n) FAIL(MPMC_ERR_INVALID_INPUT, "mark_moved: range out of bounds");
+	mark_moved(e, first, count);
+	return MPMC_OK;
+}
+
 // developer / test hooks for the host-side numerics (no device needed): the radial tables and the r^2 cutoff thresholds
 int mpmc_debug_radial_table(int kind, double param, double u_lo, double u_hi, const double *u, int n, double *out0, double *out1) {
 	RadialTable t;

@@ -49,7 +49,7 @@ EXPORTS = ["mpmc_abi_version", "mpmc_last_error", "mpmc_device_count", "mpmc_cre
            "mpmc_num_sites", "mpmc_energy", "mpmc_energy_enqueue", "mpmc_energy_fetch", "mpmc_download_dipoles",
            "mpmc_download_rank_metric", "mpmc_pi_potential", "mpmc_pi_chain", "mpmc_nccl_get_unique_id", "mpmc_nccl_init", "mpmc_pi_potential_allreduce",
            "mpmc_pi_chain_allreduce", "mpmc_set_timing", "mpmc_get_timing", "mpmc_debug_gs_profile", "mpmc_stream", "mpmc_kernel_launches",
-           "mpmc_probe_fp64_peak", "mpmc_debug_radial_table", "mpmc_debug_cutoff_thresholds", "mpmc_pi_collective"]
+           "mpmc_probe_fp64_peak", "mpmc_debug_radial_table", "mpmc_debug_cutoff_thresholds", "mpmc_pi_collective", "mpmc_debug_mark_moved"]
 
 
 KERNEL_CLASSES = ["energy_total", "pair", "structure", "field_recip", "field_real", "rank", "dipole_sweep", "gs_sweep", "palmo", "gs_precompute"]
@@ -96,6 +96,7 @@ def lib():
         L.mpmc_pi_collective.argtypes = [vp]
         L.mpmc_debug_radial_table.argtypes = [C.c_int, C.c_double, C.c_double, C.c_double, _dp, C.c_int, _dp, C.c_void_p]
         L.mpmc_debug_cutoff_thresholds.argtypes = [C.c_double, _dp]
+        L.mpmc_debug_mark_moved.argtypes = [vp, C.c_int, C.c_int]
         _lib = L
     return _lib
 
@@ -265,6 +266,9 @@ class Engine:
         k = nm.value
         com = com.reshape(-1)[: self.B * k * 3].reshape(self.B, k, 3).copy()
         return v.value, com, mm[:k].copy()
+
+    def mark_moved(self, first, count):
+        _ck(lib().mpmc_debug_mark_moved(self.h, first, count))
 
     def set_timing(self, on=True):
         _ck(lib().mpmc_set_timing(self.h, 1 if on else 0))
