@@ -156,6 +156,9 @@ struct mpmc_engine {
 	bool sk_valid = false;
 	std::vector<int> sk_dirty;
 	DevBuf<int> d_sk_dirty, d_pi_done;
+	DevBuf<long long> d_pi_launch;   // launches of k_pi_finish that post their result to the host themselves
+	long long pi_posted = 0;         // ... as counted by the host
+	bool pi_direct = false;          // the last sweep enqueued posts its own result (no copy node, no stream synchronise)
 	int *h_sk_dirty = nullptr;
 	long long xchg_timeout_cycles = 0;
 	DevBuf<double> d_erf_tab;
@@ -1171,10 +1174,14 @@ static int enqueue_energy(mpmc_engine *e, bool pi_fused = false) {
 		}
 		if ((rc = e->d_pisums.ensure(8 + 4 * (size_t)B)) || (rc = e->d_pi_done.ensure(1))) return rc;
 		const bool xchg = e->p2p;
+		// single GPU or peer-memory exchange: the kernel's sums are final and it posts them to the host itself; with the NCCL
+		// fallback the all-reduce still follows and the result is copied afterwards
+		e->pi_direct = xchg || !e->comm;
 		k_pi_finish<<<B, 256, 0, e->stream>>>(e->d_partials.p, nitems, e->d_item_ctr.p, e->pair_ctr_start, e->d_sk_part.p,
 		                                      ((int)e->mobile_q.size() + kSkSites - 1) / kSkSites, e->d_kvec.p, nk, 4.0 * kPi / e->cell.volume, e->d_S_mobile.p,
 		                                      e->d_result.p, B, e->lrc_pair + e->lrc_self, e->es_self, es ? 1 : 0, e->d_pisums.p,
-		                                      xchg ? e->d_peers.p : nullptr, e->rank, e->nranks, xchg ? e->d_step.p : nullptr, e->xchg_timeout_cycles, e->d_pi_done.p);
+		                                      xchg ? e->d_peers.p : nullptr, e->rank, e->nranks, xchg ? e->d_step.p : nullptr, e->xchg_timeout_cycles, e->d_pi_done.p,
+		                                      e->pi_direct ? e->h_pisums : nullptr, e->d_pi_launch.p);
 		LAUNCHED(e);
 		CK(cudaGetLastError());
 		e->enqueued = true;
@@ -1239,8 +1246,12 @@ int mpmc_create(const mpmc_config *cfg, mpmc_engine **out) {
 	if ((rc = e->d_result.ensure(res_len(e->B))) || (rc = e->d_flags.ensure(e->B)) || (rc = e->d_rmin.ensure(e->B))) { mpmc_destroy(e); return rc; }
 	e->last_failed.assign(e->B, 0);
 	CK(cudaMallocHost(&e->h_sk_dirty, sizeof(int) * (1 + kSkMaxDirty)));
-	if ((rc = e->d_sk_dirty.ensure(1 + kSkMaxDirty)) || (rc = e->d_pi_done.ensure(1)) || (rc = e->d_pisums.ensure(8 + 4 * (size_t)e->B))) { mpmc_destroy(e); return rc; }
+	if ((rc = e->d_sk_dirty.ensure(1 + kSkMaxDirty)) || (rc = e->d_pi_done.ensure(1)) || (rc = e->d_pisums.ensure(8 + 4 * (size_t)e->B)) ||
+	    (rc = e->d_pi_launch.ensure(1))) { mpmc_destroy(e); return rc; }
 	CK(cudaMemset(e->d_pi_done.p, 0, sizeof(int)));
+	CK(cudaMemset(e->d_pi_launch.p, 0, sizeof(long long)));
+	CK(cudaMallocHost(&e->h_pisums, sizeof(double) * (8 + 4 * (size_t)e->B)));
+	memset(e->h_pisums, 0, sizeof(double) * (8 + 4 * (size_t)e->B));
 	CK(cudaMemset(e->d_pisums.p, 0, sizeof(double) * 8));
 	{
 		const char *ts = getenv("MPMC_PI_XCHG_TIMEOUT_S");
@@ -1311,7 +1322,7 @@ int mpmc_destroy(mpmc_engine *e) {
 	e->d_rmin.release(); e->d_result.release();
 	for (int q = 0; q < 2; q++) if (e->h_stage[q]) cudaFreeHost(e->h_stage[q]);
 	if (e->h_sk_dirty) cudaFreeHost(e->h_sk_dirty);
-	e->d_iperm.release(); e->d_sk_dirty.release(); e->d_pi_done.release();
+	e->d_iperm.release(); e->d_sk_dirty.release(); e->d_pi_done.release(); e->d_pi_launch.release();
 	if (e->h_result) cudaFreeHost(e->h_result);
 	if (e->h_flags) cudaFreeHost(e->h_flags);
 	drop_pi_graph(e);
@@ -1627,7 +1638,10 @@ int mpmc_pi_potential_allreduce(mpmc_engine *e, int P_global, double means[4], d
 	// third of that.
 	const bool es = !e->cfg.rd_only;
 	const bool graphable = e->pi_warm && !e->pi_graph_off && !e->timing && !e->cfg.polarization && !e->topo_dirty && !e->frozen_sk_dirty && (!es || e->sk_valid);
-	auto copy_back = [&]() { return cudaMemcpyAsync(e->h_pisums, e->d_pisums.p, sizeof(double) * 6, cudaMemcpyDeviceToHost, e->stream); };
+	// single GPU or peer-memory exchange (and no polarization loop): the sweep's last kernel posts sums + launch number into the pinned
+	// result buffer itself; otherwise (NCCL fallback, polarizable beads) the result is copied after the last operation
+	const bool direct = !e->cfg.polarization && (e->p2p || !e->comm);
+	auto copy_back = [&]() { return direct ? cudaSuccess : cudaMemcpyAsync(e->h_pisums, e->d_pisums.p, sizeof(double) * 6, cudaMemcpyDeviceToHost, e->stream); };
 	if (graphable && e->pi_graph) {
 		// what run_structure_mobile does on the host when it is not replayed from a graph
 		e->h_sk_dirty[0] = (int)e->sk_dirty.size();
@@ -1667,7 +1681,19 @@ int mpmc_pi_potential_allreduce(mpmc_engine *e, int P_global, double means[4], d
 		if (e->comm && !e->p2p) NK(g_nccl.AllReduce(e->d_pisums.p, e->d_pisums.p, 4, kNcclFloat64, kNcclSum, e->comm, e->stream));
 		CK(copy_back());
 	}
-	{ int _rc = sync_stream(e); if (_rc) return _rc; }
+	if (direct && !e->timing) {
+		// wait for the launch number in host memory instead of a stream synchronisation (its wake-up costs ~10 us of a 100 us sweep);
+		// if it does not come soon — a long exchange wait, a fault — fall back to the synchronisation, which also reports errors
+		const double want = (double)(++e->pi_posted);
+		volatile double *hp = e->h_pisums;
+		long spins = 0;
+		while (hp[7] != want && ++spins < 20000000L) { }
+		if (hp[7] != want) { int _rc = sync_stream(e); if (_rc) return _rc; if (hp[7] != want) FAIL(MPMC_ERR_INTERNAL, "path-integral sweep finished without posting its result"); }
+		e->stage_busy[0] = e->stage_busy[1] = false;        // everything staged before this sweep has been consumed
+	} else {
+		if (direct) ++e->pi_posted;
+		int _rc = sync_stream(e); if (_rc) return _rc;
+	}
 	e->enqueued = false;
 	e->pi_warm = true;
 	if (e->timing) collect_timing(e);
