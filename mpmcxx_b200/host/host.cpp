@@ -139,6 +139,8 @@ System::System(const System &o) {
 	// settings only; the bead systems read their own geometry (initialize_PI_NVT_Systems, PathIntegral.cpp:618-631)
 	cuda = o.cuda; ensemble = o.ensemble;
 	memcpy(job_name, o.job_name, sizeof job_name); memcpy(pqr_input, o.pqr_input, sizeof pqr_input);
+	memcpy(pqr_output, o.pqr_output, sizeof pqr_output); memcpy(pqr_restart, o.pqr_restart, sizeof pqr_restart);
+	long_output = o.long_output; independent_particle = o.independent_particle; write_files = o.write_files;
 	numsteps = o.numsteps; corrtime = o.corrtime; move_factor = o.move_factor; rot_factor = o.rot_factor;
 	insert_probability = o.insert_probability; bead_perturb_probability = o.bead_perturb_probability;
 	temperature = o.temperature; pressure = o.pressure; free_volume = o.free_volume; scale_charge = o.scale_charge;
@@ -194,6 +196,11 @@ void System::read_molecules(const char *file) {
 		Atom *a = new Atom();
 		a->id = ++atom_counter; a->frozen = fz; a->adiabatic = ad; a->spectre = sp; a->target = tg;
 		a->pos[0] = x; a->pos[1] = y; a->pos[2] = z; a->mass = mass; a->charge = q; a->polarizability = al; a->epsilon = ep; a->sigma = sg; a->omega = om;
+		if (t.size() > 15) a->gwp_alpha = to_double(t[15]);
+		if (t.size() > 16) a->c6 = to_double(t[16]);
+		if (t.size() > 17) a->c8 = to_double(t[17]);
+		if (t.size() > 18) a->c10 = to_double(t[18]);
+		if (t.size() > 19) a->c9 = to_double(t[19]);
 		strncpy(a->atomtype, t[2].c_str(), sizeof a->atomtype - 1);
 		*atail = a; atail = &a->next;
 	}
@@ -201,6 +208,91 @@ void System::read_molecules(const char *file) {
 	if (!atom_counter) throw molecule_wo_atoms;
 	if (!moveable) throw missing_required_datum;      // "no moveable molecules found" (:757-760)
 	gpu_table_stale = true;
+}
+
+// The PQR file as the reference writes it (src/System.Output.cpp:900-1091): CRYST1 record (lengths %9.3f, angles %7.2f with VMD's
+// alpha <-> beta convention), one ATOM record per site — PDB-style %8.3f coordinates, or %11.6f when `long_output` is on or a basis
+// component reaches 100 A; wrapped coordinates when `wrapall` — the eight corners of the cell as a frozen BOX pseudo-molecule with
+// CONECT records along its edges (wrapall only), the basis as REMARK records, END.
+int System::write_molecules(FILE *fp) {
+	auto dot = [](const double *a, const double *b) { return a[0] * b[0] + a[1] * b[1] + a[2] * b[2]; };
+	bool ext = long_output != 0;
+	for (int i = 0; i < 3 && !ext; i++) for (int j = 0; j < 3; j++) if (pbc.basis[i][j] >= 100.0) ext = true;
+	const double *b0 = pbc.basis[0], *b1 = pbc.basis[1], *b2 = pbc.basis[2];
+	fprintf(fp, "CRYST1");
+	fprintf(fp, "%9.3f", std::sqrt(dot(b0, b0)));
+	fprintf(fp, "%9.3f", std::sqrt(dot(b1, b1)));
+	fprintf(fp, "%9.3f", std::sqrt(dot(b2, b2)));
+	fprintf(fp, "%7.2f", 180.0 / pi * std::acos(dot(b2, b0) / std::sqrt(dot(b0, b0) * dot(b2, b2))));
+	fprintf(fp, "%7.2f", 180.0 / pi * std::acos(dot(b1, b2) / std::sqrt(dot(b1, b1) * dot(b2, b2))));
+	fprintf(fp, "%7.2f", 180.0 / pi * std::acos(dot(b0, b1) / std::sqrt(dot(b1, b1) * dot(b0, b0))));
+	fprintf(fp, "\n");
+	int i = 1, j = 1;
+	for (Molecule *m = molecules; m; m = m->next, j++)
+		for (Atom *a = m->atoms; a; a = a->next, i++) {
+			fprintf(fp, "ATOM  ");
+			fprintf(fp, "%5d", i);
+			fprintf(fp, " %-4.45s", a->atomtype);
+			fprintf(fp, " %-3.3s ", m->moleculetype);
+			fprintf(fp, "%-1.1s", a->adiabatic ? "A" : a->frozen ? "F" : a->spectre ? "S" : a->target ? "T" : "M");
+			fprintf(fp, " %4d   ", independent_particle ? i : j);
+			const double *x = wrapall ? a->wrapped_pos : a->pos;
+			for (int p = 0; p < 3; p++) { if (ext) fprintf(fp, "%11.6f ", x[p]); else fprintf(fp, "%8.3f", x[p]); }
+			fprintf(fp, " %8.5f", a->mass);
+			fprintf(fp, " %8.5f", a->charge / E2REDUCED);
+			fprintf(fp, " %8.5f", a->polarizability);
+			fprintf(fp, " %8.5f", a->epsilon);
+			fprintf(fp, " %8.5f", a->sigma);
+			fprintf(fp, " %8.5f", a->omega);
+			fprintf(fp, " %8.5f", a->gwp_alpha);
+			fprintf(fp, " %8.5f", a->c6);
+			fprintf(fp, " %8.5f", a->c8);
+			fprintf(fp, " %8.5f", a->c10);
+			fprintf(fp, " %8.5f", a->c9);
+			fprintf(fp, "\n");
+		}
+	if (wrapall) {
+		int atom_box = i, label[2][2][2];
+		const int molecule_box = j;
+		for (int a = 0; a < 2; a++) for (int b = 0; b < 2; b++) for (int c = 0; c < 2; c++) {
+			fprintf(fp, "ATOM  ");
+			fprintf(fp, "%5d", atom_box);
+			fprintf(fp, " %-4.45s", "X");
+			fprintf(fp, " %-3.3s ", "BOX");
+			fprintf(fp, "%-1.1s", "F");
+			fprintf(fp, " %4d   ", molecule_box);
+			const double occ[3] = {a - 0.5, b - 0.5, c - 0.5};
+			for (int p = 0; p < 3; p++) {
+				double v = 0;
+				for (int q = 0; q < 3; q++) v += pbc.basis[q][p] * occ[q];
+				if (ext) fprintf(fp, "%11.6f ", v); else fprintf(fp, "%8.3f", v);
+			}
+			fprintf(fp, " %8.4f", 0.0); fprintf(fp, " %8.4f", 0.0); fprintf(fp, " %8.5f", 0.0); fprintf(fp, " %8.5f", 0.0); fprintf(fp, " %8.5f", 0.0);
+			fprintf(fp, "\n");
+			label[a][b][c] = atom_box++;
+		}
+		for (int a = 0; a < 2; a++) for (int b = 0; b < 2; b++) for (int c = 0; c < 2; c++)
+			for (int l = 0; l < 2; l++) for (int m = 0; m < 2; m++) for (int n = 0; n < 2; n++)
+				if (std::abs(a - l) + std::abs(b - m) + std::abs(c - n) == 1) fprintf(fp, "CONECT %4d %4d\n", label[a][b][c], label[l][m][n]);
+	}
+	for (int r = 0; r < 3; r++) fprintf(fp, "REMARK BOX BASIS[%d] = %20.14lf %20.14lf %20.14lf\n", r, pbc.basis[r][0], pbc.basis[r][1], pbc.basis[r][2]);
+	fprintf(fp, "END\n");
+	fflush(fp);
+	return 0;
+}
+
+// :837-895 (single-process branch): the previous file becomes "<name>.last"
+int System::write_molecules_wrapper(const char *filename) {
+	if (FILE *t = fopen(filename, "r")) {
+		fclose(t);
+		const std::string old = std::string(filename) + ".last";
+		if (rename(filename, old.c_str())) fprintf(stderr, "WARNING: Unable to rename .last file.\n");
+	}
+	FILE *fp = fopen(filename, "w");
+	if (!fp) throw 1001;                              // fopen_fail_write
+	const int rc = write_molecules(fp);
+	fclose(fp);
+	return rc;
 }
 
 // PeriodicBoundary::update (src/PeriodicBoundary.cpp:31-101) + update_pbc (src/System.cpp:859-876)
@@ -524,7 +616,10 @@ bool System::mc(std::vector<step_record> *log) {       // :20-134
 			nodestats->reject++;
 		}
 		if (log) log->push_back({movetype, final_energy, bf, accepted, observables->N});
+		// every correlation time: the restart geometry (do_corrtime_bookkeeping, System.MonteCarlo.cpp:1925-1934)
+		if (write_files && corrtime && !(step % corrtime) && pqr_restart[0]) { update_com(); wrap_all(); write_molecules_wrapper(pqr_restart); }
 	}
+	if (write_files && pqr_output[0]) { update_com(); wrap_all(); write_molecules_wrapper(pqr_output); }   // the final state (:112-120)
 	return true;
 }
 

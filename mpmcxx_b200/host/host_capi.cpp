@@ -74,6 +74,25 @@ int mpmc_host_run_sharded(const char *input_file, int P, int max_steps, int rank
 	return 0;
 }
 
+// The PQR file the mirror writes for (bead system `s` of) the job an input file describes, as read — no device work: readers +
+// update_com + wrap_all + write_molecules_wrapper.  Also returns the three file names chosen for that system ('\n'-separated:
+// pqr_input, pqr_restart, pqr_output) in names (capacity cap).
+int mpmc_host_write_pqr(const char *input_file, int P, int s, const char *out_path, char *names, int cap) {
+	try {
+		SimulationControl sc(input_file, P);
+		sc.sys.write_files = false;
+		sc.initializeSimulationObjects();
+		System &S = sc.systems.empty() ? sc.sys : *sc.systems[s];
+		S.update_com();
+		S.wrap_all();
+		if (out_path && out_path[0]) S.write_molecules_wrapper(out_path);
+		if (names) snprintf(names, cap, "%s\n%s\n%s", S.pqr_input, S.pqr_restart, S.pqr_output);
+	} catch (int e) {
+		return e ? e : internal_error;
+	}
+	return 0;
+}
+
 // One energy() of the system an input file describes, through the mirror (reader + flatten + engine): out[5] = energy, rd,
 // coulombic, polarization, iterations.
 int mpmc_host_energy(const char *input_file, double *out) {

@@ -57,6 +57,7 @@ public:
 	char atomtype[64] = {0};
 	int id = 0, frozen = 0, adiabatic = 0, spectre = 0, target = 0;
 	double mass = 0, charge = 0, polarizability = 0, epsilon = 0, sigma = 0, omega = 0;
+	double gwp_alpha = 0, c6 = 0, c8 = 0, c10 = 0, c9 = 0;   // carried from the PQR file to the PQR file (not used on this path)
 	double pos[3] = {0, 0, 0}, wrapped_pos[3] = {0, 0, 0};
 	double ef_static[3] = {0, 0, 0}, ef_induced[3] = {0, 0, 0}, ef_induced_change[3] = {0, 0, 0}, mu[3] = {0, 0, 0};
 	double rank_metric = 0;
@@ -109,6 +110,8 @@ public:
 
 	// geometry
 	void read_molecules(const char *pqr_file);      // src/System.cpp:507-770
+	int write_molecules(FILE *fp);                   // src/System.Output.cpp:900-1091: the PQR format, field for field
+	int write_molecules_wrapper(const char *filename);   // :837-895: previous file -> "<name>.last", then write
 	void update_pbc();                               // src/System.cpp:859-876 + PeriodicBoundary::update
 	int countNatoms() const;
 	unsigned int countN();
@@ -129,7 +132,9 @@ public:
 
 	// settings (names as in src/System.h)
 	int cuda = 1, ensemble = ENSEMBLE_NVT;
-	char job_name[256] = "untitled", pqr_input[512] = {0};
+	char job_name[256] = "untitled", pqr_input[512] = {0}, pqr_output[512] = {0}, pqr_restart[512] = {0};
+	int long_output = 0, independent_particle = 0;
+	bool write_files = true;         // restart / final PQR files are written like the reference's (tests and benches may switch it off)
 	uint32_t numsteps = 0, corrtime = 0, step = 0;
 	double move_factor = 1.0, rot_factor = 1.0, insert_probability = 0, bead_perturb_probability = 0;
 	double temperature = 0, pressure = 0, free_volume = 0, scale_charge = 1.0;
@@ -180,6 +185,10 @@ public:
 	double loop_seconds = 0;
 	long long loop_sweeps = 0, pi_sweeps = 0;
 	void set_sharding(int r, int nr, const char id[128]) { rank = r; nranks = nr; memcpy(nccl_id, id, 128); }
+	// file names per system (check_io_files_options, src/SimulationControl.cpp:2196-2360)
+	std::vector<std::string> pqr_input_filenames, pqr_restart_filenames, pqr_final_filenames;
+	void check_io_files_options();
+	static std::string make_filename(const char *basename, int fileno);   // src/Output.cpp:46-92
 
 	// path integrals (src/SimulationControl.PathIntegral.cpp)
 	bool PI_nvt_mc(std::vector<System::step_record> *log = nullptr);

@@ -82,6 +82,9 @@ bool SimulationControl::process_command(const std::vector<std::string> &t) {
 		return true;
 	}
 	if (ieq(k, "pqr_input")) { strncpy(sys.pqr_input, arg(1).c_str(), sizeof sys.pqr_input - 1); return true; }
+	if (ieq(k, "pqr_output")) { strncpy(sys.pqr_output, arg(1).c_str(), sizeof sys.pqr_output - 1); return true; }
+	if (ieq(k, "pqr_restart")) { strncpy(sys.pqr_restart, arg(1).c_str(), sizeof sys.pqr_restart - 1); return true; }
+	if (ieq(k, "long_output")) { sys.long_output = onoff(arg(1)); return true; }
 	if (ieq(k, "rd_only")) { sys.rd_only = onoff(arg(1)); return true; }
 	if (ieq(k, "rd_lrc")) { sys.rd_lrc = onoff(arg(1)); return true; }
 	if (ieq(k, "wrapall")) { sys.wrapall = onoff(arg(1)); return true; }
@@ -117,8 +120,8 @@ bool SimulationControl::process_command(const std::vector<std::string> &t) {
 	                      "halgren_mixing", "c6_mixing", "axilrod_teller", "disp_expansion", "lj_buffered_14_7", "cdvdw", "rd_crystal"})
 		if (ieq(k, w)) { if (onoff(arg(1))) throw unsupported_setting; return true; }
 	// bookkeeping / output options: accepted, not used on this path
-	for (const char *w : {"pop_histogram", "traj_output", "energy_output", "energy_output_csv", "pqr_output", "pqr_restart", "dipole_output", "field_output",
-	                      "frozen_output", "pop_histogram_output", "pop_hist_resolution", "read_pqr_box", "long_output", "traj_input", "insert_input",
+	for (const char *w : {"pop_histogram", "traj_output", "energy_output", "energy_output_csv", "dipole_output", "field_output",
+	                      "frozen_output", "pop_histogram_output", "pop_hist_resolution", "read_pqr_box", "traj_input", "insert_input",
 	                      "max_bondlength", "calc_pressure", "rot_probability", "move_probability"})
 		if (ieq(k, w)) return true;
 	return false;
@@ -127,7 +130,7 @@ bool SimulationControl::process_command(const std::vector<std::string> &t) {
 void SimulationControl::check_system() {
 	if (sys.temperature <= 0) throw missing_setting;
 	if (!sys.numsteps) throw missing_setting;
-	if (!sys.pqr_input[0]) { strncpy(sys.pqr_input, sys.job_name, sizeof sys.pqr_input - 16); strcat(sys.pqr_input, ".initial.pqr"); }
+	check_io_files_options();
 	if (sys.ensemble == ENSEMBLE_PATH_INTEGRAL_NVT) {      // check_PI_options, PathIntegral.cpp:552-606
 		int bits = 0;
 		for (unsigned v = (unsigned)nSys; v; v >>= 1) bits += v & 1;
@@ -135,6 +138,45 @@ void SimulationControl::check_system() {
 		if (!PI_trial_chain_length || PI_trial_chain_length >= nSys) throw invalid_setting;
 	}
 	if (sys.ensemble == ENSEMBLE_UVT && sys.pressure <= 0) throw missing_setting;
+}
+
+// Output::make_filename (src/Output.cpp:46-92): "<base>-%04d<.ext>" when the name ends in a three-character extension, else
+// "<base>-%04d"; /dev/null stays /dev/null
+std::string SimulationControl::make_filename(const char *basename, int fileno) {
+	if (!strncmp("/dev/null", basename, 9)) return "/dev/null";
+	const size_t len = strlen(basename);
+	char num[32];
+	snprintf(num, sizeof num, "-%04d", fileno);
+	if (len > 4 && basename[len - 4] == '.') return std::string(basename, len - 4) + num + std::string(basename + len - 4);
+	return std::string(basename) + num;
+}
+
+// The restart / final / input file names of every system (src/SimulationControl.cpp:2196-2360, single-process branches).  With
+// `parallel_restarts on` system j restarts from "<restart>-000j<.ext>" when that file exists, else from the ".last" copy — the reference
+// builds that name from its rank, which is 0 in a single process, so it is system 0's for every j — else from pqr_input.
+void SimulationControl::check_io_files_options() {
+	const int file_count = std::max(nSys, 1);
+	if (ieq(sys.pqr_restart, "off")) strcpy(sys.pqr_restart, "/dev/null");
+	else if (!sys.pqr_restart[0]) { strncpy(sys.pqr_restart, sys.job_name, sizeof sys.pqr_restart - 16); strcat(sys.pqr_restart, ".restart.pqr"); }
+	if (ieq(sys.pqr_output, "off")) strcpy(sys.pqr_output, "/dev/null");
+	else if (!sys.pqr_output[0]) { strncpy(sys.pqr_output, sys.job_name, sizeof sys.pqr_output - 16); strcat(sys.pqr_output, ".final.pqr"); }
+	pqr_restart_filenames.clear(); pqr_final_filenames.clear(); pqr_input_filenames.clear();
+	for (int j = 0; j < file_count; j++) {
+		pqr_restart_filenames.push_back(file_count > 1 ? make_filename(sys.pqr_restart, j) : std::string(sys.pqr_restart));
+		pqr_final_filenames.push_back(file_count > 1 ? make_filename(sys.pqr_output, j) : std::string(sys.pqr_output));
+	}
+	auto exists = [](const std::string &f) { FILE *t = fopen(f.c_str(), "r"); if (t) fclose(t); return t != nullptr; };
+	if (sys.parallel_restarts) {
+		if (file_count > 1)
+			for (int j = 0; j < file_count; j++) {
+				std::string filename = make_filename(sys.pqr_restart, j);
+				if (!exists(filename)) {
+					filename = make_filename(sys.pqr_restart, 0) + ".last";
+					if (!exists(filename) && !sys.pqr_input[0]) filename = std::string(sys.job_name) + ".initial.pqr";
+				}
+				pqr_input_filenames.push_back(filename);
+			}
+	} else if (!sys.pqr_input[0]) { strncpy(sys.pqr_input, sys.job_name, sizeof sys.pqr_input - 16); strcat(sys.pqr_input, ".initial.pqr"); }
 }
 
 void SimulationControl::initializeSimulationObjects() {      // src/SimulationControl.cpp:80-199
@@ -157,7 +199,10 @@ bool SimulationControl::runSimulation(std::vector<System::step_record> *log) {
 void SimulationControl::initialize_PI_NVT_Systems() {        // PathIntegral.cpp:611-694
 	for (int i = 0; i < nSys; i++) {
 		System *s = new System(sys);
-		s->read_molecules(sys.pqr_input);
+		if (sys.parallel_restarts && i < (int)pqr_input_filenames.size()) strncpy(s->pqr_input, pqr_input_filenames[i].c_str(), sizeof s->pqr_input - 1);
+		strncpy(s->pqr_output, pqr_final_filenames[i].c_str(), sizeof s->pqr_output - 1);
+		strncpy(s->pqr_restart, pqr_restart_filenames[i].c_str(), sizeof s->pqr_restart - 1);
+		s->read_molecules(s->pqr_input);
 		s->update_pbc();
 		for (Molecule *m = s->molecules; m; m = m->next) m->update_COM();
 		systems.push_back(s);
@@ -499,9 +544,14 @@ bool SimulationControl::PI_nvt_mc(std::vector<System::step_record> *log) {     /
 		}
 		if (log) log->push_back({move, pot_trial, bf, accepted, sys.observables->kinetic_energy});
 		move = PI_pick_NVT_move();
+		// every correlation time and at the very end: the restart geometry of every bead system (:176-178, :280-310)
+		if (sys.write_files && rank == 0 && sys.corrtime && (!(sys.step % sys.corrtime) || sys.step == sys.numsteps))
+			for (System *S : systems) { S->update_com(); S->wrap_all(); S->write_molecules_wrapper(S->pqr_restart); }
 	}
 	loop_seconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - t_loop).count();
 	loop_sweeps = pi_sweeps - sweeps0;
+	if (sys.write_files && rank == 0)                  // the final state (:182-194)
+		for (System *S : systems) { S->update_com(); S->wrap_all(); S->write_molecules_wrapper(S->pqr_output); }
 	return true;
 }
 

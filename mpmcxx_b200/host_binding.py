@@ -18,6 +18,7 @@ def lib():
         L = C.CDLL(path)
         L.mpmc_host_run.argtypes = [C.c_char_p, C.c_int, C.c_int, C.c_void_p, C.c_int, C.POINTER(C.c_int), C.c_void_p]
         L.mpmc_host_run_sharded.argtypes = [C.c_char_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_char_p, C.c_void_p, C.c_int, C.POINTER(C.c_int), C.c_void_p]
+        L.mpmc_host_write_pqr.argtypes = [C.c_char_p, C.c_int, C.c_int, C.c_char_p, C.c_char_p, C.c_int]
         L.mpmc_host_last_stats.argtypes = [C.c_void_p]
         L.mpmc_host_last_stats.restype = None
         L.mpmc_host_energy.argtypes = [C.c_char_p, C.c_void_p]
@@ -59,6 +60,21 @@ def run_sharded(input_file: str, P: int, rank: int, nranks: int, device: int, nc
     if rc:
         raise RuntimeError("sharded host run failed with code %d" % rc)
     return log[: n.value].copy(), summary
+
+
+def write_pqr(input_file: str, out_path: str = "", P: int = 0, s: int = 0):
+    """The PQR file the mirror writes for (bead system s of) the job, as read (no GPU needed), and the file names it chose for that
+    system: returns (pqr_input, pqr_restart, pqr_output)."""
+    names = C.create_string_buffer(4096)
+    cwd = os.getcwd()
+    os.chdir(os.path.dirname(os.path.abspath(input_file)))
+    try:
+        rc = lib().mpmc_host_write_pqr(os.path.basename(input_file).encode(), P, s, out_path.encode(), names, 4096)
+    finally:
+        os.chdir(cwd)
+    if rc:
+        raise RuntimeError("host write_pqr failed with code %d" % rc)
+    return tuple(names.value.decode().split("\n"))
 
 
 def last_stats():

@@ -37,6 +37,8 @@ def lib():
         L.mref_pi_energy.argtypes = [C.c_void_p, _dp]
         L.mref_mc_trajectory.argtypes = [C.c_void_p, C.c_int, _dp]
         L.mref_pi_trajectory.argtypes = [C.c_void_p, C.c_int, _dp]
+        L.mref_write_pqr.argtypes = [C.c_void_p, C.c_int, C.c_char_p, C.c_int]
+        L.mref_io_filenames.argtypes = [C.c_void_p, C.c_int, C.c_char_p, C.c_int]
         L.mref_pi_potential.argtypes = [C.c_void_p]
         L.mref_pi_potential.restype = C.c_double
         _lib = L
@@ -151,6 +153,18 @@ class RefSystem:
         if rc:
             raise RuntimeError("reference PI loop threw %d" % rc)
         return log.reshape(nsteps, 5)
+
+    def write_pqr(self, path: str, s: int = -1, after_energy: bool = False) -> None:
+        """The reference's own PQR writer (System::write_molecules_wrapper) for system s."""
+        rc = lib().mref_write_pqr(self.h, s, path.encode(), 1 if after_energy else 0)
+        if rc:
+            raise RuntimeError("reference write_molecules_wrapper returned %d" % rc)
+
+    def io_filenames(self, s: int = -1):
+        """(pqr_input, pqr_restart, pqr_output) the reference chose for system s."""
+        buf = C.create_string_buffer(4096)
+        lib().mref_io_filenames(self.h, s, buf, 4096)
+        return tuple(buf.value.decode().split("\n"))
 
     def pi_potential(self) -> float:
         return lib().mref_pi_potential(self.h)

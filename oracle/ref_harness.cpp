@@ -299,4 +299,28 @@ int mref_pi_trajectory(void *h, int nsteps, double *log) {
 	return 0;
 }
 
+/* System::write_molecules_wrapper (src/System.Output.cpp:837-1091) of system s into `path`: the reference's own PQR writer, for
+ * pinning the mirror's writer byte for byte.  Runs energy() first when `after_energy` so that wrapped coordinates are current. */
+int mref_write_pqr(void *h, int s, const char *path, int after_energy) {
+	SimulationControl *sc = (SimulationControl *)h;
+	System *S = (s < 0 || sc->systems.empty()) ? &sc->sys : sc->systems[s];
+	try {
+		Quiet q;
+		if (after_energy) S->energy();
+		char *p = strdup(path);
+		int rc = S->write_molecules_wrapper(p);
+		free(p);
+		return rc;
+	} catch (int e) { return e ? e : -1; }
+}
+
+/* pqr_input / pqr_restart / pqr_output file names the reference chose for system s (check_io_files_options,
+ * src/SimulationControl.cpp:2196-2360), '\n'-separated into out (capacity cap) */
+int mref_io_filenames(void *h, int s, char *out, int cap) {
+	SimulationControl *sc = (SimulationControl *)h;
+	System *S = (s < 0 || sc->systems.empty()) ? &sc->sys : sc->systems[s];
+	snprintf(out, cap, "%s\n%s\n%s", S->pqr_input, S->pqr_restart, S->pqr_output);
+	return 0;
+}
+
 } // extern "C"

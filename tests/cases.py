@@ -106,8 +106,20 @@ SHIPPED = {
     # BASELINE config 1: two free argon atoms (eps = 0) at 2 K, potential == 0 -> the kinetic-energy series of the bead-spring path
     # (src/SimulationControl.PathIntegral.cpp:810-828) and the host loop; PQR with CRYST1 / BOX pseudo-molecule / CONECT records
     "shipped_pi000_free_argon": ("pi000-free-argon-2K", ["equilibrate.in", "Ar.pqr"], "equilibrate.in", 8, 10000),
+    # the same directory's production input (`parallel_restarts on`): every bead system restarts from its own shipped restart file
+    "shipped_pi000_input_restarts": ("pi000-free-argon-2K", ["input.in"] + ["Ar2K.restart-%04d.pqr" % i for i in range(4)] + ["Ar2K.restart-0000.pqr.last"],
+                                     "input.in", 8, 10000),
     # BASELINE config 2: the argon dimer (LJ pair + bead springs), as shipped
     "shipped_pi001_argon_dimer": ("pi001-argon-dimer-2K", ["equilibrate.in", "Ar-Ar-4A.pqr"], "equilibrate.in", 8, 10000),
+}
+
+
+# PQR files as the reference writes them (System::write_molecules, src/System.Output.cpp:900-1091): name -> (builder, P, system index)
+WRITTEN = {
+    "tri_gs_ranked_palmo": (lambda: W.triclinic_mix(solver=W.SOLVER_GS_RANKED_PALMO), 0, -1),     # triclinic cell, unwrapped input, PDB-style coordinates
+    "h2fw_6_jacobi10": (lambda: W.h2_framework(ncell=6, n_h2=20, solver=W.SOLVER_JACOBI10, ensemble="nvt"), 0, -1),
+    "pi_argon_dimer": (W.argon_dimer_pi, 8, 3),                                                    # 10^4 A cell: extended coordinates, file names with -0003
+    "lj_nowrap": (lambda: _with(W.lj_lattice(4, 20.0, jitter=3.0, round4=False), wrapall="off"), 0, -1),
 }
 
 

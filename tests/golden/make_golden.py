@@ -151,6 +151,39 @@ def averages_golden():
               z["aux"].mean(), z["aux"].std(ddof=1) / np.sqrt(z["aux"].size), z["acceptance"].round(3).tolist()), flush=True)
 
 
+def written():
+    """PQR files written by the reference's own writer, and what its restart selection picks for the shipped pi000 `input.in`
+    (parallel_restarts on, `-P 8`: four restart files in the directory, the other four bead systems fall back to system 0's ".last" copy)."""
+    import shutil
+    import tempfile
+    from mpmcxx_b200 import workloads
+    out = {}
+    for name, (build, P, sidx) in cases.WRITTEN.items():
+        s = build()
+        with tempfile.TemporaryDirectory(prefix="mref_written_") as d:
+            r = ref.RefSystem(s, P=P, workdir=d)
+            path = os.path.join(d, "written.pqr")
+            r.write_pqr(path, sidx)
+            out["text_" + name] = np.array(open(path).read())
+            out["names_" + name] = np.array("\n".join(r.io_filenames(sidx)))
+        print("written %-22s %d bytes  %s" % (name, len(str(out["text_" + name])), str(out["names_" + name]).replace("\n", " | ")))
+    src = "/root/reference/sample-input/pi000-free-argon-2K"
+    with tempfile.TemporaryDirectory(prefix="mref_restart_") as d:
+        files = ["input.in"] + ["Ar2K.restart-%04d.pqr" % i for i in range(4)] + ["Ar2K.restart-0000.pqr.last"]
+        for f in files:
+            shutil.copy(os.path.join(src, f), os.path.join(d, f))
+        r = ref.RefSystem.from_directory(d, "input.in", 8)
+        out["restart_files"] = np.array(files)
+        out["restart_texts"] = np.array([open(os.path.join(src, f)).read() for f in files])
+        out["restart_names"] = np.array(["\n".join(os.path.basename(x) for x in r.io_filenames(i)) for i in range(8)])
+        out["restart_pos"] = np.stack([r.sites(i)["pos"] for i in range(8)])
+        e = r.pi_energy()
+        out["restart_kinetic"] = np.float64(e["kinetic"])
+        out["restart_chain"] = np.float64(e["chain_mass_len2"])
+        print("restart selection:", [str(x).replace("\n", " | ") for x in out["restart_names"]], "kinetic", e["kinetic"])
+    np.savez_compressed(os.path.join(HERE, "pqr_written.npz"), **out)
+
+
 def shipped():
     import subprocess
     for name in cases.SHIPPED:
@@ -160,6 +193,9 @@ def shipped():
 if __name__ == "__main__":
     if len(sys.argv) > 3 and sys.argv[1] == "avg1":
         one_average(sys.argv[2], int(sys.argv[3]))
+        sys.exit(0)
+    if len(sys.argv) > 1 and sys.argv[1] == "written":
+        written()
         sys.exit(0)
     if len(sys.argv) > 1 and sys.argv[1] == "averages":
         averages_golden()
@@ -187,3 +223,4 @@ if __name__ == "__main__":
     trajectories()
     shipped()
     averages_golden()
+    written()
