@@ -469,6 +469,10 @@ def run_ours(args):
     eng.close()
     if rank == 0 and world == 1 and not args.no_extra:
         out["extra"] = extra_workloads(engine, local, peak_tflops)
+        try:
+            out["extra"]["h2_framework_uvt_mirror"] = uvt_through_mirror(local)
+        except Exception as ex:                                         # secondary figure: never lose the line over it
+            out["extra"]["h2_framework_uvt_mirror"] = {"error": str(ex)}
     if not args.no_extra:
         # BASELINE config 5, the bead-sharded path-integral workloads (STRONG scaling over the same N GPUs; one exchange of 4 doubles per
         # sweep): the five-site + Ewald variant (enough work per GPU for the scaling target) and the primary single-site variant
@@ -659,6 +663,24 @@ def extra_workloads(engine, device, peak_tflops, steps=20):
         res[name] = r
         eng.close()
     return res
+
+
+def uvt_through_mirror(device, steps=150):
+    """BASELINE config 4 as the grand-canonical run it is named as (insert_probability 0.3: insertions, removals and displacements) through
+    the C++ host mirror's System::mc over the engine — every insertion / removal re-sends the site table (mpmc_insert_sites /
+    mpmc_remove_sites semantics), every rejection restores it: MC moves per second, wall clock of the step loop in C++."""
+    import tempfile
+    from mpmcxx_b200 import host_binding
+    s = W.h2_framework(solver=W.SOLVER_GS_RANKED_PALMO, ensemble="uvt")
+    s.opts.update({"h2_fugacity": "off", "pressure": "1.0", "seed": "7", "numsteps": str(steps), "corrtime": "1000000", "pqr_output": "off", "pqr_restart": "off"})
+    inp = W.write_reference_job(s, tempfile.mkdtemp(prefix="mpmc_uvt_bench_"))
+    host_binding.run(inp, max_steps=20, capacity=20)                    # warm-up (allocations, tables)
+    log, summary = host_binding.run(inp, max_steps=steps, capacity=steps)
+    loop_s, _ = host_binding.last_stats()
+    kinds = np.bincount(log[:, 0].astype(int), minlength=3)
+    return {"workload": "config4 as uVT (insert_probability 0.3, fugacity = pressure) through the C++ mirror's System::mc", "moves_per_sec": steps / loop_s,
+            "ms_per_move": 1e3 * loop_s / steps, "steps": steps, "moves": {"insert": int(kinds[0]), "remove": int(kinds[1]), "displace": int(kinds[2])},
+            "acceptance": float(log[:, 3].mean()), "final_N": float(summary[5])}
 
 
 def run_reference(args):

@@ -135,7 +135,7 @@ struct mpmc_engine {
 	std::vector<int> plist, mobile_q, frozen_q, mol_start;
 	std::vector<unsigned char> mol_mobile;
 	double lrc_pair = 0, lrc_self = 0, es_self = 0, n_pair_evals = 0;
-	bool topo_dirty = true, frozen_sk_dirty = true;
+	bool topo_dirty = true, frozen_sk_dirty = true, cell_tables_dirty = true;
 	// device
 	DevBuf<double4> d_posq;
 	DevBuf<double2> d_lj;
@@ -330,6 +330,7 @@ int compute_cell(mpmc_engine *e, const double basis[9]) {
 	{ int _rc = sync_stream(e); if (_rc) return _rc; }
 	e->frozen_sk_dirty = true;
 	e->sk_valid = false;
+	e->cell_tables_dirty = true;
 	e->topo_dirty = true;   // LRC and self terms depend on volume / cutoff / alpha
 	return MPMC_OK;
 }
@@ -389,6 +390,7 @@ int rebuild_topology(mpmc_engine *e) {
 	{ int _rc = sync_stream(e); if (_rc) return _rc; }   // the std::vectors above go out of scope / may be rebuilt
 	if ((rc = prepare_pair_sweep(e))) return rc;
 	if ((rc = prepare_polar(e))) return rc;
+	e->cell_tables_dirty = false;
 
 	// configuration-independent terms, by (eps, sigma) type instead of by pair.  Pair LRC covers every non-frozen pair with
 	// eps_ij != 0 and sigma_ij != 0, intramolecular pairs included (System.Energy.cpp:1045-1050); self LRC every non-frozen
@@ -442,25 +444,32 @@ int prepare_pair_sweep(mpmc_engine *e) {
 	const int n = e->n;
 	const CellDev &c = e->cell;
 	PairParams &pp = e->pp;
-	// the reference's cutoff tests as thresholds on r^2 (both act on rimg = sqrt(r^2), correctly rounded on the reference's host and here)
-	const volatile double rc = c.cutoff;
-	const double top = 4.0 * c.cutoff * c.cutoff + 1.0;
-	pp.t2_lj = largest_true([&](double x) { volatile double r = std::sqrt(x); volatile double d = r - kSmallDr; return d < rc; }, top);   // System.Energy.cpp:934
-	pp.t2_es = largest_true([&](double x) { volatile double r = std::sqrt(x); return !(r > rc); }, top);                                  // :1490
-	pp.t2_adm = pp.t2_lj * (1.0 + 1e-9);
-	pp.t2_safe = std::min(pp.t2_es, pp.t2_lj) * (1.0 - 1e-9);
 	int rc2;
 	const bool es = !e->cfg.rd_only;
-	if (es) {
-		const long double alpha = c.ewald_alpha;
-		e->erf_tab.build(1, std::min(0.25, pp.t2_adm / 64.0), pp.t2_adm * 1.001, [&](long double u, long double *o) {
-			const long double r = sqrtl(u);
-			o[0] = erfcl(alpha * r) / r;
-		});
-		pp.u_tab_lo = e->erf_tab.u_lo; pp.tab_base = e->erf_tab.base; pp.tab_rows = e->erf_tab.nrows;
-		if ((rc2 = e->d_erf_tab.ensure(e->erf_tab.rows.size()))) return rc2;
-		CK(cudaMemcpyAsync(e->d_erf_tab.p, e->erf_tab.rows.data(), e->erf_tab.rows.size() * sizeof(double), cudaMemcpyHostToDevice, e->stream));
-	} else { pp.u_tab_lo = 0; pp.tab_base = 0; pp.tab_rows = 0; }
+	// What depends on the CELL only — the r^2 thresholds of the reference's cutoff tests and the erfc table (built in long double:
+	// ~5 ms) — is rebuilt when the cell changes, not when the site table does: a uVT insertion or removal changes the topology on
+	// every such move (and again on its rejection).
+	if (e->cell_tables_dirty) {
+		// the reference's cutoff tests as thresholds on r^2 (both act on rimg = sqrt(r^2), correctly rounded on the reference's host and here)
+		const volatile double rc = c.cutoff;
+		const double top = 4.0 * c.cutoff * c.cutoff + 1.0;
+		pp.t2_lj = largest_true([&](double x) { volatile double r = std::sqrt(x); volatile double d = r - kSmallDr; return d < rc; }, top);   // System.Energy.cpp:934
+		pp.t2_es = largest_true([&](double x) { volatile double r = std::sqrt(x); return !(r > rc); }, top);                                  // :1490
+		pp.t2_adm = pp.t2_lj * (1.0 + 1e-9);
+		pp.t2_safe = std::min(pp.t2_es, pp.t2_lj) * (1.0 - 1e-9);
+		if (es) {
+			const long double alpha = c.ewald_alpha;
+			e->erf_tab.build(1, std::min(0.25, pp.t2_adm / 64.0), pp.t2_adm * 1.001, [&](long double u, long double *o) {
+				const long double r = sqrtl(u);
+				o[0] = erfcl(alpha * r) / r;
+			});
+			pp.u_tab_lo = e->erf_tab.u_lo; pp.tab_base = e->erf_tab.base; pp.tab_rows = e->erf_tab.nrows;
+			if ((rc2 = e->d_erf_tab.ensure(e->erf_tab.rows.size()))) return rc2;
+			CK(cudaMemcpyAsync(e->d_erf_tab.p, e->erf_tab.rows.data(), e->erf_tab.rows.size() * sizeof(double), cudaMemcpyHostToDevice, e->stream));
+		} else { pp.u_tab_lo = 0; pp.tab_base = 0; pp.tab_rows = 0; }
+		pp.h_adm = (unsigned)RadialTable::hi_word(pp.t2_adm); pp.h_safe = (unsigned)RadialTable::hi_word(pp.t2_safe);
+		pp.h_tab_lo = (unsigned)RadialTable::hi_word(pp.u_tab_lo);
+	}
 	// the class-sorted site table of the sweep: class = (frozen, charged, LJ-active); sites keep their list order inside a class
 	std::vector<int> cls(n), perm(n);
 	for (int i = 0; i < n; i++) {
@@ -504,8 +513,6 @@ int prepare_pair_sweep(mpmc_engine *e) {
 		}
 	}
 	pp.ncols = col; pp.nseg = (int)e->segs.size();
-	pp.h_adm = (unsigned)RadialTable::hi_word(pp.t2_adm); pp.h_safe = (unsigned)RadialTable::hi_word(pp.t2_safe);
-	pp.h_tab_lo = (unsigned)RadialTable::hi_word(pp.u_tab_lo);
 	// items: ranges of the flattened columns, dealt in ROUNDS of one item per resident warp (item index = k * B + bead, k-major).
 	// The first round is assigned by warp index, the later ones through a counter.  Guided sizes: the rounds carry 1/2, 1/4, 1/8 ...
 	// of the cost (the last two rounds the same), so that the sweep ends within a fraction of the SMALLEST item's duration of the
@@ -610,7 +617,7 @@ int prepare_polar(mpmc_engine *e) {
 	if ((rc = e->d_r2min_ff.ensure(e->B)) || (rc = e->d_t2.ensure(e->B)) || (rc = e->d_t2_cached.ensure(e->B)) || (rc = e->d_recount.ensure(e->B)) ||
 	    (rc = e->d_cnt_ff.ensure((size_t)e->B * n))) return rc;
 	e->rank_ff_dirty = true;
-	{
+	if (e->cell_tables_dirty) {
 		FieldParams &fp = e->fpar;
 		fp.t2_in = cf.polar_ewald ? e->pp.t2_es : e->pp.t2_lj;          // `r > rc` (:2917) / `r - 1e-12 < rc` (:3319)
 		fp.t2_adm = fp.t2_in * (1.0 + 1e-9); fp.t2_safe = fp.t2_in * (1.0 - 1e-9);

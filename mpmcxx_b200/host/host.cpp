@@ -596,6 +596,7 @@ bool System::mc(std::vector<step_record> *log) {       // :20-134
 	observables->volume = pbc.volume;
 	double initial_energy = mc_initial_energy(), final_energy = 0;
 	do_checkpoint();
+	const auto t_loop = std::chrono::steady_clock::now();
 	for (step = 1; step <= numsteps; step++) {
 		initial_energy = observables->energy;
 		make_move();
@@ -619,6 +620,7 @@ bool System::mc(std::vector<step_record> *log) {       // :20-134
 		// every correlation time: the restart geometry (do_corrtime_bookkeeping, System.MonteCarlo.cpp:1925-1934)
 		if (write_files && corrtime && !(step % corrtime) && pqr_restart[0]) { update_com(); wrap_all(); write_molecules_wrapper(pqr_restart); }
 	}
+	loop_seconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - t_loop).count();
 	if (write_files && pqr_output[0]) { update_com(); wrap_all(); write_molecules_wrapper(pqr_output); }   // the final state (:112-120)
 	return true;
 }

@@ -24,7 +24,8 @@ int mpmc_host_run(const char *input_file, int P, int max_steps, double *log, int
 		sc.initializeSimulationObjects();
 		std::vector<System::step_record> rec;
 		sc.runSimulation(&rec);
-		g_last_loop_seconds = sc.loop_seconds; g_last_loop_sweeps = (double)sc.loop_sweeps;
+		g_last_loop_seconds = sc.sys.ensemble == ENSEMBLE_PATH_INTEGRAL_NVT ? sc.loop_seconds : sc.sys.loop_seconds;
+		g_last_loop_sweeps = (double)sc.loop_sweeps;
 		const int n = (int)std::min<size_t>(rec.size(), (size_t)log_capacity);
 		for (int i = 0; i < n; i++) {
 			log[5 * i] = rec[i].movetype; log[5 * i + 1] = rec[i].final_energy; log[5 * i + 2] = rec[i].boltzmann_factor;
@@ -56,7 +57,8 @@ int mpmc_host_run_sharded(const char *input_file, int P, int max_steps, int rank
 		sc.initializeSimulationObjects();
 		std::vector<System::step_record> rec;
 		sc.runSimulation(&rec);
-		g_last_loop_seconds = sc.loop_seconds; g_last_loop_sweeps = (double)sc.loop_sweeps;
+		g_last_loop_seconds = sc.sys.ensemble == ENSEMBLE_PATH_INTEGRAL_NVT ? sc.loop_seconds : sc.sys.loop_seconds;
+		g_last_loop_sweeps = (double)sc.loop_sweeps;
 		const int n = (int)std::min<size_t>(rec.size(), (size_t)log_capacity);
 		for (int i = 0; i < n; i++) {
 			log[5 * i] = rec[i].movetype; log[5 * i + 1] = rec[i].final_energy; log[5 * i + 2] = rec[i].boltzmann_factor;

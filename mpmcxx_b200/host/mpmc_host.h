@@ -134,6 +134,7 @@ public:
 	int cuda = 1, ensemble = ENSEMBLE_NVT;
 	char job_name[256] = "untitled", pqr_input[512] = {0}, pqr_output[512] = {0}, pqr_restart[512] = {0};
 	int long_output = 0, independent_particle = 0;
+	double loop_seconds = 0;         // wall seconds of the last mc() step loop (initial energy excluded)
 	bool write_files = true;         // restart / final PQR files are written like the reference's (tests and benches may switch it off)
 	uint32_t numsteps = 0, corrtime = 0, step = 0;
 	double move_factor = 1.0, rot_factor = 1.0, insert_probability = 0, bead_perturb_probability = 0;
