@@ -584,7 +584,7 @@ def run_pi(args, embedded=False):
     # ---- e2e through the C++ mirror -----------------------------------------------------------------------------------
     e2e_steps = max(args.steps, 200)
     t = tmpl.copy()
-    t.opts.update({"seed": "1", "numsteps": str(e2e_steps + 50), "corrtime": "1000000"})
+    t.opts.update({"seed": "1", "numsteps": str(e2e_steps + 50), "corrtime": "1000000", "pqr_restart": "off", "pqr_output": "off"})   # no restart / final files in the timed loop
     d = tempfile.mkdtemp(prefix="mpmc_pi_bench_")
     inp = W.write_reference_job(t, d)
     uid2 = shared_uid()

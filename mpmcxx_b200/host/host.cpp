@@ -283,6 +283,7 @@ int System::write_molecules(FILE *fp) {
 
 // :837-895 (single-process branch): the previous file becomes "<name>.last"
 int System::write_molecules_wrapper(const char *filename) {
+	if (!strncmp(filename, "/dev/null", 9)) return 0;    // `pqr_restart off` / `pqr_output off`: nothing to format
 	if (FILE *t = fopen(filename, "r")) {
 		fclose(t);
 		const std::string old = std::string(filename) + ".last";
