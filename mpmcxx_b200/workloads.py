@@ -90,7 +90,10 @@ def write_input(system: SiteSystem, path: str, pqr_name: str) -> None:
     opts.update(system.opts)
     with open(path, "w") as fp:
         for k, v in opts.items():
-            fp.write("%-30s %s\n" % (k, v))
+            if not k.startswith("_"):
+                fp.write("%-30s %s\n" % (k, v))
+        for line in opts.get("_lines", ()):      # keywords that may repeat (sorbate_bondlength <type> <A>, ...), in the order given
+            fp.write(line + "\n")
         for i in range(3):
             fp.write("basis%d %.17g %.17g %.17g\n" % (i + 1, *system.basis[i]))
         fp.write("pqr_input %s\n" % pqr_name)
