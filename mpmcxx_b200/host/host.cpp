@@ -132,6 +132,28 @@ void Molecule::rotate(double x, double y, double z, double angle_degrees) {
 	}
 }
 
+// Turn the molecule about its COM so that the site `orientation_site` points along `orientation` (src/Molecule.cpp:211-254):
+// angle = acos(c . o / |o|) with c the normalised COM->site vector, axis = c x o, p' = (R p) R*.  A site that sits ON the COM gives
+// c = 0, axis = 0 and the identity rotation, exactly like the reference.
+void Molecule::orient(const double o[3], int orientation_site) {
+	update_COM();
+	const double rc[3] = {com[0], com[1], com[2]};
+	translate(-rc[0], -rc[1], -rc[2]);
+	Atom *a = atoms;
+	for (int site = 0; site != orientation_site; site++) a = a->next;
+	double cx = a->pos[0], cy = a->pos[1], cz = a->pos[2];
+	const double mag = std::sqrt(cx * cx + cy * cy + cz * cz);
+	if (mag != 0) { cx = cx / mag; cy = cy / mag; cz = cz / mag; } else cx = cy = cz = 0;
+	const double angle = std::acos((cx * o[0] + cy * o[1] + cz * o[2]) / std::sqrt(o[0] * o[0] + o[1] * o[1] + o[2] * o[2]));
+	const Quat R = Quat::axis_angle(cy * o[2] - cz * o[1], cz * o[0] - cx * o[2], cx * o[1] - cy * o[0], angle), Rc = R.conj();
+	for (a = atoms; a; a = a->next) {
+		const Quat p{a->pos[0], a->pos[1], a->pos[2], 0.0};
+		const Quat ans = (R * p) * Rc;
+		a->pos[0] = ans.X; a->pos[1] = ans.Y; a->pos[2] = ans.Z;
+	}
+	translate(rc[0], rc[1], rc[2]);
+}
+
 // ------------------------------------------------------------------------------------------------------------
 // System: geometry
 // ------------------------------------------------------------------------------------------------------------

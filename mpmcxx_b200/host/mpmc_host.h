@@ -12,6 +12,7 @@
 #include <cstdint>
 #include <cstdio>
 #include <cstring>
+#include <map>
 #include <random>
 #include <string>
 #include <vector>
@@ -76,6 +77,7 @@ public:
 	void translate_rand_pbc(double scale, const PeriodicBoundary &pbc, double dice[6]);
 	void translate(double x, double y, double z);
 	void move_to_(double x, double y, double z);
+	void orient(const double orientation[3], int orientation_site);   // src/Molecule.cpp:211-254
 	void update_COM();
 	int natoms() const;
 
@@ -207,7 +209,23 @@ public:
 	void PI_perturb_bead_COMs();
 	void PI_perturb_bead_COMs(int n);
 	void restore_PI_systems();
-	double PI_NVT_boltzmann_factor(double d_potential, double d_chain, int movetype);
+	double PI_NVT_boltzmann_factor(double d_potential, double d_chain, double d_orient, int movetype);
+	// orientational degree of freedom of a diatomic sorbate (sorbate_orientation_site / sorbate_bondlength / sorbate_reducedMass)
+	struct molecular_metadata { int orientation_site; double bond_length, reduced_mass; };   // src/SimulationControl.h:66-74
+	std::vector<molecular_metadata> sorbate_data;          // (static in the reference: one input file per process either way)
+	std::map<std::string, uint32_t> sorbate_data_index;
+	std::vector<double> orientations;                      // 3 per bead system, kept from one call to the next like the reference's
+	void add_orientation_site_entry(const char *id, int site_idx);
+	void add_bond_length_entry(const char *id, double bond_length);
+	void add_reduced_mass_entry(const char *id, double reduced_mass);
+	int get_orientation_site(const std::string &molecule_id);
+	double get_bond_length(const std::string &molecule_id);
+	double get_reduced_mass(const std::string &molecule_id);
+	double PI_orientational_mu_length2();
+	void PI_perturb_beads_orientations();
+	void generate_orientation_configs();
+	void generate_orientation_configs(unsigned int start, unsigned int end, unsigned int p, unsigned int numBeads, double b2, double ukT);
+	void apply_orientation_configs();
 
 private:
 	void read_config(const char *inFilename);

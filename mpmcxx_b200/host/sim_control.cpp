@@ -29,6 +29,7 @@ static int onoff(const std::string &s) {
 }
 
 SimulationControl::SimulationControl(const char *inFilename, int P) : nSys(P) {
+	orientations.assign(3 * (size_t)std::max(P, 0), 0.0);      // one orientation vector per bead (src/SimulationControl.cpp:74)
 	read_config(inFilename);
 	check_system();
 }
@@ -72,6 +73,10 @@ bool SimulationControl::process_command(const std::vector<std::string> &t) {
 	if (ieq(k, "insert_probability")) { sys.insert_probability = num(arg(1)); return true; }
 	if (ieq(k, "bead_perturb_probability")) { sys.bead_perturb_probability = num(arg(1)); return true; }
 	if (ieq(k, "PI_trial_chain_length")) { PI_trial_chain_length = (int)num(arg(1)); return true; }
+	// <molecule type> <value>  (src/SimulationControl.cpp:306-339)
+	if (ieq(k, "sorbate_orientation_site")) { add_orientation_site_entry(arg(1).c_str(), (int)num(arg(2))); return true; }
+	if (ieq(k, "sorbate_bondlength")) { add_bond_length_entry(arg(1).c_str(), num(arg(2))); return true; }
+	if (ieq(k, "sorbate_reducedMass")) { add_reduced_mass_entry(arg(1).c_str(), num(arg(2))); return true; }
 	if (ieq(k, "temperature")) { sys.temperature = num(arg(1)); return true; }
 	if (ieq(k, "pressure")) { sys.pressure = num(arg(1)); return true; }
 	if (ieq(k, "free_volume")) { sys.free_volume = num(arg(1)); return true; }
@@ -425,10 +430,157 @@ void SimulationControl::PI_displace() {
 	}
 }
 
-void SimulationControl::PI_perturb_beads() {
-	// PI_perturb_beads_orientations() returns at once unless sorbate_orientation_site / bond length metadata are configured
-	// (:1559-1572); this mirror has no such keywords.
+void SimulationControl::PI_perturb_beads() {       // :1391-1396
+	PI_perturb_beads_orientations();
 	PI_perturb_bead_COMs();
+}
+
+// ---- orientational degree of freedom of a diatomic sorbate -------------------------------------------------------------------
+// One metadata record per molecule type, created by whichever of the three keywords names the type first
+// (src/SimulationControl.cpp:2976-3071).
+static SimulationControl::molecular_metadata &sorbate_entry(SimulationControl &sc, const char *id) {
+	auto it = sc.sorbate_data_index.find(id);
+	if (it == sc.sorbate_data_index.end()) {
+		sc.sorbate_data.push_back({-1, 0.0, 0.0});
+		it = sc.sorbate_data_index.insert(std::make_pair(std::string(id), (uint32_t)sc.sorbate_data.size() - 1)).first;
+	}
+	return sc.sorbate_data[it->second];
+}
+void SimulationControl::add_orientation_site_entry(const char *id, int site_idx) { sorbate_entry(*this, id).orientation_site = site_idx; }
+void SimulationControl::add_bond_length_entry(const char *id, double bond_length) { sorbate_entry(*this, id).bond_length = bond_length; }
+void SimulationControl::add_reduced_mass_entry(const char *id, double reduced_mass) { sorbate_entry(*this, id).reduced_mass = reduced_mass; }
+
+// NOTE the reference returns the INDEX of the type's metadata record, not the configured site (:2996-3004): with one sorbate type
+// configured the "orientation site" is atom 0 whatever the input said, with two types it is atom 0 for the first and atom 1 for the
+// second.  Reproduced, because the trajectories are compared with the reference's.
+int SimulationControl::get_orientation_site(const std::string &molecule_id) {
+	auto it = sorbate_data_index.find(molecule_id);
+	return it == sorbate_data_index.end() ? -1 : (int)it->second;
+}
+double SimulationControl::get_bond_length(const std::string &molecule_id) {
+	auto it = sorbate_data_index.find(molecule_id);
+	return it == sorbate_data_index.end() ? 0 : sorbate_data[it->second].bond_length;
+}
+double SimulationControl::get_reduced_mass(const std::string &molecule_id) {
+	auto it = sorbate_data_index.find(molecule_id);
+	return it == sorbate_data_index.end() ? -1.0 : sorbate_data[it->second].reduced_mass;
+}
+
+// Sum over the bead ring of |b_s - b_{s+1}|^2, b_s = bond_length * unit(COM -> handle site) of the moved molecule's image in bead
+// system s, in m^2 (:978-1039).  0 unless a site record and a positive bond length exist for the molecule's type.
+double SimulationControl::PI_orientational_mu_length2() {
+	const char *moleculeID = systems[0]->checkpoint->molecule_altered->moleculetype;
+	const int orientation_site = get_orientation_site(moleculeID);
+	const double bond_length = get_bond_length(moleculeID);
+	if (orientation_site < 0 || bond_length <= 0) return 0.0;
+	std::vector<double> bond(3 * (size_t)nSys);
+	for (int s = 0; s < nSys; s++) {
+		Molecule *m = systems[s]->checkpoint->molecule_altered;
+		m->update_COM();
+		Atom *a = m->atoms;
+		for (int site = 0; site != orientation_site; site++) a = a->next;
+		double x = a->pos[0] - m->com[0], y = a->pos[1] - m->com[1], z = a->pos[2] - m->com[2];
+		const double mag = std::sqrt(x * x + y * y + z * z);
+		if (mag != 0) { x = x / mag; y = y / mag; z = z / mag; } else x = y = z = 0;
+		bond[3 * s] = bond_length * x; bond[3 * s + 1] = bond_length * y; bond[3 * s + 2] = bond_length * z;
+	}
+	double diff = 0.0;
+	for (int i = 0; i < nSys; i++) {
+		const int j = (i + 1) % nSys;
+		const double dx = bond[3 * i] - bond[3 * j], dy = bond[3 * i + 1] - bond[3 * j + 1], dz = bond[3 * i + 2] - bond[3 * j + 2];
+		diff += dx * dx + dy * dy + dz * dz;
+	}
+	diff *= (ANGSTROM2METER * ANGSTROM2METER);
+	return diff;
+}
+
+void SimulationControl::PI_perturb_beads_orientations() {     // :1559-1572
+	const char *moleculeID = systems[0]->checkpoint->molecule_altered->moleculetype;
+	if (get_orientation_site(moleculeID) < 0 || get_bond_length(moleculeID) <= 0) return;
+	generate_orientation_configs();
+	apply_orientation_configs();
+}
+
+namespace {
+struct V3 { double x, y, z; };
+inline double dot(const V3 &a, const V3 &b) { return a.x * b.x + a.y * b.y + a.z * b.z; }
+inline double norm(const V3 &a) { return std::sqrt(dot(a, a)); }
+inline V3 unit(V3 a) { const double m = norm(a); if (m != 0) return {a.x / m, a.y / m, a.z / m}; return {0, 0, 0}; }
+inline V3 cross(const V3 &a, const V3 &b) { return {a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x}; }
+// Quaternion(axis, angle, AXIS_ANGLE_RADIAN).rotate(v) = (q v) q*   (src/Quaternion.cpp)
+inline V3 rotate_about(const V3 &axis, double angle, const V3 &v) {
+	double X = 0, Y = 0, Z = 0, W = 1;
+	const double mag = std::sqrt(axis.x * axis.x + axis.y * axis.y + axis.z * axis.z);
+	if (mag != 0.0) {
+		const double x = axis.x / mag, y = axis.y / mag, z = axis.z / mag, sn = std::sin(angle / 2.0);
+		X = x * sn; Y = y * sn; Z = z * sn; W = std::cos(angle / 2.0);
+	}
+	const double vw = 0;
+	const double tw = W * vw - X * v.x - Y * v.y - Z * v.z;
+	const double tx = W * v.x + X * vw + Y * v.z - Z * v.y;
+	const double ty = W * v.y - X * v.z + Y * vw + Z * v.x;
+	const double tz = W * v.z + X * v.y - Y * v.x + Z * vw;
+	const double cx = -X, cy = -Y, cz = -Z, cw = W;
+	return {tw * cx + tx * cw + ty * cz - tz * cy, tw * cy - tx * cz + ty * cw + tz * cx, tw * cz + tx * cy - ty * cx + tz * cw};
+}
+} // namespace
+
+// Rando order: three normals for bead 0's orientation, then per placed bead one uniform (C) and one uniform (beta)  (:1577-1680)
+void SimulationControl::generate_orientation_configs() {
+	const char *moleculeID = systems[0]->checkpoint->molecule_altered->moleculetype;
+	const double sorbate_reduced_mass = get_reduced_mass(moleculeID);
+	if (sorbate_reduced_mass < 0) throw missing_required_datum;
+	double sorbate_bond_length = get_bond_length(moleculeID);
+	if (sorbate_bond_length < 0) throw missing_required_datum;
+	sorbate_bond_length /= METER2ANGSTROM;
+	const double b2 = sorbate_bond_length * sorbate_bond_length;
+	const double u_kB_T = sorbate_reduced_mass * kB * sys.temperature;
+	V3 o0;
+	o0.x = Rando::rand_normal(); o0.y = Rando::rand_normal(); o0.z = Rando::rand_normal();      // Vector3D::randomize
+	o0 = unit(o0);
+	orientations[0] = o0.x; orientations[1] = o0.y; orientations[2] = o0.z;
+	const unsigned int n = (unsigned int)(orientations.size() / 3);
+	generate_orientation_configs(0, n, 2, n, b2, u_kB_T);
+}
+
+// Recursive bisection of the bead ring (Subramanian et al., J. Chem. Phys. 146, 094105): bead J halfway between I and K gets the
+// normalised mean of their orientations, tilted by alpha drawn from the spring distribution of stiffness K = 4 kh p cos(psi/2)
+// about an axis picked uniformly (beta) around that mean.
+void SimulationControl::generate_orientation_configs(unsigned int start, unsigned int end, unsigned int p, unsigned int numBeads, double b2, double ukT) {
+	const double two_PI = 2.0 * pi;
+	if (p > numBeads) return;
+	const unsigned int J_idx = (start + end) / 2, K_idx = (end == numBeads) ? 0 : end;
+	const V3 vec_I{orientations[3 * start], orientations[3 * start + 1], orientations[3 * start + 2]};
+	const V3 vec_K{orientations[3 * K_idx], orientations[3 * K_idx + 1], orientations[3 * K_idx + 2]};
+	const V3 bisector = unit({(vec_I.x + vec_K.x) / 2.0, (vec_I.y + vec_K.y) / 2.0, (vec_I.z + vec_K.z) / 2.0});
+	V3 vec_IK;
+	double psi_IK = 0;
+	if (p > 2) {
+		vec_IK = {vec_K.x - vec_I.x, vec_K.y - vec_I.y, vec_K.z - vec_I.z};
+		psi_IK = std::acos(dot(vec_I, vec_K) / (norm(vec_I) * norm(vec_K)));
+	} else {                                         // I == K: any vector orthogonal to the bisector
+		const V3 different_vec = unit({1 + bisector.x, 2 + bisector.y, -3 + bisector.z});
+		vec_IK = cross(different_vec, bisector);
+	}
+	const double C = Rando::rand();
+	const double lambda2 = h * h / (two_PI * ukT);
+	const double kh = pi * b2 / lambda2;
+	const double K = 4.0 * kh * p * std::cos(psi_IK * 0.5);
+	const double angle_A = std::acos(1.0 + (1.0 / K) * std::log(1.0 - C * (1.0 - std::exp(-2.0 * K))));
+	const double angle_B = Rando::rand() * two_PI;
+	const V3 vec_Beta = rotate_about(bisector, angle_B, vec_IK);
+	const V3 vec_J = rotate_about(vec_Beta, angle_A, bisector);
+	orientations[3 * J_idx] = vec_J.x; orientations[3 * J_idx + 1] = vec_J.y; orientations[3 * J_idx + 2] = vec_J.z;
+	if (p < numBeads) {
+		generate_orientation_configs(start, J_idx, p * 2, numBeads, b2, ukT);
+		generate_orientation_configs(J_idx, end, p * 2, numBeads, b2, ukT);
+	}
+}
+
+void SimulationControl::apply_orientation_configs() {         // :1684-1697
+	const int orientation_site = get_orientation_site(systems[0]->checkpoint->molecule_altered->moleculetype);
+	if (orientation_site < 0) return;
+	for (int s = 0; s < (int)systems.size(); s++) systems[s]->checkpoint->molecule_altered->orient(&orientations[3 * (size_t)s], orientation_site);
 }
 
 void SimulationControl::PI_perturb_bead_COMs_ENTIRE_SYSTEM() {      // :1402-1449
@@ -499,11 +651,17 @@ void SimulationControl::restore_PI_systems() {
 	// (the chain terms need nothing: they were last computed for exactly the coordinates that have just been put back)
 }
 
-double SimulationControl::PI_NVT_boltzmann_factor(double d_potential, double d_chain, int movetype) {   // :490-547
+// The orientational contribution uses the same factor as the COM chain's although its length carries no (reduced) mass — the
+// reference reads the reduced mass and does not use it (:520-524) — so with an orientation configured the factor is exp(-/+ ~1e26):
+// such a bead move is accepted exactly when the ring of bond vectors got shorter.  Reproduced as it is.
+double SimulationControl::PI_NVT_boltzmann_factor(double d_potential, double d_chain, double d_orient, int movetype) {   // :490-547
 	const double P = (double)nSys, T = sys.temperature;
 	if (movetype == MOVETYPE_PERTURB_BEADS) {
 		const double PIchain_2_K = (P * pi * pi * kB * T) / (2.0 * h * h);
-		const double potential_contrib = d_potential / T, PI_COM_contrib = d_chain * PIchain_2_K, PI_orientation_contrib = 0;
+		const double potential_contrib = d_potential / T, PI_COM_contrib = d_chain * PIchain_2_K;
+		double PI_orientation_contrib = 0;
+		if (sorbate_data_index.find(systems[0]->checkpoint->molecule_altered->moleculetype) != sorbate_data_index.end())
+			PI_orientation_contrib = d_orient * PIchain_2_K;
 		return exp(-potential_contrib - PI_COM_contrib - PI_orientation_contrib);
 	}
 	return exp(-d_potential / T);
@@ -522,12 +680,14 @@ bool SimulationControl::PI_nvt_mc(std::vector<System::step_record> *log) {     /
 	for (sys.step = 1; sys.step <= sys.numsteps; sys.step++) {
 		const double pot_init = pot_current;
 		const double chain_init = (move == MOVETYPE_PERTURB_BEADS) ? PI_chain_mass_length2() : 0;
+		const double orient_init = (move == MOVETYPE_PERTURB_BEADS) ? PI_orientational_mu_length2() : 0;
 		PI_make_move(move);
 		double pot_trial = PI_calculate_potential();
 		const double chain_trial = (move == MOVETYPE_PERTURB_BEADS) ? PI_chain_mass_length2() : 0;
+		const double orient_trial = (move == MOVETYPE_PERTURB_BEADS) ? PI_orientational_mu_length2() : 0;
 		double bf;
 		if (!std::isfinite(pot_trial)) { pot_trial = sys.observables->energy = MAXVALUE; bf = 0; }
-		else bf = PI_NVT_boltzmann_factor(pot_trial - pot_init, chain_trial - chain_init, move);
+		else bf = PI_NVT_boltzmann_factor(pot_trial - pot_init, chain_trial - chain_init, orient_trial - orient_init, move);
 		sys.nodestats->boltzmann_factor = bf;
 		int accepted;
 		if ((Rando::rand() < bf) && (systems[0]->iterator_failed == 0)) {

@@ -91,12 +91,30 @@ def _traj_pi_h2():
     return tmpl
 
 
+def _traj_pi_orient(dummy_first):
+    """Five-site H2, 8 molecules x 8 beads, with the orientational degree of freedom configured (sorbate_orientation_site /
+    sorbate_bondlength / sorbate_reducedMass, src/SimulationControl.cpp:306-339; bead orientations by recursive bisection,
+    src/SimulationControl.PathIntegral.cpp:1559-1697; orientational term of the acceptance, :978-1039, :490-547).  The reference
+    uses the INDEX of the type's metadata record as the handle site (src/SimulationControl.cpp:2996-3004): with H2 alone that is
+    site 0 (the massless-free centre site ON the COM: no rotation, zero bond vectors); with another type declared first it is
+    site 1 (an H2E site 0.371 A from the COM: the beads really turn)."""
+    def build():
+        tmpl, _ = W.pi_h2_cluster(n_side=2, P=8, L=30.0, five_site=True)
+        lines = ["sorbate_bondlength XX 1.0"] if dummy_first else []
+        lines += ["sorbate_orientation_site H2 1", "sorbate_bondlength H2 0.742", "sorbate_reducedMass H2 8.368618e-28"]
+        tmpl.opts.update({"seed": "17", "numsteps": "10000", "PI_trial_chain_length": "3", "rot_factor": "5.0", "_lines": lines})
+        return tmpl
+    return build
+
+
 TRAJ = {
     "traj_nvt_lj216": (_traj_lj, 0, 10000),
     "traj_nvt_kat_gs_ranked": (_traj_kat, 0, 10000),
     "traj_uvt_pore": (_traj_uvt, 0, 10000),
     "traj_pi_argon_dimer": (W.argon_dimer_pi, 8, 10000),
     "traj_pi_h2_27x8": (_traj_pi_h2, 8, 10000),
+    "traj_pi_h2_orient_site1": (_traj_pi_orient(True), 8, 10000),
+    "traj_pi_h2_orient_site0": (_traj_pi_orient(False), 8, 4000),
 }
 
 
