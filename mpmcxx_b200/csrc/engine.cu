@@ -146,7 +146,8 @@ struct mpmc_engine {
 	PairParams pp;
 	RadialTable erf_tab;
 	DevBuf<PairSeg> d_segs;
-	DevBuf<int> d_pmeta, d_item_seg, d_item_col, d_item_ctr, d_perm;
+	DevBuf<int> d_pmeta, d_item_ctr, d_perm;
+	DevBuf<PairItem> d_items;
 	int pair_ctr_start = 0;
 	DevBuf<double2> d_slj;
 	DevBuf<double4> d_spq, d_stage;
@@ -564,9 +565,14 @@ int prepare_pair_sweep(mpmc_engine *e) {
 		while (sgi + 1 < pp.nseg && e->segs[sgi + 1].col0 <= item_col[k]) sgi++;
 		item_seg[k] = sgi;
 	}
-	if ((rc2 = e->d_item_seg.ensure(K)) || (rc2 = e->d_item_col.ensure(K + 1)) || (rc2 = e->d_item_ctr.ensure(1))) return rc2;
-	CK(cudaMemcpyAsync(e->d_item_seg.p, item_seg.data(), K * sizeof(int), cudaMemcpyHostToDevice, e->stream));
-	CK(cudaMemcpyAsync(e->d_item_col.p, item_col.data(), (K + 1) * sizeof(int), cudaMemcpyHostToDevice, e->stream));
+	std::vector<PairItem> items(K);
+	for (int k = 0; k < K; k++) {
+		items[k] = PairItem{item_col[k], item_col[k + 1], item_seg[k], 0, e->segs.empty() ? PairSeg{0, 0, 0, 0, 0, 0} : e->segs[item_seg[k]], 0, 0};
+	}
+	// one item per warp and nothing left for the counter: the sweep neither reads nor advances it
+	pp.single_round = (e->B * K <= e->pair_grid * pair_warps(es)) ? 1 : 0;
+	if ((rc2 = e->d_items.ensure(K)) || (rc2 = e->d_item_ctr.ensure(1))) return rc2;
+	CK(cudaMemcpyAsync(e->d_items.p, items.data(), K * sizeof(PairItem), cudaMemcpyHostToDevice, e->stream));
 	e->pair_ctr_start = e->pair_grid * pair_warps(es);
 	CK(cudaMemcpyAsync(e->d_item_ctr.p, &e->pair_ctr_start, sizeof(int), cudaMemcpyHostToDevice, e->stream));
 	if ((rc2 = e->d_pmeta.ensure(std::max(n, 1))) || (rc2 = e->d_segs.ensure(std::max<size_t>(e->segs.size(), 1))) || (rc2 = e->d_perm.ensure(std::max(n, 1))) || (rc2 = e->d_iperm.ensure(std::max(n, 1))) ||
@@ -1169,8 +1175,8 @@ static int enqueue_energy(mpmc_engine *e, bool pi_fused = false) {
 			}
 			spq = e->d_spq.p;
 		}
-		if (es) k_pair_sweep<ORTHO, true><<<e->pair_grid, pair_warps(true) * 32, smem, e->stream>>>(spq, e->d_slj.p, e->d_pmeta.p, e->cap, B, e->d_segs.p, e->d_item_seg.p, e->d_item_col.p, e->pp, e->cell, e->d_erf_tab.p, e->d_partials.p, e->d_item_ctr.p);
-		else k_pair_sweep<ORTHO, false><<<e->pair_grid, pair_warps(false) * 32, smem, e->stream>>>(spq, e->d_slj.p, e->d_pmeta.p, e->cap, B, e->d_segs.p, e->d_item_seg.p, e->d_item_col.p, e->pp, e->cell, nullptr, e->d_partials.p, e->d_item_ctr.p);
+		if (es) k_pair_sweep<ORTHO, true><<<e->pair_grid, pair_warps(true) * 32, smem, e->stream>>>(spq, e->d_slj.p, e->d_pmeta.p, e->cap, B, e->d_segs.p, e->d_items.p, e->pp, e->cell, e->d_erf_tab.p, e->d_partials.p, e->d_item_ctr.p);
+		else k_pair_sweep<ORTHO, false><<<e->pair_grid, pair_warps(false) * 32, smem, e->stream>>>(spq, e->d_slj.p, e->d_pmeta.p, e->cap, B, e->d_segs.p, e->d_items.p, e->pp, e->cell, nullptr, e->d_partials.p, e->d_item_ctr.p);
 		LAUNCHED(e);
 	}
 	if (pi_fused) {
@@ -1322,7 +1328,7 @@ int mpmc_destroy(mpmc_engine *e) {
 	if (e->stream) cudaStreamSynchronize(e->stream);
 	e->d_posq.release(); e->d_lj.release(); e->d_alpha.release(); e->d_mass.release(); e->d_meta.release(); e->d_plist.release();
 	e->d_mobile_q.release(); e->d_frozen_q.release(); e->d_mol_start.release(); e->d_order.release(); e->d_flags.release();
-	e->d_segs.release(); e->d_item_seg.release(); e->d_item_col.release(); e->d_item_ctr.release(); e->d_pmeta.release(); e->d_perm.release(); e->d_slj.release(); e->d_spq.release(); e->d_stage.release(); e->d_erf_tab.release(); e->d_mol_mobile.release(); e->d_kvec.release(); e->d_partials.release();
+	e->d_segs.release(); e->d_items.release(); e->d_item_ctr.release(); e->d_pmeta.release(); e->d_perm.release(); e->d_slj.release(); e->d_spq.release(); e->d_stage.release(); e->d_erf_tab.release(); e->d_mol_mobile.release(); e->d_kvec.release(); e->d_partials.release();
 	e->d_sk_part.release(); e->d_S_mobile.release(); e->d_S_frozen.release(); e->d_S_all.release();
 	e->d_efs.release(); e->d_efi.release(); e->d_efic.release(); e->d_mu.release(); e->d_new_mu.release(); e->d_old_mu.release();
 	e->d_rrms.release(); e->d_rank.release(); e->d_acc.release(); e->d_dmu.release(); e->d_tri.release(); e->d_near.release(); e->d_gsctl.release(); e->d_gmeta.release(); e->d_nplist.release(); e->d_gpq.release(); e->d_cparts.release(); e->d_field_tab.release(); e->d_fp_list.release(); e->d_mp_list.release(); e->d_recount.release(); e->d_r2min_ff.release(); e->d_t2.release(); e->d_t2_cached.release(); e->d_cnt_ff.release(); e->d_mobile_sites.release(); e->d_frozen_sites.release(); e->d_allq.release(); e->d_com.release(); e->d_mol_mass.release(); e->d_chain.release();

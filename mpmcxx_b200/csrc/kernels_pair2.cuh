@@ -47,6 +47,11 @@ enum { kPairLJ = 1, kPairES = 2 };                      // what a block of pairs
 
 // i-group = sorted sites [i_begin, min(i_begin + 32, i_end)) meets sorted sites [j_begin, j_end), which need `kind`; col0 = columns before it
 struct PairSeg { int i_begin, i_end, j_begin, j_end, col0, kind; };
+// one item of the work list: columns [col, col_end) of the flattened blocks, starting in segment `seg`, whose record rides along so
+// that a warp knows which sites to fetch after ONE round trip to L2 instead of three dependent ones (a single-round sweep is one
+// item per warp: its prologue is not hidden by anything)
+struct __align__(16) PairItem { int col, col_end, seg, pad0; PairSeg first; int pad1, pad2; };
+static_assert(sizeof(PairItem) == 48, "PairItem is read as three 16-byte words");
 
 struct PairParams {
 	double t2_lj;       // largest r^2 with  sqrt(r^2) - 1e-12 < cutoff      (lj, :934)
@@ -57,8 +62,9 @@ struct PairParams {
 	unsigned h_adm, h_safe, h_tab_lo;   // high words of t2_adm, t2_safe, u_tab_lo (u_tab_lo sits on a word boundary)
 	int tab_base, tab_rows;
 	int ncols;          // columns per bead system
-	int items_per_bead; // items of one bead system; item k covers columns [item_col[k], item_col[k+1])
+	int items_per_bead; // items of one bead system
 	int nseg;
+	int single_round;   // every warp owns exactly one item: no counter traffic
 };
 
 // relative cost of one column (32 pairs) of each kind, ~ 2 x FP64 + other instructions of its inner loop: equal-cost items
@@ -99,7 +105,7 @@ __device__ __forceinline__ double r2_fast(const CellDev &c, double dx, double dy
 	return fma(iz, iz, fma(iy, iy, ix * ix));
 }
 
-struct PairAcc { double rd, re, in; int cnt; };
+struct PairAcc { double rd, re, in; int cnt; double rd1, re1; };
 
 // acc += v (and cnt += 1) under a predicate, as predicated instructions: the compiler's own if-conversion turns `if (p) acc += v`
 // into two selects and an unconditional add, three issue slots more per pair
@@ -208,10 +214,11 @@ __device__ __forceinline__ void pair_chunk(const CellDev &c, const PairParams &p
 				if (nearu[u]) { const double r = sqrt(r2[u]); ees[u] = s_pq[jj + u].w * erfc(c.ewald_alpha * r) / r; }
 		}
 		if (!(band[0] || band[1] || band[2] || band[3])) {
+			// even and odd columns into two accumulators each: the serial chain of dependent adds per pass is halved
 #pragma unroll
 			for (int u = 0; u < kPwCols; u++) {
-				if (LJ) add_if(a.rd, a.cnt, elj[u], in[u]);
-				if (ES) add_if(a.re, ees[u], in[u]);
+				if (LJ) add_if((u & 1) ? a.rd1 : a.rd, a.cnt, elj[u], in[u]);
+				if (ES) add_if((u & 1) ? a.re1 : a.re, ees[u], in[u]);
 			}
 		} else {
 			// next to a cutoff: decide on the reference's own rounding of r^2 (System.cpp:1228-1255), from the unfolded coordinates.
@@ -248,12 +255,12 @@ __device__ __forceinline__ void pair_chunk(const CellDev &c, const PairParams &p
 	}
 }
 
-// item_col[k], k <= items_per_bead: column boundaries of the items; ctr: the next item to hand out (gridDim.x * warps per CTA when the
-// kernel starts — k_reduce_partials puts it back)
+// item_list[k], k < items_per_bead: the work list; ctr: the next item to hand out (gridDim.x * warps per CTA when the kernel starts —
+// k_reduce_partials puts it back)
 template <bool ORTHO, bool ES>
 __global__ void __launch_bounds__(pair_warps(ES) * 32, pair_ctas(ES))
 k_pair_sweep(const double4 *__restrict__ spq, const double2 *__restrict__ lj, const int *__restrict__ pmeta, int stride, int nbeads,
-             const PairSeg *__restrict__ seg, const int *__restrict__ item_seg, const int *__restrict__ item_col, const PairParams pp, const CellDev c,
+             const PairSeg *__restrict__ seg, const PairItem *__restrict__ item_list, const PairParams pp, const CellDev c,
              const double *__restrict__ tab, PairPartial *__restrict__ partials, int *__restrict__ ctr) {
 	extern __shared__ __align__(16) double s_raw[];
 	double *s_tab = s_raw;
@@ -278,13 +285,15 @@ k_pair_sweep(const double4 *__restrict__ spq, const double2 *__restrict__ lj, co
 	for (int it = gw; it < items;) {
 		const int k = it / nbeads, bead = it - k * nbeads;      // k-major: the rounds of prepare_pair_sweep() follow each other
 		const double4 *pq = spq + (size_t)bead * stride;
-		int col = item_col[k];
-		const int col_end = item_col[k + 1];
-		PairAcc a = {0.0, 0.0, 0.0, 0};
+		const int4 w0 = reinterpret_cast<const int4 *>(item_list + k)[0], w1 = reinterpret_cast<const int4 *>(item_list + k)[1],
+		           w2 = reinterpret_cast<const int4 *>(item_list + k)[2];
+		int col = w0.x;
+		const int col_end = w0.y;
+		PairAcc a = {0.0, 0.0, 0.0, 0, 0.0, 0.0};
 		if (col < col_end) {
-			int s = item_seg[k];                             // segment that holds `col`
+			int s = w0.z;                                    // segment that holds `col`
+			PairSeg sg = {w1.x, w1.y, w1.z, w1.w, w2.x, w2.y};
 			while (col < col_end) {
-				const PairSeg sg = seg[s];
 				const int j0 = sg.j_begin + (col - sg.col0);
 				const int j1 = min(sg.j_end, j0 + (col_end - col));
 				int i = sg.i_begin + lane;
@@ -292,7 +301,7 @@ k_pair_sweep(const double4 *__restrict__ spq, const double2 *__restrict__ lj, co
 				double2 li = make_double2(0, 0);
 				int mi = kPmPad;
 				if (i < sg.i_end) { pi = fold_site<ORTHO>(c, pq[i]); li = lj[i]; mi = pmeta[i]; } else i = -1;
-				PairAcc sa = {0.0, 0.0, 0.0, 0};                 // this segment's sums, without the factors of site i
+				PairAcc sa = {0.0, 0.0, 0.0, 0, 0.0, 0.0};       // this segment's sums, without the factors of site i
 				// first chunk of the segment into registers; later chunks are fetched while the previous one is being swept
 				double4 npq = nan_site(); double2 nlj = make_double2(0, 0); int npm = kPmPad;
 				if (j0 + lane < j1) { npq = pq[j0 + lane]; nlj = lj[j0 + lane]; npm = pmeta[j0 + lane]; }
@@ -320,9 +329,10 @@ k_pair_sweep(const double4 *__restrict__ spq, const double2 *__restrict__ lj, co
 					}
 #undef MPMC_PAIR_CHUNK
 				}
-				a.rd = fma(li.x, sa.rd, a.rd); a.re = fma(pi.w, sa.re, a.re); a.in += sa.in; a.cnt += sa.cnt;
+				a.rd = fma(li.x, sa.rd + sa.rd1, a.rd); a.re = fma(pi.w, sa.re + sa.re1, a.re); a.in += sa.in; a.cnt += sa.cnt;
 				col += j1 - j0;
 				s++;
+				if (col < col_end) sg = seg[s];
 			}
 		}
 		// the four sums over the warp in one shrinking xor tree (6 shuffles instead of 20, fixed order): lanes 0, 8, 16, 24 end up
@@ -338,6 +348,7 @@ k_pair_sweep(const double4 *__restrict__ spq, const double2 *__restrict__ lj, co
 			v0 += __shfl_xor_sync(F, v0, 4); v0 += __shfl_xor_sync(F, v0, 2); v0 += __shfl_xor_sync(F, v0, 1);
 			if ((lane & 7) == 0) reinterpret_cast<double *>(partials + ((size_t)bead * pp.items_per_bead + k))[lane >> 3] = lane == 0 ? 4.0 * v0 : v0;
 		}
+		if (pp.single_round) break;
 		if (lane == 0) it = atomicAdd(ctr, 1);
 		it = __shfl_sync(0xffffffffu, it, 0);
 	}
