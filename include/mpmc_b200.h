@@ -184,6 +184,7 @@ enum {
 int mpmc_set_timing(mpmc_engine *e, int on);
 /* developer hook: SM-clock stamps of the Gauss-Seidel pipeline (solver and one updater CTA), see tools/gs_profile.py */
 int mpmc_debug_gs_profile(mpmc_engine *e, int enable, long long *out, int max_blocks, int *nblk);
+int mpmc_debug_pair_profile(mpmc_engine *e, int enable, long long *out, int max_warps, int *nwarps);   /* per-warp timeline of the pair sweep */
 int mpmc_debug_mark_moved(mpmc_engine *e, int first, int count);   /* bench hook: next evaluation treats these sites as moved */
 int mpmc_get_timing(mpmc_engine *e, double ms[MPMC_NUM_KERNEL_CLASSES], long long count[MPMC_NUM_KERNEL_CLASSES]);
 /* test hooks for the host-side numerics (no device needed).

@@ -196,6 +196,9 @@ struct mpmc_engine {
 	int ct_parts = 1, ct_part_len = 0;
 	DevBuf<long long> d_gsprof;
 	bool gs_prof_enabled = false;
+	DevBuf<long long> d_pairprof;
+	bool pair_prof_enabled = false;
+	int pair_prof_warps = 0;
 	int gs_prof_nblk = 0;
 	DevBuf<unsigned long long> d_rmin;
 	DevBuf<double> d_result;
@@ -1175,8 +1178,15 @@ static int enqueue_energy(mpmc_engine *e, bool pi_fused = false) {
 			}
 			spq = e->d_spq.p;
 		}
-		if (es) k_pair_sweep<ORTHO, true><<<e->pair_grid, pair_warps(true) * 32, smem, e->stream>>>(spq, e->d_slj.p, e->d_pmeta.p, e->cap, B, e->d_segs.p, e->d_items.p, e->pp, e->cell, e->d_erf_tab.p, e->d_partials.p, e->d_item_ctr.p);
-		else k_pair_sweep<ORTHO, false><<<e->pair_grid, pair_warps(false) * 32, smem, e->stream>>>(spq, e->d_slj.p, e->d_pmeta.p, e->cap, B, e->d_segs.p, e->d_items.p, e->pp, e->cell, nullptr, e->d_partials.p, e->d_item_ctr.p);
+		long long *pprof = nullptr;
+		if (e->pair_prof_enabled) {
+			e->pair_prof_warps = e->pair_grid * pair_warps(es);
+			if ((rc = e->d_pairprof.ensure((size_t)4 * e->pair_prof_warps))) return rc;
+			CK(cudaMemsetAsync(e->d_pairprof.p, 0, sizeof(long long) * 4 * (size_t)e->pair_prof_warps, e->stream));
+			pprof = e->d_pairprof.p;
+		}
+		if (es) k_pair_sweep<ORTHO, true><<<e->pair_grid, pair_warps(true) * 32, smem, e->stream>>>(spq, e->d_slj.p, e->d_pmeta.p, e->cap, B, e->d_segs.p, e->d_items.p, e->pp, e->cell, e->d_erf_tab.p, e->d_partials.p, e->d_item_ctr.p, pprof);
+		else k_pair_sweep<ORTHO, false><<<e->pair_grid, pair_warps(false) * 32, smem, e->stream>>>(spq, e->d_slj.p, e->d_pmeta.p, e->cap, B, e->d_segs.p, e->d_items.p, e->pp, e->cell, nullptr, e->d_partials.p, e->d_item_ctr.p, pprof);
 		LAUNCHED(e);
 	}
 	if (pi_fused) {
@@ -1328,7 +1338,7 @@ int mpmc_destroy(mpmc_engine *e) {
 	if (e->stream) cudaStreamSynchronize(e->stream);
 	e->d_posq.release(); e->d_lj.release(); e->d_alpha.release(); e->d_mass.release(); e->d_meta.release(); e->d_plist.release();
 	e->d_mobile_q.release(); e->d_frozen_q.release(); e->d_mol_start.release(); e->d_order.release(); e->d_flags.release();
-	e->d_segs.release(); e->d_items.release(); e->d_item_ctr.release(); e->d_pmeta.release(); e->d_perm.release(); e->d_slj.release(); e->d_spq.release(); e->d_stage.release(); e->d_erf_tab.release(); e->d_mol_mobile.release(); e->d_kvec.release(); e->d_partials.release();
+	e->d_segs.release(); e->d_items.release(); e->d_item_ctr.release(); e->d_pairprof.release(); e->d_pmeta.release(); e->d_perm.release(); e->d_slj.release(); e->d_spq.release(); e->d_stage.release(); e->d_erf_tab.release(); e->d_mol_mobile.release(); e->d_kvec.release(); e->d_partials.release();
 	e->d_sk_part.release(); e->d_S_mobile.release(); e->d_S_frozen.release(); e->d_S_all.release();
 	e->d_efs.release(); e->d_efi.release(); e->d_efic.release(); e->d_mu.release(); e->d_new_mu.release(); e->d_old_mu.release();
 	e->d_rrms.release(); e->d_rank.release(); e->d_acc.release(); e->d_dmu.release(); e->d_tri.release(); e->d_near.release(); e->d_gsctl.release(); e->d_gmeta.release(); e->d_nplist.release(); e->d_gpq.release(); e->d_cparts.release(); e->d_field_tab.release(); e->d_fp_list.release(); e->d_mp_list.release(); e->d_recount.release(); e->d_r2min_ff.release(); e->d_t2.release(); e->d_t2_cached.release(); e->d_cnt_ff.release(); e->d_mobile_sites.release(); e->d_frozen_sites.release(); e->d_allq.release(); e->d_com.release(); e->d_mol_mass.release(); e->d_chain.release();
@@ -1788,6 +1798,21 @@ int mpmc_debug_gs_profile(mpmc_engine *e, int enable, long long *out, int max_bl
 		// (optional third part, when the caller's buffer has room for it: per-chunk hand-over stamps, 16 chunks per block)
 		if (enable & 0x100) CK(cudaMemcpy(out + (size_t)16 * max_blocks, e->d_gsprof.p + (size_t)16 * e->gs_prof_nblk, sizeof(long long) * 16 * nb, cudaMemcpyDeviceToHost));
 		if (nblk) *nblk = nb;
+	}
+	return MPMC_OK;
+}
+
+// developer hook: per-warp timeline of the pair sweep.  enable -> the next evaluations record it; out != NULL -> copy the last one
+// back: 4 words per warp { entry, first sites loaded, last item summed (globaltimer ns), items done | SM << 32 }
+int mpmc_debug_pair_profile(mpmc_engine *e, int enable, long long *out, int max_warps, int *nwarps) {
+	CK(cudaSetDevice(e->dev));
+	e->pair_prof_enabled = enable != 0;
+	if (nwarps) *nwarps = e->pair_prof_warps;
+	if (out && e->d_pairprof.p && e->pair_prof_warps) {
+		{ int _rc = sync_stream(e); if (_rc) return _rc; }
+		const int nw = std::min(max_warps, e->pair_prof_warps);
+		CK(cudaMemcpy(out, e->d_pairprof.p, sizeof(long long) * 4 * nw, cudaMemcpyDeviceToHost));
+		if (nwarps) *nwarps = nw;
 	}
 	return MPMC_OK;
 }

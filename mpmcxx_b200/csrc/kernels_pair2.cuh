@@ -34,8 +34,11 @@
 
 namespace mpmc {
 
-// CTA shapes: 2 CTAs x 8 warps at <= 128 registers for both kernels (3 CTAs x 6 warps at 96 registers was measured for the LJ-only
-// kernel: 28.6 us instead of 26.2 on config 3)
+// CTA shapes: 2 CTAs x 8 warps at <= 128 registers for both kernels.  Measured alternatives on config 3 (tools/pair_timeline.py,
+// tools/pair3_probe.py): 3 CTAs x 6 warps at 96 registers 28.6 us instead of 26.2; one CTA of 16 warps 24.9 us against 24.7 — the
+// schedulers serve the CTA that arrived first on the SM before the later one (its warps end after 11 us, the other's after 17.5 us;
+// with one CTA all warps end after ~16.5 us), but two warps per scheduler already reach ~3/4 of the rate of four, so the even
+// finish buys nothing, and the Coulomb kernels were 3 % slower with it.
 __host__ __device__ constexpr int pair_warps(bool) { return 8; }
 __host__ __device__ constexpr int pair_ctas(bool) { return 2; }
 constexpr int kErfRow = (kTabDeg + 1) + kTabPad;        // doubles per row of the erfc table
@@ -104,6 +107,10 @@ __device__ __forceinline__ double r2_fast(const CellDev &c, double dx, double dy
 	}
 	return fma(iz, iz, fma(iy, iy, ix * ix));
 }
+
+__device__ __forceinline__ long long pair_gtime() { long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; }
+__device__ __forceinline__ long long pair_gtime_after(double a, double b) { long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t) : "d"(a), "d"(b)); return t; }
+__device__ __forceinline__ unsigned pair_smid() { unsigned r; asm volatile("mov.u32 %0, %%smid;" : "=r"(r)); return r; }
 
 struct PairAcc { double rd, re, in; int cnt; double rd1, re1; };
 
@@ -261,7 +268,7 @@ template <bool ORTHO, bool ES>
 __global__ void __launch_bounds__(pair_warps(ES) * 32, pair_ctas(ES))
 k_pair_sweep(const double4 *__restrict__ spq, const double2 *__restrict__ lj, const int *__restrict__ pmeta, int stride, int nbeads,
              const PairSeg *__restrict__ seg, const PairItem *__restrict__ item_list, const PairParams pp, const CellDev c,
-             const double *__restrict__ tab, PairPartial *__restrict__ partials, int *__restrict__ ctr) {
+             const double *__restrict__ tab, PairPartial *__restrict__ partials, int *__restrict__ ctr, long long *__restrict__ prof) {
 	extern __shared__ __align__(16) double s_raw[];
 	double *s_tab = s_raw;
 	const int tab_len = ES ? pp.tab_rows * kErfRow : 0;
@@ -277,6 +284,8 @@ k_pair_sweep(const double4 *__restrict__ spq, const double2 *__restrict__ lj, co
 	}
 	const int gw = blockIdx.x * pair_warps(ES) + warp;
 	const int items = nbeads * pp.items_per_bead;
+	// developer timeline (mpmc_debug_pair_profile): per warp { entry, first sites in registers, last item summed, items done | SM }
+	if (prof && lane == 0) { prof[4 * gw] = pair_gtime(); prof[4 * gw + 1] = 0; }
 	const double hx = 0.5 * fabs(c.b[0][0]), hy = 0.5 * fabs(c.b[1][1]), hz = 0.5 * fabs(c.b[2][2]);
 	if (lane < kPwCols) { s_pq[32 + lane] = nan_site(); s_lj[32 + lane] = make_double2(0, 0); s_pm[32 + lane] = kPmPad; }
 	if (ES) { stage_table_wait(); __syncthreads(); }
@@ -305,6 +314,7 @@ k_pair_sweep(const double4 *__restrict__ spq, const double2 *__restrict__ lj, co
 				// first chunk of the segment into registers; later chunks are fetched while the previous one is being swept
 				double4 npq = nan_site(); double2 nlj = make_double2(0, 0); int npm = kPmPad;
 				if (j0 + lane < j1) { npq = pq[j0 + lane]; nlj = lj[j0 + lane]; npm = pmeta[j0 + lane]; }
+				if (prof && lane == 0 && prof[4 * gw + 1] == 0) prof[4 * gw + 1] = pair_gtime_after(pi.x, npq.x);
 				for (int jc = j0; jc < j1; jc += 32) {
 					const int cnt = min(32, j1 - jc);
 					__syncwarp();
@@ -348,6 +358,7 @@ k_pair_sweep(const double4 *__restrict__ spq, const double2 *__restrict__ lj, co
 			v0 += __shfl_xor_sync(F, v0, 4); v0 += __shfl_xor_sync(F, v0, 2); v0 += __shfl_xor_sync(F, v0, 1);
 			if ((lane & 7) == 0) reinterpret_cast<double *>(partials + ((size_t)bead * pp.items_per_bead + k))[lane >> 3] = lane == 0 ? 4.0 * v0 : v0;
 		}
+		if (prof && lane == 0) { prof[4 * gw + 2] = pair_gtime(); prof[4 * gw + 3] += 1 + ((long long)pair_smid() << 32) * (prof[4 * gw + 3] == 0); }
 		if (pp.single_round) break;
 		if (lane == 0) it = atomicAdd(ctr, 1);
 		it = __shfl_sync(0xffffffffu, it, 0);

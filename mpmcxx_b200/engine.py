@@ -49,7 +49,7 @@ EXPORTS = ["mpmc_abi_version", "mpmc_last_error", "mpmc_device_count", "mpmc_cre
            "mpmc_num_sites", "mpmc_energy", "mpmc_energy_enqueue", "mpmc_energy_fetch", "mpmc_download_dipoles",
            "mpmc_download_rank_metric", "mpmc_pi_potential", "mpmc_pi_chain", "mpmc_nccl_get_unique_id", "mpmc_nccl_init", "mpmc_pi_potential_allreduce",
            "mpmc_pi_chain_allreduce", "mpmc_set_timing", "mpmc_get_timing", "mpmc_debug_gs_profile", "mpmc_stream", "mpmc_kernel_launches",
-           "mpmc_probe_fp64_peak", "mpmc_debug_radial_table", "mpmc_debug_cutoff_thresholds", "mpmc_pi_collective", "mpmc_debug_mark_moved"]
+           "mpmc_probe_fp64_peak", "mpmc_debug_radial_table", "mpmc_debug_cutoff_thresholds", "mpmc_pi_collective", "mpmc_debug_mark_moved", "mpmc_debug_pair_profile"]
 
 
 KERNEL_CLASSES = ["energy_total", "pair", "structure", "field_recip", "field_real", "rank", "dipole_sweep", "gs_sweep", "palmo", "gs_precompute"]
@@ -97,6 +97,7 @@ def lib():
         L.mpmc_debug_radial_table.argtypes = [C.c_int, C.c_double, C.c_double, C.c_double, _dp, C.c_int, _dp, C.c_void_p]
         L.mpmc_debug_cutoff_thresholds.argtypes = [C.c_double, _dp]
         L.mpmc_debug_mark_moved.argtypes = [vp, C.c_int, C.c_int]
+        L.mpmc_debug_pair_profile.argtypes = [vp, C.c_int, vp, C.c_int, C.POINTER(C.c_int)]
         _lib = L
     return _lib
 
