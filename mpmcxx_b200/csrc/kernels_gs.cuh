@@ -37,8 +37,9 @@ namespace mpmc {
 constexpr int kGsB = 64;                  // sites per solver block
 constexpr int kGsRows = 4;                // rows per updater chunk (one warp: 4 rows x 8 column lanes)
 constexpr int kGsColLanes = 32 / kGsRows;
-constexpr int kGsUpdWarps = 17, kGsUpdThreads = 32 * kGsUpdWarps;   // ONE updater CTA of 17 warps per SM: 140 SMs x 17 = 2380 warps for the 2300
-                                          // four-row chunks of 9200 polarizable sites (16 or 17 busy warps on every SM; 96 registers: five warps share a scheduler's 16 K)
+constexpr int kGsUpdWarps = 16, kGsUpdThreads = 32 * kGsUpdWarps;   // ONE updater CTA of 16 warps per SM (four per scheduler): 140 SMs x 16 = 2240
+                                          // warps for the 2300 four-row chunks of 9200 polarizable sites; the 60 surplus chunks are
+                                          // split by columns over four warps of one CTA, one per scheduler (gs_updater_body)
 constexpr int kGsThreads = 256;
 constexpr int kGsWarps = kGsThreads / 32;
 constexpr int kGsPipeThreads = 512;       // the solver/helper cluster: 192 x 2 threads walk, 512 per helper push
@@ -111,6 +112,23 @@ __device__ __forceinline__ void st_async_f64(unsigned remote_addr, double v, uns
 __device__ __forceinline__ void bulk_s2peer(unsigned remote_dst, unsigned local_src, unsigned bytes, unsigned remote_bar) {
 	asm volatile("fence.proxy.async.shared::cta;" ::: "memory");     // my generic-proxy stores to the source are visible to the copy engine
 	asm volatile("cp.async.bulk.shared::cluster.shared::cta.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(remote_dst), "r"(local_src), "r"(bytes), "r"(remote_bar) : "memory");
+}
+// plain 16-byte store into a peer CTA's shared memory; arrival on a peer's barrier that releases this thread's (and, behind a
+// __syncwarp, its warp's) earlier stores to the cluster; the matching wait
+__device__ __forceinline__ void st_peer_v2(unsigned remote_addr, double a, double b) {
+	asm volatile("st.shared::cluster.v2.f64 [%0], {%1, %2};" ::"r"(remote_addr), "d"(a), "d"(b) : "memory");
+}
+__device__ __forceinline__ void st_async_v2(unsigned remote_addr, double a, double b, unsigned remote_bar) {
+	asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v2.b64 [%0], {%1, %2}, [%3];" ::"r"(remote_addr), "l"(__double_as_longlong(a)),
+	             "l"(__double_as_longlong(b)), "r"(remote_bar) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_peer(unsigned remote_bar) {
+	asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(remote_bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait_cluster(unsigned bar, unsigned parity) {
+	unsigned ok = 0;
+	while (!ok)
+		asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }" : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
 }
 __device__ __forceinline__ void mbar_wait(unsigned bar, unsigned parity) {
 	unsigned ok;
@@ -288,6 +306,8 @@ __device__ __forceinline__ void gs_updater_body(double *s_raw, int cta, int U, c
 	// warp has finished with the buffer's previous panel, loads, and posts it; the others meanwhile work on what is already there.
 	double4 *ring = (double4 *)s_raw;                               // [kGsRing][2][kGsB]
 	__shared__ int s_ready, s_token, s_done[kGsRing];               // panels in the ring so far; loader token; warps finished with a buffer's panel
+	__shared__ double s_split[8][2][4][kGsRows * 3];                // split chunks: [group of four warps][flush][warp of the group][row][xyz]
+	__shared__ int s_split_cnt[8][2];
 	// (warp-major numbering: when there are more chunks than warps, the second chunks go one to each CTA instead of eight to a
 	// few CTAs — an SM with twice the work falls behind by a few thousand cycles per panel and stalls the solver at the end)
 	const int GW = U * (int)(blockDim.x >> 5), gwid = warp * U + cta;
@@ -296,15 +316,27 @@ __device__ __forceinline__ void gs_updater_body(double *s_raw, int cta, int U, c
 	for (int w = 0; w < (int)(blockDim.x >> 5); w++) nlive += w * U + cta < nchunks;
 	if (tid == 0) { s_ready = 0; s_token = 0; }
 	if (tid < kGsRing) s_done[tid] = nlive;                         // every buffer starts free
+	if (tid < 16) s_split_cnt[tid >> 1][tid & 1] = 0;
 	__syncthreads();
 	if (gwid >= nchunks) return;
+	// More chunks than warps.  With one chunk too many on an SM one scheduler would carry five warps' worth of contraction against four
+	// on the others and set the pace of the whole sweep (config 4: 2300 chunks for 2240 warps).  Up to one surplus chunk per four warps
+	// of a CTA is therefore SPLIT BY COLUMNS over those four warps — consecutive warps sit on the four schedulers — each taking a
+	// quarter of every panel's columns on top of its own chunk; their partial sums meet in shared memory, in a fixed order, when the
+	// chunk is written out.  Beyond that (larger systems) a warp simply owns a second whole chunk.
+	const int nwarp = (int)(blockDim.x >> 5), surplus = nchunks - GW;
+	const bool split = surplus > 0 && surplus <= U * (nwarp / 4) && nwarp <= 32;
+	const int grp = warp >> 2, gq = warp & 3;
+	constexpr int kIters = kGsB / kGsColLanes;                      // column iterations of a whole panel (8)
+	int nflush = 0;
 	// my rows (constant over the sweep) and their sums
 	double4 pr[kGsOwn];
 	int mr[kGsOwn], chs[kGsOwn], cblk[kGsOwn];
 	double sx[kGsOwn], sy[kGsOwn], sz[kGsOwn];
 #pragma unroll
 	for (int w = 0; w < kGsOwn; w++) {
-		const int ch = gwid + w * GW;
+		int ch = gwid + w * GW;
+		if (split && w > 0) ch = (w == 1 && grp < nwarp / 4 && grp * U + cta < surplus) ? GW + grp * U + cta : nchunks;
 		chs[w] = ch < nchunks ? ch : -1;
 		cblk[w] = ch / kChunksPerBlk;
 		const int pos = ch * kGsRows + r;
@@ -314,7 +346,8 @@ __device__ __forceinline__ void gs_updater_body(double *s_raw, int cta, int U, c
 		if (!on && chs[w] >= 0) mr[w] = -1;                 // a row past the end of a last, partial chunk
 		sx[w] = sy[w] = sz[w] = 0.0;
 	}
-	const bool more = gwid + kGsOwn * GW < nchunks;
+	const bool more = !split && gwid + kGsOwn * GW < nchunks;
+	const int it0 = split ? gq * (kIters / 4) : 0, it1 = split ? (gq + 1) * (kIters / 4) : kIters;   // slot 1's share of a panel's column iterations
 	// reduce a chunk's sums over the column lanes and add them to acc (one writer per row: a plain read-modify-write)
 	auto flush = [&](int w) {
 		double ax = sx[w], ay = sy[w], az = sz[w];
@@ -322,7 +355,34 @@ __device__ __forceinline__ void gs_updater_body(double *s_raw, int cta, int U, c
 		ax += __shfl_xor_sync(0xffffffffu, ax, 8); ay += __shfl_xor_sync(0xffffffffu, ay, 8); az += __shfl_xor_sync(0xffffffffu, az, 8);
 		ax += __shfl_xor_sync(0xffffffffu, ax, 16); ay += __shfl_xor_sync(0xffffffffu, ay, 16); az += __shfl_xor_sync(0xffffffffu, az, 16);
 		const int pos = chs[w] * kGsRows + r;
-		if (cl == 0 && pos < np) {
+		if (split && w == 1) {
+			// the four warps' column quarters, added in the order of the quarters by the group's first warp
+			double *mine = s_split[grp][nflush & 1][gq] + 3 * r;
+			if (cl == 0) { mine[0] = ax; mine[1] = ay; mine[2] = az; }
+			__threadfence_block();
+			__syncwarp();
+			if (gq != 0) { if (lane == 0) atomicAdd(&s_split_cnt[grp][nflush & 1], 1); }
+			else {
+				if (lane == 0) {
+					int spins = 0;
+					while (*(volatile int *)&s_split_cnt[grp][nflush & 1] < 3 && !ld_flag(&ctl->abort)) {
+						__nanosleep(20);
+						if (++spins > 20 * kGsWaitLimit) st_flag(&ctl->abort, 1);
+					}
+				}
+				__syncwarp();
+				__threadfence_block();
+				if (cl == 0 && pos < np) {
+					const double *q0 = s_split[grp][nflush & 1][0] + 3 * r;
+					double tx = q0[0], ty = q0[1], tz = q0[2];
+#pragma unroll
+					for (int q = 1; q < 4; q++) { tx += q0[q * kGsRows * 3]; ty += q0[q * kGsRows * 3 + 1]; tz += q0[q * kGsRows * 3 + 2]; }
+					double *a = acc + 3 * order[pos];
+					__stcg(a, __ldcg(a) + tx); __stcg(a + 1, __ldcg(a + 1) + ty); __stcg(a + 2, __ldcg(a + 2) + tz);
+				}
+			}
+			nflush++;
+		} else if (cl == 0 && pos < np) {
 			double *a = acc + 3 * order[pos];
 			__stcg(a, __ldcg(a) + ax); __stcg(a + 1, __ldcg(a + 1) + ay); __stcg(a + 2, __ldcg(a + 2) + az);
 		}
@@ -387,9 +447,12 @@ __device__ __forceinline__ void gs_updater_body(double *s_raw, int cta, int U, c
 			if (chs[w] < 0 || (chs[w] >= skip0 && chs[w] < skip1)) continue;       // warp-uniform
 			if (mr[w] != -1) {
 				double ax = 0, ay = 0, az = 0;
+				// slot 0 always sweeps the whole panel (compile-time bounds); slot 1 its share [it0, it1) of the column iterations
+				const int ib = w == 0 ? 0 : it0, ie = w == 0 ? kIters : it1;
 				if (EXPD) {
 #pragma unroll
-					for (int i = 0; i < kGsB / kGsColLanes; i += 2) {    // the whole panel, no bounds: columns past the end carry a zero change
+					for (int i = 0; i < kIters; i += 2) {                // no bounds on the columns: those past the end carry a zero change
+						if (w != 0 && (i < ib || i >= ie)) continue;
 						const int cc = cl + kGsColLanes * i;
 						const double4 p0 = w_col[cc], p1 = w_col[cc + kGsColLanes];
 						const double4 m0 = w_dm[cc], m1 = w_dm[cc + kGsColLanes];
@@ -398,7 +461,8 @@ __device__ __forceinline__ void gs_updater_body(double *s_raw, int cta, int U, c
 					}
 				} else {
 #pragma unroll
-					for (int i = 0; i < kGsB / kGsColLanes; i++) {
+					for (int i = 0; i < kIters; i++) {
+						if (w != 0 && (i < ib || i >= ie)) continue;
 						const int cc = cl + kGsColLanes * i;
 						double4 pc = w_col[cc];
 						const double4 dm = w_dm[cc];
@@ -412,10 +476,12 @@ __device__ __forceinline__ void gs_updater_body(double *s_raw, int cta, int U, c
 			// the last panel before the cluster takes these rows over: to memory, then the flag
 			if (blk == cblk[w] - kGsAhead - 1) {
 				flush(w);
-				__threadfence();
-				__syncwarp();
-				if (lane == 0) st_flag(applied + chs[w], gbase + blk + 1);
-				if (prof && lane == 0) prof[nblk * 16 + chs[w]] = gtime();      // when this chunk's rows were handed to the cluster
+				if (!(split && w == 1) || gq == 0) {                        // (a split chunk is written out by its group's first warp)
+					__threadfence();
+					__syncwarp();
+					if (lane == 0) st_flag(applied + chs[w], gbase + blk + 1);
+					if (prof && lane == 0) prof[nblk * 16 + chs[w]] = gtime();      // when this chunk's rows were handed to the cluster
+				}
 			}
 		}
 		if (pw) prof[(nblk + blk) * 8 + 2] = gtime();
@@ -461,6 +527,9 @@ __device__ __forceinline__ void gs_updater_body(double *s_raw, int cta, int U, c
 
 // columns of a 64-site panel a helper pushes: 2 hj + cs + 14 m  (cs = 0, 1 the thread's column slice)
 __host__ __device__ constexpr int gs_helper_cols(int hj) { int n = 0; for (int k = 0; k < kGsB; k++) n += (k % (2 * kGsHelpers)) / 2 == hj; return n; }
+// where helper hj's columns sit in the solver's outgoing panel (double4 units): the helpers' columns one after the other, each
+// helper's in the order (m, slice) = the order its threads walk them, so that ONE bulk copy per helper delivers them
+__host__ __device__ constexpr int gs_helper_first(int hj) { int n = 0; for (int h = 0; h < hj; h++) n += gs_helper_cols(h); return n; }
 
 template <bool ORTHO, bool EXPD>
 __global__ void __cluster_dims__(kGsCluster, 1, 1) __launch_bounds__(kGsPipeThreads, 1)
@@ -491,12 +560,16 @@ k_gs_pipeline(const double4 *__restrict__ gpq, const int *__restrict__ gmeta, co
 		double *s_site0 = s_mat + kGsMat;                              // [2][kGsSiteCols][kGsB], buffer = block & 1
 		double *s_in = s_raw + kGsSolIn;                               // [kGsHelpers][kGsN] what the helpers pushed into the rows of the block about to be solved
 		unsigned long long *s_bars = (unsigned long long *)(s_raw + kGsSolBar);
-		double4 *s_dm = (double4 *)(s_raw + kGsSolBar + 2);            // [kGsB] dmu of the block being walked
+		double4 *s_dm = (double4 *)(s_raw + kGsSolBar + 2);            // [kGsB] the outgoing panel, grouped by owning helper (gs_helper_first)
 		double *s_rho = (double *)(s_dm + kGsB);                       // [kGsN] right-hand side of the block being walked
 		double *s_tpart = s_rho + kGsN;                                // [kGsTiles][32] per-tile partial dot products
 		int *s_idx = (int *)(s_tpart + kGsTiles * kGsTileDim);         // [2][kGsB] site ids of this block / the next block
 		volatile int *s_clk = s_idx;                                   // any shared word: anchors the profiling clock reads behind the barriers
 		constexpr int kPublisherWarp = 12, kLoaderWarp = 13;
+		constexpr int kProductWarps = kGsPipeThreads / 32 - 2;       // every warp but the publisher and the loader
+		// named barriers: 1 = the product warps among themselves (right-hand side complete, product complete), 2 = top of the block
+		// (all but the publisher), 3 = end of the block (the product warps + the publisher), 4 = the outgoing panel is in shared memory
+		// (the row threads arrive, the publisher waits)
 		auto load_cols = [&](int blk, int m) {                     // site id and site columns of row m (all but the running contraction)
 			const int pos = blk * kGsB + m;
 			const bool on = pos < np;
@@ -515,24 +588,51 @@ k_gs_pipeline(const double4 *__restrict__ gpq, const int *__restrict__ gmeta, co
 			double *s_site = s_site0 + (blk & 1) * kGsSiteCols * kGsB;
 			for (int q = 0; q < 3; q++) s_site[(7 + q) * kGsB + m] = on ? __ldcg(acc + 3 * s + q) : 0.0;
 		};
-		const unsigned bar_in = smem_u32(&s_bars[0]), bar = smem_u32(&s_bars[1]);
+		// the inverse arrives in three pieces of seven tiles, each on its own barrier: the product starts on the tiles of a piece as soon
+		// as that piece is there (172 KB take ~3 k cycles through this SM's port; waiting for all of it cost ~0.7 k cycles per block)
+		unsigned long long *s_bars_m = (unsigned long long *)(s_raw + kGsSolverDoubles - 4);
+		const unsigned bar_in = smem_u32(&s_bars[0]);
+		const unsigned bar_m[3] = {smem_u32(&s_bars[1]), smem_u32(&s_bars_m[0]), smem_u32(&s_bars_m[1])};
+		constexpr int kPieceTiles = kGsTiles / 3;
+		static_assert(kPieceTiles * 3 == kGsTiles, "three equal pieces");
 		constexpr unsigned kMatBytes = sizeof(double) * kGsMat, kMatPiece = kMatBytes / 3;
 		static_assert(kMatPiece % 16 == 0, "bulk copies move multiples of 16 bytes");
-		auto fetch_inverse = [&](int blk) {                        // one thread: the whole inverse of block blk -> s_mat, completion on the barrier
-			mbar_expect_tx(bar, kMatBytes);
+		auto fetch_inverse = [&](int blk) {                        // one thread: the whole inverse of block blk -> s_mat, completion on the pieces' barriers
 			const char *src = (const char *)(tri + (size_t)blk * kGsMat);
-			for (int q = 0; q < 3; q++) bulk_g2s(smem_u32(s_mat) + q * kMatPiece, src + q * kMatPiece, kMatPiece, bar);
+			for (int q = 0; q < 3; q++) {
+				mbar_expect_tx(bar_m[q], kMatPiece);
+				bulk_g2s(smem_u32(s_mat) + q * kMatPiece, src + q * kMatPiece, kMatPiece, bar_m[q]);
+			}
 		};
-		// my component's place in its helper's panel buffer: column site wm belongs to helper (wm % 14) / 2
+		// my component's place in the outgoing panel: column site wm belongs to helper (wm % 14) / 2, as its column 2 (wm / 14) + (wm % 2)
 		const int wm = tid / 3, wq = tid - 3 * wm;                     // my site of the block and component (threads 0..191)
-		unsigned r_dm = 0, r_bar = 0;
+		int out_at = 0;
 		if (tid < kGsN) {
-			const unsigned owner = 1 + (wm % (2 * kGsHelpers)) / 2;
-			r_dm = map_to_cta(smem_u32(s_raw + kGsHelpDm + 4 * wm + wq), owner);
-			r_bar = map_to_cta(smem_u32(s_raw + kGsHelpBar), owner);
+			const int w14 = wm % (2 * kGsHelpers), owner = w14 / 2;
+			out_at = 4 * (gs_helper_first(owner) + 2 * (wm / (2 * kGsHelpers)) + (w14 & 1)) + wq;
 		}
+		// the publisher warp's lanes 0..6 deliver: one bulk copy each, shared -> the helper's panel buffer, signalling the helper's barrier
+		// (192 eight-byte st.async took the row warps ~650 cycles per block to issue)
+		// Warp 15 delivers the panel: 2 KB as four 16-byte st.async per lane into the helpers' panel buffers, each signalling the owning
+		// helper's barrier.  (192 eight-byte st.async from the row threads reached the helpers ~1.3 k cycles after the product and kept
+		// the row warps busy for ~650 of them; a bulk copy per helper took 640 ns to land; plain peer stores followed by a
+		// release.cluster arrival took 1.3 us.)
+		unsigned r_unit[4] = {0, 0, 0, 0}, r_ubar[4] = {0, 0, 0, 0};
+		constexpr int kSenderWarp = 15;                             // a product-only warp with no global stores of its own in flight
+		if (warp == kSenderWarp) {
+#pragma unroll
+			for (int k = 0; k < 4; k++) {
+				const int u = lane + 32 * k, d4 = u >> 1;
+				int h = 0;
+				while (h + 1 < kGsHelpers && gs_helper_first(h + 1) <= d4) h++;
+				r_unit[k] = map_to_cta(smem_u32(s_raw + kGsHelpDm) + (unsigned)((d4 - gs_helper_first(h)) * 32 + (u & 1) * 16), 1 + h);
+				r_ubar[k] = map_to_cta(smem_u32(s_raw + kGsHelpBar), 1 + h);
+			}
+		}
+		if (tid < kGsB) s_dm[tid] = make_double4(0.0, 0.0, 0.0, 0.0);
 		if (tid == 0) {
-			mbar_init(bar_in, 1); mbar_init(bar, 1);
+			mbar_init(bar_in, 1);
+			for (int q = 0; q < 3; q++) mbar_init(bar_m[q], 1);
 			asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
 		}
 		if (tid < kGsB) { load_cols(0, tid); load_acc(0, tid); }
@@ -589,6 +689,18 @@ k_gs_pipeline(const double4 *__restrict__ gpq, const int *__restrict__ gmeta, co
 				}
 				continue;
 			}
+			if (warp == kPublisherWarp) {
+				// the publisher: waits for the block's write-back, sends the panel to the helpers (they may be waiting for it already), then
+				// publishes it for the updaters: the change of every dipole of the block, then the flag — after the write-back of the
+				// block's rows: the updaters add this panel to those rows too.  (The end-of-block barrier makes the row threads' stores part
+				// of what this fence orders.)  It takes no part in the product: its fence lasts ~1 us, and while it shared the product's
+				// barriers every block waited ~0.5 k cycles for it.
+				asm volatile("bar.sync 3, %0;" :: "n"((kProductWarps + 1) * 32) : "memory");
+				__threadfence();
+				__syncwarp();
+				if (lane == 0) st_flag(&ctl->solved, gbase + blk + 1);
+				continue;
+			}
 			// (B) the walk: rhs = alpha E_s - mu_old - alpha acc, dmu = rhs + X rhs (k_gs_inverse): a 192 x 192 triangular matrix-vector
 			// product cut in 21 tiles of 32 x 32, one or two tiles per warp, lane = row; every load has a compile-time offset (the
 			// first version walked the packed triangle with ~100 instructions of address arithmetic per 12 FMAs: 3 000 cycles)
@@ -605,15 +717,15 @@ k_gs_pipeline(const double4 *__restrict__ gpq, const int *__restrict__ gmeta, co
 				rhs_r = fma(-al_r, a_r, fma(al_r, es_r, -mo_r));
 				s_rho[tid] = rhs_r;
 			}
-			mbar_wait(bar, blk & 1);                                       // the inverse has landed (every reader observes the phase itself)
-			asm volatile("bar.sync 1, %0;" :: "n"(kGsPipeThreads - 32) : "memory");
+			asm volatile("bar.sync 1, %0;" :: "n"(kProductWarps * 32) : "memory");   // the right-hand side is complete
 			if (prof && tid == 0) prof[blk * 8 + 1] = clock_after(s_clk);
 			{
-				const int wslot = warp < kLoaderWarp ? warp : warp - 1;    // 15 warps take part (the loader does not)
-				for (int t = wslot; t < kGsTiles; t += kGsPipeThreads / 32 - 1) {
+				const int wslot = warp < kPublisherWarp ? warp : warp - 2;   // 14 warps take part: seven of them take two tiles
+				for (int t = wslot; t < kGsTiles; t += kProductWarps) {
 					int I = 0;
 					while (gs_tile(I + 1, 0) <= t) I++;
 					const int J = t - gs_tile(I, 0);
+					mbar_wait(bar_m[t / kPieceTiles], blk & 1);                // the tile's piece has landed (every reader observes the phase itself)
 					const double *xt = s_mat + t * (kGsTileDim * kGsTileDim) + lane;
 					const double2 *rh = reinterpret_cast<const double2 *>(s_rho + kGsTileDim * J);
 					double d0 = 0.0, d1 = 0.0, d2 = 0.0, d3 = 0.0;
@@ -629,14 +741,37 @@ k_gs_pipeline(const double4 *__restrict__ gpq, const int *__restrict__ gmeta, co
 				}
 				if (prof && tid == 191) prof[blk * 8 + 6] = clock64();
 			}
-			asm volatile("bar.sync 1, %0;" :: "n"(kGsPipeThreads - 32) : "memory");
-			if (tid == (kLoaderWarp + 1) * 32 && blk + 1 < nblk) fetch_inverse(blk + 1);   // s_mat is free: every warp is past the product
+			asm volatile("bar.sync 1, %0;" :: "n"(kProductWarps * 32) : "memory");
+			if (warp == kSenderWarp) {
+				// the panel to the helpers, as soon as the row threads have put it into s_dm (this warp has signed the end-of-block barrier
+				// off already: see the fetching warp below)
+				asm volatile("bar.arrive 3, %0;" :: "n"((kProductWarps + 1) * 32) : "memory");
+				asm volatile("bar.sync 4, %0;" :: "n"(kGsN + 32) : "memory");
+				if (blk + 1 < nblk) {
+#pragma unroll
+					for (int k = 0; k < 4; k++) {
+						const double2 v = reinterpret_cast<const double2 *>(s_dm)[lane + 32 * k];
+						st_async_v2(r_unit[k], v.x, v.y, r_ubar[k]);
+					}
+				}
+				__syncwarp();
+				continue;
+			}
+			if (warp == kLoaderWarp + 1) {
+				// s_mat is free: every warp is past the product.  This warp owns no row: it signs the end-of-block barrier off at once and
+				// issues the three bulk copies behind it, so that nobody waits for their issue (the next barrier it meets is the next
+				// block's `bar.sync 2`, which the others reach only after this block's barrier has completed)
+				asm volatile("bar.arrive 3, %0;" :: "n"((kProductWarps + 1) * 32) : "memory");
+				if (lane == 0 && blk + 1 < nblk) fetch_inverse(blk + 1);
+				__syncwarp();
+				continue;
+			}
 			if (tid < kGsN) {
 				double d = rhs_r;                                              // + (X rhs)_row: the row block's tiles in a fixed order
 				const int I = tid / kGsTileDim;
 				for (int J = 0; J <= I; J++) d += s_tpart[gs_tile(I, J) * kGsTileDim + (tid & (kGsTileDim - 1))];
-				// the panel, component by component, to the helper that pushes this column (it may be waiting for it already)
-				if (blk + 1 < nblk) st_async_f64(r_dm, d, r_bar);
+				reinterpret_cast<double *>(s_dm)[out_at] = d;              // the panel for the helpers, grouped by owner
+				asm volatile("bar.arrive 4, %0;" :: "n"(kGsN + 32) : "memory");      // ... which the publisher warp sends off while the rows are written back
 				if (wm < cnt) __stcg(dmu + 3 * (base + wm) + wq, d);               // for the updaters (the publisher warp fences and raises the flag)
 				// contract_dipoles: mu = alpha (E_s + ef_induced), ef_induced = -acc at the moment of the update  (:3583-3592):
 				// mu = mu_old + dmu; ef_induced is recovered from mu after the sweep (k_gs_efi)
@@ -648,16 +783,8 @@ k_gs_pipeline(const double4 *__restrict__ gpq, const int *__restrict__ gmeta, co
 					__stcg(acc + 3 * sidx + wq, a_r);                      // what the cluster knows of this row; the updaters add the panel itself
 				}
 			}
-			asm volatile("bar.sync 1, %0;" :: "n"(kGsPipeThreads - 32) : "memory");
+			asm volatile("bar.sync 3, %0;" :: "n"((kProductWarps + 1) * 32) : "memory");
 			if (prof && tid == 0) { prof[blk * 8 + 2] = clock_after(s_clk); prof[(nblk + blk) * 8 + 6] = gtime(); }
-			if (warp == kPublisherWarp) {
-				// publish the panel for the updaters: the change of every dipole of the block, then the flag (after the write-back
-				// of the block's rows above: the updaters add this panel to those rows too)
-				// (the barrier above makes the row threads' stores of the panel and of the rows' write-back part of what this fence orders)
-				__threadfence();
-				__syncwarp();
-				if (lane == 0) st_flag(&ctl->solved, gbase + blk + 1);
-			}
 		}
 		__syncthreads();
 		cluster.sync();                                            // nothing of the cluster is in flight towards my shared memory any more
@@ -672,7 +799,7 @@ k_gs_pipeline(const double4 *__restrict__ gpq, const int *__restrict__ gmeta, co
 		double *h_part = s_raw + kGsHelpPart;                      // [2 column slices][kGsAhead * kGsB][3]
 		const unsigned bar_p = smem_u32(s_raw + kGsHelpBar);
 		const unsigned r_in = map_to_cta(smem_u32(s_raw + kGsSolIn + hj * kGsN), 0), r_bar_in = map_to_cta(smem_u32(s_raw + kGsSolBar), 0);
-		const unsigned panel_bytes = (unsigned)(sizeof(double) * 3 * gs_helper_cols(hj));
+		const unsigned panel_bytes = (unsigned)(sizeof(double4) * gs_helper_cols(hj));   // my columns of the panel, in the order (m, slice)
 		for (int q = tid; q < kGsAhead * kGsN; q += kGsPipeThreads) h_acc[q] = 0.0;
 		if (tid < kGsB) h_dm[tid] = make_double4(0.0, 0.0, 0.0, 0.0);
 		if (tid == 0) { mbar_init(bar_p, 1); asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
@@ -713,7 +840,7 @@ k_gs_pipeline(const double4 *__restrict__ gpq, const int *__restrict__ gmeta, co
 			double ax = 0.0, ay = 0.0, az = 0.0;
 #pragma unroll
 			for (int m = 0; m < kCols; m++) {
-				const double4 d = h_dm[min(2 * hj + cs + 2 * kGsHelpers * m, kGsB - 1)];      // (xx yy) (zz xy) (xz yz); zero tensor where there is no column
+				const double4 d = h_dm[2 * m + cs];                        // (xx yy) (zz xy) (xz yz); zero tensor (and a zero entry) where there is no column
 				ax = fma(t[m][0].x, d.x, fma(t[m][1].y, d.y, fma(t[m][2].x, d.z, ax)));
 				ay = fma(t[m][1].y, d.x, fma(t[m][0].y, d.y, fma(t[m][2].y, d.z, ay)));
 				az = fma(t[m][2].x, d.x, fma(t[m][2].y, d.y, fma(t[m][1].x, d.z, az)));

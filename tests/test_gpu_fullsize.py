@@ -80,14 +80,23 @@ def test_config4_full_size_against_oracle(solver):
     e.close()
 
 
-def test_config4_two_kernel_pipeline_equals_single_launch_fallback():
-    """The solver-cluster + updater-kernel pipeline and the single-launch fallback (MPMC_GS_FUSED=1, what ncu profiles) give the
-    same bits at N = 10 000: every row receives its panels in the same order whatever the timing."""
+def test_config4_two_kernel_pipeline_is_reproducible_and_agrees_with_single_launch_fallback():
+    """The solver-cluster + updater-kernel pipeline gives the same BITS on every run at N = 10 000 — every row receives its panels
+    in a fixed order whatever the timing — and agrees with the single-launch fallback (MPMC_GS_FUSED=1, what ncu profiles) to
+    rounding: the fallback runs on a different grid, and the 60 chunks of rows the pipeline splits by columns over four warps
+    (kernels_gs.cuh, gs_updater_body) add their column sums in a different association there."""
     from mpmcxx_b200 import workloads as W
     s = W.h2_framework(solver=W.SOLVER_GS_RANKED_PALMO)
     e = _eng().Engine(s)
     a, da = e.energy(), e.dipoles()
     e.close()
+    e = _eng().Engine(s)
+    a2, da2 = e.energy(), e.dipoles()
+    a3 = e.energy()
+    e.close()
+    assert a == a2 == a3
+    for k in ("mu", "ef_induced", "ef_induced_change"):
+        assert np.array_equal(da[k], da2[k]), k
     os.environ["MPMC_GS_FUSED"] = "1"
     try:
         f = _eng().Engine(s)
@@ -95,9 +104,12 @@ def test_config4_two_kernel_pipeline_equals_single_launch_fallback():
         f.close()
     finally:
         del os.environ["MPMC_GS_FUSED"]
-    assert a == b
+    assert a["polarization_iterations"] == b["polarization_iterations"] and a["iterator_failed"] == b["iterator_failed"]
+    for k in ("polarization_energy", "energy"):
+        assert abs(a[k] - b[k]) <= 1e-12 * abs(b[k]), k
     for k in ("mu", "ef_induced", "ef_induced_change"):
-        assert np.array_equal(da[k], db[k]), k
+        scale = np.abs(db[k]).max()
+        assert np.abs(da[k] - db[k]).max() <= 1e-12 * scale, k
 
 
 @pytest.mark.parametrize("ncell,n_h2", [(12, 86), (10, 123)])
