@@ -76,7 +76,7 @@ constexpr int kGsRing = 4;                // panels an updater CTA keeps in shar
 constexpr size_t kGsUpdaterDoubles = (size_t)kGsRing * 8 * kGsB;
 constexpr size_t kGsUpdaterSmemBytes = sizeof(double) * kGsUpdaterDoubles;
 
-__device__ int g_gs_debug = 0;            // developer switch (mpmc_debug_gs_profile enable bits 1..): 2 = pushers idle, 4 = no rolling copy
+__device__ int g_gs_debug = 0;            // developer switch (mpmc_debug_gs_profile enable bits 1..): 2 = pushers idle, 4 = no rolling copy, 8 = surplus chunks not split
 struct GsCtl { int solved; int abort; int pad[30]; };   // followed in memory by int applied[nchunks]
 // The flags are never cleared between sweeps: every launch gets a generation number and counts from `gbase` = generation << 16
 // (solved = gbase + blocks solved, applied[chunk] = gbase + panels in memory), so whatever the previous sweep left compares as "not
@@ -325,7 +325,7 @@ __device__ __forceinline__ void gs_updater_body(double *s_raw, int cta, int U, c
 	// quarter of every panel's columns on top of its own chunk; their partial sums meet in shared memory, in a fixed order, when the
 	// chunk is written out.  Beyond that (larger systems) a warp simply owns a second whole chunk.
 	const int nwarp = (int)(blockDim.x >> 5), surplus = nchunks - GW;
-	const bool split = surplus > 0 && surplus <= U * (nwarp / 4) && nwarp <= 32;
+	const bool split = !(g_gs_debug & 8) && surplus > 0 && surplus <= U * (nwarp / 4) && nwarp <= 32;   // (developer switch 8: never split)
 	const int grp = warp >> 2, gq = warp & 3;
 	constexpr int kIters = kGsB / kGsColLanes;                      // column iterations of a whole panel (8)
 	int nflush = 0;

@@ -84,7 +84,8 @@ def test_config4_two_kernel_pipeline_is_reproducible_and_agrees_with_single_laun
     """The solver-cluster + updater-kernel pipeline gives the same BITS on every run at N = 10 000 — every row receives its panels
     in a fixed order whatever the timing — and agrees with the single-launch fallback (MPMC_GS_FUSED=1, what ncu profiles) to
     rounding: the fallback runs on a different grid, and the 60 chunks of rows the pipeline splits by columns over four warps
-    (kernels_gs.cuh, gs_updater_body) add their column sums in a different association there."""
+    (kernels_gs.cuh, gs_updater_body) add their column sums in a different association there.  With that split switched off the two
+    are equal bit for bit."""
     from mpmcxx_b200 import workloads as W
     s = W.h2_framework(solver=W.SOLVER_GS_RANKED_PALMO)
     e = _eng().Engine(s)
@@ -104,6 +105,15 @@ def test_config4_two_kernel_pipeline_is_reproducible_and_agrees_with_single_laun
         f.close()
     finally:
         del os.environ["MPMC_GS_FUSED"]
+    # with the column split switched off (developer switch 8) every row is summed exactly as in the fallback: the two-kernel
+    # pipeline — solver cluster, updater kernel, flags across kernels — must then give the fallback's bits
+    e = _eng().Engine(s)
+    _eng()._ck(_eng().lib().mpmc_debug_gs_profile(e.h, 8, None, 0, None))
+    c, dc = e.energy(), e.dipoles()
+    e.close()
+    assert c == b
+    for k in ("mu", "ef_induced", "ef_induced_change"):
+        assert np.array_equal(dc[k], db[k]), k
     assert a["polarization_iterations"] == b["polarization_iterations"] and a["iterator_failed"] == b["iterator_failed"]
     for k in ("polarization_energy", "energy"):
         assert abs(a[k] - b[k]) <= 1e-12 * abs(b[k]), k
