@@ -602,7 +602,7 @@ def run_pi(args, embedded=False):
     kms = pk[0] / max(pk[1], 1)
     flop = (FLOP_PER_ES_PAIR if five else FLOP_PER_LJ_PAIR) * out1["n_pair_evals"] * (hi - lo)
     ach = flop / (kms * 1e-3) / 1e12 if kms > 0 else float("nan")
-    res = {"metric": "mc_moves_per_sec", "value": args.steps / t_dev, "unit": "sweeps/s (one potential sweep over all beads; a rejected move costs one, an accepted move two)",
+    res = {"metric": "mc_moves_per_sec", "value": args.steps / t_dev, "unit": "sweeps/s (one potential sweep over all beads = one trial move; the reference evaluates an accepted move a second time with unchanged coordinates — the host mirror reuses the answer it already has)",
            "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
            "ms_per_step": 1e3 * t_dev / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
            "config": {"workload": "config5: path-integral H2 cluster, 512 molecules x %d beads, %s, beads sharded %d per GPU, one exchange of 4 doubles per sweep (see `collective`)"

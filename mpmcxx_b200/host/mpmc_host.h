@@ -242,6 +242,8 @@ private:
 	std::vector<double> pi_chain_term;              // per molecule: PI_chain_mass_length2 of its chain, as last computed
 	std::vector<int> pi_chain_stale;                // list positions whose term must be recomputed
 	void pi_index_build();
+	double pi_last_means[4] = {0, 0, 0, 0};         // the last sweep's bead means (reused when nothing has moved since)
+	bool pi_have_means = false;
 };
 
 } // namespace mpmc_host

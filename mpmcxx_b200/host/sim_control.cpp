@@ -225,6 +225,7 @@ double SimulationControl::PI_calculate_potential() {
 	const int b_lo = (int)((long long)P * rank / nranks), b_hi = (int)((long long)P * (rank + 1) / nranks), PL = b_hi - b_lo;
 	if (PL < 1) throw invalid_MPI_size_for_PI;
 	int rc;
+	bool nothing_moved = false;
 	if (!pi_gpu) {
 		const int n = systems[0]->countNatoms();
 		std::vector<double> pos, q, al, ep, sg, ms;
@@ -249,6 +250,7 @@ double SimulationControl::PI_calculate_potential() {
 		if (nranks > 1 && (rc = mpmc_nccl_init(pi_gpu, nccl_id, rank, nranks))) throw rc;
 		pi_dirty.clear();
 	} else {
+		nothing_moved = pi_dirty.empty();
 		std::sort(pi_dirty.begin(), pi_dirty.end());
 		pi_dirty.erase(std::unique(pi_dirty.begin(), pi_dirty.end()), pi_dirty.end());
 		for (int lp : pi_dirty) {
@@ -266,9 +268,17 @@ double SimulationControl::PI_calculate_potential() {
 		}
 		pi_dirty.clear();
 	}
+	// Nothing moved since the last sweep (the reference recomputes the energy of a move it has just accepted, :148: same
+	// coordinates, same answer): the device holds exactly what it was asked about last time, so its answer is reused.  Every rank
+	// sees the same list of moved molecules, so every rank skips the same sweeps.
 	double means[4], U;
-	pi_sweeps++;
-	if ((rc = mpmc_pi_potential_allreduce(pi_gpu, P, means, &U))) throw rc;
+	if (nothing_moved && pi_have_means) memcpy(means, pi_last_means, sizeof means);
+	else {
+		pi_sweeps++;
+		if ((rc = mpmc_pi_potential_allreduce(pi_gpu, P, means, &U))) throw rc;
+		memcpy(pi_last_means, means, sizeof means);
+		pi_have_means = true;
+	}
 	System::observables_t *obs = sys.observables;
 	obs->rd_energy = means[0]; obs->coulombic_energy = means[1]; obs->polarization_energy = means[2]; obs->vdw_energy = means[3];
 	return obs->rd_energy + obs->coulombic_energy + obs->vdw_energy + obs->polarization_energy;
@@ -693,7 +703,7 @@ bool SimulationControl::PI_nvt_mc(std::vector<System::step_record> *log) {     /
 		if ((Rando::rand() < bf) && (systems[0]->iterator_failed == 0)) {
 			accepted = 1;
 			pot_current = pot_trial;
-			PI_calculate_energy();                           // an accepted move costs a second sweep (:148)
+			PI_calculate_energy();                           // (:148) nothing has moved since the trial sweep: its answer is reused
 			saved = *sys.observables;
 			sys.nodestats->accept++;
 		} else {
