@@ -101,34 +101,21 @@ __device__ __forceinline__ void mbar_expect_tx(unsigned bar, unsigned bytes) { a
 __device__ __forceinline__ void bulk_g2s(unsigned dst, const void *src, unsigned bytes, unsigned bar) {
 	asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
 }
-// address of the same shared-memory location in CTA `rank` of the cluster, and an 8-byte store into a peer's shared memory that
-// signals the peer's mbarrier when it lands (no flag, no fence, no polling over the cluster network: the reader sleeps on its own barrier)
+// address of the same shared-memory location in CTA `rank` of the cluster
 __device__ __forceinline__ unsigned map_to_cta(unsigned addr, unsigned rank) { unsigned r; asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank)); return r; }
-__device__ __forceinline__ void st_async_f64(unsigned remote_addr, double v, unsigned remote_bar) {
-	asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.b64 [%0], %1, [%2];" ::"r"(remote_addr), "l"(__double_as_longlong(v)), "r"(remote_bar) : "memory");
-}
 // bulk copy from my shared memory into a peer's, completion signalled on the PEER's barrier (one wide transfer instead of hundreds of
 // 8-byte stores: the cluster port handles ~1 small store per 1.5 cycles, which made 7 x 192 doubles take 1 us)
 __device__ __forceinline__ void bulk_s2peer(unsigned remote_dst, unsigned local_src, unsigned bytes, unsigned remote_bar) {
 	asm volatile("fence.proxy.async.shared::cta;" ::: "memory");     // my generic-proxy stores to the source are visible to the copy engine
 	asm volatile("cp.async.bulk.shared::cluster.shared::cta.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(remote_dst), "r"(local_src), "r"(bytes), "r"(remote_bar) : "memory");
 }
-// plain 16-byte store into a peer CTA's shared memory; arrival on a peer's barrier that releases this thread's (and, behind a
-// __syncwarp, its warp's) earlier stores to the cluster; the matching wait
-__device__ __forceinline__ void st_peer_v2(unsigned remote_addr, double a, double b) {
-	asm volatile("st.shared::cluster.v2.f64 [%0], {%1, %2};" ::"r"(remote_addr), "d"(a), "d"(b) : "memory");
-}
+// a 16-byte store into a peer's shared memory that signals the peer's mbarrier when it lands (no flag, no fence, no polling over the
+// cluster network: the reader sleeps on its own barrier).  Measured alternatives for the solver's 2 KB panel: plain peer stores +
+// `mbarrier.arrive.release.cluster` (the arrival takes 1.3 us), one bulk copy per helper (640 ns to land), 8 bytes per store (twice
+// the stores; the cluster port takes ~1 small store per 3-6 cycles)
 __device__ __forceinline__ void st_async_v2(unsigned remote_addr, double a, double b, unsigned remote_bar) {
 	asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v2.b64 [%0], {%1, %2}, [%3];" ::"r"(remote_addr), "l"(__double_as_longlong(a)),
 	             "l"(__double_as_longlong(b)), "r"(remote_bar) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive_peer(unsigned remote_bar) {
-	asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(remote_bar) : "memory");
-}
-__device__ __forceinline__ void mbar_wait_cluster(unsigned bar, unsigned parity) {
-	unsigned ok = 0;
-	while (!ok)
-		asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }" : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
 }
 __device__ __forceinline__ void mbar_wait(unsigned bar, unsigned parity) {
 	unsigned ok;
