@@ -10,24 +10,26 @@
 // and reused by all sweeps: the inverse of each block's triangular system (k_gs_inverse) and the tensors between a block and
 // the kGsAhead blocks that follow it (k_gs_near).  One sweep is then:
 //   * the SOLVER CTA (rank 0 of an 8-CTA cluster) owns the critical path.  Per block: fold what the cluster pushed into the
-//     block's rows, form the right-hand side, one 192 x 192 triangular matrix-vector product (two threads per row, the matrix
-//     in shared memory), write mu and the rows' running contraction back, publish the panel of dipole changes.  A dedicated
-//     warp fetches the next block's site data during the walk, the others copy the next inverse into shared memory after it.
+//     block's rows, form the right-hand side, one 192 x 192 triangular matrix-vector product (21 tiles of 32 x 32 over 14 warps,
+//     the matrix in shared memory), write mu and the rows' running contraction back, publish the panel of dipole changes.
+//     Dedicated warps fetch the next block's site data during the walk, send the panel to the helpers, fence and flag it for the
+//     updaters, and issue the bulk copies of the next inverse, which is awaited piece by piece.
 //   * seven HELPER CTAs share the cluster.  They push each panel into the rows of the next kGsAhead = 4 blocks — the rows
-//     the solver needs before any updater could deliver: tensors prefetched into registers before the panel exists, the panel
-//     read from the solver's shared memory (distributed shared memory), 45 FMAs per thread, and the sums stay in the helper's
-//     own shared memory where the solver reads them: only flags travel, no remote stores, no cluster-wide fences (the first
-//     version's push + fence cost 2 us per panel).  The part for the very next block is folded before the walk, the rest after.
-//   * the UPDATER CTAs (every other SM, 4 per SM) push each published panel into all remaining rows, including the panel's own
-//     block — 4 rows per warp, 8 column lanes per row, every warp on its own, tensors on the fly — in panel order, and flag
-//     each 4-row chunk when it has received a panel.  An updater has kGsAhead block periods to deliver.
+//     the solver needs before any updater could deliver: tensors prefetched into registers before the panel exists, each helper's
+//     columns of the panel stored into its shared memory by the solver (st.async that signals the helper's barrier), 45 FMAs per
+//     thread; a helper keeps what it has pushed into the blocks ahead in its own shared memory and returns only the sums of the
+//     block solved next (one bulk copy that signals the solver's barrier).  Nothing is polled or fenced across the cluster.
+//   * the UPDATER CTAs (every other SM, one CTA of 16 warps per SM) push each published panel into all remaining rows, including
+//     the panel's own block — 4 rows per warp, 8 column lanes per row, tensors on the fly, a row's sum in registers from panel to
+//     panel — in panel order, and flag each 4-row chunk when the solver is about to need it.  An updater has kGsAhead block
+//     periods to deliver.
 //   * the solver may start block b when its rows have received panels 0..b-1-kGsAhead from the updaters; the later panels
 //     are the cluster's own pushes.
 // Every row receives its updates in a fixed order, so the result does not depend on timing.  Pushing panels into rows that
 // were already swept prepares acc for the next sweep, and after the last sweep acc_i is exactly the contraction
 // palmo_contraction() needs (:3602-3627), so Palmo costs no extra sweep.  ef_induced follows from mu after the sweep (k_gs_efi).
 // One launch = one sweep; every CTA must be resident (the grid is sized from cudaOccupancyMaxActiveClusters), which makes the
-// flag waits safe.  What was tried on the way is in profiles/r01b_gs_pipeline.md.
+// flag waits safe.  What was tried on the way is in profiles/r01c_gs_pipeline.md and profiles/r02_gs_pipeline.md.
 #pragma once
 #include <cuda_pipeline.h>
 #include "kernels_polar2.cuh"
