@@ -43,6 +43,23 @@ int mpmc_host_run(const char *input_file, int P, int max_steps, double *log, int
 	return 0;
 }
 
+// Molecule::orient on a bare list of sites (test hook): pos[n][3] in / out, mass[n], the handle site and the target orientation
+int mpmc_host_debug_orient(int n, double *pos, const double *mass, int orientation_site, const double orientation[3]) {
+	if (n < 1 || orientation_site < 0 || orientation_site >= n) return invalid_datum;
+	Molecule m;
+	Atom **tail = &m.atoms;
+	for (int i = 0; i < n; i++) {
+		Atom *a = new Atom;
+		a->mass = mass[i];
+		for (int p = 0; p < 3; p++) a->pos[p] = pos[3 * i + p];
+		*tail = a; tail = &a->next;
+	}
+	m.orient(orientation, orientation_site);
+	int i = 0;
+	for (Atom *a = m.atoms; a; a = a->next, i++) for (int p = 0; p < 3; p++) pos[3 * i + p] = a->pos[p];
+	return 0;
+}
+
 // The same for a path-integral run whose bead systems are sharded over `nranks` processes, one GPU each (launched e.g. by torchrun):
 // every rank calls this with its rank, the device it owns and the 128-byte NCCL id rank 0 obtained from mpmc_nccl_get_unique_id().
 // All ranks replay the same random stream and return the same log.

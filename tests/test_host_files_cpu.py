@@ -12,6 +12,8 @@ import pytest
 from mpmcxx_b200 import host_binding, workloads as W
 from tests import cases
 
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
 Z = np.load(os.path.join(cases.GOLDEN_DIR, "pqr_written.npz"))
 
 
@@ -57,3 +59,57 @@ def test_restart_selection_of_the_shipped_parallel_restart_job(tmp_path):
         assert "\n".join(os.path.basename(x) for x in names) == str(Z["restart_names"][i])
     d = host_binding.describe(inp, P=8)                # the first bead system's sites as read
     assert np.array_equal(d["pos"], Z["restart_pos"][0])
+
+
+# ---- orientational degree of freedom of path-integral sorbates (src/Molecule.cpp:211-254, src/SimulationControl.cpp:306-339) ----
+def test_orient_turns_the_handle_site_onto_the_orientation_and_nothing_else(tmp_path):
+    import ctypes as C
+    import subprocess
+    lib = str(tmp_path / "libhost_orient.so")
+    host = os.path.join(ROOT, "mpmcxx_b200", "host")
+    # Molecule lives in host.cpp, which also holds System::energy(): link it against the oracle-backed shim like the trajectory tests
+    inc = ["-I" + os.path.join(ROOT, "include"), "-I" + os.path.join(ROOT, "oracle")]
+    cflags = ["-O2", "-std=c11", "-fPIC", "-fopenmp", "-ffp-contract=off"]
+    subprocess.run(["gcc"] + cflags + inc + ["-c", os.path.join(ROOT, "oracle", "oracle.c"), "-o", str(tmp_path / "oracle.o")], check=True)
+    subprocess.run(["gcc"] + cflags + inc + ["-c", os.path.join(ROOT, "tests", "shim", "oracle_engine.c"), "-o", str(tmp_path / "shim.o")], check=True)
+    subprocess.run(["g++", "-O2", "-std=c++17", "-ffp-contract=off", "-fPIC", "-shared", "-fopenmp"] + inc + ["-o", lib] +
+                   [os.path.join(host, f) for f in ("host.cpp", "sim_control.cpp", "host_capi.cpp")] + [str(tmp_path / "shim.o"), str(tmp_path / "oracle.o"), "-lm"], check=True)
+    L = C.CDLL(lib)
+    L.mpmc_host_debug_orient.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
+    rs = np.random.RandomState(5)
+    # a five-site linear molecule (centre site on the COM, +-0.371, +-0.329 along a random axis), somewhere in space
+    axis = rs.normal(size=3); axis /= np.linalg.norm(axis)
+    off = np.array([0.0, 0.371, -0.371, 0.329, -0.329])
+    mass = np.array([0.0, 1.008, 1.008, 0.0, 0.0])
+    centre = np.array([3.0, -7.0, 11.0])
+    pos0 = centre + off[:, None] * axis
+    for site, o in ((1, rs.normal(size=3)), (2, np.array([0.0, 0.0, 2.5])), (3, rs.normal(size=3) * 0.3)):   # (generic directions: an orientation exactly
+    # opposite to the handle leaves the reference's rotation axis, a cross product, to rounding noise)
+        pos = np.ascontiguousarray(pos0.copy())
+        o = np.ascontiguousarray(o, dtype=np.float64)
+        assert L.mpmc_host_debug_orient(5, pos.ctypes.data_as(C.c_void_p), mass.ctypes.data_as(C.c_void_p), site, o.ctypes.data_as(C.c_void_p)) == 0
+        com = (mass[:, None] * pos).sum(0) / mass.sum()
+        assert np.allclose(com, centre, atol=1e-12)                                       # the COM stays
+        d0 = np.linalg.norm(pos0[:, None] - pos0[None], axis=-1)
+        assert np.allclose(np.linalg.norm(pos[:, None] - pos[None], axis=-1), d0, atol=1e-12)      # rigid
+        h = pos[site] - com
+        assert np.allclose(h / np.linalg.norm(h), o / np.linalg.norm(o), atol=1e-9)              # the handle points along the orientation
+    # the reference's usual case: the handle is the site ON the centre of mass -> no direction, identity rotation
+    pos = np.ascontiguousarray(pos0.copy())
+    o = np.array([0.3, -0.2, 0.9])
+    assert L.mpmc_host_debug_orient(5, pos.ctypes.data_as(C.c_void_p), mass.ctypes.data_as(C.c_void_p), 0, o.ctypes.data_as(C.c_void_p)) == 0
+    assert np.allclose(pos, pos0, atol=1e-12)
+
+
+def test_malformed_orientation_keyword_is_rejected(tmp_path):
+    """sorbate_orientation_site / sorbate_bondlength / sorbate_reducedMass take `<type> <value>`; a malformed line is rejected like
+    any other (invalid_input, 3000)."""
+    from mpmcxx_b200 import host_binding
+    tmpl, _ = W.pi_h2_cluster(n_side=2, P=4, L=30.0, five_site=True)
+    tmpl.opts.update({"seed": "1", "numsteps": "2", "PI_trial_chain_length": "1", "_lines": ["sorbate_bondlength H2"]})
+    inp = W.write_reference_job(tmpl, str(tmp_path))
+    L = host_binding.lib()
+    import ctypes as C
+    n = C.c_int()
+    rc = L.mpmc_host_describe(inp.encode(), 4, 0, C.byref(n), *([None] * 9))
+    assert rc == 3000
