@@ -122,6 +122,18 @@ def test_config4_two_kernel_pipeline_is_reproducible_and_agrees_with_single_laun
         assert np.abs(da[k] - db[k]).max() <= 1e-12 * scale, k
 
 
+def test_gauss_seidel_several_split_chunks_per_updater_cta_against_oracle():
+    """10 100 polarizable sites = 2525 four-row chunks for the updaters' 2240 warps: 285 surplus chunks, i.e. up to three per CTA split
+    by columns over groups of four warps (config 4 has at most one): every sub-term, the iteration count and all dipoles against
+    the oracle."""
+    from mpmcxx_b200 import workloads as W
+    s = W.h2_framework(n_h2=700, solver=W.SOLVER_GS_RANKED_PALMO)
+    assert int((s.alpha != 0).sum()) == 10100
+    e = _eng().Engine(s)
+    _compare_with_oracle(e, s)
+    e.close()
+
+
 @pytest.mark.parametrize("ncell,n_h2", [(12, 86), (10, 123)])
 def test_gauss_seidel_tens_of_blocks_against_oracle(ncell, n_h2):
     """1728 + 258 = 1986 polarizable sites (31.03 blocks: a last block of two sites) and 1000 + 369 = 1369 (21.4 blocks)."""
