@@ -53,16 +53,20 @@ struct PeriodicBoundary {            // src/PeriodicBoundary.h
 	double basis[3][3] = {{0}}, reciprocal_basis[3][3] = {{0}};
 };
 
-class Atom {                         // src/Atom.h (the fields the energy path and the PQR format use)
+class alignas(64) Atom {             // src/Atom.h (the fields the energy path and the PQR format use)
 public:
-	char atomtype[64] = {0};
+	// what a move touches — the list link, the mass (centre of mass) and the position — shares the object's first cache line: a
+	// path-integral move walks the picked molecule's atoms in every bead system, and none of them is in cache
+	Atom *next = nullptr;
+	double mass = 0;
+	double pos[3] = {0, 0, 0};
 	int id = 0, frozen = 0, adiabatic = 0, spectre = 0, target = 0;
-	double mass = 0, charge = 0, polarizability = 0, epsilon = 0, sigma = 0, omega = 0;
+	double charge = 0, polarizability = 0, epsilon = 0, sigma = 0, omega = 0;
 	double gwp_alpha = 0, c6 = 0, c8 = 0, c10 = 0, c9 = 0;   // carried from the PQR file to the PQR file (not used on this path)
-	double pos[3] = {0, 0, 0}, wrapped_pos[3] = {0, 0, 0};
+	double wrapped_pos[3] = {0, 0, 0};
 	double ef_static[3] = {0, 0, 0}, ef_induced[3] = {0, 0, 0}, ef_induced_change[3] = {0, 0, 0}, mu[3] = {0, 0, 0};
 	double rank_metric = 0;
-	Atom *next = nullptr;
+	char atomtype[64] = {0};
 };
 
 class Molecule {                     // src/Molecule.h
@@ -242,6 +246,9 @@ private:
 	std::vector<double> pi_chain_term;              // per molecule: PI_chain_mass_length2 of its chain, as last computed
 	std::vector<int> pi_chain_stale;                // list positions whose term must be recomputed
 	void pi_index_build();
+	std::vector<std::vector<double>> pi_backup;     // per bead system: mass, COM and site coordinates of the molecule picked for the move
+	std::vector<Atom *> pi_walk;                    // scratch of PI_pick_NVT_move's level-by-level prefetch
+	int pi_N = -1;                                  // molecules the Markov chain may move (constant over a path-integral run)
 	double pi_last_means[4] = {0, 0, 0, 0};         // the last sweep's bead means (reused when nothing has moved since)
 	bool pi_have_means = false;
 };
