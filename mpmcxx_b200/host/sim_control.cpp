@@ -62,7 +62,11 @@ bool SimulationControl::process_command(const std::vector<std::string> &t) {
 		if (ieq(arg(1), "nvt")) sys.ensemble = ENSEMBLE_NVT;
 		else if (ieq(arg(1), "uvt")) sys.ensemble = ENSEMBLE_UVT;
 		else if (ieq(arg(1), "pi_nvt")) sys.ensemble = ENSEMBLE_PATH_INTEGRAL_NVT;
-		else throw unsupported_setting;
+		else {
+			// ensembles the reference knows and this mirror does not drive; any other word is a malformed line (:280-301 -> invalid_input)
+			for (const char *w : {"surf", "surf_fit", "nve", "total_energy", "npt", "replay", "nvt_gibbs"}) if (ieq(arg(1), w)) throw unsupported_setting;
+			return false;
+		}
 		return true;
 	}
 	if (ieq(k, "seed")) { sys.preset_seed = (unsigned int)std::stoul(arg(1)); sys.preset_seed_on = 1; return true; }
@@ -132,9 +136,10 @@ bool SimulationControl::process_command(const std::vector<std::string> &t) {
 	return false;
 }
 
+// A job that fails the reference's validation (check_system / check_mc_options, src/SimulationControl.cpp:1617-1850: steps,
+// correlation time, temperature, ...) makes its constructor throw invalid_input (:67-72); the path-integral checks throw their own codes.
 void SimulationControl::check_system() {
-	if (sys.temperature <= 0) throw missing_setting;
-	if (!sys.numsteps) throw missing_setting;
+	if (sys.numsteps < 1 || sys.corrtime < 1 || sys.temperature <= 0) throw invalid_input;
 	check_io_files_options();
 	if (sys.ensemble == ENSEMBLE_PATH_INTEGRAL_NVT) {      // check_PI_options, PathIntegral.cpp:552-606
 		int bits = 0;
@@ -142,7 +147,7 @@ void SimulationControl::check_system() {
 		if (nSys < 4 || bits != 1) throw invalid_MPI_size_for_PI;
 		if (!PI_trial_chain_length || PI_trial_chain_length >= nSys) throw invalid_setting;
 	}
-	if (sys.ensemble == ENSEMBLE_UVT && sys.pressure <= 0) throw missing_setting;
+	if (sys.ensemble == ENSEMBLE_UVT && sys.pressure <= 0) throw invalid_input;
 }
 
 // Output::make_filename (src/Output.cpp:46-92): "<base>-%04d<.ext>" when the name ends in a three-character extension, else

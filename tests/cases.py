@@ -211,3 +211,43 @@ def load_golden_traj(name):
     s = W.SiteSystem(z["basis"], z["pos"], z["charge_e"], z["alpha"], z["eps"], z["sigma"], z["mass"], z["mol"], z["frozen"],
                      [str(a) for a in z["atomtype"]], [str(a) for a in z["moltype"]], json.loads(str(z["opts"])))
     return s, {"P": z["P"], "traj": z["traj"]}
+
+
+# malformed jobs and the error code the reference throws for them when it reads the job (main.cpp:54-63 catches the int): name ->
+# (builder, P, mutation of the SiteSystem).  tests/golden/input_errors.json holds the reference's codes.
+def _pi_small():
+    return W.pi_h2_cluster(n_side=2, P=4, L=30.0, five_site=False)[0]
+
+
+def _opt(**kw):
+    def m(s):
+        for k, v in kw.items():
+            if v is None:
+                s.opts.pop(k, None)
+            else:
+                s.opts[k] = v
+    return m
+
+
+def _line(text):
+    def m(s):
+        s.opts["_lines"] = list(s.opts.get("_lines", ())) + [text]
+    return m
+
+
+INPUT_ERRORS = {
+    "ok_nvt": (lambda: W.lj_lattice(3, 20.0), 0, _opt(seed="1", numsteps="5")),
+    "zero_temperature": (lambda: W.lj_lattice(3, 20.0), 0, _opt(seed="1", numsteps="5", temperature="0.0")),
+    "zero_numsteps": (lambda: W.lj_lattice(3, 20.0), 0, _opt(seed="1", numsteps="0")),
+    "zero_corrtime": (lambda: W.lj_lattice(3, 20.0), 0, _opt(seed="1", numsteps="5", corrtime="0")),
+    "missing_argument": (lambda: W.lj_lattice(3, 20.0), 0, _line("temperature")),
+    "unknown_keyword": (lambda: W.lj_lattice(3, 20.0), 0, _line("no_such_keyword on")),
+    "bad_switch_value": (lambda: W.lj_lattice(3, 20.0), 0, _opt(seed="1", numsteps="5", rd_only="maybe")),
+    "bad_ensemble": (lambda: W.lj_lattice(3, 20.0), 0, _opt(seed="1", numsteps="5", ensemble="nonsense")),
+    "uvt_without_pressure": (lambda: W.lj_lattice(3, 20.0), 0, _opt(seed="1", numsteps="5", ensemble="uvt", insert_probability="0.3", free_volume="8000.0")),
+    "pi_three_beads": (_pi_small, 3, _opt(seed="1", numsteps="5", PI_trial_chain_length="1")),
+    "pi_two_beads": (_pi_small, 2, _opt(seed="1", numsteps="5", PI_trial_chain_length="1")),
+    "pi_chain_too_long": (_pi_small, 4, _opt(seed="1", numsteps="5", PI_trial_chain_length="4")),
+    "pi_chain_missing": (_pi_small, 4, _opt(seed="1", numsteps="5", PI_trial_chain_length=None)),
+    "pi_ok": (_pi_small, 4, _opt(seed="1", numsteps="5", PI_trial_chain_length="2")),
+}

@@ -190,7 +190,38 @@ def shipped():
         subprocess.run([sys.executable, os.path.abspath(__file__), "shipped1", name], check=True)
 
 
+def one_input_error(name):
+    """The error code the reference throws while it reads and validates a (malformed) job; 0 = accepted.  Fresh process per job."""
+    build, P, mutate = cases.INPUT_ERRORS[name]
+    s = build()
+    mutate(s)
+    try:
+        ref.RefSystem(s, P=P)
+        code = 0
+    except RuntimeError as e:
+        code = int(str(e).split()[-1])
+    print("%s %d" % (name, code), flush=True)
+
+
+def input_errors():
+    import subprocess
+    out = {}
+    for name in cases.INPUT_ERRORS:
+        r = subprocess.run([sys.executable, os.path.abspath(__file__), "error1", name], capture_output=True, text=True)
+        line = [l for l in r.stdout.splitlines() if l.startswith(name + " ")][-1]
+        out[name] = int(line.split()[-1])
+        print(line)
+    with open(os.path.join(HERE, "input_errors.json"), "w") as fp:
+        json.dump(out, fp, indent=1, sort_keys=True)
+
+
 if __name__ == "__main__":
+    if len(sys.argv) > 2 and sys.argv[1] == "error1":
+        one_input_error(sys.argv[2])
+        sys.exit(0)
+    if len(sys.argv) > 1 and sys.argv[1] == "errors":
+        input_errors()
+        sys.exit(0)
     if len(sys.argv) > 3 and sys.argv[1] == "avg1":
         one_average(sys.argv[2], int(sys.argv[3]))
         sys.exit(0)

@@ -5,6 +5,7 @@ import os
 import pytest
 
 from mpmcxx_b200 import host_binding, workloads as W
+from tests import cases
 
 
 def _job(tmp_path, system, extra=None, drop=()):
@@ -30,7 +31,7 @@ def test_parser_error_codes(tmp_path):
     with open(inp) as f:
         text = "".join(l for l in f if not l.startswith("temperature"))
     open(inp, "w").write(text)
-    assert _code(lambda: host_binding.run(inp)) == 4003              # missing_setting
+    assert _code(lambda: host_binding.run(inp)) == 3000              # failed validation -> invalid_input, like the reference's constructor
     inp = _job(tmp_path / "c", lj, {"feynman_hibbs": "on"})
     assert _code(lambda: host_binding.run(inp)) == 4004              # unsupported_setting
     tmpl, _ = W.pi_h2_cluster(n_side=2, P=8, L=30.0)
@@ -74,3 +75,25 @@ def test_readers_match_the_reference(tmp_path, name):
         assert np.array_equal(got[k], g["cell_" + k]), k
     for k in ("volume", "cutoff", "ewald_alpha", "polar_ewald_alpha"):
         assert got[k] == float(g["cell_" + k]), (k, got[k], float(g["cell_" + k]))
+
+
+def test_malformed_jobs_are_refused_with_the_reference_error_codes(tmp_path):
+    """The mirror's reader and validator throw what the reference throws for the same malformed job (its constructor turns a failed
+    validation into invalid_input, src/SimulationControl.cpp:67-72; the path-integral checks throw their own codes, :552-606);
+    codes recorded from the unmodified reference by tests/golden/make_golden.py errors."""
+    import json
+    from mpmcxx_b200 import host_binding
+    golden = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "input_errors.json")))
+    assert set(golden) == set(cases.INPUT_ERRORS)
+    for name, (build, P, mutate) in cases.INPUT_ERRORS.items():
+        s = build()
+        mutate(s)
+        d = tmp_path / name
+        d.mkdir()
+        inp = W.write_reference_job(s, str(d))
+        try:
+            host_binding.describe(inp, P=P)
+            code = 0
+        except RuntimeError as e:
+            code = int(str(e).split()[-1])
+        assert code == golden[name], (name, code, golden[name])
