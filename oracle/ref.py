@@ -39,6 +39,7 @@ def lib():
         L.mref_pi_trajectory.argtypes = [C.c_void_p, C.c_int, _dp]
         L.mref_write_pqr.argtypes = [C.c_void_p, C.c_int, C.c_char_p, C.c_int]
         L.mref_io_filenames.argtypes = [C.c_void_p, C.c_int, C.c_char_p, C.c_int]
+        L.mref_root_averages.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
         L.mref_pi_potential.argtypes = [C.c_void_p]
         L.mref_pi_potential.restype = C.c_double
         _lib = L
@@ -153,6 +154,16 @@ class RefSystem:
         if rc:
             raise RuntimeError("reference PI loop threw %d" % rc)
         return log.reshape(nsteps, 5)
+
+    def root_averages(self, samples, s: int = -1):
+        """update_root_averages over `samples` [n, 6] = (energy, coulombic, rd, polarization, N, NU) -> 25 numbers (see the harness).
+        The reference counts its samples in a function-static: call once per process."""
+        x = np.ascontiguousarray(samples, dtype=np.float64)
+        o = np.zeros(25)
+        rc = lib().mref_root_averages(self.h, s, len(x), x.ctypes.data_as(C.c_void_p), o.ctypes.data_as(C.c_void_p))
+        if rc:
+            raise RuntimeError("reference update_root_averages threw %d" % rc)
+        return o
 
     def write_pqr(self, path: str, s: int = -1, after_energy: bool = False) -> None:
         """The reference's own PQR writer (System::write_molecules_wrapper) for system s."""

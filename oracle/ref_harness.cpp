@@ -316,6 +316,32 @@ int mref_write_pqr(void *h, int s, const char *path, int after_energy) {
 
 /* pqr_input / pqr_restart / pqr_output file names the reference chose for system s (check_io_files_options,
  * src/SimulationControl.cpp:2196-2360), '\n'-separated into out (capacity cap) */
+// System::update_root_averages (src/System.Averages.cpp:8-208) fed with n samples of (energy, coulombic, rd, polarization, N, NU);
+// out[25]: the averages and derived adsorption observables the reference reports, then frozen mass, volume, fugacities[0].  The routine keeps its sample counter in a
+// function-static: one call per process.
+int mref_root_averages(void *h, int s, int n, const double *x, double *out) {
+	System *sys = pick((SimulationControl *)h, s);
+	try {
+		Quiet q;
+		if (!sys->avg_observables) sys->avg_observables = (System::avg_observables_t *)calloc(1, sizeof(System::avg_observables_t));
+		sys->calc_system_mass();
+		for (int i = 0; i < n; i++) {
+			System::observables_t o = *sys->observables;
+			o.energy = x[6 * i]; o.coulombic_energy = x[6 * i + 1]; o.rd_energy = x[6 * i + 2]; o.polarization_energy = x[6 * i + 3];
+			o.N = x[6 * i + 4]; o.NU = x[6 * i + 5];
+			o.temperature = sys->temperature; o.volume = sys->pbc.volume;
+			sys->update_root_averages(&o);
+		}
+		const System::avg_observables_t &a = *sys->avg_observables;
+		const double v[20] = {a.energy, a.energy_error, a.N, a.N_error, a.coulombic_energy, a.coulombic_energy_error, a.rd_energy, a.rd_energy_error,
+		                      a.polarization_energy, a.polarization_energy_error, a.density, a.density_error, a.heat_capacity, a.heat_capacity_error,
+		                      a.compressibility, a.compressibility_error, a.percent_wt, a.percent_wt_me, a.excess_ratio, a.qst};
+		memcpy(out, v, sizeof v);
+		out[20] = a.pore_density; out[21] = a.NU; out[22] = sys->observables->frozen_mass; out[23] = sys->pbc.volume; out[24] = sys->fugacities[0];
+	} catch (int e) { return g_last_error = e; }
+	return 0;
+}
+
 int mref_io_filenames(void *h, int s, char *out, int cap) {
 	SimulationControl *sc = (SimulationControl *)h;
 	System *S = (s < 0 || sc->systems.empty()) ? &sc->sys : sc->systems[s];

@@ -251,3 +251,22 @@ INPUT_ERRORS = {
     "pi_chain_missing": (_pi_small, 4, _opt(seed="1", numsteps="5", PI_trial_chain_length=None)),
     "pi_ok": (_pi_small, 4, _opt(seed="1", numsteps="5", PI_trial_chain_length="2")),
 }
+
+
+# System::update_root_averages (src/System.Averages.cpp:8-208): the job and the synthetic samples behind tests/golden/root_averages.npz
+def uvt_pore_for_averages():
+    s = W.uvt_pore()
+    s.opts.update({"h2_fugacity": "on"})        # a fugacity keyword fills fugacities[0], which the excess adsorption uses
+    return s
+
+
+def root_average_samples(n=300, seed=3):
+    """[n, 6] = (energy, coulombic, rd, polarization, N, NU = N * energy): N wanders between 20 and 40, the energy follows it with noise"""
+    import numpy as _np
+    rs = _np.random.RandomState(seed)
+    x = _np.zeros((n, 6))
+    x[:, 4] = rs.randint(20, 40, size=n)
+    x[:, 0] = -50.0 * x[:, 4] + rs.normal(scale=30.0, size=n)
+    x[:, 1] = 0.3 * x[:, 0]; x[:, 2] = 0.6 * x[:, 0]; x[:, 3] = 0.1 * x[:, 0]
+    x[:, 5] = x[:, 0] * x[:, 4]
+    return x

@@ -190,6 +190,22 @@ def shipped():
         subprocess.run([sys.executable, os.path.abspath(__file__), "shipped1", name], check=True)
 
 
+ROOT_AVG_KEYS = ["energy", "energy_error", "N", "N_error", "coulombic_energy", "coulombic_energy_error", "rd_energy", "rd_energy_error",
+                 "polarization_energy", "polarization_energy_error", "density", "density_error", "heat_capacity", "heat_capacity_error",
+                 "compressibility", "compressibility_error", "percent_wt", "percent_wt_me", "excess_ratio", "qst", "pore_density", "NU"]
+
+
+def root_averages_golden():
+    """System::update_root_averages of the unmodified reference over a synthetic series of 300 samples on the uVT pore job (frozen
+    framework, free volume): the means, errors and derived adsorption observables mpmcxx_b200/averages.py restates."""
+    s = cases.uvt_pore_for_averages()
+    r = ref.RefSystem(s)
+    x = cases.root_average_samples()
+    o = r.root_averages(x)
+    np.savez_compressed(os.path.join(HERE, "root_averages.npz"), samples=x, keys=np.array(ROOT_AVG_KEYS), values=o[:22], frozen_mass=o[22], volume=o[23], fugacity=o[24])
+    print("root averages:", dict(zip(ROOT_AVG_KEYS, o[:22].tolist())))
+
+
 def one_input_error(name):
     """The error code the reference throws while it reads and validates a (malformed) job; 0 = accepted.  Fresh process per job."""
     build, P, mutate = cases.INPUT_ERRORS[name]
@@ -218,6 +234,9 @@ def input_errors():
 if __name__ == "__main__":
     if len(sys.argv) > 2 and sys.argv[1] == "error1":
         one_input_error(sys.argv[2])
+        sys.exit(0)
+    if len(sys.argv) > 1 and sys.argv[1] == "rootavg":
+        root_averages_golden()
         sys.exit(0)
     if len(sys.argv) > 1 and sys.argv[1] == "errors":
         input_errors()

@@ -1,5 +1,7 @@
 """Pin the CPU oracle (oracle/oracle.c) against the reference: committed golden vectors generated from the
 unmodified reference (tests/golden/make_golden.py), and — where oracle/_ref is present — the reference itself."""
+import os
+
 import numpy as np
 import pytest
 
@@ -94,3 +96,25 @@ def test_port_matches_live_reference(name):
     pc = port.cell(s.basis)
     assert np.allclose(pc["recip"], c["recip"], rtol=0, atol=0)
     assert pc["cutoff"] == c["cutoff"] and pc["volume"] == c["volume"]
+
+
+def test_root_averages_restate_the_reference():
+    """mpmcxx_b200/averages.py root_averages == System::update_root_averages of the unmodified reference (tests/golden/root_averages.npz,
+    made by `make_golden.py rootavg`) on 300 samples of a uVT job with a frozen framework: means, errors, density, heat capacity,
+    compressibility, weight percent, excess adsorption, pore density, qst — the same arithmetic, to the last bits."""
+    from mpmcxx_b200 import averages
+    from tests import cases
+    z = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "root_averages.npz"))
+    s = cases.uvt_pore_for_averages()
+    x = cases.root_average_samples()
+    assert np.array_equal(x, z["samples"])
+    mobile = ~s.frozen.astype(bool)
+    particle_mass = float(s.mass[s.mol == s.mol[mobile][0]].sum())
+    a = averages.root_averages(x, float(s.opts["temperature"]), float(z["volume"]), particle_mass, frozen_mass=float(z["frozen_mass"]),
+                               free_volume=float(s.opts["free_volume"]), fugacity=float(z["fugacity"]))
+    assert float(z["fugacity"]) > 0
+    for k, v in zip(z["keys"], z["values"]):
+        assert abs(a[str(k)] - v) <= 1e-13 * abs(v), (str(k), a[str(k)], float(v))
+    # the two-column helper used by the comparison tests is the same recursion
+    m, e = averages.root_average(x[:, 0])
+    assert m == a["energy"] and abs(e - a["energy_error"]) <= 1e-15 * e
