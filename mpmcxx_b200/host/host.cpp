@@ -615,6 +615,61 @@ void System::restore() {
 	do_checkpoint();
 }
 
+void System::calc_system_mass() {
+	observables->total_mass = 0;
+	observables->frozen_mass = 0;
+	for (Molecule *m = molecules; m; m = m->next) {
+		observables->total_mass += m->mass;
+		if (m->frozen || m->adiabatic) observables->frozen_mass += m->mass;
+	}
+}
+
+// Running means (weight (m-1)/m for the old average, 1/m for the new sample), errors sqrt(<x^2> - <x>^2) / sqrt(m - 1), and what the
+// reference derives from them: density, heat capacity and compressibility with the Stirling form of their errors, weight percent,
+// excess adsorption, pore density, isosteric heat.  `fugacities` is an array member in the reference, so its excess adsorption always
+// uses fugacities[0] (0 without a fugacity keyword), never the pressure (:189-194).
+void System::update_root_averages(observables_t *obs) {
+	constexpr double NA = 6.0221415e23, A32CM3 = 1.0e-24, ATM2PASCALS = 101325.0;
+	avg_observables_t *a = avg_observables;
+	const double frozen_mass = obs->frozen_mass;
+	avg_counter++;
+	const double m = (double)avg_counter;
+	const double sdom = 1.0 / sqrt(m - 1.0), factor = (m - 1.0) / m;
+	auto fold = [&](double &avg, double &sq, double &err, double x) {
+		avg = factor * avg + x / m;
+		sq = factor * sq + (x * x) / m;
+		err = sdom * sqrt(sq - avg * avg);
+	};
+	fold(a->energy, a->energy_sq, a->energy_error, obs->energy);
+	fold(a->coulombic_energy, a->coulombic_energy_sq, a->coulombic_energy_error, obs->coulombic_energy);
+	fold(a->rd_energy, a->rd_energy_sq, a->rd_energy_error, obs->rd_energy);
+	fold(a->polarization_energy, a->polarization_energy_sq, a->polarization_energy_error, obs->polarization_energy);
+	fold(a->N, a->N_sq, a->N_error, obs->N);
+	a->NU = factor * a->NU + obs->NU / m;
+	double particle_mass = 0;
+	for (Molecule *mp = molecules; mp; mp = mp->next) if (!mp->frozen && !mp->adiabatic) { particle_mass = mp->mass; break; }
+	const double curr_density = obs->N * particle_mass / (pbc.volume * NA * A32CM3);
+	fold(a->density, a->density_sq, a->density_error, curr_density);
+	double gammaratio = pow((m - 2.0) / (m - 1.0), 0.5 * m - 1.0) * sqrt(0.5 * (m - 2.0)) * exp(0.5);
+	gammaratio = sqrt(1.0 / avg_counter * (m - 1.0 - 2.0 * gammaratio * gammaratio));
+	a->heat_capacity = (kB * NA / 1000.0) * (a->energy_sq - a->energy * a->energy) / (temperature * temperature);
+	a->heat_capacity_error = sdom * 2.0 * gammaratio * a->heat_capacity;
+	a->compressibility = ATM2PASCALS * (pbc.volume / pow(METER2ANGSTROM, 3)) * (a->N_sq - a->N * a->N) / (kB * temperature * a->N * a->N);
+	a->compressibility_error = sdom * 2.0 * gammaratio * a->compressibility;
+	if (frozen_mass > 0.0) {
+		a->percent_wt = 100.0 * a->N * particle_mass / (frozen_mass + a->N * particle_mass);
+		a->percent_wt_me = 100.0 * a->N * particle_mass / frozen_mass;
+		if (free_volume > 0.0) {
+			a->excess_ratio = 1000.0 * (a->N * particle_mass - (particle_mass * free_volume * fugacities[0] * ATM2REDUCED) / temperature) / frozen_mass;
+			a->pore_density = curr_density * pbc.volume / free_volume;
+		}
+		a->qst = -(a->NU - a->N * a->energy);
+		a->qst /= (a->N_sq - a->N * a->N);
+		a->qst += temperature;
+		a->qst *= kB * NA / 1000.0;
+	}
+}
+
 bool System::mc(std::vector<step_record> *log) {       // :20-134
 	observables->volume = pbc.volume;
 	double initial_energy = mc_initial_energy(), final_energy = 0;
@@ -642,6 +697,8 @@ bool System::mc(std::vector<step_record> *log) {       // :20-134
 		if (log) log->push_back({movetype, final_energy, bf, accepted, observables->N});
 		// every correlation time: the restart geometry (do_corrtime_bookkeeping, System.MonteCarlo.cpp:1925-1934)
 		if (write_files && corrtime && !(step % corrtime) && pqr_restart[0]) { update_com(); wrap_all(); write_molecules_wrapper(pqr_restart); }
+		// ... and the node's averages, also at the very end (:104-106, :1912, :1973-2022)
+		if (corrtime && (!(step % corrtime) || step == numsteps)) { calc_system_mass(); update_root_averages(observables); }
 	}
 	loop_seconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - t_loop).count();
 	if (write_files && pqr_output[0]) { update_com(); wrap_all(); write_molecules_wrapper(pqr_output); }   // the final state (:112-120)

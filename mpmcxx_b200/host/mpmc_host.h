@@ -106,6 +106,13 @@ public:
 		Molecule *molecule_backup = nullptr, *molecule_altered = nullptr, *head = nullptr, *tail = nullptr;
 		observables_t observables;
 	};
+	struct avg_observables_t {       // src/System.h:44-92 (what a constant-volume Markov chain reports)
+		double energy = 0, energy_sq = 0, energy_error = 0, N = 0, N_sq = 0, N_error = 0;
+		double coulombic_energy = 0, coulombic_energy_sq = 0, coulombic_energy_error = 0, rd_energy = 0, rd_energy_sq = 0, rd_energy_error = 0;
+		double polarization_energy = 0, polarization_energy_sq = 0, polarization_energy_error = 0;
+		double density = 0, density_sq = 0, density_error = 0, pore_density = 0, percent_wt = 0, percent_wt_me = 0, excess_ratio = 0;
+		double NU = 0, qst = 0, heat_capacity = 0, heat_capacity_error = 0, compressibility = 0, compressibility_error = 0;
+	};
 	struct nodestats_t { double boltzmann_factor = 0, polarization_iterations = 0; int accept = 0, reject = 0; };
 	struct step_record { int movetype; double final_energy, boltzmann_factor; int accepted; double N; };
 
@@ -135,6 +142,10 @@ public:
 	void restore();
 	void displace(Molecule *molecule, const PeriodicBoundary &pbc, double trans_scale, double rot_scale);
 	double get_rand() { return dist(mt_rand); }
+	// averages over the samples taken every correlation time and at the very end (src/System.Averages.cpp:8-208,
+	// src/System.MonteCarlo.cpp:104-106 -> do_corrtime_bookkeeping)
+	void calc_system_mass();                         // src/System.cpp:1537-1550
+	void update_root_averages(observables_t *obs);
 
 	// settings (names as in src/System.h)
 	int cuda = 1, ensemble = ENSEMBLE_NVT;
@@ -161,6 +172,9 @@ public:
 	observables_t observables_store, *observables = &observables_store;
 	checkpoint_t checkpoint_store, *checkpoint = &checkpoint_store;
 	nodestats_t nodestats_store, *nodestats = &nodestats_store;
+	avg_observables_t avg_observables_store, *avg_observables = &avg_observables_store;
+	int avg_counter = 0;             // the function-static sample counter of update_root_averages
+	double fugacities[1] = {0};      // fugacities[0] of the reference: 0 unless a fugacity keyword sets it (this mirror accepts none)
 	double last_volume = 0;
 	std::mt19937 mt_rand;
 	std::uniform_real_distribution<double> dist{0, 1};

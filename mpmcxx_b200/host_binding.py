@@ -20,6 +20,7 @@ def lib():
         L.mpmc_host_run_sharded.argtypes = [C.c_char_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_char_p, C.c_void_p, C.c_int, C.POINTER(C.c_int), C.c_void_p]
         L.mpmc_host_write_pqr.argtypes = [C.c_char_p, C.c_int, C.c_int, C.c_char_p, C.c_char_p, C.c_int]
         L.mpmc_host_last_stats.argtypes = [C.c_void_p]
+        L.mpmc_host_last_averages.argtypes = [C.c_void_p]
         L.mpmc_host_last_stats.restype = None
         L.mpmc_host_energy.argtypes = [C.c_char_p, C.c_void_p]
         L.mpmc_host_describe.argtypes = [C.c_char_p, C.c_int, C.c_int, C.POINTER(C.c_int)] + [C.c_void_p] * 9
@@ -75,6 +76,20 @@ def write_pqr(input_file: str, out_path: str = "", P: int = 0, s: int = 0):
     if rc:
         raise RuntimeError("host write_pqr failed with code %d" % rc)
     return tuple(names.value.decode().split("\n"))
+
+
+AVERAGE_KEYS = ("energy", "energy_error", "N", "N_error", "coulombic_energy", "coulombic_energy_error", "rd_energy", "rd_energy_error",
+                "polarization_energy", "polarization_energy_error", "density", "density_error", "heat_capacity", "heat_capacity_error",
+                "compressibility", "compressibility_error", "percent_wt", "percent_wt_me", "excess_ratio", "qst", "pore_density", "NU",
+                "frozen_mass", "volume", "samples")
+
+
+def last_averages():
+    """What the last classic run (nvt / uvt) averaged every correlation time and at its end, the way the reference does
+    (System::update_root_averages, src/System.Averages.cpp:8-208)."""
+    o = np.zeros(25)
+    lib().mpmc_host_last_averages(o.ctypes.data_as(C.c_void_p))
+    return dict(zip(AVERAGE_KEYS, o.tolist()))
 
 
 def last_stats():

@@ -40,6 +40,7 @@ def lib():
         L.mref_write_pqr.argtypes = [C.c_void_p, C.c_int, C.c_char_p, C.c_int]
         L.mref_io_filenames.argtypes = [C.c_void_p, C.c_int, C.c_char_p, C.c_int]
         L.mref_root_averages.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
+        L.mref_mc_averages.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p]
         L.mref_pi_potential.argtypes = [C.c_void_p]
         L.mref_pi_potential.restype = C.c_double
         _lib = L
@@ -154,6 +155,15 @@ class RefSystem:
         if rc:
             raise RuntimeError("reference PI loop threw %d" % rc)
         return log.reshape(nsteps, 5)
+
+    def mc_averages(self, nsteps: int, corrtime: int):
+        """The classic Markov chain with update_root_averages every `corrtime` steps and at the end -> 25 numbers (see the harness);
+        once per process (the reference counts its samples in a function-static)."""
+        o = np.zeros(25)
+        rc = lib().mref_mc_averages(self.h, nsteps, corrtime, o.ctypes.data_as(C.c_void_p))
+        if rc:
+            raise RuntimeError("reference mc loop threw %d" % rc)
+        return o
 
     def root_averages(self, samples, s: int = -1):
         """update_root_averages over `samples` [n, 6] = (energy, coulombic, rd, polarization, N, NU) -> 25 numbers (see the harness).

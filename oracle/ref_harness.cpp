@@ -253,6 +253,39 @@ int mref_mc_trajectory(void *h, int nsteps, double *log) {
 	return 0;
 }
 
+// The same chain with the averaging the reference does every correlation time and at the very end (System.MonteCarlo.cpp:104-106 ->
+// do_corrtime_bookkeeping :1902-1912, 1973-2022: calc_system_mass, then update_root_averages over the node's observables — the
+// rest of that routine is file output and the MPI gather that a non-MPI build cannot run).  out[25] as mref_root_averages.
+int mref_mc_averages(void *h, int nsteps, int corrtime, double *out) {
+	SimulationControl *sc = (SimulationControl *)h;
+	System &s = sc->sys;
+	try {
+		Quiet q;
+		if (!s.avg_observables) s.avg_observables = (System::avg_observables_t *)calloc(1, sizeof(System::avg_observables_t));
+		s.observables->volume = s.pbc.volume;
+		double initial_energy = s.mc_initial_energy(), final_energy = 0;
+		s.do_checkpoint();
+		for (int step = 1; step <= nsteps; step++) {
+			s.step = step;
+			initial_energy = s.observables->energy;
+			s.make_move();
+			final_energy = s.energy();
+			if (!std::isfinite(final_energy)) { s.observables->energy = MAXVALUE; s.nodestats->boltzmann_factor = 0; }
+			else s.boltzmann_factor(initial_energy, final_energy);
+			if ((s.get_rand() < s.nodestats->boltzmann_factor) && !s.iterator_failed) s.do_checkpoint();
+			else { s.iterator_failed = 0; s.restore(); }
+			if (!(step % corrtime) || step == nsteps) { s.calc_system_mass(); s.update_root_averages(s.observables); }
+		}
+		const System::avg_observables_t &a = *s.avg_observables;
+		const double v[22] = {a.energy, a.energy_error, a.N, a.N_error, a.coulombic_energy, a.coulombic_energy_error, a.rd_energy, a.rd_energy_error,
+		                      a.polarization_energy, a.polarization_energy_error, a.density, a.density_error, a.heat_capacity, a.heat_capacity_error,
+		                      a.compressibility, a.compressibility_error, a.percent_wt, a.percent_wt_me, a.excess_ratio, a.qst, a.pore_density, a.NU};
+		memcpy(out, v, sizeof v);
+		out[22] = s.observables->frozen_mass; out[23] = s.pbc.volume; out[24] = s.fugacities[0];
+	} catch (int e) { return g_last_error = e; }
+	return 0;
+}
+
 // The reference's path-integral chain, step by step: the body of SimulationControl::PI_nvt_mc() (PathIntegral.cpp:31-196) without
 // the file output and statistics.  log: 5 doubles per step = move, trial potential, boltzmann_factor, accepted, kinetic energy.
 int mref_pi_trajectory(void *h, int nsteps, double *log) {

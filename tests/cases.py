@@ -270,3 +270,11 @@ def root_average_samples(n=300, seed=3):
     x[:, 1] = 0.3 * x[:, 0]; x[:, 2] = 0.6 * x[:, 0]; x[:, 3] = 0.1 * x[:, 0]
     x[:, 5] = x[:, 0] * x[:, 4]
     return x
+
+
+# classic chains with the reference's averaging every correlation time (System::update_root_averages inside the mc loop):
+# name -> (builder, steps, corrtime); tests/golden/mc_averages.npz holds what the unmodified reference accumulates
+MC_AVERAGES = {
+    "nvt_lj216": (_traj_lj, 2000, 10),
+    "uvt_pore": (_traj_uvt, 1500, 10),
+}

@@ -206,6 +206,27 @@ def root_averages_golden():
     print("root averages:", dict(zip(ROOT_AVG_KEYS, o[:22].tolist())))
 
 
+def one_mc_average(name):
+    build, steps, corrtime = cases.MC_AVERAGES[name]
+    s = build()
+    s.opts.update({"numsteps": str(steps), "corrtime": str(corrtime)})
+    r = ref.RefSystem(s)
+    o = r.mc_averages(steps, corrtime)
+    np.save(os.path.join(HERE, "_mcavg_%s.npy" % name), o)
+    print("%-12s" % name, dict(zip(ROOT_AVG_KEYS, o[:22].tolist())), flush=True)
+
+
+def mc_averages_golden():
+    """Fresh process per chain (function-static sample counter, Rando's cached normal)."""
+    import subprocess
+    out = {}
+    for name in cases.MC_AVERAGES:
+        subprocess.run([sys.executable, os.path.abspath(__file__), "mcavg1", name], check=True)
+        out[name] = np.load(os.path.join(HERE, "_mcavg_%s.npy" % name))
+        os.remove(os.path.join(HERE, "_mcavg_%s.npy" % name))
+    np.savez_compressed(os.path.join(HERE, "mc_averages.npz"), keys=np.array(ROOT_AVG_KEYS + ["frozen_mass", "volume", "fugacity"]), **out)
+
+
 def one_input_error(name):
     """The error code the reference throws while it reads and validates a (malformed) job; 0 = accepted.  Fresh process per job."""
     build, P, mutate = cases.INPUT_ERRORS[name]
@@ -234,6 +255,12 @@ def input_errors():
 if __name__ == "__main__":
     if len(sys.argv) > 2 and sys.argv[1] == "error1":
         one_input_error(sys.argv[2])
+        sys.exit(0)
+    if len(sys.argv) > 2 and sys.argv[1] == "mcavg1":
+        one_mc_average(sys.argv[2])
+        sys.exit(0)
+    if len(sys.argv) > 1 and sys.argv[1] == "mcavg":
+        mc_averages_golden()
         sys.exit(0)
     if len(sys.argv) > 1 and sys.argv[1] == "rootavg":
         root_averages_golden()

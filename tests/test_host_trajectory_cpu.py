@@ -90,3 +90,36 @@ def test_shipped_sample_directory_runs_unmodified_on_cpu(host_cpu, name, tmp_pat
     assert (np.abs(log[:, 1] - ref[:, 1]) <= 1e-10 * np.maximum(np.abs(ref[:, 1]), 1.0)).all()     # potential (identically 0 for free argon)
     assert (np.abs(log[:, 2] - ref[:, 2]) <= 1e-9 * np.maximum(np.abs(ref[:, 2]), 1e-300)).all()
     assert summary[6] == ref[:, 3].sum()
+
+
+@pytest.mark.parametrize("name", sorted(cases.MC_AVERAGES))
+def test_averages_accumulated_in_the_loop_match_the_reference(host_cpu, name, tmp_path):
+    """System::mc of the mirror averages its observables every correlation time and at the end like the reference's loop does
+    (do_corrtime_bookkeeping -> update_root_averages, src/System.MonteCarlo.cpp:104-106, src/System.Averages.cpp:8-208): energies,
+    N, density, heat capacity, compressibility, weight percent, excess adsorption, pore density, qst against what the unmodified
+    reference accumulated over the same seeded chain (tests/golden/mc_averages.npz)."""
+    z = np.load(os.path.join(ROOT, "tests", "golden", "mc_averages.npz"))
+    build, steps, corrtime = cases.MC_AVERAGES[name]
+    s = build()
+    s.opts.update({"numsteps": str(steps), "corrtime": str(corrtime), "pqr_restart": "off", "pqr_output": "off"})
+    inp = W.write_reference_job(s, str(tmp_path))
+    log, summary = _run(host_cpu, inp, 0, steps)
+    assert len(log) == steps
+    host_cpu.mpmc_host_last_averages.argtypes = [C.c_void_p]
+    o = np.zeros(25)
+    host_cpu.mpmc_host_last_averages(o.ctypes.data_as(C.c_void_p))
+    ref = z[name]
+    assert o[24] == steps // corrtime + (1 if steps % corrtime else 0)
+    assert o[22] == ref[22] and o[23] == ref[23]                          # frozen mass, volume
+    for k, a, b in zip(z["keys"][:22], o[:22], ref[:22]):
+        k = str(k)
+        if np.isnan(b):
+            assert np.isnan(a), k                                         # e.g. the density error of a constant-N chain: sqrt of a rounding residue
+        elif b == 0.0:
+            assert a == 0.0, k
+        elif k in ("N", "N_error", "density", "density_error", "percent_wt", "percent_wt_me", "excess_ratio", "pore_density", "compressibility",
+                   "compressibility_error") and name.startswith("nvt"):
+            assert a == b, (k, a, b)                                      # functions of N alone: the same arithmetic, the same bits
+        else:
+            tol = 1e-6 if k.endswith("_error") or k in ("heat_capacity", "qst") else 1e-9    # (differences of nearly equal means)
+            assert abs(a - b) <= tol * abs(b), (k, a, b)
