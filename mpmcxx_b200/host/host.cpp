@@ -644,6 +644,7 @@ void System::update_root_averages(observables_t *obs) {
 	fold(a->coulombic_energy, a->coulombic_energy_sq, a->coulombic_energy_error, obs->coulombic_energy);
 	fold(a->rd_energy, a->rd_energy_sq, a->rd_energy_error, obs->rd_energy);
 	fold(a->polarization_energy, a->polarization_energy_sq, a->polarization_energy_error, obs->polarization_energy);
+	fold(a->kinetic_energy, a->kinetic_energy_sq, a->kinetic_energy_error, obs->kinetic_energy);
 	fold(a->N, a->N_sq, a->N_error, obs->N);
 	a->NU = factor * a->NU + obs->NU / m;
 	double particle_mass = 0;

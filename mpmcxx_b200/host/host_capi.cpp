@@ -7,17 +7,26 @@
 using namespace mpmc_host;
 
 static double g_last_loop_seconds = 0, g_last_loop_sweeps = 0;
-static double g_last_averages[25] = {0};
+static double g_last_averages[27] = {0};
+static void keep_averages(const System &sys) {
+	const System::avg_observables_t &a = *sys.avg_observables;
+	const double v[27] = {a.energy, a.energy_error, a.N, a.N_error, a.coulombic_energy, a.coulombic_energy_error, a.rd_energy, a.rd_energy_error,
+	                      a.polarization_energy, a.polarization_energy_error, a.density, a.density_error, a.heat_capacity, a.heat_capacity_error,
+	                      a.compressibility, a.compressibility_error, a.percent_wt, a.percent_wt_me, a.excess_ratio, a.qst, a.pore_density, a.NU,
+	                      sys.observables->frozen_mass, sys.pbc.volume, (double)sys.avg_counter, a.kinetic_energy, a.kinetic_energy_error};
+	memcpy(g_last_averages, v, sizeof v);
+}
 
 extern "C" {
 
 // wall seconds of the last run's step loop (set-up and initial energy excluded) and the potential sweeps it made (path integrals)
 void mpmc_host_last_stats(double out[2]) { out[0] = g_last_loop_seconds; out[1] = g_last_loop_sweeps; }
 
-// the averages the last classic run (nvt / uvt) accumulated every correlation time and at the end (System::update_root_averages):
-// energy, N, coulombic, rd, polarization (value, error each), density (value, error), heat capacity (value, error), compressibility
-// (value, error), percent_wt, percent_wt_me, excess_ratio, qst, pore_density, NU, then frozen mass, volume, samples taken
-void mpmc_host_last_averages(double out[25]) { memcpy(out, g_last_averages, sizeof g_last_averages); }
+// the averages the last run accumulated every correlation time and at the end (System::update_root_averages; a path-integral run
+// also counts its initial state): energy, N, coulombic, rd, polarization (value, error each), density (value, error), heat capacity
+// (value, error), compressibility (value, error), percent_wt, percent_wt_me, excess_ratio, qst, pore_density, NU, then frozen mass,
+// volume, samples taken, kinetic energy (value, error)
+void mpmc_host_last_averages(double out[27]) { memcpy(out, g_last_averages, sizeof g_last_averages); }
 
 // Run the simulation an input file describes (ensemble nvt | uvt | pi_nvt), with `P` beads for pi_nvt, for at most max_steps
 // steps (0 = numsteps from the file).  log receives 5 doubles per step: move type, trial energy (potential for pi_nvt),
@@ -32,14 +41,7 @@ int mpmc_host_run(const char *input_file, int P, int max_steps, double *log, int
 		sc.runSimulation(&rec);
 		g_last_loop_seconds = sc.sys.ensemble == ENSEMBLE_PATH_INTEGRAL_NVT ? sc.loop_seconds : sc.sys.loop_seconds;
 		g_last_loop_sweeps = (double)sc.loop_sweeps;
-		{
-			const System::avg_observables_t &a = *sc.sys.avg_observables;
-			const double v[25] = {a.energy, a.energy_error, a.N, a.N_error, a.coulombic_energy, a.coulombic_energy_error, a.rd_energy, a.rd_energy_error,
-			                      a.polarization_energy, a.polarization_energy_error, a.density, a.density_error, a.heat_capacity, a.heat_capacity_error,
-			                      a.compressibility, a.compressibility_error, a.percent_wt, a.percent_wt_me, a.excess_ratio, a.qst, a.pore_density, a.NU,
-			                      sc.sys.observables->frozen_mass, sc.sys.pbc.volume, (double)sc.sys.avg_counter};
-			memcpy(g_last_averages, v, sizeof v);
-		}
+		keep_averages(sc.sys);
 		const int n = (int)std::min<size_t>(rec.size(), (size_t)log_capacity);
 		for (int i = 0; i < n; i++) {
 			log[5 * i] = rec[i].movetype; log[5 * i + 1] = rec[i].final_energy; log[5 * i + 2] = rec[i].boltzmann_factor;
@@ -90,6 +92,7 @@ int mpmc_host_run_sharded(const char *input_file, int P, int max_steps, int rank
 		sc.runSimulation(&rec);
 		g_last_loop_seconds = sc.sys.ensemble == ENSEMBLE_PATH_INTEGRAL_NVT ? sc.loop_seconds : sc.sys.loop_seconds;
 		g_last_loop_sweeps = (double)sc.loop_sweeps;
+		keep_averages(sc.sys);
 		const int n = (int)std::min<size_t>(rec.size(), (size_t)log_capacity);
 		for (int i = 0; i < n; i++) {
 			log[5 * i] = rec[i].movetype; log[5 * i + 1] = rec[i].final_energy; log[5 * i + 2] = rec[i].boltzmann_factor;

@@ -110,6 +110,7 @@ public:
 		double energy = 0, energy_sq = 0, energy_error = 0, N = 0, N_sq = 0, N_error = 0;
 		double coulombic_energy = 0, coulombic_energy_sq = 0, coulombic_energy_error = 0, rd_energy = 0, rd_energy_sq = 0, rd_energy_error = 0;
 		double polarization_energy = 0, polarization_energy_sq = 0, polarization_energy_error = 0;
+		double kinetic_energy = 0, kinetic_energy_sq = 0, kinetic_energy_error = 0;
 		double density = 0, density_sq = 0, density_error = 0, pore_density = 0, percent_wt = 0, percent_wt_me = 0, excess_ratio = 0;
 		double NU = 0, qst = 0, heat_capacity = 0, heat_capacity_error = 0, compressibility = 0, compressibility_error = 0;
 	};
@@ -240,6 +241,8 @@ public:
 	double get_bond_length(const std::string &molecule_id);
 	double get_reduced_mass(const std::string &molecule_id);
 	double PI_orientational_mu_length2();
+	void PI_calc_system_mass();                                       // :833-837
+	void average_current_observables_into_PI_avgObservables();        // :211-232
 	void PI_perturb_beads_orientations();
 	void generate_orientation_configs();
 	void generate_orientation_configs(unsigned int start, unsigned int end, unsigned int p, unsigned int numBeads, double b2, double ukT);

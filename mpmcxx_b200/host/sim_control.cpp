@@ -698,6 +698,27 @@ void SimulationControl::restore_PI_systems() {
 // The orientational contribution uses the same factor as the COM chain's although its length carries no (reduced) mass — the
 // reference reads the reduced mass and does not use it (:520-524) — so with an orientation configured the factor is exp(-/+ ~1e26):
 // such a bead move is accepted exactly when the ring of bond vectors got shorter.  Reproduced as it is.
+void SimulationControl::PI_calc_system_mass() {
+	systems[0]->calc_system_mass();
+	sys.observables->frozen_mass = systems[0]->observables->frozen_mass;
+	sys.observables->total_mass = systems[0]->observables->total_mass;
+}
+
+// The aggregate observables (means over the bead systems, kinetic estimator) averaged the way a classic chain's are; what the
+// aggregate does not carry comes from the first bead system, whose molecule list also serves for the sorbate's mass.  (The reference
+// takes NU from that bead system's own energy(); the engine evaluates the bead systems as one batch and returns their means, so NU
+// — and with it qst — is not accumulated here.)
+void SimulationControl::average_current_observables_into_PI_avgObservables() {
+	sys.molecules = systems[0]->molecules;
+	sys.pbc = systems[0]->pbc;
+	sys.observables->N = systems[0]->observables->N;
+	sys.observables->volume = systems[0]->observables->volume;
+	sys.observables->temperature = systems[0]->observables->temperature;
+	sys.observables->spin_ratio = systems[0]->observables->spin_ratio;
+	sys.update_root_averages(sys.observables);
+	sys.molecules = nullptr;                             // (the list belongs to the bead system)
+}
+
 double SimulationControl::PI_NVT_boltzmann_factor(double d_potential, double d_chain, double d_orient, int movetype) {   // :490-547
 	const double P = (double)nSys, T = sys.temperature;
 	if (movetype == MOVETYPE_PERTURB_BEADS) {
@@ -715,8 +736,11 @@ bool SimulationControl::PI_nvt_mc(std::vector<System::step_record> *log) {     /
 	for (System *S : systems) { S->observables->temperature = sys.temperature; S->observables->volume = S->pbc.volume; }
 	if (!sys.parallel_restarts) PI_perturb_bead_COMs_ENTIRE_SYSTEM();
 	PI_calculate_energy();
+	PI_calc_system_mass();
+	average_current_observables_into_PI_avgObservables();      // the initial state counts once (:63-66)
 	int move = PI_pick_NVT_move();
-	System::observables_t saved = *sys.observables;
+	System::observables_t saved = *sys.observables;          // backup_observables_ALL_SYSTEMS (:699-709): the aggregate ...
+	for (System *S : systems) S->checkpoint->observables = *S->observables;   // ... and every bead system's own (restore() puts them back)
 	double pot_current = sys.observables->potential();
 	if (!std::isfinite(pot_current)) sys.observables->energy = pot_current = MAXVALUE;
 	const auto t_loop = std::chrono::steady_clock::now();
@@ -739,6 +763,7 @@ bool SimulationControl::PI_nvt_mc(std::vector<System::step_record> *log) {     /
 			pot_current = pot_trial;
 			PI_calculate_energy();                           // (:148) nothing has moved since the trial sweep: its answer is reused
 			saved = *sys.observables;
+			for (System *S : systems) S->checkpoint->observables = *S->observables;
 			sys.nodestats->accept++;
 		} else {
 			accepted = 0;
@@ -748,7 +773,14 @@ bool SimulationControl::PI_nvt_mc(std::vector<System::step_record> *log) {     /
 		}
 		if (log) log->push_back({move, pot_trial, bf, accepted, sys.observables->kinetic_energy});
 		move = PI_pick_NVT_move();
-		// every correlation time and at the very end: the restart geometry of every bead system (:176-178, :280-310)
+		// every correlation time and at the very end (:176-178): the averages (do_PI_corrtime_bookkeeping, :248-270) ...
+		if (sys.corrtime && (!(sys.step % sys.corrtime) || sys.step == sys.numsteps)) {
+			for (System *S : systems) S->calc_system_mass();
+			sys.observables->total_mass = systems[0]->observables->total_mass;
+			sys.observables->frozen_mass = systems[0]->observables->frozen_mass;
+			average_current_observables_into_PI_avgObservables();
+		}
+		// ... and the restart geometry of every bead system (:280-310)
 		if (sys.write_files && rank == 0 && sys.corrtime && (!(sys.step % sys.corrtime) || sys.step == sys.numsteps))
 			for (System *S : systems) { S->update_com(); S->wrap_all(); S->write_molecules_wrapper(S->pqr_restart); }
 	}

@@ -81,13 +81,13 @@ def write_pqr(input_file: str, out_path: str = "", P: int = 0, s: int = 0):
 AVERAGE_KEYS = ("energy", "energy_error", "N", "N_error", "coulombic_energy", "coulombic_energy_error", "rd_energy", "rd_energy_error",
                 "polarization_energy", "polarization_energy_error", "density", "density_error", "heat_capacity", "heat_capacity_error",
                 "compressibility", "compressibility_error", "percent_wt", "percent_wt_me", "excess_ratio", "qst", "pore_density", "NU",
-                "frozen_mass", "volume", "samples")
+                "frozen_mass", "volume", "samples", "kinetic_energy", "kinetic_energy_error")
 
 
 def last_averages():
     """What the last classic run (nvt / uvt) averaged every correlation time and at its end, the way the reference does
     (System::update_root_averages, src/System.Averages.cpp:8-208)."""
-    o = np.zeros(25)
+    o = np.zeros(27)
     lib().mpmc_host_last_averages(o.ctypes.data_as(C.c_void_p))
     return dict(zip(AVERAGE_KEYS, o.tolist()))
 

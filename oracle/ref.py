@@ -41,6 +41,7 @@ def lib():
         L.mref_io_filenames.argtypes = [C.c_void_p, C.c_int, C.c_char_p, C.c_int]
         L.mref_root_averages.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
         L.mref_mc_averages.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p]
+        L.mref_pi_averages.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p]
         L.mref_pi_potential.argtypes = [C.c_void_p]
         L.mref_pi_potential.restype = C.c_double
         _lib = L
@@ -163,6 +164,15 @@ class RefSystem:
         rc = lib().mref_mc_averages(self.h, nsteps, corrtime, o.ctypes.data_as(C.c_void_p))
         if rc:
             raise RuntimeError("reference mc loop threw %d" % rc)
+        return o
+
+    def pi_averages(self, nsteps: int, corrtime: int):
+        """The path-integral chain with the reference's averaging (initial state + every `corrtime` steps + the end) -> 20 numbers
+        (see the harness); once per process."""
+        o = np.zeros(20)
+        rc = lib().mref_pi_averages(self.h, nsteps, corrtime, o.ctypes.data_as(C.c_void_p))
+        if rc:
+            raise RuntimeError("reference PI loop threw %d" % rc)
         return o
 
     def root_averages(self, samples, s: int = -1):

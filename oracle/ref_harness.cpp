@@ -332,6 +332,65 @@ int mref_pi_trajectory(void *h, int nsteps, double *log) {
 	return 0;
 }
 
+// The path-integral chain with the reference's averaging: once for the initial state (PathIntegral.cpp:63-66), then every
+// correlation time and at the very end (:176-178 -> do_PI_corrtime_bookkeeping :237-270: system masses, then
+// average_current_observables_into_PI_avgObservables -> sys.update_root_averages; the rest of that routine is file output).
+// out[20]: energy, kinetic, rd, coulombic, polarization, N, density, heat capacity, compressibility (value, error each), then frozen
+// mass and volume.
+int mref_pi_averages(void *h, int nsteps, int corrtime, double *out) {
+	SimulationControl *sc = (SimulationControl *)h;
+	try {
+		Quiet q;
+		if (!sc->sys.avg_observables) sc->sys.avg_observables = (System::avg_observables_t *)calloc(1, sizeof(System::avg_observables_t));
+		for (System *S : sc->systems) { S->observables->temperature = sc->sys.temperature; S->observables->volume = S->pbc.volume; }
+		if (!sc->sys.parallel_restarts) sc->PI_perturb_bead_COMs_ENTIRE_SYSTEM();
+		sc->PI_calculate_energy();
+		sc->PI_calc_system_mass();
+		sc->average_current_observables_into_PI_avgObservables();
+		int move = sc->PI_pick_NVT_move();
+		sc->backup_observables_ALL_SYSTEMS();
+		auto &B = sc->BFC;
+		B.potential.current = sc->sys.observables->potential();
+		if (!std::isfinite(B.potential.current)) sc->sys.observables->energy = B.potential.current = MAXVALUE;
+		B.chain_mass_len2.current = 0; B.orient_mu_len2.current = 0;
+		for (int step = 1; step <= nsteps; step++) {
+			sc->sys.step = step;
+			B.potential.init = B.potential.current;
+			B.chain_mass_len2.init = (move == MOVETYPE_PERTURB_BEADS) ? sc->PI_chain_mass_length2() : 0;
+			B.orient_mu_len2.init = (move == MOVETYPE_PERTURB_BEADS) ? sc->PI_orientational_mu_length2() : 0;
+			sc->PI_make_move(move);
+			B.potential.trial = sc->PI_calculate_potential();
+			B.chain_mass_len2.trial = (move == MOVETYPE_PERTURB_BEADS) ? sc->PI_chain_mass_length2() : 0;
+			B.orient_mu_len2.trial = (move == MOVETYPE_PERTURB_BEADS) ? sc->PI_orientational_mu_length2() : 0;
+			double bf;
+			if (!std::isfinite(B.potential.trial)) { B.potential.trial = sc->sys.observables->energy = MAXVALUE; bf = 0; }
+			else bf = sc->PI_NVT_boltzmann_factor(B);
+			if ((Rando::rand() < bf) && (sc->systems[0]->iterator_failed == 0)) {
+				B.potential.current = B.potential.trial;
+				sc->PI_calculate_energy();
+				sc->backup_observables_ALL_SYSTEMS();
+			} else {
+				sc->restore_PI_systems();
+				*sc->sys.observables = *sc->sys.checkpoint->observables;
+			}
+			move = sc->PI_pick_NVT_move();
+			if (!(step % corrtime) || step == nsteps) {
+				for (System *S : sc->systems) S->calc_system_mass();
+				sc->sys.observables->total_mass = sc->systems[0]->observables->total_mass;
+				sc->sys.observables->frozen_mass = sc->systems[0]->observables->frozen_mass;
+				sc->average_current_observables_into_PI_avgObservables();
+			}
+		}
+		const System::avg_observables_t &a = *sc->sys.avg_observables;
+		const double v[18] = {a.energy, a.energy_error, a.kinetic_energy, a.kinetic_energy_error, a.rd_energy, a.rd_energy_error, a.coulombic_energy,
+		                      a.coulombic_energy_error, a.polarization_energy, a.polarization_energy_error, a.N, a.N_error, a.density, a.density_error,
+		                      a.heat_capacity, a.heat_capacity_error, a.compressibility, a.compressibility_error};
+		memcpy(out, v, sizeof v);
+		out[18] = sc->sys.observables->frozen_mass; out[19] = sc->sys.pbc.volume;
+	} catch (int e) { return g_last_error = e; }
+	return 0;
+}
+
 /* System::write_molecules_wrapper (src/System.Output.cpp:837-1091) of system s into `path`: the reference's own PQR writer, for
  * pinning the mirror's writer byte for byte.  Runs energy() first when `after_energy` so that wrapped coordinates are current. */
 int mref_write_pqr(void *h, int s, const char *path, int after_energy) {

@@ -278,3 +278,9 @@ MC_AVERAGES = {
     "nvt_lj216": (_traj_lj, 2000, 10),
     "uvt_pore": (_traj_uvt, 1500, 10),
 }
+
+# path-integral chains with the reference's averaging (initial state + every correlation time + the end): name -> (builder, P, steps, corrtime)
+PI_AVERAGES = {
+    "pi_h2_27x8": (_traj_pi_h2, 8, 600, 10),
+    "pi_argon_dimer": (W.argon_dimer_pi, 8, 1500, 25),
+}

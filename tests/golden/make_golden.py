@@ -227,6 +227,31 @@ def mc_averages_golden():
     np.savez_compressed(os.path.join(HERE, "mc_averages.npz"), keys=np.array(ROOT_AVG_KEYS + ["frozen_mass", "volume", "fugacity"]), **out)
 
 
+PI_AVG_KEYS = ["energy", "energy_error", "kinetic_energy", "kinetic_energy_error", "rd_energy", "rd_energy_error", "coulombic_energy",
+               "coulombic_energy_error", "polarization_energy", "polarization_energy_error", "N", "N_error", "density", "density_error",
+               "heat_capacity", "heat_capacity_error", "compressibility", "compressibility_error", "frozen_mass", "volume"]
+
+
+def one_pi_average(name):
+    build, P, steps, corrtime = cases.PI_AVERAGES[name]
+    s = build()
+    s.opts.update({"numsteps": str(steps), "corrtime": str(corrtime)})
+    r = ref.RefSystem(s, P=P)
+    o = r.pi_averages(steps, corrtime)
+    np.save(os.path.join(HERE, "_piavg_%s.npy" % name), o)
+    print("%-16s" % name, dict(zip(PI_AVG_KEYS, o.tolist())), flush=True)
+
+
+def pi_averages_golden():
+    import subprocess
+    out = {}
+    for name in cases.PI_AVERAGES:
+        subprocess.run([sys.executable, os.path.abspath(__file__), "piavg1", name], check=True)
+        out[name] = np.load(os.path.join(HERE, "_piavg_%s.npy" % name))
+        os.remove(os.path.join(HERE, "_piavg_%s.npy" % name))
+    np.savez_compressed(os.path.join(HERE, "pi_averages.npz"), keys=np.array(PI_AVG_KEYS), **out)
+
+
 def one_input_error(name):
     """The error code the reference throws while it reads and validates a (malformed) job; 0 = accepted.  Fresh process per job."""
     build, P, mutate = cases.INPUT_ERRORS[name]
@@ -255,6 +280,12 @@ def input_errors():
 if __name__ == "__main__":
     if len(sys.argv) > 2 and sys.argv[1] == "error1":
         one_input_error(sys.argv[2])
+        sys.exit(0)
+    if len(sys.argv) > 2 and sys.argv[1] == "piavg1":
+        one_pi_average(sys.argv[2])
+        sys.exit(0)
+    if len(sys.argv) > 1 and sys.argv[1] == "piavg":
+        pi_averages_golden()
         sys.exit(0)
     if len(sys.argv) > 2 and sys.argv[1] == "mcavg1":
         one_mc_average(sys.argv[2])

@@ -106,7 +106,7 @@ def test_averages_accumulated_in_the_loop_match_the_reference(host_cpu, name, tm
     log, summary = _run(host_cpu, inp, 0, steps)
     assert len(log) == steps
     host_cpu.mpmc_host_last_averages.argtypes = [C.c_void_p]
-    o = np.zeros(25)
+    o = np.zeros(27)
     host_cpu.mpmc_host_last_averages(o.ctypes.data_as(C.c_void_p))
     ref = z[name]
     assert o[24] == steps // corrtime + (1 if steps % corrtime else 0)
@@ -122,4 +122,38 @@ def test_averages_accumulated_in_the_loop_match_the_reference(host_cpu, name, tm
             assert a == b, (k, a, b)                                      # functions of N alone: the same arithmetic, the same bits
         else:
             tol = 1e-6 if k.endswith("_error") or k in ("heat_capacity", "qst") else 1e-9    # (differences of nearly equal means)
+            assert abs(a - b) <= tol * abs(b), (k, a, b)
+
+
+@pytest.mark.parametrize("name", sorted(cases.PI_AVERAGES))
+def test_path_integral_averages_match_the_reference(host_cpu, name, tmp_path):
+    """PI_nvt_mc of the mirror averages the aggregate observables — total, kinetic estimator, potential terms, N, density, heat
+    capacity, compressibility — for the initial state, every correlation time and at the end, like the reference
+    (src/SimulationControl.PathIntegral.cpp:63-66, 176-178, 211-270) — against what the unmodified reference accumulates over the same
+    seeded chain (tests/golden/pi_averages.npz)."""
+    z = np.load(os.path.join(ROOT, "tests", "golden", "pi_averages.npz"))
+    build, P, steps, corrtime = cases.PI_AVERAGES[name]
+    s = build()
+    s.opts.update({"numsteps": str(steps), "corrtime": str(corrtime), "pqr_restart": "off", "pqr_output": "off"})
+    inp = W.write_reference_job(s, str(tmp_path))
+    log, summary = _run(host_cpu, inp, P, steps)
+    assert len(log) == steps
+    host_cpu.mpmc_host_last_averages.argtypes = [C.c_void_p]
+    o = np.zeros(27)
+    host_cpu.mpmc_host_last_averages(o.ctypes.data_as(C.c_void_p))
+    ours = {"energy": o[0], "energy_error": o[1], "N": o[2], "N_error": o[3], "coulombic_energy": o[4], "coulombic_energy_error": o[5],
+            "rd_energy": o[6], "rd_energy_error": o[7], "polarization_energy": o[8], "polarization_energy_error": o[9], "density": o[10],
+            "density_error": o[11], "heat_capacity": o[12], "heat_capacity_error": o[13], "compressibility": o[14], "compressibility_error": o[15],
+            "frozen_mass": o[22], "volume": o[23], "kinetic_energy": o[25], "kinetic_energy_error": o[26]}
+    assert o[24] == 1 + steps // corrtime + (1 if steps % corrtime else 0)       # the initial state counts once
+    for k, b in zip(z["keys"], z[name]):
+        k, a = str(k), ours[str(k)]
+        if np.isnan(b):
+            assert np.isnan(a), k
+        elif b == 0.0:
+            assert a == 0.0, k
+        elif k in ("N", "N_error", "density", "density_error", "compressibility", "compressibility_error", "frozen_mass", "volume"):
+            assert a == b, (k, a, b)                                              # functions of N and the cell alone: the same bits
+        else:
+            tol = 1e-6 if k.endswith("_error") or k == "heat_capacity" else 1e-9
             assert abs(a - b) <= tol * abs(b), (k, a, b)
