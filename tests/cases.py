@@ -284,3 +284,11 @@ PI_AVERAGES = {
     "pi_h2_27x8": (_traj_pi_h2, 8, 600, 10),
     "pi_argon_dimer": (W.argon_dimer_pi, 8, 1500, 25),
 }
+
+# the geometry a chain ends with, as the PQR file the reference writes for it (final / restart state after real moves, insertions and
+# removals included): name -> (builder, P, steps, bead system written); texts in tests/golden/final_pqr.npz
+FINAL_PQR = {
+    "uvt_pore": (_traj_uvt, 0, 400, -1),
+    "nvt_lj216": (_traj_lj, 0, 300, -1),
+    "pi_h2_27x8": (_traj_pi_h2, 8, 200, 3),
+}

@@ -252,6 +252,31 @@ def pi_averages_golden():
     np.savez_compressed(os.path.join(HERE, "pi_averages.npz"), keys=np.array(PI_AVG_KEYS), **out)
 
 
+def one_final_pqr(name):
+    import tempfile
+    build, P, steps, sidx = cases.FINAL_PQR[name]
+    s = build()
+    s.opts.update({"numsteps": str(steps)})
+    with tempfile.TemporaryDirectory(prefix="mref_final_") as d:
+        r = ref.RefSystem(s, P=P, workdir=d)
+        traj = r.pi_trajectory(steps) if P else r.mc_trajectory(steps)
+        path = os.path.join(d, "final_state.pqr")
+        r.write_pqr(path, sidx)
+        text = open(path).read()
+    np.save(os.path.join(HERE, "_final_%s.npy" % name), np.array(text))
+    print("%-12s %d steps, acceptance %.3f, %d bytes" % (name, steps, traj[:, 3].mean(), len(text)), flush=True)
+
+
+def final_pqr_golden():
+    import subprocess
+    out = {}
+    for name in cases.FINAL_PQR:
+        subprocess.run([sys.executable, os.path.abspath(__file__), "final1", name], check=True)
+        out[name] = np.load(os.path.join(HERE, "_final_%s.npy" % name))
+        os.remove(os.path.join(HERE, "_final_%s.npy" % name))
+    np.savez_compressed(os.path.join(HERE, "final_pqr.npz"), **out)
+
+
 def one_input_error(name):
     """The error code the reference throws while it reads and validates a (malformed) job; 0 = accepted.  Fresh process per job."""
     build, P, mutate = cases.INPUT_ERRORS[name]
@@ -280,6 +305,12 @@ def input_errors():
 if __name__ == "__main__":
     if len(sys.argv) > 2 and sys.argv[1] == "error1":
         one_input_error(sys.argv[2])
+        sys.exit(0)
+    if len(sys.argv) > 2 and sys.argv[1] == "final1":
+        one_final_pqr(sys.argv[2])
+        sys.exit(0)
+    if len(sys.argv) > 1 and sys.argv[1] == "finalpqr":
+        final_pqr_golden()
         sys.exit(0)
     if len(sys.argv) > 2 and sys.argv[1] == "piavg1":
         one_pi_average(sys.argv[2])

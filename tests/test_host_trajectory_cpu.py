@@ -157,3 +157,25 @@ def test_path_integral_averages_match_the_reference(host_cpu, name, tmp_path):
         else:
             tol = 1e-6 if k.endswith("_error") or k == "heat_capacity" else 1e-9
             assert abs(a - b) <= tol * abs(b), (k, a, b)
+
+
+@pytest.mark.parametrize("name", sorted(cases.FINAL_PQR))
+def test_final_state_file_after_a_run_matches_the_reference(host_cpu, name, tmp_path):
+    """The geometry a chain ends with — after displacements, insertions and removals (uVT) or bead moves (path integrals) — written by
+    the mirror as its final PQR file (`pqr_output`; `-000k` per bead system) is byte for byte the file the reference writes for its
+    own state after the same seeded chain (tests/golden/final_pqr.npz)."""
+    z = np.load(os.path.join(ROOT, "tests", "golden", "final_pqr.npz"))
+    build, P, steps, sidx = cases.FINAL_PQR[name]
+    s = build()
+    s.opts.update({"numsteps": str(steps), "corrtime": "1000000", "pqr_restart": "off", "pqr_output": "final_state.pqr"})
+    inp = W.write_reference_job(s, str(tmp_path))
+    log, summary = _run(host_cpu, inp, P, steps)
+    assert len(log) == steps
+    fn = "final_state.pqr" if not P else "final_state-%04d.pqr" % sidx
+    text = open(os.path.join(str(tmp_path), fn)).read()
+    want = str(z[name])
+    if text != want:
+        a, b = text.splitlines(), want.splitlines()
+        bad = [i for i in range(min(len(a), len(b))) if a[i] != b[i]]
+        raise AssertionError("%d / %d lines differ (lengths %d, %d); first: %r vs %r" % (len(bad), len(b), len(a), len(b),
+                             a[bad[0]] if bad else None, b[bad[0]] if bad else None))
