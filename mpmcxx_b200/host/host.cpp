@@ -484,7 +484,7 @@ void System::download_dipoles() {
 // ------------------------------------------------------------------------------------------------------------
 double System::mc_initial_energy() {
 	double e = energy();
-	if (!std::isfinite(e)) throw 11000;              // infinite_energy_calc
+	if (!std::isfinite(e)) e = observables->energy = MAXVALUE;    // "be a bit forgiving of the initial state" (:165-167)
 	return e;
 }
 
@@ -674,6 +674,7 @@ void System::update_root_averages(observables_t *obs) {
 bool System::mc(std::vector<step_record> *log) {       // :20-134
 	observables->volume = pbc.volume;
 	double initial_energy = mc_initial_energy(), final_energy = 0;
+	if (corrtime) { calc_system_mass(); update_root_averages(observables); }    // the initial values count once (setup_mpi, :186-190)
 	do_checkpoint();
 	const auto t_loop = std::chrono::steady_clock::now();
 	for (step = 1; step <= numsteps; step++) {

@@ -253,7 +253,8 @@ int mref_mc_trajectory(void *h, int nsteps, double *log) {
 	return 0;
 }
 
-// The same chain with the averaging the reference does every correlation time and at the very end (System.MonteCarlo.cpp:104-106 ->
+// The same chain with the averaging the reference does for the initial state (setup_mpi, :186-190), every correlation time and at the
+// very end (System.MonteCarlo.cpp:104-106 ->
 // do_corrtime_bookkeeping :1902-1912, 1973-2022: calc_system_mass, then update_root_averages over the node's observables — the
 // rest of that routine is file output and the MPI gather that a non-MPI build cannot run).  out[25] as mref_root_averages.
 int mref_mc_averages(void *h, int nsteps, int corrtime, double *out) {
@@ -264,6 +265,7 @@ int mref_mc_averages(void *h, int nsteps, int corrtime, double *out) {
 		if (!s.avg_observables) s.avg_observables = (System::avg_observables_t *)calloc(1, sizeof(System::avg_observables_t));
 		s.observables->volume = s.pbc.volume;
 		double initial_energy = s.mc_initial_energy(), final_energy = 0;
+		s.calc_system_mass(); s.update_root_averages(s.observables);      // setup_mpi (:186-190): the initial values count once
 		s.do_checkpoint();
 		for (int step = 1; step <= nsteps; step++) {
 			s.step = step;

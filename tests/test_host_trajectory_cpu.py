@@ -109,7 +109,7 @@ def test_averages_accumulated_in_the_loop_match_the_reference(host_cpu, name, tm
     o = np.zeros(27)
     host_cpu.mpmc_host_last_averages(o.ctypes.data_as(C.c_void_p))
     ref = z[name]
-    assert o[24] == steps // corrtime + (1 if steps % corrtime else 0)
+    assert o[24] == 1 + steps // corrtime + (1 if steps % corrtime else 0)       # the initial state counts once (setup_mpi)
     assert o[22] == ref[22] and o[23] == ref[23]                          # frozen mass, volume
     for k, a, b in zip(z["keys"][:22], o[:22], ref[:22]):
         k = str(k)
