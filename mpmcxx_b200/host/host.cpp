@@ -167,7 +167,7 @@ System::System(const System &o) {
 	insert_probability = o.insert_probability; bead_perturb_probability = o.bead_perturb_probability;
 	temperature = o.temperature; pressure = o.pressure; free_volume = o.free_volume; scale_charge = o.scale_charge;
 	preset_seed_on = o.preset_seed_on; preset_seed = o.preset_seed;
-	rd_lrc = o.rd_lrc; rd_only = o.rd_only; wrapall = o.wrapall; parallel_restarts = o.parallel_restarts;
+	rd_lrc = o.rd_lrc; rd_only = o.rd_only; wrapall = o.wrapall; parallel_restarts = o.parallel_restarts; read_pqr_box_on = o.read_pqr_box_on;
 	ewald_alpha_set = o.ewald_alpha_set; polar_ewald_alpha_set = o.polar_ewald_alpha_set; ewald_kmax = o.ewald_kmax;
 	ewald_alpha = o.ewald_alpha; polar_ewald_alpha = o.polar_ewald_alpha;
 	polarization = o.polarization; polar_iterative = o.polar_iterative; polar_ewald = o.polar_ewald; polar_zodid = o.polar_zodid;
@@ -181,6 +181,40 @@ System::~System() {
 	if (gpu) mpmc_destroy(gpu);
 	for (Molecule *m = molecules; m;) { Molecule *n = m->next; delete m; m = n; }
 	delete checkpoint->molecule_backup;
+}
+
+// The cell from the geometry file (src/System.cpp:775-850): up to the first line that starts with END, every line whose first seven
+// whitespace-separated words read  REMARK BOX BASIS[k] = x y z  sets basis row k when all three numbers convert; a row that is
+// not found keeps what the input file gave.
+void System::read_pqr_box(const char *file) {
+	std::ifstream in(file);
+	if (!in) throw fopen_fail_read;
+	std::string line;
+	bool have[3] = {false, false, false};
+	while (std::getline(in, line)) {
+		if (have[0] && have[1] && have[2]) break;
+		std::istringstream ss(line);
+		std::string t[7];
+		int n = 0;
+		while (n < 7 && (ss >> t[n])) n++;
+		if (n == 0) continue;
+		if (!t[0].compare(0, 3, "END")) break;
+		if (n < 7 || t[0] != "REMARK" || t[1] != "BOX" || t[3] != "=") continue;
+		for (int k = 0; k < 3; k++) {
+			if (t[2] != "BASIS[" + std::to_string(k) + "]") continue;
+			// SafeOps::atod (src/SafeOps.cpp:70-82): std::stod into the target, failure when the word has trailing characters or is no
+			// number at all; the first failure abandons the line, and only a line whose three words all convert marks the row as read
+			bool ok = true;
+			for (int p = 0; p < 3 && ok; p++) {
+				try {
+					size_t idx = 0;
+					pbc.basis[k][p] = std::stod(t[4 + p], &idx);
+					ok = idx == t[4 + p].size();
+				} catch (...) { ok = false; }
+			}
+			if (ok) have[k] = true;
+		}
+	}
 }
 
 // PQR reader (src/System.cpp:515-770): whitespace tokens ATOM id atomtype moltype F|M molid x y z mass q alpha eps sigma omega ...;

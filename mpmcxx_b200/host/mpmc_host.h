@@ -124,6 +124,7 @@ public:
 
 	// geometry
 	void read_molecules(const char *pqr_file);      // src/System.cpp:507-770
+	void read_pqr_box(const char *pqr_file);         // src/System.cpp:775-850: "REMARK BOX BASIS[k] = x y z" lines override the input's basis
 	int write_molecules(FILE *fp);                   // src/System.Output.cpp:900-1091: the PQR format, field for field
 	int write_molecules_wrapper(const char *filename);   // :837-895: previous file -> "<name>.last", then write
 	void update_pbc();                               // src/System.cpp:859-876 + PeriodicBoundary::update
@@ -158,7 +159,7 @@ public:
 	double move_factor = 1.0, rot_factor = 1.0, insert_probability = 0, bead_perturb_probability = 0;
 	double temperature = 0, pressure = 0, free_volume = 0, scale_charge = 1.0;
 	int preset_seed_on = 0; unsigned int preset_seed = 0;
-	int rd_lrc = 1, rd_only = 0, wrapall = 1, parallel_restarts = 0;
+	int rd_lrc = 1, rd_only = 0, wrapall = 1, parallel_restarts = 0, read_pqr_box_on = 0;
 	int ewald_alpha_set = 0, polar_ewald_alpha_set = 0, ewald_kmax = 7;
 	double ewald_alpha = 0.5, polar_ewald_alpha = 0.5;
 	int polarization = 0, polar_iterative = 0, polar_ewald = 0, polar_zodid = 0, polar_palmo = 0, polar_rrms = 0, polar_gs = 0, polar_gs_ranked = 0,

@@ -98,6 +98,11 @@ bool SimulationControl::process_command(const std::vector<std::string> &t) {
 	if (ieq(k, "rd_lrc")) { sys.rd_lrc = onoff(arg(1)); return true; }
 	if (ieq(k, "wrapall")) { sys.wrapall = onoff(arg(1)); return true; }
 	if (ieq(k, "parallel_restarts")) { sys.parallel_restarts = onoff(arg(1)); return true; }
+	if (ieq(k, "read_pqr_box")) { sys.read_pqr_box_on = onoff(arg(1)); return true; }
+	// (the reference rejects these two by name, :806-813)
+	if (ieq(k, "move_probability") || ieq(k, "rot_probability")) return false;
+	// insertions from a list of candidate molecules: not driven by this mirror
+	if (ieq(k, "insert_input")) throw unsupported_setting;
 	if (ieq(k, "cuda")) { sys.cuda = onoff(arg(1)); return true; }
 	if (ieq(k, "ewald_alpha")) { sys.ewald_alpha = num(arg(1)); sys.ewald_alpha_set = 1; return true; }
 	if (ieq(k, "ewald_kmax")) { sys.ewald_kmax = (int)num(arg(1)); return true; }
@@ -130,8 +135,8 @@ bool SimulationControl::process_command(const std::vector<std::string> &t) {
 		if (ieq(k, w)) { if (onoff(arg(1))) throw unsupported_setting; return true; }
 	// bookkeeping / output options: accepted, not used on this path
 	for (const char *w : {"pop_histogram", "traj_output", "energy_output", "energy_output_csv", "dipole_output", "field_output",
-	                      "frozen_output", "pop_histogram_output", "pop_hist_resolution", "read_pqr_box", "traj_input", "insert_input",
-	                      "max_bondlength", "calc_pressure", "rot_probability", "move_probability"})
+	                      "frozen_output", "pop_histogram_output", "pop_hist_resolution", "traj_input",
+	                      "max_bondlength", "calc_pressure"})
 		if (ieq(k, w)) return true;
 	return false;
 }
@@ -194,6 +199,7 @@ void SimulationControl::initializeSimulationObjects() {      // src/SimulationCo
 	Rando::seed(sys.preset_seed);
 	if (sys.ensemble == ENSEMBLE_PATH_INTEGRAL_NVT) { initialize_PI_NVT_Systems(); return; }
 	sys.read_molecules(sys.pqr_input);
+	if (sys.read_pqr_box_on) sys.read_pqr_box(sys.pqr_input);
 	sys.update_pbc();
 	sys.mt_rand.seed(sys.preset_seed);
 }
@@ -213,6 +219,7 @@ void SimulationControl::initialize_PI_NVT_Systems() {        // PathIntegral.cpp
 		strncpy(s->pqr_output, pqr_final_filenames[i].c_str(), sizeof s->pqr_output - 1);
 		strncpy(s->pqr_restart, pqr_restart_filenames[i].c_str(), sizeof s->pqr_restart - 1);
 		s->read_molecules(s->pqr_input);
+		if (s->read_pqr_box_on) s->read_pqr_box(s->pqr_input);
 		s->update_pbc();
 		for (Molecule *m = s->molecules; m; m = m->next) m->update_COM();
 		systems.push_back(s);

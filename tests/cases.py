@@ -242,6 +242,8 @@ INPUT_ERRORS = {
     "zero_corrtime": (lambda: W.lj_lattice(3, 20.0), 0, _opt(seed="1", numsteps="5", corrtime="0")),
     "missing_argument": (lambda: W.lj_lattice(3, 20.0), 0, _line("temperature")),
     "unknown_keyword": (lambda: W.lj_lattice(3, 20.0), 0, _line("no_such_keyword on")),
+    "retired_rot_probability": (lambda: W.lj_lattice(3, 20.0), 0, _line("rot_probability 0.5")),
+    "retired_move_probability": (lambda: W.lj_lattice(3, 20.0), 0, _line("move_probability 0.5")),
     "bad_switch_value": (lambda: W.lj_lattice(3, 20.0), 0, _opt(seed="1", numsteps="5", rd_only="maybe")),
     "bad_ensemble": (lambda: W.lj_lattice(3, 20.0), 0, _opt(seed="1", numsteps="5", ensemble="nonsense")),
     "uvt_without_pressure": (lambda: W.lj_lattice(3, 20.0), 0, _opt(seed="1", numsteps="5", ensemble="uvt", insert_probability="0.3", free_volume="8000.0")),

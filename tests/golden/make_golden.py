@@ -81,6 +81,26 @@ def parsed():
         print("parsed_%-20s n=%d" % (name, len(out["ref_charge"])))
 
 
+def parsed_box_from_pqr():
+    """`read_pqr_box on`: the cell comes from the REMARK BOX BASIS lines of the geometry file (here: a file the reference itself wrote for
+    a triclinic system, CRYST1 / CONECT records included), not from the basis lines of the input, which this job sets to a wrong cube."""
+    import tempfile
+    z = np.load(os.path.join(HERE, "pqr_written.npz"))
+    s = cases._with(cases.W.triclinic_mix(solver=cases.W.SOLVER_GS_RANKED_PALMO), read_pqr_box="on")
+    s.basis = np.eye(3) * 11.0
+    with tempfile.TemporaryDirectory(prefix="mref_parsed_") as d:
+        cases.W.write_reference_job(s, d)
+        with open(os.path.join(d, "input.pqr"), "w") as fp:
+            fp.write(str(z["text_tri_gs_ranked_palmo"]))
+        r = ref.RefSystem.from_directory(d, "input.in", 0)
+        out = {"input_in": np.array(open(os.path.join(d, "input.in")).read()), "input_pqr": np.array(open(os.path.join(d, "input.pqr")).read()),
+               "P": np.int32(0)}
+        out.update({"ref_" + k: v for k, v in r.sites(-1).items()})
+        out.update({"cell_" + k: v for k, v in r.cell(-1).items()})
+    np.savez_compressed(os.path.join(HERE, "parsed_tri_box_from_pqr.npz"), **out)
+    print("parsed_tri_box_from_pqr n=%d basis %s" % (len(out["ref_charge"]), out["cell_basis"].tolist()))
+
+
 def one_trajectory(name):
     build, P, steps = cases.TRAJ[name]
     s = build()
@@ -347,6 +367,9 @@ if __name__ == "__main__":
         sys.exit(0)
     if len(sys.argv) > 2 and sys.argv[1] == "traj1":
         one_trajectory(sys.argv[2])
+        sys.exit(0)
+    if len(sys.argv) > 1 and sys.argv[1] == "parsedbox":
+        parsed_box_from_pqr()
         sys.exit(0)
     if len(sys.argv) > 1 and sys.argv[1] == "parsed":
         parsed()

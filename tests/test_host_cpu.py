@@ -54,7 +54,7 @@ def test_no_gpu_means_loud_failure(tmp_path):
     assert os.path.exists(os.path.join(os.path.dirname(host_binding.__file__), "mpmcxx-b200"))
 
 
-@pytest.mark.parametrize("name", ["lj_lattice_4", "tri_gs_ranked_palmo", "h2fw_6_jacobi10", "tri_alpha_set", "pi_h2_five_8x4"])
+@pytest.mark.parametrize("name", ["lj_lattice_4", "tri_gs_ranked_palmo", "h2fw_6_jacobi10", "tri_alpha_set", "pi_h2_five_8x4", "tri_box_from_pqr"])
 def test_readers_match_the_reference(tmp_path, name):
     """The mirror's input-file and PQR readers against the reference's own (src/SimulationControl.cpp:1090-2300,
     src/System.cpp:361-700, read by oracle/ref_harness.cpp into tests/golden/parsed_*.npz): same flat site table in the same order
