@@ -93,6 +93,15 @@ def root_averages(samples: np.ndarray, temperature: float, volume: float, partic
     return out
 
 
+def merge_chains(chains, **system) -> dict:
+    """Independent chains merged the way the reference's head node does it with MPI ranks (src/System.MonteCarlo.cpp:1973-2022): at
+    every correlation time the observables of node 0, 1, ... are averaged in one after the other — so the root averages run over
+    samples in the order (time, node) and the error bars shrink with sqrt(nodes x samples).  `chains`: one [n, 6] sample array per
+    chain (same n), as root_averages takes; the remaining arguments are root_averages's."""
+    x = np.stack([np.asarray(c, dtype=np.float64) for c in chains], axis=1)      # [time, node, 6]
+    return root_averages(x.reshape(-1, x.shape[-1]), **system)
+
+
 def block_means(series: np.ndarray, nblocks: int, discard: float = 0.25) -> np.ndarray:
     """Means over `nblocks` consecutive blocks after dropping the first `discard` fraction (equilibration)."""
     s = series[int(len(series) * discard):]

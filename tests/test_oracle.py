@@ -118,3 +118,21 @@ def test_root_averages_restate_the_reference():
     # the two-column helper used by the comparison tests is the same recursion
     m, e = averages.root_average(x[:, 0])
     assert m == a["energy"] and abs(e - a["energy_error"]) <= 1e-15 * e
+
+
+def test_merged_chains_are_the_root_averages_of_the_interleaved_samples():
+    """Independent chains are merged as the reference's head node merges MPI ranks (src/System.MonteCarlo.cpp:1973-2022): node after
+    node at every sample time.  With one chain it is root_averages; with K equal chains the means stay and the errors shrink."""
+    from mpmcxx_b200 import averages
+    from tests import cases
+    x = cases.root_average_samples(n=120, seed=5)
+    sysd = dict(temperature=77.0, volume=8000.0, particle_mass=2.016, frozen_mass=960.0, free_volume=8000.0)
+    one = averages.root_averages(x, **sysd)
+    assert averages.merge_chains([x], **sysd) == one
+    four = averages.merge_chains([x, x, x, x], **sysd)
+    assert abs(four["energy"] - one["energy"]) < 1e-12 * abs(one["energy"]) and abs(four["N"] - one["N"]) < 1e-12 * one["N"]
+    assert 0.45 < four["energy_error"] / one["energy_error"] < 0.55          # sqrt((n - 1) / (4 n - 1)) ~ 1/2
+    y = cases.root_average_samples(n=120, seed=6)
+    two = averages.merge_chains([x, y], **sysd)
+    inter = np.empty((240, 6)); inter[0::2] = x; inter[1::2] = y
+    assert two == averages.root_averages(inter, **sysd)
