@@ -1,5 +1,6 @@
+"""Developer tool (GPU box): pair sweep of the path-integral five-site config at 8 beads per GPU (the 8-GPU shard) under MPMC_PAIR_ROUNDS."""
 import os, sys
-sys.path.insert(0, "/root/repo")
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np
 from mpmcxx_b200 import engine, workloads as W
 t, b = W.pi_h2_cluster(P=8, five_site=True)
